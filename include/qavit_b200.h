@@ -1,0 +1,133 @@
+/* qavit_b200 -- C ABI of the B200-native QA-ViT / HQA-ViT hot path (libqavit_b200.so).
+ *
+ * The reference has no native code and no FFI: its boundary is the Python nn.Module tree
+ * (SURVEY.md section 8b).  Each entry point below replaces the ATen op sequence behind one reference
+ * module's forward (and the autograd graph behind its backward); the reference file:line it stands in
+ * for is cited per function (H = HQAViT_CIFAR100.py).  qa-vit_b200/modules.py binds them with ctypes
+ * from torch.autograd.Functions; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless said otherwise;
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*), nothing synchronises,
+ *     nothing allocates: activations to keep for backward live in `saved`, temporaries in `scratch`,
+ *     both sized by qavit_block_workspace();
+ *   - return 0 on success, non-zero on error with the message in qavit_last_error();
+ *   - dtype 0 = fp32 run (fp32 SIMT GEMMs; the 1e-4 parity mode), 1 = bf16 run (tcgen05 GEMMs with bf16
+ *     operands / fp32 accumulation, bf16 activations, fp32 residual stream, norms, softmax and gradients
+ *     of parameters -- the reference's autocast(bfloat16) recipe).
+ */
+#ifndef QAVIT_B200_H
+#define QAVIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QAVIT_ABI_VERSION 1
+
+/* Index of every parameter tensor a (TokenLearner-wrapped) quad block reads.  qavit_block_param_name(i)
+ * returns the reference state_dict suffix (relative to the wrapper prefix "stageS_blocks.I." for HQAViT,
+ * to "blocks.I." for QAViT, to "global_bank." for the bank entries). */
+enum {
+  QP_NORM1_W, QP_NORM1_B,
+  QP_SWA_QKV_W, QP_SWA_QKV_B, QP_SWA_EK, QP_SWA_EV, QP_SWA_PROJ_W, QP_SWA_PROJ_B, QP_SWA_NORM_W, QP_SWA_NORM_B,
+  QP_MSDA_QKV_W, QP_MSDA_QKV_B, QP_MSDA_EK, QP_MSDA_EV, QP_MSDA_PROJ_W, QP_MSDA_PROJ_B, QP_MSDA_NORM_W, QP_MSDA_NORM_B,
+  QP_CGA_Q_W, QP_CGA_Q_B, QP_CGA_K_W, QP_CGA_K_B, QP_CGA_V_W, QP_CGA_V_B, QP_CGA_BK_W, QP_CGA_BK_B, QP_CGA_BV_W,
+  QP_CGA_BV_B, QP_CGA_PROJ_W, QP_CGA_PROJ_B, QP_CGA_NORM_W, QP_CGA_NORM_B,
+  QP_CROSS_Q_W, QP_CROSS_Q_B, QP_CROSS_K_W, QP_CROSS_K_B, QP_CROSS_V_W, QP_CROSS_V_B, QP_CROSS_PROJ_W, QP_CROSS_PROJ_B,
+  QP_NSWA_W, QP_NSWA_B, QP_NMSDA_W, QP_NMSDA_B, QP_NCGA_W, QP_NCGA_B, QP_NCROSS_W, QP_NCROSS_B,
+  QP_CSWA_W, QP_CSWA_B, QP_CMSDA_W, QP_CMSDA_B, QP_CCGA_W, QP_CCGA_B, QP_CCROSS_W, QP_CCROSS_B,
+  QP_FUSION_W,
+  QP_BMLP_FC1_W, QP_BMLP_FC1_B, QP_BMLP_FC2_W, QP_BMLP_FC2_B,
+  QP_NORM2_W, QP_NORM2_B,
+  QP_FFN_GAMMA, QP_FFN_FC1_W, QP_FFN_FC1_B, QP_FFN_DWN_W, QP_FFN_DWN_B, QP_FFN_SCALE, QP_FFN_DW_W, QP_FFN_DW_B,
+  QP_FFN_PDN_W, QP_FFN_PDN_B, QP_FFN_FC2_W, QP_FFN_FC2_B,
+  QP_TL_LN_W, QP_TL_LN_B, QP_TL_FC_W, QP_TL_FC_B, QP_UP_FC_W, QP_UP_FC_B, QP_UP_LN_W, QP_UP_LN_B,
+  QP_BANK_K, QP_BANK_V, QP_BANK_WN_W, QP_BANK_WN_B, QP_BANK_WC_W, QP_BANK_WC_B, QP_BANK_WG_W, QP_BANK_WG_B,
+  QP_COUNT
+};
+
+typedef struct qavit_block_cfg {
+  int32_t batch;             /* images in this call                                                       */
+  int32_t tokens;            /* tokens the quad block sees (learned tokens M when token_learner, else N)   */
+  int32_t tokens_full;       /* N of the surrounding stream (== tokens when token_learner == 0)            */
+  int32_t token_learner;     /* 1: TokenLearner -> block -> TokenUpMix wrapper (H:1104-1123)               */
+  int32_t dim, heads, bank_size, groups, window, linformer_k, msda_seq_len;
+  int32_t n_dilations, dilations[4], pool_stride;
+  int32_t compress_dim, bottleneck_hidden, ffn_hidden;
+  int32_t ffn_v1;            /* 1: QAViT.py CCFFFN (no norms / scale / gamma, QAViT.py:553-582)            */
+  int32_t dwconv_bias;       /* depthwise conv carries a bias (QAViT.py, QAViTv2.py)                       */
+  int32_t bank_v1;           /* 1: QAViT.py bank constants, no update counter (QAViT.py:203-224)           */
+  int32_t train;             /* 1: bank writes happen (module.training)                                    */
+  int32_t dtype;             /* 0 fp32, 1 bf16                                                             */
+} qavit_block_cfg;
+
+const char* qavit_last_error(void);
+int qavit_abi_version(void);
+/* state_dict suffix of parameter `index` (NULL when out of range); *scope: 0 = quad block, 1 = wrapper, 2 = bank */
+const char* qavit_block_param_name(int index, int* scope);
+
+/* Bytes of `saved` (forward -> backward) and `scratch` (max of forward / backward temporaries). */
+int qavit_block_workspace(const qavit_block_cfg* cfg, size_t* saved_bytes, size_t* scratch_bytes);
+
+/* QuadAttentionBlock.forward (H:1071-1085) incl. the four branches (H:403-626), GlobalTokenBank.write
+ * (H:296-321, mutates params[QP_BANK_K/V] and *update_count in train mode), HybridFusion, BottleneckMLP,
+ * CCFFFN (H:632-712), and -- when cfg->token_learner -- TokenLearner / TokenUpMix (H:971-1031).
+ *   params[QP_COUNT] : fp32 parameter tensors (reference layouts); entries not used by the config may be NULL
+ *   x   [batch, tokens_full, dim] fp32      out [batch, tokens_full, dim] fp32 */
+int qavit_block_forward(const qavit_block_cfg* cfg, const void* const* params, long long* update_count, const float* x,
+                        float* out, void* saved, void* scratch, void* stream);
+
+/* Backward of the above.  grads[QP_COUNT]: fp32 buffers the parameter gradients are ACCUMULATED into (zero them
+ * first; NULL for the write_* / branch .norm parameters, which the reference never trains, H:315).
+ *   dout [batch, tokens_full, dim] fp32     dx [batch, tokens_full, dim] fp32 (overwritten) */
+int qavit_block_backward(const qavit_block_cfg* cfg, const void* const* params, float* const* grads, const float* x,
+                         const float* dout, float* dx, const void* saved, void* scratch, void* stream);
+
+/* PatchEmbed.forward + pos_embed (H:1136-1138, 1250): im2col-free conv-as-GEMM -> LayerNorm -> + pos.
+ *   img [B, Cin, S, S] fp32; W [d, Cin, p, p]; pre [B*N, d] and stats [B*N, 2] are kept for backward. */
+int qavit_patch_embed_forward(const float* img, int B, int Cin, int S, int p, int d, const float* W, const float* bias,
+                              const float* ln_w, const float* ln_b, const float* pos, float* pre, float* stats,
+                              float* out, void* stream);
+int qavit_patch_embed_backward(const float* img, const float* dout, int B, int Cin, int S, int p, int d,
+                               const float* pre, const float* stats, const float* ln_w, float* dpre_scratch, float* dW,
+                               float* dbias, float* dln_w, float* dln_b, float* dpos, void* stream);
+
+/* Final norm -> token mean -> head (H:1273-1275).  x [B, N, d] fp32 -> logits [B, classes]. */
+int qavit_head_forward(const float* x, int B, int N, int d, const float* ln_w, const float* ln_b, const float* W,
+                       const float* bias, int classes, float* stats, float* pooled, float* logits, void* stream);
+int qavit_head_backward(const float* x, const float* dlogits, int B, int N, int d, const float* ln_w, const float* stats,
+                        const float* pooled, const float* W, int classes, float* dpooled_scratch, float* dx,
+                        float* dln_w, float* dln_b, float* dW, float* dbias, void* stream);
+
+/* CrossEntropyLoss(label_smoothing) with optional two-target mixup form (H:1373, 1404-1408).
+ *   ya / yb: int64 class ids (yb may be NULL); loss: 1 float; dlogits may be NULL (forward only). */
+int qavit_cross_entropy(const float* logits, const long long* ya, const long long* yb, float lam, int B, int classes,
+                        float label_smoothing, float* loss, float* dlogits, void* stream);
+
+/* Gradient clipping + AdamW on flat fp32 buffers (H:1413-1439; torch.optim.AdamW single-tensor rule).
+ * The n_seg segments [seg_off[i], seg_off[i+1]) are the parameter tensors: seg_flags bit0 = has a gradient this
+ * step (others are skipped entirely, also by weight decay), bit1 = per-parameter clip to per_param_max first
+ * (names containing cnn_stem / dwconv).  Segments start on 4-float boundaries (padding belongs to the preceding
+ * segment and stays zero); total_elems = seg_off[n_seg].  norms: n_seg + 2 floats; norms[n_seg] returns the global
+ * norm before the global clip, norms[n_seg + 1] the global clip coefficient. */
+int qavit_clip_grads(float* grads, const long long* seg_off, const int* seg_flags, int n_seg, float per_param_max,
+                     float max_norm, float* norms, long long total_elems, void* stream);
+int qavit_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const long long* seg_off,
+                     const int* seg_flags, int n_seg, const float* hyper /* device: lr, beta1, beta2, eps, wd, bc1, bc2 */,
+                     long long total_elems, void* stream);
+
+/* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
+int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,
+                       const float* bias, void* C, int c_f32, void* stream);
+int qavit_test_gemm_tn(int use_tc, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW,
+                       float* db, void* stream);
+int qavit_convert_weight(const float* w, int N, int K, void* wb, void* wbt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

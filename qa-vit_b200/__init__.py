@@ -1,0 +1,13 @@
+"""qavit_b200: B200-native (sm_100a) hot path of QA-ViT / HQA-ViT behind the reference's nn.Module interface.
+
+The directory is named ``qa-vit_b200`` (not importable as such); ``import qavit_b200`` resolves here through the
+shim package at the repo root."""
+from ._lib import EXPORTS, LIB_PATH, lib  # noqa: F401  (raises ImportError when the CUDA extension is not built)
+from .functional import cross_entropy  # noqa: F401
+from .modules import (HQAViT, HQAViTConfig, PatchEmbed, QAViT, QAViTConfig, QuadAttentionBlock,  # noqa: F401
+                      QuadBlockWithTokenLearner)
+from .optim import FusedAdamW, clip_grad_norms_  # noqa: F401
+from .dp import GradAllReducer  # noqa: F401
+
+__all__ = ["QAViT", "HQAViT", "QAViTConfig", "HQAViTConfig", "QuadAttentionBlock", "QuadBlockWithTokenLearner",
+           "PatchEmbed", "cross_entropy", "FusedAdamW", "clip_grad_norms_", "GradAllReducer"]

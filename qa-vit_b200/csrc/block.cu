@@ -1,0 +1,765 @@
+// C-ABI entry points and the quad-block schedule (forward and backward) over the kernels in this directory.
+// See include/qavit_b200.h for the contract and DESIGN.md for the data layout of `saved` / `scratch`.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/qavit_b200.h"
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+void qv_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* qavit_last_error(void) { return g_err; }
+extern "C" int qavit_abi_version(void) { return QAVIT_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------ names
+namespace {
+struct PName { const char* name; int scope; };
+const PName kNames[QP_COUNT] = {
+    {"norm1.weight", 0}, {"norm1.bias", 0},
+    {"swa.qkv.weight", 0}, {"swa.qkv.bias", 0}, {"swa.linformer.E_k", 0}, {"swa.linformer.E_v", 0},
+    {"swa.proj.weight", 0}, {"swa.proj.bias", 0}, {"swa.norm.weight", 0}, {"swa.norm.bias", 0},
+    {"msda.qkv.weight", 0}, {"msda.qkv.bias", 0}, {"msda.linformer.E_k", 0}, {"msda.linformer.E_v", 0},
+    {"msda.proj.weight", 0}, {"msda.proj.bias", 0}, {"msda.norm.weight", 0}, {"msda.norm.bias", 0},
+    {"cga.q_proj.weight", 0}, {"cga.q_proj.bias", 0}, {"cga.k_proj.weight", 0}, {"cga.k_proj.bias", 0},
+    {"cga.v_proj.weight", 0}, {"cga.v_proj.bias", 0}, {"cga.bank_k_proj.weight", 0}, {"cga.bank_k_proj.bias", 0},
+    {"cga.bank_v_proj.weight", 0}, {"cga.bank_v_proj.bias", 0}, {"cga.proj.weight", 0}, {"cga.proj.bias", 0},
+    {"cga.norm.weight", 0}, {"cga.norm.bias", 0},
+    {"cross_attn.q_proj.weight", 0}, {"cross_attn.q_proj.bias", 0}, {"cross_attn.k_proj.weight", 0},
+    {"cross_attn.k_proj.bias", 0}, {"cross_attn.v_proj.weight", 0}, {"cross_attn.v_proj.bias", 0},
+    {"cross_attn.proj.weight", 0}, {"cross_attn.proj.bias", 0},
+    {"norm_swa.weight", 0}, {"norm_swa.bias", 0}, {"norm_msda.weight", 0}, {"norm_msda.bias", 0},
+    {"norm_cga.weight", 0}, {"norm_cga.bias", 0}, {"norm_cross.weight", 0}, {"norm_cross.bias", 0},
+    {"compress_swa.weight", 0}, {"compress_swa.bias", 0}, {"compress_msda.weight", 0}, {"compress_msda.bias", 0},
+    {"compress_cga.weight", 0}, {"compress_cga.bias", 0}, {"compress_cross.weight", 0}, {"compress_cross.bias", 0},
+    {"fusion.fusion_weights", 0},
+    {"bottleneck_mlp.fc1.weight", 0}, {"bottleneck_mlp.fc1.bias", 0}, {"bottleneck_mlp.fc2.weight", 0},
+    {"bottleneck_mlp.fc2.bias", 0},
+    {"norm2.weight", 0}, {"norm2.bias", 0},
+    {"ccf_ffn.gamma", 0}, {"ccf_ffn.fc1.weight", 0}, {"ccf_ffn.fc1.bias", 0}, {"ccf_ffn.dwconv_norm.weight", 0},
+    {"ccf_ffn.dwconv_norm.bias", 0}, {"ccf_ffn.dwconv.scale", 0}, {"ccf_ffn.dwconv.dwconv.weight", 0},
+    {"ccf_ffn.dwconv.dwconv.bias", 0}, {"ccf_ffn.post_dwconv_norm.weight", 0}, {"ccf_ffn.post_dwconv_norm.bias", 0},
+    {"ccf_ffn.fc2.weight", 0}, {"ccf_ffn.fc2.bias", 0},
+    {"token_learner.attention.0.weight", 1}, {"token_learner.attention.0.bias", 1},
+    {"token_learner.attention.1.weight", 1}, {"token_learner.attention.1.bias", 1},
+    {"token_upmix.upsample_attn.weight", 1}, {"token_upmix.upsample_attn.bias", 1},
+    {"token_upmix.norm.weight", 1}, {"token_upmix.norm.bias", 1},
+    {"global_k", 2}, {"global_v", 2}, {"write_norm.weight", 2}, {"write_norm.bias", 2},
+    {"write_compression.weight", 2}, {"write_compression.bias", 2}, {"write_gate.weight", 2}, {"write_gate.bias", 2},
+};
+}  // namespace
+
+extern "C" const char* qavit_block_param_name(int index, int* scope) {
+  if (index < 0 || index >= QP_COUNT) return nullptr;
+  if (scope) *scope = kNames[index].scope;
+  return kNames[index].name;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM dispatch
+int gemm_nt(cudaStream_t s, int dt, const void* A, int lda, int M, const Weight& W, const GemmEpi& e) {
+  if (dt == QV_BF16 && W.wb && tc_shape_ok_nt(M, W.N, W.K, lda))
+    return tc_gemm_nt(s, (const bf16*)A, lda, M, W.N, W.K, W.wb, e);
+  return simt_gemm_nt(s, dt, A, lda, M, W.N, W.K, W.w, e);
+}
+int gemm_nn(cudaStream_t s, int dt, const void* dY, int ldy, int M, const Weight& W, const GemmEpi& e) {
+  // dX[M, K] = dY[M, N] W[N, K] = dY (W^T)^T : the NT kernel on the transposed bf16 copy
+  if (dt == QV_BF16 && W.wbt && tc_shape_ok_nt(M, W.K, W.N, ldy))
+    return tc_gemm_nt(s, (const bf16*)dY, ldy, M, W.K, W.N, W.wbt, e);
+  return simt_gemm_nn(s, dt, dY, ldy, M, W.N, W.K, W.w, e);
+}
+int gemm_tn(cudaStream_t s, int dt, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW,
+            float* db, const float* scale) {
+  if (dt == QV_BF16 && tc_shape_ok_tn(M, N, K, ldy, ldx)) {
+    QV_TRY(tc_gemm_tn(s, (const bf16*)dY, ldy, (const bf16*)X, ldx, M, N, K, dW, scale));
+    if (db) QV_TRY(colsum_accum(s, dt, dY, ldy, M, N, db, scale));
+    return 0;
+  }
+  return simt_gemm_tn(s, dt, dY, ldy, X, ldx, M, N, K, dW, db, scale);
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+namespace {
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t r = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return r;
+  }
+};
+
+struct Dims {
+  int B, Nt, Nf, R, Rf, d, H, hd, kb, G, cg, cpg, ws, side, klin, NM, Lm, cd, bh, fh, dt;
+  size_t ts;
+  bool tl, v1;
+};
+
+// gemm weights that get bf16 copies in bf16 runs
+enum { W_SWA_QKV, W_SWA_PROJ, W_MSDA_Q, W_MSDA_KV, W_MSDA_PROJ, W_CGA_PROJ, W_CROSS_Q, W_CROSS_PROJ, W_C0, W_C1, W_C2,
+       W_C3, W_B1, W_B2, W_F1, W_F2, W_TL, W_WRITE, W_COUNT };
+
+struct Saved {  // byte offsets into `saved`
+  size_t tl_stats, tl_ln, tl_S, xc, n1_stats, xn, alpha, snap[4], qkv_swa, attn_swa, xp, kv_msda, q_msda, attn_msda,
+      attn_cga, kbp, vbp, q_cross, Kc, Vc, attn_cross, branch[4], nb_stats[4], nb[4], fused, h1_pre, h1, x1, n2_stats, y,
+      h_pre, h, dn_stats, hn, cs, pd_stats, hn2, o, out_blk, up, up_stats, wb[W_COUNT], wbt[W_COUNT], wstack, bstack, total;
+};
+struct Scratch {  // byte offsets into `scratch`
+  size_t tl_logits, tn, cgbuf, partial, total_fwd;
+  size_t d_up, d_blk, d_o, d_hn2, d_cs, d_hn, d_hpre, d_y, d_x1, d_x1t, d_h1, d_h1pre, d_fused, d_nb, d_branch, d_attn,
+      d_qkv, d_kv, d_xp, d_q, d_xn, dKc, dVc, dkbp, dvbp, draw, d_logits, d_tl_ln, total_bwd;
+};
+
+int msda_tokens(const qavit_block_cfg& c, int side) {
+  int n = 0;
+  for (int i = 0; i < c.n_dilations; ++i) {
+    const int nd = (side + c.dilations[i] - 1) / c.dilations[i];
+    n += nd * nd;
+  }
+  return (n - c.pool_stride) / c.pool_stride + 1;
+}
+
+int make_dims(const qavit_block_cfg& c, Dims* D) {
+  D->B = c.batch; D->Nt = c.tokens; D->Nf = c.tokens_full; D->tl = c.token_learner != 0;
+  D->R = c.batch * c.tokens; D->Rf = c.batch * c.tokens_full;
+  D->d = c.dim; D->H = c.heads; D->hd = c.dim / c.heads; D->kb = c.bank_size; D->G = c.groups;
+  D->cg = c.dim / c.groups; D->cpg = (c.dim / 2) / c.groups; D->ws = c.window; D->klin = c.linformer_k;
+  D->cd = c.compress_dim; D->bh = c.bottleneck_hidden; D->fh = c.ffn_hidden; D->dt = c.dtype; D->v1 = c.ffn_v1 != 0;
+  D->ts = c.dtype == QV_BF16 ? 2 : 4;
+  int side = 1;
+  while (side * side < c.tokens) ++side;
+  QV_CHECK(side * side == c.tokens, "tokens=%d is not a square grid", c.tokens);
+  QV_CHECK(side % c.window == 0, "grid side %d %% window %d != 0 (the reference requires it, H:466)", side, c.window);
+  QV_CHECK(c.dim % c.heads == 0 && c.dim % c.groups == 0 && (c.dim / 2) % c.groups == 0, "dim/heads/groups mismatch");
+  QV_CHECK(c.dim % 8 == 0 && c.dim <= 256, "dim=%d unsupported (multiple of 8, <= 256)", c.dim);
+  QV_CHECK(4 * c.compress_dim == c.dim, "4 * compress_dim must equal dim");
+  QV_CHECK(c.dtype == QV_F32 || c.dtype == QV_BF16, "dtype %d", c.dtype);
+  QV_CHECK(!c.token_learner || c.tokens_full >= c.tokens, "token learner: tokens_full < tokens");
+  QV_CHECK(c.token_learner || c.tokens_full == c.tokens, "tokens_full must equal tokens without token learner");
+  D->side = side;
+  D->NM = msda_tokens(c, side);
+  D->Lm = D->NM < c.msda_seq_len ? D->NM : c.msda_seq_len;
+  return 0;
+}
+
+void weight_shape(const Dims& D, int wi, int* N, int* K) {
+  const int d = D.d;
+  switch (wi) {
+    case W_SWA_QKV: *N = 3 * d; *K = d; break;
+    case W_MSDA_KV: *N = 2 * d; *K = d; break;
+    case W_CGA_PROJ: *N = d; *K = d / 2; break;
+    case W_C0: case W_C1: case W_C2: case W_C3: *N = D.cd; *K = d; break;
+    case W_B1: *N = D.bh; *K = d; break;
+    case W_B2: *N = d; *K = D.bh; break;
+    case W_F1: *N = D.fh; *K = d; break;
+    case W_F2: *N = d; *K = D.fh; break;
+    case W_TL: *N = D.Nt; *K = d; break;
+    case W_WRITE: *N = d + D.kb; *K = d; break;
+    default: *N = d; *K = d; break;
+  }
+}
+
+void layout_saved(const Dims& D, Saved* S) {
+  Bump b;
+  const size_t ts = D.ts, R = D.R, Rf = D.Rf, d = D.d;
+  S->tl_stats = b.take(D.tl ? Rf * 8 : 0);
+  S->tl_ln = b.take(D.tl ? Rf * d * ts : 0);
+  S->tl_S = b.take(D.tl ? Rf * D.Nt * 4 : 0);
+  S->xc = b.take(D.tl ? R * d * 4 : 0);
+  S->n1_stats = b.take(R * 8);
+  S->xn = b.take(R * d * ts);
+  S->alpha = b.take(16);
+  for (int i = 0; i < 4; ++i) S->snap[i] = b.take(2 * D.kb * d * 4);
+  S->qkv_swa = b.take(R * 3 * d * ts);
+  S->attn_swa = b.take(R * d * ts);
+  S->xp = b.take((size_t)D.B * D.NM * d * ts);
+  S->kv_msda = b.take((size_t)D.B * D.NM * 2 * d * ts);
+  S->q_msda = b.take(R * d * ts);
+  S->attn_msda = b.take(R * d * ts);
+  S->attn_cga = b.take(R * (d / 2) * ts);
+  S->kbp = b.take(D.kb * D.cpg * 4);
+  S->vbp = b.take(D.kb * D.cpg * 4);
+  S->q_cross = b.take(R * d * ts);
+  S->Kc = b.take(D.kb * d * 4);
+  S->Vc = b.take(D.kb * d * 4);
+  S->attn_cross = b.take(R * d * ts);
+  for (int i = 0; i < 4; ++i) S->branch[i] = b.take(R * d * ts);
+  for (int i = 0; i < 4; ++i) S->nb_stats[i] = b.take(R * 8);
+  for (int i = 0; i < 4; ++i) S->nb[i] = b.take(R * d * ts);
+  S->fused = b.take(R * d * ts);
+  S->h1_pre = b.take(R * D.bh * ts);
+  S->h1 = b.take(R * D.bh * ts);
+  S->x1 = b.take(R * d * 4);
+  S->n2_stats = b.take(R * 8);
+  S->y = b.take(R * d * ts);
+  S->h_pre = b.take(R * D.fh * ts);
+  S->h = b.take(D.v1 ? R * D.fh * ts : 0);
+  S->dn_stats = b.take(R * 8);
+  S->hn = b.take(R * D.fh * ts);
+  S->cs = b.take(R * D.fh * ts);
+  S->pd_stats = b.take(R * 8);
+  S->hn2 = b.take(R * D.fh * ts);
+  S->o = b.take(R * d * ts);
+  S->out_blk = b.take(D.tl ? R * d * 4 : 0);
+  S->up = b.take(D.tl ? Rf * d * 4 : 0);
+  S->up_stats = b.take(D.tl ? Rf * 8 : 0);
+  for (int i = 0; i < W_COUNT; ++i) {
+    int N, K;
+    weight_shape(D, i, &N, &K);
+    const bool need = D.dt == QV_BF16 && (i != W_TL || D.tl);
+    S->wb[i] = b.take(need ? (size_t)N * K * 2 : 0);
+    S->wbt[i] = b.take(need && i != W_WRITE ? (size_t)N * K * 2 : 0);
+  }
+  S->wstack = b.take((size_t)(d + D.kb) * d * 4);
+  S->bstack = b.take((size_t)(d + D.kb) * 4);
+  S->total = b.off;
+}
+
+void layout_scratch(const Dims& D, Scratch* S) {
+  const size_t ts = D.ts, R = D.R, Rf = D.Rf, d = D.d;
+  {
+    Bump b;
+    S->tl_logits = b.take(D.tl ? Rf * D.Nt * ts : 0);
+    S->tn = b.take(R * d * ts);
+    S->cgbuf = b.take(R * (d + D.kb) * ts);
+    S->partial = b.take((size_t)320 * 2 * D.kb * d * 4);   // bank_write_reduce uses <= 320 CTAs
+    S->total_fwd = b.off;
+  }
+  {
+    Bump b;
+    S->d_up = b.take(D.tl ? Rf * d * 4 : 0);
+    S->d_blk = b.take(D.tl ? R * d * 4 : 0);
+    S->d_o = b.take(R * d * ts);
+    S->d_hn2 = b.take(R * D.fh * ts);
+    S->d_cs = b.take(R * D.fh * ts);
+    S->d_hn = b.take(R * D.fh * ts);
+    S->d_hpre = b.take(R * D.fh * ts);
+    S->d_y = b.take(R * d * ts);
+    S->d_x1 = b.take(R * d * 4);
+    S->d_x1t = b.take(R * d * ts);
+    S->d_h1 = b.take(R * D.bh * ts);
+    S->d_h1pre = b.take(R * D.bh * ts);
+    S->d_fused = b.take(R * d * ts);
+    S->d_nb = b.take(R * d * ts);
+    S->d_branch = b.take(R * d * ts);
+    S->d_attn = b.take(R * d * ts);
+    S->d_qkv = b.take(R * 3 * d * ts);
+    S->d_kv = b.take((size_t)D.B * D.NM * 2 * d * ts);
+    S->d_xp = b.take((size_t)D.B * D.NM * d * ts);
+    S->d_q = b.take(R * d * ts);
+    // ---- zero-initialised accumulators, contiguous: d_xn | dKc | dVc | dkbp | dvbp | draw
+    S->d_xn = b.take(R * d * 4);
+    S->dKc = b.take(D.kb * d * 4);
+    S->dVc = b.take(D.kb * d * 4);
+    S->dkbp = b.take(D.kb * D.cpg * 4);
+    S->dvbp = b.take(D.kb * D.cpg * 4);
+    S->draw = b.take(16);
+    const size_t zero_end = b.off;
+    (void)zero_end;
+    S->d_logits = b.take(D.tl ? Rf * D.Nt * ts : 0);
+    S->d_tl_ln = b.take(D.tl ? Rf * d * ts : 0);
+    S->total_bwd = b.off;
+  }
+}
+
+struct Ctx {
+  Dims D;
+  Saved S;
+  Scratch X;
+  const void* const* P;
+  uint8_t* saved;
+  uint8_t* scratch;
+  cudaStream_t st;
+  const float* pf(int i) const { return static_cast<const float*>(P[i]); }
+  void* sv(size_t off) const { return saved + off; }
+  float* svf(size_t off) const { return reinterpret_cast<float*>(saved + off); }
+  void* sc(size_t off) const { return scratch + off; }
+  float* scf(size_t off) const { return reinterpret_cast<float*>(scratch + off); }
+  Weight W(int wi, const float* w) const {
+    Weight r;
+    weight_shape(D, wi, &r.N, &r.K);
+    r.w = w;
+    if (D.dt == QV_BF16) {
+      r.wb = reinterpret_cast<const bf16*>(saved + S.wb[wi]);
+      r.wbt = wi == W_WRITE ? nullptr : reinterpret_cast<const bf16*>(saved + S.wbt[wi]);
+    }
+    return r;
+  }
+};
+
+const float* weight_src(const Ctx& c, int wi) {
+  const int d = c.D.d;
+  switch (wi) {
+    case W_SWA_QKV: return c.pf(QP_SWA_QKV_W);
+    case W_SWA_PROJ: return c.pf(QP_SWA_PROJ_W);
+    case W_MSDA_Q: return c.pf(QP_MSDA_QKV_W);
+    case W_MSDA_KV: return c.pf(QP_MSDA_QKV_W) + (size_t)d * d;
+    case W_MSDA_PROJ: return c.pf(QP_MSDA_PROJ_W);
+    case W_CGA_PROJ: return c.pf(QP_CGA_PROJ_W);
+    case W_CROSS_Q: return c.pf(QP_CROSS_Q_W);
+    case W_CROSS_PROJ: return c.pf(QP_CROSS_PROJ_W);
+    case W_C0: return c.pf(QP_CSWA_W);
+    case W_C1: return c.pf(QP_CMSDA_W);
+    case W_C2: return c.pf(QP_CCGA_W);
+    case W_C3: return c.pf(QP_CCROSS_W);
+    case W_B1: return c.pf(QP_BMLP_FC1_W);
+    case W_B2: return c.pf(QP_BMLP_FC2_W);
+    case W_F1: return c.pf(QP_FFN_FC1_W);
+    case W_F2: return c.pf(QP_FFN_FC2_W);
+    case W_TL: return c.pf(QP_TL_FC_W);
+    case W_WRITE: return c.svf(c.S.wstack);
+  }
+  return nullptr;
+}
+
+int init_ctx(Ctx* c, const qavit_block_cfg* cfg, const void* const* params, const void* saved, void* scratch, void* stream) {
+  QV_CHECK(cfg && params && saved && scratch, "null argument");
+  QV_TRY(make_dims(*cfg, &c->D));
+  layout_saved(c->D, &c->S);
+  layout_scratch(c->D, &c->X);
+  c->P = params;
+  c->saved = static_cast<uint8_t*>(const_cast<void*>(saved));
+  c->scratch = static_cast<uint8_t*>(scratch);
+  c->st = static_cast<cudaStream_t>(stream);
+  return 0;
+}
+
+// GlobalTokenBank.write(branch.norm(out)) -- H:468 / 531 / 594 -> H:296-321
+int bank_write(const Ctx& c, const qavit_block_cfg& cfg, const void* branch_out, int nw, int nb, long long* update_count) {
+  const Dims& D = c.D;
+  void* tn = c.sc(c.X.tn);
+  void* cg = c.sc(c.X.cgbuf);
+  QV_TRY(ln_fwd(c.st, D.dt, branch_out, D.d, D.R, D.d, c.pf(nw), c.pf(nb), 1e-5f, 0, c.pf(QP_BANK_WN_W), c.pf(QP_BANK_WN_B),
+                D.dt, tn, D.d, nullptr));
+  GemmEpi e;
+  e.bias = c.svf(c.S.bstack); e.C = cg; e.ldc = D.d + D.kb;
+  e.c_f32 = D.dt == QV_F32;
+  QV_TRY(gemm_nt(c.st, D.dt, tn, D.d, D.R, c.W(W_WRITE, weight_src(c, W_WRITE)), e));
+  int np = 0;
+  QV_TRY(bank_write_reduce(c.st, D.dt, tn, cg, D.d + D.kb, D.B, D.Nt, D.d, D.kb, c.scf(c.X.partial), &np));
+  QV_TRY(bank_write_apply(c.st, c.scf(c.X.partial), np, D.B, D.d, D.kb, const_cast<float*>(c.pf(QP_BANK_K)),
+                          const_cast<float*>(c.pf(QP_BANK_V)), update_count, cfg.bank_v1));
+  return 0;
+}
+
+int snapshot_bank(const Ctx& c, int i) {
+  const size_t n = (size_t)c.D.kb * c.D.d * 4;
+  QV_CUDA(cudaMemcpyAsync(c.sv(c.S.snap[i]), c.pf(QP_BANK_K), n, cudaMemcpyDeviceToDevice, c.st));
+  QV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(c.sv(c.S.snap[i])) + n, c.pf(QP_BANK_V), n, cudaMemcpyDeviceToDevice, c.st));
+  return 0;
+}
+const float* snap_k(const Ctx& c, int i) { return c.svf(c.S.snap[i]); }
+const float* snap_v(const Ctx& c, int i) { return c.svf(c.S.snap[i]) + (size_t)c.D.kb * c.D.d; }
+
+GemmEpi epi_t(const Ctx& c, const float* bias, void* C, int ldc) {
+  GemmEpi e;
+  e.bias = bias; e.C = C; e.ldc = ldc; e.c_f32 = c.D.dt == QV_F32;
+  return e;
+}
+
+AttnP attn_params(const Ctx& c, int mode) {
+  const Dims& D = c.D;
+  AttnP p{};
+  p.mode = mode; p.B = D.B; p.Nt = D.Nt; p.side = D.side; p.ws = D.ws; p.H = D.H; p.hd = D.hd; p.kb = D.kb;
+  p.klin = D.klin; p.NM = D.NM;
+  p.L = mode == 0 ? D.ws * D.ws : (mode == 1 ? D.Lm : 0);
+  return p;
+}
+
+}  // namespace
+
+extern "C" int qavit_block_workspace(const qavit_block_cfg* cfg, size_t* saved_bytes, size_t* scratch_bytes) {
+  QV_CHECK(cfg, "null cfg");
+  Dims D;
+  QV_TRY(make_dims(*cfg, &D));
+  Saved S;
+  Scratch X;
+  layout_saved(D, &S);
+  layout_scratch(D, &X);
+  if (saved_bytes) *saved_bytes = S.total + 256;
+  if (scratch_bytes) *scratch_bytes = (X.total_fwd > X.total_bwd ? X.total_fwd : X.total_bwd) + 256;
+  return 0;
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const* params, long long* update_count,
+                                   const float* x_in, float* out, void* saved, void* scratch, void* stream) {
+  Ctx c;
+  QV_TRY(init_ctx(&c, cfg, params, saved, scratch, stream));
+  const Dims& D = c.D;
+  const Saved& S = c.S;
+  const int dt = D.dt, d = D.d, R = D.R;
+  cudaStream_t st = c.st;
+  const bool train = cfg->train != 0;
+  QV_CHECK(!train || cfg->bank_v1 || update_count, "train mode needs update_count");
+
+  // ---- stacked write weight [write_compression ; write_gate] and bf16 weight copies
+  if (train) {
+    QV_CUDA(cudaMemcpyAsync(c.sv(S.wstack), c.pf(QP_BANK_WC_W), (size_t)d * d * 4, cudaMemcpyDeviceToDevice, st));
+    QV_CUDA(cudaMemcpyAsync(c.svf(S.wstack) + (size_t)d * d, c.pf(QP_BANK_WG_W), (size_t)D.kb * d * 4, cudaMemcpyDeviceToDevice, st));
+    QV_CUDA(cudaMemcpyAsync(c.sv(S.bstack), c.pf(QP_BANK_WC_B), (size_t)d * 4, cudaMemcpyDeviceToDevice, st));
+    QV_CUDA(cudaMemcpyAsync(c.svf(S.bstack) + d, c.pf(QP_BANK_WG_B), (size_t)D.kb * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (dt == QV_BF16) {
+    for (int wi = 0; wi < W_COUNT; ++wi) {
+      if ((wi == W_TL && !D.tl) || (wi == W_WRITE && !train)) continue;
+      int N, K;
+      weight_shape(D, wi, &N, &K);
+      QV_TRY(convert_weight(st, weight_src(c, wi), N, K, reinterpret_cast<bf16*>(c.sv(S.wb[wi])),
+                            wi == W_WRITE ? nullptr : reinterpret_cast<bf16*>(c.sv(S.wbt[wi]))));
+    }
+  }
+
+  // ---- TokenLearner (H:985-1002)
+  const float* x = x_in;
+  if (D.tl) {
+    QV_TRY(ln_fwd(st, QV_F32, x_in, d, D.Rf, d, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), 1e-5f, 0, nullptr, nullptr, dt,
+                  c.sv(S.tl_ln), d, c.svf(S.tl_stats)));
+    QV_TRY(gemm_nt(st, dt, c.sv(S.tl_ln), d, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)),
+                   epi_t(c, c.pf(QP_TL_FC_B), c.sc(c.X.tl_logits), D.Nt)));
+    QV_TRY(token_learner_fwd(st, dt, x_in, c.sc(c.X.tl_logits), D.B, D.Nf, D.Nt, d, c.svf(S.tl_S), c.svf(S.xc)));
+    x = c.svf(S.xc);
+  }
+
+  // ---- norm1, fusion weights
+  void* xn = c.sv(S.xn);
+  QV_TRY(ln_fwd(st, QV_F32, x, d, R, d, c.pf(QP_NORM1_W), c.pf(QP_NORM1_B), 1e-5f, 0, nullptr, nullptr, dt, xn, d, c.svf(S.n1_stats)));
+  QV_TRY(fusion_softmax(st, c.pf(QP_FUSION_W), 4, c.svf(S.alpha)));
+
+  // ---- SWA (H:441-469)
+  QV_TRY(snapshot_bank(c, 0));
+  QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_SWA_QKV, c.pf(QP_SWA_QKV_W)), epi_t(c, c.pf(QP_SWA_QKV_B), c.sv(S.qkv_swa), 3 * d)));
+  {
+    AttnP p = attn_params(c, 0);
+    p.q = c.sv(S.qkv_swa); p.ldq = 3 * d; p.qcol = 0;
+    p.kv = c.sv(S.qkv_swa); p.ldkv = 3 * d; p.kcol = d; p.vcol = 2 * d;
+    p.Ek = c.pf(QP_SWA_EK); p.Ev = c.pf(QP_SWA_EV);
+    p.bank_k = snap_k(c, 0); p.bank_v = snap_v(c, 0);
+    p.out = c.sv(S.attn_swa); p.ldo = d;
+    QV_TRY(attn_fwd(st, dt, p));
+  }
+  QV_TRY(gemm_nt(st, dt, c.sv(S.attn_swa), d, R, c.W(W_SWA_PROJ, c.pf(QP_SWA_PROJ_W)), epi_t(c, c.pf(QP_SWA_PROJ_B), c.sv(S.branch[0]), d)));
+  if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[0]), QP_SWA_NORM_W, QP_SWA_NORM_B, update_count));
+
+  // ---- MSDA (H:496-532)
+  QV_TRY(snapshot_bank(c, 1));
+  QV_TRY(msda_pool_fwd(st, dt, xn, D.B, D.Nt, D.side, d, cfg->dilations, cfg->n_dilations, cfg->pool_stride, D.NM, c.sv(S.xp)));
+  QV_TRY(gemm_nt(st, dt, c.sv(S.xp), d, D.B * D.NM, c.W(W_MSDA_KV, weight_src(c, W_MSDA_KV)),
+                 epi_t(c, c.pf(QP_MSDA_QKV_B) + d, c.sv(S.kv_msda), 2 * d)));
+  QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_MSDA_Q, c.pf(QP_MSDA_QKV_W)), epi_t(c, c.pf(QP_MSDA_QKV_B), c.sv(S.q_msda), d)));
+  {
+    AttnP p = attn_params(c, 1);
+    p.q = c.sv(S.q_msda); p.ldq = d; p.qcol = 0;
+    p.kv = c.sv(S.kv_msda); p.ldkv = 2 * d; p.kcol = 0; p.vcol = d;
+    p.Ek = c.pf(QP_MSDA_EK); p.Ev = c.pf(QP_MSDA_EV);
+    p.bank_k = snap_k(c, 1); p.bank_v = snap_v(c, 1);
+    p.out = c.sv(S.attn_msda); p.ldo = d;
+    QV_TRY(attn_fwd(st, dt, p));
+  }
+  QV_TRY(gemm_nt(st, dt, c.sv(S.attn_msda), d, R, c.W(W_MSDA_PROJ, c.pf(QP_MSDA_PROJ_W)), epi_t(c, c.pf(QP_MSDA_PROJ_B), c.sv(S.branch[1]), d)));
+  if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[1]), QP_MSDA_NORM_W, QP_MSDA_NORM_B, update_count));
+
+  // ---- CGA (H:559-595)
+  QV_TRY(snapshot_bank(c, 2));
+  QV_TRY(small_linear_fwd(st, snap_k(c, 2), D.kb, d, c.pf(QP_CGA_BK_W), c.pf(QP_CGA_BK_B), D.cpg, c.svf(S.kbp)));
+  QV_TRY(small_linear_fwd(st, snap_v(c, 2), D.kb, d, c.pf(QP_CGA_BV_W), c.pf(QP_CGA_BV_B), D.cpg, c.svf(S.vbp)));
+  {
+    CgaP p{};
+    p.B = D.B; p.Nt = D.Nt; p.G = D.G; p.H = D.H; p.kb = D.kb; p.cg = D.cg; p.cpg = D.cpg;
+    p.xn = xn; p.ldx = d;
+    p.Wq = c.pf(QP_CGA_Q_W); p.bq = c.pf(QP_CGA_Q_B); p.Wk = c.pf(QP_CGA_K_W); p.bk = c.pf(QP_CGA_K_B);
+    p.Wv = c.pf(QP_CGA_V_W); p.bv = c.pf(QP_CGA_V_B);
+    p.kbp = c.svf(S.kbp); p.vbp = c.svf(S.vbp);
+    p.out = c.sv(S.attn_cga); p.ldo = d / 2;
+    QV_TRY(cga_fwd(st, dt, p));
+  }
+  QV_TRY(gemm_nt(st, dt, c.sv(S.attn_cga), d / 2, R, c.W(W_CGA_PROJ, c.pf(QP_CGA_PROJ_W)), epi_t(c, c.pf(QP_CGA_PROJ_B), c.sv(S.branch[2]), d)));
+  if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[2]), QP_CGA_NORM_W, QP_CGA_NORM_B, update_count));
+
+  // ---- Cross (H:613-626)
+  QV_TRY(snapshot_bank(c, 3));
+  QV_TRY(small_linear_fwd(st, snap_k(c, 3), D.kb, d, c.pf(QP_CROSS_K_W), c.pf(QP_CROSS_K_B), d, c.svf(S.Kc)));
+  QV_TRY(small_linear_fwd(st, snap_v(c, 3), D.kb, d, c.pf(QP_CROSS_V_W), c.pf(QP_CROSS_V_B), d, c.svf(S.Vc)));
+  QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), epi_t(c, c.pf(QP_CROSS_Q_B), c.sv(S.q_cross), d)));
+  {
+    AttnP p = attn_params(c, 2);
+    p.q = c.sv(S.q_cross); p.ldq = d; p.qcol = 0;
+    p.kc = c.svf(S.Kc); p.vc = c.svf(S.Vc);
+    p.out = c.sv(S.attn_cross); p.ldo = d;
+    QV_TRY(attn_fwd(st, dt, p));
+  }
+  QV_TRY(gemm_nt(st, dt, c.sv(S.attn_cross), d, R, c.W(W_CROSS_PROJ, c.pf(QP_CROSS_PROJ_W)), epi_t(c, c.pf(QP_CROSS_PROJ_B), c.sv(S.branch[3]), d)));
+
+  // ---- per-branch LN -> compress -> fusion scale + concat (H:1074-1079)
+  static const int kNormW[4] = {QP_NSWA_W, QP_NMSDA_W, QP_NCGA_W, QP_NCROSS_W};
+  static const int kCompW[4] = {QP_CSWA_W, QP_CMSDA_W, QP_CCGA_W, QP_CCROSS_W};
+  for (int i = 0; i < 4; ++i) {
+    QV_TRY(ln_fwd(st, dt, c.sv(S.branch[i]), d, R, d, c.pf(kNormW[i]), c.pf(kNormW[i] + 1), 1e-5f, 0, nullptr, nullptr, dt,
+                  c.sv(S.nb[i]), d, c.svf(S.nb_stats[i])));
+    GemmEpi e = epi_t(c, c.pf(kCompW[i] + 1), static_cast<uint8_t*>(c.sv(S.fused)) + (size_t)i * D.cd * D.ts, d);
+    e.scale_pre = c.svf(S.alpha) + i;
+    QV_TRY(gemm_nt(st, dt, c.sv(S.nb[i]), d, R, c.W(W_C0 + i, c.pf(kCompW[i])), e));
+  }
+  // ---- BottleneckMLP + residual (H:651-656, 1082)
+  {
+    GemmEpi e = epi_t(c, c.pf(QP_BMLP_FC1_B), c.sv(S.h1_pre), D.bh);
+    e.gelu = 1; e.C2 = c.sv(S.h1); e.ldc2 = D.bh; e.c2_f32 = dt == QV_F32;
+    QV_TRY(gemm_nt(st, dt, c.sv(S.fused), d, R, c.W(W_B1, c.pf(QP_BMLP_FC1_W)), e));
+    GemmEpi e2;
+    e2.bias = c.pf(QP_BMLP_FC2_B); e2.resid = x; e2.ldr = d; e2.C2 = c.sv(S.x1); e2.ldc2 = d; e2.c2_f32 = 1;
+    QV_TRY(gemm_nt(st, dt, c.sv(S.h1), D.bh, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), e2));
+  }
+  // ---- norm2 + CCF-FFN + residual (H:700-712, 1083)
+  float* blk_out = D.tl ? c.svf(S.out_blk) : out;
+  QV_TRY(ln_fwd(st, QV_F32, c.sv(S.x1), d, R, d, c.pf(QP_NORM2_W), c.pf(QP_NORM2_B), 1e-5f, 0, nullptr, nullptr, dt, c.sv(S.y), d, c.svf(S.n2_stats)));
+  if (!D.v1) {
+    QV_TRY(gemm_nt(st, dt, c.sv(S.y), d, R, c.W(W_F1, c.pf(QP_FFN_FC1_W)), epi_t(c, c.pf(QP_FFN_FC1_B), c.sv(S.h_pre), D.fh)));
+    QV_TRY(ln_fwd(st, dt, c.sv(S.h_pre), D.fh, R, D.fh, c.pf(QP_FFN_DWN_W), c.pf(QP_FFN_DWN_B), 1e-5f, 1, nullptr, nullptr, dt,
+                  c.sv(S.hn), D.fh, c.svf(S.dn_stats)));
+    QV_TRY(dwconv_fwd(st, dt, c.sv(S.hn), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W), cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr,
+                      c.pf(QP_FFN_SCALE), c.sv(S.cs)));
+    QV_TRY(ln_fwd(st, dt, c.sv(S.cs), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.pf(QP_FFN_PDN_B), 1e-5f, 0, nullptr, nullptr, dt,
+                  c.sv(S.hn2), D.fh, c.svf(S.pd_stats)));
+    GemmEpi e = epi_t(c, c.pf(QP_FFN_FC2_B), c.sv(S.o), d);
+    e.resid = c.svf(S.x1); e.ldr = d; e.scale_res = c.pf(QP_FFN_GAMMA); e.C2 = blk_out; e.ldc2 = d; e.c2_f32 = 1;
+    QV_TRY(gemm_nt(st, dt, c.sv(S.hn2), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e));
+  } else {
+    GemmEpi e = epi_t(c, c.pf(QP_FFN_FC1_B), c.sv(S.h_pre), D.fh);
+    e.gelu = 1; e.C2 = c.sv(S.h); e.ldc2 = D.fh; e.c2_f32 = dt == QV_F32;
+    QV_TRY(gemm_nt(st, dt, c.sv(S.y), d, R, c.W(W_F1, c.pf(QP_FFN_FC1_W)), e));
+    QV_TRY(dwconv_fwd(st, dt, c.sv(S.h), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W), cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, nullptr, c.sv(S.cs)));
+    GemmEpi e2;
+    e2.bias = c.pf(QP_FFN_FC2_B); e2.resid = c.svf(S.x1); e2.ldr = d; e2.C2 = blk_out; e2.ldc2 = d; e2.c2_f32 = 1;
+    QV_TRY(gemm_nt(st, dt, c.sv(S.cs), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e2));
+  }
+  // ---- TokenUpMix (H:1016-1031)
+  if (D.tl) {
+    QV_TRY(token_upmix_fwd(st, blk_out, D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.svf(S.up)));
+    QV_TRY(ln_fwd(st, QV_F32, c.sv(S.up), d, D.Rf, d, c.pf(QP_UP_LN_W), c.pf(QP_UP_LN_B), 1e-5f, 0, nullptr, nullptr, QV_F32, out, d, c.svf(S.up_stats)));
+  }
+  return 0;
+}
+
+// =====================================================================================================
+// backward
+// =====================================================================================================
+extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* const* params, float* const* grads,
+                                    const float* x_in, const float* dout, float* dx, const void* saved, void* scratch,
+                                    void* stream) {
+  Ctx c;
+  QV_TRY(init_ctx(&c, cfg, params, saved, scratch, stream));
+  QV_CHECK(grads && dout && dx, "null argument");
+  const Dims& D = c.D;
+  const Saved& S = c.S;
+  const Scratch& X = c.X;
+  const int dt = D.dt, d = D.d, R = D.R;
+  cudaStream_t st = c.st;
+  auto G = [&](int i) { return grads[i]; };
+  const float* x = D.tl ? c.svf(S.xc) : x_in;
+  const float* blk_out = D.tl ? c.svf(S.out_blk) : nullptr;
+  (void)blk_out;
+
+  // zero the accumulators (one contiguous range: d_xn .. draw)
+  QV_CUDA(cudaMemsetAsync(c.sc(X.d_xn), 0, X.draw + 16 - X.d_xn, st));
+
+  // ---- TokenUpMix backward
+  const float* dblk = dout;
+  if (D.tl) {
+    QV_TRY(ln_bwd(st, QV_F32, c.sv(S.up), d, QV_F32, dout, d, D.Rf, d, c.pf(QP_UP_LN_W), c.svf(S.up_stats), 0, QV_F32, nullptr,
+                  c.scf(X.d_up), nullptr, G(QP_UP_LN_W), G(QP_UP_LN_B)));
+    QV_TRY(token_upmix_bwd(st, c.svf(S.out_blk), c.scf(X.d_up), D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.scf(X.d_blk),
+                           G(QP_UP_FC_W), G(QP_UP_FC_B)));
+    dblk = c.scf(X.d_blk);
+  }
+
+  // ---- CCF-FFN backward
+  if (!D.v1) {
+    QV_TRY(gamma_bwd(st, dt, dblk, c.sv(S.o), (long)R * d, c.pf(QP_FFN_GAMMA), c.sc(X.d_o), G(QP_FFN_GAMMA)));
+    QV_TRY(gemm_tn(st, dt, c.sc(X.d_o), d, c.sv(S.hn2), D.fh, R, d, D.fh, G(QP_FFN_FC2_W), G(QP_FFN_FC2_B), nullptr));
+    QV_TRY(gemm_nn(st, dt, c.sc(X.d_o), d, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, nullptr, c.sc(X.d_hn2), D.fh)));
+    QV_TRY(ln_bwd(st, dt, c.sv(S.cs), D.fh, dt, c.sc(X.d_hn2), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.svf(S.pd_stats), 0, dt,
+                  c.sc(X.d_cs), nullptr, nullptr, G(QP_FFN_PDN_W), G(QP_FFN_PDN_B)));
+    QV_TRY(dwconv_bwd(st, dt, c.sv(S.hn), c.sc(X.d_cs), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W),
+                      cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, c.pf(QP_FFN_SCALE), c.sc(X.d_hn), G(QP_FFN_DW_W),
+                      cfg->dwconv_bias ? G(QP_FFN_DW_B) : nullptr, G(QP_FFN_SCALE)));
+    QV_TRY(ln_bwd(st, dt, c.sv(S.h_pre), D.fh, dt, c.sc(X.d_hn), D.fh, R, D.fh, c.pf(QP_FFN_DWN_W), c.svf(S.dn_stats), 1, dt,
+                  c.sc(X.d_hpre), nullptr, nullptr, G(QP_FFN_DWN_W), G(QP_FFN_DWN_B)));
+  } else {
+    QV_TRY(cast_f32_to_t(st, dt, dblk, (long)R * d, c.sc(X.d_o)));
+    QV_TRY(gemm_tn(st, dt, c.sc(X.d_o), d, c.sv(S.cs), D.fh, R, d, D.fh, G(QP_FFN_FC2_W), G(QP_FFN_FC2_B), nullptr));
+    QV_TRY(gemm_nn(st, dt, c.sc(X.d_o), d, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, nullptr, c.sc(X.d_cs), D.fh)));
+    QV_TRY(dwconv_bwd(st, dt, c.sv(S.h), c.sc(X.d_cs), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W),
+                      cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, nullptr, c.sc(X.d_hn), G(QP_FFN_DW_W),
+                      cfg->dwconv_bias ? G(QP_FFN_DW_B) : nullptr, nullptr));
+    QV_TRY(gelu_bwd(st, dt, c.sv(S.h_pre), c.sc(X.d_hn), (long)R * D.fh, c.sc(X.d_hpre)));
+  }
+  QV_TRY(gemm_tn(st, dt, c.sc(X.d_hpre), D.fh, c.sv(S.y), d, R, D.fh, d, G(QP_FFN_FC1_W), G(QP_FFN_FC1_B), nullptr));
+  QV_TRY(gemm_nn(st, dt, c.sc(X.d_hpre), D.fh, R, c.W(W_F1, c.pf(QP_FFN_FC1_W)), epi_t(c, nullptr, c.sc(X.d_y), d)));
+  // d_x1 = dblk + LN2-backward(d_y)   (fp32 and a T copy for the next GEMMs)
+  QV_TRY(ln_bwd(st, QV_F32, c.sv(S.x1), d, dt, c.sc(X.d_y), d, R, d, c.pf(QP_NORM2_W), c.svf(S.n2_stats), 0, dt, c.sc(X.d_x1t),
+                c.scf(X.d_x1), dblk, G(QP_NORM2_W), G(QP_NORM2_B)));
+
+  // ---- BottleneckMLP backward
+  QV_TRY(gemm_tn(st, dt, c.sc(X.d_x1t), d, c.sv(S.h1), D.bh, R, d, D.bh, G(QP_BMLP_FC2_W), G(QP_BMLP_FC2_B), nullptr));
+  QV_TRY(gemm_nn(st, dt, c.sc(X.d_x1t), d, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), epi_t(c, nullptr, c.sc(X.d_h1), D.bh)));
+  QV_TRY(gelu_bwd(st, dt, c.sv(S.h1_pre), c.sc(X.d_h1), (long)R * D.bh, c.sc(X.d_h1pre)));
+  QV_TRY(gemm_tn(st, dt, c.sc(X.d_h1pre), D.bh, c.sv(S.fused), d, R, D.bh, d, G(QP_BMLP_FC1_W), G(QP_BMLP_FC1_B), nullptr));
+  QV_TRY(gemm_nn(st, dt, c.sc(X.d_h1pre), D.bh, R, c.W(W_B1, c.pf(QP_BMLP_FC1_W)), epi_t(c, nullptr, c.sc(X.d_fused), d)));
+  // ---- fusion weights
+  QV_TRY(fusion_bwd(st, dt, c.sc(X.d_fused), c.sv(S.fused), R, 4, D.cd, c.svf(S.alpha), c.scf(X.draw)));
+  QV_TRY(fusion_bwd_final(st, c.svf(S.alpha), c.scf(X.draw), 4, G(QP_FUSION_W)));
+
+  static const int kNormW[4] = {QP_NSWA_W, QP_NMSDA_W, QP_NCGA_W, QP_NCROSS_W};
+  static const int kCompW[4] = {QP_CSWA_W, QP_CMSDA_W, QP_CCGA_W, QP_CCROSS_W};
+  float* d_xn = c.scf(X.d_xn);
+  GemmEpi acc_xn;
+  acc_xn.C = d_xn; acc_xn.ldc = d; acc_xn.c_f32 = 1; acc_xn.c_accum = 1;
+
+  for (int i = 3; i >= 0; --i) {
+    // compress_i and norm_i backward -> d_branch
+    const uint8_t* dfs = static_cast<const uint8_t*>(c.sc(X.d_fused)) + (size_t)i * D.cd * D.ts;
+    const float* alpha_i = c.svf(S.alpha) + i;
+    QV_TRY(gemm_tn(st, dt, dfs, d, c.sv(S.nb[i]), d, R, D.cd, d, G(kCompW[i]), G(kCompW[i] + 1), alpha_i));
+    GemmEpi e = epi_t(c, nullptr, c.sc(X.d_nb), d);
+    e.scale_pre = alpha_i;
+    QV_TRY(gemm_nn(st, dt, dfs, d, R, c.W(W_C0 + i, c.pf(kCompW[i])), e));
+    QV_TRY(ln_bwd(st, dt, c.sv(S.branch[i]), d, dt, c.sc(X.d_nb), d, R, d, c.pf(kNormW[i]), c.svf(S.nb_stats[i]), 0, dt,
+                  c.sc(X.d_branch), nullptr, nullptr, G(kNormW[i]), G(kNormW[i] + 1)));
+    const void* d_branch = c.sc(X.d_branch);
+    if (i == 3) {  // ---- cross
+      QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_cross), d, R, d, d, G(QP_CROSS_PROJ_W), G(QP_CROSS_PROJ_B), nullptr));
+      QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_CROSS_PROJ, c.pf(QP_CROSS_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d)));
+      AttnP p = attn_params(c, 2);
+      p.q = c.sv(S.q_cross); p.ldq = d; p.qcol = 0;
+      p.kc = c.svf(S.Kc); p.vc = c.svf(S.Vc);
+      p.dout = c.sc(X.d_attn); p.lddo = d;
+      p.dq = c.sc(X.d_q); p.lddq = d; p.dqcol = 0;
+      p.dbank_k = c.scf(X.dKc); p.dbank_v = c.scf(X.dVc);
+      QV_TRY(attn_bwd(st, dt, p));
+      QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_CROSS_Q_W), G(QP_CROSS_Q_B), nullptr));
+      QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), acc_xn));
+      QV_TRY(small_linear_bwd(st, snap_k(c, 3), D.kb, d, c.pf(QP_CROSS_K_W), d, c.scf(X.dKc), G(QP_CROSS_K_W), G(QP_CROSS_K_B), G(QP_BANK_K)));
+      QV_TRY(small_linear_bwd(st, snap_v(c, 3), D.kb, d, c.pf(QP_CROSS_V_W), d, c.scf(X.dVc), G(QP_CROSS_V_W), G(QP_CROSS_V_B), G(QP_BANK_V)));
+    } else if (i == 2) {  // ---- CGA
+      QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_cga), d / 2, R, d, d / 2, G(QP_CGA_PROJ_W), G(QP_CGA_PROJ_B), nullptr));
+      QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_CGA_PROJ, c.pf(QP_CGA_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d / 2)));
+      CgaP p{};
+      p.B = D.B; p.Nt = D.Nt; p.G = D.G; p.H = D.H; p.kb = D.kb; p.cg = D.cg; p.cpg = D.cpg;
+      p.xn = c.sv(S.xn); p.ldx = d;
+      p.Wq = c.pf(QP_CGA_Q_W); p.bq = c.pf(QP_CGA_Q_B); p.Wk = c.pf(QP_CGA_K_W); p.bk = c.pf(QP_CGA_K_B);
+      p.Wv = c.pf(QP_CGA_V_W); p.bv = c.pf(QP_CGA_V_B);
+      p.kbp = c.svf(S.kbp); p.vbp = c.svf(S.vbp);
+      p.dout = c.sc(X.d_attn); p.lddo = d / 2;
+      p.dxn = d_xn; p.lddx = d;
+      p.dWq = G(QP_CGA_Q_W); p.dbq = G(QP_CGA_Q_B); p.dWk = G(QP_CGA_K_W); p.dbk = G(QP_CGA_K_B);
+      p.dWv = G(QP_CGA_V_W); p.dbv = G(QP_CGA_V_B);
+      p.dkbp = c.scf(X.dkbp); p.dvbp = c.scf(X.dvbp);
+      QV_TRY(cga_bwd(st, dt, p));
+      QV_TRY(small_linear_bwd(st, snap_k(c, 2), D.kb, d, c.pf(QP_CGA_BK_W), D.cpg, c.scf(X.dkbp), G(QP_CGA_BK_W), G(QP_CGA_BK_B), G(QP_BANK_K)));
+      QV_TRY(small_linear_bwd(st, snap_v(c, 2), D.kb, d, c.pf(QP_CGA_BV_W), D.cpg, c.scf(X.dvbp), G(QP_CGA_BV_W), G(QP_CGA_BV_B), G(QP_BANK_V)));
+    } else if (i == 1) {  // ---- MSDA
+      QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_msda), d, R, d, d, G(QP_MSDA_PROJ_W), G(QP_MSDA_PROJ_B), nullptr));
+      QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_MSDA_PROJ, c.pf(QP_MSDA_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d)));
+      AttnP p = attn_params(c, 1);
+      p.q = c.sv(S.q_msda); p.ldq = d; p.qcol = 0;
+      p.kv = c.sv(S.kv_msda); p.ldkv = 2 * d; p.kcol = 0; p.vcol = d;
+      p.Ek = c.pf(QP_MSDA_EK); p.Ev = c.pf(QP_MSDA_EV);
+      p.bank_k = snap_k(c, 1); p.bank_v = snap_v(c, 1);
+      p.dout = c.sc(X.d_attn); p.lddo = d;
+      p.dq = c.sc(X.d_q); p.lddq = d; p.dqcol = 0;
+      p.dkv = c.sc(X.d_kv); p.lddkv = 2 * d; p.dkcol = 0; p.dvcol = d;
+      p.dEk = G(QP_MSDA_EK); p.dEv = G(QP_MSDA_EV); p.dbank_k = G(QP_BANK_K); p.dbank_v = G(QP_BANK_V);
+      QV_TRY(attn_bwd(st, dt, p));
+      QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_MSDA_QKV_W), G(QP_MSDA_QKV_B), nullptr));
+      QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_MSDA_Q, c.pf(QP_MSDA_QKV_W)), acc_xn));
+      QV_TRY(gemm_tn(st, dt, c.sc(X.d_kv), 2 * d, c.sv(S.xp), d, D.B * D.NM, 2 * d, d, G(QP_MSDA_QKV_W) + (size_t)d * d,
+                     G(QP_MSDA_QKV_B) + d, nullptr));
+      QV_TRY(gemm_nn(st, dt, c.sc(X.d_kv), 2 * d, D.B * D.NM, c.W(W_MSDA_KV, weight_src(c, W_MSDA_KV)), epi_t(c, nullptr, c.sc(X.d_xp), d)));
+      QV_TRY(msda_pool_bwd(st, dt, c.sc(X.d_xp), D.B, D.Nt, D.side, d, cfg->dilations, cfg->n_dilations, cfg->pool_stride, D.NM, d_xn));
+    } else {  // ---- SWA
+      QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_swa), d, R, d, d, G(QP_SWA_PROJ_W), G(QP_SWA_PROJ_B), nullptr));
+      QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_SWA_PROJ, c.pf(QP_SWA_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d)));
+      AttnP p = attn_params(c, 0);
+      p.q = c.sv(S.qkv_swa); p.ldq = 3 * d; p.qcol = 0;
+      p.kv = c.sv(S.qkv_swa); p.ldkv = 3 * d; p.kcol = d; p.vcol = 2 * d;
+      p.Ek = c.pf(QP_SWA_EK); p.Ev = c.pf(QP_SWA_EV);
+      p.bank_k = snap_k(c, 0); p.bank_v = snap_v(c, 0);
+      p.dout = c.sc(X.d_attn); p.lddo = d;
+      p.dq = c.sc(X.d_qkv); p.lddq = 3 * d; p.dqcol = 0;
+      p.dkv = c.sc(X.d_qkv); p.lddkv = 3 * d; p.dkcol = d; p.dvcol = 2 * d;
+      p.dEk = G(QP_SWA_EK); p.dEv = G(QP_SWA_EV); p.dbank_k = G(QP_BANK_K); p.dbank_v = G(QP_BANK_V);
+      QV_TRY(attn_bwd(st, dt, p));
+      QV_TRY(gemm_tn(st, dt, c.sc(X.d_qkv), 3 * d, c.sv(S.xn), d, R, 3 * d, d, G(QP_SWA_QKV_W), G(QP_SWA_QKV_B), nullptr));
+      QV_TRY(gemm_nn(st, dt, c.sc(X.d_qkv), 3 * d, R, c.W(W_SWA_QKV, c.pf(QP_SWA_QKV_W)), acc_xn));
+    }
+  }
+
+  // ---- norm1 backward: d_x = d_x1 + LN1-backward(d_xn)
+  float* dxc = D.tl ? c.scf(X.d_blk) : dx;   // d_blk is free again (consumed by the FFN backward)
+  QV_TRY(ln_bwd(st, QV_F32, x, d, QV_F32, d_xn, d, R, d, c.pf(QP_NORM1_W), c.svf(S.n1_stats), 0, QV_F32, nullptr, dxc,
+                c.scf(X.d_x1), G(QP_NORM1_W), G(QP_NORM1_B)));
+
+  // ---- TokenLearner backward
+  if (D.tl) {
+    QV_TRY(token_learner_bwd(st, dt, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, D.Nt, d, c.sc(X.d_logits), dx));
+    QV_TRY(gemm_tn(st, dt, c.sc(X.d_logits), D.Nt, c.sv(S.tl_ln), d, D.Rf, D.Nt, d, G(QP_TL_FC_W), G(QP_TL_FC_B), nullptr));
+    QV_TRY(gemm_nn(st, dt, c.sc(X.d_logits), D.Nt, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)), epi_t(c, nullptr, c.sc(X.d_tl_ln), d)));
+    QV_TRY(ln_bwd(st, QV_F32, x_in, d, dt, c.sc(X.d_tl_ln), d, D.Rf, d, c.pf(QP_TL_LN_W), c.svf(S.tl_stats), 0, QV_F32, nullptr, dx,
+                  dx, G(QP_TL_LN_W), G(QP_TL_LN_B)));
+  }
+  return 0;
+}
+
+// =====================================================================================================
+// thin wrappers
+// =====================================================================================================
+extern "C" int qavit_patch_embed_forward(const float* img, int B, int Cin, int S, int p, int d, const float* W,
+                                         const float* bias, const float* ln_w, const float* ln_b, const float* pos,
+                                         float* pre, float* stats, float* out, void* stream) {
+  return patch_embed_fwd((cudaStream_t)stream, img, B, Cin, S, p, d, W, bias, ln_w, ln_b, pos, pre, stats, out);
+}
+extern "C" int qavit_patch_embed_backward(const float* img, const float* dout, int B, int Cin, int S, int p, int d,
+                                          const float* pre, const float* stats, const float* ln_w, float* dpre_scratch,
+                                          float* dW, float* dbias, float* dln_w, float* dln_b, float* dpos, void* stream) {
+  return patch_embed_bwd((cudaStream_t)stream, img, dout, B, Cin, S, p, d, pre, stats, ln_w, dpre_scratch, dW, dbias, dln_w, dln_b, dpos);
+}
+extern "C" int qavit_head_forward(const float* x, int B, int N, int d, const float* ln_w, const float* ln_b, const float* W,
+                                  const float* bias, int classes, float* stats, float* pooled, float* logits, void* stream) {
+  return head_fwd((cudaStream_t)stream, x, B, N, d, ln_w, ln_b, W, bias, classes, stats, pooled, logits);
+}
+extern "C" int qavit_head_backward(const float* x, const float* dlogits, int B, int N, int d, const float* ln_w,
+                                   const float* stats, const float* pooled, const float* W, int classes,
+                                   float* dpooled_scratch, float* dx, float* dln_w, float* dln_b, float* dW, float* dbias,
+                                   void* stream) {
+  return head_bwd((cudaStream_t)stream, x, dlogits, B, N, d, ln_w, stats, pooled, W, classes, dpooled_scratch, dx, dln_w, dln_b, dW, dbias);
+}
+extern "C" int qavit_cross_entropy(const float* logits, const long long* ya, const long long* yb, float lam, int B,
+                                   int classes, float label_smoothing, float* loss, float* dlogits, void* stream) {
+  return ce_loss_fwd_bwd((cudaStream_t)stream, logits, ya, yb, lam, B, classes, label_smoothing, loss, dlogits);
+}
+extern "C" int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,
+                                  const float* bias, void* C, int c_f32, void* stream) {
+  GemmEpi e;
+  e.bias = bias; e.C = C; e.ldc = N; e.c_f32 = c_f32;
+  if (use_tc) return tc_gemm_nt((cudaStream_t)stream, (const bf16*)A, lda, M, N, K, (const bf16*)Wb, e);
+  return simt_gemm_nt((cudaStream_t)stream, QV_F32, A, lda, M, N, K, W, e);
+}
+extern "C" int qavit_test_gemm_tn(int use_tc, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K,
+                                  float* dW, float* db, void* stream) {
+  if (use_tc) {
+    QV_TRY(tc_gemm_tn((cudaStream_t)stream, (const bf16*)dY, ldy, (const bf16*)X, ldx, M, N, K, dW, nullptr));
+    if (db) QV_TRY(colsum_accum((cudaStream_t)stream, QV_BF16, dY, ldy, M, N, db, nullptr));
+    return 0;
+  }
+  return simt_gemm_tn((cudaStream_t)stream, QV_F32, dY, ldy, X, ldx, M, N, K, dW, db, nullptr);
+}
+extern "C" int qavit_convert_weight(const float* w, int N, int K, void* wb, void* wbt, void* stream) {
+  return convert_weight((cudaStream_t)stream, w, N, K, (bf16*)wb, (bf16*)wbt);
+}

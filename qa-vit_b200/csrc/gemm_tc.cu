@@ -1,0 +1,506 @@
+// tcgen05 / TMEM / TMA GEMMs for sm_100a (bf16 operands, fp32 accumulation in tensor memory).
+//
+//   tc_gemm_nt : C[M, N] = A[M, K] W[N, K]^T (+ epilogue).  Persistent, warp-specialised: warp 0 = TMA producer,
+//                warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
+//                128 x BLOCK_N output tiles, K streamed in 64-wide (128 B, SWIZZLE_128B) k-blocks through a 4-stage
+//                mbarrier ring; two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
+//                Used for every forward projection and (with the W^T copy) every dX GEMM.
+//   tc_gemm_tn : dW[N, K] += scale * dY[M, N]^T X[M, K].  Both operands are MN-major for the MMA (the contraction
+//                runs over rows), loaded by TMA as [64 rows x 64 cols] SWIZZLE_128B boxes and consumed through
+//                MN-major UMMA descriptors -- no transposed copies of activations are ever made.  The row range is
+//                split over CTAs; each CTA accumulates its slice in TMEM and reduces into dW with fp32 atomics.
+//
+// Descriptor bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables.
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (an error the tests report), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors
+// shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::f16: D=f32 [4,6)=1 | A=bf16 [7,10)=1 | B=bf16 [10,13)=1 | a_major [15] | b_major [16]
+//                                   | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int BM = 128;       // output rows per tile (UMMA M)
+constexpr int BK = 64;        // k-block: 64 bf16 = 128 B = one SWIZZLE_128B span
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 192;
+
+struct NtArgs {
+  int M, N, K;     // C[M, N], contraction K
+  int BN;          // columns per tile (multiple of 16, <= 256)
+  int n_slices;    // ceil(N / BN)
+  int m_tiles;
+  uint32_t tmem_cols;
+  GemmEpi e;
+};
+
+__device__ __forceinline__ void epilogue_store(const GemmEpi& e, long row, int col, const float* v, int ncols_valid,
+                                               float s_pre, float s_res) {
+  // v[0..15] -> columns col..col+15 of `row`
+  float val[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) val[j] = (v[j] + (e.bias ? e.bias[min(col + j, col + ncols_valid - 1)] : 0.f)) * s_pre;
+  if (e.C) {
+    if (e.c_f32) {
+      float* c = static_cast<float*>(e.C) + row * e.ldc + col;
+      if (ncols_valid == 16 && !e.c_accum) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
+      } else {
+        for (int j = 0; j < ncols_valid; ++j) c[j] = e.c_accum ? c[j] + val[j] : val[j];
+      }
+    } else {
+      bf16* c = static_cast<bf16*>(e.C) + row * e.ldc + col;
+      if (ncols_valid == 16) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(val[2 * j], val[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      } else {
+        for (int j = 0; j < ncols_valid; ++j) c[j] = __float2bfloat16_rn(val[j]);
+      }
+    }
+  }
+  if (e.C2) {
+    float v2[16];
+    if (e.gelu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v2[j] = gelu_f(val[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v2[j] = s_res * val[j];
+      if (e.resid) {
+        const float* r = e.resid + row * e.ldr + col;
+        for (int j = 0; j < ncols_valid; ++j) v2[j] += r[j];
+      }
+    }
+    if (e.c2_f32) {
+      float* c = static_cast<float*>(e.C2) + row * e.ldc2 + col;
+      if (ncols_valid == 16) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
+      } else {
+        for (int j = 0; j < ncols_valid; ++j) c[j] = v2[j];
+      }
+    } else {
+      bf16* c = static_cast<bf16*>(e.C2) + row * e.ldc2 + col;
+      if (ncols_valid == 16) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v2[2 * j], v2[2 * j + 1]);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      } else {
+        for (int j = 0; j < ncols_valid; ++j) c[j] = __float2bfloat16_rn(v2[j]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, NtArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2, stage_bytes = a_bytes + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = (p.K + BK - 1) / BK;
+  const int n0 = blockIdx.y * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty + s, ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          mbar_expect_tx(full + s, (uint32_t)stage_bytes);
+          tma_load_2d(sa, &map_a, full + s, kb * BK, mt * BM);
+          tma_load_2d(sa + a_bytes, &map_w, full + s, kb * BK, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, p.BN, 0, 0);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+        mbar_wait(tempty + acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sw = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(sw + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty + s);
+          if (kb == kblocks - 1) umma_commit(tfull + acc);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps (TMEM lane quarter = warp % 4)
+    const int quarter = warp & 3;
+    const GemmEpi& e = p.e;
+    const float s_pre = e.scale_pre ? *e.scale_pre : 1.f;
+    const float s_res = e.scale_res ? *e.scale_res : 1.f;
+    int acc = 0;
+    uint32_t aph = 0;
+    for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
+      mbar_wait(tfull + acc, aph);
+      tc_fence_after();
+      const long row = (long)mt * BM + quarter * 32 + lane;
+      const int ncols = min(p.BN, p.N - n0);
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + c0), v);
+        if (row < p.M) epilogue_store(e, row, n0 + c0, v, min(16, ncols - c0), s_pre, s_res);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + acc);
+      if (++acc == 2) { acc = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ dW kernel
+struct TnArgs {
+  int M, N, K;         // dW[N, K], contraction over M rows
+  int KD;              // K rounded up to 16 (UMMA N)
+  int kboxes;          // ceil(K / 64)
+  int mblocks;         // ceil(M / 64)
+  int mb_per_cta;
+  uint32_t tmem_cols;
+  float* dW;
+  const float* scale;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, TnArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int BOX = 64 * 64 * 2;                    // one [64 rows x 128 B] box
+  const int a_bytes = 2 * BOX, b_bytes = p.kboxes * BOX, stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BM;
+  const int mb0 = blockIdx.y * p.mb_per_cta;
+  const int mb1 = min(p.mblocks, mb0 + p.mb_per_cta);
+  const int nmb = mb1 - mb0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_y);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nmb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int mb = mb0; mb < mb1; ++mb) {
+          mbar_wait(empty + s, ph ^ 1);
+          uint8_t* sa = smem + s * stage_bytes;
+          mbar_expect_tx(full + s, (uint32_t)stage_bytes);
+          tma_load_2d(sa, &map_y, full + s, n0, mb * 64);
+          tma_load_2d(sa + BOX, &map_y, full + s, n0 + 64, mb * 64);
+          for (int kx = 0; kx < p.kboxes; ++kx) tma_load_2d(sa + a_bytes + kx * BOX, &map_x, full + s, kx * 64, mb * 64);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(BM, p.KD, 1, 1);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < nmb; ++i) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // 64 contraction rows = 4 x UMMA_K(16); 16 rows x 128 B = 2048 B apart
+            const uint64_t adesc = make_smem_desc(sa + k * 2048, BOX, 1024);
+            const uint64_t bdesc = make_smem_desc(sb + k * 2048, BOX, 1024);
+            umma_bf16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty + s);
+          if (i == nmb - 1) umma_commit(tfull);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else {
+      const int quarter = warp & 3;
+      const float sc = p.scale ? *p.scale : 1.f;
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const int n = n0 + quarter * 32 + lane;
+      for (int c0 = 0; c0 < p.KD; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        if (n < p.N) {
+          float* dst = p.dW + (long)n * p.K + c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.K) atomicAdd(dst + j, v[j] * sc);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows x 64 cols], SWIZZLE_128B, zero OOB fill
+int make_map(CUtensorMap* map, const bf16* base, long rows, long cols, long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  QV_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  QV_CHECK(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16 B aligned (ptr %p, ld %ld)", (const void*)base, ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%ld cols=%ld ld=%ld box_rows=%d", (int)r, rows, cols, ld, box_rows);
+  return 0;
+}
+
+uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while ((int)c < n) c <<= 1;
+  return c;
+}
+
+int pick_bn(int N) {
+  // largest multiple of 16 that is <= 256 and splits N into equal-ish slices
+  if (N <= 256) return ((N + 15) / 16) * 16;
+  for (int s = 2; s <= 8; ++s) {
+    if (N % s == 0 && (N / s) % 16 == 0 && N / s <= 256) return N / s;
+  }
+  return 256;
+}
+
+}  // namespace
+
+bool tc_shape_ok_nt(int M, int N, int K, int lda) {
+  return M >= 1 && N >= 16 && K >= 8 && K % 8 == 0 && lda % 8 == 0;
+}
+bool tc_shape_ok_tn(int M, int N, int K, int ldy, int ldx) {
+  return M >= 1 && N >= 8 && K >= 8 && K <= 256 && N % 8 == 0 && K % 8 == 0 && ldy % 8 == 0 && ldx % 8 == 0;
+}
+
+int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, const bf16* Wb, const GemmEpi& e) {
+  if (M <= 0) return 0;
+  QV_CHECK(tc_shape_ok_nt(M, N, K, lda), "tc_gemm_nt: unsupported shape M=%d N=%d K=%d lda=%d", M, N, K, lda);
+  QV_CHECK(!(e.c_accum && !e.c_f32), "gemm: accumulate needs an fp32 C");
+  NtArgs p{};
+  p.M = M; p.N = N; p.K = K;
+  p.BN = pick_bn(N);
+  p.n_slices = cdiv(N, p.BN);
+  p.m_tiles = cdiv(M, BM);
+  p.tmem_cols = pow2_cols(2 * p.BN);
+  p.e = e;
+  QV_CHECK(p.tmem_cols <= 512, "tc_gemm_nt: BN=%d needs %u TMEM columns", p.BN, p.tmem_cols);
+  CUtensorMap ma, mw;
+  QV_TRY(make_map(&ma, A, M, K, lda, BM));
+  QV_TRY(make_map(&mw, Wb, N, K, K, p.BN));
+  const size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + p.BN * BK * 2) + 256;
+  QV_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int gx = max(1, min(p.m_tiles, qv_num_sms() / p.n_slices));
+  tc_gemm_nt_kernel<<<dim3(gx, p.n_slices), NTHREADS, smem, s>>>(ma, mw, p);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
+               const float* scale) {
+  if (M <= 0) return 0;
+  QV_CHECK(tc_shape_ok_tn(M, N, K, ldy, ldx), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
+  TnArgs p{};
+  p.M = M; p.N = N; p.K = K;
+  p.KD = ((K + 15) / 16) * 16;
+  p.kboxes = cdiv(K, 64);
+  p.mblocks = cdiv(M, 64);
+  p.tmem_cols = pow2_cols(p.KD);
+  p.dW = dW;
+  p.scale = scale;
+  const int n_tiles = cdiv(N, BM);
+  int splits = max(1, min(p.mblocks, (2 * qv_num_sms()) / n_tiles));
+  p.mb_per_cta = cdiv(p.mblocks, splits);
+  splits = cdiv(p.mblocks, p.mb_per_cta);
+  CUtensorMap my, mx;
+  QV_TRY(make_map(&my, dY, M, N, ldy, 64));
+  QV_TRY(make_map(&mx, X, M, K, ldx, 64));
+  const size_t smem = 1024 + (size_t)STAGES * (2 + p.kboxes) * (64 * 64 * 2) + 256;
+  QV_CHECK(smem <= 227 * 1024, "tc_gemm_tn: K=%d needs %zu B smem", K, smem);
+  QV_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_gemm_tn_kernel<<<dim3(n_tiles, splits), NTHREADS, smem, s>>>(my, mx, p);
+  QV_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,280 @@
+// Patch embedding (im2col-free), classifier head, label-smoothed cross entropy, gradient clipping and the
+// fused AdamW step.  Warp-shuffle reductions, coalesced/vectorised streams; all fp32.
+#include "kernels.h"
+
+// =============================================================================== patch embed (H:1129-1138, :1250)
+namespace {
+constexpr int PE_KC = 48;  // contraction chunk staged in shared memory
+// One CTA per image.  stride == kernel, so patch row (py, px) is the [Cin, p, p] box at (py*p, px*p): read straight
+// from the image, no im2col buffer.  pre = conv (saved for backward), out = LN(pre) + pos.
+__global__ void __launch_bounds__(192) patch_embed_fwd_kernel(const float* __restrict__ img, int B, int Cin, int S, int p,
+                                                              int d, const float* __restrict__ W,
+                                                              const float* __restrict__ bias,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const float* __restrict__ pos, float* __restrict__ pre,
+                                                              float* __restrict__ stats, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int n_side = S / p, N = n_side * n_side, K = Cin * p * p;
+  float* sP = sm;                      // [N][PE_KC]      patch chunk
+  float* sW = sP + N * PE_KC;          // [d][PE_KC + 1]  weight chunk
+  float* sO = sW + d * (PE_KC + 1);    // [N][d]          conv output
+  const int tid = threadIdx.x;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int idx = tid; idx < N * d; idx += blockDim.x) sO[idx] = bias[idx % d];
+    for (int k0 = 0; k0 < K; k0 += PE_KC) {
+      const int kc = min(PE_KC, K - k0);
+      __syncthreads();
+      for (int idx = tid; idx < N * kc; idx += blockDim.x) {
+        const int n = idx / kc, k = k0 + idx % kc;
+        const int c = k / (p * p), r = (k / p) % p, q = k % p;
+        sP[n * PE_KC + idx % kc] = img[(((long)b * Cin + c) * S + (n / n_side) * p + r) * S + (n % n_side) * p + q];
+      }
+      for (int idx = tid; idx < d * kc; idx += blockDim.x) sW[(idx / kc) * (PE_KC + 1) + idx % kc] = W[(long)(idx / kc) * K + k0 + idx % kc];
+      __syncthreads();
+      for (int o = tid; o < d; o += blockDim.x) {
+        for (int n = 0; n < N; ++n) {
+          float a = sO[n * d + o];
+          for (int k = 0; k < kc; ++k) a = fmaf(sP[n * PE_KC + k], sW[o * (PE_KC + 1) + k], a);
+          sO[n * d + o] = a;
+        }
+      }
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int n = warp; n < N; n += nwarp) {
+      float s = 0.f;
+      for (int c = lane; c < d; c += 32) s += sO[n * d + c];
+      const float mean = warp_sum(s) / d;
+      float q = 0.f;
+      for (int c = lane; c < d; c += 32) { const float t = sO[n * d + c] - mean; q += t * t; }
+      const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+      const long row = (long)b * N + n;
+      if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+      for (int c = lane; c < d; c += 32) {
+        const float v = sO[n * d + c];
+        pre[row * d + c] = v;
+        out[row * d + c] = (v - mean) * rstd * gamma[c] + beta[c] + (pos ? pos[n * d + c] : 0.f);
+      }
+    }
+    __syncthreads();
+  }
+}
+// dW[o, k] += sum_{b, n} dpre[b, n, o] * patch[b, n, k].  thread = output channel, 48 accumulators in registers.
+__global__ void __launch_bounds__(192) patch_embed_dw_kernel(const float* __restrict__ img, const float* __restrict__ dpre,
+                                                             int B, int Cin, int S, int p, int d,
+                                                             float* __restrict__ dW) {
+  extern __shared__ float sP[];  // [N][PE_KC]
+  const int n_side = S / p, N = n_side * n_side, K = Cin * p * p;
+  const int tid = threadIdx.x;
+  for (int k0 = 0; k0 < K; k0 += PE_KC) {
+    const int kc = min(PE_KC, K - k0);
+    float acc[PE_KC];
+#pragma unroll
+    for (int k = 0; k < PE_KC; ++k) acc[k] = 0.f;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+      __syncthreads();
+      for (int idx = tid; idx < N * kc; idx += blockDim.x) {
+        const int n = idx / kc, k = k0 + idx % kc;
+        const int c = k / (p * p), r = (k / p) % p, q = k % p;
+        sP[n * PE_KC + idx % kc] = img[(((long)b * Cin + c) * S + (n / n_side) * p + r) * S + (n % n_side) * p + q];
+      }
+      __syncthreads();
+      if (tid < d) {
+        for (int n = 0; n < N; ++n) {
+          const float g = dpre[((long)b * N + n) * d + tid];
+#pragma unroll
+          for (int k = 0; k < PE_KC; ++k) if (k < kc) acc[k] = fmaf(g, sP[n * PE_KC + k], acc[k]);
+        }
+      }
+    }
+    if (tid < d) {
+#pragma unroll
+      for (int k = 0; k < PE_KC; ++k) if (k < kc) atomicAdd(dW + (long)tid * K + k0 + k, acc[k]);
+    }
+  }
+}
+}  // namespace
+
+int patch_embed_fwd(cudaStream_t s, const float* img, int B, int Cin, int S, int p, int d, const float* W,
+                    const float* bias, const float* gamma, const float* beta, const float* pos, float* pre, float* stats,
+                    float* out) {
+  if (B <= 0) return 0;
+  const int N = (S / p) * (S / p);
+  const size_t smem = (size_t)(N * PE_KC + d * (PE_KC + 1) + N * d) * sizeof(float);
+  QV_CHECK(smem <= 227 * 1024 && d <= 192 * 2, "patch_embed: %d tokens x %d dims needs %zu B smem: not supported", N, d, smem);
+  QV_CUDA(cudaFuncSetAttribute(patch_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  patch_embed_fwd_kernel<<<min(B, qv_num_sms() * 2), 192, smem, s>>>(img, B, Cin, S, p, d, W, bias, gamma, beta, pos, pre, stats, out);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+int patch_embed_bwd(cudaStream_t s, const float* img, const float* dout, int B, int Cin, int S, int p, int d,
+                    const float* pre, const float* stats, const float* gamma, float* dpre, float* dW, float* dbias,
+                    float* dgamma, float* dbeta, float* dpos) {
+  if (B <= 0) return 0;
+  const int N = (S / p) * (S / p);
+  QV_CHECK(d <= 192, "patch_embed_bwd: d=%d > 192", d);
+  // dpos[n, c] += sum_b dout[b, n, c]
+  if (dpos) QV_TRY(colsum_accum(s, QV_F32, dout, N * d, B, N * d, dpos, nullptr));
+  QV_TRY(ln_bwd(s, QV_F32, pre, d, QV_F32, dout, d, B * N, d, gamma, stats, 0, QV_F32, nullptr, dpre, nullptr, dgamma, dbeta));
+  QV_TRY(colsum_accum(s, QV_F32, dpre, d, B * N, d, dbias, nullptr));
+  const size_t smem = (size_t)N * PE_KC * sizeof(float);
+  QV_CUDA(cudaFuncSetAttribute(patch_embed_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  patch_embed_dw_kernel<<<min(B, qv_num_sms()), 192, smem, s>>>(img, dpre, B, Cin, S, p, d, dW);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================== head (H:1273-1275)
+namespace {
+// pooled[b, :] = mean_n LN(x[b, n, :]).  One CTA (8 warps) per image.
+__global__ void __launch_bounds__(256) ln_mean_kernel(const float* __restrict__ x, int B, int N, int d,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float* __restrict__ stats, float* __restrict__ pooled) {
+  __shared__ float acc[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+    for (int n = warp; n < N; n += 8) {
+      const long row = (long)b * N + n;
+      float v[8], s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; v[i] = c < d ? x[row * d + c] : 0.f; s += v[i]; }
+      const float mean = warp_sum(s) / d;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; if (c < d) { const float t = v[i] - mean; q += t * t; } }
+      const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+      if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; if (c < d) a[i] += (v[i] - mean) * rstd * gamma[c] + beta[c]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[warp][lane + 32 * i] = a[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += acc[w][c];
+      pooled[(long)b * d + c] = t / N;
+    }
+  }
+}
+// LN backward where every token row of image b receives dy = dpooled[b, :] / N.
+__global__ void __launch_bounds__(256) ln_mean_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dpooled,
+                                                          int B, int N, int d, const float* __restrict__ gamma,
+                                                          const float* __restrict__ stats, float* __restrict__ dx,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[2][8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ag[8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ag[i] = ab[i] = 0.f;
+  const float invN = 1.f / N, invd = 1.f / d;
+  for (long row = (long)blockIdx.x * 8 + warp; row < (long)B * N; row += (long)gridDim.x * 8) {
+    const long b = row / N;
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float xh[8], g[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      xh[i] = g[i] = 0.f;
+      if (c < d) {
+        const float dyv = dpooled[b * d + c] * invN;
+        xh[i] = (x[row * d + c] - mean) * rstd;
+        g[i] = dyv * gamma[c];
+        ag[i] += dyv * xh[i];
+        ab[i] += dyv;
+        s1 += g[i];
+        s2 += g[i] * xh[i];
+      }
+    }
+    const float c1 = warp_sum(s1) * invd, c2 = warp_sum(s2) * invd;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; if (c < d) dx[row * d + c] = rstd * (g[i] - c1 - xh[i] * c2); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][warp][lane + 32 * i] = ag[i]; red[1][warp][lane + 32 * i] = ab[i]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float a = 0.f, bsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += red[0][w][c]; bsum += red[1][w][c]; }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, bsum);
+  }
+}
+}  // namespace
+
+int head_fwd(cudaStream_t s, const float* x, int B, int N, int d, const float* gamma, const float* beta, const float* W,
+             const float* bias, int ncls, float* stats, float* pooled, float* logits) {
+  if (B <= 0) return 0;
+  QV_CHECK(d <= 256, "head: d=%d > 256", d);
+  ln_mean_kernel<<<min(B, qv_num_sms() * 4), 256, 0, s>>>(x, B, N, d, gamma, beta, stats, pooled);
+  QV_LAUNCH_CHECK();
+  GemmEpi e;
+  e.bias = bias; e.C = logits; e.ldc = ncls; e.c_f32 = 1;
+  return simt_gemm_nt(s, QV_F32, pooled, d, B, ncls, d, W, e);
+}
+
+int head_bwd(cudaStream_t s, const float* x, const float* dlogits, int B, int N, int d, const float* gamma,
+             const float* stats, const float* pooled, const float* W, int ncls, float* dpooled, float* dx,
+             float* dgamma, float* dbeta, float* dW, float* dbias) {
+  if (B <= 0) return 0;
+  QV_TRY(simt_gemm_tn(s, QV_F32, dlogits, ncls, pooled, d, B, ncls, d, dW, dbias, nullptr));
+  GemmEpi e;
+  e.C = dpooled; e.ldc = d; e.c_f32 = 1;
+  QV_TRY(simt_gemm_nn(s, QV_F32, dlogits, ncls, B, ncls, d, W, e));
+  ln_mean_bwd_kernel<<<min(cdiv((long)B * N, 8), qv_num_sms() * 4), 256, 0, s>>>(x, dpooled, B, N, d, gamma, stats, dx, dgamma, dbeta);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================== cross entropy (H:1373, :1404-1408)
+namespace {
+// loss = mean_b [ lam * CE_ls(y_a) + (1 - lam) * CE_ls(y_b) ],  CE_ls = (1-eps) * nll + eps * mean_c(-log p_c)
+__global__ void ce_kernel(const float* __restrict__ logits, const long long* __restrict__ ya,
+                          const long long* __restrict__ yb, float lam, int B, int C, float eps, float* __restrict__ loss,
+                          float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* l = logits + (long)row * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, l[c]);
+  m = warp_max(m);
+  float z = 0.f, sl = 0.f;
+  for (int c = lane; c < C; c += 32) { z += expf(l[c] - m); sl += l[c]; }
+  z = warp_sum(z);
+  sl = warp_sum(sl);
+  const float lse = m + logf(z);
+  const int a = (int)ya[row], b2 = yb ? (int)yb[row] : a;
+  const float wa = yb ? lam : 1.f, wb = yb ? 1.f - lam : 0.f;
+  if (lane == 0) {
+    const float nll = wa * (lse - l[a]) + wb * (lse - l[b2]);
+    const float smooth = lse - sl / C;
+    atomicAdd(loss, ((1.f - eps) * nll + eps * smooth) / B);
+  }
+  if (dlogits) {
+    for (int c = lane; c < C; c += 32) {
+      float t = eps / C;
+      if (c == a) t += (1.f - eps) * wa;
+      if (c == b2) t += (1.f - eps) * wb;
+      dlogits[(long)row * C + c] = (expf(l[c] - lse) - t) / B;
+    }
+  }
+}
+}  // namespace
+
+int ce_loss_fwd_bwd(cudaStream_t s, const float* logits, const long long* ya, const long long* yb, float lam, int B,
+                    int ncls, float smoothing, float* loss, float* dlogits) {
+  QV_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+  if (B <= 0) return 0;
+  ce_kernel<<<cdiv(B, 4), 128, 0, s>>>(logits, ya, yb, lam, B, ncls, smoothing, loss, dlogits);
+  QV_LAUNCH_CHECK();
+  return 0;
+}

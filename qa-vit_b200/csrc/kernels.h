@@ -1,0 +1,146 @@
+// Internal launcher interface shared by the .cu files of libqavit_b200.so.
+// dt codes: 0 = float32, 1 = bfloat16 ("T" = the activation storage type of the run).
+#pragma once
+#include "common.cuh"
+
+enum { QV_F32 = 0, QV_BF16 = 1 };
+
+// Epilogue of every GEMM flavour:  val = acc (+ bias[j]);  if (scale_pre) val *= *scale_pre;
+//   C  [i, j] (T or fp32; += if c_accum)  = val            (pre-activation when gelu != 0)
+//   C2 [i, j] (T or fp32)                 = gelu ? gelu(val) : resid[i, j] + (scale_res ? *scale_res : 1) * val
+struct GemmEpi {
+  const float* bias = nullptr;
+  const float* scale_pre = nullptr;
+  const float* scale_res = nullptr;
+  int gelu = 0;
+  const float* resid = nullptr;
+  int ldr = 0;
+  void* C = nullptr;
+  int ldc = 0;
+  int c_f32 = 0;
+  int c_accum = 0;
+  void* C2 = nullptr;
+  int ldc2 = 0;
+  int c2_f32 = 0;
+};
+
+// A weight as the GEMMs see it: fp32 master [N, K] row-major, plus (bf16 runs) bf16 copies of W and W^T.
+struct Weight {
+  const float* w = nullptr;   // [N, K]
+  const bf16* wb = nullptr;   // [N, K]   bf16 copy      (tcgen05 forward GEMM B operand)
+  const bf16* wbt = nullptr;  // [K, N]   bf16 transpose (tcgen05 dX GEMM B operand)
+  int N = 0, K = 0;
+};
+
+// Y[M, N] = A[M, K] W^T             (A: dt, row stride lda)
+int gemm_nt(cudaStream_t s, int dt, const void* A, int lda, int M, const Weight& W, const GemmEpi& e);
+// dX[M, K] = dY[M, N] W             (dY: dt, row stride ldy)
+int gemm_nn(cudaStream_t s, int dt, const void* dY, int ldy, int M, const Weight& W, const GemmEpi& e);
+// dW[N, K] += scale * dY[M, N]^T X[M, K] ; db[N] += scale * colsum(dY)     (fp32 outputs, atomically accumulated)
+int gemm_tn(cudaStream_t s, int dt, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW,
+            float* db, const float* scale);
+
+// fp32 SIMT flavours (always available; the parity-mode GEMM and the small-shape GEMM of bf16 runs)
+int simt_gemm_nt(cudaStream_t s, int dtA, const void* A, int lda, int M, int N, int K, const float* W, const GemmEpi& e);
+int simt_gemm_nn(cudaStream_t s, int dtA, const void* dY, int ldy, int M, int N, int K, const float* W, const GemmEpi& e);
+int simt_gemm_tn(cudaStream_t s, int dt, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K,
+                 float* dW, float* db, const float* scale);
+
+// tcgen05 / TMEM / TMA flavours (bf16 operands, fp32 accumulate)
+int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, const bf16* Wb, const GemmEpi& e);
+int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
+               const float* scale);
+bool tc_shape_ok_nt(int M, int N, int K, int lda);
+bool tc_shape_ok_tn(int M, int N, int K, int ldy, int ldx);
+int colsum_accum(cudaStream_t s, int dt, const void* dY, int ldy, int M, int N, float* db, const float* scale);
+int convert_weight(cudaStream_t s, const float* w, int N, int K, bf16* wb, bf16* wbt);
+
+// ---- norms
+int ln_fwd(cudaStream_t s, int dt_in, const void* x, int ldx, int rows, int C, const float* gamma, const float* beta,
+           float eps, int gelu_in, const float* gamma2, const float* beta2, int dt_out, void* y, int ldy, float* stats);
+int ln_bwd(cudaStream_t s, int dt_x, const void* x, int ldx, int dt_dy, const void* dy, int lddy, int rows, int C,
+           const float* gamma, const float* stats, int gelu_in, int dt_out, void* dx_t, float* dx_f32,
+           const float* resid, float* dgamma, float* dbeta);
+
+// ---- attention family
+struct AttnP {
+  int mode;          // 0 = SWA (windowed, linformer), 1 = MSDA (pooled kv, linformer), 2 = cross (direct bank kv)
+  int B, Nt, side, ws, H, hd, kb, klin, L;   // L: rows of E actually contracted (ws^2 | min(NM, 128)); NMrows below
+  int NM;            // pooled tokens per image (MSDA kv rows per image)
+  const void* q; int ldq; int qcol;          // T
+  const void* kv; int ldkv; int kcol, vcol;  // T (mode 0/1); mode 2: fp32 Kc/Vc [kb, H*hd] in kc/vc
+  const float* kc; const float* vc;
+  const float* Ek; const float* Ev;          // [Lfull, klin]
+  const float* bank_k; const float* bank_v;  // [kb, H*hd] snapshot
+  void* out; int ldo;                        // T  [rows, H*hd]
+  // backward only
+  const void* dout; int lddo;                // T
+  void* dq; int lddq; int dqcol;             // T
+  void* dkv; int lddkv; int dkcol, dvcol;    // T
+  float* dEk; float* dEv; float* dbank_k; float* dbank_v;   // fp32 accumulators (mode 2: dKc/dVc in dbank_k/v)
+};
+int attn_fwd(cudaStream_t s, int dt, const AttnP& p);
+int attn_bwd(cudaStream_t s, int dt, const AttnP& p);
+
+struct CgaP {
+  int B, Nt, G, H, kb, cg, cpg;              // cg = 32 channels/group, cpg = 16 compressed/group
+  const void* xn; int ldx;                   // T [B*Nt, G*cg]
+  const float *Wq, *bq, *Wk, *bk, *Wv, *bv;  // [cpg, cg], [cpg]
+  const float *kbp, *vbp;                    // projected bank [kb, cpg] fp32
+  void* out; int ldo;                        // T [B*Nt, G*cpg]
+  const void* dout; int lddo;                // T
+  float* dxn; int lddx;                      // fp32 accumulate [B*Nt, G*cg]
+  float *dWq, *dbq, *dWk, *dbk, *dWv, *dbv, *dkbp, *dvbp;
+};
+int cga_fwd(cudaStream_t s, int dt, const CgaP& p);
+int cga_bwd(cudaStream_t s, int dt, const CgaP& p);
+
+// small dense [rows<=64] projections of the bank: Y = X W^T + b and its backward (single CTA, fp32)
+int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y);
+int small_linear_bwd(cudaStream_t s, const float* X, int rows, int K, const float* W, int N, const float* dY,
+                     float* dW, float* db, float* dX_accum);
+
+// ---- bank write (train-mode forward only, no gradient)
+int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, int kb,
+                      float* partial, int* n_partial);
+int bank_write_apply(cudaStream_t s, const float* partial, int n_partial, int B, int d, int kb, float* bank_k,
+                     float* bank_v, long long* update_count, int v1);
+
+// ---- misc per-image kernels
+int msda_pool_fwd(cudaStream_t s, int dt, const void* xn, int B, int Nt, int side, int C, const int* dil, int ndil,
+                  int stride, int NM, void* xp);
+int msda_pool_bwd(cudaStream_t s, int dt, const void* dxp, int B, int Nt, int side, int C, const int* dil, int ndil,
+                  int stride, int NM, float* dxn);
+int dwconv_fwd(cudaStream_t s, int dt, const void* x, int B, int side, int C, const float* w, const float* bias,
+               const float* scale, void* y);
+int dwconv_bwd(cudaStream_t s, int dt, const void* x, const void* dy, int B, int side, int C, const float* w,
+               const float* bias, const float* scale, void* dx, float* dw, float* dbias, float* dscale);
+int gelu_bwd(cudaStream_t s, int dt, const void* pre, const void* dact, long n, void* dpre);
+int gamma_bwd(cudaStream_t s, int dt, const float* dout, const void* o, long n, const float* gamma, void* d_o,
+              float* dgamma);
+int cast_f32_to_t(cudaStream_t s, int dt, const float* x, long n, void* y);
+int fusion_softmax(cudaStream_t s, const float* w, int n, float* alpha);
+int fusion_bwd(cudaStream_t s, int dt, const void* dfused, const void* fused, long rows, int nb, int cw,
+               const float* alpha, float* dalpha_raw);
+int fusion_bwd_final(cudaStream_t s, const float* alpha, const float* dalpha_raw, int nb, float* dw);
+int token_learner_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, int N, int M, int C, float* S,
+                      float* xc);
+int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float* dxc, int B, int N, int M,
+                      int C, void* dlogits, float* dx);
+int token_upmix_fwd(cudaStream_t s, const float* xc, int B, int M, int N, int C, const float* W, const float* bias,
+                    float* up);
+int token_upmix_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int M, int N, int C, const float* W,
+                    float* dxc, float* dW, float* dbias);
+int patch_embed_fwd(cudaStream_t s, const float* img, int B, int Cin, int S, int p, int d, const float* W,
+                    const float* bias, const float* gamma, const float* beta, const float* pos, float* pre, float* stats,
+                    float* out);
+int patch_embed_bwd(cudaStream_t s, const float* img, const float* dout, int B, int Cin, int S, int p, int d,
+                    const float* pre, const float* stats, const float* gamma, float* dpre_scratch, float* dW,
+                    float* dbias, float* dgamma, float* dbeta, float* dpos);
+int head_fwd(cudaStream_t s, const float* x, int B, int N, int d, const float* gamma, const float* beta, const float* W,
+             const float* bias, int ncls, float* stats, float* pooled, float* logits);
+int head_bwd(cudaStream_t s, const float* x, const float* dlogits, int B, int N, int d, const float* gamma,
+             const float* stats, const float* pooled, const float* W, int ncls, float* dpooled_scratch, float* dx,
+             float* dgamma, float* dbeta, float* dW, float* dbias);
+int ce_loss_fwd_bwd(cudaStream_t s, const float* logits, const long long* ya, const long long* yb, float lam, int B,
+                    int ncls, float smoothing, float* loss, float* dlogits);

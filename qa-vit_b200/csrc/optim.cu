@@ -1,0 +1,139 @@
+// Gradient clipping (per-parameter + global L2, H:1413-1432) and the fused AdamW step (H:1436, torch single-tensor
+// rule) on flat fp32 buffers.  HBM-bound: AdamW reads p, g, m, v (16 B/elem) and writes p, m, v (12 B/elem).
+// Segments (= parameter tensors) start on 4-float boundaries so every access is a float4.
+#include "../../include/qavit_b200.h"
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;  // valid in thread 0
+}
+
+// norms[s] = ||g_s||_2, one CTA per segment
+__global__ void __launch_bounds__(256) seg_norm_kernel(const float* __restrict__ g, const long long* __restrict__ off,
+                                                       const int* __restrict__ flags, float* __restrict__ norms) {
+  __shared__ float red[32];
+  const int s = blockIdx.x;
+  float acc = 0.f;
+  if (flags[s] & 1) {
+    const long long b = off[s], e = off[s + 1];
+    for (long long i = b + threadIdx.x * 4LL; i < e; i += blockDim.x * 4LL) {
+      const float4 v = *reinterpret_cast<const float4*>(g + i);
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  }
+  const float t = block_sum(acc, red);
+  if (threadIdx.x == 0) norms[s] = sqrtf(t);
+}
+
+// per-segment scale = per-param coef * global coef (written over norms[s]); norms[n] = global norm before global clip
+__global__ void __launch_bounds__(1024) clip_coef_kernel(const int* __restrict__ flags, int n, float per_param_max,
+                                                         float max_norm, float* __restrict__ norms) {
+  __shared__ float red[32];
+  __shared__ float gcoef;
+  float acc = 0.f;
+  for (int s = threadIdx.x; s < n; s += blockDim.x) {
+    float c = 1.f;
+    const float nm = norms[s];
+    if (flags[s] & 2) c = fminf(1.f, per_param_max / (nm + 1e-6f));
+    const float cn = (flags[s] & 1) ? c * nm : 0.f;
+    acc += cn * cn;
+    norms[s] = c;
+  }
+  const float t = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float total = sqrtf(t);
+    norms[n] = total;
+    gcoef = fminf(1.f, max_norm / (total + 1e-6f));
+    norms[n + 1] = gcoef;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < n; s += blockDim.x) norms[s] *= gcoef;
+}
+
+__device__ __forceinline__ int find_seg(const long long* __restrict__ off, int n, long long i) {
+  int lo = 0, hi = n;  // off[lo] <= i < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) scale_grads_kernel(float* __restrict__ g, const long long* __restrict__ off,
+                                                          const int* __restrict__ flags, int n,
+                                                          const float* __restrict__ scale, long long total) {
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
+    const int s = find_seg(off, n, i);
+    if (!(flags[s] & 1)) continue;
+    const float c = scale[s];
+    float4 v = *reinterpret_cast<float4*>(g + i);
+    v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+    *reinterpret_cast<float4*>(g + i) = v;
+  }
+}
+
+// hyper: lr, beta1, beta2, eps, wd, 1 - beta1^t, 1 - beta2^t
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, const long long* __restrict__ off,
+                                                    const int* __restrict__ flags, int n, const float* __restrict__ hyper,
+                                                    long long total) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6];
+  const float step = lr / bc1, rs2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
+    const int s = find_seg(off, n, i);
+    if (!(flags[s] & 1)) continue;   // grad is None: skipped entirely, also by weight decay
+    float4 pp = *reinterpret_cast<float4*>(p + i);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i);
+    float4 mm = *reinterpret_cast<float4*>(m + i);
+    float4 vv = *reinterpret_cast<float4*>(v + i);
+#define ADAM1(P, G, M, V)                              \
+  P *= decay;                                          \
+  M = b1 * M + (1.f - b1) * G;                         \
+  V = b2 * V + (1.f - b2) * G * G;                     \
+  P -= step * M / (sqrtf(V) * rs2 + eps);
+    ADAM1(pp.x, gg.x, mm.x, vv.x)
+    ADAM1(pp.y, gg.y, mm.y, vv.y)
+    ADAM1(pp.z, gg.z, mm.z, vv.z)
+    ADAM1(pp.w, gg.w, mm.w, vv.w)
+#undef ADAM1
+    *reinterpret_cast<float4*>(p + i) = pp;
+    *reinterpret_cast<float4*>(m + i) = mm;
+    *reinterpret_cast<float4*>(v + i) = vv;
+  }
+}
+
+}  // namespace
+
+extern "C" int qavit_clip_grads(float* grads, const long long* seg_off, const int* seg_flags, int n_seg, float per_param_max,
+                                float max_norm, float* norms, long long total, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_seg <= 0) return 0;
+  seg_norm_kernel<<<n_seg, 256, 0, s>>>(grads, seg_off, seg_flags, norms);
+  QV_LAUNCH_CHECK();
+  clip_coef_kernel<<<1, 1024, 0, s>>>(seg_flags, n_seg, per_param_max, max_norm, norms);
+  QV_LAUNCH_CHECK();
+  const int grid = (int)max(1LL, min((long long)qv_num_sms() * 8, (total / 4 + 255) / 256));
+  scale_grads_kernel<<<grid, 256, 0, s>>>(grads, seg_off, seg_flags, n_seg, norms, total);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qavit_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const long long* seg_off,
+                                const int* seg_flags, int n_seg, const float* hyper, long long total, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_seg <= 0) return 0;
+  const int grid = (int)max(1LL, min((long long)qv_num_sms() * 8, (total / 4 + 255) / 256));
+  adamw_kernel<<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, seg_off, seg_flags, n_seg, hyper, total);
+  QV_LAUNCH_CHECK();
+  return 0;
+}

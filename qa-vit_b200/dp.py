@@ -1,0 +1,106 @@
+"""Data-parallel gradient all-reduce (new functionality: the reference is single-GPU).
+
+One process per GPU; gradients live in FusedAdamW's flat fp32 buffer, cut into a few contiguous buckets in
+*reverse registration order* (head / stage4 first ... patch_embed / cnn_stem last, the order autograd produces them).
+Each bucket is all-reduced (mean) on a side stream as soon as autograd has accumulated its last gradient
+(post-accumulate-grad hooks), overlapping the remaining backward.  The only collective on the path.
+The GlobalTokenBank state (global_k / global_v are parameters mutated inside forward) is averaged with the last
+bucket so replicas do not drift (SURVEY.md hard part 2, option b)."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradAllReducer:
+    def __init__(self, opt, n_buckets: int = 4, bank_params: Optional[List[torch.nn.Parameter]] = None, group=None):
+        self.opt, self.group = opt, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        params = opt.param_groups[0]["params"]
+        offs = opt.seg_off.tolist()
+        total = offs[-1]
+        # bucket boundaries on parameter boundaries, roughly equal bytes, indexed from the END of the buffer
+        target = total / n_buckets
+        bounds, acc = [len(params)], 0
+        for i in range(len(params) - 1, -1, -1):
+            acc += offs[i + 1] - offs[i]
+            if acc >= target and i > 0 and len(bounds) < n_buckets:
+                bounds.append(i)
+                acc = 0
+        bounds.append(0)
+        self.buckets = []                      # (first_param, last_param_exclusive, flat slice)
+        for hi, lo in zip(bounds[:-1], bounds[1:]):
+            if hi > lo:
+                self.buckets.append((lo, hi, opt.flat_g[offs[lo]:offs[hi]]))
+        self.bank_params = bank_params or []
+        self._bank_flat = None
+        self._pending = [0] * len(self.buckets)
+        self._param_bucket = {}
+        for bi, (lo, hi, _) in enumerate(self.buckets):
+            for i in range(lo, hi):
+                self._param_bucket[i] = bi
+        self._stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self._handles = []
+        self._hooks = []
+        if self.world > 1:
+            for i, p in enumerate(params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+        self.reset()
+
+    def reset(self):
+        """Call before every backward: every bucket waits for all of its parameters that will get a gradient."""
+        flags = self.opt._flags_host if self.opt._have_flags else None
+        for bi, (lo, hi, _) in enumerate(self.buckets):
+            self._pending[bi] = sum(1 for i in range(lo, hi) if flags is None or int(flags[i]) & 1)
+        self._handles = []
+
+    def _make_hook(self, i):
+        def hook(_p):
+            bi = self._param_bucket[i]
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    def _launch(self, bi):
+        buf = self.buckets[bi][2]
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                buf.div_(self.world)
+                self._handles.append(dist.all_reduce(buf, group=self.group, async_op=True))
+        else:
+            buf.div_(self.world)
+            self._handles.append(dist.all_reduce(buf, group=self.group, async_op=True))
+
+    def finish(self):
+        """After backward: flush buckets whose hooks did not all fire, average the bank state, join the side stream."""
+        if self.world == 1:
+            return
+        for bi in range(len(self.buckets)):
+            if self._pending[bi] > 0:
+                self._pending[bi] = 0
+                self._launch(bi)
+        if self.bank_params:
+            flat = torch.cat([p.data.reshape(-1) for p in self.bank_params])
+            if self._stream is not None:
+                self._stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._stream):
+                    flat.div_(self.world)
+                    self._handles.append(dist.all_reduce(flat, group=self.group, async_op=True))
+            else:
+                flat.div_(self.world)
+                self._handles.append(dist.all_reduce(flat, group=self.group, async_op=True))
+            self._bank_flat = flat
+        for h in self._handles:
+            h.wait()
+        if self._stream is not None:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        if self.bank_params and self._bank_flat is not None:
+            o = 0
+            for p in self.bank_params:
+                p.data.copy_(self._bank_flat[o:o + p.numel()].view(p.shape))
+                o += p.numel()
+        self._handles = []

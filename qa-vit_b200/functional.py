@@ -1,0 +1,214 @@
+"""torch.autograd.Functions over the C ABI: each one stands in for the autograd graph of one reference module.
+
+All tensors stay on the device; the C side runs on torch's current stream, allocates nothing and never
+synchronises, so the Functions are safe under autocast and CUDA-graph capture."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import BlockCfg, QP_COUNT, check, lib
+
+_scratch = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _scratch_buf(device, nbytes: int) -> torch.Tensor:
+    """One reusable scratch allocation per device (temporaries of a block call; stream-ordered reuse)."""
+    buf = _scratch.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=device)
+        _scratch[device] = buf
+    return buf
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"qavit_b200: {what} must be a CUDA tensor -- there is no CPU path in this package")
+
+
+def resolve_dtype(precision: str) -> int:
+    """'fp32' | 'bf16' | 'auto' (bf16 under torch.autocast(bfloat16), like the reference train loop H:1402)."""
+    if precision == "auto":
+        return 1 if (torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16) else 0
+    return {"fp32": 0, "bf16": 1}[precision]
+
+
+class BlockMeta:
+    """Static description of one block call: the cfg struct and which tensor sits at which QP_* index."""
+
+    def __init__(self, cfg: BlockCfg, index: Sequence[int], no_grad_idx: Sequence[int], update_count: Optional[torch.Tensor]):
+        self.cfg = cfg
+        self.index = list(index)               # QP index of the i-th tensor argument
+        self.no_grad = set(no_grad_idx)        # QP indices that never receive a gradient (write_*, branch .norm)
+        self.update_count = update_count
+
+
+class QuadBlockFn(torch.autograd.Function):
+    """QuadAttentionBlock.forward (+ TokenLearner / TokenUpMix wrapper) -- HQAViT_CIFAR100.py:1071-1123."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, meta: BlockMeta, *tensors: torch.Tensor):
+        _require_cuda(x, "block input")
+        x = x.detach().float().contiguous()
+        cfg = meta.cfg
+        saved_b, scratch_b = C.c_size_t(0), C.c_size_t(0)
+        check(lib.qavit_block_workspace(C.byref(cfg), C.byref(saved_b), C.byref(scratch_b)))
+        saved = torch.empty(saved_b.value, dtype=torch.uint8, device=x.device)
+        scratch = _scratch_buf(x.device, scratch_b.value)
+        params = (C.c_void_p * QP_COUNT)()
+        for qi, t in zip(meta.index, tensors):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("qavit_b200: parameters must be contiguous fp32 tensors")
+            params[qi] = t.data_ptr()
+        out = torch.empty_like(x)
+        check(lib.qavit_block_forward(C.byref(cfg), params, _ptr(meta.update_count), x.data_ptr(), out.data_ptr(),
+                                      saved.data_ptr(), scratch.data_ptr(), _stream()))
+        ctx.meta, ctx.saved_buf, ctx.x, ctx.params_arr = meta, saved, x, params
+        ctx.tensors = tensors
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        meta, x = ctx.meta, ctx.x
+        cfg = meta.cfg
+        dout = dout.float().contiguous()
+        sizes: List[int] = []
+        for qi, t in zip(meta.index, ctx.tensors):
+            sizes.append(0 if qi in meta.no_grad else (t.numel() + 3) // 4 * 4)
+        gbuf = torch.zeros(sum(sizes), dtype=torch.float32, device=x.device)
+        grads_arr = (C.c_void_p * QP_COUNT)()
+        views: List[Optional[torch.Tensor]] = []
+        off = 0
+        for (qi, t), n in zip(zip(meta.index, ctx.tensors), sizes):
+            if n == 0:
+                views.append(None)
+                continue
+            v = gbuf[off:off + t.numel()].view(t.shape)
+            grads_arr[qi] = v.data_ptr()
+            views.append(v)
+            off += n
+        saved_b, scratch_b = C.c_size_t(0), C.c_size_t(0)
+        check(lib.qavit_block_workspace(C.byref(cfg), C.byref(saved_b), C.byref(scratch_b)))
+        scratch = _scratch_buf(x.device, scratch_b.value)
+        dx = torch.empty_like(x)
+        check(lib.qavit_block_backward(C.byref(cfg), ctx.params_arr, grads_arr, x.data_ptr(), dout.data_ptr(), dx.data_ptr(),
+                                       ctx.saved_buf.data_ptr(), scratch.data_ptr(), _stream()))
+        ctx.saved_buf = None
+        return (dx, None, *views)
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """PatchEmbed.forward (+ pos_embed) -- HQAViT_CIFAR100.py:1136-1138, 1250."""
+
+    @staticmethod
+    def forward(ctx, img, W, bias, ln_w, ln_b, pos):
+        _require_cuda(img, "image batch")
+        img = img.detach().float().contiguous()
+        B, Cin, S, _ = img.shape
+        d, _, p, _ = W.shape
+        N = (S // p) ** 2
+        pre = torch.empty(B * N, d, dtype=torch.float32, device=img.device)
+        stats = torch.empty(B * N, 2, dtype=torch.float32, device=img.device)
+        out = torch.empty(B, N, d, dtype=torch.float32, device=img.device)
+        check(lib.qavit_patch_embed_forward(img.data_ptr(), B, Cin, S, p, d, W.data_ptr(), bias.data_ptr(), ln_w.data_ptr(),
+                                            ln_b.data_ptr(), _ptr(pos), pre.data_ptr(), stats.data_ptr(), out.data_ptr(),
+                                            _stream()))
+        ctx.save_for_backward(img, W, ln_w, pre, stats)
+        ctx.has_pos = pos is not None
+        ctx.pos_shape = None if pos is None else pos.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        img, W, ln_w, pre, stats = ctx.saved_tensors
+        B, Cin, S, _ = img.shape
+        d, _, p, _ = W.shape
+        dout = dout.float().contiguous()
+        dev = img.device
+        dW = torch.zeros_like(W)
+        db = torch.zeros(d, dtype=torch.float32, device=dev)
+        dg = torch.zeros(d, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
+        dpos = torch.zeros(ctx.pos_shape, dtype=torch.float32, device=dev) if ctx.has_pos else None
+        dpre = torch.empty_like(pre)
+        check(lib.qavit_patch_embed_backward(img.data_ptr(), dout.data_ptr(), B, Cin, S, p, d, pre.data_ptr(), stats.data_ptr(),
+                                             ln_w.data_ptr(), dpre.data_ptr(), dW.data_ptr(), db.data_ptr(), dg.data_ptr(),
+                                             dbeta.data_ptr(), _ptr(dpos), _stream()))
+        return None, dW, db, dg, dbeta, dpos
+
+
+class HeadFn(torch.autograd.Function):
+    """norm -> mean over tokens -> head -- HQAViT_CIFAR100.py:1273-1275."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, W, bias):
+        _require_cuda(x, "head input")
+        x = x.detach().float().contiguous()
+        B, N, d = x.shape
+        ncls = W.shape[0]
+        stats = torch.empty(B * N, 2, dtype=torch.float32, device=x.device)
+        pooled = torch.empty(B, d, dtype=torch.float32, device=x.device)
+        logits = torch.empty(B, ncls, dtype=torch.float32, device=x.device)
+        check(lib.qavit_head_forward(x.data_ptr(), B, N, d, ln_w.data_ptr(), ln_b.data_ptr(), W.data_ptr(), bias.data_ptr(), ncls,
+                                     stats.data_ptr(), pooled.data_ptr(), logits.data_ptr(), _stream()))
+        ctx.save_for_backward(x, ln_w, W, stats, pooled)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, ln_w, W, stats, pooled = ctx.saved_tensors
+        B, N, d = x.shape
+        ncls = W.shape[0]
+        dlogits = dlogits.float().contiguous()
+        dev = x.device
+        dx = torch.empty_like(x)
+        dg = torch.zeros(d, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
+        dW = torch.zeros_like(W)
+        db = torch.zeros(ncls, dtype=torch.float32, device=dev)
+        dpooled = torch.empty_like(pooled)
+        check(lib.qavit_head_backward(x.data_ptr(), dlogits.data_ptr(), B, N, d, ln_w.data_ptr(), stats.data_ptr(), pooled.data_ptr(),
+                                      W.data_ptr(), ncls, dpooled.data_ptr(), dx.data_ptr(), dg.data_ptr(), dbeta.data_ptr(),
+                                      dW.data_ptr(), db.data_ptr(), _stream()))
+        return dx, dg, dbeta, dW, db
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """CrossEntropyLoss(label_smoothing) and its two-target mixup form -- HQAViT_CIFAR100.py:1373, 1404-1408."""
+
+    @staticmethod
+    def forward(ctx, logits, ya, yb, lam, smoothing):
+        _require_cuda(logits, "logits")
+        logits = logits.detach().float().contiguous()
+        B, ncls = logits.shape
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        check(lib.qavit_cross_entropy(logits.data_ptr(), ya.data_ptr(), _ptr(yb), float(lam), B, ncls, float(smoothing),
+                                      loss.data_ptr(), dlogits.data_ptr(), _stream()))
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * dloss, None, None, None, None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, label_smoothing: float = 0.0,
+                  target_b: Optional[torch.Tensor] = None, lam: float = 1.0) -> torch.Tensor:
+    """Drop-in for ``nn.CrossEntropyLoss(label_smoothing=...)(logits, target)``; with ``target_b`` the
+    ``lam * CE(a) + (1 - lam) * CE(b)`` mixup form of the reference's train loop."""
+    ya = target.to(torch.int64).contiguous()
+    yb = None if target_b is None else target_b.to(torch.int64).contiguous()
+    return CrossEntropyFn.apply(logits, ya, yb, lam, label_smoothing)

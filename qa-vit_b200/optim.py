@@ -1,0 +1,128 @@
+"""Gradient clipping + AdamW on flat fp32 buffers (reference: HQAViT_CIFAR100.py:1413-1439, 1566-1586).
+
+``FusedAdamW`` re-homes every parameter (and its gradient) as a view into one flat fp32 buffer -- each tensor
+starting on a 4-float boundary -- so the per-parameter / global clip is 3 launches and the AdamW step is 1,
+instead of torch's ~10 multi-tensor launches plus ~60 single-tensor norms with host syncs.  lr and beta1 are
+per-step device scalars (OneCycleLR rewrites both every iteration): ``param_groups[0]['lr']`` /
+``['betas']`` are read at each step, so torch LR schedulers drive it unchanged."""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=1e-2, max_grad_norm: Optional[float] = None, per_param_clip: float = 0.1,
+                 per_param_clip_names: Sequence[str] = ("cnn_stem", "dwconv")):
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        if not named:
+            raise ValueError("no parameters")
+        self.names = [n for n, _ in named]
+        params = [p for _, p in named]
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdamW needs CUDA parameters (no CPU path)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.max_grad_norm, self.per_param_clip = max_grad_norm, per_param_clip
+        offs, off = [], 0
+        for p in params:
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        offs.append(off)
+        self.total = off
+        self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self._pviews: List[torch.Tensor] = []
+        self._gviews: List[torch.Tensor] = []
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                v = self.flat_p[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v                                  # parameter now lives in the flat buffer
+                g = self.flat_g[o:o + p.numel()].view(p.shape)
+                self._pviews.append(v)
+                self._gviews.append(g)
+        self.seg_off = torch.tensor(offs, dtype=torch.int64, device=dev)
+        clip_bit = [2 if any(s in n for s in per_param_clip_names) else 0 for n in self.names]
+        self._clip_bits = clip_bit
+        self.seg_flags = torch.zeros(len(params), dtype=torch.int32, device=dev)
+        self._flags_host = torch.zeros(len(params), dtype=torch.int32).pin_memory()
+        self.norms = torch.zeros(len(params) + 2, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        self._have_flags = False
+
+    def attach_grads(self):
+        """Point every .grad at its slice of the flat gradient buffer (zeroed): autograd then accumulates in place
+        and the DP all-reduce / clip / AdamW kernels see one contiguous tensor."""
+        self.flat_g.zero_()
+        for p, g in zip(self.param_groups[0]["params"], self._gviews):
+            p.grad = g
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.attach_grads()
+
+    def _sync_flags(self, grads_present: Optional[Sequence[bool]] = None):
+        params = self.param_groups[0]["params"]
+        for i, p in enumerate(params):
+            has = (p.grad is not None) if grads_present is None else grads_present[i]
+            self._flags_host[i] = (1 if has else 0) | self._clip_bits[i]
+        self.seg_flags.copy_(self._flags_host, non_blocking=True)
+        self._have_flags = True
+
+    def set_grad_mask(self, has_grad: Sequence[bool]):
+        """With attach_grads() every .grad is non-None; the set of parameters the reference leaves at grad=None
+        (bank write_* and branch .norm) must then be declared so AdamW skips them as torch does."""
+        self._sync_flags(list(has_grad))
+
+    @torch.no_grad()
+    def clip(self) -> torch.Tensor:
+        """Per-parameter clip (names containing cnn_stem / dwconv, to 0.1) then global clip to max_grad_norm.
+        Returns the device scalar of the global norm (what clip_grad_norm_ returns); no host sync."""
+        self._gather_foreign_grads()
+        if not self._have_flags:
+            self._sync_flags()
+        check(lib.qavit_clip_grads(self.flat_g.data_ptr(), self.seg_off.data_ptr(), self.seg_flags.data_ptr(), len(self.names),
+                                   float(self.per_param_clip), float(self.max_grad_norm if self.max_grad_norm else 3.0e38),
+                                   self.norms.data_ptr(), self.total, _stream()))
+        return self.norms[len(self.names)]
+
+    def _gather_foreign_grads(self):
+        """Gradients produced as fresh tensors (attach_grads() not used) are copied into the flat buffer."""
+        for p, g in zip(self.param_groups[0]["params"], self._gviews):
+            if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
+                g.copy_(p.grad)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        grp = self.param_groups[0]
+        self._gather_foreign_grads()
+        if not self._have_flags:
+            self._sync_flags()
+        self.step_count += 1
+        b1, b2 = grp["betas"]
+        t = self.step_count
+        h = self._hyper_host
+        h[0], h[1], h[2], h[3], h[4] = grp["lr"], b1, b2, grp["eps"], grp["weight_decay"]
+        h[5], h[6] = 1.0 - b1 ** t, 1.0 - b2 ** t
+        self.hyper.copy_(h, non_blocking=True)
+        check(lib.qavit_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                   self.seg_off.data_ptr(), self.seg_flags.data_ptr(), len(self.names), self.hyper.data_ptr(),
+                                   self.total, _stream()))
+        return None
+
+
+def clip_grad_norms_(opt: FusedAdamW) -> torch.Tensor:
+    return opt.clip()
