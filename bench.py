@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: HQAViT CIFAR-100-shape training (bf16) images/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One "step" = forward + backward + per-parameter/global clip + AdamW (+ the bucketed gradient all-reduce when N > 1)
+over one synthetic batch of `--batch` images per GPU (weak scaling).  Prints ONE JSON line (rank 0).
+
+  value      whole-job images/sec, batch already resident in HBM, CUDA-event timed, max over ranks
+  e2e        same step through the public API with the batch coming from pinned host memory every step
+             (H2D inside the timed region) and the loss read back to the host every step
+  roofline   the dominant kernel (tcgen05 projection GEMM, qkv shape) timed alone with CUDA events
+  cpu_baseline  the CPU oracle port of the reference step on the host cores, on a bounded sample
+  --impl reference   times that CPU path alone (the reference's own implementation of the step is CPU/eager
+             PyTorch; /root/reference does not exist on the GPU box, the oracle is its pinned restatement)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train images/sec (HQAViT CIFAR-100 shape, fwd+bwd+clip+AdamW)"
+WORKLOAD = "HQAViT CIFAR-100 32x32 training step, bf16, synthetic batch"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_rate(sample_b, steps, warmup, threads=None):
+    """The reference training step (CPU restatement, fp32, AdamW + clips) on `sample_b` images; images/sec."""
+    from oracle import qavit_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    ocfg = O.OracleConfig(family="hqavit")
+    sd = O.synthetic_state(ocfg)
+    keys = O.trainable_keys(ocfg)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(sample_b, 3, 32, 32, generator=g)
+    y = torch.randint(0, 100, (sample_b,), generator=g)
+    state = {}
+    ts = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, grads, new_state = O.loss_and_grads(sd, ocfg, x, y, label_smoothing=0.12)
+        sd.update(new_state)
+        O.clip_grads_(grads)
+        O.adamw_step_({k: sd[k] for k in keys}, grads, state, lr=6e-4, beta1=0.95, wd=0.06)
+        if it >= warmup:
+            ts.append(time.perf_counter() - t0)
+    dt = sum(ts) / len(ts)
+    return sample_b / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 64
+    rate, dt, cores = cpu_step_rate(sample, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": max(1, min(args.steps, 8)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "note": "CPU path of the reference step (oracle port, "
+                   "pinned to the live reference's golden vectors); each step = a bounded sample of the workload"},
+        "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+                         "sample": f"{sample} images/step (of per-GPU batch {args.batch}), fp32, fwd+bwd+clip+AdamW"},
+        "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def gemm_roofline(device):
+    """Dominant kernel: tc_gemm_nt at the SWA qkv shape ([B*16, 192] x [576, 192]^T), timed alone."""
+    import math
+    from qavit_b200 import _lib as L
+    M, N, K = 65536, 576, 192
+    A = torch.randn(M, K, device=device).bfloat16()
+    W = torch.randn(N, K, device=device) / math.sqrt(K)
+    Wb = W.bfloat16()
+    bias = torch.zeros(N, device=device)
+    C = torch.empty(M, N, device=device, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    s = torch.cuda.current_stream().cuda_stream
+    ts = []
+    for i in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib.qavit_test_gemm_nt(1, A.data_ptr(), K, M, N, K, W.data_ptr(), Wb.data_ptr(), bias.data_ptr(), C.data_ptr(), 0, s))
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+    t = sum(ts) / len(ts)
+    bytes_alg = M * K * 2 + N * K * 2 + M * N * 2
+    flops = 2.0 * M * N * K
+    return t, bytes_alg, flops
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import qavit_b200 as Q
+    from qavit_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(42)
+    cfg = Q.HQAViTConfig(dropout=0.0, drop_path=0.0)
+    model = Q.HQAViT(cfg)
+    for n in ("fuse2", "fuse3", "fuse4"):
+        getattr(model, n).cat_mlp[3].p = 0.0
+    model = model.to(dev).train().set_precision("bf16")
+    if world > 1:       # identical replicas
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    names = [n for n, _ in model.named_parameters()]
+    opt = Q.FusedAdamW(model.named_parameters(), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06, max_grad_norm=0.5)
+    nograd = ("swa.norm.", "msda.norm.", "cga.norm.", "write_norm.", "write_compression.", "write_gate.")
+    opt.set_grad_mask([not any(s in n for s in nograd) for n in names])
+    reducer = Q.GradAllReducer(opt, n_buckets=4, bank_params=[model.global_bank.global_k, model.global_bank.global_v]) if world > 1 else None
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
+    y_host = torch.randint(0, 100, (B,), generator=g).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def step(x, y):
+        opt.zero_grad()
+        if reducer:
+            reducer.reset()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = model(x)
+        loss = Q.cross_entropy(logits, y, label_smoothing=0.12)
+        loss.backward()
+        if reducer:
+            reducer.finish()
+        opt.clip()
+        opt.step()
+        return loss
+
+    def timed(nsteps, from_host):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(nsteps):
+            if from_host:
+                xb = x_host.to(dev, non_blocking=True)
+                yb = y_host.to(dev, non_blocking=True)
+                last = step(xb, yb).item()          # D2H read of the step's result
+            else:
+                last = step(x_dev, y_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, last
+
+    for _ in range(max(3, args.warmup)):
+        step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.lib.qavit_launch_count()
+    ms, loss = timed(args.steps, from_host=False)
+    launches = (L.lib.qavit_launch_count() - launches0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, loss_e2e = timed(args.steps, from_host=True)
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        hbm, tf_burst, tf_sus, src = peaks()
+        t_g, bytes_g, flops_g = gemm_roofline(dev)
+        roof = {"kernel": "tc_gemm_nt_kernel (SWA qkv projection, M=65536 N=576 K=192, timed alone, L2 flushed)",
+                "bound": "hbm", "achieved": bytes_g / t_g / 1e9, "peak": hbm, "unit": "GB/s", "frac": bytes_g / t_g / 1e9 / hbm,
+                "traffic": None, "peak_source": src, "tensor_tflops": flops_g / t_g / 1e12,
+                "tensor_frac_of_burst": flops_g / t_g / 1e12 / tf_burst}
+        # whole-step tensor utilisation against the sustained peak, F_min_train = 3 x (185.4 + 1.2 + 199.7) MFLOP / image
+        f_train = 3 * (185.4 + 1.22 + 199.7) * 1e6
+        roof["step_tflops_fmin"] = value / world * f_train / 1e12
+        roof["step_frac_of_sustained_peak"] = roof["step_tflops_fmin"] / tf_sus
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, dt, cores = cpu_step_rate(64, 4, 1)
+            cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+                   "sample": f"64 images/step x 4 steps ({4 * dt:.1f} s), fp32 oracle port, fwd+bwd+clip+AdamW"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "dropout": 0.0, "drop_path": 0.0, "label_smoothing": 0.12, "optimizer": "AdamW+clip(0.1 per-param, 0.5 global)",
+                       "l2": "working set (saved activations ~1.4 MB/image) >> 126 MB L2; no explicit flush",
+                       "lateral_cnn_path": "torch/cuDNN under autocast (scope row f-1)"},
+            "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "final_loss": float(loss.item() if hasattr(loss, "item") else loss),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

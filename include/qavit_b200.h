@@ -67,6 +67,8 @@ typedef struct qavit_block_cfg {
 
 const char* qavit_last_error(void);
 int qavit_abi_version(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py reports the per-step delta) */
+long long qavit_launch_count(void);
 /* state_dict suffix of parameter `index` (NULL when out of range); *scope: 0 = quad block, 1 = wrapper, 2 = bank */
 const char* qavit_block_param_name(int index, int* scope);
 

@@ -39,6 +39,7 @@ _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 _SIGS = {
     "qavit_last_error": (C.c_char_p, []),
     "qavit_abi_version": (_i, []),
+    "qavit_launch_count": (_ll, []),
     "qavit_block_param_name": (C.c_char_p, [_i, C.POINTER(_i)]),
     "qavit_block_workspace": (_i, [C.POINTER(BlockCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "qavit_block_forward": (_i, [C.POINTER(BlockCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),

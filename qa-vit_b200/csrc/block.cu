@@ -16,6 +16,8 @@ void qv_set_error(const char* fmt, ...) {
 }
 extern "C" const char* qavit_last_error(void) { return g_err; }
 extern "C" int qavit_abi_version(void) { return QAVIT_ABI_VERSION; }
+unsigned long long g_qv_launches = 0;
+extern "C" long long qavit_launch_count(void) { return (long long)g_qv_launches; }
 
 // ------------------------------------------------------------------------------------------------ names
 namespace {

@@ -24,7 +24,12 @@ void qv_set_error(const char* fmt, ...);
       return 1;                                                                             \
     }                                                                                       \
   } while (0)
-#define QV_LAUNCH_CHECK() QV_CUDA(cudaPeekAtLastError())
+extern unsigned long long g_qv_launches;   // kernels launched by this library (bench.py's gpu_launches)
+#define QV_LAUNCH_CHECK()            \
+  do {                               \
+    ++g_qv_launches;                 \
+    QV_CUDA(cudaPeekAtLastError());  \
+  } while (0)
 #define QV_TRY(expr)          \
   do {                        \
     int _s = (expr);          \

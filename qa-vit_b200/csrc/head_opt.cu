@@ -5,8 +5,9 @@
 // =============================================================================== patch embed (H:1129-1138, :1250)
 namespace {
 constexpr int PE_KC = 48;  // contraction chunk staged in shared memory
-// One CTA per image.  stride == kernel, so patch row (py, px) is the [Cin, p, p] box at (py*p, px*p): read straight
-// from the image, no im2col buffer.  pre = conv (saved for backward), out = LN(pre) + pos.
+// One CTA per (image, chunk of <= 64 patches).  stride == kernel, so patch row (py, px) is the [Cin, p, p] box at
+// (py*p, px*p): read straight from the image, no im2col buffer.  pre = conv (saved for backward), out = LN(pre) + pos.
+constexpr int PE_NC = 64;
 __global__ void __launch_bounds__(192) patch_embed_fwd_kernel(const float* __restrict__ img, int B, int Cin, int S, int p,
                                                               int d, const float* __restrict__ W,
                                                               const float* __restrict__ bias,
@@ -16,24 +17,26 @@ __global__ void __launch_bounds__(192) patch_embed_fwd_kernel(const float* __res
                                                               float* __restrict__ stats, float* __restrict__ out) {
   extern __shared__ float sm[];
   const int n_side = S / p, N = n_side * n_side, K = Cin * p * p;
-  float* sP = sm;                      // [N][PE_KC]      patch chunk
-  float* sW = sP + N * PE_KC;          // [d][PE_KC + 1]  weight chunk
-  float* sO = sW + d * (PE_KC + 1);    // [N][d]          conv output
+  const int chunks = (N + PE_NC - 1) / PE_NC;
+  float* sP = sm;                      // [PE_NC][PE_KC]  patch chunk
+  float* sW = sP + PE_NC * PE_KC;      // [d][PE_KC + 1]  weight chunk
+  float* sO = sW + d * (PE_KC + 1);    // [PE_NC][d]      conv output
   const int tid = threadIdx.x;
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
-    for (int idx = tid; idx < N * d; idx += blockDim.x) sO[idx] = bias[idx % d];
+  for (int task = blockIdx.x; task < B * chunks; task += gridDim.x) {
+    const int b = task / chunks, n0 = (task % chunks) * PE_NC, nn = min(PE_NC, N - n0);
+    for (int idx = tid; idx < nn * d; idx += blockDim.x) sO[idx] = bias[idx % d];
     for (int k0 = 0; k0 < K; k0 += PE_KC) {
       const int kc = min(PE_KC, K - k0);
       __syncthreads();
-      for (int idx = tid; idx < N * kc; idx += blockDim.x) {
-        const int n = idx / kc, k = k0 + idx % kc;
+      for (int idx = tid; idx < nn * kc; idx += blockDim.x) {
+        const int n = n0 + idx / kc, k = k0 + idx % kc;
         const int c = k / (p * p), r = (k / p) % p, q = k % p;
-        sP[n * PE_KC + idx % kc] = img[(((long)b * Cin + c) * S + (n / n_side) * p + r) * S + (n % n_side) * p + q];
+        sP[(idx / kc) * PE_KC + idx % kc] = img[(((long)b * Cin + c) * S + (n / n_side) * p + r) * S + (n % n_side) * p + q];
       }
       for (int idx = tid; idx < d * kc; idx += blockDim.x) sW[(idx / kc) * (PE_KC + 1) + idx % kc] = W[(long)(idx / kc) * K + k0 + idx % kc];
       __syncthreads();
       for (int o = tid; o < d; o += blockDim.x) {
-        for (int n = 0; n < N; ++n) {
+        for (int n = 0; n < nn; ++n) {
           float a = sO[n * d + o];
           for (int k = 0; k < kc; ++k) a = fmaf(sP[n * PE_KC + k], sW[o * (PE_KC + 1) + k], a);
           sO[n * d + o] = a;
@@ -42,19 +45,19 @@ __global__ void __launch_bounds__(192) patch_embed_fwd_kernel(const float* __res
     }
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    for (int n = warp; n < N; n += nwarp) {
+    for (int n = warp; n < nn; n += nwarp) {
       float s = 0.f;
       for (int c = lane; c < d; c += 32) s += sO[n * d + c];
       const float mean = warp_sum(s) / d;
       float q = 0.f;
       for (int c = lane; c < d; c += 32) { const float t = sO[n * d + c] - mean; q += t * t; }
       const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
-      const long row = (long)b * N + n;
+      const long row = (long)b * N + n0 + n;
       if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
       for (int c = lane; c < d; c += 32) {
         const float v = sO[n * d + c];
         pre[row * d + c] = v;
-        out[row * d + c] = (v - mean) * rstd * gamma[c] + beta[c] + (pos ? pos[n * d + c] : 0.f);
+        out[row * d + c] = (v - mean) * rstd * gamma[c] + beta[c] + (pos ? pos[(n0 + n) * d + c] : 0.f);
       }
     }
     __syncthreads();
@@ -64,25 +67,27 @@ __global__ void __launch_bounds__(192) patch_embed_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(192) patch_embed_dw_kernel(const float* __restrict__ img, const float* __restrict__ dpre,
                                                              int B, int Cin, int S, int p, int d,
                                                              float* __restrict__ dW) {
-  extern __shared__ float sP[];  // [N][PE_KC]
+  extern __shared__ float sP[];  // [PE_NC][PE_KC]
   const int n_side = S / p, N = n_side * n_side, K = Cin * p * p;
+  const int chunks = (N + PE_NC - 1) / PE_NC;
   const int tid = threadIdx.x;
   for (int k0 = 0; k0 < K; k0 += PE_KC) {
     const int kc = min(PE_KC, K - k0);
     float acc[PE_KC];
 #pragma unroll
     for (int k = 0; k < PE_KC; ++k) acc[k] = 0.f;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int task = blockIdx.x; task < B * chunks; task += gridDim.x) {
+      const int b = task / chunks, n0 = (task % chunks) * PE_NC, nn = min(PE_NC, N - n0);
       __syncthreads();
-      for (int idx = tid; idx < N * kc; idx += blockDim.x) {
-        const int n = idx / kc, k = k0 + idx % kc;
+      for (int idx = tid; idx < nn * kc; idx += blockDim.x) {
+        const int n = n0 + idx / kc, k = k0 + idx % kc;
         const int c = k / (p * p), r = (k / p) % p, q = k % p;
-        sP[n * PE_KC + idx % kc] = img[(((long)b * Cin + c) * S + (n / n_side) * p + r) * S + (n % n_side) * p + q];
+        sP[(idx / kc) * PE_KC + idx % kc] = img[(((long)b * Cin + c) * S + (n / n_side) * p + r) * S + (n % n_side) * p + q];
       }
       __syncthreads();
       if (tid < d) {
-        for (int n = 0; n < N; ++n) {
-          const float g = dpre[((long)b * N + n) * d + tid];
+        for (int n = 0; n < nn; ++n) {
+          const float g = dpre[((long)b * N + n0 + n) * d + tid];
 #pragma unroll
           for (int k = 0; k < PE_KC; ++k) if (k < kc) acc[k] = fmaf(g, sP[n * PE_KC + k], acc[k]);
         }
@@ -101,10 +106,10 @@ int patch_embed_fwd(cudaStream_t s, const float* img, int B, int Cin, int S, int
                     float* out) {
   if (B <= 0) return 0;
   const int N = (S / p) * (S / p);
-  const size_t smem = (size_t)(N * PE_KC + d * (PE_KC + 1) + N * d) * sizeof(float);
-  QV_CHECK(smem <= 227 * 1024 && d <= 192 * 2, "patch_embed: %d tokens x %d dims needs %zu B smem: not supported", N, d, smem);
+  const size_t smem = (size_t)(PE_NC * PE_KC + d * (PE_KC + 1) + PE_NC * d) * sizeof(float);
+  QV_CHECK(smem <= 227 * 1024, "patch_embed: d=%d needs %zu B smem: not supported", d, smem);
   QV_CUDA(cudaFuncSetAttribute(patch_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  patch_embed_fwd_kernel<<<min(B, qv_num_sms() * 2), 192, smem, s>>>(img, B, Cin, S, p, d, W, bias, gamma, beta, pos, pre, stats, out);
+  patch_embed_fwd_kernel<<<min(B * cdiv(N, PE_NC), qv_num_sms() * 2), 192, smem, s>>>(img, B, Cin, S, p, d, W, bias, gamma, beta, pos, pre, stats, out);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -119,9 +124,8 @@ int patch_embed_bwd(cudaStream_t s, const float* img, const float* dout, int B, 
   if (dpos) QV_TRY(colsum_accum(s, QV_F32, dout, N * d, B, N * d, dpos, nullptr));
   QV_TRY(ln_bwd(s, QV_F32, pre, d, QV_F32, dout, d, B * N, d, gamma, stats, 0, QV_F32, nullptr, dpre, nullptr, dgamma, dbeta));
   QV_TRY(colsum_accum(s, QV_F32, dpre, d, B * N, d, dbias, nullptr));
-  const size_t smem = (size_t)N * PE_KC * sizeof(float);
-  QV_CUDA(cudaFuncSetAttribute(patch_embed_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  patch_embed_dw_kernel<<<min(B, qv_num_sms()), 192, smem, s>>>(img, dpre, B, Cin, S, p, d, dW);
+  const size_t smem = (size_t)PE_NC * PE_KC * sizeof(float);
+  patch_embed_dw_kernel<<<min(B * cdiv(N, PE_NC), qv_num_sms()), 192, smem, s>>>(img, dpre, B, Cin, S, p, d, dW);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -104,6 +104,7 @@ class FusedAdamW(torch.optim.Optimizer):
         for p, g in zip(self.param_groups[0]["params"], self._gviews):
             if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
                 g.copy_(p.grad)
+                p.grad = g
 
     @torch.no_grad()
     def step(self, closure=None):

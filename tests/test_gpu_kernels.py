@@ -1,0 +1,150 @@
+"""GPU unit tests of the GEMM flavours and the small standalone ops, through the C ABI (ctypes)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from qavit_b200 import _lib
+    return _lib
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 192, 192), (64, 576, 192), (1000, 48, 192), (130, 100, 192), (77, 192, 96)])
+def test_simt_gemm_nt_and_tn(M, N, K):
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    Cc = torch.empty(M, N, device="cuda")
+    L.check(L.lib.qavit_test_gemm_nt(0, A.data_ptr(), K, M, N, K, W.data_ptr(), None, b.data_ptr(), Cc.data_ptr(), 1, _s()))
+    ref = (A.double() @ W.double().t() + b.double()).float()
+    assert (Cc - ref).abs().max().item() < 1e-4
+    dY = torch.randn(M, N, device="cuda", generator=g)
+    dW = torch.zeros(N, K, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    L.check(L.lib.qavit_test_gemm_tn(0, dY.data_ptr(), N, A.data_ptr(), K, M, N, K, dW.data_ptr(), db.data_ptr(), _s()))
+    refW = (dY.double().t() @ A.double()).float()
+    assert (dW - refW).abs().max().item() < 1e-3 * refW.abs().max().item()
+    assert (db - dY.sum(0)).abs().max().item() < 1e-3 * dY.sum(0).abs().max().item()
+
+
+TC_NT = [(128, 192, 192), (4096, 192, 192), (1000, 576, 192), (333, 96, 192), (256, 192, 96), (64, 48, 192),
+         (512, 16, 192), (2048, 208, 192), (640, 192, 576), (300, 192, 48), (1024, 192, 16), (160, 384, 192)]
+
+
+@pytest.mark.parametrize("M,N,K", TC_NT)
+def test_tcgen05_gemm_nt(M, N, K):
+    """bf16 operands, fp32 accumulation: equal to an fp64 product of the same bf16-rounded operands to ~1e-5."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    Wb = W.bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    Cc = torch.full((M, N), float("nan"), device="cuda")
+    L.check(L.lib.qavit_test_gemm_nt(1, A.data_ptr(), K, M, N, K, W.data_ptr(), Wb.data_ptr(), b.data_ptr(), Cc.data_ptr(), 1, _s()))
+    torch.cuda.synchronize()
+    ref = (A.double() @ Wb.double().t() + b.double()).float()
+    err = (Cc - ref).abs().max().item()
+    assert err < 2e-4, f"max abs err {err} (ref max {ref.abs().max().item()})"
+
+
+TC_TN = [(4096, 192, 192), (1000, 576, 192), (333, 96, 192), (2048, 192, 96), (640, 48, 192), (512, 16, 192),
+         (64, 192, 192), (3000, 384, 192), (130, 192, 48)]
+
+
+@pytest.mark.parametrize("M,N,K", TC_TN)
+def test_tcgen05_gemm_tn(M, N, K):
+    """dW[N, K] += dY[M, N]^T X[M, K] with MN-major UMMA operands (no transposed copies)."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    dY = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    X = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    dW = torch.zeros(N, K, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    L.check(L.lib.qavit_test_gemm_tn(1, dY.data_ptr(), N, X.data_ptr(), K, M, N, K, dW.data_ptr(), db.data_ptr(), _s()))
+    torch.cuda.synchronize()
+    ref = (dY.double().t() @ X.double()).float()
+    err = (dW - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err} (ref max {ref.abs().max().item()})"
+    assert (db - dY.float().sum(0)).abs().max().item() < 1e-2
+
+
+def test_tcgen05_gemm_nt_strided_slice():
+    """A operand that is a 48-column slice of a 192-wide buffer (the compress dX GEMM): TMA must zero-fill beyond it."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K = 500, 192, 48
+    buf = torch.randn(M, 192, device="cuda", generator=g).bfloat16()
+    W = torch.randn(N, K, device="cuda", generator=g) / 7
+    Wb = W.bfloat16()
+    Cc = torch.empty(M, N, device="cuda")
+    A = buf[:, 48:96]
+    L.check(L.lib.qavit_test_gemm_nt(1, A.data_ptr(), 192, M, N, K, W.data_ptr(), Wb.data_ptr(), None, Cc.data_ptr(), 1, _s()))
+    ref = (A.double() @ Wb.double().t()).float()
+    assert (Cc - ref).abs().max().item() < 2e-4
+
+
+def test_cross_entropy_matches_torch():
+    import qavit_b200 as Q
+    g = torch.Generator(device="cuda").manual_seed(4)
+    logits = torch.randn(37, 100, device="cuda", generator=g, requires_grad=True)
+    ya = torch.randint(0, 100, (37,), device="cuda", generator=g)
+    yb = torch.randint(0, 100, (37,), device="cuda", generator=g)
+    loss = Q.cross_entropy(logits, ya, label_smoothing=0.12)
+    loss.backward()
+    l2 = logits.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(l2, ya, label_smoothing=0.12)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert (logits.grad - l2.grad).abs().max().item() < 1e-6
+    # mixup / cutmix two-target form, H:1407
+    loss2 = Q.cross_entropy(logits.detach(), ya, label_smoothing=0.12, target_b=yb, lam=0.3)
+    ce = torch.nn.CrossEntropyLoss(label_smoothing=0.12)
+    ref2 = 0.3 * ce(l2.detach(), ya) + 0.7 * ce(l2.detach(), yb)
+    assert abs(loss2.item() - ref2.item()) < 1e-5
+
+
+def test_clip_and_adamw_match_torch():
+    """H:1413-1439: per-parameter clip (dwconv / cnn_stem names), global clip, AdamW; params without grad are skipped."""
+    import qavit_b200 as Q
+    torch.manual_seed(5)
+    shapes = {"a.weight": (33, 7), "cnn_stem.x.weight": (64, 3), "b.dwconv.weight": (96, 9), "c.bias": (5,), "never.used": (11,)}
+    ours = {n: torch.nn.Parameter(torch.randn(s, device="cuda")) for n, s in shapes.items()}
+    ref = {n: torch.nn.Parameter(p.detach().clone()) for n, p in ours.items()}
+    opt = Q.FusedAdamW(list(ours.items()), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06, max_grad_norm=0.5)
+    ropt = torch.optim.AdamW(ref.values(), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06)
+    for step in range(3):
+        opt.zero_grad()
+        ropt.zero_grad(set_to_none=True)
+        gs = {n: torch.randn(s, device="cuda") * (3.0 if "dwconv" in n else 0.2) for n, s in shapes.items() if n != "never.used"}
+        for n, gval in gs.items():
+            ours[n].grad.copy_(gval)
+            ref[n].grad = gval.clone()
+        opt.set_grad_mask([n != "never.used" for n in shapes])
+        for n, p in ref.items():
+            if p.grad is not None and ("cnn_stem" in n or "dwconv" in n):
+                torch.nn.utils.clip_grad_norm_([p], 0.1)
+        rnorm = torch.nn.utils.clip_grad_norm_(ref.values(), 0.5)
+        norm = opt.clip()
+        assert abs(norm.item() - rnorm.item()) < 1e-5 * max(1.0, rnorm.item())
+        for n in gs:
+            assert (ours[n].grad - ref[n].grad).abs().max().item() < 1e-6, n
+        for g_ in opt.param_groups:
+            g_["lr"] = 6e-4 * (step + 1)
+            g_["betas"] = (0.95 - 0.01 * step, 0.999)
+        for g_ in ropt.param_groups:
+            g_["lr"] = 6e-4 * (step + 1)
+            g_["betas"] = (0.95 - 0.01 * step, 0.999)
+        opt.step()
+        ropt.step()
+        for n in shapes:
+            assert (ours[n].data - ref[n].data).abs().max().item() < 2e-6, (n, step)
