@@ -122,6 +122,14 @@ int qavit_adamw_step(float* params, const float* grads, float* exp_avg, float* e
                      const int* seg_flags, int n_seg, const float* hyper /* device: lr, beta1, beta2, eps, wd, bc1, bc2 */,
                      long long total_elems, void* stream);
 
+/* nn.LayerNorm (eps configurable, C <= 256) for the modules around the blocks -- SplitFusion / LMFAdapter / RRCV /
+ * ConvNeXtBlock norms (H:723, 816, 875, 922-939).  x fp32 or bf16 (x_bf16), y / dy fp32, dx in x's dtype,
+ * stats [rows, 2] kept for backward, dgamma / dbeta accumulated. */
+int qavit_layer_norm_forward(const void* x, int x_bf16, long long rows, int C, const float* w, const float* b, float eps,
+                             float* y, float* stats, void* stream);
+int qavit_layer_norm_backward(const void* x, int x_bf16, const float* dy, long long rows, int C, const float* w,
+                              const float* stats, void* dx, float* dgamma, float* dbeta, void* stream);
+
 /* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
 int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,
                        const float* bias, void* C, int c_f32, void* stream);

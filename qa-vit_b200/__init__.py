@@ -8,6 +8,7 @@ from .modules import (HQAViT, HQAViTConfig, PatchEmbed, QAViT, QAViTConfig, Quad
                       QuadBlockWithTokenLearner)
 from .optim import FusedAdamW, clip_grad_norms_  # noqa: F401
 from .dp import GradAllReducer  # noqa: F401
+from .graph import GraphedTrainStep  # noqa: F401
 
 __all__ = ["QAViT", "HQAViT", "QAViTConfig", "HQAViTConfig", "QuadAttentionBlock", "QuadBlockWithTokenLearner",
-           "PatchEmbed", "cross_entropy", "FusedAdamW", "clip_grad_norms_", "GradAllReducer"]
+           "PatchEmbed", "cross_entropy", "FusedAdamW", "clip_grad_norms_", "GradAllReducer", "GraphedTrainStep"]

@@ -4,61 +4,72 @@
 //   mode 1  MSDA  (H:496-532): K,V from the pooled dilated tokens (rows >= NM are the zero padding of
 //                 H:507-509 and are skipped), Linformer, bank concat, full-resolution Q
 //   mode 2  Cross (H:613-626): K,V = projected bank (batch invariant), no Linformer
-//   CGA           (H:559-595): 6 channel groups x 4 heads of head_dim 4, own tokens + projected bank keys;
-//                 the per-group q/k/v projections (32 -> 16) are fused in (they are 1.5 % of block FLOPs)
-// Every attention problem here fits one KV tile (Nkv <= 80), so softmax is a single pass in shared memory.
-// One CTA walks (window, head) tasks grid-stride; the batch reductions (dE_k, dE_v, d bank) accumulate in
-// shared memory across a CTA's tasks and are flushed once with atomics.
+// (CGA lives in cga.cu.)  Every attention problem here fits one KV tile (Nkv <= 80), so softmax is a single pass in
+// shared memory.  One CTA walks (window, head) tasks grid-stride; the batch reductions (dE_k, dE_v, d bank)
+// accumulate in shared memory across a CTA's tasks and are flushed once with atomics.
+// Thread mapping: warp = one query / key row, lanes = head-dim channels or keys; head_dim is a template constant
+// (48 in every shipped config) so all index arithmetic is multiply-shift and the inner products unroll.
 #include "kernels.h"
 
 namespace {
 
 constexpr int NT = 128;  // threads per CTA
+constexpr int NW = NT / 32;
 
 struct Lay {  // shared-memory carve-up (float offsets), computed on host and passed by value
   int HDP, NKV, SP, QC, nq, L;
-  int oEk, oEv, odEk, odEv, oKs, oVs, oKf, oVf, odKf, odVf, oQ, odO, oP, odS, odbk, odbv, total;
+  int oEk, oEv, odEk, odEv, oKs, oVs, oKf, oVf, odKf, odVf, oQ, odO, oP, odS, odbk, odbv, oRow, total;
 };
 
-__device__ __forceinline__ long q_row(const AttnP& p, int w, int i) {
+__device__ __forceinline__ int q_row(const AttnP& p, int w, int i) {
   if (p.mode == 0) {
     const int nws = p.side / p.ws, nW = nws * nws;
     const int b = w / nW, wi = w % nW;
     const int r = (wi / nws) * p.ws + i / p.ws, c = (wi % nws) * p.ws + i % p.ws;
-    return (long)b * p.Nt + r * p.side + c;
+    return b * p.Nt + r * p.side + c;
   }
-  return (long)w * p.Nt + i;
+  return w * p.Nt + i;
 }
-__device__ __forceinline__ long kv_row(const AttnP& p, int w, int l) {
-  if (p.mode == 0) return q_row(p, w, l);
-  return (long)w * p.NM + l;
+
+// Row indices of the task (queries, then kv sources) -> smem, once per task instead of once per element.
+__device__ __forceinline__ void task_rows(const AttnP& p, const Lay& ly, int* rows, int w) {
+  for (int i = threadIdx.x; i < ly.nq; i += NT) rows[i] = q_row(p, w, i);
+  if (p.mode != 2) {
+    const int nl = (p.mode == 1) ? p.NM : ly.L;
+    for (int l = threadIdx.x; l < nl; l += NT) rows[ly.nq + l] = (p.mode == 0) ? q_row(p, w, l) : w * p.NM + l;
+  }
 }
 
 // Loads K/V sources, builds Kf/Vf = [E^T Ksrc ; bank] for task (w, h).  Ends with __syncthreads().
-template <typename T>
-__device__ void build_kv(const AttnP& p, const Lay& ly, float* sm, int w, int h) {
-  const int tid = threadIdx.x, hd = p.hd, HDP = ly.HDP, D = p.H * p.hd;
+template <typename T, int HD>
+__device__ void build_kv(const AttnP& p, const Lay& ly, float* sm, const int* rows, int h) {
+  const int tid = threadIdx.x, HDP = ly.HDP, D = p.H * HD;
   float *Ks = sm + ly.oKs, *Vs = sm + ly.oVs, *Kf = sm + ly.oKf, *Vf = sm + ly.oVf;
   if (p.mode == 2) {
-    for (int idx = tid; idx < p.kb * hd; idx += NT) {
-      const int j = idx / hd, d = idx % hd;
-      Kf[j * HDP + d] = p.kc[j * D + h * hd + d];
-      Vf[j * HDP + d] = p.vc[j * D + h * hd + d];
+    for (int idx = tid; idx < p.kb * HD; idx += NT) {
+      const int j = idx / HD, d = idx % HD;
+      Kf[j * HDP + d] = p.kc[j * D + h * HD + d];
+      Vf[j * HDP + d] = p.vc[j * D + h * HD + d];
     }
     __syncthreads();
     return;
   }
   const T* kv = static_cast<const T*>(p.kv);
-  for (int idx = tid; idx < ly.L * hd; idx += NT) {
-    const int l = idx / hd, d = idx % hd;
-    const long r = kv_row(p, w, l);
-    Ks[l * HDP + d] = ldf(kv + r * p.ldkv + p.kcol + h * hd + d);
-    Vs[l * HDP + d] = ldf(kv + r * p.ldkv + p.vcol + h * hd + d);
+  for (int idx = tid; idx < ly.L * HD; idx += NT) {
+    const int l = idx / HD, d = idx % HD;
+    const long r = rows[ly.nq + l];
+    Ks[l * HDP + d] = ldf(kv + r * p.ldkv + p.kcol + h * HD + d);
+    Vs[l * HDP + d] = ldf(kv + r * p.ldkv + p.vcol + h * HD + d);
+  }
+  for (int idx = tid; idx < p.kb * HD; idx += NT) {
+    const int j = idx / HD, d = idx % HD;
+    Kf[(p.klin + j) * HDP + d] = p.bank_k[j * D + h * HD + d];
+    Vf[(p.klin + j) * HDP + d] = p.bank_v[j * D + h * HD + d];
   }
   __syncthreads();
   const float *Ek = sm + ly.oEk, *Ev = sm + ly.oEv;
-  for (int idx = tid; idx < p.klin * hd; idx += NT) {
-    const int j = idx / hd, d = idx % hd;
+  for (int idx = tid; idx < p.klin * HD; idx += NT) {
+    const int j = idx / HD, d = idx % HD;
     float ak = 0.f, av = 0.f;
     for (int l = 0; l < ly.L; ++l) {
       ak = fmaf(Ek[l * p.klin + j], Ks[l * HDP + d], ak);
@@ -67,31 +78,25 @@ __device__ void build_kv(const AttnP& p, const Lay& ly, float* sm, int w, int h)
     Kf[j * HDP + d] = ak;
     Vf[j * HDP + d] = av;
   }
-  for (int idx = tid; idx < p.kb * hd; idx += NT) {
-    const int j = idx / hd, d = idx % hd;
-    Kf[(p.klin + j) * HDP + d] = p.bank_k[j * D + h * hd + d];
-    Vf[(p.klin + j) * HDP + d] = p.bank_v[j * D + h * hd + d];
-  }
   __syncthreads();
 }
 
-// S = softmax(scale * Q Kf^T) for the loaded Q chunk of n rows.  Ends with __syncthreads().
+// P = softmax(scale * Q Kf^T) for the loaded Q chunk of n rows: one warp per query row, lanes over keys.
+template <int HD>
 __device__ void scores_softmax(const Lay& ly, float* sm, int n, float scale) {
-  const int tid = threadIdx.x, HDP = ly.HDP, NKV = ly.NKV, SP = ly.SP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, HDP = ly.HDP, NKV = ly.NKV, SP = ly.SP;
   const float *Q = sm + ly.oQ, *Kf = sm + ly.oKf;
   float* P = sm + ly.oP;
-  const int hd = HDP - 1;
-  for (int idx = tid; idx < n * NKV; idx += NT) {
-    const int i = idx / NKV, j = idx % NKV;
-    float a = 0.f;
-    for (int d = 0; d < hd; ++d) a = fmaf(Q[i * HDP + d], Kf[j * HDP + d], a);
-    P[i * SP + j] = a * scale;
-  }
-  __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int i = warp; i < n; i += NT / 32) {
+  for (int i = warp; i < n; i += NW) {
     float m = -INFINITY;
-    for (int j = lane; j < NKV; j += 32) m = fmaxf(m, P[i * SP + j]);
+    for (int j = lane; j < NKV; j += 32) {
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) a = fmaf(Q[i * HDP + d], Kf[j * HDP + d], a);
+      a *= scale;
+      P[i * SP + j] = a;
+      m = fmaxf(m, a);
+    }
     m = warp_max(m);
     float s = 0.f;
     for (int j = lane; j < NKV; j += 32) { const float e = __expf(P[i * SP + j] - m); P[i * SP + j] = e; s += e; }
@@ -101,44 +106,49 @@ __device__ void scores_softmax(const Lay& ly, float* sm, int n, float scale) {
   __syncthreads();
 }
 
-template <typename T>
+template <typename T, int HD>
 __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnP p, Lay ly, int ntask) {
   extern __shared__ float sm[];
-  const int tid = threadIdx.x, hd = p.hd, HDP = ly.HDP;
+  const int tid = threadIdx.x, HDP = ly.HDP;
+  int* rows = reinterpret_cast<int*>(sm + ly.oRow);
   if (p.mode != 2) {
     for (int idx = tid; idx < ly.L * p.klin; idx += NT) { sm[ly.oEk + idx] = p.Ek[idx]; sm[ly.oEv + idx] = p.Ev[idx]; }
   }
-  __syncthreads();
-  const float scale = rsqrtf((float)hd);
+  const float scale = rsqrtf((float)HD);
   const T* q = static_cast<const T*>(p.q);
   T* out = static_cast<T*>(p.out);
+  float *Q = sm + ly.oQ, *P = sm + ly.oP, *Vf = sm + ly.oVf;
   for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
     const int w = task / p.H, h = task % p.H;
-    build_kv<T>(p, ly, sm, w, h);
-    float *Q = sm + ly.oQ, *P = sm + ly.oP, *Vf = sm + ly.oVf;
+    __syncthreads();
+    task_rows(p, ly, rows, w);
+    __syncthreads();
+    build_kv<T, HD>(p, ly, sm, rows, h);
     for (int q0 = 0; q0 < ly.nq; q0 += ly.QC) {
       const int n = min(ly.QC, ly.nq - q0);
-      for (int idx = tid; idx < n * hd; idx += NT) {
-        const int i = idx / hd, d = idx % hd;
-        Q[i * HDP + d] = ldf(q + q_row(p, w, q0 + i) * p.ldq + p.qcol + h * hd + d);
+      for (int idx = tid; idx < n * HD; idx += NT) {
+        const int i = idx / HD, d = idx % HD;
+        Q[i * HDP + d] = ldf(q + (long)rows[q0 + i] * p.ldq + p.qcol + h * HD + d);
       }
       __syncthreads();
-      scores_softmax(ly, sm, n, scale);
-      for (int idx = tid; idx < n * hd; idx += NT) {
-        const int i = idx / hd, d = idx % hd;
+      scores_softmax<HD>(ly, sm, n, scale);
+      for (int idx = tid; idx < n * HD; idx += NT) {
+        const int i = idx / HD, d = idx % HD;
         float a = 0.f;
         for (int j = 0; j < ly.NKV; ++j) a = fmaf(P[i * ly.SP + j], Vf[j * HDP + d], a);
-        stf(out + q_row(p, w, q0 + i) * p.ldo + h * hd + d, a);
+        stf(out + (long)rows[q0 + i] * p.ldo + h * HD + d, a);
       }
       __syncthreads();
     }
   }
 }
 
-template <typename T>
+template <typename T, int HD>
 __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask) {
   extern __shared__ float sm[];
-  const int tid = threadIdx.x, hd = p.hd, HDP = ly.HDP, NKV = ly.NKV, SP = ly.SP, D = p.H * p.hd;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HDP = ly.HDP, NKV = ly.NKV, SP = ly.SP, D = p.H * HD;
+  int* rows = reinterpret_cast<int*>(sm + ly.oRow);
   if (p.mode != 2) {
     for (int idx = tid; idx < ly.L * p.klin; idx += NT) {
       sm[ly.oEk + idx] = p.Ek[idx]; sm[ly.oEv + idx] = p.Ev[idx];
@@ -146,8 +156,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask
     }
   }
   for (int idx = tid; idx < p.kb * D; idx += NT) { sm[ly.odbk + idx] = 0.f; sm[ly.odbv + idx] = 0.f; }
-  __syncthreads();
-  const float scale = rsqrtf((float)hd);
+  const float scale = rsqrtf((float)HD);
   const T* q = static_cast<const T*>(p.q);
   const T* dout = static_cast<const T*>(p.dout);
   T* dq = static_cast<T*>(p.dq);
@@ -156,46 +165,44 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask
   float *Kf = sm + ly.oKf, *Vf = sm + ly.oVf, *dKf = sm + ly.odKf, *dVf = sm + ly.odVf;
   for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
     const int w = task / p.H, h = task % p.H;
-    build_kv<T>(p, ly, sm, w, h);
+    __syncthreads();
+    task_rows(p, ly, rows, w);
+    __syncthreads();
+    build_kv<T, HD>(p, ly, sm, rows, h);
     for (int idx = tid; idx < NKV * HDP; idx += NT) { dKf[idx] = 0.f; dVf[idx] = 0.f; }
     for (int q0 = 0; q0 < ly.nq; q0 += ly.QC) {
       const int n = min(ly.QC, ly.nq - q0);
-      for (int idx = tid; idx < n * hd; idx += NT) {
-        const int i = idx / hd, d = idx % hd;
-        const long r = q_row(p, w, q0 + i);
-        Q[i * HDP + d] = ldf(q + r * p.ldq + p.qcol + h * hd + d);
-        dO[i * HDP + d] = ldf(dout + r * p.lddo + h * hd + d);
+      for (int idx = tid; idx < n * HD; idx += NT) {
+        const int i = idx / HD, d = idx % HD;
+        const long r = rows[q0 + i];
+        Q[i * HDP + d] = ldf(q + r * p.ldq + p.qcol + h * HD + d);
+        dO[i * HDP + d] = ldf(dout + r * p.lddo + h * HD + d);
       }
       __syncthreads();
-      scores_softmax(ly, sm, n, scale);
-      // dP = dO Vf^T
-      for (int idx = tid; idx < n * NKV; idx += NT) {
-        const int i = idx / NKV, j = idx % NKV;
-        float a = 0.f;
-        for (int d = 0; d < hd; ++d) a = fmaf(dO[i * HDP + d], Vf[j * HDP + d], a);
-        dS[i * SP + j] = a;
-      }
-      __syncthreads();
-      // dS = P * (dP - rowsum(dP * P)) * scale
-      {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int i = warp; i < n; i += NT / 32) {
-          float s = 0.f;
-          for (int j = lane; j < NKV; j += 32) s += dS[i * SP + j] * P[i * SP + j];
-          s = warp_sum(s);
-          for (int j = lane; j < NKV; j += 32) dS[i * SP + j] = P[i * SP + j] * (dS[i * SP + j] - s) * scale;
+      scores_softmax<HD>(ly, sm, n, scale);
+      // dS = P * (dO Vf^T - rowsum(P * dO Vf^T)) * scale : one warp per query row
+      for (int i = warp; i < n; i += NW) {
+        float s = 0.f;
+        for (int j = lane; j < NKV; j += 32) {
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) a = fmaf(dO[i * HDP + d], Vf[j * HDP + d], a);
+          dS[i * SP + j] = a;
+          s = fmaf(a, P[i * SP + j], s);
         }
+        s = warp_sum(s);
+        for (int j = lane; j < NKV; j += 32) dS[i * SP + j] = P[i * SP + j] * (dS[i * SP + j] - s) * scale;
       }
       __syncthreads();
       // dQ = dS Kf ; dVf += P^T dO ; dKf += dS^T Q
-      for (int idx = tid; idx < n * hd; idx += NT) {
-        const int i = idx / hd, d = idx % hd;
+      for (int idx = tid; idx < n * HD; idx += NT) {
+        const int i = idx / HD, d = idx % HD;
         float a = 0.f;
         for (int j = 0; j < NKV; ++j) a = fmaf(dS[i * SP + j], Kf[j * HDP + d], a);
-        stf(dq + q_row(p, w, q0 + i) * p.lddq + p.dqcol + h * hd + d, a);
+        stf(dq + (long)rows[q0 + i] * p.lddq + p.dqcol + h * HD + d, a);
       }
-      for (int idx = tid; idx < NKV * hd; idx += NT) {
-        const int j = idx / hd, d = idx % hd;
+      for (int idx = tid; idx < NKV * HD; idx += NT) {
+        const int j = idx / HD, d = idx % HD;
         float av = 0.f, ak = 0.f;
         for (int i = 0; i < n; ++i) {
           av = fmaf(P[i * SP + j], dO[i * HDP + d], av);
@@ -208,48 +215,50 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask
     }
     // ---- distribute dKf / dVf
     const int boff = (p.mode == 2) ? 0 : p.klin;
-    for (int idx = tid; idx < p.kb * hd; idx += NT) {
-      const int j = idx / hd, d = idx % hd;
-      sm[ly.odbk + j * D + h * hd + d] += dKf[(boff + j) * HDP + d];
-      sm[ly.odbv + j * D + h * hd + d] += dVf[(boff + j) * HDP + d];
+    for (int idx = tid; idx < p.kb * HD; idx += NT) {
+      const int j = idx / HD, d = idx % HD;
+      sm[ly.odbk + j * D + h * HD + d] += dKf[(boff + j) * HDP + d];
+      sm[ly.odbv + j * D + h * HD + d] += dVf[(boff + j) * HDP + d];
     }
     if (p.mode != 2) {
       const float *Ek = sm + ly.oEk, *Ev = sm + ly.oEv, *Ks = sm + ly.oKs, *Vs = sm + ly.oVs;
       float *dEk = sm + ly.odEk, *dEv = sm + ly.odEv;
       // dKsrc[l, d] = sum_j E[l, j] dK'[j, d]
-      for (int idx = tid; idx < ly.L * hd; idx += NT) {
-        const int l = idx / hd, d = idx % hd;
+      for (int idx = tid; idx < ly.L * HD; idx += NT) {
+        const int l = idx / HD, d = idx % HD;
         float ak = 0.f, av = 0.f;
         for (int j = 0; j < p.klin; ++j) {
           ak = fmaf(Ek[l * p.klin + j], dKf[j * HDP + d], ak);
           av = fmaf(Ev[l * p.klin + j], dVf[j * HDP + d], av);
         }
-        const long r = kv_row(p, w, l);
-        stf(dkv + r * p.lddkv + p.dkcol + h * hd + d, ak);
-        stf(dkv + r * p.lddkv + p.dvcol + h * hd + d, av);
+        const long r = rows[ly.nq + l];
+        stf(dkv + r * p.lddkv + p.dkcol + h * HD + d, ak);
+        stf(dkv + r * p.lddkv + p.dvcol + h * HD + d, av);
       }
       if (p.mode == 1) {  // pooled rows beyond the Linformer length were truncated away (H:510-512): zero grad
-        for (int idx = tid; idx < (p.NM - ly.L) * hd; idx += NT) {
-          const int l = ly.L + idx / hd, d = idx % hd;
-          const long r = kv_row(p, w, l);
-          stf(dkv + r * p.lddkv + p.dkcol + h * hd + d, 0.f);
-          stf(dkv + r * p.lddkv + p.dvcol + h * hd + d, 0.f);
+        for (int idx = tid; idx < (p.NM - ly.L) * HD; idx += NT) {
+          const int l = ly.L + idx / HD, d = idx % HD;
+          const long r = rows[ly.nq + l];
+          stf(dkv + r * p.lddkv + p.dkcol + h * HD + d, 0.f);
+          stf(dkv + r * p.lddkv + p.dvcol + h * HD + d, 0.f);
         }
       }
-      // dE[l, j] += sum_d Ksrc[l, d] dK'[j, d]
-      for (int idx = tid; idx < ly.L * p.klin; idx += NT) {
-        const int l = idx / p.klin, j = idx % p.klin;
-        float ak = 0.f, av = 0.f;
-        for (int d = 0; d < hd; ++d) {
-          ak = fmaf(Ks[l * HDP + d], dKf[j * HDP + d], ak);
-          av = fmaf(Vs[l * HDP + d], dVf[j * HDP + d], av);
+      // dE[l, j] += sum_d Ksrc[l, d] dK'[j, d] : warp per l, lanes over j
+      for (int l = warp; l < ly.L; l += NW) {
+        for (int j = lane; j < p.klin; j += 32) {
+          float ak = 0.f, av = 0.f;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) {
+            ak = fmaf(Ks[l * HDP + d], dKf[j * HDP + d], ak);
+            av = fmaf(Vs[l * HDP + d], dVf[j * HDP + d], av);
+          }
+          dEk[l * p.klin + j] += ak;
+          dEv[l * p.klin + j] += av;
         }
-        dEk[idx] += ak;
-        dEv[idx] += av;
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
   // ---- flush the batch-reduced accumulators
   if (p.mode != 2) {
     for (int idx = tid; idx < ly.L * p.klin; idx += NT) {
@@ -281,6 +290,7 @@ Lay make_layout(const AttnP& p, bool bwd) {
   ly.oQ = take(ly.QC * ly.HDP); ly.odO = take(bwd ? ly.QC * ly.HDP : 0);
   ly.oP = take(ly.QC * ly.SP); ly.odS = take(bwd ? ly.QC * ly.SP : 0);
   ly.odbk = take(bwd ? p.kb * p.H * p.hd : 0); ly.odbv = take(bwd ? p.kb * p.H * p.hd : 0);
+  ly.oRow = take(ly.nq + (p.mode == 1 ? p.NM : ly.L));
   ly.total = o;
   return ly;
 }
@@ -292,355 +302,32 @@ int set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
+template <typename T, bool BWD>
+int launch_attn(cudaStream_t s, const AttnP& p) {
+  QV_CHECK(p.hd == 48, "attention kernels are instantiated for head_dim 48 (got %d)", p.hd);
+  const Lay ly = make_layout(p, BWD);
+  const int nwin = (p.mode == 0) ? p.B * (p.side / p.ws) * (p.side / p.ws) : p.B;
+  const int ntask = nwin * p.H;
+  if (ntask <= 0) return 0;
+  const size_t smem = (size_t)ly.total * sizeof(float);
+  const int occ = max(1, min(8, (int)(220 * 1024 / (smem + 1024))));
+  const int grid = min(ntask, qv_num_sms() * occ);
+  if (BWD) {
+    QV_TRY(set_smem(attn_bwd_kernel<T, 48>, smem));
+    attn_bwd_kernel<T, 48><<<grid, NT, smem, s>>>(p, ly, ntask);
+  } else {
+    QV_TRY(set_smem(attn_fwd_kernel<T, 48>, smem));
+    attn_fwd_kernel<T, 48><<<grid, NT, smem, s>>>(p, ly, ntask);
+  }
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 int attn_fwd(cudaStream_t s, int dt, const AttnP& p) {
-  const Lay ly = make_layout(p, false);
-  const int nwin = (p.mode == 0) ? p.B * (p.side / p.ws) * (p.side / p.ws) : p.B;
-  const int ntask = nwin * p.H;
-  if (ntask <= 0) return 0;
-  const size_t smem = (size_t)ly.total * sizeof(float);
-  const int occ = max(1, (int)(200 * 1024 / (smem + 1024)));
-  const int grid = min(ntask, qv_num_sms() * min(occ, 8));
-  if (dt == QV_F32) {
-    QV_TRY(set_smem(attn_fwd_kernel<float>, smem));
-    attn_fwd_kernel<float><<<grid, NT, smem, s>>>(p, ly, ntask);
-  } else {
-    QV_TRY(set_smem(attn_fwd_kernel<bf16>, smem));
-    attn_fwd_kernel<bf16><<<grid, NT, smem, s>>>(p, ly, ntask);
-  }
-  QV_LAUNCH_CHECK();
-  return 0;
+  return dt == QV_F32 ? launch_attn<float, false>(s, p) : launch_attn<bf16, false>(s, p);
 }
-
 int attn_bwd(cudaStream_t s, int dt, const AttnP& p) {
-  const Lay ly = make_layout(p, true);
-  const int nwin = (p.mode == 0) ? p.B * (p.side / p.ws) * (p.side / p.ws) : p.B;
-  const int ntask = nwin * p.H;
-  if (ntask <= 0) return 0;
-  const size_t smem = (size_t)ly.total * sizeof(float);
-  const int occ = max(1, (int)(200 * 1024 / (smem + 1024)));
-  const int grid = min(ntask, qv_num_sms() * min(occ, 8));
-  if (dt == QV_F32) {
-    QV_TRY(set_smem(attn_bwd_kernel<float>, smem));
-    attn_bwd_kernel<float><<<grid, NT, smem, s>>>(p, ly, ntask);
-  } else {
-    QV_TRY(set_smem(attn_bwd_kernel<bf16>, smem));
-    attn_bwd_kernel<bf16><<<grid, NT, smem, s>>>(p, ly, ntask);
-  }
-  QV_LAUNCH_CHECK();
-  return 0;
-}
-
-// =====================================================================================================
-// Channel-group attention
-// =====================================================================================================
-namespace {
-
-struct CgaLay { int NKV, SP, QC, oX, oQ, oK, oV, oP, odS, odO, odQ, odK, odV, oW, odW, odkb, total; };
-
-// per-group projections for image b: q/k/v[Nt, cpg] from xg[Nt, cg]; bank rows appended to k, v.
-template <typename T>
-__device__ void cga_project(const CgaP& p, const CgaLay& ly, float* sm, int b, int g) {
-  const int tid = threadIdx.x, cg = p.cg, cpg = p.cpg, Nt = p.Nt;
-  const T* xn = static_cast<const T*>(p.xn);
-  float *X = sm + ly.oX, *Q = sm + ly.oQ, *K = sm + ly.oK, *V = sm + ly.oV;
-  const float* W = sm + ly.oW;  // [3][cpg][cg] then biases [3][cpg]
-  const float* Bv = W + 3 * cpg * cg;
-  for (int idx = tid; idx < Nt * cg; idx += NT) {
-    const int n = idx / cg, c = idx % cg;
-    X[n * (cg + 1) + c] = ldf(xn + ((long)b * Nt + n) * p.ldx + g * cg + c);
-  }
-  __syncthreads();
-  for (int idx = tid; idx < Nt * cpg; idx += NT) {
-    const int n = idx / cpg, o = idx % cpg;
-    float aq = Bv[o], ak = Bv[cpg + o], av = Bv[2 * cpg + o];
-    for (int c = 0; c < cg; ++c) {
-      const float x = X[n * (cg + 1) + c];
-      aq = fmaf(x, W[o * cg + c], aq);
-      ak = fmaf(x, W[(cpg + o) * cg + c], ak);
-      av = fmaf(x, W[(2 * cpg + o) * cg + c], av);
-    }
-    Q[n * cpg + o] = aq; K[n * cpg + o] = ak; V[n * cpg + o] = av;
-  }
-  for (int idx = tid; idx < p.kb * cpg; idx += NT) {
-    K[Nt * cpg + idx] = p.kbp[idx];
-    V[Nt * cpg + idx] = p.vbp[idx];
-  }
-  __syncthreads();
-}
-
-// P[h][i][j] for query rows q0..q0+n of the current group.  Ends with __syncthreads().
-__device__ void cga_scores(const CgaP& p, const CgaLay& ly, float* sm, int q0, int n) {
-  const int tid = threadIdx.x, cpg = p.cpg, hdc = p.cpg / p.H, NKV = ly.NKV, SP = ly.SP;
-  const float *Q = sm + ly.oQ, *K = sm + ly.oK;
-  float* P = sm + ly.oP;
-  const float scale = rsqrtf((float)hdc);
-  for (int idx = tid; idx < p.H * n * NKV; idx += NT) {
-    const int h = idx / (n * NKV), r = idx % (n * NKV), i = r / NKV, j = r % NKV;
-    float a = 0.f;
-    for (int d = 0; d < hdc; ++d) a = fmaf(Q[(q0 + i) * cpg + h * hdc + d], K[j * cpg + h * hdc + d], a);
-    P[(h * ly.QC + i) * SP + j] = a * scale;
-  }
-  __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int r = warp; r < p.H * n; r += NT / 32) {
-    const int h = r / n, i = r % n;
-    float* row = P + (h * ly.QC + i) * SP;
-    float m = -INFINITY;
-    for (int j = lane; j < NKV; j += 32) m = fmaxf(m, row[j]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int j = lane; j < NKV; j += 32) { const float e = __expf(row[j] - m); row[j] = e; s += e; }
-    s = 1.f / warp_sum(s);
-    for (int j = lane; j < NKV; j += 32) row[j] *= s;
-  }
-  __syncthreads();
-}
-
-__device__ void cga_load_weights(const CgaP& p, const CgaLay& ly, float* sm) {
-  float* W = sm + ly.oW;
-  const int n = p.cpg * p.cg;
-  for (int idx = threadIdx.x; idx < n; idx += NT) { W[idx] = p.Wq[idx]; W[n + idx] = p.Wk[idx]; W[2 * n + idx] = p.Wv[idx]; }
-  for (int idx = threadIdx.x; idx < p.cpg; idx += NT) {
-    W[3 * n + idx] = p.bq[idx]; W[3 * n + p.cpg + idx] = p.bk[idx]; W[3 * n + 2 * p.cpg + idx] = p.bv[idx];
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(NT) cga_fwd_kernel(CgaP p, CgaLay ly) {
-  extern __shared__ float sm[];
-  const int tid = threadIdx.x, cpg = p.cpg, hdc = p.cpg / p.H;
-  cga_load_weights(p, ly, sm);
-  __syncthreads();
-  T* out = static_cast<T*>(p.out);
-  const float *V = sm + ly.oV, *P = sm + ly.oP;
-  for (int task = blockIdx.x; task < p.B * p.G; task += gridDim.x) {
-    const int b = task / p.G, g = task % p.G;
-    cga_project<T>(p, ly, sm, b, g);
-    for (int q0 = 0; q0 < p.Nt; q0 += ly.QC) {
-      const int n = min(ly.QC, p.Nt - q0);
-      cga_scores(p, ly, sm, q0, n);
-      for (int idx = tid; idx < n * cpg; idx += NT) {
-        const int i = idx / cpg, o = idx % cpg, h = o / hdc;
-        float a = 0.f;
-        for (int j = 0; j < ly.NKV; ++j) a = fmaf(P[(h * ly.QC + i) * ly.SP + j], V[j * cpg + o], a);
-        stf(out + ((long)b * p.Nt + q0 + i) * p.ldo + g * cpg + o, a);
-      }
-      __syncthreads();
-    }
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(NT) cga_bwd_kernel(CgaP p, CgaLay ly) {
-  extern __shared__ float sm[];
-  const int tid = threadIdx.x, cpg = p.cpg, cg = p.cg, hdc = p.cpg / p.H, Nt = p.Nt, NKV = ly.NKV, SP = ly.SP;
-  cga_load_weights(p, ly, sm);
-  const int nW = 3 * cpg * cg + 3 * cpg;
-  for (int idx = tid; idx < nW; idx += NT) sm[ly.odW + idx] = 0.f;
-  for (int idx = tid; idx < 2 * p.kb * cpg; idx += NT) sm[ly.odkb + idx] = 0.f;
-  __syncthreads();
-  const T* dout = static_cast<const T*>(p.dout);
-  float *X = sm + ly.oX, *Q = sm + ly.oQ, *K = sm + ly.oK, *V = sm + ly.oV, *P = sm + ly.oP, *dS = sm + ly.odS;
-  float *dO = sm + ly.odO, *dQ = sm + ly.odQ, *dK = sm + ly.odK, *dV = sm + ly.odV;
-  const float* W = sm + ly.oW;
-  float* dW = sm + ly.odW;
-  const float scale = rsqrtf((float)hdc);
-  for (int task = blockIdx.x; task < p.B * p.G; task += gridDim.x) {
-    const int b = task / p.G, g = task % p.G;
-    cga_project<T>(p, ly, sm, b, g);
-    for (int idx = tid; idx < NKV * cpg; idx += NT) { dK[idx] = 0.f; dV[idx] = 0.f; }
-    for (int q0 = 0; q0 < Nt; q0 += ly.QC) {
-      const int n = min(ly.QC, Nt - q0);
-      for (int idx = tid; idx < n * cpg; idx += NT) {
-        const int i = idx / cpg, o = idx % cpg;
-        dO[idx] = ldf(dout + ((long)b * Nt + q0 + i) * p.lddo + g * cpg + o);
-      }
-      cga_scores(p, ly, sm, q0, n);   // also orders the dO stores
-      for (int idx = tid; idx < p.H * n * NKV; idx += NT) {
-        const int h = idx / (n * NKV), r = idx % (n * NKV), i = r / NKV, j = r % NKV;
-        float a = 0.f;
-        for (int d = 0; d < hdc; ++d) a = fmaf(dO[i * cpg + h * hdc + d], V[j * cpg + h * hdc + d], a);
-        dS[(h * ly.QC + i) * SP + j] = a;
-      }
-      __syncthreads();
-      {
-        const int lane = tid & 31, warp = tid >> 5;
-        for (int r = warp; r < p.H * n; r += NT / 32) {
-          const int h = r / n, i = r % n;
-          float* ds = dS + (h * ly.QC + i) * SP;
-          const float* pr = P + (h * ly.QC + i) * SP;
-          float s = 0.f;
-          for (int j = lane; j < NKV; j += 32) s += ds[j] * pr[j];
-          s = warp_sum(s);
-          for (int j = lane; j < NKV; j += 32) ds[j] = pr[j] * (ds[j] - s) * scale;
-        }
-      }
-      __syncthreads();
-      for (int idx = tid; idx < n * cpg; idx += NT) {
-        const int i = idx / cpg, o = idx % cpg, h = o / hdc;
-        float a = 0.f;
-        for (int j = 0; j < NKV; ++j) a = fmaf(dS[(h * ly.QC + i) * SP + j], K[j * cpg + o], a);
-        dQ[(q0 + i) * cpg + o] = a;
-      }
-      for (int idx = tid; idx < NKV * cpg; idx += NT) {
-        const int j = idx / cpg, o = idx % cpg, h = o / hdc;
-        float av = 0.f, ak = 0.f;
-        for (int i = 0; i < n; ++i) {
-          av = fmaf(P[(h * ly.QC + i) * SP + j], dO[i * cpg + o], av);
-          ak = fmaf(dS[(h * ly.QC + i) * SP + j], Q[(q0 + i) * cpg + o], ak);
-        }
-        dV[idx] += av;
-        dK[idx] += ak;
-      }
-      __syncthreads();
-    }
-    // bank rows -> d(projected bank); own rows -> projections backward
-    for (int idx = tid; idx < p.kb * cpg; idx += NT) {
-      sm[ly.odkb + idx] += dK[Nt * cpg + idx];
-      sm[ly.odkb + p.kb * cpg + idx] += dV[Nt * cpg + idx];
-    }
-    // dx[n, c] += sum_o dq[n,o] Wq[o,c] + dk[n,o] Wk[o,c] + dv[n,o] Wv[o,c]
-    for (int idx = tid; idx < Nt * cg; idx += NT) {
-      const int n = idx / cg, c = idx % cg;
-      float a = 0.f;
-      for (int o = 0; o < cpg; ++o) {
-        a = fmaf(dQ[n * cpg + o], W[o * cg + c], a);
-        a = fmaf(dK[n * cpg + o], W[(cpg + o) * cg + c], a);
-        a = fmaf(dV[n * cpg + o], W[(2 * cpg + o) * cg + c], a);
-      }
-      p.dxn[((long)b * Nt + n) * p.lddx + g * cg + c] += a;
-    }
-    // dW[o, c] += sum_n d{q,k,v}[n, o] x[n, c] ; db[o] += sum_n d{q,k,v}[n, o]
-    for (int idx = tid; idx < 3 * cpg * cg; idx += NT) {
-      const int which = idx / (cpg * cg), r = idx % (cpg * cg), o = r / cg, c = r % cg;
-      const float* dsrc = which == 0 ? dQ : (which == 1 ? dK : dV);
-      float a = 0.f;
-      for (int n = 0; n < Nt; ++n) a = fmaf(dsrc[n * cpg + o], X[n * (cg + 1) + c], a);
-      dW[idx] += a;
-    }
-    for (int idx = tid; idx < 3 * cpg; idx += NT) {
-      const int which = idx / cpg, o = idx % cpg;
-      const float* dsrc = which == 0 ? dQ : (which == 1 ? dK : dV);
-      float a = 0.f;
-      for (int n = 0; n < Nt; ++n) a += dsrc[n * cpg + o];
-      dW[3 * cpg * cg + idx] += a;
-    }
-    __syncthreads();
-  }
-  const int n1 = cpg * cg;
-  for (int idx = tid; idx < n1; idx += NT) {
-    atomicAdd(p.dWq + idx, dW[idx]); atomicAdd(p.dWk + idx, dW[n1 + idx]); atomicAdd(p.dWv + idx, dW[2 * n1 + idx]);
-  }
-  for (int idx = tid; idx < cpg; idx += NT) {
-    atomicAdd(p.dbq + idx, dW[3 * n1 + idx]); atomicAdd(p.dbk + idx, dW[3 * n1 + cpg + idx]);
-    atomicAdd(p.dbv + idx, dW[3 * n1 + 2 * cpg + idx]);
-  }
-  for (int idx = tid; idx < p.kb * cpg; idx += NT) {
-    atomicAdd(p.dkbp + idx, sm[ly.odkb + idx]);
-    atomicAdd(p.dvbp + idx, sm[ly.odkb + p.kb * cpg + idx]);
-  }
-}
-
-CgaLay cga_layout(const CgaP& p, bool bwd) {
-  CgaLay ly{};
-  ly.NKV = p.Nt + p.kb;
-  ly.SP = ly.NKV + 1;
-  ly.QC = p.Nt < 32 ? p.Nt : 32;
-  int o = 0;
-  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-  ly.oX = take(p.Nt * (p.cg + 1));
-  ly.oQ = take(p.Nt * p.cpg);
-  ly.oK = take(ly.NKV * p.cpg);
-  ly.oV = take(ly.NKV * p.cpg);
-  ly.oP = take(p.H * ly.QC * ly.SP);
-  ly.odS = take(bwd ? p.H * ly.QC * ly.SP : 0);
-  ly.odO = take(bwd ? ly.QC * p.cpg : 0);
-  ly.odQ = take(bwd ? p.Nt * p.cpg : 0);
-  ly.odK = take(bwd ? ly.NKV * p.cpg : 0);
-  ly.odV = take(bwd ? ly.NKV * p.cpg : 0);
-  ly.oW = take(3 * p.cpg * p.cg + 3 * p.cpg);
-  ly.odW = take(bwd ? 3 * p.cpg * p.cg + 3 * p.cpg : 0);
-  ly.odkb = take(bwd ? 2 * p.kb * p.cpg : 0);
-  ly.total = o;
-  return ly;
-}
-
-}  // namespace
-
-int cga_fwd(cudaStream_t s, int dt, const CgaP& p) {
-  if (p.B <= 0) return 0;
-  QV_CHECK(p.cpg % p.H == 0, "cga: cpg %% heads != 0");
-  const CgaLay ly = cga_layout(p, false);
-  const size_t smem = (size_t)ly.total * sizeof(float);
-  const int occ = max(1, (int)(200 * 1024 / (smem + 1024)));
-  const int grid = min(p.B * p.G, qv_num_sms() * min(occ, 8));
-  if (dt == QV_F32) { QV_TRY(set_smem(cga_fwd_kernel<float>, smem)); cga_fwd_kernel<float><<<grid, NT, smem, s>>>(p, ly); }
-  else { QV_TRY(set_smem(cga_fwd_kernel<bf16>, smem)); cga_fwd_kernel<bf16><<<grid, NT, smem, s>>>(p, ly); }
-  QV_LAUNCH_CHECK();
-  return 0;
-}
-
-int cga_bwd(cudaStream_t s, int dt, const CgaP& p) {
-  if (p.B <= 0) return 0;
-  const CgaLay ly = cga_layout(p, true);
-  const size_t smem = (size_t)ly.total * sizeof(float);
-  const int occ = max(1, (int)(200 * 1024 / (smem + 1024)));
-  const int grid = min(p.B * p.G, qv_num_sms() * min(occ, 8));
-  if (dt == QV_F32) { QV_TRY(set_smem(cga_bwd_kernel<float>, smem)); cga_bwd_kernel<float><<<grid, NT, smem, s>>>(p, ly); }
-  else { QV_TRY(set_smem(cga_bwd_kernel<bf16>, smem)); cga_bwd_kernel<bf16><<<grid, NT, smem, s>>>(p, ly); }
-  QV_LAUNCH_CHECK();
-  return 0;
-}
-
-// =====================================================================================================
-// Bank projections: Y[rows, N] = X[rows, K] W^T + b with rows = 16 (batch invariant; the reference recomputes
-// them per image, H:617-619).  Single small grid, fp32.
-// =====================================================================================================
-namespace {
-__global__ void small_linear_fwd_kernel(const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * N) return;
-  const int r = idx / N, n = idx % N;
-  float a = b ? b[n] : 0.f;
-  for (int k = 0; k < K; ++k) a = fmaf(X[r * K + k], W[n * K + k], a);
-  Y[idx] = a;
-}
-// dW[n,k] += sum_r dY[r,n] X[r,k]; db[n] += sum_r dY[r,n]; dX[r,k] += sum_n dY[r,n] W[n,k]
-__global__ void small_linear_bwd_kernel(const float* X, int rows, int K, const float* W, int N, const float* dY,
-                                        float* dW, float* db, float* dX) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < N * K) {
-    const int n = idx / K, k = idx % K;
-    float a = 0.f;
-    for (int r = 0; r < rows; ++r) a = fmaf(dY[r * N + n], X[r * K + k], a);
-    dW[idx] += a;
-  }
-  if (idx < N) {
-    float a = 0.f;
-    for (int r = 0; r < rows; ++r) a += dY[r * N + idx];
-    db[idx] += a;
-  }
-  if (idx < rows * K) {
-    const int r = idx / K, k = idx % K;
-    float a = 0.f;
-    for (int n = 0; n < N; ++n) a = fmaf(dY[r * N + n], W[n * K + k], a);
-    dX[idx] += a;
-  }
-}
-}  // namespace
-
-int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
-  small_linear_fwd_kernel<<<cdiv(rows * N, 128), 128, 0, s>>>(X, rows, K, W, b, N, Y);
-  QV_LAUNCH_CHECK();
-  return 0;
-}
-
-int small_linear_bwd(cudaStream_t s, const float* X, int rows, int K, const float* W, int N, const float* dY, float* dW,
-                     float* db, float* dX_accum) {
-  const int n = max(N * K, rows * K);
-  small_linear_bwd_kernel<<<cdiv(n, 128), 128, 0, s>>>(X, rows, K, W, N, dY, dW, db, dX_accum);
-  QV_LAUNCH_CHECK();
-  return 0;
+  return dt == QV_F32 ? launch_attn<float, true>(s, p) : launch_attn<bf16, true>(s, p);
 }

@@ -402,21 +402,30 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   const bool train = cfg->train != 0;
   QV_CHECK(!train || cfg->bank_v1 || update_count, "train mode needs update_count");
 
-  // ---- stacked write weight [write_compression ; write_gate] and bf16 weight copies
+  // ---- stacked write weight [write_compression ; write_gate] and the bf16 weight copies (one batched launch)
   if (train) {
-    QV_CUDA(cudaMemcpyAsync(c.sv(S.wstack), c.pf(QP_BANK_WC_W), (size_t)d * d * 4, cudaMemcpyDeviceToDevice, st));
-    QV_CUDA(cudaMemcpyAsync(c.svf(S.wstack) + (size_t)d * d, c.pf(QP_BANK_WG_W), (size_t)D.kb * d * 4, cudaMemcpyDeviceToDevice, st));
+    if (dt == QV_F32) {
+      QV_CUDA(cudaMemcpyAsync(c.sv(S.wstack), c.pf(QP_BANK_WC_W), (size_t)d * d * 4, cudaMemcpyDeviceToDevice, st));
+      QV_CUDA(cudaMemcpyAsync(c.svf(S.wstack) + (size_t)d * d, c.pf(QP_BANK_WG_W), (size_t)D.kb * d * 4, cudaMemcpyDeviceToDevice, st));
+    }
     QV_CUDA(cudaMemcpyAsync(c.sv(S.bstack), c.pf(QP_BANK_WC_B), (size_t)d * 4, cudaMemcpyDeviceToDevice, st));
     QV_CUDA(cudaMemcpyAsync(c.svf(S.bstack) + d, c.pf(QP_BANK_WG_B), (size_t)D.kb * 4, cudaMemcpyDeviceToDevice, st));
   }
   if (dt == QV_BF16) {
+    ConvertJobs jobs{};
     for (int wi = 0; wi < W_COUNT; ++wi) {
       if ((wi == W_TL && !D.tl) || (wi == W_WRITE && !train)) continue;
       int N, K;
       weight_shape(D, wi, &N, &K);
-      QV_TRY(convert_weight(st, weight_src(c, wi), N, K, reinterpret_cast<bf16*>(c.sv(S.wb[wi])),
-                            wi == W_WRITE ? nullptr : reinterpret_cast<bf16*>(c.sv(S.wbt[wi]))));
+      bf16* wb = reinterpret_cast<bf16*>(c.sv(S.wb[wi]));
+      if (wi == W_WRITE) {   // two sources stacked along N
+        jobs.j[jobs.n++] = ConvertJob{c.pf(QP_BANK_WC_W), d, K, wb, nullptr};
+        jobs.j[jobs.n++] = ConvertJob{c.pf(QP_BANK_WG_W), D.kb, K, wb + (size_t)d * K, nullptr};
+      } else {
+        jobs.j[jobs.n++] = ConvertJob{weight_src(c, wi), N, K, wb, reinterpret_cast<bf16*>(c.sv(S.wbt[wi]))};
+      }
     }
+    QV_TRY(convert_weights_batched(st, jobs));
   }
 
   // ---- TokenLearner (H:985-1002)
@@ -764,4 +773,17 @@ extern "C" int qavit_test_gemm_tn(int use_tc, const void* dY, int ldy, const voi
 }
 extern "C" int qavit_convert_weight(const float* w, int N, int K, void* wb, void* wbt, void* stream) {
   return convert_weight((cudaStream_t)stream, w, N, K, (bf16*)wb, (bf16*)wbt);
+}
+
+// nn.LayerNorm forward / backward for the modules around the blocks (SplitFusion, LMFAdapter, RRCV, ConvNeXt; C <= 256).
+// x: fp32 (x_bf16 = 0) or bf16; y and dy are fp32 (autocast keeps LayerNorm outputs in fp32);
+// dx has x's dtype; dgamma / dbeta are accumulated.
+extern "C" int qavit_layer_norm_forward(const void* x, int x_bf16, long long rows, int C, const float* w, const float* b,
+                                        float eps, float* y, float* stats, void* stream) {
+  return ln_fwd((cudaStream_t)stream, x_bf16 ? QV_BF16 : QV_F32, x, C, (int)rows, C, w, b, eps, 0, nullptr, nullptr, QV_F32, y, C, stats);
+}
+extern "C" int qavit_layer_norm_backward(const void* x, int x_bf16, const float* dy, long long rows, int C, const float* w,
+                                         const float* stats, void* dx, float* dgamma, float* dbeta, void* stream) {
+  return ln_bwd((cudaStream_t)stream, x_bf16 ? QV_BF16 : QV_F32, x, C, QV_F32, dy, C, (int)rows, C, w, stats, 0,
+                x_bf16 ? QV_BF16 : QV_F32, x_bf16 ? dx : nullptr, x_bf16 ? nullptr : (float*)dx, nullptr, dgamma, dbeta);
 }

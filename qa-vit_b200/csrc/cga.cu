@@ -1,0 +1,332 @@
+// Channel-group attention (H:559-595) and the batch-invariant bank projections.  See attn.cu for the other branches.
+#include "kernels.h"
+
+namespace {
+constexpr int NT = 128;  // threads per CTA
+// compile-time shapes of every shipped config (d = 192, 6 groups, 4 heads): 32 channels / group -> 16 -> 4 heads of 4
+constexpr int CG = 32, CPG = 16, NH = 4, HDC = 4;
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  QV_CHECK(bytes <= 227 * 1024, "attention kernel needs %zu B of shared memory (> 227 KB): config not supported", bytes);
+  if (bytes > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+}  // namespace
+
+// =====================================================================================================
+// Channel-group attention
+// =====================================================================================================
+namespace {
+
+struct CgaLay { int NKV, SP, QC, oX, oQ, oK, oV, oP, odS, odO, odQ, odK, odV, oW, odW, odkb, total; };
+
+// per-group projections for image b: q/k/v[Nt, cpg] from xg[Nt, cg]; bank rows appended to k, v.
+template <typename T>
+__device__ void cga_project(const CgaP& p, const CgaLay& ly, float* sm, int b, int g) {
+  const int tid = threadIdx.x, Nt = p.Nt;
+  constexpr int cg = CG, cpg = CPG;
+  const T* xn = static_cast<const T*>(p.xn);
+  float *X = sm + ly.oX, *Q = sm + ly.oQ, *K = sm + ly.oK, *V = sm + ly.oV;
+  const float* W = sm + ly.oW;  // [3][cpg][cg] then biases [3][cpg]
+  const float* Bv = W + 3 * cpg * cg;
+  for (int idx = tid; idx < Nt * cg; idx += NT) {
+    const int n = idx / cg, c = idx % cg;
+    X[n * (cg + 1) + c] = ldf(xn + ((long)b * Nt + n) * p.ldx + g * cg + c);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Nt * cpg; idx += NT) {
+    const int n = idx / cpg, o = idx % cpg;
+    float aq = Bv[o], ak = Bv[cpg + o], av = Bv[2 * cpg + o];
+    for (int c = 0; c < cg; ++c) {
+      const float x = X[n * (cg + 1) + c];
+      aq = fmaf(x, W[o * cg + c], aq);
+      ak = fmaf(x, W[(cpg + o) * cg + c], ak);
+      av = fmaf(x, W[(2 * cpg + o) * cg + c], av);
+    }
+    Q[n * cpg + o] = aq; K[n * cpg + o] = ak; V[n * cpg + o] = av;
+  }
+  for (int idx = tid; idx < p.kb * cpg; idx += NT) {
+    K[Nt * cpg + idx] = p.kbp[idx];
+    V[Nt * cpg + idx] = p.vbp[idx];
+  }
+  __syncthreads();
+}
+
+// P[h][i][j] for query rows q0..q0+n of the current group.  Ends with __syncthreads().
+__device__ void cga_scores(const CgaP& p, const CgaLay& ly, float* sm, int q0, int n) {
+  const int tid = threadIdx.x, NKV = ly.NKV, SP = ly.SP;
+  constexpr int cpg = CPG, hdc = HDC;
+  const float *Q = sm + ly.oQ, *K = sm + ly.oK;
+  float* P = sm + ly.oP;
+  const float scale = rsqrtf((float)hdc);
+  for (int idx = tid; idx < NH * n * NKV; idx += NT) {
+    const int h = idx / (n * NKV), r = idx % (n * NKV), i = r / NKV, j = r % NKV;
+    float a = 0.f;
+    _Pragma("unroll") for (int d = 0; d < hdc; ++d) a = fmaf(Q[(q0 + i) * cpg + h * hdc + d], K[j * cpg + h * hdc + d], a);
+    P[(h * ly.QC + i) * SP + j] = a * scale;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int r = warp; r < NH * n; r += NT / 32) {
+    const int h = r / n, i = r % n;
+    float* row = P + (h * ly.QC + i) * SP;
+    float m = -INFINITY;
+    for (int j = lane; j < NKV; j += 32) m = fmaxf(m, row[j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < NKV; j += 32) { const float e = __expf(row[j] - m); row[j] = e; s += e; }
+    s = 1.f / warp_sum(s);
+    for (int j = lane; j < NKV; j += 32) row[j] *= s;
+  }
+  __syncthreads();
+}
+
+__device__ void cga_load_weights(const CgaP& p, const CgaLay& ly, float* sm) {
+  float* W = sm + ly.oW;
+  constexpr int n = CPG * CG;
+  for (int idx = threadIdx.x; idx < n; idx += NT) { W[idx] = p.Wq[idx]; W[n + idx] = p.Wk[idx]; W[2 * n + idx] = p.Wv[idx]; }
+  for (int idx = threadIdx.x; idx < CPG; idx += NT) {
+    W[3 * n + idx] = p.bq[idx]; W[3 * n + CPG + idx] = p.bk[idx]; W[3 * n + 2 * CPG + idx] = p.bv[idx];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) cga_fwd_kernel(CgaP p, CgaLay ly) {
+  extern __shared__ float sm[];
+  const int tid = threadIdx.x;
+  constexpr int cpg = CPG, hdc = HDC;
+  cga_load_weights(p, ly, sm);
+  __syncthreads();
+  T* out = static_cast<T*>(p.out);
+  const float *V = sm + ly.oV, *P = sm + ly.oP;
+  for (int task = blockIdx.x; task < p.B * p.G; task += gridDim.x) {
+    const int b = task / p.G, g = task % p.G;
+    cga_project<T>(p, ly, sm, b, g);
+    for (int q0 = 0; q0 < p.Nt; q0 += ly.QC) {
+      const int n = min(ly.QC, p.Nt - q0);
+      cga_scores(p, ly, sm, q0, n);
+      for (int idx = tid; idx < n * cpg; idx += NT) {
+        const int i = idx / cpg, o = idx % cpg, h = o / hdc;
+        float a = 0.f;
+        for (int j = 0; j < ly.NKV; ++j) a = fmaf(P[(h * ly.QC + i) * ly.SP + j], V[j * cpg + o], a);
+        stf(out + ((long)b * p.Nt + q0 + i) * p.ldo + g * cpg + o, a);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) cga_bwd_kernel(CgaP p, CgaLay ly) {
+  extern __shared__ float sm[];
+  const int tid = threadIdx.x, Nt = p.Nt, NKV = ly.NKV, SP = ly.SP;
+  constexpr int cpg = CPG, cg = CG, hdc = HDC;
+  cga_load_weights(p, ly, sm);
+  const int nW = 3 * cpg * cg + 3 * cpg;
+  for (int idx = tid; idx < nW; idx += NT) sm[ly.odW + idx] = 0.f;
+  for (int idx = tid; idx < 2 * p.kb * cpg; idx += NT) sm[ly.odkb + idx] = 0.f;
+  __syncthreads();
+  const T* dout = static_cast<const T*>(p.dout);
+  float *X = sm + ly.oX, *Q = sm + ly.oQ, *K = sm + ly.oK, *V = sm + ly.oV, *P = sm + ly.oP, *dS = sm + ly.odS;
+  float *dO = sm + ly.odO, *dQ = sm + ly.odQ, *dK = sm + ly.odK, *dV = sm + ly.odV;
+  const float* W = sm + ly.oW;
+  float* dW = sm + ly.odW;
+  const float scale = rsqrtf((float)hdc);
+  for (int task = blockIdx.x; task < p.B * p.G; task += gridDim.x) {
+    const int b = task / p.G, g = task % p.G;
+    cga_project<T>(p, ly, sm, b, g);
+    for (int idx = tid; idx < NKV * cpg; idx += NT) { dK[idx] = 0.f; dV[idx] = 0.f; }
+    for (int q0 = 0; q0 < Nt; q0 += ly.QC) {
+      const int n = min(ly.QC, Nt - q0);
+      for (int idx = tid; idx < n * cpg; idx += NT) {
+        const int i = idx / cpg, o = idx % cpg;
+        dO[idx] = ldf(dout + ((long)b * Nt + q0 + i) * p.lddo + g * cpg + o);
+      }
+      cga_scores(p, ly, sm, q0, n);   // also orders the dO stores
+      for (int idx = tid; idx < NH * n * NKV; idx += NT) {
+        const int h = idx / (n * NKV), r = idx % (n * NKV), i = r / NKV, j = r % NKV;
+        float a = 0.f;
+        _Pragma("unroll") for (int d = 0; d < hdc; ++d) a = fmaf(dO[i * cpg + h * hdc + d], V[j * cpg + h * hdc + d], a);
+        dS[(h * ly.QC + i) * SP + j] = a;
+      }
+      __syncthreads();
+      {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int r = warp; r < NH * n; r += NT / 32) {
+          const int h = r / n, i = r % n;
+          float* ds = dS + (h * ly.QC + i) * SP;
+          const float* pr = P + (h * ly.QC + i) * SP;
+          float s = 0.f;
+          for (int j = lane; j < NKV; j += 32) s += ds[j] * pr[j];
+          s = warp_sum(s);
+          for (int j = lane; j < NKV; j += 32) ds[j] = pr[j] * (ds[j] - s) * scale;
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < n * cpg; idx += NT) {
+        const int i = idx / cpg, o = idx % cpg, h = o / hdc;
+        float a = 0.f;
+        for (int j = 0; j < NKV; ++j) a = fmaf(dS[(h * ly.QC + i) * SP + j], K[j * cpg + o], a);
+        dQ[(q0 + i) * cpg + o] = a;
+      }
+      for (int idx = tid; idx < NKV * cpg; idx += NT) {
+        const int j = idx / cpg, o = idx % cpg, h = o / hdc;
+        float av = 0.f, ak = 0.f;
+        for (int i = 0; i < n; ++i) {
+          av = fmaf(P[(h * ly.QC + i) * SP + j], dO[i * cpg + o], av);
+          ak = fmaf(dS[(h * ly.QC + i) * SP + j], Q[(q0 + i) * cpg + o], ak);
+        }
+        dV[idx] += av;
+        dK[idx] += ak;
+      }
+      __syncthreads();
+    }
+    // bank rows -> d(projected bank); own rows -> projections backward
+    for (int idx = tid; idx < p.kb * cpg; idx += NT) {
+      sm[ly.odkb + idx] += dK[Nt * cpg + idx];
+      sm[ly.odkb + p.kb * cpg + idx] += dV[Nt * cpg + idx];
+    }
+    // dx[n, c] += sum_o dq[n,o] Wq[o,c] + dk[n,o] Wk[o,c] + dv[n,o] Wv[o,c]
+    for (int idx = tid; idx < Nt * cg; idx += NT) {
+      const int n = idx / cg, c = idx % cg;
+      float a = 0.f;
+      for (int o = 0; o < cpg; ++o) {
+        a = fmaf(dQ[n * cpg + o], W[o * cg + c], a);
+        a = fmaf(dK[n * cpg + o], W[(cpg + o) * cg + c], a);
+        a = fmaf(dV[n * cpg + o], W[(2 * cpg + o) * cg + c], a);
+      }
+      p.dxn[((long)b * Nt + n) * p.lddx + g * cg + c] += a;
+    }
+    // dW[o, c] += sum_n d{q,k,v}[n, o] x[n, c] ; db[o] += sum_n d{q,k,v}[n, o]
+    for (int idx = tid; idx < 3 * cpg * cg; idx += NT) {
+      const int which = idx / (cpg * cg), r = idx % (cpg * cg), o = r / cg, c = r % cg;
+      const float* dsrc = which == 0 ? dQ : (which == 1 ? dK : dV);
+      float a = 0.f;
+      for (int n = 0; n < Nt; ++n) a = fmaf(dsrc[n * cpg + o], X[n * (cg + 1) + c], a);
+      dW[idx] += a;
+    }
+    for (int idx = tid; idx < 3 * cpg; idx += NT) {
+      const int which = idx / cpg, o = idx % cpg;
+      const float* dsrc = which == 0 ? dQ : (which == 1 ? dK : dV);
+      float a = 0.f;
+      for (int n = 0; n < Nt; ++n) a += dsrc[n * cpg + o];
+      dW[3 * cpg * cg + idx] += a;
+    }
+    __syncthreads();
+  }
+  const int n1 = cpg * cg;
+  for (int idx = tid; idx < n1; idx += NT) {
+    atomicAdd(p.dWq + idx, dW[idx]); atomicAdd(p.dWk + idx, dW[n1 + idx]); atomicAdd(p.dWv + idx, dW[2 * n1 + idx]);
+  }
+  for (int idx = tid; idx < cpg; idx += NT) {
+    atomicAdd(p.dbq + idx, dW[3 * n1 + idx]); atomicAdd(p.dbk + idx, dW[3 * n1 + cpg + idx]);
+    atomicAdd(p.dbv + idx, dW[3 * n1 + 2 * cpg + idx]);
+  }
+  for (int idx = tid; idx < p.kb * cpg; idx += NT) {
+    atomicAdd(p.dkbp + idx, sm[ly.odkb + idx]);
+    atomicAdd(p.dvbp + idx, sm[ly.odkb + p.kb * cpg + idx]);
+  }
+}
+
+CgaLay cga_layout(const CgaP& p, bool bwd) {
+  CgaLay ly{};
+  ly.NKV = p.Nt + p.kb;
+  ly.SP = ly.NKV + 1;
+  ly.QC = p.Nt < 32 ? p.Nt : 32;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  ly.oX = take(p.Nt * (p.cg + 1));
+  ly.oQ = take(p.Nt * p.cpg);
+  ly.oK = take(ly.NKV * p.cpg);
+  ly.oV = take(ly.NKV * p.cpg);
+  ly.oP = take(p.H * ly.QC * ly.SP);
+  ly.odS = take(bwd ? p.H * ly.QC * ly.SP : 0);
+  ly.odO = take(bwd ? ly.QC * p.cpg : 0);
+  ly.odQ = take(bwd ? p.Nt * p.cpg : 0);
+  ly.odK = take(bwd ? ly.NKV * p.cpg : 0);
+  ly.odV = take(bwd ? ly.NKV * p.cpg : 0);
+  ly.oW = take(3 * p.cpg * p.cg + 3 * p.cpg);
+  ly.odW = take(bwd ? 3 * p.cpg * p.cg + 3 * p.cpg : 0);
+  ly.odkb = take(bwd ? 2 * p.kb * p.cpg : 0);
+  ly.total = o;
+  return ly;
+}
+
+}  // namespace
+
+int cga_fwd(cudaStream_t s, int dt, const CgaP& p) {
+  if (p.B <= 0) return 0;
+  QV_CHECK(p.cg == 32 && p.cpg == 16 && p.H == 4, "CGA kernels are instantiated for 32 -> 16 channels per group and 4 heads (got %d -> %d, %d heads)", p.cg, p.cpg, p.H);
+  const CgaLay ly = cga_layout(p, false);
+  const size_t smem = (size_t)ly.total * sizeof(float);
+  const int occ = max(1, (int)(200 * 1024 / (smem + 1024)));
+  const int grid = min(p.B * p.G, qv_num_sms() * min(occ, 8));
+  if (dt == QV_F32) { QV_TRY(set_smem(cga_fwd_kernel<float>, smem)); cga_fwd_kernel<float><<<grid, NT, smem, s>>>(p, ly); }
+  else { QV_TRY(set_smem(cga_fwd_kernel<bf16>, smem)); cga_fwd_kernel<bf16><<<grid, NT, smem, s>>>(p, ly); }
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+int cga_bwd(cudaStream_t s, int dt, const CgaP& p) {
+  if (p.B <= 0) return 0;
+  QV_CHECK(p.cg == 32 && p.cpg == 16 && p.H == 4, "CGA kernels are instantiated for 32 -> 16 channels per group and 4 heads");
+  const CgaLay ly = cga_layout(p, true);
+  const size_t smem = (size_t)ly.total * sizeof(float);
+  const int occ = max(1, (int)(200 * 1024 / (smem + 1024)));
+  const int grid = min(p.B * p.G, qv_num_sms() * min(occ, 8));
+  if (dt == QV_F32) { QV_TRY(set_smem(cga_bwd_kernel<float>, smem)); cga_bwd_kernel<float><<<grid, NT, smem, s>>>(p, ly); }
+  else { QV_TRY(set_smem(cga_bwd_kernel<bf16>, smem)); cga_bwd_kernel<bf16><<<grid, NT, smem, s>>>(p, ly); }
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================
+// Bank projections: Y[rows, N] = X[rows, K] W^T + b with rows = 16 (batch invariant; the reference recomputes
+// them per image, H:617-619).  Single small grid, fp32.
+// =====================================================================================================
+namespace {
+__global__ void small_linear_fwd_kernel(const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * N) return;
+  const int r = idx / N, n = idx % N;
+  float a = b ? b[n] : 0.f;
+  for (int k = 0; k < K; ++k) a = fmaf(X[r * K + k], W[n * K + k], a);
+  Y[idx] = a;
+}
+// dW[n,k] += sum_r dY[r,n] X[r,k]; db[n] += sum_r dY[r,n]; dX[r,k] += sum_n dY[r,n] W[n,k]
+__global__ void small_linear_bwd_kernel(const float* X, int rows, int K, const float* W, int N, const float* dY,
+                                        float* dW, float* db, float* dX) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < N * K) {
+    const int n = idx / K, k = idx % K;
+    float a = 0.f;
+    for (int r = 0; r < rows; ++r) a = fmaf(dY[r * N + n], X[r * K + k], a);
+    dW[idx] += a;
+  }
+  if (idx < N) {
+    float a = 0.f;
+    for (int r = 0; r < rows; ++r) a += dY[r * N + idx];
+    db[idx] += a;
+  }
+  if (idx < rows * K) {
+    const int r = idx / K, k = idx % K;
+    float a = 0.f;
+    for (int n = 0; n < N; ++n) a = fmaf(dY[r * N + n], W[n * K + k], a);
+    dX[idx] += a;
+  }
+}
+}  // namespace
+
+int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
+  small_linear_fwd_kernel<<<cdiv(rows * N, 128), 128, 0, s>>>(X, rows, K, W, b, N, Y);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+int small_linear_bwd(cudaStream_t s, const float* X, int rows, int K, const float* W, int N, const float* dY, float* dW,
+                     float* db, float* dX_accum) {
+  const int n = max(N * K, rows * K);
+  small_linear_bwd_kernel<<<cdiv(n, 128), 128, 0, s>>>(X, rows, K, W, N, dY, dW, db, dX_accum);
+  QV_LAUNCH_CHECK();
+  return 0;
+}

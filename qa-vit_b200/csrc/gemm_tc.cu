@@ -126,76 +126,70 @@ struct NtArgs {
   int n_slices;    // ceil(N / BN)
   int m_tiles;
   uint32_t tmem_cols;
+  int stages;      // depth of the TMA ring (4; 3 for the widest tiles so staging still fits)
   GemmEpi e;
 };
 
-__device__ __forceinline__ void epilogue_store(const GemmEpi& e, long row, int col, const float* v, int ncols_valid,
-                                               float s_pre, float s_res) {
-  // v[0..15] -> columns col..col+15 of `row`
-  float val[16];
+// ---- epilogue staging.  tcgen05.ld hands every thread one accumulator ROW; writing rows straight to global memory
+// makes each warp store touch 32 different lines with 16 B each (measured: 4x the needed L2 write sectors, 9 % tensor
+// pipe).  Instead each epilogue warp stages 32 rows x 32 columns in shared memory and flushes them with row-contiguous,
+// sector-complete 16 B accesses; residual inputs come in the same way and the bias sits in shared memory.
+constexpr int EPI_GROUP = 32;                    // columns staged per pass
+constexpr int EPI_ROWB = 144;                    // staging row pitch in bytes (32 fp32 + 16 pad: conflict-free row writes)
+constexpr int EPI_WARP_BYTES = 2 * 32 * EPI_ROWB;
+
+__device__ __forceinline__ void stage_store16(uint8_t* rowp, int c, const float* val, bool f32) {
+  if (f32) {
+    float4* d = reinterpret_cast<float4*>(rowp + c * 64);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) val[j] = (v[j] + (e.bias ? e.bias[min(col + j, col + ncols_valid - 1)] : 0.f)) * s_pre;
-  if (e.C) {
-    if (e.c_f32) {
-      float* c = static_cast<float*>(e.C) + row * e.ldc + col;
-      if (ncols_valid == 16 && !e.c_accum) {
+    for (int j = 0; j < 4; ++j) d[j] = make_float4(val[4 * j], val[4 * j + 1], val[4 * j + 2], val[4 * j + 3]);
+  } else {
+    uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(val[j], val[j + 1], val[j + 2], val[j + 3]);
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(val[2 * j], val[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* d = reinterpret_cast<uint4*>(rowp + c * 32);
+    d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// staged [32 rows x gw cols] -> global, consecutive lanes on consecutive 16 B chunks of a row
+__device__ __forceinline__ void stage_flush(const uint8_t* st, void* C, long ldc, bool f32, bool accum, long row0, int M,
+                                            int col0, int gw, int lane) {
+  const int esz = f32 ? 4 : 2;
+  const int cpr = gw * esz / 16;                               // 16 B chunks per row: 2, 4 or 8
+  const int sh = (cpr == 8) ? 3 : (cpr == 4 ? 2 : 1);
+  uint8_t* base = static_cast<uint8_t*>(C);
+  for (int k = 0; k < cpr; ++k) {
+    const int idx = k * 32 + lane, r = idx >> sh, ch = idx & (cpr - 1);
+    const long row = row0 + r;
+    if (row < M) {
+      const uint4 v = *reinterpret_cast<const uint4*>(st + r * EPI_ROWB + ch * 16);
+      uint8_t* g = base + (row * ldc + col0) * esz + ch * 16;
+      if (accum) {
+        float4 o = *reinterpret_cast<float4*>(g);
+        o.x += __uint_as_float(v.x); o.y += __uint_as_float(v.y); o.z += __uint_as_float(v.z); o.w += __uint_as_float(v.w);
+        *reinterpret_cast<float4*>(g) = o;
       } else {
-        for (int j = 0; j < ncols_valid; ++j) c[j] = e.c_accum ? c[j] + val[j] : val[j];
-      }
-    } else {
-      bf16* c = static_cast<bf16*>(e.C) + row * e.ldc + col;
-      if (ncols_valid == 16) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(val[2 * j], val[2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        *reinterpret_cast<uint4*>(c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      } else {
-        for (int j = 0; j < ncols_valid; ++j) c[j] = __float2bfloat16_rn(val[j]);
+        *reinterpret_cast<uint4*>(g) = v;
       }
     }
   }
-  if (e.C2) {
-    float v2[16];
-    if (e.gelu) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v2[j] = gelu_f(val[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v2[j] = s_res * val[j];
-      if (e.resid) {
-        const float* r = e.resid + row * e.ldr + col;
-        for (int j = 0; j < ncols_valid; ++j) v2[j] += r[j];
-      }
-    }
-    if (e.c2_f32) {
-      float* c = static_cast<float*>(e.C2) + row * e.ldc2 + col;
-      if (ncols_valid == 16) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
-      } else {
-        for (int j = 0; j < ncols_valid; ++j) c[j] = v2[j];
-      }
-    } else {
-      bf16* c = static_cast<bf16*>(e.C2) + row * e.ldc2 + col;
-      if (ncols_valid == 16) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v2[2 * j], v2[2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        *reinterpret_cast<uint4*>(c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      } else {
-        for (int j = 0; j < ncols_valid; ++j) c[j] = __float2bfloat16_rn(v2[j]);
-      }
-    }
+}
+
+// fp32 global [32 rows x gw cols] -> staging (row-contiguous reads)
+__device__ __forceinline__ void stage_fill_f32(uint8_t* st, const float* R, long ldr, long row0, int M, int col0, int gw, int lane) {
+  const int cpr = gw / 4;                                      // 8 or 4
+  const int sh = (cpr == 8) ? 3 : 2;
+  for (int k = 0; k < cpr; ++k) {
+    const int idx = k * 32 + lane, r = idx >> sh, ch = idx & (cpr - 1);
+    const long row = row0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < M) v = *reinterpret_cast<const float4*>(R + row * ldr + col0 + ch * 4);
+    *reinterpret_cast<float4*>(st + r * EPI_ROWB + ch * 16) = v;
   }
 }
 
@@ -203,10 +197,13 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, NtArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int STG = p.stages;
   const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2, stage_bytes = a_bytes + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
-  uint64_t *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STG * stage_bytes);
+  uint64_t *full = bars, *empty = bars + STG, *tfull = bars + 2 * STG, *tempty = bars + 2 * STG + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STG + 4);
+  uint8_t* epi_stage = smem + STG * stage_bytes + 256;
+  float* bias_s = reinterpret_cast<float*>(epi_stage + 4 * EPI_WARP_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = (p.K + BK - 1) / BK;
@@ -215,10 +212,11 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
     fence_barrier_init();
   }
+  for (int j = threadIdx.x; j < p.BN; j += NTHREADS) bias_s[j] = (p.e.bias && n0 + j < p.N) ? p.e.bias[n0 + j] : 0.f;
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -237,7 +235,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           mbar_expect_tx(full + s, (uint32_t)stage_bytes);
           tma_load_2d(sa, &map_a, full + s, kb * BK, mt * BM);
           tma_load_2d(sa + a_bytes, &map_w, full + s, kb * BK, n0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == STG) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -264,7 +262,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
           umma_commit(empty + s);
           if (kb == kblocks - 1) umma_commit(tfull + acc);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
+          if (++s == STG) { s = 0; ph ^= 1; }
         }
         if (++acc == 2) { acc = 0; aph ^= 1; }
       }
@@ -275,17 +273,42 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const GemmEpi& e = p.e;
     const float s_pre = e.scale_pre ? *e.scale_pre : 1.f;
     const float s_res = e.scale_res ? *e.scale_res : 1.f;
+    uint8_t* st0 = epi_stage + (warp - 2) * EPI_WARP_BYTES;
+    uint8_t* st1 = st0 + 32 * EPI_ROWB;
+    const bool use_resid = e.C2 && !e.gelu && e.resid;
+    const int ncols = min(p.BN, p.N - n0);
     int acc = 0;
     uint32_t aph = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       mbar_wait(tfull + acc, aph);
       tc_fence_after();
-      const long row = (long)mt * BM + quarter * 32 + lane;
-      const int ncols = min(p.BN, p.N - n0);
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + c0), v);
-        if (row < p.M) epilogue_store(e, row, n0 + c0, v, min(16, ncols - c0), s_pre, s_res);
+      const long row0 = (long)mt * BM + quarter * 32;
+      for (int g = 0; g < ncols; g += EPI_GROUP) {
+        const int gw = min(EPI_GROUP, ncols - g);
+        if (use_resid) stage_fill_f32(st1, e.resid, e.ldr, row0, p.M, n0 + g, gw, lane);
+        __syncwarp();
+        for (int c = 0; c < gw / 16; ++c) {
+          float v[16], v2[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g + c * 16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = (v[j] + bias_s[g + c * 16 + j]) * s_pre;
+          if (e.C) stage_store16(st0 + lane * EPI_ROWB, c, v, e.c_f32 != 0);
+          if (e.C2) {
+            if (e.gelu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v2[j] = gelu_f(v[j]);
+            } else {
+              const float* rr = reinterpret_cast<const float*>(st1 + lane * EPI_ROWB) + c * 16;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v2[j] = s_res * v[j] + (use_resid ? rr[j] : 0.f);
+            }
+            stage_store16(st1 + lane * EPI_ROWB, c, v2, e.c2_f32 != 0);
+          }
+        }
+        __syncwarp();
+        if (e.C) stage_flush(st0, e.C, e.ldc, e.c_f32 != 0, e.c_accum != 0, row0, p.M, n0 + g, gw, lane);
+        if (e.C2) stage_flush(st1, e.C2, e.ldc2, e.c2_f32 != 0, false, row0, p.M, n0 + g, gw, lane);
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -449,7 +472,7 @@ int pick_bn(int N) {
 }  // namespace
 
 bool tc_shape_ok_nt(int M, int N, int K, int lda) {
-  return M >= 1 && N >= 16 && K >= 8 && K % 8 == 0 && lda % 8 == 0;
+  return M >= 1 && N >= 16 && N % 16 == 0 && K >= 8 && K % 8 == 0 && lda % 8 == 0;
 }
 bool tc_shape_ok_tn(int M, int N, int K, int ldy, int ldx) {
   return M >= 1 && N >= 8 && K >= 8 && K <= 256 && N % 8 == 0 && K % 8 == 0 && ldy % 8 == 0 && ldx % 8 == 0;
@@ -470,7 +493,13 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
   CUtensorMap ma, mw;
   QV_TRY(make_map(&ma, A, M, K, lda, BM));
   QV_TRY(make_map(&mw, Wb, N, K, K, p.BN));
-  const size_t smem = 1024 + (size_t)STAGES * (BM * BK * 2 + p.BN * BK * 2) + 256;
+  QV_CHECK((!e.C || (e.ldc % (e.c_f32 ? 4 : 8) == 0 && ((uintptr_t)e.C & 15) == 0)) &&
+               (!e.C2 || (e.ldc2 % (e.c2_f32 ? 4 : 8) == 0 && ((uintptr_t)e.C2 & 15) == 0)) &&
+               (!e.resid || (e.ldr % 4 == 0 && ((uintptr_t)e.resid & 15) == 0)),
+           "tc_gemm_nt: outputs / residual must be 16 B aligned with 16 B-multiple row pitch");
+  p.stages = p.BN > 208 ? 3 : STAGES;
+  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2) + 256 + 4 * EPI_WARP_BYTES + 1024;
+  QV_CHECK(smem <= 227 * 1024, "tc_gemm_nt: BN=%d needs %zu B of shared memory", p.BN, smem);
   QV_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gx = max(1, min(p.m_tiles, qv_num_sms() / p.n_slices));
   tc_gemm_nt_kernel<<<dim3(gx, p.n_slices), NTHREADS, smem, s>>>(ma, mw, p);
@@ -491,7 +520,9 @@ int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, 
   p.dW = dW;
   p.scale = scale;
   const int n_tiles = cdiv(N, BM);
-  int splits = max(1, min(p.mblocks, (2 * qv_num_sms()) / n_tiles));
+  // Every CTA ends with 128 x K fp32 atomics, so a CTA must own enough rows to amortise them: >= 16 m-blocks
+  // (1024 rows) each, and no more CTAs than SMs.
+  int splits = max(1, min(cdiv(p.mblocks, 16), qv_num_sms() / n_tiles));
   p.mb_per_cta = cdiv(p.mblocks, splits);
   splits = cdiv(p.mblocks, p.mb_per_cta);
   CUtensorMap my, mx;

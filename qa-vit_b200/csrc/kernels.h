@@ -54,6 +54,9 @@ bool tc_shape_ok_nt(int M, int N, int K, int lda);
 bool tc_shape_ok_tn(int M, int N, int K, int ldy, int ldx);
 int colsum_accum(cudaStream_t s, int dt, const void* dY, int ldy, int M, int N, float* db, const float* scale);
 int convert_weight(cudaStream_t s, const float* w, int N, int K, bf16* wb, bf16* wbt);
+struct ConvertJob { const float* w; int N, K; bf16* wb; bf16* wbt; };
+struct ConvertJobs { ConvertJob j[24]; int n; };
+int convert_weights_batched(cudaStream_t s, const ConvertJobs& jobs);   // all fp32 -> bf16 (+ transposed) copies, one launch
 
 // ---- norms
 int ln_fwd(cudaStream_t s, int dt_in, const void* x, int ldx, int rows, int C, const float* gamma, const float* beta,

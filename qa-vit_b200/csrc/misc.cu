@@ -52,24 +52,43 @@ __global__ void bank_write_reduce_kernel(const T* __restrict__ tn, const T* __re
   }
 }
 
-// mean over batch -> clamp -> bank += rate * u -> clamp -> update_count += 1.  Single CTA.
-__global__ void bank_write_apply_kernel(const float* __restrict__ partial, int n_partial, int B, int n,
-                                        float* __restrict__ bank_k, float* __restrict__ bank_v,
-                                        long long* __restrict__ update_count, int v1) {
+// mean over batch -> clamp -> bank += rate * u -> clamp -> update_count += 1.  One thread per bank element, the
+// partials are summed in a fixed order (deterministic); the last CTA to finish bumps the write counter, which every
+// CTA has read before taking its ticket.
+__device__ unsigned int g_bank_ticket = 0;
+__global__ void __launch_bounds__(256) bank_write_apply_kernel(const float* __restrict__ partial, int n_partial, int B,
+                                                               int n, float* __restrict__ bank_k,
+                                                               float* __restrict__ bank_v,
+                                                               long long* __restrict__ update_count, int v1) {
   float uclamp, rate, bclamp;
   if (v1) { uclamp = 0.1f; rate = 0.01f; bclamp = 1.0f; }                    // QAViT.py:217-224
   else { uclamp = 0.05f; bclamp = 0.5f; rate = (*update_count < 1000) ? 0.005f : 0.01f; }   // H:310-319
-  __syncthreads();
   const float invB = 1.f / (float)B;
-  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
-    float s = 0.f;
-    for (int p = 0; p < n_partial; ++p) s += partial[(long)p * 2 * n + i];
-    float u = fminf(fmaxf(s * invB, -uclamp), uclamp);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * n) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int p = 0;
+    for (; p + 4 <= n_partial; p += 4) {
+      s0 += partial[(long)p * 2 * n + i];
+      s1 += partial[(long)(p + 1) * 2 * n + i];
+      s2 += partial[(long)(p + 2) * 2 * n + i];
+      s3 += partial[(long)(p + 3) * 2 * n + i];
+    }
+    for (; p < n_partial; ++p) s0 += partial[(long)p * 2 * n + i];
+    const float u = fminf(fmaxf(((s0 + s1) + (s2 + s3)) * invB, -uclamp), uclamp);
     float* dst = (i < n) ? bank_k + i : bank_v + (i - n);
     *dst = fminf(fmaxf(*dst + rate * u, -bclamp), bclamp);
   }
+  if (v1) return;
   __syncthreads();
-  if (!v1 && threadIdx.x == 0) *update_count += 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&g_bank_ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *update_count += 1;
+      g_bank_ticket = 0;
+    }
+  }
 }
 }  // namespace
 
@@ -77,7 +96,7 @@ int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, in
                       float* partial, int* n_partial) {
   QV_CHECK(kb == 16, "bank write kernel is instantiated for bank size 16 (got %d)", kb);
   QV_CHECK(d <= 256, "bank write: d=%d > 256", d);
-  const int grid = min(B, min(320, qv_num_sms() * 2));
+  const int grid = min(cdiv(B, 4), min(320, qv_num_sms() * 2));   // >= 4 images per CTA: fewer partials to re-read
   *n_partial = grid;
   const size_t smem = (size_t)Nt * kb * sizeof(float);
   DISPATCH_T(dt, (bank_write_reduce_kernel<T, 16><<<grid, 256, smem, s>>>((const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
@@ -87,7 +106,7 @@ int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, in
 
 int bank_write_apply(cudaStream_t s, const float* partial, int n_partial, int B, int d, int kb, float* bank_k,
                      float* bank_v, long long* update_count, int v1) {
-  bank_write_apply_kernel<<<1, 1024, 0, s>>>(partial, n_partial, B, kb * d, bank_k, bank_v, update_count, v1);
+  bank_write_apply_kernel<<<cdiv(2 * kb * d, 256), 256, 0, s>>>(partial, n_partial, B, kb * d, bank_k, bank_v, update_count, v1);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -363,6 +382,15 @@ __global__ void convert_weight_kernel(const float* __restrict__ w, int N, int K,
   if (wb) wb[idx] = v;
   if (wbt) wbt[(long)(idx % K) * N + idx / K] = v;
 }
+__global__ void convert_weights_batched_kernel(ConvertJobs jobs) {
+  const ConvertJob jb = jobs.j[blockIdx.y];
+  const int total = jb.N * jb.K;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const bf16 v = __float2bfloat16_rn(jb.w[idx]);
+    jb.wb[idx] = v;
+    if (jb.wbt) jb.wbt[(long)(idx % jb.K) * jb.N + idx / jb.K] = v;
+  }
+}
 int ew_grid(long n) { return (int)max(1L, min((long)qv_num_sms() * 8, (n / 2 + 255) / 256)); }
 }  // namespace
 
@@ -411,6 +439,12 @@ int colsum_accum(cudaStream_t s, int dt, const void* dY, int ldy, int M, int N, 
   const int rpb = cdiv(M, gy);
   gy = cdiv(M, rpb);
   DISPATCH_T(dt, (colsum_kernel<T><<<dim3(gx, gy), dim3(32, 8), 0, s>>>((const T*)dY, ldy, M, N, rpb, db, scale)));
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int convert_weights_batched(cudaStream_t s, const ConvertJobs& jobs) {
+  if (jobs.n <= 0) return 0;
+  convert_weights_batched_kernel<<<dim3(32, jobs.n), 256, 0, s>>>(jobs);
   QV_LAUNCH_CHECK();
   return 0;
 }

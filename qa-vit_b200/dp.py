@@ -44,9 +44,15 @@ class GradAllReducer:
         self._stream = torch.cuda.Stream() if torch.cuda.is_available() else None
         self._handles = []
         self._hooks = []
+        self._pindex = {id(p): i for i, p in enumerate(params)}
         if self.world > 1:
             for i, p in enumerate(params):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+            try:        # parameters whose gradients the native kernels accumulate in place announce themselves here
+                from . import functional as QF
+                QF.register_grad_ready_callback(self._on_native_ready)
+            except Exception:      # pragma: no cover  (CPU-only unit tests of the bucket logic)
+                pass
         self.reset()
 
     def reset(self):
@@ -55,6 +61,8 @@ class GradAllReducer:
         for bi, (lo, hi, _) in enumerate(self.buckets):
             self._pending[bi] = sum(1 for i in range(lo, hi) if flags is None or int(flags[i]) & 1)
         self._handles = []
+        self._seen = set()
+        self._multi = {id(p) for p in self.bank_params}
 
     def _make_hook(self, i):
         def hook(_p):
@@ -63,6 +71,21 @@ class GradAllReducer:
             if self._pending[bi] == 0:
                 self._launch(bi)
         return hook
+
+    def _on_native_ready(self, params):
+        for p in params:
+            i = self._pindex.get(id(p))
+            if i is None:
+                continue
+            bi = self._param_bucket[i]
+            if p in self._seen:            # shared parameters (the bank) are reported by every block: count once,
+                continue                   # when the LAST user has run -- handled by finish() for those
+            self._seen.add(p)
+            if id(p) in self._multi:
+                continue
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._launch(bi)
 
     def _launch(self, bi):
         buf = self.buckets[bi][2]

@@ -44,6 +44,46 @@ def resolve_dtype(precision: str) -> int:
     return {"fp32": 0, "bf16": 1}[precision]
 
 
+_grad_ready_callbacks = []
+
+
+def register_grad_ready_callback(fn):
+    """fn(list_of_parameters) is called at the end of every native backward with the parameters whose gradients were
+    accumulated IN PLACE into an already-attached .grad (autograd's post-accumulate hooks do not fire for those)."""
+    _grad_ready_callbacks.append(fn)
+    return fn
+
+
+def unregister_grad_ready_callback(fn):
+    if fn in _grad_ready_callbacks:
+        _grad_ready_callbacks.remove(fn)
+
+
+def _inplace_target(t: torch.Tensor) -> Optional[torch.Tensor]:
+    """The attached gradient buffer of a leaf parameter, if the kernels can accumulate straight into it."""
+    g = getattr(t, "grad", None)
+    if g is not None and t.is_leaf and g.dtype == torch.float32 and g.is_contiguous() and g.device == t.device:
+        return g
+    return None
+
+
+def _notify(params):
+    if params and _grad_ready_callbacks:
+        for fn in list(_grad_ready_callbacks):
+            fn(params)
+
+
+def _grad_out(t: torch.Tensor, direct: list):
+    """(buffer the kernel accumulates into, value to return to autograd).  With .grad attached (FusedAdamW's flat
+    buffer) the kernel adds in place and autograd gets None: no add kernel, no copy."""
+    g = _inplace_target(t)
+    if g is not None:
+        direct.append(t)
+        return g, None
+    z = torch.zeros_like(t, dtype=torch.float32)
+    return z, z
+
+
 class BlockMeta:
     """Static description of one block call: the cfg struct and which tensor sits at which QP_* index."""
 
@@ -83,21 +123,36 @@ class QuadBlockFn(torch.autograd.Function):
         meta, x = ctx.meta, ctx.x
         cfg = meta.cfg
         dout = dout.float().contiguous()
+        # gradients accumulate straight into an attached .grad (flat optimizer buffer) when there is one; the rest
+        # share one zeroed flat allocation whose views are handed back to autograd.
         sizes: List[int] = []
+        direct: List[torch.Tensor] = []
+        targets: List[Optional[torch.Tensor]] = []
         for qi, t in zip(meta.index, ctx.tensors):
-            sizes.append(0 if qi in meta.no_grad else (t.numel() + 3) // 4 * 4)
-        gbuf = torch.zeros(sum(sizes), dtype=torch.float32, device=x.device)
+            if qi in meta.no_grad:
+                targets.append(None)
+                sizes.append(0)
+                continue
+            g = _inplace_target(t)
+            targets.append(g)
+            sizes.append(0 if g is not None else (t.numel() + 3) // 4 * 4)
+            if g is not None:
+                direct.append(t)
+        gbuf = torch.zeros(sum(sizes), dtype=torch.float32, device=x.device) if sum(sizes) else None
         grads_arr = (C.c_void_p * QP_COUNT)()
         views: List[Optional[torch.Tensor]] = []
         off = 0
-        for (qi, t), n in zip(zip(meta.index, ctx.tensors), sizes):
-            if n == 0:
+        for (qi, t), n, g in zip(zip(meta.index, ctx.tensors), sizes, targets):
+            if g is not None:
+                grads_arr[qi] = g.data_ptr()
                 views.append(None)
-                continue
-            v = gbuf[off:off + t.numel()].view(t.shape)
-            grads_arr[qi] = v.data_ptr()
-            views.append(v)
-            off += n
+            elif n == 0:
+                views.append(None)
+            else:
+                v = gbuf[off:off + t.numel()].view(t.shape)
+                grads_arr[qi] = v.data_ptr()
+                views.append(v)
+                off += n
         saved_b, scratch_b = C.c_size_t(0), C.c_size_t(0)
         check(lib.qavit_block_workspace(C.byref(cfg), C.byref(saved_b), C.byref(scratch_b)))
         scratch = _scratch_buf(x.device, scratch_b.value)
@@ -105,6 +160,7 @@ class QuadBlockFn(torch.autograd.Function):
         check(lib.qavit_block_backward(C.byref(cfg), ctx.params_arr, grads_arr, x.data_ptr(), dout.data_ptr(), dx.data_ptr(),
                                        ctx.saved_buf.data_ptr(), scratch.data_ptr(), _stream()))
         ctx.saved_buf = None
+        _notify(direct)
         return (dx, None, *views)
 
 
@@ -125,6 +181,7 @@ class PatchEmbedFn(torch.autograd.Function):
                                             ln_b.data_ptr(), _ptr(pos), pre.data_ptr(), stats.data_ptr(), out.data_ptr(),
                                             _stream()))
         ctx.save_for_backward(img, W, ln_w, pre, stats)
+        ctx.params = (W, bias, ln_w, ln_b, pos)
         ctx.has_pos = pos is not None
         ctx.pos_shape = None if pos is None else pos.shape
         return out
@@ -136,16 +193,15 @@ class PatchEmbedFn(torch.autograd.Function):
         d, _, p, _ = W.shape
         dout = dout.float().contiguous()
         dev = img.device
-        dW = torch.zeros_like(W)
-        db = torch.zeros(d, dtype=torch.float32, device=dev)
-        dg = torch.zeros(d, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
-        dpos = torch.zeros(ctx.pos_shape, dtype=torch.float32, device=dev) if ctx.has_pos else None
+        direct = []
+        (dW, rW), (db, rb), (dg, rg), (dbeta, rbeta) = (_grad_out(t, direct) for t in ctx.params[:4])
+        dpos, rpos = _grad_out(ctx.params[4], direct) if ctx.has_pos else (None, None)
         dpre = torch.empty_like(pre)
         check(lib.qavit_patch_embed_backward(img.data_ptr(), dout.data_ptr(), B, Cin, S, p, d, pre.data_ptr(), stats.data_ptr(),
                                              ln_w.data_ptr(), dpre.data_ptr(), dW.data_ptr(), db.data_ptr(), dg.data_ptr(),
                                              dbeta.data_ptr(), _ptr(dpos), _stream()))
-        return None, dW, db, dg, dbeta, dpos
+        _notify(direct)
+        return None, rW, rb, rg, rbeta, rpos
 
 
 class HeadFn(torch.autograd.Function):
@@ -163,6 +219,7 @@ class HeadFn(torch.autograd.Function):
         check(lib.qavit_head_forward(x.data_ptr(), B, N, d, ln_w.data_ptr(), ln_b.data_ptr(), W.data_ptr(), bias.data_ptr(), ncls,
                                      stats.data_ptr(), pooled.data_ptr(), logits.data_ptr(), _stream()))
         ctx.save_for_backward(x, ln_w, W, stats, pooled)
+        ctx.params = (ln_w, ln_b, W, bias)
         return logits
 
     @staticmethod
@@ -173,15 +230,48 @@ class HeadFn(torch.autograd.Function):
         dlogits = dlogits.float().contiguous()
         dev = x.device
         dx = torch.empty_like(x)
-        dg = torch.zeros(d, dtype=torch.float32, device=dev)
-        dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
-        dW = torch.zeros_like(W)
-        db = torch.zeros(ncls, dtype=torch.float32, device=dev)
+        direct = []
+        (dg, rg), (dbeta, rbeta), (dW, rW), (db, rb) = (_grad_out(t, direct) for t in ctx.params)
         dpooled = torch.empty_like(pooled)
         check(lib.qavit_head_backward(x.data_ptr(), dlogits.data_ptr(), B, N, d, ln_w.data_ptr(), stats.data_ptr(), pooled.data_ptr(),
                                       W.data_ptr(), ncls, dpooled.data_ptr(), dx.data_ptr(), dg.data_ptr(), dbeta.data_ptr(),
                                       dW.data_ptr(), db.data_ptr(), _stream()))
-        return dx, dg, dbeta, dW, db
+        _notify(direct)
+        return dx, rg, rbeta, rW, rb
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last axis (C <= 256) for the modules around the blocks; fp32 output like autocast."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        _require_cuda(x, "LayerNorm input")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.detach().contiguous()
+        C_ = x.shape[-1]
+        rows = x.numel() // C_
+        y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device)
+        check(lib.qavit_layer_norm_forward(x.data_ptr(), int(x.dtype == torch.bfloat16), rows, C_, w.data_ptr(), b.data_ptr(),
+                                           float(eps), y.data_ptr(), stats.data_ptr(), _stream()))
+        ctx.save_for_backward(x, w, stats)
+        ctx.params = (w, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, stats = ctx.saved_tensors
+        C_ = x.shape[-1]
+        rows = x.numel() // C_
+        dy = dy.float().contiguous()
+        dx = torch.empty_like(x)
+        direct = []
+        (dg, rg), (db, rb) = (_grad_out(t, direct) for t in ctx.params)
+        check(lib.qavit_layer_norm_backward(x.data_ptr(), int(x.dtype == torch.bfloat16), dy.data_ptr(), rows, C_, w.data_ptr(),
+                                            stats.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), _stream()))
+        _notify(direct)
+        return dx, rg, rb, None
 
 
 class CrossEntropyFn(torch.autograd.Function):

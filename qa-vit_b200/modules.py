@@ -386,13 +386,24 @@ class QAViT(_Base):
 
 
 # --------------------------------------------------------------------------------------------- HQAViT lateral path ("next" row f-1)
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm (same parameters / state_dict entries) whose CUDA forward + backward are the library's one-pass
+    warp-per-row kernels: torch's LayerNorm gamma/beta backward was 11 % of the first profiled step."""
+
+    def forward(self, x):
+        if x.is_cuda and self.normalized_shape[0] <= 256 and len(self.normalized_shape) == 1:
+            return QF.LayerNormFn.apply(x, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
+
 class ConvNeXtBlock(nn.Module):
     """H:718-739."""
 
     def __init__(self, dim, drop_path=0.):
         super().__init__()
         self.dwconv = nn.Conv2d(dim, dim, kernel_size=7, padding=3, groups=dim)
-        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.norm = LayerNorm(dim, eps=1e-6)
         self.pwconv1 = nn.Linear(dim, 4 * dim)
         self.act = nn.GELU()
         self.pwconv2 = nn.Linear(4 * dim, dim)
@@ -428,14 +439,14 @@ class LMFAdapter(nn.Module):
         self.dwconv_3x3 = nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels)
         self.dwconv_5x5 = nn.Conv2d(in_channels, in_channels, 5, padding=2, groups=in_channels)
         self.proj = nn.Conv2d(3 * in_channels, embed_dim, 1)
-        self.norm = nn.LayerNorm(embed_dim)
+        self.norm = LayerNorm(embed_dim)
         self.act = nn.GELU()
 
     def forward(self, feat):
         f = self.proj(torch.cat([self.dwconv_3x3(feat), self.dwconv_5x5(feat), feat], dim=1))
         if f.shape[2] != self.target_hw or f.shape[3] != self.target_hw:
             f = F.interpolate(f, size=(self.target_hw, self.target_hw), mode="bilinear", align_corners=False)
-        return self.act(self.norm(f.flatten(2).transpose(1, 2)))
+        return self.act(self.norm(f.permute(0, 2, 3, 1).reshape(f.shape[0], -1, f.shape[1])))   # NHWC view: no copy in channels_last
 
 
 class RRCV(nn.Module):
@@ -446,15 +457,15 @@ class RRCV(nn.Module):
         self.reverse_proj = nn.Conv2d(embed_dim, rec_channels, 1)
         self.blocks = nn.ModuleList([ConvNeXtBlock(rec_channels) for _ in range(num_blocks)])
         self.reembed_proj = nn.Conv2d(rec_channels, embed_dim, 1)
-        self.norm = nn.LayerNorm(embed_dim)
+        self.norm = LayerNorm(embed_dim)
         self.beta = nn.Parameter(torch.tensor(0.1))
 
     def forward(self, A, H: int, W: int):
         B, N, C = A.shape
-        r = self.reverse_proj(A.permute(0, 2, 1).reshape(B, C, H, W))
+        r = self.reverse_proj(A.reshape(B, H, W, C).permute(0, 3, 1, 2))   # tokens ARE the NHWC feature map: channels_last view, no copy
         for blk in self.blocks:
             r = blk(r)
-        r = self.reembed_proj(r).flatten(2).transpose(1, 2)
+        r = self.reembed_proj(r).permute(0, 2, 3, 1).reshape(B, N, C)
         return A + self.beta * self.norm(r)
 
 
@@ -463,11 +474,11 @@ class SplitFusion(nn.Module):
 
     def __init__(self, embed_dim: int):
         super().__init__()
-        self.gate_norm = nn.LayerNorm(embed_dim)
+        self.gate_norm = LayerNorm(embed_dim)
         self.gate_fc = nn.Linear(embed_dim, embed_dim)
-        self.cat_mlp = nn.Sequential(nn.Linear(2 * embed_dim, embed_dim), nn.LayerNorm(embed_dim), nn.GELU(), nn.Dropout(0.1))
+        self.cat_mlp = nn.Sequential(nn.Linear(2 * embed_dim, embed_dim), LayerNorm(embed_dim), nn.GELU(), nn.Dropout(0.1))
         self.fusion_weights = nn.Parameter(torch.tensor([0.75, 0.25]))
-        self.final_norm = nn.LayerNorm(embed_dim)
+        self.final_norm = LayerNorm(embed_dim)
 
     def forward(self, T_in, R):
         gate = torch.sigmoid(self.gate_fc(self.gate_norm(T_in + R)))
@@ -517,9 +528,13 @@ class HQAViT(_Base):
         self.head = nn.Linear(d, config.num_classes)
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
         self.apply(_init_weights)
+        for m in (self.cnn_stem, self.lmfa2, self.lmfa3, self.lmfa4, self.rrcv2, self.rrcv3, self.rrcv4):
+            m.to(memory_format=torch.channels_last)
 
     def forward(self, x):
-        f2, f3, f4 = self.cnn_stem(x)
+        # lateral CNN path in channels_last: cuDNN's NHWC depthwise / pointwise kernels are 1.7x faster here
+        # (measured, tools/lateral_probe.py); memory format does not change values or the state_dict.
+        f2, f3, f4 = self.cnn_stem(x.contiguous(memory_format=torch.channels_last) if x.is_cuda else x)
         R2 = self.rrcv2(self.lmfa2(f2), self.H, self.W)
         R3 = self.rrcv3(self.lmfa3(f3), self.H, self.W)
         R4 = self.rrcv4(self.lmfa4(f4), self.H, self.W)

@@ -106,19 +106,25 @@ class FusedAdamW(torch.optim.Optimizer):
                 g.copy_(p.grad)
                 p.grad = g
 
-    @torch.no_grad()
-    def step(self, closure=None):
+    def write_hyper(self):
+        """Advance the step counter and write this step's scalars (lr, betas, eps, wd, bias corrections) into the pinned
+        host buffer the step kernel's H2D copy reads -- the only per-step host work when the step is graph-replayed."""
         grp = self.param_groups[0]
-        self._gather_foreign_grads()
-        if not self._have_flags:
-            self._sync_flags()
         self.step_count += 1
         b1, b2 = grp["betas"]
         t = self.step_count
         h = self._hyper_host
         h[0], h[1], h[2], h[3], h[4] = grp["lr"], b1, b2, grp["eps"], grp["weight_decay"]
         h[5], h[6] = 1.0 - b1 ** t, 1.0 - b2 ** t
-        self.hyper.copy_(h, non_blocking=True)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        self._gather_foreign_grads()
+        if not self._have_flags:
+            self._sync_flags()
+        if not torch.cuda.is_current_stream_capturing():
+            self.write_hyper()
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
         check(lib.qavit_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                    self.seg_off.data_ptr(), self.seg_flags.data_ptr(), len(self.names), self.hyper.data_ptr(),
                                    self.total, _stream()))
