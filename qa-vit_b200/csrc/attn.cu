@@ -326,8 +326,10 @@ int launch_attn(cudaStream_t s, const AttnP& p) {
 }  // namespace
 
 int attn_fwd(cudaStream_t s, int dt, const AttnP& p) {
+  if (dt == QV_BF16 && attn_mma_ok(p)) return attn_mma_fwd(s, p);   // tensor-core path (attn_mma.cu)
   return dt == QV_F32 ? launch_attn<float, false>(s, p) : launch_attn<bf16, false>(s, p);
 }
 int attn_bwd(cudaStream_t s, int dt, const AttnP& p) {
+  if (dt == QV_BF16 && attn_mma_ok(p)) return attn_mma_bwd(s, p);
   return dt == QV_F32 ? launch_attn<float, true>(s, p) : launch_attn<bf16, true>(s, p);
 }

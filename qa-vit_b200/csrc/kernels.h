@@ -83,6 +83,9 @@ struct AttnP {
   float* dEk; float* dEv; float* dbank_k; float* dbank_v;   // fp32 accumulators (mode 2: dKc/dVc in dbank_k/v)
 };
 int attn_fwd(cudaStream_t s, int dt, const AttnP& p);
+bool attn_mma_ok(const AttnP& p);   // bf16 tensor-core (mma.sync) flavour for the 16-query shapes
+int attn_mma_fwd(cudaStream_t s, const AttnP& p);
+int attn_mma_bwd(cudaStream_t s, const AttnP& p);
 int attn_bwd(cudaStream_t s, int dt, const AttnP& p);
 
 struct CgaP {
@@ -97,6 +100,9 @@ struct CgaP {
 };
 int cga_fwd(cudaStream_t s, int dt, const CgaP& p);
 int cga_bwd(cudaStream_t s, int dt, const CgaP& p);
+bool cga_mma_ok(const CgaP& p);
+int cga_mma_fwd(cudaStream_t s, const CgaP& p);
+int cga_mma_bwd(cudaStream_t s, const CgaP& p);
 
 // small dense [rows<=64] projections of the bank: Y = X W^T + b and its backward (single CTA, fp32)
 int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y);
