@@ -291,7 +291,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step (the reference's 256 was sized for a "
+                    "6 GB laptop GPU; SURVEY.md 8d lists 256 / 1024 / 4096 / 16384 per GPU)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the step eagerly instead of as one CUDA graph")

@@ -97,6 +97,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// The wait names the destination registers as in/out operands so no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_wait16(float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                 "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
+
 // ---- descriptors
 // shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -118,7 +138,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 constexpr int BM = 128;       // output rows per tile (UMMA M)
 constexpr int BK = 64;        // k-block: 64 bf16 = 128 B = one SWIZZLE_128B span
 constexpr int STAGES = 4;
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 12;                  // 3 per TMEM lane quarter: one warp per SMSP cannot hide its own latencies
+constexpr int NTHREADS = 64 + EPI_WARPS * 32;   // NT kernel: TMA warp + MMA warp + epilogue warps
+constexpr int TN_THREADS = 192;                 // TN kernel: TMA warp + MMA warp + 4 epilogue warps
 
 struct NtArgs {
   int M, N, K;     // C[M, N], contraction K
@@ -136,7 +158,7 @@ struct NtArgs {
 // sector-complete 16 B accesses; residual inputs come in the same way and the bias sits in shared memory.
 constexpr int EPI_GROUP = 32;                    // columns staged per pass
 constexpr int EPI_ROWB = 144;                    // staging row pitch in bytes (32 fp32 + 16 pad: conflict-free row writes)
-constexpr int EPI_WARP_BYTES = 2 * 32 * EPI_ROWB;
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROWB;   // one staging buffer per warp, reused for residual-in, C and C2
 
 __device__ __forceinline__ void stage_store16(uint8_t* rowp, int c, const float* val, bool f32) {
   if (f32) {
@@ -196,14 +218,14 @@ __device__ __forceinline__ void stage_fill_f32(uint8_t* st, const float* R, long
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, NtArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int STG = p.stages;
   const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2, stage_bytes = a_bytes + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STG * stage_bytes);
   uint64_t *full = bars, *empty = bars + STG, *tfull = bars + 2 * STG, *tempty = bars + 2 * STG + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STG + 4);
   uint8_t* epi_stage = smem + STG * stage_bytes + 256;
-  float* bias_s = reinterpret_cast<float*>(epi_stage + 4 * EPI_WARP_BYTES);
+  float* bias_s = reinterpret_cast<float*>(epi_stage + EPI_WARPS * EPI_WARP_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = (p.K + BK - 1) / BK;
@@ -213,7 +235,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS); }
     fence_barrier_init();
   }
   for (int j = threadIdx.x; j < p.BN; j += NTHREADS) bias_s[j] = (p.e.bias && n0 + j < p.N) ? p.e.bias[n0 + j] : 0.f;
@@ -268,13 +290,14 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    // ================= epilogue warps (TMEM lane quarter = warp % 4)
-    const int quarter = warp & 3;
+    // ================= epilogue warps: TMEM lane quarter = warp % 4, column groups dealt round-robin to the 3 warps
+    // of a quarter
+    const int quarter = warp & 3, sub = (warp - 2) >> 2;
     const GemmEpi& e = p.e;
     const float s_pre = e.scale_pre ? *e.scale_pre : 1.f;
     const float s_res = e.scale_res ? *e.scale_res : 1.f;
-    uint8_t* st0 = epi_stage + (warp - 2) * EPI_WARP_BYTES;
-    uint8_t* st1 = st0 + 32 * EPI_ROWB;
+    uint8_t* st = epi_stage + (warp - 2) * EPI_WARP_BYTES;
+    uint8_t* my_row = st + lane * EPI_ROWB;
     const bool use_resid = e.C2 && !e.gelu && e.resid;
     const int ncols = min(p.BN, p.N - n0);
     int acc = 0;
@@ -283,32 +306,58 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_wait(tfull + acc, aph);
       tc_fence_after();
       const long row0 = (long)mt * BM + quarter * 32;
-      for (int g = 0; g < ncols; g += EPI_GROUP) {
-        const int gw = min(EPI_GROUP, ncols - g);
-        if (use_resid) stage_fill_f32(st1, e.resid, e.ldr, row0, p.M, n0 + g, gw, lane);
-        __syncwarp();
-        for (int c = 0; c < gw / 16; ++c) {
-          float v[16], v2[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g + c * 16), v);
+      for (int g = sub * EPI_GROUP; g < ncols; g += (EPI_WARPS / 4) * EPI_GROUP) {
+        const int gw = min(EPI_GROUP, ncols - g), nch = gw / 16;
+        float v[2][16], r[2][16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = (v[j] + bias_s[g + c * 16 + j]) * s_pre;
-          if (e.C) stage_store16(st0 + lane * EPI_ROWB, c, v, e.c_f32 != 0);
-          if (e.C2) {
-            if (e.gelu) {
+        for (int c = 0; c < 2; ++c)
+          if (c < nch) tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g + c * 16), v[c]);
+        if (use_resid) {
+          stage_fill_f32(st, e.resid, e.ldr, row0, p.M, n0 + g, gw, lane);
+          __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v2[j] = gelu_f(v[j]);
-            } else {
-              const float* rr = reinterpret_cast<const float*>(st1 + lane * EPI_ROWB) + c * 16;
+          for (int c = 0; c < 2; ++c)
+            if (c < nch) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v2[j] = s_res * v[j] + (use_resid ? rr[j] : 0.f);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(my_row + (c * 16 + j) * 4);
+                r[c][j] = q.x; r[c][j + 1] = q.y; r[c][j + 2] = q.z; r[c][j + 3] = q.w;
+              }
             }
-            stage_store16(st1 + lane * EPI_ROWB, c, v2, e.c2_f32 != 0);
-          }
+          __syncwarp();
         }
-        __syncwarp();
-        if (e.C) stage_flush(st0, e.C, e.ldc, e.c_f32 != 0, e.c_accum != 0, row0, p.M, n0 + g, gw, lane);
-        if (e.C2) stage_flush(st1, e.C2, e.ldc2, e.c2_f32 != 0, false, row0, p.M, n0 + g, gw, lane);
-        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          if (c < nch) {
+            tmem_ld_wait16(v[c]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[c][j] = (v[c][j] + bias_s[g + c * 16 + j]) * s_pre;
+          }
+        if (e.C) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (c < nch) stage_store16(my_row, c, v[c], e.c_f32 != 0);
+          __syncwarp();
+          stage_flush(st, e.C, e.ldc, e.c_f32 != 0, e.c_accum != 0, row0, p.M, n0 + g, gw, lane);
+          __syncwarp();
+        }
+        if (e.C2) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (c < nch) {
+              if (e.gelu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[c][j] = gelu_f(v[c][j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[c][j] = s_res * v[c][j] + (use_resid ? r[c][j] : 0.f);
+              }
+              stage_store16(my_row, c, v[c], e.c2_f32 != 0);
+            }
+          __syncwarp();
+          stage_flush(st, e.C2, e.ldc2, e.c2_f32 != 0, false, row0, p.M, n0 + g, gw, lane);
+          __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -333,7 +382,7 @@ struct TnArgs {
   const float* scale;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(TN_THREADS, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, TnArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -498,7 +547,7 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
                (!e.resid || (e.ldr % 4 == 0 && ((uintptr_t)e.resid & 15) == 0)),
            "tc_gemm_nt: outputs / residual must be 16 B aligned with 16 B-multiple row pitch");
   p.stages = p.BN > 208 ? 3 : STAGES;
-  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2) + 256 + 4 * EPI_WARP_BYTES + 1024;
+  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2) + 256 + EPI_WARPS * EPI_WARP_BYTES + 1024;
   QV_CHECK(smem <= 227 * 1024, "tc_gemm_nt: BN=%d needs %zu B of shared memory", p.BN, smem);
   QV_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gx = max(1, min(p.m_tiles, qv_num_sms() / p.n_slices));
@@ -531,7 +580,7 @@ int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, 
   const size_t smem = 1024 + (size_t)STAGES * (2 + p.kboxes) * (64 * 64 * 2) + 256;
   QV_CHECK(smem <= 227 * 1024, "tc_gemm_tn: K=%d needs %zu B smem", K, smem);
   QV_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_gemm_tn_kernel<<<dim3(n_tiles, splits), NTHREADS, smem, s>>>(my, mx, p);
+  tc_gemm_tn_kernel<<<dim3(n_tiles, splits), TN_THREADS, smem, s>>>(my, mx, p);
   QV_LAUNCH_CHECK();
   return 0;
 }
