@@ -229,7 +229,7 @@ void layout_scratch(const Dims& D, Scratch* S) {
     S->tl_logits = b.take(D.tl ? Rf * D.Nt * ts : 0);
     S->tn = b.take(R * d * ts);
     S->cgbuf = b.take(R * (d + D.kb) * ts);
-    S->partial = b.take((size_t)320 * 2 * D.kb * d * 4);   // bank_write_reduce uses <= 320 CTAs
+    S->partial = b.take((size_t)592 * 2 * D.kb * d * 4);   // bank_write_reduce uses <= 592 CTAs
     S->total_fwd = b.off;
   }
   {
@@ -719,11 +719,11 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
 
   // ---- TokenLearner backward
   if (D.tl) {
-    QV_TRY(token_learner_bwd(st, dt, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, D.Nt, d, c.sc(X.d_logits), dx));
+    QV_TRY(token_learner_bwd(st, dt, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, D.Nt, d, c.sc(X.d_logits), c.scf(X.d_up)));   // d_up is free again
     QV_TRY(gemm_tn(st, dt, c.sc(X.d_logits), D.Nt, c.sv(S.tl_ln), d, D.Rf, D.Nt, d, G(QP_TL_FC_W), G(QP_TL_FC_B), nullptr));
     QV_TRY(gemm_nn(st, dt, c.sc(X.d_logits), D.Nt, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)), epi_t(c, nullptr, c.sc(X.d_tl_ln), d)));
     QV_TRY(ln_bwd(st, QV_F32, x_in, d, dt, c.sc(X.d_tl_ln), d, D.Rf, d, c.pf(QP_TL_LN_W), c.svf(S.tl_stats), 0, QV_F32, nullptr, dx,
-                  dx, G(QP_TL_LN_W), G(QP_TL_LN_B)));
+                  c.scf(X.d_up), G(QP_TL_LN_W), G(QP_TL_LN_B)));
   }
   return 0;
 }

@@ -140,6 +140,12 @@ int token_upmix_fwd(cudaStream_t s, const float* xc, int B, int M, int N, int C,
                     float* up);
 int token_upmix_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int M, int N, int C, const float* W,
                     float* dxc, float* dW, float* dbias);
+// register-blocked flavours for 16 learned tokens (tokens.cu)
+bool tokens16_ok(int M, int C);
+int tl16_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, int N, int C, float* S, float* xc);
+int tl16_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx);
+int up16_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W, const float* bias, float* up);
+int up16_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int C, const float* W, float* dxc, float* dW, float* dbias);
 int patch_embed_fwd(cudaStream_t s, const float* img, int B, int Cin, int S, int p, int d, const float* W,
                     const float* bias, const float* gamma, const float* beta, const float* pos, float* pre, float* stats,
                     float* out);

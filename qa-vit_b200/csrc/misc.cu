@@ -37,11 +37,22 @@ __global__ void bank_write_reduce_kernel(const T* __restrict__ tn, const T* __re
     }
     __syncthreads();
     if (c < d) {
-      for (int n = 0; n < Nt; ++n) {
-        const float cv = ldf(cg + ((long)b * Nt + n) * ldcg + c);
-        const float tv = ldf(tn + ((long)b * Nt + n) * d + c);
+      // loads are independent: issue 8 tokens' worth before the FMAs (the kernel is latency-bound otherwise)
+      for (int n0 = 0; n0 < Nt; n0 += 8) {
+        float cv[8], tv[8];
 #pragma unroll
-        for (int s = 0; s < KB; ++s) { ak[s] = fmaf(g[n * KB + s], cv, ak[s]); av[s] = fmaf(g[n * KB + s], tv, av[s]); }
+        for (int k = 0; k < 8; ++k) {
+          const int n = min(n0 + k, Nt - 1);
+          cv[k] = ldf(cg + ((long)b * Nt + n) * ldcg + c);
+          tv[k] = ldf(tn + ((long)b * Nt + n) * d + c);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (n0 + k < Nt) {
+#pragma unroll
+            for (int s = 0; s < KB; ++s) { ak[s] = fmaf(g[(n0 + k) * KB + s], cv[k], ak[s]); av[s] = fmaf(g[(n0 + k) * KB + s], tv[k], av[s]); }
+          }
+        }
       }
     }
   }
@@ -96,7 +107,7 @@ int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, in
                       float* partial, int* n_partial) {
   QV_CHECK(kb == 16, "bank write kernel is instantiated for bank size 16 (got %d)", kb);
   QV_CHECK(d <= 256, "bank write: d=%d > 256", d);
-  const int grid = min(cdiv(B, 4), min(320, qv_num_sms() * 2));   // >= 4 images per CTA: fewer partials to re-read
+  const int grid = min(cdiv(B, 4), min(592, qv_num_sms() * 4));   // >= 4 images per CTA; 4 CTAs / SM for latency hiding
   *n_partial = grid;
   const size_t smem = (size_t)Nt * kb * sizeof(float);
   DISPATCH_T(dt, (bank_write_reduce_kernel<T, 16><<<grid, 256, smem, s>>>((const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
@@ -611,6 +622,7 @@ int opt_in_smem(K kernel, size_t bytes) {
 int token_learner_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, int N, int M, int C, float* S,
                       float* xc) {
   if (B <= 0) return 0;
+  if (tokens16_ok(M, C)) return tl16_fwd(s, dt, x, logits, B, N, C, S, xc);
   QV_CHECK(M % 16 == 0, "token_learner: M=%d must be a multiple of 16", M);
   const size_t smem = (size_t)N * M * sizeof(float);
   const int grid = min(B, qv_num_sms() * 8);
@@ -622,6 +634,7 @@ int token_learner_fwd(cudaStream_t s, int dt, const float* x, const void* logits
 int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float* dxc, int B, int N, int M,
                       int C, void* dlogits, float* dx) {
   if (B <= 0) return 0;
+  if (tokens16_ok(M, C)) return tl16_bwd(s, dt, x, S, dxc, B, N, C, dlogits, dx);
   QV_CHECK(C <= 256, "token_learner_bwd: C=%d > 256", C);
   const size_t smem = (size_t)(2 * N * M + M * (C + 1) + M) * sizeof(float);
   const int grid = min(B, qv_num_sms() * 4);
@@ -632,6 +645,7 @@ int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, co
 }
 int token_upmix_fwd(cudaStream_t s, const float* xc, int B, int M, int N, int C, const float* W, const float* bias, float* up) {
   if (B <= 0) return 0;
+  if (tokens16_ok(M, C)) return up16_fwd(s, xc, B, N, C, W, bias, up);
   const size_t smem = (size_t)(N * M + M * C) * sizeof(float);
   QV_TRY(opt_in_smem(token_upmix_fwd_kernel, smem));
   token_upmix_fwd_kernel<<<min(B, qv_num_sms() * 4), 192, smem, s>>>(xc, B, M, N, C, W, bias, up);
@@ -641,6 +655,7 @@ int token_upmix_fwd(cudaStream_t s, const float* xc, int B, int M, int N, int C,
 int token_upmix_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int M, int N, int C, const float* W,
                     float* dxc, float* dW, float* dbias) {
   if (B <= 0) return 0;
+  if (tokens16_ok(M, C)) return up16_bwd(s, xc, dup, B, N, C, W, dxc, dW, dbias);
   QV_CHECK(N % 16 == 0, "token_upmix_bwd: N=%d must be a multiple of 16", N);
   const size_t smem = (size_t)(N * M + M * (C + 1) + 16 * (C + 1)) * sizeof(float);
   QV_TRY(opt_in_smem(token_upmix_bwd_kernel, smem));

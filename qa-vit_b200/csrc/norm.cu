@@ -1,124 +1,161 @@
-// LayerNorm forward / backward: one warp per row, row held in registers (C <= 256, C even),
-// two-pass statistics in fp32.  HBM-bound kernels: algorithmic bytes = rows*C*(in + out) (+8 B/row stats).
+// LayerNorm forward / backward: one warp per row, the row held in registers, two-pass statistics in fp32.
+// Every lane owns EPL contiguous channels (8 when C > 128, else 4) so all global traffic is 8 / 16 B vectors
+// (C <= 256, C % EPL == 0).  HBM-bound: algorithmic bytes = rows * C * (in + out) (+ 8 B/row of statistics).
 //   gelu_in : the LN input is gelu(x) of the stored pre-activation x (CCF-FFN fc1 -> GELU -> LN, H:704-706)
 //   chain   : y = LN2(LN1(x))  (branch .norm followed by bank write_norm, H:468 + H:301)
 #include "kernels.h"
 
 namespace {
 
-constexpr int MAXV = 8;  // values per lane (C <= 256)
+template <int EPL>
+__device__ __forceinline__ void load_vec(const float* p, float* v) {
+#pragma unroll
+  for (int i = 0; i < EPL; i += 4) {
+    const float4 q = *reinterpret_cast<const float4*>(p + i);
+    v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void load_vec(const bf16* p, float* v) {
+  if (EPL == 8) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  } else {
+    const uint2 q = *reinterpret_cast<const uint2*>(p);
+    const uint32_t w[2] = {q.x, q.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void store_vec(float* p, const float* v) {
+#pragma unroll
+  for (int i = 0; i < EPL; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+template <int EPL>
+__device__ __forceinline__ void store_vec(bf16* p, const float* v) {
+  uint32_t w[EPL / 2];
+#pragma unroll
+  for (int i = 0; i < EPL / 2; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  if (EPL == 8) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[EPL / 2 - 1]);
+}
 
-template <typename TI, typename TO, bool GELU_IN>
+template <typename TI, typename TO, int EPL, bool GELU_IN>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, int ldx, int rows, int C,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, const float* __restrict__ gamma2,
                                                      const float* __restrict__ beta2, TO* __restrict__ y, int ldy,
                                                      float* __restrict__ stats) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const int nper = (C + 31) / 32;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int c0 = lane * EPL;
+  const bool act = c0 < C;
   const float invC = 1.f / (float)C;
+  float gm[EPL], bt[EPL], gm2[EPL], bt2[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) { gm[i] = bt[i] = gm2[i] = bt2[i] = 0.f; }
+  if (act) {
+    load_vec<EPL>(gamma + c0, gm);
+    load_vec<EPL>(beta + c0, bt);
+    if (gamma2) { load_vec<EPL>(gamma2 + c0, gm2); load_vec<EPL>(beta2 + c0, bt2); }
+  }
   for (long row = (long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long)gridDim.x * wpb) {
-    float v[MAXV];
+    float v[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) v[i] = 0.f;
+    if (act) load_vec<EPL>(x + row * ldx + c0, v);
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + i * 32;
-      v[i] = 0.f;
-      if (i < nper && c < C) {
-        float t = ldf(x + row * ldx + c);
-        if (GELU_IN) t = gelu_f(t);
-        v[i] = t;
-        s += t;
-      }
-    }
+    for (int i = 0; i < EPL; ++i) { if (GELU_IN) v[i] = gelu_f(v[i]); s += v[i]; }
     const float mean = warp_sum(s) * invC;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + i * 32;
-      if (i < nper && c < C) { const float d = v[i] - mean; q += d * d; }
-    }
+    for (int i = 0; i < EPL; ++i) { const float d = act ? v[i] - mean : 0.f; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) * invC + eps);
     if (stats && lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + i * 32;
-      if (i < nper && c < C) v[i] = (v[i] - mean) * rstd * gamma[c] + beta[c];
-    }
-    if (gamma2) {  // chained second LayerNorm (no stats kept: the write path has no backward)
+    for (int i = 0; i < EPL; ++i) v[i] = (v[i] - mean) * rstd * gm[i] + bt[i];
+    if (gamma2) {  // chained second LayerNorm (no statistics kept: the bank write path has no backward)
       float s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) { const int c = lane + i * 32; if (i < nper && c < C) s2 += v[i]; }
+      for (int i = 0; i < EPL; ++i) s2 += act ? v[i] : 0.f;
       const float m2 = warp_sum(s2) * invC;
       float q2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) { const int c = lane + i * 32; if (i < nper && c < C) { const float d = v[i] - m2; q2 += d * d; } }
+      for (int i = 0; i < EPL; ++i) { const float d = act ? v[i] - m2 : 0.f; q2 += d * d; }
       const float r2 = rsqrtf(warp_sum(q2) * invC + eps);
 #pragma unroll
-      for (int i = 0; i < MAXV; ++i) { const int c = lane + i * 32; if (i < nper && c < C) v[i] = (v[i] - m2) * r2 * gamma2[c] + beta2[c]; }
+      for (int i = 0; i < EPL; ++i) v[i] = (v[i] - m2) * r2 * gm2[i] + bt2[i];
     }
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + i * 32;
-      if (i < nper && c < C) stf(y + row * ldy + c, v[i]);
-    }
+    if (act) store_vec<EPL>(y + row * ldy + c0, v);
   }
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) [+ resid],  g = dy * gamma;  dgamma += dy * xhat, dbeta += dy.
-// dx is written as T (dx_t) and/or fp32 (dx_f32); resid may alias dx_f32 (same element, same thread).
-template <typename TX, typename TDY, typename TO, bool GELU_IN>
+// dx is written as T (dx_t) and / or fp32 (dx_f32).  resid must not alias an output.
+template <typename TX, typename TDY, typename TO, int EPL, bool GELU_IN>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const TX* __restrict__ x, int ldx, const TDY* __restrict__ dy,
                                                      int lddy, int rows, int C, const float* __restrict__ gamma,
                                                      const float* __restrict__ stats, TO* __restrict__ dx_t,
-                                                     float* dx_f32, const float* resid,
+                                                     float* __restrict__ dx_f32, const float* __restrict__ resid,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float red[2][8][256];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  const int nper = (C + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int c0 = lane * EPL;
+  const bool act = c0 < C;
   const float invC = 1.f / (float)C;
-  float ag[MAXV], ab[MAXV];
+  float gm[EPL], ag[EPL], ab[EPL];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) ag[i] = ab[i] = 0.f;
+  for (int i = 0; i < EPL; ++i) gm[i] = ag[i] = ab[i] = 0.f;
+  if (act) load_vec<EPL>(gamma + c0, gm);
   for (long row = (long)blockIdx.x * wpb + warp; row < rows; row += (long)gridDim.x * wpb) {
-    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-    float xh[MAXV], g[MAXV], u[MAXV];
-    float s1 = 0.f, s2 = 0.f;
+    float xv[EPL], dv[EPL], rs[EPL];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + i * 32;
-      xh[i] = g[i] = u[i] = 0.f;
-      if (i < nper && c < C) {
-        float t = ldf(x + row * ldx + c);
-        if (GELU_IN) { u[i] = t; t = gelu_f(t); }
-        const float d = ldf(dy + row * lddy + c);
-        xh[i] = (t - mean) * rstd;
-        g[i] = d * gamma[c];
-        ag[i] += d * xh[i];
-        ab[i] += d;
-        s1 += g[i];
-        s2 += g[i] * xh[i];
-      }
+    for (int i = 0; i < EPL; ++i) xv[i] = dv[i] = rs[i] = 0.f;
+    if (act) {
+      load_vec<EPL>(x + row * ldx + c0, xv);
+      load_vec<EPL>(dy + row * lddy + c0, dv);
+      if (resid) load_vec<EPL>(resid + row * C + c0, rs);
     }
-    const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float s1 = 0.f, s2 = 0.f, u[EPL];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = lane + i * 32;
-      if (i < nper && c < C) {
-        float d = rstd * (g[i] - c1 - xh[i] * c2);
-        if (GELU_IN) d *= gelu_grad_f(u[i]);
-        if (resid) d += resid[row * C + c];
-        if (dx_t) stf(dx_t + row * C + c, d);
-        if (dx_f32) dx_f32[row * C + c] = d;
-      }
+    for (int i = 0; i < EPL; ++i) {
+      u[i] = xv[i];
+      if (GELU_IN) xv[i] = gelu_f(xv[i]);
+      xv[i] = act ? (xv[i] - mean) * rstd : 0.f;        // xhat
+      ag[i] += dv[i] * xv[i];
+      ab[i] += dv[i];
+      dv[i] *= gm[i];                                   // g
+      s1 += dv[i];
+      s2 += dv[i] * xv[i];
+    }
+    const float m1 = warp_sum(s1) * invC, m2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      float d = rstd * (dv[i] - m1 - xv[i] * m2);
+      if (GELU_IN) d *= gelu_grad_f(u[i]);
+      dv[i] = d + rs[i];
+    }
+    if (act) {
+      if (dx_t) store_vec<EPL>(dx_t + row * C + c0, dv);
+      if (dx_f32) store_vec<EPL>(dx_f32 + row * C + c0, dv);
     }
   }
   if (dgamma == nullptr) return;
-  // block reduction of the per-warp partial dgamma / dbeta, then one atomic per channel per block
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) { red[0][warp][lane + i * 32] = ag[i]; red[1][warp][lane + i * 32] = ab[i]; }
+  for (int i = 0; i < EPL; ++i) { red[0][warp][lane * EPL + i] = ag[i]; red[1][warp][lane * EPL + i] = ab[i]; }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, b = 0.f;
@@ -128,22 +165,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TX* __restrict__ x, i
   }
 }
 
-int grid_for(int rows) { return max(1, min(cdiv(rows, 8), qv_num_sms() * 4)); }
+int pick_epl(int C) { return C > 128 ? 8 : 4; }
 
 }  // namespace
 
 int ln_fwd(cudaStream_t s, int dt_in, const void* x, int ldx, int rows, int C, const float* gamma, const float* beta,
            float eps, int gelu_in, const float* gamma2, const float* beta2, int dt_out, void* y, int ldy, float* stats) {
   if (rows <= 0) return 0;
-  QV_CHECK(C <= 256, "ln_fwd: C=%d > 256", C);
-  const int grid = grid_for(rows);
-#define LN_F(TI, TO, G) \
-  ln_fwd_kernel<TI, TO, G><<<grid, 256, 0, s>>>((const TI*)x, ldx, rows, C, gamma, beta, eps, gamma2, beta2, (TO*)y, ldy, stats)
-  if (dt_in == QV_F32 && dt_out == QV_F32) { if (gelu_in) LN_F(float, float, true); else LN_F(float, float, false); }
-  else if (dt_in == QV_F32 && dt_out == QV_BF16) { if (gelu_in) LN_F(float, bf16, true); else LN_F(float, bf16, false); }
-  else if (dt_in == QV_BF16 && dt_out == QV_BF16) { if (gelu_in) LN_F(bf16, bf16, true); else LN_F(bf16, bf16, false); }
-  else if (dt_in == QV_BF16 && dt_out == QV_F32) { if (gelu_in) LN_F(bf16, float, true); else LN_F(bf16, float, false); }
+  const int epl = pick_epl(C);
+  QV_CHECK(C <= 256 && C % epl == 0 && ldx % epl == 0 && ldy % epl == 0, "ln_fwd: C=%d ldx=%d ldy=%d unsupported", C, ldx, ldy);
+  const int grid = max(1, min(cdiv(rows, 8), qv_num_sms() * 8));
+#define LN_F3(TI, TO, E, G) \
+  ln_fwd_kernel<TI, TO, E, G><<<grid, 256, 0, s>>>((const TI*)x, ldx, rows, C, gamma, beta, eps, gamma2, beta2, (TO*)y, ldy, stats)
+#define LN_F2(TI, TO, G) do { if (epl == 8) LN_F3(TI, TO, 8, G); else LN_F3(TI, TO, 4, G); } while (0)
+#define LN_F(TI, TO) do { if (gelu_in) LN_F2(TI, TO, true); else LN_F2(TI, TO, false); } while (0)
+  if (dt_in == QV_F32 && dt_out == QV_F32) LN_F(float, float);
+  else if (dt_in == QV_F32 && dt_out == QV_BF16) LN_F(float, bf16);
+  else if (dt_in == QV_BF16 && dt_out == QV_BF16) LN_F(bf16, bf16);
+  else LN_F(bf16, float);
 #undef LN_F
+#undef LN_F2
+#undef LN_F3
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -152,12 +194,15 @@ int ln_bwd(cudaStream_t s, int dt_x, const void* x, int ldx, int dt_dy, const vo
            const float* gamma, const float* stats, int gelu_in, int dt_out, void* dx_t, float* dx_f32,
            const float* resid, float* dgamma, float* dbeta) {
   if (rows <= 0) return 0;
-  QV_CHECK(C <= 256, "ln_bwd: C=%d > 256", C);
-  const int grid = max(1, min(cdiv(rows, 8 * 4), qv_num_sms() * 2));
-#define LN_B(TX, TDY, TO, G)                                                                                      \
-  ln_bwd_kernel<TX, TDY, TO, G><<<grid, 256, 0, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, rows, C, gamma, stats, \
-                                                     (TO*)dx_t, dx_f32, resid, dgamma, dbeta)
-#define LN_B2(TX, TDY, TO) do { if (gelu_in) LN_B(TX, TDY, TO, true); else LN_B(TX, TDY, TO, false); } while (0)
+  const int epl = pick_epl(C);
+  QV_CHECK(C <= 256 && C % epl == 0 && ldx % epl == 0 && lddy % epl == 0, "ln_bwd: C=%d ldx=%d lddy=%d unsupported", C, ldx, lddy);
+  QV_CHECK(resid == nullptr || (resid != dx_f32 && (const void*)resid != dx_t), "ln_bwd: resid must not alias an output");
+  const int grid = max(1, min(cdiv(rows, 8 * 2), qv_num_sms() * 6));
+#define LN_B4(TX, TDY, TO, E, G)                                                                                      \
+  ln_bwd_kernel<TX, TDY, TO, E, G><<<grid, 256, 0, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, rows, C, gamma, stats, \
+                                                        (TO*)dx_t, dx_f32, resid, dgamma, dbeta)
+#define LN_B3(TX, TDY, TO, G) do { if (epl == 8) LN_B4(TX, TDY, TO, 8, G); else LN_B4(TX, TDY, TO, 4, G); } while (0)
+#define LN_B2(TX, TDY, TO) do { if (gelu_in) LN_B3(TX, TDY, TO, true); else LN_B3(TX, TDY, TO, false); } while (0)
   const int key = dt_x * 4 + dt_dy * 2 + dt_out;
   switch (key) {
     case 0: LN_B2(float, float, float); break;
@@ -170,7 +215,8 @@ int ln_bwd(cudaStream_t s, int dt_x, const void* x, int ldx, int dt_dy, const vo
     default: LN_B2(bf16, bf16, bf16); break;
   }
 #undef LN_B2
-#undef LN_B
+#undef LN_B3
+#undef LN_B4
   QV_LAUNCH_CHECK();
   return 0;
 }
