@@ -130,6 +130,14 @@ int qavit_layer_norm_forward(const void* x, int x_bf16, long long rows, int C, c
 int qavit_layer_norm_backward(const void* x, int x_bf16, const float* dy, long long rows, int C, const float* w,
                               const float* stats, void* dx, float* dgamma, float* dbeta, void* stream);
 
+/* Depthwise k x k convolution (k = 3 / 5 / 7, stride 1, same padding, bias) on channels-last maps [B, H, W, C]:
+ * ConvNeXtBlock.dwconv H:722, LMFAdapter.dwconv_3x3 / dwconv_5x5 H:811-812 (lateral path, scope row f-1).
+ * w [C, 1, k, k] fp32, x / y / dy / dx fp32 or bf16 (is_bf16); dw / dbias fp32, accumulated. dx may be NULL. */
+int qavit_dwconv_forward(const void* x, int is_bf16, int B, int H, int W, int C, int K, const float* w, const float* bias,
+                         void* y, void* stream);
+int qavit_dwconv_backward(const void* x, const void* dy, int is_bf16, int B, int H, int W, int C, int K, const float* w,
+                          void* dx, float* dw, float* dbias, void* stream);
+
 /* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
 int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,
                        const float* bias, void* C, int c_f32, void* stream);

@@ -263,21 +263,18 @@ __device__ __forceinline__ void At_times_Bt_k16(float (*c)[6][4], const bf16* As
   }
 }
 
-// Consume dXf (X = K or V): bank rows -> CTA accumulator; Linformer rows -> dXs = E dX' (global) and dE += Xs dX'^T
+// Consume dXf (X = K or V): bank rows -> the warp's register accumulator (a warp always serves the same head);
+// Linformer rows -> dXs = E dX' (global) and dE += Xs dX'^T (accumulated in the mma C registers across tasks).
 template <int NKV, bool LINF>
 __device__ __forceinline__ void consume_dXf(const AttnP& p, float (*c)[6][4], bf16* stage /*[32][PT]*/, const bf16* E,
-                                            const bf16* Xs, float* dE_acc, float* dbank_acc, int h, int my_kv, int dcol,
-                                            int lane) {
-  const int g = lane >> 2, t = lane & 3, D = p.H * HD;
+                                            const bf16* Xs, float (*dE_acc)[4], float (*dbank_acc)[4], int h, int my_kv,
+                                            int dcol, int lane) {
+  const int g = lane >> 2, t = lane & 3;
   constexpr int MT = NKV / 16;
-  // bank rows = last m-tile
 #pragma unroll
-  for (int n = 0; n < 6; ++n) {
-    float* d0 = dbank_acc + g * D + h * HD + n * 8 + 2 * t;
-    float* d1 = dbank_acc + (g + 8) * D + h * HD + n * 8 + 2 * t;
-    atomicAdd(d0, c[MT - 1][n][0]); atomicAdd(d0 + 1, c[MT - 1][n][1]);
-    atomicAdd(d1, c[MT - 1][n][2]); atomicAdd(d1 + 1, c[MT - 1][n][3]);
-  }
+  for (int n = 0; n < 6; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dbank_acc[n][e] += c[MT - 1][n][e];
   if (!LINF) return;
   // dX' (32 x 48) -> bf16 staging [j][d]
 #pragma unroll
@@ -311,26 +308,16 @@ __device__ __forceinline__ void consume_dXf(const AttnP& p, float (*c)[6][4], bf
     }
   }
   // dE[l, j] += sum_d Xs[l, d] dX'[j, d] : A = Xs [m = l][k = d], B = dX' [n = j][k = d]
-  {
-    float e[4][4];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) e[n][0] = e[n][1] = e[n][2] = e[n][3] = 0.f;
+  for (int kk = 0; kk < 3; ++kk) {
+    uint32_t a[4];
+    ldA(a, Xs, PT, 0, kk * 16, lane);
 #pragma unroll
-    for (int kk = 0; kk < 3; ++kk) {
-      uint32_t a[4];
-      ldA(a, Xs, PT, 0, kk * 16, lane);
-#pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        uint32_t b[4];
-        ldB(b, stage, PT, np * 16, kk * 16, lane);
-        mma16816(e[2 * np], a, b[0], b[1]);
-        mma16816(e[2 * np + 1], a, b[2], b[3]);
-      }
-    }
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      atomicAdd(dE_acc + g * KLIN + n * 8 + 2 * t, e[n][0]); atomicAdd(dE_acc + g * KLIN + n * 8 + 2 * t + 1, e[n][1]);
-      atomicAdd(dE_acc + (g + 8) * KLIN + n * 8 + 2 * t, e[n][2]); atomicAdd(dE_acc + (g + 8) * KLIN + n * 8 + 2 * t + 1, e[n][3]);
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b[4];
+      ldB(b, stage, PT, np * 16, kk * 16, lane);
+      mma16816(dE_acc[2 * np], a, b[0], b[1]);
+      mma16816(dE_acc[2 * np + 1], a, b[2], b[3]);
     }
   }
   __syncwarp();
@@ -340,20 +327,29 @@ template <int NKV, bool LINF>
 __global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int ntask) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int D = p.H * HD;
-  float* acc = reinterpret_cast<float*>(smraw);                     // dEk [16][32] | dEv | dbank_k [16][D] | dbank_v
-  float *dEk = acc, *dEv = acc + LP * KLIN, *dbk = acc + 2 * LP * KLIN, *dbv = dbk + KB * D;
-  bf16* Es = reinterpret_cast<bf16*>(dbv + KB * D);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bf16* Es = reinterpret_cast<bf16*>(smraw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   bf16* W = Es + 2 * LP * PE + warp * WarpSmem::END;
-  for (int i = threadIdx.x; i < 2 * LP * KLIN + 2 * KB * D; i += blockDim.x) acc[i] = 0.f;
   if (LINF) load_E(Es, p);
   __syncthreads();
   const float scale = rsqrtf((float)HD);
   const bf16* dout = static_cast<const bf16*>(p.dout);
   bf16* dq = static_cast<bf16*>(p.dq);
   constexpr int NT = NKV / 8;
+  // batch reductions live in registers: H == WARPS and the task stride is a multiple of WARPS, so this warp's head is
+  // fixed (h == warp) and its bank-row gradients are one [16 x 48] C tile per K and V; dE_k / dE_v are [16 x 32] tiles.
+  float dbk[6][4], dbv[6][4], dEk[4][4], dEv[4][4];
+#pragma unroll
+  for (int n = 0; n < 6; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dbk[n][e] = dbv[n][e] = 0.f;
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dEk[n][e] = dEv[n][e] = 0.f;
+  const int h = warp;
   for (int task = blockIdx.x * WARPS + warp; task < ntask; task += gridDim.x * WARPS) {
-    const int w = task / p.H, h = task % p.H;
+    const int w = task / p.H;
     int my_q, my_kv = 0;
     stage_task<NKV, LINF>(p, W, Es, w, h, lane, my_q, my_kv);
     load_rows(W + WarpSmem::DO, dout, p.lddo, h * HD, my_q, NQ, lane);
@@ -404,17 +400,29 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int n
     }
     __syncwarp();
   }
-  __syncthreads();
-  if (LINF) {
-    for (int i = threadIdx.x; i < p.L * KLIN; i += blockDim.x) { atomicAdd(p.dEk + i, dEk[i]); atomicAdd(p.dEv + i, dEv[i]); }
+  // ---- flush the per-warp register accumulators (one atomic per element per warp)
+#pragma unroll
+  for (int n = 0; n < 6; ++n) {
+    float* k0 = p.dbank_k + g * D + h * HD + n * 8 + 2 * t;
+    float* v0 = p.dbank_v + g * D + h * HD + n * 8 + 2 * t;
+    atomicAdd(k0, dbk[n][0]); atomicAdd(k0 + 1, dbk[n][1]); atomicAdd(k0 + 8 * D, dbk[n][2]); atomicAdd(k0 + 8 * D + 1, dbk[n][3]);
+    atomicAdd(v0, dbv[n][0]); atomicAdd(v0 + 1, dbv[n][1]); atomicAdd(v0 + 8 * D, dbv[n][2]); atomicAdd(v0 + 8 * D + 1, dbv[n][3]);
   }
-  for (int i = threadIdx.x; i < KB * D; i += blockDim.x) { atomicAdd(p.dbank_k + i, dbk[i]); atomicAdd(p.dbank_v + i, dbv[i]); }
+  if (LINF) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int j = n * 8 + 2 * t;
+      if (g < p.L) { atomicAdd(p.dEk + g * KLIN + j, dEk[n][0]); atomicAdd(p.dEk + g * KLIN + j + 1, dEk[n][1]);
+                     atomicAdd(p.dEv + g * KLIN + j, dEv[n][0]); atomicAdd(p.dEv + g * KLIN + j + 1, dEv[n][1]); }
+      if (g + 8 < p.L) { atomicAdd(p.dEk + (g + 8) * KLIN + j, dEk[n][2]); atomicAdd(p.dEk + (g + 8) * KLIN + j + 1, dEk[n][3]);
+                         atomicAdd(p.dEv + (g + 8) * KLIN + j, dEv[n][2]); atomicAdd(p.dEv + (g + 8) * KLIN + j + 1, dEv[n][3]); }
+    }
+  }
 }
 
 size_t smem_bytes(const AttnP& p, bool bwd) {
-  size_t b = (size_t)(2 * LP * PE + WARPS * WarpSmem::END) * sizeof(bf16);
-  if (bwd) b += (size_t)(2 * LP * KLIN + 2 * KB * p.H * HD) * sizeof(float);
-  return b;
+  (void)p; (void)bwd;
+  return (size_t)(2 * LP * PE + WARPS * WarpSmem::END) * sizeof(bf16);
 }
 
 template <typename K>
@@ -436,7 +444,7 @@ int launch(K kernel, cudaStream_t s, const AttnP& p, bool bwd) {
 // shapes this file is instantiated for
 bool attn_mma_ok(const AttnP& p) {
   const int nq = (p.mode == 0) ? p.ws * p.ws : p.Nt;
-  if (p.hd != HD || nq != NQ || p.kb != KB || p.H * p.hd > 256) return false;
+  if (p.hd != HD || nq != NQ || p.kb != KB || p.H != WARPS) return false;   // H == WARPS: a warp serves one head
   if (p.ldq % 8 || p.qcol % 8 || p.ldo % 8) return false;
   if (p.mode != 2) {
     if (p.klin != KLIN || p.L > LP || p.L < 1 || p.ldkv % 8 || p.kcol % 8 || p.vcol % 8) return false;

@@ -17,9 +17,10 @@ int opt_in(K kernel, size_t bytes) {
 
 // ---------------------------------------------------------------------------------------------- TokenLearner forward
 // S = softmax over tokens of logits[b, n, m];  xc[b, m, c] = sum_n S[n, m] x[b, n, c].   One CTA per image.
-template <typename T>
+template <typename T, int CT>
 __global__ void __launch_bounds__(192) tl16_fwd_kernel(const float* __restrict__ x, const T* __restrict__ logits, int B, int N,
-                                                       int C, float* __restrict__ S, float* __restrict__ xc) {
+                                                       int Crt, float* __restrict__ S, float* __restrict__ xc) {
+  const int C = CT ? CT : Crt;
   extern __shared__ __align__(16) float sS[];   // [N][16]
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int idx = tid; idx < N * M16; idx += blockDim.x) sS[idx] = ldf(logits + (long)b * N * M16 + idx);
@@ -77,10 +78,11 @@ __global__ void __launch_bounds__(192) tl16_fwd_kernel(const float* __restrict__
 
 // ---------------------------------------------------------------------------------------------- TokenLearner backward
 // dS[n, m] = x[n, :] . dxc[m, :];  dlogits = S (dS - colsum_n(S dS));  dx[n, :] = sum_m S[n, m] dxc[m, :]
-template <typename T>
+template <typename T, int CT>
 __global__ void __launch_bounds__(256) tl16_bwd_kernel(const float* __restrict__ x, const float* __restrict__ S,
-                                                       const float* __restrict__ dxc, int B, int N, int C,
+                                                       const float* __restrict__ dxc, int B, int N, int Crt,
                                                        T* __restrict__ dlogits, float* __restrict__ dx) {
+  const int C = CT ? CT : Crt;
   extern __shared__ __align__(16) float sm[];
   constexpr int RC = 64;                          // tokens staged per pass
   const int CP = C + 1;
@@ -96,11 +98,17 @@ __global__ void __launch_bounds__(256) tl16_bwd_kernel(const float* __restrict__
   for (int n0 = 0; n0 < N; n0 += RC) {
     const int nr = min(RC, N - n0);
     __syncthreads();
-    for (int idx = tid; idx < nr * C; idx += blockDim.x) sX[(idx / C) * CP + idx % C] = x[((long)b * N + n0) * C + idx];
+    for (int idx = tid; idx < nr * (C / 4); idx += blockDim.x) {
+      const int r = idx / (C / 4), c4 = idx % (C / 4);
+      const float4 v = *reinterpret_cast<const float4*>(x + ((long)b * N + n0 + r) * C + 4 * c4);
+      float* d = sX + r * CP + 4 * c4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
     __syncthreads();
     if (nl < nr) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       const float* xr = sX + nl * CP;
+#pragma unroll 8
       for (int c = 0; c < C; ++c) {
         const float xv = xr[c];
         const float4 dv = *reinterpret_cast<const float4*>(sDT + c * M16 + 4 * mq);
@@ -207,8 +215,10 @@ __global__ void __launch_bounds__(192) up16_dx_kernel(const float* __restrict__ 
 
 // dW[n, m] += sum_{b, c} dup[b, n, c] xc[b, m, c];  dbias[n] += sum_{b, c} dup[b, n, c].
 // Thread tile (token, 4 slots); 64 tokens staged per pass; accumulators in shared memory across the CTA's images.
+template <int CT>
 __global__ void __launch_bounds__(256) up16_dw_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B, int N,
-                                                      int C, float* __restrict__ dW, float* __restrict__ dbias) {
+                                                      int Crt, float* __restrict__ dW, float* __restrict__ dbias) {
+  const int C = CT ? CT : Crt;
   extern __shared__ __align__(16) float sm[];
   constexpr int RC = 64;
   const int CP = C + 1;
@@ -225,11 +235,17 @@ __global__ void __launch_bounds__(256) up16_dw_kernel(const float* __restrict__ 
     for (int n0 = 0; n0 < N; n0 += RC) {
       const int nr = min(RC, N - n0);
       __syncthreads();
-      for (int idx = tid; idx < nr * C; idx += blockDim.x) sG[(idx / C) * CP + idx % C] = dup[((long)b * N + n0) * C + idx];
+      for (int idx = tid; idx < nr * (C / 4); idx += blockDim.x) {
+        const int r = idx / (C / 4), c4 = idx % (C / 4);
+        const float4 v = *reinterpret_cast<const float4*>(dup + ((long)b * N + n0 + r) * C + 4 * c4);
+        float* d = sG + r * CP + 4 * c4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
       __syncthreads();
       if (nl < nr) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, sb = 0.f;
         const float* gr = sG + nl * CP;
+#pragma unroll 8
         for (int c = 0; c < C; ++c) {
           const float gv = gr[c];
           const float4 xv = *reinterpret_cast<const float4*>(sXT + c * M16 + 4 * mq);
@@ -255,15 +271,19 @@ bool tokens16_ok(int M, int C) { return M == 16 && C % 4 == 0 && C <= 1024; }
 
 int tl16_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, int N, int C, float* S, float* xc) {
   const size_t smem = (size_t)N * M16 * sizeof(float);
-  if (dt == QV_F32) { QV_TRY(opt_in(tl16_fwd_kernel<float>, smem)); tl16_fwd_kernel<float><<<B, 192, smem, s>>>(x, (const float*)logits, B, N, C, S, xc); }
-  else { QV_TRY(opt_in(tl16_fwd_kernel<bf16>, smem)); tl16_fwd_kernel<bf16><<<B, 192, smem, s>>>(x, (const bf16*)logits, B, N, C, S, xc); }
+#define TLF(T, CT) do { QV_TRY(opt_in(tl16_fwd_kernel<T, CT>, smem)); tl16_fwd_kernel<T, CT><<<B, 192, smem, s>>>(x, (const T*)logits, B, N, C, S, xc); } while (0)
+  if (dt == QV_F32) { if (C == 192) TLF(float, 192); else TLF(float, 0); }
+  else { if (C == 192) TLF(bf16, 192); else TLF(bf16, 0); }
+#undef TLF
   QV_LAUNCH_CHECK();
   return 0;
 }
 int tl16_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx) {
   const size_t smem = (size_t)(2 * N * M16 + C * M16 + M16 + 64 * (C + 1)) * sizeof(float);
-  if (dt == QV_F32) { QV_TRY(opt_in(tl16_bwd_kernel<float>, smem)); tl16_bwd_kernel<float><<<B, 256, smem, s>>>(x, S, dxc, B, N, C, (float*)dlogits, dx); }
-  else { QV_TRY(opt_in(tl16_bwd_kernel<bf16>, smem)); tl16_bwd_kernel<bf16><<<B, 256, smem, s>>>(x, S, dxc, B, N, C, (bf16*)dlogits, dx); }
+#define TLB(T, CT) do { QV_TRY(opt_in(tl16_bwd_kernel<T, CT>, smem)); tl16_bwd_kernel<T, CT><<<B, 256, smem, s>>>(x, S, dxc, B, N, C, (T*)dlogits, dx); } while (0)
+  if (dt == QV_F32) { if (C == 192) TLB(float, 192); else TLB(float, 0); }
+  else { if (C == 192) TLB(bf16, 192); else TLB(bf16, 0); }
+#undef TLB
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -281,9 +301,10 @@ int up16_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, in
   up16_dx_kernel<<<min(B, qv_num_sms() * 16), 192, smem, s>>>(dup, B, N, C, W, dxc);
   QV_LAUNCH_CHECK();
   smem = (size_t)(N * M16 + ((N + 3) & ~3) + C * M16 + 64 * (C + 1)) * sizeof(float);
-  QV_TRY(opt_in(up16_dw_kernel, smem));
   const int occ = max(1, (int)(220 * 1024 / (smem + 1024)));
-  up16_dw_kernel<<<min(B, qv_num_sms() * min(occ, 4)), 256, smem, s>>>(xc, dup, B, N, C, dW, dbias);
+  const int grid = min(B, qv_num_sms() * min(occ, 4));
+  if (C == 192) { QV_TRY(opt_in(up16_dw_kernel<192>, smem)); up16_dw_kernel<192><<<grid, 256, smem, s>>>(xc, dup, B, N, C, dW, dbias); }
+  else { QV_TRY(opt_in(up16_dw_kernel<0>, smem)); up16_dw_kernel<0><<<grid, 256, smem, s>>>(xc, dup, B, N, C, dW, dbias); }
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -274,6 +274,47 @@ class LayerNormFn(torch.autograd.Function):
         return dx, rg, rb, None
 
 
+class DepthwiseConvFn(torch.autograd.Function):
+    """Depthwise k x k conv (stride 1, same padding, bias) on a channels-last feature map -- ConvNeXtBlock.dwconv
+    (H:722) and LMFAdapter.dwconv_3x3 / 5x5 (H:811-812).  x: logical [B, C, H, W], channels_last strides."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        _require_cuda(x, "conv input")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.detach().contiguous(memory_format=torch.channels_last)
+        B, C_, H, W = x.shape
+        K = w.shape[-1]
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        check(lib.qavit_dwconv_forward(x.data_ptr(), int(x.dtype == torch.bfloat16), B, H, W, C_, K, w.data_ptr(), _ptr(bias),
+                                       y.data_ptr(), _stream()))
+        ctx.save_for_backward(x, w)
+        ctx.params = (w, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        B, C_, H, W = x.shape
+        K = w.shape[-1]
+        dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x, memory_format=torch.channels_last) if ctx.needs_input_grad[0] else None
+        direct = []
+        dw, rw = _grad_out(ctx.params[0], direct)
+        db, rb = _grad_out(ctx.params[1], direct) if ctx.params[1] is not None else (None, None)
+        check(lib.qavit_dwconv_backward(x.data_ptr(), dy.data_ptr(), int(x.dtype == torch.bfloat16), B, H, W, C_, K, w.data_ptr(),
+                                        _ptr(dx), dw.data_ptr(), _ptr(db), _stream()))
+        _notify(direct)
+        return dx, rw, rb
+
+
+def depthwise_conv(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """conv(x) for a depthwise, stride-1, same-padded nn.Conv2d with k in (3, 5, 7) through the library's kernels."""
+    x = x.to(torch.get_autocast_gpu_dtype()) if torch.is_autocast_enabled() and x.dtype == torch.float32 else x
+    return DepthwiseConvFn.apply(x, conv.weight, conv.bias)
+
+
 class CrossEntropyFn(torch.autograd.Function):
     """CrossEntropyLoss(label_smoothing) and its two-target mixup form -- HQAViT_CIFAR100.py:1373, 1404-1408."""
 

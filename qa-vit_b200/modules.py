@@ -409,7 +409,7 @@ class ConvNeXtBlock(nn.Module):
         self.pwconv2 = nn.Linear(4 * dim, dim)
 
     def forward(self, x):
-        h = self.dwconv(x).permute(0, 2, 3, 1)
+        h = (QF.depthwise_conv(x, self.dwconv) if x.is_cuda else self.dwconv(x)).permute(0, 2, 3, 1)
         h = self.pwconv2(self.act(self.pwconv1(self.norm(h))))
         return x + h.permute(0, 3, 1, 2)
 
@@ -443,7 +443,12 @@ class LMFAdapter(nn.Module):
         self.act = nn.GELU()
 
     def forward(self, feat):
-        f = self.proj(torch.cat([self.dwconv_3x3(feat), self.dwconv_5x5(feat), feat], dim=1))
+        if feat.is_cuda:
+            f1, f2 = QF.depthwise_conv(feat, self.dwconv_3x3), QF.depthwise_conv(feat, self.dwconv_5x5)
+            feat = feat.to(f1.dtype)
+        else:
+            f1, f2 = self.dwconv_3x3(feat), self.dwconv_5x5(feat)
+        f = self.proj(torch.cat([f1, f2, feat], dim=1))
         if f.shape[2] != self.target_hw or f.shape[3] != self.target_hw:
             f = F.interpolate(f, size=(self.target_hw, self.target_hw), mode="bilinear", align_corners=False)
         return self.act(self.norm(f.permute(0, 2, 3, 1).reshape(f.shape[0], -1, f.shape[1])))   # NHWC view: no copy in channels_last
