@@ -138,6 +138,13 @@ int qavit_dwconv_forward(const void* x, int is_bf16, int B, int H, int W, int C,
 int qavit_dwconv_backward(const void* x, const void* dy, int is_bf16, int B, int H, int W, int C, int K, const float* w,
                           void* dx, float* dw, float* dbias, void* stream);
 
+/* nn.Linear / 1x1 convolution on row-major activations: y[M, N] = x[M, K] W^T + b and its backward (dW, db
+ * accumulated; dx may be NULL).  x / y / dy / dx fp32 or bf16 (is_bf16); *_scratch: N*K bf16 for the converted weight. */
+int qavit_linear_forward(const void* x, int is_bf16, long long M, int K, const float* W, const float* bias, int N, void* y,
+                         void* wb_scratch, void* stream);
+int qavit_linear_backward(const void* x, const void* dy, int is_bf16, long long M, int K, int N, const float* W, void* dx,
+                          float* dW, float* db, void* wbt_scratch, void* stream);
+
 /* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
 int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,
                        const float* bias, void* C, int c_f32, void* stream);

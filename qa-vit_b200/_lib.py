@@ -55,6 +55,8 @@ _SIGS = {
     "qavit_layer_norm_backward": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_dwconv_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "qavit_dwconv_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_linear_forward": (_i, [_vp, _i, _ll, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "qavit_linear_backward": (_i, [_vp, _vp, _i, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_test_gemm_nt": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "qavit_test_gemm_tn": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "qavit_convert_weight": (_i, [_vp, _i, _i, _vp, _vp, _vp]),

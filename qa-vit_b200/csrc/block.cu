@@ -787,3 +787,42 @@ extern "C" int qavit_layer_norm_backward(const void* x, int x_bf16, const float*
   return ln_bwd((cudaStream_t)stream, x_bf16 ? QV_BF16 : QV_F32, x, C, QV_F32, dy, C, (int)rows, C, w, stats, 0,
                 x_bf16 ? QV_BF16 : QV_F32, x_bf16 ? dx : nullptr, x_bf16 ? nullptr : (float*)dx, nullptr, dgamma, dbeta);
 }
+
+// nn.Linear / 1x1 convolution on row-major activations (the lateral path's pointwise layers: ConvNeXt pwconv1/2 H:724-726,
+// LMFAdapter.proj H:815, RRCV reverse/reembed_proj H:866-874, SplitFusion gate_fc / cat_mlp.0 H:923-927, cnn_stem 1x1s).
+// y[M, N] = x[M, K] W^T + b through the same GEMM flavours as the block (tcgen05 when is_bf16, fp32 SIMT otherwise).
+// wb_scratch: N*K bf16 (forward) / wbt_scratch: N*K bf16 (backward) for the converted weight; unused in fp32 runs.
+extern "C" int qavit_linear_forward(const void* x, int is_bf16, long long M, int K, const float* W, const float* bias, int N,
+                                    void* y, void* wb_scratch, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int dt = is_bf16 ? QV_BF16 : QV_F32;
+  Weight w;
+  w.w = W; w.N = N; w.K = K;
+  if (is_bf16 && tc_shape_ok_nt((int)M, N, K, K)) {
+    QV_CHECK(wb_scratch, "linear_forward: bf16 run needs wb_scratch");
+    QV_TRY(convert_weight(s, W, N, K, (bf16*)wb_scratch, nullptr));
+    w.wb = (const bf16*)wb_scratch;
+  }
+  GemmEpi e;
+  e.bias = bias; e.C = y; e.ldc = N; e.c_f32 = !is_bf16;
+  return gemm_nt(s, dt, x, K, (int)M, w, e);
+}
+extern "C" int qavit_linear_backward(const void* x, const void* dy, int is_bf16, long long M, int K, int N, const float* W,
+                                     void* dx, float* dW, float* db, void* wbt_scratch, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const int dt = is_bf16 ? QV_BF16 : QV_F32;
+  QV_TRY(gemm_tn(s, dt, dy, N, x, K, (int)M, N, K, dW, db, nullptr));
+  if (dx) {
+    Weight w;
+    w.w = W; w.N = N; w.K = K;
+    if (is_bf16 && tc_shape_ok_nt((int)M, K, N, N)) {
+      QV_CHECK(wbt_scratch, "linear_backward: bf16 run needs wbt_scratch");
+      QV_TRY(convert_weight(s, W, N, K, nullptr, (bf16*)wbt_scratch));
+      w.wbt = (const bf16*)wbt_scratch;
+    }
+    GemmEpi e;
+    e.C = dx; e.ldc = K; e.c_f32 = !is_bf16;
+    QV_TRY(gemm_nn(s, dt, dy, N, (int)M, w, e));
+  }
+  return 0;
+}

@@ -315,6 +315,59 @@ def depthwise_conv(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
     return DepthwiseConvFn.apply(x, conv.weight, conv.bias)
 
 
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b on [M, K] rows (nn.Linear, and 1x1 convolutions on channels-last maps) through the library's GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        _require_cuda(x, "linear input")
+        x = x.detach().contiguous()
+        M, K = x.shape
+        N = W.shape[0]
+        bf = x.dtype == torch.bfloat16
+        y = torch.empty(M, N, dtype=x.dtype, device=x.device)
+        wb = torch.empty(N * K, dtype=torch.bfloat16, device=x.device) if bf else None
+        check(lib.qavit_linear_forward(x.data_ptr(), int(bf), M, K, W.data_ptr(), _ptr(bias), N, y.data_ptr(), _ptr(wb), _stream()))
+        ctx.save_for_backward(x, W)
+        ctx.params = (W, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        M, K = x.shape
+        N = W.shape[0]
+        bf = x.dtype == torch.bfloat16
+        dy = dy.to(x.dtype).contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        direct = []
+        dW, rW = _grad_out(ctx.params[0], direct)
+        db, rb = _grad_out(ctx.params[1], direct) if ctx.params[1] is not None else (None, None)
+        wbt = torch.empty(N * K, dtype=torch.bfloat16, device=x.device) if bf else None
+        check(lib.qavit_linear_backward(x.data_ptr(), dy.data_ptr(), int(bf), M, K, N, W.data_ptr(), _ptr(dx), dW.data_ptr(), _ptr(db),
+                                        _ptr(wbt), _stream()))
+        _notify(direct)
+        return dx, rW, rb
+
+
+def linear(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """F.linear(x, W, bias) over the last axis (W may be a [N, K, 1, 1] conv weight): bf16 under autocast, else fp32."""
+    K = x.shape[-1]
+    if torch.is_autocast_enabled():
+        x = x.to(torch.get_autocast_gpu_dtype())
+    elif x.dtype != torch.float32:
+        x = x.float()
+    y = LinearFn.apply(x.reshape(-1, K), W.view(W.shape[0], -1) if W.dim() != 2 else W, bias)
+    return y.view(*x.shape[:-1], W.shape[0])
+
+
+def conv1x1(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """1x1 nn.Conv2d on a (channels-last) [B, C, H, W] map as a GEMM over its [B*H*W, C] rows."""
+    B, C_, H, W_ = x.shape
+    y = linear(x.permute(0, 2, 3, 1), conv.weight, conv.bias)          # [B, H, W, N]; no copy for channels_last x
+    return y.permute(0, 3, 1, 2)
+
+
 class CrossEntropyFn(torch.autograd.Function):
     """CrossEntropyLoss(label_smoothing) and its two-target mixup form -- HQAViT_CIFAR100.py:1373, 1404-1408."""
 
