@@ -145,6 +145,47 @@ int qavit_linear_forward(const void* x, int is_bf16, long long M, int K, const f
 int qavit_linear_backward(const void* x, const void* dy, int is_bf16, long long M, int K, int N, const float* W, void* dx,
                           float* dW, float* db, void* wbt_scratch, void* stream);
 
+/* ---- HQAViT lateral CNN path (scope row f-1): CNNStemModel H:742-793 -> LMFAdapter x3 H:799-849 -> RRCV x3 H:855-907.
+ * One call per direction for the whole path: image in, the refined token maps R2 / R3 / R4 out.  Activations are
+ * channels-last [B * H * W, C] in the run's activation type (dtype 0: fp32, 1: bf16); R2..R4 / dR2..dR4 are fp32
+ * [B, grid * grid, dim] (LayerNorm outputs stay fp32 under autocast).
+ * params[i] / grads[i] follow qavit_lateral_param_name(cfg, i) (state_dict names relative to the HQAViT module;
+ * BatchNorm running_mean / running_var / num_batches_tracked entries are buffers: updated in train mode, grads NULL).
+ * train = module.training (BatchNorm batch statistics).  The bilinear resize of H:824 is not implemented: the token
+ * grid must equal img_size / 4 (all reference configurations). */
+typedef struct qavit_lateral_cfg {
+  int32_t batch, img_size, in_channels;
+  int32_t c_stem, c2, c3, c4;        /* 32, cnn_c2, cnn_c3, cnn_c4 */
+  int32_t rrcv_channels, rrcv_blocks;
+  int32_t dim, grid;                 /* embed_dim, tokens per side */
+  int32_t train, dtype;
+  float bn_eps, bn_momentum;
+} qavit_lateral_cfg;
+int qavit_lateral_param_count(const qavit_lateral_cfg* cfg);
+const char* qavit_lateral_param_name(const qavit_lateral_cfg* cfg, int index);
+int qavit_lateral_workspace(const qavit_lateral_cfg* cfg, size_t* saved_bytes, size_t* scratch_bytes);
+int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* const* params, const float* img, float* R2, float* R3,
+                          float* R4, void* saved, void* scratch, void* stream);
+/* dR2..dR4 may be NULL (stage not fused); parameter gradients are accumulated; the image receives no gradient. */
+int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* const* params, float* const* grads, const float* img,
+                           const float* dR2, const float* dR3, const float* dR4, const void* saved, void* scratch, void* stream);
+
+/* ---- SplitFusion.forward H:945-963: T_in, R, out, dT, dR fp32 [rows, dim] (the residual stream).
+ * params / grads follow qavit_splitfusion_param_name(i).  drop_p is cat_mlp[3].p (applied when train != 0; the mask is
+ * regenerated in backward from the Philox state `rng` = {seed, offset} (device), which forward snapshots and advances). */
+typedef struct qavit_splitfusion_cfg {
+  long long rows;
+  int32_t dim, dtype, train;
+  float drop_p;
+} qavit_splitfusion_cfg;
+const char* qavit_splitfusion_param_name(int index);
+int qavit_splitfusion_workspace(const qavit_splitfusion_cfg* cfg, size_t* saved_bytes, size_t* scratch_bytes);
+int qavit_splitfusion_forward(const qavit_splitfusion_cfg* cfg, const void* const* params, unsigned long long* rng,
+                              const float* T_in, const float* R, float* out, void* saved, void* scratch, void* stream);
+int qavit_splitfusion_backward(const qavit_splitfusion_cfg* cfg, const void* const* params, float* const* grads, const float* T_in,
+                               const float* R, const float* dout, float* dT, float* dR, const void* saved, void* scratch,
+                               void* stream);
+
 /* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
 int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,
                        const float* bias, void* C, int c_f32, void* stream);

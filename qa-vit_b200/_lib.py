@@ -25,6 +25,21 @@ class BlockCfg(C.Structure):
     ]
 
 
+class LateralCfg(C.Structure):
+    """Mirror of ``qavit_lateral_cfg``."""
+    _fields_ = [
+        ("batch", C.c_int32), ("img_size", C.c_int32), ("in_channels", C.c_int32),
+        ("c_stem", C.c_int32), ("c2", C.c_int32), ("c3", C.c_int32), ("c4", C.c_int32),
+        ("rrcv_channels", C.c_int32), ("rrcv_blocks", C.c_int32), ("dim", C.c_int32), ("grid", C.c_int32),
+        ("train", C.c_int32), ("dtype", C.c_int32), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+    ]
+
+
+class SplitFusionCfg(C.Structure):
+    """Mirror of ``qavit_splitfusion_cfg``."""
+    _fields_ = [("rows", C.c_longlong), ("dim", C.c_int32), ("dtype", C.c_int32), ("train", C.c_int32), ("drop_p", C.c_float)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -57,6 +72,15 @@ _SIGS = {
     "qavit_dwconv_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "qavit_linear_forward": (_i, [_vp, _i, _ll, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "qavit_linear_backward": (_i, [_vp, _vp, _i, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_lateral_param_count": (_i, [C.POINTER(LateralCfg)]),
+    "qavit_lateral_param_name": (C.c_char_p, [C.POINTER(LateralCfg), _i]),
+    "qavit_lateral_workspace": (_i, [C.POINTER(LateralCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "qavit_lateral_forward": (_i, [C.POINTER(LateralCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_lateral_backward": (_i, [C.POINTER(LateralCfg), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_splitfusion_param_name": (C.c_char_p, [_i]),
+    "qavit_splitfusion_workspace": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "qavit_splitfusion_forward": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_splitfusion_backward": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_test_gemm_nt": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "qavit_test_gemm_tn": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "qavit_convert_weight": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
@@ -90,3 +114,16 @@ def param_table():
 PARAMS = param_table()
 QP_COUNT = len(PARAMS)
 QP = {name if scope != 2 else "bank." + name: i for i, (name, scope) in enumerate(PARAMS)}
+
+
+def lateral_param_names(cfg: LateralCfg):
+    """state_dict names (relative to the HQAViT module) of the lateral path's tensors, in the C side's order."""
+    n = lib.qavit_lateral_param_count(C.byref(cfg))
+    if n < 0:
+        check(1)
+    return [lib.qavit_lateral_param_name(C.byref(cfg), i).decode() for i in range(n)]
+
+
+SPLITFUSION_PARAMS = []
+while lib.qavit_splitfusion_param_name(len(SPLITFUSION_PARAMS)) is not None:
+    SPLITFUSION_PARAMS.append(lib.qavit_splitfusion_param_name(len(SPLITFUSION_PARAMS)).decode())

@@ -81,6 +81,11 @@ int gemm_tn(cudaStream_t s, int dt, const void* dY, int ldy, const void* X, int 
     if (db) QV_TRY(colsum_accum(s, dt, dY, ldy, M, N, db, scale));
     return 0;
   }
+  if (dt == QV_BF16 && K > 256 && tc_shape_ok_tn(M, K, N, ldx, ldy)) {   // wide-K weight: accumulate X^T dY, store transposed
+    QV_TRY(tc_gemm_tn(s, (const bf16*)X, ldx, (const bf16*)dY, ldy, M, K, N, dW, scale, 1, K));
+    if (db) QV_TRY(colsum_accum(s, dt, dY, ldy, M, N, db, scale));
+    return 0;
+  }
   return simt_gemm_tn(s, dt, dY, ldy, X, ldx, M, N, K, dW, db, scale);
 }
 

@@ -71,6 +71,73 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// Abramowitz-Stegun 7.1.26 erf (|err| < 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 6 FMAs.  Used by the bf16-run GEMM
+// epilogues, where erff's ~35 instructions per element would make the 12 epilogue warps the bottleneck.
+__device__ __forceinline__ float erf_as_f(float x, float* expmx2) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float e = __expf(-ax * ax);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * e;
+  if (expmx2) *expmx2 = e;
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_fast_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752f, nullptr)); }
+__device__ __forceinline__ float gelu_grad_fast_f(float x) {
+  float e;
+  const float cdf = 0.5f * (1.0f + erf_as_f(x * 0.70710678118654752f, &e));   // e = exp(-x^2 / 2)
+  return fmaf(x * 0.39894228040143268f, e, cdf);
+}
+
+// EPL-wide (4 or 8) vector load / store of a row slice, math in fp32 (shared by the row kernels)
+template <int EPL>
+__device__ __forceinline__ void load_vec(const float* p, float* v) {
+#pragma unroll
+  for (int i = 0; i < EPL; i += 4) {
+    const float4 q = *reinterpret_cast<const float4*>(p + i);
+    v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void load_vec(const bf16* p, float* v) {
+  if (EPL == 8) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  } else {
+    const uint2 q = *reinterpret_cast<const uint2*>(p);
+    const uint32_t w[2] = {q.x, q.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void store_vec(float* p, const float* v) {
+#pragma unroll
+  for (int i = 0; i < EPL; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+template <int EPL>
+__device__ __forceinline__ void store_vec(bf16* p, const float* v) {
+  uint32_t w[EPL / 2];
+#pragma unroll
+  for (int i = 0; i < EPL / 2; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  if (EPL == 8) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[EPL / 2 - 1]);
+}
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 static inline int qv_num_sms() {
   static int n = 0;

@@ -1,91 +1,134 @@
 // Depthwise k x k convolutions (k = 3, 5, 7; stride 1, 'same' padding, bias) on channels-last feature maps
 // [B, H, W, C] -- the ConvNeXt / LMFAdapter stencils of HQAViT's lateral path (H:722, 811-812; scope row f-1).
-// One CTA per (image, 64-channel slab): the slab's H x W x 64 tile sits in shared memory, a thread owns one channel
-// (its k*k taps live in registers) and walks output positions, so global traffic is each element once, coalesced
-// over channels.  HBM-bound: algorithmic bytes = B*H*W*C * (in + out).
+//
+// One CTA per (image, 64-channel slab): the slab's H x W x 64 tile sits in shared memory (fp32), consecutive lanes own
+// consecutive channels (coalesced global traffic, conflict-free shared loads).  A thread computes 8 outputs of one row
+// at a time: per kernel row it loads the 8 + k - 1 inputs once into registers and issues 8 * k FMAs on them, so the
+// stencil is FMA-bound (k * k FMAs per output, ~4 FMAs per shared load) instead of shared-load-bound.
+// HBM-bound in the ideal: algorithmic bytes = B*H*W*C * (in + out).
 #include "../../include/qavit_b200.h"
 #include "kernels.h"
 
 namespace {
 
 constexpr int CS = 64;     // channels per CTA
-constexpr int PG = 4;      // position groups (threads per channel)
+constexpr int PG = 4;      // thread groups per channel (CTA = 256 threads)
+constexpr int SEG = 8;     // outputs per thread task (one row segment)
 
+template <typename T>
+__device__ __forceinline__ void load_tile(float* xs, const T* __restrict__ x, long ldx, long row0, int HW, int c0, int C) {
+  // [HW][CS] tile, two channels per thread
+  for (int idx = threadIdx.x; idx < HW * (CS / 2); idx += CS * PG) {
+    const int p = idx / (CS / 2), cc = (idx % (CS / 2)) * 2;
+    float2 v = make_float2(0.f, 0.f);
+    if (c0 + cc < C) v = ld2(x + (row0 + p) * ldx + c0 + cc);
+    *reinterpret_cast<float2*>(xs + p * CS + cc) = v;
+  }
+}
+
+// y = conv(x) (+ bias) (+ resid) (+ resid2); FLIP: correlate with the flipped kernel (= the input gradient).
+// copy (optional): also writes the input tile to copy[row, c] (LMFAdapter's identity branch of the concat).
 template <typename T, int K, bool FLIP>
-__global__ void __launch_bounds__(CS * PG) dw_fwd_kernel(const T* __restrict__ x, int B, int H, int W, int C,
+__global__ void __launch_bounds__(CS * PG) dw_fwd_kernel(const T* __restrict__ x, int ldx, int H, int W, int C,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
-                                                         T* __restrict__ y) {
+                                                         T* y, int ldy, const T* resid, int ldr,
+                                                         const T* resid2, int ldr2, T* __restrict__ copy, int ldcp) {
   extern __shared__ float xs[];                 // [H*W][CS]
   const int b = blockIdx.x, c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS, c = c0 + cl;
   const int HW = H * W;
+  const long row0 = (long)b * HW;
   const bool act = c < C;
-  for (int idx = threadIdx.x; idx < HW * CS; idx += CS * PG) {
-    const int p = idx / CS, cc = idx % CS;
-    xs[idx] = (c0 + cc < C) ? ldf(x + ((long)b * HW + p) * C + c0 + cc) : 0.f;
-  }
+  load_tile(xs, x, ldx, row0, HW, c0, C);
   float wr[K * K];
 #pragma unroll
   for (int t = 0; t < K * K; ++t) wr[t] = act ? w[c * K * K + (FLIP ? K * K - 1 - t : t)] : 0.f;
   const float bs = (bias && act) ? bias[c] : 0.f;
   __syncthreads();
   if (!act) return;
-  for (int p = pg; p < HW; p += PG) {
-    const int py = p / W, px = p % W;
-    float a = bs;
+  if (copy) {
+    for (int p = pg; p < HW; p += PG) stf(copy + (row0 + p) * ldcp + c, xs[p * CS + cl]);
+  }
+  const int segs = (W + SEG - 1) / SEG;
+  for (int task = pg; task < H * segs; task += PG) {
+    const int py = task / segs, px0 = (task % segs) * SEG;
+    float acc[SEG];
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) acc[j] = bs;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
       const int yy = py + ky - K / 2;
       if (yy < 0 || yy >= H) continue;
+      float xr[SEG + K - 1];
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const int xx = px + kx - K / 2;
-        if (xx < 0 || xx >= W) continue;
-        a = fmaf(wr[ky * K + kx], xs[(yy * W + xx) * CS + cl], a);
+      for (int i = 0; i < SEG + K - 1; ++i) {
+        const int xx = px0 + i - K / 2;
+        xr[i] = (xx >= 0 && xx < W) ? xs[(yy * W + xx) * CS + cl] : 0.f;
       }
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) acc[j] = fmaf(wr[ky * K + kx], xr[j + kx], acc[j]);
     }
-    stf(y + ((long)b * HW + p) * C + c, a);
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) {
+      if (px0 + j >= W) break;
+      const long row = row0 + py * W + px0 + j;
+      float v = acc[j];
+      if (resid) v += ldf(resid + row * ldr + c);
+      if (resid2) v += ldf(resid2 + row * ldr2 + c);
+      stf(y + row * ldy + c, v);
+    }
   }
 }
 
 // dw[c, ky, kx] += sum_{b, p} dy[b, p, c] x[b, p + (ky, kx) - K/2, c];  dbias[c] += sum dy
 template <typename T, int K>
-__global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, int B, int H,
-                                                           int W, int C, float* __restrict__ dw, float* __restrict__ dbias) {
+__global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy,
+                                                           int lddy, int B, int H, int W, int C, float* __restrict__ dw,
+                                                           float* __restrict__ dbias) {
   extern __shared__ float sm[];
   const int HW = H * W;
   float* xs = sm;                    // [HW][CS]
   float* gs = sm + HW * CS;          // [HW][CS]
-  const int c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS, c = c0 + cl;
+  const int c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS;
+  const int segs = (W + SEG - 1) / SEG;
   float acc[K * K], ab = 0.f;
 #pragma unroll
   for (int t = 0; t < K * K; ++t) acc[t] = 0.f;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < HW * CS; idx += CS * PG) {
-      const int p = idx / CS, cc = idx % CS;
-      const bool ok = c0 + cc < C;
-      xs[idx] = ok ? ldf(x + ((long)b * HW + p) * C + c0 + cc) : 0.f;
-      gs[idx] = ok ? ldf(dy + ((long)b * HW + p) * C + c0 + cc) : 0.f;
-    }
+    load_tile(xs, x, ldx, (long)b * HW, HW, c0, C);
+    load_tile(gs, dy, lddy, (long)b * HW, HW, c0, C);
     __syncthreads();
-    for (int p = pg; p < HW; p += PG) {
-      const int py = p / W, px = p % W;
-      const float g = gs[p * CS + cl];
-      ab += g;
+    for (int task = pg; task < H * segs; task += PG) {
+      const int py = task / segs, px0 = (task % segs) * SEG;
+      float g[SEG];
+#pragma unroll
+      for (int j = 0; j < SEG; ++j) {
+        g[j] = (px0 + j < W) ? gs[(py * W + px0 + j) * CS + cl] : 0.f;
+        ab += g[j];
+      }
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
         const int yy = py + ky - K / 2;
         if (yy < 0 || yy >= H) continue;
+        float xr[SEG + K - 1];
+#pragma unroll
+        for (int i = 0; i < SEG + K - 1; ++i) {
+          const int xx = px0 + i - K / 2;
+          xr[i] = (xx >= 0 && xx < W) ? xs[(yy * W + xx) * CS + cl] : 0.f;
+        }
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
-          const int xx = px + kx - K / 2;
-          if (xx < 0 || xx >= W) continue;
-          acc[ky * K + kx] = fmaf(g, xs[(yy * W + xx) * CS + cl], acc[ky * K + kx]);
+          float a = acc[ky * K + kx];
+#pragma unroll
+          for (int j = 0; j < SEG; ++j) a = fmaf(g[j], xr[j + kx], a);
+          acc[ky * K + kx] = a;
         }
       }
     }
   }
-  // reduce the PG position groups through shared memory, then one atomic per (channel, tap) per CTA
+  // reduce the PG thread groups through shared memory, then one atomic per (channel, tap) per CTA
   __syncthreads();
   float* red = sm;                   // [PG][K*K + 1][CS]
 #pragma unroll
@@ -104,23 +147,24 @@ __global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__
 }
 
 template <typename T, int K>
-int run_fwd(cudaStream_t s, const T* x, int B, int H, int W, int C, const float* w, const float* bias, T* y, bool flip) {
-  const size_t smem = (size_t)H * W * CS * sizeof(float);
-  QV_CHECK(smem <= 200 * 1024, "dwconv: %dx%d feature map too large for one shared-memory tile", H, W);
-  dim3 grid(B, cdiv(C, CS));
-  if (flip) {
-    if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<T, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dw_fwd_kernel<T, K, true><<<grid, CS * PG, smem, s>>>(x, B, H, W, C, w, bias, y);
-  } else {
-    if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<T, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dw_fwd_kernel<T, K, false><<<grid, CS * PG, smem, s>>>(x, B, H, W, C, w, bias, y);
-  }
+int run_fwd(cudaStream_t s, const DwP& p, bool flip) {
+  const size_t smem = (size_t)p.H * p.W * CS * sizeof(float);
+  QV_CHECK(smem <= 200 * 1024, "dwconv: %dx%d feature map too large for one shared-memory tile", p.H, p.W);
+  dim3 grid(p.B, cdiv(p.C, CS));
+#define DW_GO(F)                                                                                                        \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<T, K, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dw_fwd_kernel<T, K, F><<<grid, CS * PG, smem, s>>>((const T*)p.x, p.ldx, p.H, p.W, p.C, p.w, p.bias, (T*)p.y, p.ldy,  \
+                                                       (const T*)p.resid, p.ldr, (const T*)p.resid2, p.ldr2, (T*)p.copy, p.ldcp); \
+  } while (0)
+  if (flip) DW_GO(true); else DW_GO(false);
+#undef DW_GO
   QV_LAUNCH_CHECK();
   return 0;
 }
 
 template <typename T, int K>
-int run_wgrad(cudaStream_t s, const T* x, const T* dy, int B, int H, int W, int C, float* dw, float* dbias) {
+int run_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias) {
   const size_t tile = (size_t)2 * H * W * CS * sizeof(float), red = (size_t)PG * (K * K + 1) * CS * sizeof(float);
   const size_t smem = tile > red ? tile : red;
   QV_CHECK(smem <= 200 * 1024, "dwconv wgrad: %dx%d feature map too large", H, W);
@@ -128,18 +172,27 @@ int run_wgrad(cudaStream_t s, const T* x, const T* dy, int B, int H, int W, int 
   const int cch = cdiv(C, CS);
   const int occ = max(1, min(6, (int)(200 * 1024 / (smem + 1024))));
   dim3 grid(max(1, min(B, qv_num_sms() * occ / cch)), cch);
-  dw_wgrad_kernel<T, K><<<grid, CS * PG, smem, s>>>(x, dy, B, H, W, C, dw, dbias);
+  dw_wgrad_kernel<T, K><<<grid, CS * PG, smem, s>>>(x, ldx, dy, lddy, B, H, W, C, dw, dbias);
   QV_LAUNCH_CHECK();
   return 0;
 }
 
 template <typename T>
-int dispatch(cudaStream_t s, int op, int K, const T* a, const T* b2, int B, int H, int W, int C, const float* w,
-             const float* bias, T* out, float* dw, float* dbias) {
+int fwd_t(cudaStream_t s, const DwP& p, bool flip) {
+  switch (p.K) {
+    case 3: return run_fwd<T, 3>(s, p, flip);
+    case 5: return run_fwd<T, 5>(s, p, flip);
+    case 7: return run_fwd<T, 7>(s, p, flip);
+  }
+  qv_set_error("dwconv: kernel size %d not supported (3, 5, 7)", p.K);
+  return 1;
+}
+template <typename T>
+int wgrad_t(cudaStream_t s, int K, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias) {
   switch (K) {
-    case 3: return op == 2 ? run_wgrad<T, 3>(s, a, b2, B, H, W, C, dw, dbias) : run_fwd<T, 3>(s, a, B, H, W, C, w, bias, out, op == 1);
-    case 5: return op == 2 ? run_wgrad<T, 5>(s, a, b2, B, H, W, C, dw, dbias) : run_fwd<T, 5>(s, a, B, H, W, C, w, bias, out, op == 1);
-    case 7: return op == 2 ? run_wgrad<T, 7>(s, a, b2, B, H, W, C, dw, dbias) : run_fwd<T, 7>(s, a, B, H, W, C, w, bias, out, op == 1);
+    case 3: return run_wgrad<T, 3>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias);
+    case 5: return run_wgrad<T, 5>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias);
+    case 7: return run_wgrad<T, 7>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias);
   }
   qv_set_error("dwconv: kernel size %d not supported (3, 5, 7)", K);
   return 1;
@@ -147,21 +200,34 @@ int dispatch(cudaStream_t s, int op, int K, const T* a, const T* b2, int B, int 
 
 }  // namespace
 
+int dw2d_fwd(cudaStream_t s, int dt, const DwP& p, bool flip) {
+  if (p.B <= 0) return 0;
+  QV_CHECK(p.C % 2 == 0 && p.ldx % 2 == 0, "dwconv: channel count / row pitch must be even");
+  return dt == QV_BF16 ? fwd_t<bf16>(s, p, flip) : fwd_t<float>(s, p, flip);
+}
+int dw2d_wgrad(cudaStream_t s, int dt, int K, const void* x, int ldx, const void* dy, int lddy, int B, int H, int W, int C,
+               float* dw, float* dbias) {
+  if (B <= 0) return 0;
+  QV_CHECK(C % 2 == 0 && ldx % 2 == 0 && lddy % 2 == 0, "dwconv wgrad: channel count / row pitch must be even");
+  if (dt == QV_BF16) return wgrad_t<bf16>(s, K, (const bf16*)x, ldx, (const bf16*)dy, lddy, B, H, W, C, dw, dbias);
+  return wgrad_t<float>(s, K, (const float*)x, ldx, (const float*)dy, lddy, B, H, W, C, dw, dbias);
+}
+
 extern "C" int qavit_dwconv_forward(const void* x, int is_bf16, int B, int H, int W, int C, int K, const float* w,
                                     const float* bias, void* y, void* stream) {
-  if (B <= 0) return 0;
-  if (is_bf16) return dispatch<bf16>((cudaStream_t)stream, 0, K, (const bf16*)x, nullptr, B, H, W, C, w, bias, (bf16*)y, nullptr, nullptr);
-  return dispatch<float>((cudaStream_t)stream, 0, K, (const float*)x, nullptr, B, H, W, C, w, bias, (float*)y, nullptr, nullptr);
+  DwP p{};
+  p.x = x; p.ldx = C; p.B = B; p.H = H; p.W = W; p.C = C; p.K = K; p.w = w; p.bias = bias; p.y = y; p.ldy = C;
+  return dw2d_fwd((cudaStream_t)stream, is_bf16 ? QV_BF16 : QV_F32, p, false);
 }
 
 extern "C" int qavit_dwconv_backward(const void* x, const void* dy, int is_bf16, int B, int H, int W, int C, int K,
                                      const float* w, void* dx, float* dw, float* dbias, void* stream) {
-  if (B <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (is_bf16) {
-    if (dx) QV_TRY(dispatch<bf16>(s, 1, K, (const bf16*)dy, nullptr, B, H, W, C, w, nullptr, (bf16*)dx, nullptr, nullptr));
-    return dispatch<bf16>(s, 2, K, (const bf16*)x, (const bf16*)dy, B, H, W, C, nullptr, nullptr, nullptr, dw, dbias);
+  const int dt = is_bf16 ? QV_BF16 : QV_F32;
+  if (dx) {
+    DwP p{};
+    p.x = dy; p.ldx = C; p.B = B; p.H = H; p.W = W; p.C = C; p.K = K; p.w = w; p.y = dx; p.ldy = C;
+    QV_TRY(dw2d_fwd(s, dt, p, true));
   }
-  if (dx) QV_TRY(dispatch<float>(s, 1, K, (const float*)dy, nullptr, B, H, W, C, w, nullptr, (float*)dx, nullptr, nullptr));
-  return dispatch<float>(s, 2, K, (const float*)x, (const float*)dy, B, H, W, C, nullptr, nullptr, nullptr, dw, dbias);
+  return dw2d_wgrad(s, dt, K, x, C, dy, C, B, H, W, C, dw, dbias);
 }

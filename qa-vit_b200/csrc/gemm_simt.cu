@@ -86,6 +86,10 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtArgs p) {
       float val = acc[r][c];
       if (e.bias && blockIdx.z == 0) val += e.bias[gj];
       val *= s_pre;
+      if (e.gmul) {
+        const long gi_ = (long)gi * e.ldg + gj;
+        val *= gelu_grad_f(e.g_bf16 ? ldf(static_cast<const bf16*>(e.gmul) + gi_) : static_cast<const float*>(e.gmul)[gi_]);
+      }
       if (e.C) {
         if (e.c_f32) {
           float* c_ = static_cast<float*>(e.C) + (long)gi * e.ldc + gj;
@@ -97,7 +101,12 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtArgs p) {
         }
       }
       if (e.C2) {
-        float v2 = e.gelu ? gelu_f(val) : (e.resid ? e.resid[(long)gi * e.ldr + gj] : 0.f) + s_res * val;
+        float rv = 0.f;
+        if (e.resid) {
+          const long ri = (long)gi * e.ldr + gj;
+          rv = e.r_bf16 ? ldf(static_cast<const bf16*>(e.resid) + ri) : static_cast<const float*>(e.resid)[ri];
+        }
+        float v2 = e.gelu ? gelu_f(val) : rv + s_res * val;
         if (e.c2_f32) static_cast<float*>(e.C2)[(long)gi * e.ldc2 + gj] = v2;
         else stf(static_cast<bf16*>(e.C2) + (long)gi * e.ldc2 + gj, v2);
       }

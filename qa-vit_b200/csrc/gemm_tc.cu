@@ -215,6 +215,40 @@ __device__ __forceinline__ void stage_fill_f32(uint8_t* st, const float* R, long
   }
 }
 
+// bf16 global [32 rows x gw cols] -> staging (row-contiguous 16 B reads)
+__device__ __forceinline__ void stage_fill_bf16(uint8_t* st, const bf16* R, long ldr, long row0, int M, int col0, int gw, int lane) {
+  const int cpr = gw / 8;                                      // 4 or 2
+  const int sh = (cpr == 4) ? 2 : 1;
+  for (int k = 0; k < cpr; ++k) {
+    const int idx = k * 32 + lane, r = idx >> sh, ch = idx & (cpr - 1);
+    const long row = row0 + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row < M) v = *reinterpret_cast<const uint4*>(R + row * ldr + col0 + ch * 8);
+    *reinterpret_cast<uint4*>(st + r * EPI_ROWB + ch * 16) = v;
+  }
+}
+// 16 staged values of this thread's row, chunk c
+__device__ __forceinline__ void stage_read16(const uint8_t* my_row, int c, bool f32, float* r) {
+  if (f32) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(my_row + (c * 16 + j) * 4);
+      r[j] = q.x; r[j + 1] = q.y; r[j + 2] = q.z; r[j + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 q = *reinterpret_cast<const uint4*>(my_row + c * 32 + h * 16);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        r[h * 8 + 2 * i] = f.x; r[h * 8 + 2 * i + 1] = f.y;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, NtArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -299,6 +333,10 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint8_t* st = epi_stage + (warp - 2) * EPI_WARP_BYTES;
     uint8_t* my_row = st + lane * EPI_ROWB;
     const bool use_resid = e.C2 && !e.gelu && e.resid;
+    const bool use_gmul = !use_resid && e.gmul != nullptr;
+    const void* aux = use_resid ? e.resid : e.gmul;
+    const long aux_ld = use_resid ? e.ldr : e.ldg;
+    const bool aux_f32 = use_resid ? !e.r_bf16 : !e.g_bf16;
     const int ncols = min(p.BN, p.N - n0);
     int acc = 0;
     uint32_t aph = 0;
@@ -312,18 +350,13 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
         for (int c = 0; c < 2; ++c)
           if (c < nch) tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g + c * 16), v[c]);
-        if (use_resid) {
-          stage_fill_f32(st, e.resid, e.ldr, row0, p.M, n0 + g, gw, lane);
+        if (use_resid || use_gmul) {
+          if (aux_f32) stage_fill_f32(st, static_cast<const float*>(aux), aux_ld, row0, p.M, n0 + g, gw, lane);
+          else stage_fill_bf16(st, static_cast<const bf16*>(aux), aux_ld, row0, p.M, n0 + g, gw, lane);
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < 2; ++c)
-            if (c < nch) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 q = *reinterpret_cast<const float4*>(my_row + (c * 16 + j) * 4);
-                r[c][j] = q.x; r[c][j + 1] = q.y; r[c][j + 2] = q.z; r[c][j + 3] = q.w;
-              }
-            }
+            if (c < nch) stage_read16(my_row, c, aux_f32, r[c]);
           __syncwarp();
         }
 #pragma unroll
@@ -332,6 +365,10 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             tmem_ld_wait16(v[c]);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[c][j] = (v[c][j] + bias_s[g + c * 16 + j]) * s_pre;
+            if (use_gmul) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[c][j] *= gelu_grad_fast_f(r[c][j]);
+            }
           }
         if (e.C) {
 #pragma unroll
@@ -347,7 +384,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (c < nch) {
               if (e.gelu) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[c][j] = gelu_f(v[c][j]);
+                for (int j = 0; j < 16; ++j) v[c][j] = gelu_fast_f(v[c][j]);
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[c][j] = s_res * v[c][j] + (use_resid ? r[c][j] : 0.f);
@@ -380,6 +417,8 @@ struct TnArgs {
   uint32_t tmem_cols;
   float* dW;
   const float* scale;
+  int transposed;      // write dW[k * ldw + n] instead of dW[n * K + k]
+  int ldw;
 };
 
 __global__ void __launch_bounds__(TN_THREADS, 1)
@@ -456,7 +495,13 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
       for (int c0 = 0; c0 < p.KD; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-        if (n < p.N) {
+        if (p.transposed) {
+          if (n < p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.K) atomicAdd(p.dW + (long)(c0 + j) * p.ldw + n, v[j] * sc);   // lanes = consecutive n: coalesced
+          }
+        } else if (n < p.N) {
           float* dst = p.dW + (long)n * p.K + c0;
           if (c0 + 16 <= p.K && (p.K & 3) == 0) {      // 16 B vector reductions: 4x fewer RED instructions
 #pragma unroll
@@ -552,7 +597,8 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
   QV_TRY(make_map(&mw, Wb, N, K, K, p.BN));
   QV_CHECK((!e.C || (e.ldc % (e.c_f32 ? 4 : 8) == 0 && ((uintptr_t)e.C & 15) == 0)) &&
                (!e.C2 || (e.ldc2 % (e.c2_f32 ? 4 : 8) == 0 && ((uintptr_t)e.C2 & 15) == 0)) &&
-               (!e.resid || (e.ldr % 4 == 0 && ((uintptr_t)e.resid & 15) == 0)),
+               (!e.resid || (e.ldr % (e.r_bf16 ? 8 : 4) == 0 && ((uintptr_t)e.resid & 15) == 0)) &&
+               (!e.gmul || (e.ldg % (e.g_bf16 ? 8 : 4) == 0 && ((uintptr_t)e.gmul & 15) == 0)),
            "tc_gemm_nt: outputs / residual must be 16 B aligned with 16 B-multiple row pitch");
   p.stages = p.BN > 208 ? 3 : STAGES;
   const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2) + 256 + EPI_WARPS * EPI_WARP_BYTES + 1024;
@@ -565,7 +611,7 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
 }
 
 int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
-               const float* scale) {
+               const float* scale, int transposed, int ldw) {
   if (M <= 0) return 0;
   QV_CHECK(tc_shape_ok_tn(M, N, K, ldy, ldx), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
   TnArgs p{};
@@ -576,6 +622,8 @@ int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, 
   p.tmem_cols = pow2_cols(p.KD);
   p.dW = dW;
   p.scale = scale;
+  p.transposed = transposed;
+  p.ldw = ldw;
   const int n_tiles = cdiv(N, BM);
   // Every CTA ends with 128 x K fp32 atomics, so a CTA must own enough rows to amortise them: >= 16 m-blocks
   // (1024 rows) each, and no more CTAs than SMs.

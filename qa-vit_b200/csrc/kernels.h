@@ -8,13 +8,18 @@ enum { QV_F32 = 0, QV_BF16 = 1 };
 // Epilogue of every GEMM flavour:  val = acc (+ bias[j]);  if (scale_pre) val *= *scale_pre;
 //   C  [i, j] (T or fp32; += if c_accum)  = val            (pre-activation when gelu != 0)
 //   C2 [i, j] (T or fp32)                 = gelu ? gelu(val) : resid[i, j] + (scale_res ? *scale_res : 1) * val
+// gmul (dX GEMMs that feed a GELU backward): val *= gelu'(gmul[i, j]) before C is written; not combined with resid.
 struct GemmEpi {
   const float* bias = nullptr;
   const float* scale_pre = nullptr;
   const float* scale_res = nullptr;
   int gelu = 0;
-  const float* resid = nullptr;
+  const void* resid = nullptr;   // fp32, or bf16 when r_bf16
   int ldr = 0;
+  int r_bf16 = 0;
+  const void* gmul = nullptr;    // fp32, or bf16 when g_bf16: the stored pre-activation
+  int ldg = 0;
+  int g_bf16 = 0;
   void* C = nullptr;
   int ldc = 0;
   int c_f32 = 0;
@@ -48,8 +53,10 @@ int simt_gemm_tn(cudaStream_t s, int dt, const void* dY, int ldy, const void* X,
 
 // tcgen05 / TMEM / TMA flavours (bf16 operands, fp32 accumulate)
 int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, const bf16* Wb, const GemmEpi& e);
+// transposed != 0: the product is written transposed, dW[k * ldw + n] (lets a weight gradient with K > 256 be
+// computed as X^T dY, whose accumulator width is N)
 int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
-               const float* scale);
+               const float* scale, int transposed = 0, int ldw = 0);
 bool tc_shape_ok_nt(int M, int N, int K, int lda);
 bool tc_shape_ok_tn(int M, int N, int K, int ldy, int ldx);
 int colsum_accum(cudaStream_t s, int dt, const void* dY, int ldy, int M, int N, float* db, const float* scale);
@@ -57,6 +64,55 @@ int convert_weight(cudaStream_t s, const float* w, int N, int K, bf16* wb, bf16*
 struct ConvertJob { const float* w; int N, K; bf16* wb; bf16* wbt; };
 struct ConvertJobs { ConvertJob j[24]; int n; };
 int convert_weights_batched(cudaStream_t s, const ConvertJobs& jobs);   // all fp32 -> bf16 (+ transposed) copies, one launch
+
+// ---- depthwise k x k stencils on channels-last maps (dwconv_nhwc.cu).  Row pitches in elements; resid / resid2 are
+// added to the output, copy receives the input tile (LMFAdapter's identity branch); all optional.
+struct DwP {
+  const void* x; int ldx;
+  int B, H, W, C, K;
+  const float* w; const float* bias;
+  void* y; int ldy;
+  const void* resid; int ldr;
+  const void* resid2; int ldr2;
+  void* copy; int ldcp;
+};
+int dw2d_fwd(cudaStream_t s, int dt, const DwP& p, bool flip);
+int dw2d_wgrad(cudaStream_t s, int dt, int K, const void* x, int ldx, const void* dy, int lddy, int B, int H, int W, int C,
+               float* dw, float* dbias);
+
+// ---- lateral path / SplitFusion kernels (lateral_kernels.cu)
+// BatchNorm over rows of [rows, C] (+ GELU): mr[2C] = per-channel mean | rstd (kept for backward), sums_scratch[2C].
+int bn_fwd(cudaStream_t s, int dt, const void* x, long rows, int C, const float* gamma, const float* beta, float eps,
+           float momentum, int train, float* running_mean, float* running_var, long long* num_batches, int gelu,
+           float* sums_scratch, float* mr, void* y);
+int bn_bwd(cudaStream_t s, int dt, const void* x, const void* dy, long rows, int C, const float* gamma, const float* beta,
+           const float* mr, int train, int gelu, float* sums_scratch, void* dx, float* dgamma, float* dbeta);
+// 3x3 stride-2 pad-1 convolution as GEMM: column order k = (ky * 3 + kx) * Cin + cin
+int im2col_img(cudaStream_t s, int dt, const float* img, int B, int Cin, int S, int Kp, void* col);
+int im2col_nhwc(cudaStream_t s, int dt, const void* x, int B, int Hi, int Cin, void* col);
+int col2im_nhwc(cudaStream_t s, int dt, const void* dcol, int B, int Hi, int Cin, void* dx);
+int conv_w_pack(cudaStream_t s, const float* W, int N, int Cin, int Kp, float* Wp);
+int conv_w_unpack_add(cudaStream_t s, const float* dWp, int N, int Cin, int Kp, float* dW);
+// y = [resid +] [*scale *] f(LN(x)), f = GELU when gelu_out
+// (x / dx: dt; y / resid: dt_y; y32: optional extra fp32 copy of y; dy: dt_dy)
+int rowln_fwd(cudaStream_t s, int dt, const void* x, long rows, int C, const float* gamma, const float* beta, float eps,
+              int gelu_out, int dt_y, const void* resid, const float* scale, void* y, float* y32, float* stats);
+int rowln_bwd(cudaStream_t s, int dt, const void* x, int dt_dy, const void* dy, long rows, int C, const float* gamma, const float* beta,
+              const float* stats, int gelu_out, const float* scale, float* dscale, void* dx, float* dgamma, float* dbeta);
+struct SfArgs {
+  const float* Tin; const float* R; const void* glin; const void* cpre;
+  const float *cat_g, *cat_b, *fin_g, *fin_b, *fw;
+  float drop_p; const unsigned long long* rng; uint32_t site;
+  long rows; int C;
+};
+int sf_pre_fwd(cudaStream_t s, int dt, const float* Tin, const float* R, long rows, int C, const float* gamma, const float* beta,
+               void* g_in, void* cat, float* stats);
+int sf_post_fwd(cudaStream_t s, int dt, const SfArgs& a, float* out, float* cat_stats, float* fin_stats);
+int sf_post_bwd(cudaStream_t s, int dt, const SfArgs& a, const float* dout, const float* cat_stats, const float* fin_stats, float* dT,
+                float* dR, void* dglin, void* dcpre, float* d_fin_g, float* d_fin_b, float* d_cat_g, float* d_cat_b, float* draw);
+int sf_pre_bwd(cudaStream_t s, int dt, const float* Tin, const float* R, const void* dg_in, const void* dcat, long rows, int C,
+               const float* gamma, const float* stats, float* dT, float* dR, float* dgamma, float* dbeta);
+int rng_snapshot_advance(cudaStream_t s, unsigned long long* rng, unsigned long long* snap);
 
 // ---- norms
 int ln_fwd(cudaStream_t s, int dt_in, const void* x, int ldx, int rows, int C, const float* gamma, const float* beta,

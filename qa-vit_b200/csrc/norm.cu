@@ -7,51 +7,6 @@
 
 namespace {
 
-template <int EPL>
-__device__ __forceinline__ void load_vec(const float* p, float* v) {
-#pragma unroll
-  for (int i = 0; i < EPL; i += 4) {
-    const float4 q = *reinterpret_cast<const float4*>(p + i);
-    v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
-  }
-}
-template <int EPL>
-__device__ __forceinline__ void load_vec(const bf16* p, float* v) {
-  if (EPL == 8) {
-    const uint4 q = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-      v[2 * i] = f.x; v[2 * i + 1] = f.y;
-    }
-  } else {
-    const uint2 q = *reinterpret_cast<const uint2*>(p);
-    const uint32_t w[2] = {q.x, q.y};
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-      v[2 * i] = f.x; v[2 * i + 1] = f.y;
-    }
-  }
-}
-template <int EPL>
-__device__ __forceinline__ void store_vec(float* p, const float* v) {
-#pragma unroll
-  for (int i = 0; i < EPL; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-}
-template <int EPL>
-__device__ __forceinline__ void store_vec(bf16* p, const float* v) {
-  uint32_t w[EPL / 2];
-#pragma unroll
-  for (int i = 0; i < EPL / 2; ++i) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    w[i] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  if (EPL == 8) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-  else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[EPL / 2 - 1]);
-}
-
 template <typename TI, typename TO, int EPL, bool GELU_IN>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, int ldx, int rows, int C,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import BlockCfg, QP_COUNT, check, lib
+from ._lib import BlockCfg, LateralCfg, QP_COUNT, SplitFusionCfg, check, lib
 
 _scratch = {}
 
@@ -366,6 +366,145 @@ def conv1x1(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
     B, C_, H, W_ = x.shape
     y = linear(x.permute(0, 2, 3, 1), conv.weight, conv.bias)          # [B, H, W, N]; no copy for channels_last x
     return y.permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------------------------------------ dropout RNG state
+_rng_states = {}
+
+
+def rng_state(device) -> torch.Tensor:
+    """Device-resident Philox state [seed, offset] (int64) behind every in-kernel dropout: forward calls snapshot it
+    into their saved buffer and advance the offset on the device, so CUDA-graph replays draw fresh masks."""
+    t = _rng_states.get(device)
+    if t is None:
+        t = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        _rng_states[device] = t
+    return t
+
+
+def manual_seed(seed: int) -> None:
+    """Re-seed the dropout generators of every device (offset back to 0)."""
+    for dev, t in _rng_states.items():
+        t.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+
+
+def _param_array(tensors, n):
+    arr = (C.c_void_p * n)()
+    for i, t in enumerate(tensors):
+        if not t.is_contiguous() or t.dtype not in (torch.float32, torch.int64):
+            raise RuntimeError("qavit_b200: parameters / buffers must be contiguous fp32 (int64 counters) tensors")
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _grad_arrays(tensors, skip, device):
+    """ctypes array of gradient accumulators (+ the values to hand back to autograd): attached .grad buffers are
+    accumulated in place, the rest share one zeroed flat allocation."""
+    direct, sizes, targets = [], [], []
+    for i, t in enumerate(tensors):
+        if i in skip or not t.requires_grad:
+            targets.append(None)
+            sizes.append(0)
+            continue
+        g = _inplace_target(t)
+        targets.append(g)
+        sizes.append(0 if g is not None else (t.numel() + 3) // 4 * 4)
+        if g is not None:
+            direct.append(t)
+    gbuf = torch.zeros(sum(sizes), dtype=torch.float32, device=device) if sum(sizes) else None
+    arr = (C.c_void_p * len(tensors))()
+    views, off = [], 0
+    for i, (t, n, g) in enumerate(zip(tensors, sizes, targets)):
+        if g is not None:
+            arr[i] = g.data_ptr()
+            views.append(None)
+        elif n == 0:
+            views.append(None)
+        else:
+            v = gbuf[off:off + t.numel()].view(t.shape)
+            arr[i] = v.data_ptr()
+            views.append(v)
+            off += n
+    return arr, views, direct
+
+
+class LateralMeta:
+    def __init__(self, cfg: LateralCfg, buffer_idx):
+        self.cfg = cfg
+        self.buffers = set(buffer_idx)      # indices of BatchNorm running statistics / counters (no gradient)
+
+
+class LateralFn(torch.autograd.Function):
+    """CNNStemModel -> LMFAdapter x3 -> RRCV x3 (HQAViT_CIFAR100.py:1236-1247): image -> (R2, R3, R4)."""
+
+    @staticmethod
+    def forward(ctx, img, meta: LateralMeta, *tensors):
+        _require_cuda(img, "image batch")
+        img = img.detach().float().contiguous()
+        cfg = meta.cfg
+        saved_b, scratch_b = C.c_size_t(0), C.c_size_t(0)
+        check(lib.qavit_lateral_workspace(C.byref(cfg), C.byref(saved_b), C.byref(scratch_b)))
+        saved = torch.empty(saved_b.value, dtype=torch.uint8, device=img.device)
+        scratch = _scratch_buf(img.device, scratch_b.value)
+        params = _param_array(tensors, len(tensors))
+        N = cfg.grid * cfg.grid
+        R = [torch.empty(cfg.batch, N, cfg.dim, dtype=torch.float32, device=img.device) for _ in range(3)]
+        check(lib.qavit_lateral_forward(C.byref(cfg), params, img.data_ptr(), R[0].data_ptr(), R[1].data_ptr(), R[2].data_ptr(),
+                                        saved.data_ptr(), scratch.data_ptr(), _stream()))
+        ctx.meta, ctx.saved_buf, ctx.img, ctx.params_arr, ctx.tensors = meta, saved, img, params, tensors
+        return tuple(R)
+
+    @staticmethod
+    def backward(ctx, dR2, dR3, dR4):
+        meta, img = ctx.meta, ctx.img
+        cfg = meta.cfg
+        dRs = [None if g is None else g.float().contiguous() for g in (dR2, dR3, dR4)]
+        grads_arr, views, direct = _grad_arrays(ctx.tensors, meta.buffers, img.device)
+        saved_b, scratch_b = C.c_size_t(0), C.c_size_t(0)
+        check(lib.qavit_lateral_workspace(C.byref(cfg), C.byref(saved_b), C.byref(scratch_b)))
+        scratch = _scratch_buf(img.device, scratch_b.value)
+        check(lib.qavit_lateral_backward(C.byref(cfg), ctx.params_arr, grads_arr, img.data_ptr(), _ptr(dRs[0]), _ptr(dRs[1]),
+                                         _ptr(dRs[2]), ctx.saved_buf.data_ptr(), scratch.data_ptr(), _stream()))
+        ctx.saved_buf = None
+        _notify(direct)
+        return (None, None, *views)
+
+
+class SplitFusionFn(torch.autograd.Function):
+    """SplitFusion.forward -- HQAViT_CIFAR100.py:945-963."""
+
+    @staticmethod
+    def forward(ctx, T_in, R, cfg: SplitFusionCfg, *tensors):
+        _require_cuda(T_in, "SplitFusion input")
+        T_in = T_in.detach().float().contiguous()
+        R = R.detach().float().contiguous()
+        saved_b, scratch_b = C.c_size_t(0), C.c_size_t(0)
+        check(lib.qavit_splitfusion_workspace(C.byref(cfg), C.byref(saved_b), C.byref(scratch_b)))
+        saved = torch.empty(saved_b.value, dtype=torch.uint8, device=T_in.device)
+        scratch = _scratch_buf(T_in.device, scratch_b.value)
+        params = _param_array(tensors, len(tensors))
+        out = torch.empty_like(T_in)
+        rng = rng_state(T_in.device) if (cfg.train and cfg.drop_p > 0) else None
+        check(lib.qavit_splitfusion_forward(C.byref(cfg), params, _ptr(rng), T_in.data_ptr(), R.data_ptr(), out.data_ptr(),
+                                            saved.data_ptr(), scratch.data_ptr(), _stream()))
+        ctx.cfg, ctx.saved_buf, ctx.T_in, ctx.R, ctx.params_arr, ctx.tensors = cfg, saved, T_in, R, params, tensors
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg, T_in, R = ctx.cfg, ctx.T_in, ctx.R
+        dout = dout.float().contiguous()
+        grads_arr, views, direct = _grad_arrays(ctx.tensors, (), T_in.device)
+        saved_b, scratch_b = C.c_size_t(0), C.c_size_t(0)
+        check(lib.qavit_splitfusion_workspace(C.byref(cfg), C.byref(saved_b), C.byref(scratch_b)))
+        scratch = _scratch_buf(T_in.device, scratch_b.value)
+        dT = torch.empty_like(T_in)
+        dR = torch.empty_like(R)
+        check(lib.qavit_splitfusion_backward(C.byref(cfg), ctx.params_arr, grads_arr, T_in.data_ptr(), R.data_ptr(), dout.data_ptr(),
+                                             dT.data_ptr(), dR.data_ptr(), ctx.saved_buf.data_ptr(), scratch.data_ptr(), _stream()))
+        ctx.saved_buf = None
+        _notify(direct)
+        return (dT, dR, None, *views)
 
 
 class CrossEntropyFn(torch.autograd.Function):

@@ -4,8 +4,8 @@ Same constructor arguments (a duck-typed config dataclass), same attribute / par
 ``state_dict()`` keys, including the GlobalTokenBank entries aliased under every branch -- and the same
 ``forward(x[B, C, S, S]) -> logits[B, classes]``.  The encoder blocks, patch embedding and
 head run through the hand-written sm_100a kernels behind include/qavit_b200.h; there is no eager fallback.
-HQAViT's CNN lateral path (cnn_stem / lmfa / rrcv / fuse) is scope row (f)-1 ("next") and is expressed with
-stock torch modules for now.
+HQAViT's CNN lateral path (cnn_stem / lmfa / rrcv) is one native call per direction (qavit_lateral_*), SplitFusion
+another (qavit_splitfusion_*); their sub-modules only hold parameters under the reference's names.
 
 Reference: HQAViT_CIFAR100.py (H), QAViT.py, QAViTv2.py, QAViTv2_CIFAR100.py, HQAViT_IN_Tiny.py.
 """
@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as QF
-from ._lib import PARAMS, QP, BlockCfg
+from ._lib import PARAMS, QP, SPLITFUSION_PARAMS, BlockCfg, LateralCfg, SplitFusionCfg, lateral_param_names
 
 
 # --------------------------------------------------------------------------------------------- configs
@@ -346,8 +346,9 @@ class _Base(nn.Module):
     def set_precision(self, precision: str):
         """'auto' (bf16 under torch.autocast, else fp32), 'fp32' or 'bf16' for every native block."""
         assert precision in ("auto", "fp32", "bf16")
+        self.precision = precision
         for m in self.modules():
-            if isinstance(m, QuadAttentionBlock):
+            if isinstance(m, (QuadAttentionBlock, SplitFusion)):
                 m.precision = precision
         return self
 
@@ -385,36 +386,28 @@ class QAViT(_Base):
         return QF.HeadFn.apply(T, self.norm.weight, self.norm.bias, self.head.weight, self.head.bias)
 
 
-# --------------------------------------------------------------------------------------------- HQAViT lateral path ("next" row f-1)
-class LayerNorm(nn.LayerNorm):
-    """nn.LayerNorm (same parameters / state_dict entries) whose CUDA forward + backward are the library's one-pass
-    warp-per-row kernels: torch's LayerNorm gamma/beta backward was 11 % of the first profiled step."""
+# --------------------------------------------------------------------------------------------- HQAViT lateral path (row f-1)
+class _LateralHolder(nn.Module):
+    """The lateral modules hold parameters / buffers under the reference's names; their arithmetic is part of ONE native
+    call per direction (HQAViT.lateral -> qavit_lateral_forward / backward)."""
 
-    def forward(self, x):
-        if x.is_cuda and self.normalized_shape[0] <= 256 and len(self.normalized_shape) == 1:
-            return QF.LayerNormFn.apply(x, self.weight, self.bias, self.eps)
-        return super().forward(x)
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError(f"{type(self).__name__} is fused into HQAViT.lateral()'s native call (qavit_lateral_forward)")
 
 
-
-class ConvNeXtBlock(nn.Module):
+class ConvNeXtBlock(_LateralHolder):
     """H:718-739."""
 
     def __init__(self, dim, drop_path=0.):
         super().__init__()
         self.dwconv = nn.Conv2d(dim, dim, kernel_size=7, padding=3, groups=dim)
-        self.norm = LayerNorm(dim, eps=1e-6)
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
         self.pwconv1 = nn.Linear(dim, 4 * dim)
         self.act = nn.GELU()
         self.pwconv2 = nn.Linear(4 * dim, dim)
 
-    def forward(self, x):
-        h = (QF.depthwise_conv(x, self.dwconv) if x.is_cuda else self.dwconv(x)).permute(0, 2, 3, 1)
-        h = self.pwconv2(self.act(self.pwconv1(self.norm(h))))
-        return x + h.permute(0, 3, 1, 2)
 
-
-class CNNStemModel(nn.Module):
+class CNNStemModel(_LateralHolder):
     """H:742-793."""
 
     def __init__(self, in_ch=3, c2=64, c3=128, c4=256):
@@ -424,13 +417,8 @@ class CNNStemModel(nn.Module):
         self.stage2 = nn.Sequential(nn.Conv2d(c2, c3, 1), nn.BatchNorm2d(c3), ConvNeXtBlock(c3))
         self.stage3 = nn.Sequential(nn.Conv2d(c3, c4, 1), nn.BatchNorm2d(c4), ConvNeXtBlock(c4))
 
-    def forward(self, x):
-        f2 = self.stage1(self.stem(x))
-        f3 = self.stage2(f2)
-        return f2, f3, self.stage3(f3)
 
-
-class LMFAdapter(nn.Module):
+class LMFAdapter(_LateralHolder):
     """H:799-849."""
 
     def __init__(self, in_channels: int, embed_dim: int, target_hw: int = 8):
@@ -439,22 +427,11 @@ class LMFAdapter(nn.Module):
         self.dwconv_3x3 = nn.Conv2d(in_channels, in_channels, 3, padding=1, groups=in_channels)
         self.dwconv_5x5 = nn.Conv2d(in_channels, in_channels, 5, padding=2, groups=in_channels)
         self.proj = nn.Conv2d(3 * in_channels, embed_dim, 1)
-        self.norm = LayerNorm(embed_dim)
+        self.norm = nn.LayerNorm(embed_dim)
         self.act = nn.GELU()
 
-    def forward(self, feat):
-        if feat.is_cuda:
-            f1, f2 = QF.depthwise_conv(feat, self.dwconv_3x3), QF.depthwise_conv(feat, self.dwconv_5x5)
-            feat = feat.to(f1.dtype)
-        else:
-            f1, f2 = self.dwconv_3x3(feat), self.dwconv_5x5(feat)
-        f = self.proj(torch.cat([f1, f2, feat], dim=1))
-        if f.shape[2] != self.target_hw or f.shape[3] != self.target_hw:
-            f = F.interpolate(f, size=(self.target_hw, self.target_hw), mode="bilinear", align_corners=False)
-        return self.act(self.norm(f.permute(0, 2, 3, 1).reshape(f.shape[0], -1, f.shape[1])))   # NHWC view: no copy in channels_last
 
-
-class RRCV(nn.Module):
+class RRCV(_LateralHolder):
     """H:855-907."""
 
     def __init__(self, embed_dim: int, rec_channels: int = 64, num_blocks: int = 1):
@@ -462,35 +439,38 @@ class RRCV(nn.Module):
         self.reverse_proj = nn.Conv2d(embed_dim, rec_channels, 1)
         self.blocks = nn.ModuleList([ConvNeXtBlock(rec_channels) for _ in range(num_blocks)])
         self.reembed_proj = nn.Conv2d(rec_channels, embed_dim, 1)
-        self.norm = LayerNorm(embed_dim)
+        self.norm = nn.LayerNorm(embed_dim)
         self.beta = nn.Parameter(torch.tensor(0.1))
-
-    def forward(self, A, H: int, W: int):
-        B, N, C = A.shape
-        r = self.reverse_proj(A.reshape(B, H, W, C).permute(0, 3, 1, 2))   # tokens ARE the NHWC feature map: channels_last view, no copy
-        for blk in self.blocks:
-            r = blk(r)
-        r = self.reembed_proj(r).permute(0, 2, 3, 1).reshape(B, N, C)
-        return A + self.beta * self.norm(r)
 
 
 class SplitFusion(nn.Module):
-    """H:913-965 (keeps the hard-coded Dropout(0.1) of H:930 as cat_mlp[3])."""
+    """H:913-965 (keeps the hard-coded Dropout(0.1) of H:930 as cat_mlp[3]); one native call per direction."""
 
     def __init__(self, embed_dim: int):
         super().__init__()
-        self.gate_norm = LayerNorm(embed_dim)
+        self.gate_norm = nn.LayerNorm(embed_dim)
         self.gate_fc = nn.Linear(embed_dim, embed_dim)
-        self.cat_mlp = nn.Sequential(nn.Linear(2 * embed_dim, embed_dim), LayerNorm(embed_dim), nn.GELU(), nn.Dropout(0.1))
+        self.cat_mlp = nn.Sequential(nn.Linear(2 * embed_dim, embed_dim), nn.LayerNorm(embed_dim), nn.GELU(), nn.Dropout(0.1))
         self.fusion_weights = nn.Parameter(torch.tensor([0.75, 0.25]))
-        self.final_norm = LayerNorm(embed_dim)
+        self.final_norm = nn.LayerNorm(embed_dim)
+        self.precision = "auto"
 
     def forward(self, T_in, R):
-        gate = torch.sigmoid(self.gate_fc(self.gate_norm(T_in + R)))
-        t_add = T_in + gate * R
-        t_cat = T_in + self.cat_mlp(torch.cat([T_in, R], dim=-1))
-        w = F.softmax(self.fusion_weights, dim=0)
-        return self.final_norm(w[0] * t_add + w[1] * t_cat)
+        B, N, d = T_in.shape
+        c = SplitFusionCfg()
+        c.rows, c.dim = B * N, d
+        c.dtype = QF.resolve_dtype(self.precision)
+        c.train = 1 if self.training else 0
+        c.drop_p = float(self.cat_mlp[3].p)
+        tensors = [_resolve(self, n) for n in SPLITFUSION_PARAMS]
+        return QF.SplitFusionFn.apply(T_in, R, c, *tensors)
+
+
+def _resolve(root, dotted):
+    obj = root
+    for part in dotted.split("."):
+        obj = getattr(obj, part)
+    return obj
 
 
 class HQAViT(_Base):
@@ -533,16 +513,31 @@ class HQAViT(_Base):
         self.head = nn.Linear(d, config.num_classes)
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
         self.apply(_init_weights)
-        for m in (self.cnn_stem, self.lmfa2, self.lmfa3, self.lmfa4, self.rrcv2, self.rrcv3, self.rrcv4):
-            m.to(memory_format=torch.channels_last)
+        self._lateral_names = None
+
+    def lateral(self, x):
+        """cnn_stem -> lmfa{2,3,4} -> rrcv{2,3,4} (H:1236-1247) as one native call: image -> (R2, R3, R4)."""
+        cfg = self.config
+        c = LateralCfg()
+        c.batch, c.img_size, c.in_channels = x.shape[0], x.shape[-1], x.shape[1]
+        c.c_stem = self.cnn_stem.stem[0].out_channels
+        c.c2, c.c3, c.c4 = (self.cnn_stem.stage1[0].out_channels, self.cnn_stem.stage2[0].out_channels,
+                            self.cnn_stem.stage3[0].out_channels)
+        c.rrcv_channels, c.rrcv_blocks = self.rrcv2.reverse_proj.out_channels, len(self.rrcv2.blocks)
+        c.dim, c.grid = cfg.embed_dim, self.H
+        c.train = 1 if self.training else 0
+        c.dtype = QF.resolve_dtype(self.precision)
+        bn = self.cnn_stem.stem[1]
+        c.bn_eps, c.bn_momentum = float(bn.eps), float(bn.momentum)
+        if self._lateral_names is None:
+            self._lateral_names = lateral_param_names(c)
+        names = self._lateral_names
+        tensors = [_resolve(self, n) for n in names]
+        buffers = [i for i, n in enumerate(names) if n.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+        return QF.LateralFn.apply(x, QF.LateralMeta(c, buffers), *tensors)
 
     def forward(self, x):
-        # lateral CNN path in channels_last: cuDNN's NHWC depthwise / pointwise kernels are 1.7x faster here
-        # (measured, tools/lateral_probe.py); memory format does not change values or the state_dict.
-        f2, f3, f4 = self.cnn_stem(x.contiguous(memory_format=torch.channels_last) if x.is_cuda else x)
-        R2 = self.rrcv2(self.lmfa2(f2), self.H, self.W)
-        R3 = self.rrcv3(self.lmfa3(f3), self.H, self.W)
-        R4 = self.rrcv4(self.lmfa4(f4), self.H, self.W)
+        R2, R3, R4 = self.lateral(x)
         T = self.patch_embed(x, self.pos_embed)
         T = self._stream_dropout(T)
         for blk in self.stage1_blocks:
