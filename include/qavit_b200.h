@@ -189,6 +189,10 @@ int qavit_splitfusion_backward(const qavit_splitfusion_cfg* cfg, const void* con
 /* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
 int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,
                        const float* bias, void* C, int c_f32, void* stream);
+/* tcgen05 NT GEMM with the fused epilogues: mode 0: C = A W^T + b | 1: C = pre-activation, C2 = gelu(pre) |
+ * 2: C2 = aux + pre (aux: bf16 residual) | 3: C = pre * gelu'(aux) (aux: bf16 stored pre-activation).  All bf16 [M, N]. */
+int qavit_test_gemm_epi(const void* A, int lda, int M, int N, int K, const void* Wb, const float* bias, void* C, void* C2,
+                        int mode, const void* aux, void* stream);
 int qavit_test_gemm_tn(int use_tc, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW,
                        float* db, void* stream);
 int qavit_convert_weight(const float* w, int N, int K, void* wb, void* wbt, void* stream);

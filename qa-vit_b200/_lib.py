@@ -82,6 +82,7 @@ _SIGS = {
     "qavit_splitfusion_forward": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_splitfusion_backward": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_test_gemm_nt": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "qavit_test_gemm_epi": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "qavit_test_gemm_tn": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "qavit_convert_weight": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
 }

@@ -77,14 +77,10 @@ int gemm_nn(cudaStream_t s, int dt, const void* dY, int ldy, int M, const Weight
 int gemm_tn(cudaStream_t s, int dt, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K, float* dW,
             float* db, const float* scale) {
   if (dt == QV_BF16 && tc_shape_ok_tn(M, N, K, ldy, ldx)) {
-    QV_TRY(tc_gemm_tn(s, (const bf16*)dY, ldy, (const bf16*)X, ldx, M, N, K, dW, scale));
-    if (db) QV_TRY(colsum_accum(s, dt, dY, ldy, M, N, db, scale));
-    return 0;
+    return tc_gemm_tn(s, (const bf16*)dY, ldy, (const bf16*)X, ldx, M, N, K, dW, scale, 0, 0, db, 1, N);
   }
   if (dt == QV_BF16 && K > 256 && tc_shape_ok_tn(M, K, N, ldx, ldy)) {   // wide-K weight: accumulate X^T dY, store transposed
-    QV_TRY(tc_gemm_tn(s, (const bf16*)X, ldx, (const bf16*)dY, ldy, M, K, N, dW, scale, 1, K));
-    if (db) QV_TRY(colsum_accum(s, dt, dY, ldy, M, N, db, scale));
-    return 0;
+    return tc_gemm_tn(s, (const bf16*)X, ldx, (const bf16*)dY, ldy, M, K, N, dW, scale, 1, K, db, 2, N);
   }
   return simt_gemm_tn(s, dt, dY, ldy, X, ldx, M, N, K, dW, db, scale);
 }
@@ -767,13 +763,20 @@ extern "C" int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int
   if (use_tc) return tc_gemm_nt((cudaStream_t)stream, (const bf16*)A, lda, M, N, K, (const bf16*)Wb, e);
   return simt_gemm_nt((cudaStream_t)stream, QV_F32, A, lda, M, N, K, W, e);
 }
+// mode 0: C = A W^T + b | 1: C = pre, C2 = gelu(pre) | 2: C2 = aux + pre (aux bf16 residual) | 3: C = pre * gelu'(aux)
+extern "C" int qavit_test_gemm_epi(const void* A, int lda, int M, int N, int K, const void* Wb, const float* bias, void* C,
+                                   void* C2, int mode, const void* aux, void* stream) {
+  GemmEpi e;
+  e.bias = bias;
+  if (mode == 0 || mode == 1 || mode == 3) { e.C = C; e.ldc = N; }
+  if (mode == 1) { e.gelu = 1; e.C2 = C2; e.ldc2 = N; }
+  if (mode == 2) { e.resid = aux; e.ldr = N; e.r_bf16 = 1; e.C2 = C2; e.ldc2 = N; }
+  if (mode == 3) { e.gmul = aux; e.ldg = N; e.g_bf16 = 1; }
+  return tc_gemm_nt((cudaStream_t)stream, (const bf16*)A, lda, M, N, K, (const bf16*)Wb, e);
+}
 extern "C" int qavit_test_gemm_tn(int use_tc, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K,
                                   float* dW, float* db, void* stream) {
-  if (use_tc) {
-    QV_TRY(tc_gemm_tn((cudaStream_t)stream, (const bf16*)dY, ldy, (const bf16*)X, ldx, M, N, K, dW, nullptr));
-    if (db) QV_TRY(colsum_accum((cudaStream_t)stream, QV_BF16, dY, ldy, M, N, db, nullptr));
-    return 0;
-  }
+  if (use_tc) return gemm_tn((cudaStream_t)stream, QV_BF16, dY, ldy, X, ldx, M, N, K, dW, db, nullptr);   // incl. the wide-K transposed flavour
   return simt_gemm_tn((cudaStream_t)stream, QV_F32, dY, ldy, X, ldx, M, N, K, dW, db, nullptr);
 }
 extern "C" int qavit_convert_weight(const float* w, int N, int K, void* wb, void* wbt, void* stream) {

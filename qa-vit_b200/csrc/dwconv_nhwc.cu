@@ -26,63 +26,122 @@ __device__ __forceinline__ void load_tile(float* xs, const T* __restrict__ x, lo
   }
 }
 
+// 8 x 8 maps: the next image's tile is fetched into registers while the current one is being computed (a CTA
+// otherwise alternates between waiting for its 8 KB tile and computing on it).
+constexpr int NPF = 8 * 8 * (CS / 2) / (CS * PG);   // float2 registers per thread for one 8 x 8 x 64 tile
+template <typename T>
+__device__ __forceinline__ void tile_prefetch(float2* pf, const T* __restrict__ x, long ldx, long row0, int c0, int C) {
+#pragma unroll
+  for (int i = 0; i < NPF; ++i) {
+    const int idx = threadIdx.x + i * CS * PG, p = idx / (CS / 2), cc = (idx % (CS / 2)) * 2;
+    pf[i] = (c0 + cc < C) ? ld2(x + (row0 + p) * ldx + c0 + cc) : make_float2(0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void tile_commit(float* xs, const float2* pf) {
+#pragma unroll
+  for (int i = 0; i < NPF; ++i) {
+    const int idx = threadIdx.x + i * CS * PG, p = idx / (CS / 2), cc = (idx % (CS / 2)) * 2;
+    *reinterpret_cast<float2*>(xs + p * CS + cc) = pf[i];
+  }
+}
+
 // y = conv(x) (+ bias) (+ resid) (+ resid2); FLIP: correlate with the flipped kernel (= the input gradient).
 // copy (optional): also writes the input tile to copy[row, c] (LMFAdapter's identity branch of the concat).
-template <typename T, int K, bool FLIP>
-__global__ void __launch_bounds__(CS * PG) dw_fwd_kernel(const T* __restrict__ x, int ldx, int H, int W, int C,
+// WT > 0: the map width is the compile-time constant WT (8 / 16 / 24): a thread owns a whole output row, loads each
+// input row once (WT shared loads with immediate offsets) and every out-of-range tap is pruned at compile time.
+// WT == 0: generic width, 8-output segments with predicated loads.
+template <typename T, int K, bool FLIP, int WT>
+__global__ void __launch_bounds__(CS * PG) dw_fwd_kernel(const T* __restrict__ x, int ldx, int B, int H, int W, int C,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
                                                          T* y, int ldy, const T* resid, int ldr,
                                                          const T* resid2, int ldr2, T* __restrict__ copy, int ldcp) {
   extern __shared__ float xs[];                 // [H*W][CS]
-  const int b = blockIdx.x, c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS, c = c0 + cl;
+  const int c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS, c = c0 + cl;
   const int HW = H * W;
-  const long row0 = (long)b * HW;
   const bool act = c < C;
-  load_tile(xs, x, ldx, row0, HW, c0, C);
-  float wr[K * K];
+  float wr[K * K];                              // this channel's taps: loaded once, reused for every image of the CTA
 #pragma unroll
   for (int t = 0; t < K * K; ++t) wr[t] = act ? w[c * K * K + (FLIP ? K * K - 1 - t : t)] : 0.f;
   const float bs = (bias && act) ? bias[c] : 0.f;
-  __syncthreads();
-  if (!act) return;
-  if (copy) {
-    for (int p = pg; p < HW; p += PG) stf(copy + (row0 + p) * ldcp + c, xs[p * CS + cl]);
-  }
-  const int segs = (W + SEG - 1) / SEG;
-  for (int task = pg; task < H * segs; task += PG) {
-    const int py = task / segs, px0 = (task % segs) * SEG;
-    float acc[SEG];
-#pragma unroll
-    for (int j = 0; j < SEG; ++j) acc[j] = bs;
-#pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-      const int yy = py + ky - K / 2;
-      if (yy < 0 || yy >= H) continue;
-      float xr[SEG + K - 1];
-#pragma unroll
-      for (int i = 0; i < SEG + K - 1; ++i) {
-        const int xx = px0 + i - K / 2;
-        xr[i] = (xx >= 0 && xx < W) ? xs[(yy * W + xx) * CS + cl] : 0.f;
-      }
-#pragma unroll
-      for (int kx = 0; kx < K; ++kx)
-#pragma unroll
-        for (int j = 0; j < SEG; ++j) acc[j] = fmaf(wr[ky * K + kx], xr[j + kx], acc[j]);
+  constexpr bool kPrefetch = (WT == 8);
+  float2 pf[NPF];
+  if (kPrefetch && (int)blockIdx.x < B) tile_prefetch(pf, x, ldx, (long)blockIdx.x * HW, c0, C);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const long row0 = (long)b * HW;
+    __syncthreads();
+    if (kPrefetch) tile_commit(xs, pf);
+    else load_tile(xs, x, ldx, row0, HW, c0, C);
+    __syncthreads();
+    if (kPrefetch && b + (int)gridDim.x < B) tile_prefetch(pf, x, ldx, (long)(b + gridDim.x) * HW, c0, C);
+    if (!act) continue;
+    if (copy) {
+      for (int p = pg; p < HW; p += PG) stf(copy + (row0 + p) * ldcp + c, xs[p * CS + cl]);
     }
+    if (WT > 0) {
+      for (int py = pg; py < H; py += PG) {
+        float acc[WT > 0 ? WT : 1], rv[WT > 0 ? WT : 1];
+        const long row = row0 + py * WT;
 #pragma unroll
-    for (int j = 0; j < SEG; ++j) {
-      if (px0 + j >= W) break;
-      const long row = row0 + py * W + px0 + j;
-      float v = acc[j];
-      if (resid) v += ldf(resid + row * ldr + c);
-      if (resid2) v += ldf(resid2 + row * ldr2 + c);
-      stf(y + row * ldy + c, v);
+        for (int j = 0; j < WT; ++j) {            // residual loads first: their latency hides behind the stencil
+          acc[j] = bs;
+          rv[j] = resid ? ldf(resid + (row + j) * ldr + c) : 0.f;
+          if (resid2) rv[j] += ldf(resid2 + (row + j) * ldr2 + c);
+        }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const int yy = py + ky - K / 2;
+          if (yy < 0 || yy >= H) continue;
+          const float* xrow = xs + (yy * WT) * CS + cl;
+          float xr[WT > 0 ? WT : 1];
+#pragma unroll
+          for (int i = 0; i < WT; ++i) xr[i] = xrow[i * CS];
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int j = 0; j < WT; ++j)
+              if (j + kx - K / 2 >= 0 && j + kx - K / 2 < WT) acc[j] = fmaf(wr[ky * K + kx], xr[j + kx - K / 2], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < WT; ++j) stf(y + (row + j) * ldy + c, acc[j] + rv[j]);
+      }
+    } else {
+      const int segs = (W + SEG - 1) / SEG;
+      for (int task = pg; task < H * segs; task += PG) {
+        const int py = task / segs, px0 = (task % segs) * SEG;
+        float acc[SEG];
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) acc[j] = bs;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const int yy = py + ky - K / 2;
+          if (yy < 0 || yy >= H) continue;
+          float xr[SEG + K - 1];
+#pragma unroll
+          for (int i = 0; i < SEG + K - 1; ++i) {
+            const int xx = px0 + i - K / 2;
+            xr[i] = (xx >= 0 && xx < W) ? xs[(yy * W + xx) * CS + cl] : 0.f;
+          }
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) acc[j] = fmaf(wr[ky * K + kx], xr[j + kx], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+          if (px0 + j >= W) break;
+          const long row = row0 + py * W + px0 + j;
+          float v = acc[j];
+          if (resid) v += ldf(resid + row * ldr + c);
+          if (resid2) v += ldf(resid2 + row * ldr2 + c);
+          stf(y + row * ldy + c, v);
+        }
+      }
     }
   }
 }
 
 // dw[c, ky, kx] += sum_{b, p} dy[b, p, c] x[b, p + (ky, kx) - K/2, c];  dbias[c] += sum dy
-template <typename T, int K>
+template <typename T, int K, int WT>
 __global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy,
                                                            int lddy, int B, int H, int W, int C, float* __restrict__ dw,
                                                            float* __restrict__ dbias) {
@@ -91,39 +150,80 @@ __global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__
   float* xs = sm;                    // [HW][CS]
   float* gs = sm + HW * CS;          // [HW][CS]
   const int c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS;
-  const int segs = (W + SEG - 1) / SEG;
   float acc[K * K], ab = 0.f;
 #pragma unroll
   for (int t = 0; t < K * K; ++t) acc[t] = 0.f;
+  constexpr bool kPrefetch = (WT == 8);
+  float2 pfx[NPF], pfg[NPF];
+  if (kPrefetch && (int)blockIdx.x < B) {
+    tile_prefetch(pfx, x, ldx, (long)blockIdx.x * HW, c0, C);
+    tile_prefetch(pfg, dy, lddy, (long)blockIdx.x * HW, c0, C);
+  }
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    load_tile(xs, x, ldx, (long)b * HW, HW, c0, C);
-    load_tile(gs, dy, lddy, (long)b * HW, HW, c0, C);
+    if (kPrefetch) {
+      tile_commit(xs, pfx);
+      tile_commit(gs, pfg);
+    } else {
+      load_tile(xs, x, ldx, (long)b * HW, HW, c0, C);
+      load_tile(gs, dy, lddy, (long)b * HW, HW, c0, C);
+    }
     __syncthreads();
-    for (int task = pg; task < H * segs; task += PG) {
-      const int py = task / segs, px0 = (task % segs) * SEG;
-      float g[SEG];
+    if (kPrefetch && b + (int)gridDim.x < B) {
+      tile_prefetch(pfx, x, ldx, (long)(b + gridDim.x) * HW, c0, C);
+      tile_prefetch(pfg, dy, lddy, (long)(b + gridDim.x) * HW, c0, C);
+    }
+    if (WT > 0) {
+      for (int py = pg; py < H; py += PG) {
+        float g[WT > 0 ? WT : 1];
+        const float* grow = gs + (py * WT) * CS + cl;
 #pragma unroll
-      for (int j = 0; j < SEG; ++j) {
-        g[j] = (px0 + j < W) ? gs[(py * W + px0 + j) * CS + cl] : 0.f;
-        ab += g[j];
+        for (int j = 0; j < WT; ++j) { g[j] = grow[j * CS]; ab += g[j]; }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const int yy = py + ky - K / 2;
+          if (yy < 0 || yy >= H) continue;
+          const float* xrow = xs + (yy * WT) * CS + cl;
+          float xr[WT > 0 ? WT : 1];
+#pragma unroll
+          for (int i = 0; i < WT; ++i) xr[i] = xrow[i * CS];
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            float a = acc[ky * K + kx];
+#pragma unroll
+            for (int j = 0; j < WT; ++j)
+              if (j + kx - K / 2 >= 0 && j + kx - K / 2 < WT) a = fmaf(g[j], xr[j + kx - K / 2], a);
+            acc[ky * K + kx] = a;
+          }
+        }
       }
+    } else {
+      const int segs = (W + SEG - 1) / SEG;
+      for (int task = pg; task < H * segs; task += PG) {
+        const int py = task / segs, px0 = (task % segs) * SEG;
+        float g[SEG];
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int yy = py + ky - K / 2;
-        if (yy < 0 || yy >= H) continue;
-        float xr[SEG + K - 1];
-#pragma unroll
-        for (int i = 0; i < SEG + K - 1; ++i) {
-          const int xx = px0 + i - K / 2;
-          xr[i] = (xx >= 0 && xx < W) ? xs[(yy * W + xx) * CS + cl] : 0.f;
+        for (int j = 0; j < SEG; ++j) {
+          g[j] = (px0 + j < W) ? gs[(py * W + px0 + j) * CS + cl] : 0.f;
+          ab += g[j];
         }
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          float a = acc[ky * K + kx];
+        for (int ky = 0; ky < K; ++ky) {
+          const int yy = py + ky - K / 2;
+          if (yy < 0 || yy >= H) continue;
+          float xr[SEG + K - 1];
 #pragma unroll
-          for (int j = 0; j < SEG; ++j) a = fmaf(g[j], xr[j + kx], a);
-          acc[ky * K + kx] = a;
+          for (int i = 0; i < SEG + K - 1; ++i) {
+            const int xx = px0 + i - K / 2;
+            xr[i] = (xx >= 0 && xx < W) ? xs[(yy * W + xx) * CS + cl] : 0.f;
+          }
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            float a = acc[ky * K + kx];
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) a = fmaf(g[j], xr[j + kx], a);
+            acc[ky * K + kx] = a;
+          }
         }
       }
     }
@@ -146,19 +246,39 @@ __global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__
   }
 }
 
+template <typename T, int K, bool F, int WT>
+int launch_fwd(cudaStream_t s, const DwP& p, dim3 grid, size_t smem) {
+  if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<T, K, F, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dw_fwd_kernel<T, K, F, WT><<<grid, CS * PG, smem, s>>>((const T*)p.x, p.ldx, p.B, p.H, p.W, p.C, p.w, p.bias, (T*)p.y, p.ldy,
+                                                         (const T*)p.resid, p.ldr, (const T*)p.resid2, p.ldr2, (T*)p.copy, p.ldcp);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+template <typename T, int K, bool F>
+int launch_fwd_w(cudaStream_t s, const DwP& p, dim3 grid, size_t smem) {
+  switch (p.H == p.W ? p.W : 0) {
+    case 8: return launch_fwd<T, K, F, 8>(s, p, grid, smem);
+    case 16: return launch_fwd<T, K, F, 16>(s, p, grid, smem);
+    case 24: return launch_fwd<T, K, F, 24>(s, p, grid, smem);
+  }
+  return launch_fwd<T, K, F, 0>(s, p, grid, smem);
+}
+
 template <typename T, int K>
 int run_fwd(cudaStream_t s, const DwP& p, bool flip) {
   const size_t smem = (size_t)p.H * p.W * CS * sizeof(float);
   QV_CHECK(smem <= 200 * 1024, "dwconv: %dx%d feature map too large for one shared-memory tile", p.H, p.W);
-  dim3 grid(p.B, cdiv(p.C, CS));
-#define DW_GO(F)                                                                                                        \
-  do {                                                                                                                  \
-    if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<T, K, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    dw_fwd_kernel<T, K, F><<<grid, CS * PG, smem, s>>>((const T*)p.x, p.ldx, p.H, p.W, p.C, p.w, p.bias, (T*)p.y, p.ldy,  \
-                                                       (const T*)p.resid, p.ldr, (const T*)p.resid2, p.ldr2, (T*)p.copy, p.ldcp); \
-  } while (0)
-  if (flip) DW_GO(true); else DW_GO(false);
-#undef DW_GO
+  const int cch = cdiv(p.C, CS);
+  const int occ = max(1, min(4, (int)(200 * 1024 / (smem + 1024))));
+  dim3 grid(max(1, min(p.B, qv_num_sms() * occ * 2 / cch)), cch);
+  return flip ? launch_fwd_w<T, K, true>(s, p, grid, smem) : launch_fwd_w<T, K, false>(s, p, grid, smem);
+}
+
+template <typename T, int K, int WT>
+int launch_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias,
+                 dim3 grid, size_t smem) {
+  if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_wgrad_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dw_wgrad_kernel<T, K, WT><<<grid, CS * PG, smem, s>>>(x, ldx, dy, lddy, B, H, W, C, dw, dbias);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -168,13 +288,15 @@ int run_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B,
   const size_t tile = (size_t)2 * H * W * CS * sizeof(float), red = (size_t)PG * (K * K + 1) * CS * sizeof(float);
   const size_t smem = tile > red ? tile : red;
   QV_CHECK(smem <= 200 * 1024, "dwconv wgrad: %dx%d feature map too large", H, W);
-  if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_wgrad_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int cch = cdiv(C, CS);
   const int occ = max(1, min(6, (int)(200 * 1024 / (smem + 1024))));
   dim3 grid(max(1, min(B, qv_num_sms() * occ / cch)), cch);
-  dw_wgrad_kernel<T, K><<<grid, CS * PG, smem, s>>>(x, ldx, dy, lddy, B, H, W, C, dw, dbias);
-  QV_LAUNCH_CHECK();
-  return 0;
+  switch (H == W ? W : 0) {
+    case 8: return launch_wgrad<T, K, 8>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem);
+    case 16: return launch_wgrad<T, K, 16>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem);
+    case 24: return launch_wgrad<T, K, 24>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem);
+  }
+  return launch_wgrad<T, K, 0>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem);
 }
 
 template <typename T>

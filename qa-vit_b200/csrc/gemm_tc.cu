@@ -419,6 +419,9 @@ struct TnArgs {
   const float* scale;
   int transposed;      // write dW[k * ldw + n] instead of dW[n * K + k]
   int ldw;
+  float* db;           // optional bias gradient: column sums of dY, accumulated by the otherwise idle epilogue warps
+  int db_mode;         // 1: dY is the A operand (columns n0 .. n0+127 of this CTA); 2: dY is the B operand (CTAs with n0 == 0)
+  int db_cols;         // number of dY columns
 };
 
 __global__ void __launch_bounds__(TN_THREADS, 1)
@@ -437,10 +440,11 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
   const int mb1 = min(p.mblocks, mb0 + p.mb_per_cta);
   const int nmb = mb1 - mb0;
 
+  const bool do_db = p.db != nullptr && (p.db_mode == 1 || blockIdx.x == 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_y);
     tma_prefetch_desc(&map_x);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, do_db ? 5 : 1); }
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
@@ -489,6 +493,54 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
     } else {
       const int quarter = warp & 3;
       const float sc = p.scale ? *p.scale : 1.f;
+      if (do_db) {
+        // bias gradient while the MMAs run.  Work item = (column pair, row half): one 32-bit shared load covers two
+        // adjacent bf16 columns, 32 rows per item with four independent accumulator chains.
+        // Box layout (SWIZZLE_128B): row r at r * 128 B, 16 B chunk j stored at chunk j ^ (r & 7).
+        const int t = threadIdx.x - 64;
+        const int ncol = p.db_mode == 1 ? 128 : p.kboxes * 64;
+        const int nitems = ncol;                       // (ncol / 2 pairs) x 2 row halves
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};    // [item slot][column of the pair]
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < nmb; ++i) {
+          mbar_wait(full + s, ph);
+          const uint8_t* tile = smem + s * stage_bytes + (p.db_mode == 1 ? 0 : a_bytes);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int item = t + h * 128;
+            if (item < nitems) {
+              const int pair = item % (ncol / 2), r0 = (item / (ncol / 2)) * 32;
+              const int col = pair * 2;
+              const uint8_t* box = tile + (col >> 6) * BOX;
+              const int j = (col & 63) >> 3, o = (col & 7) * 2;
+              float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const int r = r0 + rr;
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(box + r * 128 + ((j ^ (r & 7)) << 4) + o);
+                a0[rr & 3] += __uint_as_float(w << 16);
+                a1[rr & 3] += __uint_as_float(w & 0xFFFF0000u);
+              }
+              acc[h][0] += (a0[0] + a0[1]) + (a0[2] + a0[3]);
+              acc[h][1] += (a1[0] + a1[1]) + (a1[2] + a1[3]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty + s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        const int cbase = p.db_mode == 1 ? n0 : 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int item = t + h * 128;
+          if (item < nitems) {
+            const int col = cbase + (item % (ncol / 2)) * 2;
+            if (col < p.db_cols) atomicAdd(p.db + col, acc[h][0] * sc);
+            if (col + 1 < p.db_cols) atomicAdd(p.db + col + 1, acc[h][1] * sc);
+          }
+        }
+      }
       mbar_wait(tfull, 0);
       tc_fence_after();
       const int n = n0 + quarter * 32 + lane;
@@ -611,7 +663,7 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
 }
 
 int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
-               const float* scale, int transposed, int ldw) {
+               const float* scale, int transposed, int ldw, float* db, int db_mode, int db_cols) {
   if (M <= 0) return 0;
   QV_CHECK(tc_shape_ok_tn(M, N, K, ldy, ldx), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
   TnArgs p{};
@@ -624,6 +676,9 @@ int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, 
   p.scale = scale;
   p.transposed = transposed;
   p.ldw = ldw;
+  p.db = db;
+  p.db_mode = db_mode;
+  p.db_cols = db_cols;
   const int n_tiles = cdiv(N, BM);
   // Every CTA ends with 128 x K fp32 atomics, so a CTA must own enough rows to amortise them: >= 16 m-blocks
   // (1024 rows) each, and no more CTAs than SMs.

@@ -55,8 +55,10 @@ int simt_gemm_tn(cudaStream_t s, int dt, const void* dY, int ldy, const void* X,
 int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, const bf16* Wb, const GemmEpi& e);
 // transposed != 0: the product is written transposed, dW[k * ldw + n] (lets a weight gradient with K > 256 be
 // computed as X^T dY, whose accumulator width is N)
+// db (optional): column sums of the first operand (db_mode 1) or of the second operand (db_mode 2), db_cols wide,
+// accumulated inside the same kernel (the bias gradient; no separate pass over dY).
 int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
-               const float* scale, int transposed = 0, int ldw = 0);
+               const float* scale, int transposed = 0, int ldw = 0, float* db = nullptr, int db_mode = 0, int db_cols = 0);
 bool tc_shape_ok_nt(int M, int N, int K, int lda);
 bool tc_shape_ok_tn(int M, int N, int K, int ldy, int ldx);
 int colsum_accum(cudaStream_t s, int dt, const void* dY, int ldy, int M, int N, float* db, const float* scale);

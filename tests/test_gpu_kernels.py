@@ -57,7 +57,7 @@ def test_tcgen05_gemm_nt(M, N, K):
     assert err < 2e-4, f"max abs err {err} (ref max {ref.abs().max().item()})"
 
 
-TC_TN = [(4096, 192, 192), (1000, 576, 192), (333, 96, 192), (2048, 192, 96), (640, 48, 192), (512, 16, 192),
+TC_TN = [(700, 64, 288), (1000, 256, 1024), (900, 192, 768), (512, 192, 384), (4096, 192, 192), (1000, 576, 192), (333, 96, 192), (2048, 192, 96), (640, 48, 192), (512, 16, 192),
          (64, 192, 192), (3000, 384, 192), (130, 192, 48)]
 
 
@@ -76,6 +76,34 @@ def test_tcgen05_gemm_tn(M, N, K):
     err = (dW - ref).abs().max().item()
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), f"max abs err {err} (ref max {ref.abs().max().item()})"
     assert (db - dY.float().sum(0)).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 192, 192), (1000, 1024, 256), (640, 256, 1024), (130, 64, 288)])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_tcgen05_gemm_fused_epilogues(M, N, K, mode):
+    """GELU dual output, bf16 residual and GELU-backward multiply epilogues of the tcgen05 NT GEMM (lateral path)."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    Wb = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    aux = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    C = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    C2 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    L.check(L.lib.qavit_test_gemm_epi(A.data_ptr(), K, M, N, K, Wb.data_ptr(), bias.data_ptr(), C.data_ptr(), C2.data_ptr(), mode,
+                                      aux.data_ptr(), _s()))
+    torch.cuda.synchronize()
+    pre = A.double() @ Wb.double().t() + bias.double()
+    tol = 1.2e-2   # bf16 output rounding (2^-8 relative) on values of magnitude <= ~4
+    if mode == 1:
+        assert (C.double() - pre).abs().max().item() < tol * 4
+        assert (C2.double() - torch.nn.functional.gelu(pre)).abs().max().item() < tol * 4
+    elif mode == 2:
+        assert (C2.double() - (pre + aux.double())).abs().max().item() < tol * 6
+    else:
+        x = aux.double()
+        dg = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5
+        assert (C.double() - pre * dg).abs().max().item() < tol * 6
 
 
 def test_tcgen05_gemm_nt_strided_slice():
