@@ -90,13 +90,18 @@ int qavit_block_backward(const qavit_block_cfg* cfg, const void* const* params, 
                          const float* dout, float* dx, const void* saved, void* scratch, void* stream);
 
 /* PatchEmbed.forward + pos_embed (H:1136-1138, 1250): im2col-free conv-as-GEMM -> LayerNorm -> + pos.
- *   img [B, Cin, S, S] fp32; W [d, Cin, p, p]; pre [B*N, d] and stats [B*N, 2] are kept for backward. */
+ *   img [B, Cin, S, S] fp32; W [d, Cin, p, p]; pre [B*N, d] and stats [B*N, 2] are kept for backward.
+ *   dtype 1 (bf16 run) with `scratch` of qavit_patch_embed_scratch_bytes(): stride == kernel, so the patch rows are one
+ *   gather of the image into a bf16 [B*N, Cin*p*p] matrix and the convolution / its weight gradient are tcgen05 GEMMs;
+ *   dtype 0 (or scratch NULL): fp32 SIMT kernels (the 1e-4 parity mode). */
+size_t qavit_patch_embed_scratch_bytes(int B, int Cin, int S, int p, int d);
 int qavit_patch_embed_forward(const float* img, int B, int Cin, int S, int p, int d, const float* W, const float* bias,
                               const float* ln_w, const float* ln_b, const float* pos, float* pre, float* stats,
-                              float* out, void* stream);
+                              float* out, int dtype, void* scratch, void* stream);
 int qavit_patch_embed_backward(const float* img, const float* dout, int B, int Cin, int S, int p, int d,
                                const float* pre, const float* stats, const float* ln_w, float* dpre_scratch, float* dW,
-                               float* dbias, float* dln_w, float* dln_b, float* dpos, void* stream);
+                               float* dbias, float* dln_w, float* dln_b, float* dpos, int dtype, void* scratch,
+                               void* stream);
 
 /* Final norm -> token mean -> head (H:1273-1275).  x [B, N, d] fp32 -> logits [B, classes]. */
 int qavit_head_forward(const float* x, int B, int N, int d, const float* ln_w, const float* ln_b, const float* W,

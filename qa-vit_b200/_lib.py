@@ -59,8 +59,9 @@ _SIGS = {
     "qavit_block_workspace": (_i, [C.POINTER(BlockCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "qavit_block_forward": (_i, [C.POINTER(BlockCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_block_backward": (_i, [C.POINTER(BlockCfg), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),
-    "qavit_patch_embed_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "qavit_patch_embed_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_patch_embed_scratch_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
+    "qavit_patch_embed_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "qavit_patch_embed_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "qavit_head_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "qavit_head_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_cross_entropy": (_i, [_vp, _vp, _vp, _f, _i, _i, _f, _vp, _vp, _vp]),

@@ -732,15 +732,20 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
 // =====================================================================================================
 // thin wrappers
 // =====================================================================================================
+extern "C" size_t qavit_patch_embed_scratch_bytes(int B, int Cin, int S, int p, int d) {
+  return patch_embed_scratch_bytes(B, Cin, S, p, d) + 256;
+}
 extern "C" int qavit_patch_embed_forward(const float* img, int B, int Cin, int S, int p, int d, const float* W,
                                          const float* bias, const float* ln_w, const float* ln_b, const float* pos,
-                                         float* pre, float* stats, float* out, void* stream) {
-  return patch_embed_fwd((cudaStream_t)stream, img, B, Cin, S, p, d, W, bias, ln_w, ln_b, pos, pre, stats, out);
+                                         float* pre, float* stats, float* out, int dtype, void* scratch, void* stream) {
+  return patch_embed_fwd((cudaStream_t)stream, dtype, img, B, Cin, S, p, d, W, bias, ln_w, ln_b, pos, pre, stats, out, scratch);
 }
 extern "C" int qavit_patch_embed_backward(const float* img, const float* dout, int B, int Cin, int S, int p, int d,
                                           const float* pre, const float* stats, const float* ln_w, float* dpre_scratch,
-                                          float* dW, float* dbias, float* dln_w, float* dln_b, float* dpos, void* stream) {
-  return patch_embed_bwd((cudaStream_t)stream, img, dout, B, Cin, S, p, d, pre, stats, ln_w, dpre_scratch, dW, dbias, dln_w, dln_b, dpos);
+                                          float* dW, float* dbias, float* dln_w, float* dln_b, float* dpos, int dtype,
+                                          void* scratch, void* stream) {
+  return patch_embed_bwd((cudaStream_t)stream, dtype, img, dout, B, Cin, S, p, d, pre, stats, ln_w, dpre_scratch, dW, dbias, dln_w, dln_b,
+                         dpos, scratch);
 }
 extern "C" int qavit_head_forward(const float* x, int B, int N, int d, const float* ln_w, const float* ln_b, const float* W,
                                   const float* bias, int classes, float* stats, float* pooled, float* logits, void* stream) {

@@ -99,13 +99,95 @@ __global__ void __launch_bounds__(192) patch_embed_dw_kernel(const float* __rest
     }
   }
 }
+// ---- bf16 runs: the patch rows are gathered once into a bf16 [B*N, K] matrix (stride == kernel: every image element
+// lands in exactly one row) and the convolution is the tcgen05 GEMM; LayerNorm + pos is a warp-per-row kernel.
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, int B, int Cin, int S, int p,
+                                                       bf16* __restrict__ col) {
+  const int n_side = S / p, N = n_side * n_side, K = Cin * p * p;
+  const long total = (long)B * N * K / 2;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int k = (int)((2 * i) % K);
+    const long row = (2 * i) / K;
+    const int n = (int)(row % N);
+    const long b = row / N;
+    const int c = k / (p * p), r = (k / p) % p, q = k % p;      // p is even: (k, k + 1) share the image row
+    const float2 v = *reinterpret_cast<const float2*>(img + ((b * Cin + c) * S + (n / n_side) * p + r) * S + (n % n_side) * p + q);
+    *reinterpret_cast<__nv_bfloat162*>(col + 2 * i) = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+template <int EPL>
+__global__ void __launch_bounds__(256) ln_pos_fwd_kernel(const float* __restrict__ pre, long rows, int N, int C,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ pos, float* __restrict__ stats,
+                                                         float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, c0 = lane * EPL;
+  const bool act = c0 < C;
+  const float invC = 1.f / (float)C;
+  float gm[EPL], bt[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) gm[i] = bt[i] = 0.f;
+  if (act) { load_vec<EPL>(gamma + c0, gm); load_vec<EPL>(beta + c0, bt); }
+  for (long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long)gridDim.x * 8) {
+    float v[EPL], ps[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) v[i] = ps[i] = 0.f;
+    if (act) {
+      load_vec<EPL>(pre + row * C + c0, v);
+      if (pos) load_vec<EPL>(pos + (row % N) * C + c0, ps);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) s += v[i];
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) { const float t = act ? v[i] - mean : 0.f; q += t * t; }
+    const float rstd = rsqrtf(warp_sum(q) * invC + 1e-5f);
+    if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) v[i] = (v[i] - mean) * rstd * gm[i] + bt[i] + ps[i];
+    if (act) store_vec<EPL>(out + row * C + c0, v);
+  }
+}
+int patchify(cudaStream_t s, const float* img, int B, int Cin, int S, int p, bf16* col) {
+  const long total = (long)B * (S / p) * (S / p) * Cin * p * p / 2;
+  patchify_kernel<<<(int)max(1L, min((total + 255) / 256, (long)qv_num_sms() * 8)), 256, 0, s>>>(img, B, Cin, S, p, col);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+bool pe_tc_ok(int Cin, int S, int p, int d) {
+  const int K = Cin * p * p;
+  return p % 2 == 0 && S % p == 0 && K % 8 == 0 && d % 16 == 0 && d <= 256 && d % 4 == 0;
+}
 }  // namespace
 
-int patch_embed_fwd(cudaStream_t s, const float* img, int B, int Cin, int S, int p, int d, const float* W,
+size_t patch_embed_scratch_bytes(int B, int Cin, int S, int p, int d) {
+  const size_t K = (size_t)Cin * p * p, rows = (size_t)B * (S / p) * (S / p);
+  return ((rows * K * 2 + 255) & ~(size_t)255) + ((rows * d * 2 + 255) & ~(size_t)255) + 2 * (((size_t)d * K * 2 + 255) & ~(size_t)255);
+}
+
+int patch_embed_fwd(cudaStream_t s, int dt, const float* img, int B, int Cin, int S, int p, int d, const float* W,
                     const float* bias, const float* gamma, const float* beta, const float* pos, float* pre, float* stats,
-                    float* out) {
+                    float* out, void* scratch) {
   if (B <= 0) return 0;
   const int N = (S / p) * (S / p);
+  if (dt == QV_BF16 && scratch && pe_tc_ok(Cin, S, p, d)) {
+    const int K = Cin * p * p;
+    const long rows = (long)B * N;
+    uint8_t* sc = static_cast<uint8_t*>(scratch);
+    bf16* col = reinterpret_cast<bf16*>(sc);
+    bf16* wb = reinterpret_cast<bf16*>(sc + (((size_t)rows * K * 2 + 255) & ~(size_t)255) + (((size_t)rows * d * 2 + 255) & ~(size_t)255));
+    QV_TRY(patchify(s, img, B, Cin, S, p, col));
+    QV_TRY(convert_weight(s, W, d, K, wb, nullptr));
+    GemmEpi e;
+    e.bias = bias; e.C = pre; e.ldc = d; e.c_f32 = 1;
+    QV_TRY(tc_gemm_nt(s, col, K, (int)rows, d, K, wb, e));
+    const int grid = (int)max(1L, min((rows + 7) / 8, (long)qv_num_sms() * 8));
+    if (d > 128) ln_pos_fwd_kernel<8><<<grid, 256, 0, s>>>(pre, rows, N, d, gamma, beta, pos, stats, out);
+    else ln_pos_fwd_kernel<4><<<grid, 256, 0, s>>>(pre, rows, N, d, gamma, beta, pos, stats, out);
+    QV_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = (size_t)(PE_NC * PE_KC + d * (PE_KC + 1) + PE_NC * d) * sizeof(float);
   QV_CHECK(smem <= 227 * 1024, "patch_embed: d=%d needs %zu B smem: not supported", d, smem);
   QV_CUDA(cudaFuncSetAttribute(patch_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -114,14 +196,24 @@ int patch_embed_fwd(cudaStream_t s, const float* img, int B, int Cin, int S, int
   return 0;
 }
 
-int patch_embed_bwd(cudaStream_t s, const float* img, const float* dout, int B, int Cin, int S, int p, int d,
+int patch_embed_bwd(cudaStream_t s, int dt, const float* img, const float* dout, int B, int Cin, int S, int p, int d,
                     const float* pre, const float* stats, const float* gamma, float* dpre, float* dW, float* dbias,
-                    float* dgamma, float* dbeta, float* dpos) {
+                    float* dgamma, float* dbeta, float* dpos, void* scratch) {
   if (B <= 0) return 0;
   const int N = (S / p) * (S / p);
-  QV_CHECK(d <= 192, "patch_embed_bwd: d=%d > 192", d);
   // dpos[n, c] += sum_b dout[b, n, c]
   if (dpos) QV_TRY(colsum_accum(s, QV_F32, dout, N * d, B, N * d, dpos, nullptr));
+  if (dt == QV_BF16 && scratch && pe_tc_ok(Cin, S, p, d)) {
+    const int K = Cin * p * p;
+    const long rows = (long)B * N;
+    uint8_t* sc = static_cast<uint8_t*>(scratch);
+    bf16* col = reinterpret_cast<bf16*>(sc);
+    bf16* dpre_b = reinterpret_cast<bf16*>(sc + (((size_t)rows * K * 2 + 255) & ~(size_t)255));
+    QV_TRY(ln_bwd(s, QV_F32, pre, d, QV_F32, dout, d, (int)rows, d, gamma, stats, 0, QV_BF16, dpre_b, nullptr, nullptr, dgamma, dbeta));
+    QV_TRY(patchify(s, img, B, Cin, S, p, col));
+    return gemm_tn(s, QV_BF16, dpre_b, d, col, K, (int)rows, d, K, dW, dbias, nullptr);
+  }
+  QV_CHECK(d <= 192, "patch_embed_bwd: d=%d > 192", d);
   QV_TRY(ln_bwd(s, QV_F32, pre, d, QV_F32, dout, d, B * N, d, gamma, stats, 0, QV_F32, nullptr, dpre, nullptr, dgamma, dbeta));
   QV_TRY(colsum_accum(s, QV_F32, dpre, d, B * N, d, dbias, nullptr));
   const size_t smem = (size_t)PE_NC * PE_KC * sizeof(float);

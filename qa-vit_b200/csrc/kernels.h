@@ -204,12 +204,14 @@ int tl16_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, 
 int tl16_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx);
 int up16_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W, const float* bias, float* up);
 int up16_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int C, const float* W, float* dxc, float* dW, float* dbias);
-int patch_embed_fwd(cudaStream_t s, const float* img, int B, int Cin, int S, int p, int d, const float* W,
+// dt == bf16 with scratch (patch_embed_scratch_bytes): patch gather + tcgen05 GEMM; otherwise the fp32 SIMT kernels
+size_t patch_embed_scratch_bytes(int B, int Cin, int S, int p, int d);
+int patch_embed_fwd(cudaStream_t s, int dt, const float* img, int B, int Cin, int S, int p, int d, const float* W,
                     const float* bias, const float* gamma, const float* beta, const float* pos, float* pre, float* stats,
-                    float* out);
-int patch_embed_bwd(cudaStream_t s, const float* img, const float* dout, int B, int Cin, int S, int p, int d,
+                    float* out, void* scratch);
+int patch_embed_bwd(cudaStream_t s, int dt, const float* img, const float* dout, int B, int Cin, int S, int p, int d,
                     const float* pre, const float* stats, const float* gamma, float* dpre_scratch, float* dW,
-                    float* dbias, float* dgamma, float* dbeta, float* dpos);
+                    float* dbias, float* dgamma, float* dbeta, float* dpos, void* scratch);
 int head_fwd(cudaStream_t s, const float* x, int B, int N, int d, const float* gamma, const float* beta, const float* W,
              const float* bias, int ncls, float* stats, float* pooled, float* logits);
 int head_bwd(cudaStream_t s, const float* x, const float* dlogits, int B, int N, int d, const float* gamma,

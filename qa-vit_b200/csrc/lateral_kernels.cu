@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float o = (v[j] - mr[cv + j]) * mr[C + cv + j] * gamma[cv + j] + beta[cv + j];
-      v[j] = GELU ? gelu_f(o) : o;
+      v[j] = GELU ? gelu_t<T>(o) : o;
     }
     Vec8<T>::st(y + i * 8, v);
   }
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float xh = (v[i] - mean[i]) * rstd[i];
-      if (GELU) g[i] *= gelu_grad_f(fmaf(xh, gm[i], bt[i]));
+      if (GELU) g[i] *= gelu_grad_t<T>(fmaf(xh, gm[i], bt[i]));
       a[i] = fmaf(g[i], xh, a[i]);
       b[i] += g[i];
     }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     for (int j = 0; j < 8; ++j) {
       const float rs = mr[C + cv + j], gm = gamma[cv + j];
       const float xh = (v[j] - mr[cv + j]) * rs;
-      if (GELU) g[j] *= gelu_grad_f(fmaf(xh, gm, beta[cv + j]));
+      if (GELU) g[j] *= gelu_grad_t<T>(fmaf(xh, gm, beta[cv + j]));
       v[j] = gm * rs * (g[j] - invn * (sums[C + cv + j] + xh * sums[cv + j]));
     }
     Vec8<T>::st(dx + i * 8, v);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) rowln_fwd_kernel(const T* __restrict__ x,
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
       float o = (v[i] - mean) * rstd * gm[i] + bt[i];
-      if (gelu_out) o = gelu_f(o);
+      if (gelu_out) o = gelu_t<T>(o);
       v[i] = r[i] + sc * o;
     }
     if (act) {
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) rowln_fwd_kernel(const T* __restrict__ x,
 
 // dx = LN-backward(scale * dy * f'(LN(x)));  dgamma / dbeta accumulated;  dscale += sum dy * f(LN(x)) when scale.
 template <typename T, typename TD, int EPL>
-__global__ void __launch_bounds__(256) rowln_bwd_kernel(const T* __restrict__ x, const TD* __restrict__ dy, long rows, int C,
+__global__ void __launch_bounds__(256, 3) rowln_bwd_kernel(const T* __restrict__ x, const TD* __restrict__ dy, long rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         const float* __restrict__ stats, int gelu_out,
                                                         const float* __restrict__ scale, float* __restrict__ dscale,
@@ -337,9 +337,9 @@ __global__ void __launch_bounds__(256) rowln_bwd_kernel(const T* __restrict__ x,
     for (int i = 0; i < EPL; ++i) {
       xv[i] = act ? (xv[i] - mean) * rstd : 0.f;        // xhat
       const float o = fmaf(xv[i], gm[i], bt[i]);
-      if (scale) asc += dv[i] * (gelu_out ? gelu_f(o) : o);
+      if (scale) asc += dv[i] * (gelu_out ? gelu_t<T>(o) : o);
       float d = sc * dv[i];
-      if (gelu_out) d *= gelu_grad_f(o);
+      if (gelu_out) d *= gelu_grad_t<T>(o);
       ag[i] += d * xv[i];
       ab[i] += d;
       dv[i] = d * gm[i];
@@ -459,7 +459,7 @@ struct SfRow {
     for (int i = 0; i < EPL; ++i) {
       xc[i] = act ? (cp[i] - mean_c) * rstd_c : 0.f;
       lnc[i] = fmaf(xc[i], cg[i], cb[i]);
-      m[i] = gelu_f(lnc[i]) * dsc[i];
+      m[i] = gelu_t<T>(lnc[i]) * dsc[i];
       gate[i] = sigmoid_f(gl[i]);
       u[i] = act ? w0 * (t[i] + gate[i] * r[i]) + w1 * (t[i] + m[i]) : 0.f;
     }
@@ -474,7 +474,7 @@ __device__ __forceinline__ void softmax2(const float* fw, float* w0, float* w1) 
 
 // K2: out = LN_final(w0 * (T + sigmoid(glin) * R) + w1 * (T + dropout(gelu(LN_cat(cpre)))))
 template <typename T, int EPL>
-__global__ void __launch_bounds__(256) sf_post_fwd_kernel(SfP p, float* __restrict__ out, float* __restrict__ cat_stats,
+__global__ void __launch_bounds__(256, 3) sf_post_fwd_kernel(SfP p, float* __restrict__ out, float* __restrict__ cat_stats,
                                                           float* __restrict__ fin_stats) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, c0 = lane * EPL;
   const bool act = c0 < p.C;
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256) sf_post_fwd_kernel(SfP p, float* __restri
 // K2 backward: dT_part (fp32), dR_part, dglin, dcpre (T-type); column gradients of final_norm / cat_mlp.1 and the two
 // fusion-weight partials (draw[2], before the softmax backward) accumulated.
 template <typename T, int EPL>
-__global__ void __launch_bounds__(256) sf_post_bwd_kernel(SfP p, const float* __restrict__ dout, const float* __restrict__ cat_stats,
+__global__ void __launch_bounds__(256, 2) sf_post_bwd_kernel(SfP p, const float* __restrict__ dout, const float* __restrict__ cat_stats,
                                                           const float* __restrict__ fin_stats, float* __restrict__ dT,
                                                           float* __restrict__ dR, T* __restrict__ dglin, T* __restrict__ dcpre,
                                                           float* __restrict__ d_fin_g, float* __restrict__ d_fin_b,
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(256) sf_post_bwd_kernel(SfP p, const float* __
       o_t[i] = (w0 + w1) * du[i];
       o_r[i] = w0 * du[i] * R.gate[i];
       o_g[i] = w0 * du[i] * R.r[i] * R.gate[i] * (1.f - R.gate[i]);
-      const float dl = w1 * du[i] * R.dsc[i] * gelu_grad_f(R.lnc[i]);
+      const float dl = w1 * du[i] * R.dsc[i] * gelu_grad_t<T>(R.lnc[i]);
       a_cg[i] += dl * R.xc[i];
       a_cb[i] += dl;
       gc[i] = dl * cg[i];
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(256) sf_post_bwd_kernel(SfP p, const float* __
 
 // K1 backward: ds = LN_gate-backward(dg_in);  dT = dT_part + ds + dcat[:, :C];  dR = dR_part + ds + dcat[:, C:]
 template <typename T, int EPL>
-__global__ void __launch_bounds__(256) sf_pre_bwd_kernel(const float* __restrict__ Tin, const float* __restrict__ R,
+__global__ void __launch_bounds__(256, 3) sf_pre_bwd_kernel(const float* __restrict__ Tin, const float* __restrict__ R,
                                                          const T* __restrict__ dg_in, const T* __restrict__ dcat, long rows, int C,
                                                          const float* __restrict__ gamma, const float* __restrict__ stats,
                                                          float* dT, float* dR, float* __restrict__ dgamma, float* __restrict__ dbeta) {

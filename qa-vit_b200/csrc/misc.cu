@@ -12,32 +12,61 @@
 // =============================================================================== bank write (H:296-321)
 namespace {
 // tn[B*Nt, d] (already write_norm'ed), cg[B*Nt, d + kb] = [write_compression(tn) | write_gate(tn)].
-// CTA b-strided over images; thread = channel.  partial[cta][0] = sum_b g^T c, partial[cta][1] = sum_b g^T tn.
+// partial[cta][0] = sum_b S_b^T c_b, partial[cta][1] = sum_b S_b^T tn_b with S_b = softmax over tokens of the gate.
+// CTA strides over images; thread = channel (its 2 x KB accumulators stay in registers for all images of the CTA);
+// the softmaxed gate tile [Nt][KB] sits in shared memory and is read as broadcast float4s (8 FMAs per shared load);
+// the gate logits of the next image are prefetched into registers while the current image is accumulated.
 template <typename T, int KB>
-__global__ void bank_write_reduce_kernel(const T* __restrict__ tn, const T* __restrict__ cg, int ldcg, int B, int Nt,
-                                         int d, float* __restrict__ partial) {
-  extern __shared__ float g[];  // [Nt][KB]
+__global__ void __launch_bounds__(256) bank_write_reduce_kernel(const T* __restrict__ tn, const T* __restrict__ cg, int ldcg,
+                                                                int B, int Nt, int d, float* __restrict__ partial) {
+  extern __shared__ __align__(16) float g[];  // [Nt][KB]
   const int c = threadIdx.x;
+  const int ng = Nt * KB;                     // <= 4 * blockDim.x (checked by the launcher)
   float ak[KB], av[KB];
 #pragma unroll
   for (int s = 0; s < KB; ++s) ak[s] = av[s] = 0.f;
+  float pre[4];
+  auto fetch = [&](int b) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + q * blockDim.x;
+      pre[q] = idx < ng ? ldf(cg + ((long)b * Nt + idx / KB) * ldcg + d + idx % KB) : 0.f;
+    }
+  };
+  if ((int)blockIdx.x < B) fetch(blockIdx.x);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < Nt * KB; idx += blockDim.x)
-      g[idx] = ldf(cg + ((long)b * Nt + idx / KB) * ldcg + d + idx % KB);
-    __syncthreads();
-    if (threadIdx.x < KB) {  // softmax over the token axis for slot = threadIdx.x
-      const int s = threadIdx.x;
-      float m = -INFINITY;
-      for (int n = 0; n < Nt; ++n) m = fmaxf(m, g[n * KB + s]);
-      float z = 0.f;
-      for (int n = 0; n < Nt; ++n) { const float e = __expf(g[n * KB + s] - m); g[n * KB + s] = e; z += e; }
-      z = 1.f / z;
-      for (int n = 0; n < Nt; ++n) g[n * KB + s] *= z;
+    __syncthreads();                          // previous image's accumulation is done with g
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + q * blockDim.x;
+      if (idx < ng) g[idx] = pre[q];
     }
     __syncthreads();
+    // softmax over the token axis, every thread normalises its own entries (column statistics recomputed per thread)
+    float e[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + q * blockDim.x;
+      e[q] = 0.f;
+      if (idx < ng) {
+        const int sl = idx % KB;
+        float m = -INFINITY;
+        for (int n = 0; n < Nt; ++n) m = fmaxf(m, g[n * KB + sl]);
+        float z = 0.f;
+        for (int n = 0; n < Nt; ++n) z += __expf(g[n * KB + sl] - m);
+        e[q] = __expf(g[idx] - m) / z;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = threadIdx.x + q * blockDim.x;
+      if (idx < ng) g[idx] = e[q];
+    }
+    if (b + (int)gridDim.x < B) fetch(b + gridDim.x);
+    __syncthreads();
     if (c < d) {
-      // loads are independent: issue 8 tokens' worth before the FMAs (the kernel is latency-bound otherwise)
+      // loads are independent: issue 8 tokens' worth before the FMAs
       for (int n0 = 0; n0 < Nt; n0 += 8) {
         float cv[8], tv[8];
 #pragma unroll
@@ -50,7 +79,13 @@ __global__ void bank_write_reduce_kernel(const T* __restrict__ tn, const T* __re
         for (int k = 0; k < 8; ++k) {
           if (n0 + k < Nt) {
 #pragma unroll
-            for (int s = 0; s < KB; ++s) { ak[s] = fmaf(g[(n0 + k) * KB + s], cv[k], ak[s]); av[s] = fmaf(g[(n0 + k) * KB + s], tv[k], av[s]); }
+            for (int q = 0; q < KB / 4; ++q) {
+              const float4 w = *reinterpret_cast<const float4*>(g + (n0 + k) * KB + 4 * q);
+              ak[4 * q] = fmaf(w.x, cv[k], ak[4 * q]); ak[4 * q + 1] = fmaf(w.y, cv[k], ak[4 * q + 1]);
+              ak[4 * q + 2] = fmaf(w.z, cv[k], ak[4 * q + 2]); ak[4 * q + 3] = fmaf(w.w, cv[k], ak[4 * q + 3]);
+              av[4 * q] = fmaf(w.x, tv[k], av[4 * q]); av[4 * q + 1] = fmaf(w.y, tv[k], av[4 * q + 1]);
+              av[4 * q + 2] = fmaf(w.z, tv[k], av[4 * q + 2]); av[4 * q + 3] = fmaf(w.w, tv[k], av[4 * q + 3]);
+            }
           }
         }
       }
@@ -75,18 +110,20 @@ __global__ void __launch_bounds__(256) bank_write_apply_kernel(const float* __re
   if (v1) { uclamp = 0.1f; rate = 0.01f; bclamp = 1.0f; }                    // QAViT.py:217-224
   else { uclamp = 0.05f; bclamp = 0.5f; rate = (*update_count < 1000) ? 0.005f : 0.01f; }   // H:310-319
   const float invB = 1.f / (float)B;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 2 * n) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int p = 0;
-    for (; p + 4 <= n_partial; p += 4) {
-      s0 += partial[(long)p * 2 * n + i];
-      s1 += partial[(long)(p + 1) * 2 * n + i];
-      s2 += partial[(long)(p + 2) * 2 * n + i];
-      s3 += partial[(long)(p + 3) * 2 * n + i];
-    }
-    for (; p < n_partial; ++p) s0 += partial[(long)p * 2 * n + i];
-    const float u = fminf(fmaxf(((s0 + s1) + (s2 + s3)) * invB, -uclamp), uclamp);
+  // CTA = 32 bank elements x 8 partial groups: coalesced 128 B reads, the 8 group sums are combined in a fixed order
+  __shared__ float gs[8][33];
+  const int e = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
+  float acc = 0.f;
+  if (i < 2 * n)
+    for (int p = grp; p < n_partial; p += 8) acc += partial[(long)p * 2 * n + i];
+  gs[grp][e] = acc;
+  __syncthreads();
+  if (grp == 0 && i < 2 * n) {
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sum += gs[q][e];
+    const float u = fminf(fmaxf(sum * invB, -uclamp), uclamp);
     float* dst = (i < n) ? bank_k + i : bank_v + (i - n);
     *dst = fminf(fmaxf(*dst + rate * u, -bclamp), bclamp);
   }
@@ -107,7 +144,8 @@ int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, in
                       float* partial, int* n_partial) {
   QV_CHECK(kb == 16, "bank write kernel is instantiated for bank size 16 (got %d)", kb);
   QV_CHECK(d <= 256, "bank write: d=%d > 256", d);
-  const int grid = min(cdiv(B, 4), min(592, qv_num_sms() * 4));   // >= 4 images per CTA; 4 CTAs / SM for latency hiding
+  QV_CHECK(Nt * kb <= 4 * 256, "bank write: %d tokens x %d slots exceed the gate tile", Nt, kb);
+  const int grid = max(1, min(cdiv(B, 4), min(592, qv_num_sms() * 4)));   // >= 4 images per CTA; 4 CTAs / SM for latency hiding
   *n_partial = grid;
   const size_t smem = (size_t)Nt * kb * sizeof(float);
   DISPATCH_T(dt, (bank_write_reduce_kernel<T, 16><<<grid, 256, smem, s>>>((const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
@@ -117,7 +155,7 @@ int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, in
 
 int bank_write_apply(cudaStream_t s, const float* partial, int n_partial, int B, int d, int kb, float* bank_k,
                      float* bank_v, long long* update_count, int v1) {
-  bank_write_apply_kernel<<<cdiv(2 * kb * d, 256), 256, 0, s>>>(partial, n_partial, B, kb * d, bank_k, bank_v, update_count, v1);
+  bank_write_apply_kernel<<<cdiv(2 * kb * d, 32), 256, 0, s>>>(partial, n_partial, B, kb * d, bank_k, bank_v, update_count, v1);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -168,7 +168,7 @@ class PatchEmbedFn(torch.autograd.Function):
     """PatchEmbed.forward (+ pos_embed) -- HQAViT_CIFAR100.py:1136-1138, 1250."""
 
     @staticmethod
-    def forward(ctx, img, W, bias, ln_w, ln_b, pos):
+    def forward(ctx, img, W, bias, ln_w, ln_b, pos, dtype=0):
         _require_cuda(img, "image batch")
         img = img.detach().float().contiguous()
         B, Cin, S, _ = img.shape
@@ -177,9 +177,11 @@ class PatchEmbedFn(torch.autograd.Function):
         pre = torch.empty(B * N, d, dtype=torch.float32, device=img.device)
         stats = torch.empty(B * N, 2, dtype=torch.float32, device=img.device)
         out = torch.empty(B, N, d, dtype=torch.float32, device=img.device)
+        scratch = _scratch_buf(img.device, lib.qavit_patch_embed_scratch_bytes(B, Cin, S, p, d)) if dtype == 1 else None
         check(lib.qavit_patch_embed_forward(img.data_ptr(), B, Cin, S, p, d, W.data_ptr(), bias.data_ptr(), ln_w.data_ptr(),
                                             ln_b.data_ptr(), _ptr(pos), pre.data_ptr(), stats.data_ptr(), out.data_ptr(),
-                                            _stream()))
+                                            dtype, _ptr(scratch), _stream()))
+        ctx.dtype = dtype
         ctx.save_for_backward(img, W, ln_w, pre, stats)
         ctx.params = (W, bias, ln_w, ln_b, pos)
         ctx.has_pos = pos is not None
@@ -196,12 +198,13 @@ class PatchEmbedFn(torch.autograd.Function):
         direct = []
         (dW, rW), (db, rb), (dg, rg), (dbeta, rbeta) = (_grad_out(t, direct) for t in ctx.params[:4])
         dpos, rpos = _grad_out(ctx.params[4], direct) if ctx.has_pos else (None, None)
-        dpre = torch.empty_like(pre)
+        dpre = torch.empty_like(pre) if ctx.dtype != 1 else None
+        scratch = _scratch_buf(dev, lib.qavit_patch_embed_scratch_bytes(B, Cin, S, p, d)) if ctx.dtype == 1 else None
         check(lib.qavit_patch_embed_backward(img.data_ptr(), dout.data_ptr(), B, Cin, S, p, d, pre.data_ptr(), stats.data_ptr(),
-                                             ln_w.data_ptr(), dpre.data_ptr(), dW.data_ptr(), db.data_ptr(), dg.data_ptr(),
-                                             dbeta.data_ptr(), _ptr(dpos), _stream()))
+                                             ln_w.data_ptr(), _ptr(dpre), dW.data_ptr(), db.data_ptr(), dg.data_ptr(),
+                                             dbeta.data_ptr(), _ptr(dpos), ctx.dtype, _ptr(scratch), _stream()))
         _notify(direct)
-        return None, rW, rb, rg, rbeta, rpos
+        return None, rW, rb, rg, rbeta, rpos, None
 
 
 class HeadFn(torch.autograd.Function):

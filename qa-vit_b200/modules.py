@@ -322,9 +322,11 @@ class PatchEmbed(nn.Module):
         self.num_patches = (img_size // patch_size) ** 2
         self.proj = nn.Conv2d(in_channels, embed_dim, kernel_size=patch_size, stride=patch_size)
         self.norm = nn.LayerNorm(embed_dim)
+        self.precision = "auto"
 
     def forward(self, x, pos: Optional[torch.Tensor] = None):
-        return QF.PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias, pos)
+        return QF.PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias, pos,
+                                     QF.resolve_dtype(self.precision))
 
 
 def _init_weights(m):
@@ -348,7 +350,7 @@ class _Base(nn.Module):
         assert precision in ("auto", "fp32", "bf16")
         self.precision = precision
         for m in self.modules():
-            if isinstance(m, (QuadAttentionBlock, SplitFusion)):
+            if isinstance(m, (QuadAttentionBlock, SplitFusion, PatchEmbed)):
                 m.precision = precision
         return self
 
