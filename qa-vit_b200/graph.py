@@ -16,7 +16,8 @@ from .functional import cross_entropy
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, opt, example_x: torch.Tensor, example_y: torch.Tensor,
                  label_smoothing: float = 0.0, autocast_bf16: bool = True, warmup: int = 3,
-                 before_backward: Optional[Callable[[], None]] = None, after_backward: Optional[Callable[[], None]] = None):
+                 before_backward: Optional[Callable[[], None]] = None, after_backward: Optional[Callable[[], None]] = None,
+                 capture_error_mode: str = "global"):
         self.model, self.opt = model, opt
         self.x = example_x.clone()
         self.y = example_y.clone()
@@ -31,7 +32,9 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # data-parallel runs capture the bucketed NCCL all-reduces too; the process group's watchdog thread issues CUDA
+        # calls of its own, hence capture_error_mode="thread_local" there
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self._step_body(eager=False)
         torch.cuda.synchronize()
 
