@@ -53,16 +53,18 @@ __device__ __forceinline__ void tile_commit(float* xs, const float2* pf) {
 template <typename T, int K, bool FLIP, int WT>
 __global__ void __launch_bounds__(CS * PG) dw_fwd_kernel(const T* __restrict__ x, int ldx, int B, int H, int W, int C,
                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                         const float* __restrict__ scale,
                                                          T* y, int ldy, const T* resid, int ldr,
                                                          const T* resid2, int ldr2, T* __restrict__ copy, int ldcp) {
   extern __shared__ float xs[];                 // [H*W][CS]
   const int c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS, c = c0 + cl;
   const int HW = H * W;
   const bool act = c < C;
+  const float scl = (scale && act) ? scale[c] : 1.f;   // per-channel output scale folded into the taps and the bias
   float wr[K * K];                              // this channel's taps: loaded once, reused for every image of the CTA
 #pragma unroll
-  for (int t = 0; t < K * K; ++t) wr[t] = act ? w[c * K * K + (FLIP ? K * K - 1 - t : t)] : 0.f;
-  const float bs = (bias && act) ? bias[c] : 0.f;
+  for (int t = 0; t < K * K; ++t) wr[t] = act ? w[c * K * K + (FLIP ? K * K - 1 - t : t)] * scl : 0.f;
+  const float bs = (bias && act) ? bias[c] * scl : 0.f;
   constexpr bool kPrefetch = (WT == 8);
   float2 pf[NPF];
   if (kPrefetch && (int)blockIdx.x < B) tile_prefetch(pf, x, ldx, (long)blockIdx.x * HW, c0, C);
@@ -144,7 +146,9 @@ __global__ void __launch_bounds__(CS * PG) dw_fwd_kernel(const T* __restrict__ x
 template <typename T, int K, int WT>
 __global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy,
                                                            int lddy, int B, int H, int W, int C, float* __restrict__ dw,
-                                                           float* __restrict__ dbias) {
+                                                           float* __restrict__ dbias, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ scale,
+                                                           float* __restrict__ dscale) {
   extern __shared__ float sm[];
   const int HW = H * W;
   float* xs = sm;                    // [HW][CS]
@@ -241,15 +245,22 @@ __global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__
     float s = 0.f;
 #pragma unroll
     for (int q = 0; q < PG; ++q) s += red[(q * (K * K + 1) + t) * CS + cc];
-    if (t < K * K) atomicAdd(dw + (c0 + cc) * K * K + t, s);
-    else if (dbias) atomicAdd(dbias + c0 + cc, s);
+    // y = scale * (conv(x) + bias):  dw = scale * (dy * x), dbias = scale * sum dy, dscale = sum dy * (conv(x) + bias)
+    const float scl = scale ? scale[c0 + cc] : 1.f;
+    if (t < K * K) {
+      atomicAdd(dw + (c0 + cc) * K * K + t, s * scl);
+      if (dscale) atomicAdd(dscale + c0 + cc, s * w[(c0 + cc) * K * K + t]);
+    } else {
+      if (dbias) atomicAdd(dbias + c0 + cc, s * scl);
+      if (dscale && bias) atomicAdd(dscale + c0 + cc, s * bias[c0 + cc]);
+    }
   }
 }
 
 template <typename T, int K, bool F, int WT>
 int launch_fwd(cudaStream_t s, const DwP& p, dim3 grid, size_t smem) {
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<T, K, F, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dw_fwd_kernel<T, K, F, WT><<<grid, CS * PG, smem, s>>>((const T*)p.x, p.ldx, p.B, p.H, p.W, p.C, p.w, p.bias, (T*)p.y, p.ldy,
+  dw_fwd_kernel<T, K, F, WT><<<grid, CS * PG, smem, s>>>((const T*)p.x, p.ldx, p.B, p.H, p.W, p.C, p.w, p.bias, p.scale, (T*)p.y, p.ldy,
                                                          (const T*)p.resid, p.ldr, (const T*)p.resid2, p.ldr2, (T*)p.copy, p.ldcp);
   QV_LAUNCH_CHECK();
   return 0;
@@ -257,6 +268,7 @@ int launch_fwd(cudaStream_t s, const DwP& p, dim3 grid, size_t smem) {
 template <typename T, int K, bool F>
 int launch_fwd_w(cudaStream_t s, const DwP& p, dim3 grid, size_t smem) {
   switch (p.H == p.W ? p.W : 0) {
+    case 4: return launch_fwd<T, K, F, 4>(s, p, grid, smem);
     case 8: return launch_fwd<T, K, F, 8>(s, p, grid, smem);
     case 16: return launch_fwd<T, K, F, 16>(s, p, grid, smem);
     case 24: return launch_fwd<T, K, F, 24>(s, p, grid, smem);
@@ -276,15 +288,16 @@ int run_fwd(cudaStream_t s, const DwP& p, bool flip) {
 
 template <typename T, int K, int WT>
 int launch_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias,
-                 dim3 grid, size_t smem) {
+                 dim3 grid, size_t smem, const DwScale& sc) {
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_wgrad_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dw_wgrad_kernel<T, K, WT><<<grid, CS * PG, smem, s>>>(x, ldx, dy, lddy, B, H, W, C, dw, dbias);
+  dw_wgrad_kernel<T, K, WT><<<grid, CS * PG, smem, s>>>(x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc.w, sc.bias, sc.scale, sc.dscale);
   QV_LAUNCH_CHECK();
   return 0;
 }
 
 template <typename T, int K>
-int run_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias) {
+int run_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias,
+              const DwScale& sc) {
   const size_t tile = (size_t)2 * H * W * CS * sizeof(float), red = (size_t)PG * (K * K + 1) * CS * sizeof(float);
   const size_t smem = tile > red ? tile : red;
   QV_CHECK(smem <= 200 * 1024, "dwconv wgrad: %dx%d feature map too large", H, W);
@@ -292,11 +305,12 @@ int run_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B,
   const int occ = max(1, min(6, (int)(200 * 1024 / (smem + 1024))));
   dim3 grid(max(1, min(B, qv_num_sms() * occ / cch)), cch);
   switch (H == W ? W : 0) {
-    case 8: return launch_wgrad<T, K, 8>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem);
-    case 16: return launch_wgrad<T, K, 16>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem);
-    case 24: return launch_wgrad<T, K, 24>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem);
+    case 4: return launch_wgrad<T, K, 4>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem, sc);
+    case 8: return launch_wgrad<T, K, 8>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem, sc);
+    case 16: return launch_wgrad<T, K, 16>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem, sc);
+    case 24: return launch_wgrad<T, K, 24>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem, sc);
   }
-  return launch_wgrad<T, K, 0>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem);
+  return launch_wgrad<T, K, 0>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, grid, smem, sc);
 }
 
 template <typename T>
@@ -310,11 +324,12 @@ int fwd_t(cudaStream_t s, const DwP& p, bool flip) {
   return 1;
 }
 template <typename T>
-int wgrad_t(cudaStream_t s, int K, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias) {
+int wgrad_t(cudaStream_t s, int K, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias,
+            const DwScale& sc) {
   switch (K) {
-    case 3: return run_wgrad<T, 3>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias);
-    case 5: return run_wgrad<T, 5>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias);
-    case 7: return run_wgrad<T, 7>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias);
+    case 3: return run_wgrad<T, 3>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc);
+    case 5: return run_wgrad<T, 5>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc);
+    case 7: return run_wgrad<T, 7>(s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc);
   }
   qv_set_error("dwconv: kernel size %d not supported (3, 5, 7)", K);
   return 1;
@@ -328,11 +343,11 @@ int dw2d_fwd(cudaStream_t s, int dt, const DwP& p, bool flip) {
   return dt == QV_BF16 ? fwd_t<bf16>(s, p, flip) : fwd_t<float>(s, p, flip);
 }
 int dw2d_wgrad(cudaStream_t s, int dt, int K, const void* x, int ldx, const void* dy, int lddy, int B, int H, int W, int C,
-               float* dw, float* dbias) {
+               float* dw, float* dbias, const DwScale& sc) {
   if (B <= 0) return 0;
   QV_CHECK(C % 2 == 0 && ldx % 2 == 0 && lddy % 2 == 0, "dwconv wgrad: channel count / row pitch must be even");
-  if (dt == QV_BF16) return wgrad_t<bf16>(s, K, (const bf16*)x, ldx, (const bf16*)dy, lddy, B, H, W, C, dw, dbias);
-  return wgrad_t<float>(s, K, (const float*)x, ldx, (const float*)dy, lddy, B, H, W, C, dw, dbias);
+  if (dt == QV_BF16) return wgrad_t<bf16>(s, K, (const bf16*)x, ldx, (const bf16*)dy, lddy, B, H, W, C, dw, dbias, sc);
+  return wgrad_t<float>(s, K, (const float*)x, ldx, (const float*)dy, lddy, B, H, W, C, dw, dbias, sc);
 }
 
 extern "C" int qavit_dwconv_forward(const void* x, int is_bf16, int B, int H, int W, int C, int K, const float* w,

@@ -73,14 +73,17 @@ struct DwP {
   const void* x; int ldx;
   int B, H, W, C, K;
   const float* w; const float* bias;
+  const float* scale;                     // optional per-channel output scale: y = scale * (conv(x) + bias)
   void* y; int ldy;
   const void* resid; int ldr;
   const void* resid2; int ldr2;
   void* copy; int ldcp;
 };
 int dw2d_fwd(cudaStream_t s, int dt, const DwP& p, bool flip);
+// optional scaled form y = scale * (conv(x) + bias): dw / dbias are scaled, dscale[c] += sum dy * (conv(x) + bias)
+struct DwScale { const float* w = nullptr; const float* bias = nullptr; const float* scale = nullptr; float* dscale = nullptr; };
 int dw2d_wgrad(cudaStream_t s, int dt, int K, const void* x, int ldx, const void* dy, int lddy, int B, int H, int W, int C,
-               float* dw, float* dbias);
+               float* dw, float* dbias, const DwScale& sc = DwScale());
 
 // ---- lateral path / SplitFusion kernels (lateral_kernels.cu)
 // BatchNorm over rows of [rows, C] (+ GELU): mr[2C] = per-channel mean | rstd (kept for backward), sums_scratch[2C].

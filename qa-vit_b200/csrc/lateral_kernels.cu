@@ -179,24 +179,31 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ 3x3 stride-2 pad-1 convs
-// image [B, Cin, S, S] fp32 (NCHW) -> col [B * Ho * Wo, Kp], k = (ky * 3 + kx) * Cin + cin, zero padded to Kp
-template <typename T>
-__global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict__ img, int B, int Cin, int S, int Kp,
-                                                         T* __restrict__ col) {
+// image [B, Cin, S, S] fp32 (NCHW) -> col [B * Ho * Wo, Kp], k = (ky * 3 + kx) * Cin + cin, zero padded to Kp.
+// One thread per output pixel (adjacent threads = adjacent pixels of a row: neighbouring 3 x 3 windows share cache
+// lines); the Kp-wide row is written as 8-element vectors.  KP8 = Kp / 8 (4 for the 3-channel stem).
+template <typename T, int KP8, int CIN>
+__global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict__ img, int B, int Cin_rt, int S, T* __restrict__ col) {
+  const int Cin = CIN ? CIN : Cin_rt;     // compile-time channel count keeps the row in registers
   const int Ho = S / 2;
-  const long total = (long)B * Ho * Ho * Kp;
-  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
-    const int k = (int)(i % Kp);
-    const long row = i / Kp;
-    float v = 0.f;
-    if (k < 9 * Cin) {
-      const int cin = k % Cin, t = k / Cin, ky = t / 3, kx = t % 3;
-      const int ox = (int)(row % Ho), oy = (int)((row / Ho) % Ho);
-      const long b = row / ((long)Ho * Ho);
-      const int y = 2 * oy - 1 + ky, x = 2 * ox - 1 + kx;
-      if (y >= 0 && y < S && x >= 0 && x < S) v = img[((b * Cin + cin) * S + y) * S + x];
+  const long rows = (long)B * Ho * Ho;
+  for (long row = (long)blockIdx.x * 256 + threadIdx.x; row < rows; row += (long)gridDim.x * 256) {
+    const int ox = (int)(row % Ho), oy = (int)((row / Ho) % Ho);
+    const long b = row / ((long)Ho * Ho);
+    float v[KP8 * 8];
+#pragma unroll
+    for (int k = 0; k < KP8 * 8; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int y = 2 * oy - 1 + t / 3, x = 2 * ox - 1 + t % 3;
+      if (y >= 0 && y < S && x >= 0 && x < S) {
+#pragma unroll
+        for (int cin = 0; cin < (CIN ? CIN : 3); ++cin)
+          if (cin < Cin && t * Cin + cin < KP8 * 8) v[t * Cin + cin] = img[((b * Cin + cin) * S + y) * S + x];
+      }
     }
-    stf(col + i, v);
+#pragma unroll
+    for (int q = 0; q < KP8; ++q) Vec8<T>::st(col + row * (KP8 * 8) + q * 8, v + q * 8);
   }
 }
 // x [B, Hi, Hi, Cin] (NHWC, Cin % 8 == 0) -> col [B * Ho * Ho, 9 * Cin]
@@ -724,10 +731,13 @@ int bn_bwd(cudaStream_t s, int dt, const void* x, const void* dy, long rows, int
 }
 
 int im2col_img(cudaStream_t s, int dt, const float* img, int B, int Cin, int S, int Kp, void* col) {
-  const long total = (long)B * (S / 2) * (S / 2) * Kp;
-  const int grid = vec_grid(total);
-  DT_SWITCH(dt, (im2col_img_kernel<float><<<grid, 256, 0, s>>>(img, B, Cin, S, Kp, (float*)col)),
-            (im2col_img_kernel<bf16><<<grid, 256, 0, s>>>(img, B, Cin, S, Kp, (bf16*)col)));
+  QV_CHECK(Kp == 32 && Cin <= 3, "im2col_img: in_channels=%d (Kp=%d) not instantiated (<= 3 channels)", Cin, Kp);
+  const long rows = (long)B * (S / 2) * (S / 2);
+  const int grid = vec_grid(rows);
+  if (Cin == 3) DT_SWITCH(dt, (im2col_img_kernel<float, 4, 3><<<grid, 256, 0, s>>>(img, B, Cin, S, (float*)col)),
+                          (im2col_img_kernel<bf16, 4, 3><<<grid, 256, 0, s>>>(img, B, Cin, S, (bf16*)col)));
+  else DT_SWITCH(dt, (im2col_img_kernel<float, 4, 0><<<grid, 256, 0, s>>>(img, B, Cin, S, (float*)col)),
+                 (im2col_img_kernel<bf16, 4, 0><<<grid, 256, 0, s>>>(img, B, Cin, S, (bf16*)col)));
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -172,28 +172,56 @@ __device__ __forceinline__ int msda_src(int m, int side, const DilP& dp) {
   }
   return 0;
 }
+// xp[b, t, :] = mean_k xn[b, src(t * stride + k), :].  The source-token table is built once per CTA in shared memory;
+// a thread moves 4 channels of one pooled token.
 template <typename T>
-__global__ void msda_pool_fwd_kernel(const T* __restrict__ xn, int B, int Nt, int side, int C, DilP dp, int stride,
-                                     int NM, T* __restrict__ xp) {
-  const long total = (long)B * NM * C;
+__global__ void __launch_bounds__(256) msda_pool_fwd_kernel(const T* __restrict__ xn, int B, int Nt, int side, int C, DilP dp,
+                                                            int stride, int NM, T* __restrict__ xp) {
+  extern __shared__ int src[];   // [NM * stride]
+  for (int i = threadIdx.x; i < NM * stride; i += blockDim.x) src[i] = msda_src(i, side, dp);
+  __syncthreads();
+  const int cv = C / 4;
+  const long total = (long)B * NM * cv;
+  const float inv = 1.f / (float)stride;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c = idx % C;
-    const long r = idx / C;
-    const int t = r % NM, b = r / NM;
-    float a = 0.f;
-    for (int k = 0; k < stride; ++k) a += ldf(xn + ((long)b * Nt + msda_src(t * stride + k, side, dp)) * C + c);
-    stf(xp + idx, a / (float)stride);
+    const int c4 = (int)(idx % cv) * 4;
+    const long r = idx / cv;
+    const int t = (int)(r % NM);
+    const long b = r / NM;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < stride; ++k) {
+      float v[4];
+      load_vec<4>(xn + (b * Nt + src[t * stride + k]) * C + c4, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] *= inv;
+    store_vec<4>(xp + r * C + c4, a);
   }
 }
-// one CTA per image, thread per channel, sequential over pooled tokens: no write races on dxn
+// dxn[b, src(t * stride + k), :] += dxp[b, t, :] / stride.  A thread owns 4 channels of one image and walks the pooled
+// tokens sequentially (several pooled tokens can hit the same source token): no write races.
 template <typename T>
-__global__ void msda_pool_bwd_kernel(const T* __restrict__ dxp, int B, int Nt, int side, int C, DilP dp, int stride,
-                                     int NM, float* __restrict__ dxn) {
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      for (int t = 0; t < NM; ++t) {
-        const float g = ldf(dxp + ((long)b * NM + t) * C + c) / (float)stride;
-        for (int k = 0; k < stride; ++k) dxn[((long)b * Nt + msda_src(t * stride + k, side, dp)) * C + c] += g;
+__global__ void __launch_bounds__(256) msda_pool_bwd_kernel(const T* __restrict__ dxp, int B, int Nt, int side, int C, DilP dp,
+                                                            int stride, int NM, float* __restrict__ dxn) {
+  extern __shared__ int src[];   // [NM * stride]
+  for (int i = threadIdx.x; i < NM * stride; i += blockDim.x) src[i] = msda_src(i, side, dp);
+  __syncthreads();
+  const int cv = C / 4;
+  const long total = (long)B * cv;
+  const float inv = 1.f / (float)stride;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % cv) * 4;
+    const long b = idx / cv;
+    for (int t = 0; t < NM; ++t) {
+      float g[4];
+      load_vec<4>(dxp + (b * NM + t) * C + c4, g);
+      for (int k = 0; k < stride; ++k) {
+        float4* d = reinterpret_cast<float4*>(dxn + (b * Nt + src[t * stride + k]) * C + c4);
+        float4 o = *d;
+        o.x += g[0] * inv; o.y += g[1] * inv; o.z += g[2] * inv; o.w += g[3] * inv;
+        *d = o;
       }
     }
   }
@@ -212,8 +240,9 @@ int msda_pool_fwd(cudaStream_t s, int dt, const void* xn, int B, int Nt, int sid
   QV_TRY(make_dilp(dil, ndil, &dp));
   const long total = (long)B * NM * C;
   if (total <= 0) return 0;
-  const int grid = (int)min((long)qv_num_sms() * 8, (total + 255) / 256);
-  DISPATCH_T(dt, (msda_pool_fwd_kernel<T><<<grid, 256, 0, s>>>((const T*)xn, B, Nt, side, C, dp, stride, NM, (T*)xp)));
+  QV_CHECK(C % 4 == 0, "msda pooling: C=%d must be a multiple of 4", C);
+  const int grid = (int)max(1L, min((long)qv_num_sms() * 8, (total / 4 + 255) / 256));
+  DISPATCH_T(dt, (msda_pool_fwd_kernel<T><<<grid, 256, (size_t)NM * stride * sizeof(int), s>>>((const T*)xn, B, Nt, side, C, dp, stride, NM, (T*)xp)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -223,7 +252,9 @@ int msda_pool_bwd(cudaStream_t s, int dt, const void* dxp, int B, int Nt, int si
   DilP dp;
   QV_TRY(make_dilp(dil, ndil, &dp));
   if (B <= 0) return 0;
-  DISPATCH_T(dt, (msda_pool_bwd_kernel<T><<<B, 192, 0, s>>>((const T*)dxp, B, Nt, side, C, dp, stride, NM, dxn)));
+  QV_CHECK(C % 4 == 0, "msda pooling: C=%d must be a multiple of 4", C);
+  const int grid = (int)max(1L, min((long)qv_num_sms() * 8, ((long)B * (C / 4) + 255) / 256));
+  DISPATCH_T(dt, (msda_pool_bwd_kernel<T><<<grid, 256, (size_t)NM * stride * sizeof(int), s>>>((const T*)dxp, B, Nt, side, C, dp, stride, NM, dxn)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -309,6 +340,11 @@ int dwconv_fwd(cudaStream_t s, int dt, const void* x, int B, int side, int C, co
                const float* scale, void* y) {
   const long total = (long)B * side * side * C;
   if (total <= 0) return 0;
+  if (C % 2 == 0 && (side == 4 || side == 8 || side == 16)) {   // shared-memory tiled stencil (dwconv_nhwc.cu)
+    DwP p{};
+    p.x = x; p.ldx = C; p.B = B; p.H = side; p.W = side; p.C = C; p.K = 3; p.w = w; p.bias = bias; p.scale = scale; p.y = y; p.ldy = C;
+    return dw2d_fwd(s, dt, p, false);
+  }
   const int grid = (int)min((long)qv_num_sms() * 8, (total + 255) / 256);
   DISPATCH_T(dt, (dwconv_fwd_kernel<T><<<grid, 256, 0, s>>>((const T*)x, B, side, C, w, bias, scale, (T*)y)));
   QV_LAUNCH_CHECK();
@@ -318,6 +354,14 @@ int dwconv_fwd(cudaStream_t s, int dt, const void* x, int B, int side, int C, co
 int dwconv_bwd(cudaStream_t s, int dt, const void* x, const void* dy, int B, int side, int C, const float* w,
                const float* bias, const float* scale, void* dx, float* dw, float* dbias, float* dscale) {
   if (B <= 0) return 0;
+  if (C % 2 == 0 && (side == 4 || side == 8 || side == 16)) {
+    DwScale sc;
+    sc.w = w; sc.bias = bias; sc.scale = scale; sc.dscale = dscale;
+    QV_TRY(dw2d_wgrad(s, dt, 3, x, C, dy, C, B, side, side, C, dw, dbias, sc));
+    DwP p{};
+    p.x = dy; p.ldx = C; p.B = B; p.H = side; p.W = side; p.C = C; p.K = 3; p.w = w; p.scale = scale; p.y = dx; p.ldy = C;
+    return dw2d_fwd(s, dt, p, true);
+  }
   QV_CHECK(C <= 256, "dwconv_bwd: C=%d > 256", C);
   const int grid = min(B, qv_num_sms() * 8);
   const int threads = ((C + 31) / 32) * 32;
