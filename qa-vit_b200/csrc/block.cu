@@ -553,7 +553,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   }
   // ---- TokenUpMix (H:1016-1031)
   if (D.tl) {
-    QV_TRY(token_upmix_fwd(st, blk_out, D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.svf(S.up)));
+    QV_TRY(token_upmix_fwd(st, dt, blk_out, D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.svf(S.up)));
     QV_TRY(ln_fwd(st, QV_F32, c.sv(S.up), d, D.Rf, d, c.pf(QP_UP_LN_W), c.pf(QP_UP_LN_B), 1e-5f, 0, nullptr, nullptr, QV_F32, out, d, c.svf(S.up_stats)));
   }
   return 0;
@@ -586,7 +586,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
   if (D.tl) {
     QV_TRY(ln_bwd(st, QV_F32, c.sv(S.up), d, QV_F32, dout, d, D.Rf, d, c.pf(QP_UP_LN_W), c.svf(S.up_stats), 0, QV_F32, nullptr,
                   c.scf(X.d_up), nullptr, G(QP_UP_LN_W), G(QP_UP_LN_B)));
-    QV_TRY(token_upmix_bwd(st, c.svf(S.out_blk), c.scf(X.d_up), D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.scf(X.d_blk),
+    QV_TRY(token_upmix_bwd(st, dt, c.svf(S.out_blk), c.scf(X.d_up), D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.scf(X.d_blk),
                            G(QP_UP_FC_W), G(QP_UP_FC_B)));
     dblk = c.scf(X.d_blk);
   }

@@ -197,10 +197,16 @@ int token_learner_fwd(cudaStream_t s, int dt, const float* x, const void* logits
                       float* xc);
 int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float* dxc, int B, int N, int M,
                       int C, void* dlogits, float* dx);
-int token_upmix_fwd(cudaStream_t s, const float* xc, int B, int M, int N, int C, const float* W, const float* bias,
+int token_upmix_fwd(cudaStream_t s, int dt, const float* xc, int B, int M, int N, int C, const float* W, const float* bias,
                     float* up);
-int token_upmix_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int M, int N, int C, const float* W,
+int token_upmix_bwd(cudaStream_t s, int dt, const float* xc, const float* dup, int B, int M, int N, int C, const float* W,
                     float* dxc, float* dW, float* dbias);
+// tensor-core (mma.sync bf16) flavours for bf16 runs with 16 learned tokens (tokens_mma.cu)
+bool tokens_mma_ok(int M, int N, int C);
+int tlm_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, int C, float* S, float* xc);
+int tlm_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx);
+int upm_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W, const float* bias, float* up);
+int upm_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int C, const float* W, float* dxc, float* dW, float* dbias);
 // register-blocked flavours for 16 learned tokens (tokens.cu)
 bool tokens16_ok(int M, int C);
 int tl16_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, int N, int C, float* S, float* xc);

@@ -704,6 +704,7 @@ int opt_in_smem(K kernel, size_t bytes) {
 int token_learner_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, int N, int M, int C, float* S,
                       float* xc) {
   if (B <= 0) return 0;
+  if (dt == QV_BF16 && tokens_mma_ok(M, N, C)) return tlm_fwd(s, x, logits, B, N, C, S, xc);
   if (tokens16_ok(M, C)) return tl16_fwd(s, dt, x, logits, B, N, C, S, xc);
   QV_CHECK(M % 16 == 0, "token_learner: M=%d must be a multiple of 16", M);
   const size_t smem = (size_t)N * M * sizeof(float);
@@ -716,6 +717,7 @@ int token_learner_fwd(cudaStream_t s, int dt, const float* x, const void* logits
 int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float* dxc, int B, int N, int M,
                       int C, void* dlogits, float* dx) {
   if (B <= 0) return 0;
+  if (dt == QV_BF16 && tokens_mma_ok(M, N, C)) return tlm_bwd(s, x, S, dxc, B, N, C, dlogits, dx);
   if (tokens16_ok(M, C)) return tl16_bwd(s, dt, x, S, dxc, B, N, C, dlogits, dx);
   QV_CHECK(C <= 256, "token_learner_bwd: C=%d > 256", C);
   const size_t smem = (size_t)(2 * N * M + M * (C + 1) + M) * sizeof(float);
@@ -725,8 +727,9 @@ int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, co
   QV_LAUNCH_CHECK();
   return 0;
 }
-int token_upmix_fwd(cudaStream_t s, const float* xc, int B, int M, int N, int C, const float* W, const float* bias, float* up) {
+int token_upmix_fwd(cudaStream_t s, int dt, const float* xc, int B, int M, int N, int C, const float* W, const float* bias, float* up) {
   if (B <= 0) return 0;
+  if (dt == QV_BF16 && tokens_mma_ok(M, N, C)) return upm_fwd(s, xc, B, N, C, W, bias, up);
   if (tokens16_ok(M, C)) return up16_fwd(s, xc, B, N, C, W, bias, up);
   const size_t smem = (size_t)(N * M + M * C) * sizeof(float);
   QV_TRY(opt_in_smem(token_upmix_fwd_kernel, smem));
@@ -734,9 +737,10 @@ int token_upmix_fwd(cudaStream_t s, const float* xc, int B, int M, int N, int C,
   QV_LAUNCH_CHECK();
   return 0;
 }
-int token_upmix_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int M, int N, int C, const float* W,
+int token_upmix_bwd(cudaStream_t s, int dt, const float* xc, const float* dup, int B, int M, int N, int C, const float* W,
                     float* dxc, float* dW, float* dbias) {
   if (B <= 0) return 0;
+  if (dt == QV_BF16 && tokens_mma_ok(M, N, C)) return upm_bwd(s, xc, dup, B, N, C, W, dxc, dW, dbias);
   if (tokens16_ok(M, C)) return up16_bwd(s, xc, dup, B, N, C, W, dxc, dW, dbias);
   QV_CHECK(N % 16 == 0, "token_upmix_bwd: N=%d must be a multiple of 16", N);
   const size_t smem = (size_t)(N * M + M * (C + 1) + 16 * (C + 1)) * sizeof(float);

@@ -1,0 +1,391 @@
+// TokenLearner / TokenUpMix (H:971-1031) on tensor cores for bf16 runs with 16 learned tokens.
+//
+// Per image these are four skinny products with one dimension = 16 (the learned tokens):
+//   TokenLearner fwd : xc[16, C] = S^T[16, N] x[N, C]                     S = softmax over tokens of the gate logits
+//   TokenLearner bwd : dS[N, 16] = x[N, C] dxc^T[C, 16];  dx[N, C] = S[N, 16] dxc[16, C]
+//   TokenUpMix  fwd  : up[N, C] = W[N, 16] xc[16, C] + bias
+//   TokenUpMix  bwd  : dxc[16, C] = W^T[16, N] dup[N, C];  dW[N, 16] += dup[N, C] xc^T[C, 16];  dbias += rowsum(dup)
+// The reference runs them as torch.bmm / nn.Linear under autocast, i.e. with bf16 operands and fp32 accumulation
+// (SURVEY appendix C): exactly mma.sync.m16n8k16.  One 128-thread CTA walks images; the fp32 stream tile is converted
+// to bf16 once into shared memory and read with ldmatrix; outputs leave the accumulator fragments as fp32 float2
+// stores.  A 16-wide problem has no use for a 128-row tcgen05 tile (8 images would have to be stacked block-
+// diagonally), which is why this is warp-level MMA.  HBM-bound in the ideal: one pass over x / dx / up / dup.
+// fp32 runs and other shapes use the SIMT kernels of tokens.cu / misc.cu.
+#include "kernels.h"
+
+namespace {
+
+constexpr int M16 = 16;
+constexpr int SP = 24;      // pitch (bf16) of the [N][16] matrices: 48 B rows, conflict-free for ldmatrix
+constexpr int NWARP = 4;
+
+__device__ __forceinline__ uint32_t sa(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float x, float y) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// A (16 x 16) from smem [m][k] (k contiguous)
+__device__ __forceinline__ void ldA(uint32_t* a, const bf16* base, int pitch, int m0, int k0, int lane) {
+  const int mat = lane >> 3, r = lane & 7;
+  ldsm4(a, sa(base + (m0 + r + (mat & 1) * 8) * pitch + k0 + (mat >> 1) * 8));
+}
+// A (16 x 16) from smem [k][m] (m contiguous)
+__device__ __forceinline__ void ldAt(uint32_t* a, const bf16* base, int pitch, int m0, int k0, int lane) {
+  const int mat = lane >> 3, r = lane & 7;
+  ldsm4t(a, sa(base + (k0 + r + (mat >> 1) * 8) * pitch + m0 + (mat & 1) * 8));
+}
+// B of two adjacent n8 tiles from smem [n][k] (k contiguous)
+__device__ __forceinline__ void ldB(uint32_t* b, const bf16* base, int pitch, int n0, int k0, int lane) {
+  const int mat = lane >> 3, r = lane & 7;
+  ldsm4(b, sa(base + (n0 + r + (mat >> 1) * 8) * pitch + k0 + (mat & 1) * 8));
+}
+// same from smem [k][n] (n contiguous)
+__device__ __forceinline__ void ldBt(uint32_t* b, const bf16* base, int pitch, int n0, int k0, int lane) {
+  const int mat = lane >> 3, r = lane & 7;
+  ldsm4t(b, sa(base + (k0 + r + (mat & 1) * 8) * pitch + n0 + (mat >> 1) * 8));
+}
+
+// fp32 global [rows][C] -> bf16 smem [rows][pitch]
+__device__ __forceinline__ void tile_to_bf16(bf16* dst, int pitch, const float* __restrict__ src, int rows, int C) {
+  const int c4n = C / 4;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < rows * c4n; i += blockDim.x) {
+    const int r = i / c4n, c4 = (i % c4n) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + (long)r * C + c4);
+    *reinterpret_cast<uint2*>(dst + r * pitch + c4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+  }
+}
+
+struct Smem {
+  bf16* X;     // [N][XP]   stream tile (x or dup)
+  bf16* D;     // [16][XP]  compressed tile (xc or dxc)
+  bf16* S;     // [N][SP]   S or W
+  float* F;    // [N][16]   fp32 S / logits
+  float* R;    // [8][16] + [16] reductions
+};
+__device__ __forceinline__ Smem carve(uint8_t* base, int N, int XP) {
+  Smem s;
+  s.X = reinterpret_cast<bf16*>(base);
+  s.D = s.X + (size_t)N * XP;
+  s.S = s.D + (size_t)M16 * XP;
+  s.F = reinterpret_cast<float*>(s.S + (size_t)N * SP);
+  s.R = s.F + (size_t)N * M16;
+  return s;
+}
+size_t smem_bytes(int N, int C) {
+  const int XP = C + 8;
+  return ((size_t)N * XP + (size_t)M16 * XP + (size_t)N * SP) * 2 + ((size_t)N * M16 + 9 * M16) * 4 + 16;
+}
+
+// ---------------------------------------------------------------------------------------------- TokenLearner forward
+__global__ void __launch_bounds__(NWARP * 32) tlm_fwd_kernel(const float* __restrict__ x, const bf16* __restrict__ logits, int B, int N,
+                                                             int C, float* __restrict__ Sout, float* __restrict__ xc) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int XP = C + 8;
+  Smem sm = carve(smraw, N, XP);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int col = tid % M16, part = tid / M16;          // softmax: 8 threads per slot
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < N * M16; i += blockDim.x) sm.F[i] = __bfloat162float(logits[(long)b * N * M16 + i]);
+    tile_to_bf16(sm.X, XP, x + (long)b * N * C, N, C);
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int n = part; n < N; n += 8) mx = fmaxf(mx, sm.F[n * M16 + col]);
+    sm.R[part * M16 + col] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx = fmaxf(mx, sm.R[k * M16 + col]);
+    float z = 0.f;
+    for (int n = part; n < N; n += 8) { const float e = __expf(sm.F[n * M16 + col] - mx); sm.F[n * M16 + col] = e; z += e; }
+    __syncthreads();
+    sm.R[part * M16 + col] = z;
+    __syncthreads();
+    z = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z += sm.R[k * M16 + col];
+    z = 1.f / z;
+    for (int n = part; n < N; n += 8) {
+      const float s = sm.F[n * M16 + col] * z;
+      Sout[(long)b * N * M16 + n * M16 + col] = s;
+      sm.S[n * SP + col] = __float2bfloat16_rn(s);
+    }
+    __syncthreads();
+    // xc[16, C] = S^T x : A = S^T (from [k = token][m = slot]), B = x (from [k = token][n = channel])
+    for (int pair = warp; pair < C / 16; pair += NWARP) {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int ks = 0; ks < N / 16; ++ks) {
+        uint32_t a[4], bb[4];
+        ldAt(a, sm.S, SP, 0, ks * 16, lane);
+        ldBt(bb, sm.X, XP, pair * 16, ks * 16, lane);
+        mma16816(acc[0], a, bb[0], bb[1]);
+        mma16816(acc[1], a, bb[2], bb[3]);
+      }
+      float* o = xc + (long)b * M16 * C + pair * 16 + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        *reinterpret_cast<float2*>(o + (long)g * C + h * 8) = make_float2(acc[h][0], acc[h][1]);
+        *reinterpret_cast<float2*>(o + (long)(g + 8) * C + h * 8) = make_float2(acc[h][2], acc[h][3]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- TokenLearner backward
+__global__ void __launch_bounds__(NWARP * 32) tlm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ S,
+                                                             const float* __restrict__ dxc, int B, int N, int C,
+                                                             bf16* __restrict__ dlogits, float* __restrict__ dx) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int XP = C + 8;
+  Smem sm = carve(smraw, N, XP);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < N * M16; i += blockDim.x) {
+      const float s = S[(long)b * N * M16 + i];
+      sm.F[i] = s;
+      sm.S[(i / M16) * SP + i % M16] = __float2bfloat16_rn(s);
+    }
+    if (tid < M16) sm.R[tid] = 0.f;
+    tile_to_bf16(sm.X, XP, x + (long)b * N * C, N, C);
+    tile_to_bf16(sm.D, XP, dxc + (long)b * M16 * C, M16, C);
+    __syncthreads();
+    // dS[N, 16] = x dxc^T (this warp's token tiles), kept in registers until the column sums are known
+    constexpr int MAXT = 2;                 // token tiles per warp: N <= 128
+    float dS[MAXT][2][4];
+#pragma unroll
+    for (int nt = 0; nt < MAXT; ++nt) {
+      const int mt = warp + nt * NWARP;
+      if (mt >= N / 16) break;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dS[nt][h][j] = 0.f;
+      for (int ks = 0; ks < C / 16; ++ks) {
+        uint32_t a[4], bb[4];
+        ldA(a, sm.X, XP, mt * 16, ks * 16, lane);
+        ldB(bb, sm.D, XP, 0, ks * 16, lane);
+        mma16816(dS[nt][0], a, bb[0], bb[1]);
+        mma16816(dS[nt][1], a, bb[2], bb[3]);
+      }
+      // partial column sums of S * dS over this tile's rows
+      float cs[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = h * 8 + 2 * t + j;
+          cs[h][j] = sm.F[(mt * 16 + g) * M16 + c] * dS[nt][h][j] + sm.F[(mt * 16 + g + 8) * M16 + c] * dS[nt][h][2 + j];
+        }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float v = cs[h][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (g == 0) atomicAdd(sm.R + h * 8 + 2 * t + j, v);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < MAXT; ++nt) {
+      const int mt = warp + nt * NWARP;
+      if (mt >= N / 16) break;
+      // dlogits = S (dS - colsum)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = h * 8 + 2 * t;
+        const float t0 = sm.R[c], t1 = sm.R[c + 1];
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        const uint32_t lo = pack2(sm.F[r0 * M16 + c] * (dS[nt][h][0] - t0), sm.F[r0 * M16 + c + 1] * (dS[nt][h][1] - t1));
+        const uint32_t hi = pack2(sm.F[r1 * M16 + c] * (dS[nt][h][2] - t0), sm.F[r1 * M16 + c + 1] * (dS[nt][h][3] - t1));
+        *reinterpret_cast<uint32_t*>(dlogits + ((long)b * N + r0) * M16 + c) = lo;
+        *reinterpret_cast<uint32_t*>(dlogits + ((long)b * N + r1) * M16 + c) = hi;
+      }
+      // dx[N, C] = S dxc : A = S (from [m = token][k = slot]), B = dxc (from [k = slot][n = channel])
+      uint32_t a[4];
+      ldA(a, sm.S, SP, mt * 16, 0, lane);
+      float* o = dx + ((long)b * N + mt * 16) * C + 2 * t;
+      for (int pair = 0; pair < C / 16; ++pair) {
+        uint32_t bb[4];
+        ldBt(bb, sm.D, XP, pair * 16, 0, lane);
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        mma16816(acc[0], a, bb[0], bb[1]);
+        mma16816(acc[1], a, bb[2], bb[3]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          *reinterpret_cast<float2*>(o + (long)g * C + pair * 16 + h * 8) = make_float2(acc[h][0], acc[h][1]);
+          *reinterpret_cast<float2*>(o + (long)(g + 8) * C + pair * 16 + h * 8) = make_float2(acc[h][2], acc[h][3]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- TokenUpMix forward
+__global__ void __launch_bounds__(NWARP * 32) upm_fwd_kernel(const float* __restrict__ xc, int B, int N, int C,
+                                                             const float* __restrict__ W, const float* __restrict__ bias,
+                                                             float* __restrict__ up) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int XP = C + 8;
+  Smem sm = carve(smraw, N, XP);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < N * M16; i += blockDim.x) sm.S[(i / M16) * SP + i % M16] = __float2bfloat16_rn(W[i]);
+  for (int i = tid; i < N; i += blockDim.x) sm.F[i] = bias[i];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    tile_to_bf16(sm.D, XP, xc + (long)b * M16 * C, M16, C);
+    __syncthreads();
+    for (int mt = warp; mt < N / 16; mt += NWARP) {
+      uint32_t a[4];
+      ldA(a, sm.S, SP, mt * 16, 0, lane);
+      const float b0 = sm.F[mt * 16 + g], b1 = sm.F[mt * 16 + g + 8];
+      float* o = up + ((long)b * N + mt * 16) * C + 2 * t;
+      for (int pair = 0; pair < C / 16; ++pair) {
+        uint32_t bb[4];
+        ldBt(bb, sm.D, XP, pair * 16, 0, lane);
+        float acc[2][4] = {{b0, b0, b1, b1}, {b0, b0, b1, b1}};
+        mma16816(acc[0], a, bb[0], bb[1]);
+        mma16816(acc[1], a, bb[2], bb[3]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          *reinterpret_cast<float2*>(o + (long)g * C + pair * 16 + h * 8) = make_float2(acc[h][0], acc[h][1]);
+          *reinterpret_cast<float2*>(o + (long)(g + 8) * C + pair * 16 + h * 8) = make_float2(acc[h][2], acc[h][3]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- TokenUpMix backward
+__global__ void __launch_bounds__(NWARP * 32) upm_bwd_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B,
+                                                             int N, int C, const float* __restrict__ W, float* __restrict__ dxc,
+                                                             float* __restrict__ dW, float* __restrict__ dbias) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int XP = C + 8;
+  Smem sm = carve(smraw, N, XP);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < N * M16; i += blockDim.x) sm.S[(i / M16) * SP + i % M16] = __float2bfloat16_rn(W[i]);
+  constexpr int MAXT = 2;
+  float aW[MAXT][2][4], aB[MAXT][4];
+#pragma unroll
+  for (int q = 0; q < MAXT; ++q) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { aW[q][0][j] = aW[q][1][j] = 0.f; aB[q][j] = 0.f; }
+  }
+  const uint32_t ones = pack2(1.f, 1.f);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    tile_to_bf16(sm.X, XP, dup + (long)b * N * C, N, C);
+    tile_to_bf16(sm.D, XP, xc + (long)b * M16 * C, M16, C);
+    __syncthreads();
+    // dxc[16, C] = W^T dup : A = W^T (from [k = token][m = slot]), B = dup (from [k = token][n = channel])
+    for (int pair = warp; pair < C / 16; pair += NWARP) {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      for (int ks = 0; ks < N / 16; ++ks) {
+        uint32_t a[4], bb[4];
+        ldAt(a, sm.S, SP, 0, ks * 16, lane);
+        ldBt(bb, sm.X, XP, pair * 16, ks * 16, lane);
+        mma16816(acc[0], a, bb[0], bb[1]);
+        mma16816(acc[1], a, bb[2], bb[3]);
+      }
+      float* o = dxc + (long)b * M16 * C + pair * 16 + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        *reinterpret_cast<float2*>(o + (long)g * C + h * 8) = make_float2(acc[h][0], acc[h][1]);
+        *reinterpret_cast<float2*>(o + (long)(g + 8) * C + h * 8) = make_float2(acc[h][2], acc[h][3]);
+      }
+    }
+    // dW[N, 16] += dup xc^T, dbias += rowsum(dup) (a B tile of ones): accumulated in registers over the CTA's images
+#pragma unroll
+    for (int nt = 0; nt < MAXT; ++nt) {
+      const int mt = warp + nt * NWARP;
+      if (mt >= N / 16) break;
+      for (int ks = 0; ks < C / 16; ++ks) {
+        uint32_t a[4], bb[4];
+        ldA(a, sm.X, XP, mt * 16, ks * 16, lane);
+        ldB(bb, sm.D, XP, 0, ks * 16, lane);
+        mma16816(aW[nt][0], a, bb[0], bb[1]);
+        mma16816(aW[nt][1], a, bb[2], bb[3]);
+        mma16816(aB[nt], a, ones, ones);
+      }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < MAXT; ++nt) {
+    const int mt = warp + nt * NWARP;
+    if (mt >= N / 16) break;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = h * 8 + 2 * t;
+      atomicAdd(dW + (mt * 16 + g) * M16 + c, aW[nt][h][0]);
+      atomicAdd(dW + (mt * 16 + g) * M16 + c + 1, aW[nt][h][1]);
+      atomicAdd(dW + (mt * 16 + g + 8) * M16 + c, aW[nt][h][2]);
+      atomicAdd(dW + (mt * 16 + g + 8) * M16 + c + 1, aW[nt][h][3]);
+    }
+    if (t == 0) {
+      atomicAdd(dbias + mt * 16 + g, aB[nt][0]);
+      atomicAdd(dbias + mt * 16 + g + 8, aB[nt][2]);
+    }
+  }
+}
+
+template <typename K>
+int opt_in(K kernel, size_t bytes) {
+  QV_CHECK(bytes <= 200 * 1024, "token kernels need %zu B of shared memory", bytes);
+  if (bytes > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+int tok_grid(int B, size_t smem) {
+  const int occ = max(1, min(8, (int)(200 * 1024 / (smem + 1024))));
+  return max(1, min(B, qv_num_sms() * occ));
+}
+
+}  // namespace
+
+bool tokens_mma_ok(int M, int N, int C) { return M == 16 && N % 16 == 0 && N >= 16 && N <= 128 && C % 16 == 0 && C <= 512; }
+
+int tlm_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, int C, float* S, float* xc) {
+  const size_t smem = smem_bytes(N, C);
+  QV_TRY(opt_in(tlm_fwd_kernel, smem));
+  tlm_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, (const bf16*)logits, B, N, C, S, xc);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int tlm_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx) {
+  const size_t smem = smem_bytes(N, C);
+  QV_TRY(opt_in(tlm_bwd_kernel, smem));
+  tlm_bwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, S, dxc, B, N, C, (bf16*)dlogits, dx);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int upm_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W, const float* bias, float* up) {
+  const size_t smem = smem_bytes(N, C);
+  QV_TRY(opt_in(upm_fwd_kernel, smem));
+  upm_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(xc, B, N, C, W, bias, up);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int upm_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int C, const float* W, float* dxc, float* dW,
+            float* dbias) {
+  const size_t smem = smem_bytes(N, C);
+  QV_TRY(opt_in(upm_bwd_kernel, smem));
+  // the dW / dbias accumulators are flushed with atomics once per CTA: keep the CTA count moderate
+  const int grid = max(1, min(B, qv_num_sms() * 3));
+  upm_bwd_kernel<<<grid, NWARP * 32, smem, s>>>(xc, dup, B, N, C, W, dxc, dW, dbias);
+  QV_LAUNCH_CHECK();
+  return 0;
+}

@@ -306,7 +306,14 @@ def test_block_bf16_close_to_fp32(case, prefix, ntok):
     assert rel_max(b16, b32) < 1e-2
     # floor: 5 % of the median gradient norm (mathematically-zero gradients such as the TokenLearner biases are noise)
     med = np.median([v.norm().item() for v in g32.values()])
-    worst = max(((g16[n] - g32[n]).norm().item() / (g32[n].norm().item() + 5e-2 * med), n) for n in g32)
+    # gradients that are exactly zero in exact arithmetic (a per-token bias removed by the LayerNorm that follows,
+    # H:1027-1028; a per-slot bias removed by the softmax over tokens, H:996): both runs only hold rounding noise there,
+    # so they are bounded in absolute terms (2 % of the median gradient norm) instead of relatively
+    zero_grads = ("token_upmix.upsample_attn.bias", "token_learner.attention.1.bias")
+    for n in g32:
+        if n.endswith(zero_grads):
+            assert (g16[n] - g32[n]).norm().item() < 2e-2 * med, n
+    worst = max(((g16[n] - g32[n]).norm().item() / (g32[n].norm().item() + 5e-2 * med), n) for n in g32 if not n.endswith(zero_grads))
     print(f"block bf16 vs fp32 {case}: out {rel_l2(o16, o32):.3e} dx {rel_l2(d16, d32):.3e} worst param grad {worst}")
     assert worst[0] < 8e-2, worst
 
