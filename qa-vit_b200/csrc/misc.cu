@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256) bank_write_apply_kernel(const float* __re
 
 int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, int kb,
                       float* partial, int* n_partial) {
+  if (dt == QV_BF16 && bank_write_mma_ok(Nt, d, kb, ldcg)) return bank_write_reduce_mma(s, tn, cg, ldcg, B, Nt, d, partial, n_partial);
   QV_CHECK(kb == 16, "bank write kernel is instantiated for bank size 16 (got %d)", kb);
   QV_CHECK(d <= 256, "bank write: d=%d > 256", d);
   QV_CHECK(Nt * kb <= 4 * 256, "bank write: %d tokens x %d slots exceed the gate tile", Nt, kb);

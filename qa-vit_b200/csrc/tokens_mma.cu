@@ -58,12 +58,19 @@ __device__ __forceinline__ void ldBt(uint32_t* b, const bf16* base, int pitch, i
 
 // fp32 global [rows][C] -> bf16 smem [rows][pitch]
 __device__ __forceinline__ void tile_to_bf16(bf16* dst, int pitch, const float* __restrict__ src, int rows, int C) {
-  const int c4n = C / 4;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < rows * c4n; i += blockDim.x) {
-    const int r = i / c4n, c4 = (i % c4n) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(src + (long)r * C + c4);
-    *reinterpret_cast<uint2*>(dst + r * pitch + c4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+  const int c4n = C / 4, total = rows * c4n;
+  for (int base = 0; base < total; base += 8 * blockDim.x) {     // 8 independent 16 B loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * blockDim.x + threadIdx.x;
+      if (i < total) v[u] = *reinterpret_cast<const float4*>(src + (long)(i / c4n) * C + (i % c4n) * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * blockDim.x + threadIdx.x;
+      if (i < total) *reinterpret_cast<uint2*>(dst + (i / c4n) * pitch + (i % c4n) * 4) = make_uint2(pack2(v[u].x, v[u].y), pack2(v[u].z, v[u].w));
+    }
   }
 }
 
@@ -343,6 +350,85 @@ __global__ void __launch_bounds__(NWARP * 32) upm_bwd_kernel(const float* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------- bank write reduction
+// GlobalTokenBank.write (H:303-311): per image  K_upd[16, d] = S^T c,  V_upd[16, d] = S^T tn  with S = softmax over the
+// tokens of the gate logits; summed over the batch.  One product per image: [16 slots x Nt] x [Nt x 2d] on mma.sync;
+// the accumulator fragments stay in registers across all images of the CTA and leave once as the CTA's partial sum.
+__global__ void __launch_bounds__(NWARP * 32) bwr_mma_kernel(const bf16* __restrict__ tn, const bf16* __restrict__ cg, int ldcg, int B,
+                                                             int Nt, int d, float* __restrict__ partial) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int XP = 2 * d + 8;
+  bf16* sX = reinterpret_cast<bf16*>(smraw);                  // [Nt][XP]  [c | tn]
+  bf16* sS = sX + (size_t)Nt * XP;                             // [Nt][SP]
+  float* sF = reinterpret_cast<float*>(sS + (size_t)Nt * SP);  // [Nt][16]
+  float* sR = sF + (size_t)Nt * M16;                           // [8][16]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int col = tid % M16, part = tid / M16;
+  constexpr int MAXP = 8;                                      // n16 pairs per warp: 2d / 16 / 4 <= 8  (d <= 256)
+  const int npairs = 2 * d / 16;
+  float acc[MAXP][2][4];
+#pragma unroll
+  for (int q = 0; q < MAXP; ++q)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[q][0][j] = acc[q][1][j] = 0.f;
+  const int v8 = d / 8;                                        // 16 B vectors per d-wide row
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const long row0 = (long)b * Nt;
+    __syncthreads();
+    for (int i = tid; i < Nt * M16; i += blockDim.x) sF[i] = __bfloat162float(cg[(row0 + i / M16) * ldcg + d + i % M16]);
+    for (int i = tid; i < Nt * 2 * v8; i += blockDim.x) {
+      const int r = i / (2 * v8), c = i % (2 * v8);
+      const uint4 v = c < v8 ? *reinterpret_cast<const uint4*>(cg + (row0 + r) * ldcg + c * 8)
+                             : *reinterpret_cast<const uint4*>(tn + (row0 + r) * d + (c - v8) * 8);
+      *reinterpret_cast<uint4*>(sX + r * XP + c * 8) = v;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int n = part; n < Nt; n += 8) mx = fmaxf(mx, sF[n * M16 + col]);
+    sR[part * M16 + col] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx = fmaxf(mx, sR[k * M16 + col]);
+    float z = 0.f;
+    for (int n = part; n < Nt; n += 8) { const float e = __expf(sF[n * M16 + col] - mx); sF[n * M16 + col] = e; z += e; }
+    __syncthreads();
+    sR[part * M16 + col] = z;
+    __syncthreads();
+    z = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z += sR[k * M16 + col];
+    z = 1.f / z;
+    for (int n = part; n < Nt; n += 8) sS[n * SP + col] = __float2bfloat16_rn(sF[n * M16 + col] * z);
+    __syncthreads();
+    for (int ks = 0; ks < Nt / 16; ++ks) {
+      uint32_t a[4];
+      ldAt(a, sS, SP, 0, ks * 16, lane);
+#pragma unroll
+      for (int q = 0; q < MAXP; ++q) {
+        const int pair = warp + q * NWARP;
+        if (pair >= npairs) break;
+        uint32_t bb[4];
+        ldBt(bb, sX, XP, pair * 16, ks * 16, lane);
+        mma16816(acc[q][0], a, bb[0], bb[1]);
+        mma16816(acc[q][1], a, bb[2], bb[3]);
+      }
+    }
+  }
+  float* pk = partial + (long)blockIdx.x * 2 * M16 * d;
+#pragma unroll
+  for (int q = 0; q < MAXP; ++q) {
+    const int pair = warp + q * NWARP;
+    if (pair >= npairs) break;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cc = pair * 16 + h * 8 + 2 * t;              // column in [c | tn]
+      const int role = cc >= d ? 1 : 0, ch = cc - role * d;
+      *reinterpret_cast<float2*>(pk + ((long)role * M16 + g) * d + ch) = make_float2(acc[q][h][0], acc[q][h][1]);
+      *reinterpret_cast<float2*>(pk + ((long)role * M16 + g + 8) * d + ch) = make_float2(acc[q][h][2], acc[q][h][3]);
+    }
+  }
+}
+
 template <typename K>
 int opt_in(K kernel, size_t bytes) {
   QV_CHECK(bytes <= 200 * 1024, "token kernels need %zu B of shared memory", bytes);
@@ -386,6 +472,20 @@ int upm_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int
   // the dW / dbias accumulators are flushed with atomics once per CTA: keep the CTA count moderate
   const int grid = max(1, min(B, qv_num_sms() * 3));
   upm_bwd_kernel<<<grid, NWARP * 32, smem, s>>>(xc, dup, B, N, C, W, dxc, dW, dbias);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+bool bank_write_mma_ok(int Nt, int d, int kb, int ldcg) {
+  return kb == 16 && Nt % 16 == 0 && Nt >= 16 && Nt <= 256 && d % 16 == 0 && d <= 256 && ldcg % 8 == 0;
+}
+int bank_write_reduce_mma(cudaStream_t s, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, float* partial, int* n_partial) {
+  const size_t smem = ((size_t)Nt * (2 * d + 8) + (size_t)Nt * SP) * 2 + ((size_t)Nt * M16 + 8 * M16) * 4 + 16;
+  QV_TRY(opt_in(bwr_mma_kernel, smem));
+  const int occ = max(1, min(4, (int)(200 * 1024 / (smem + 1024))));
+  const int grid = max(1, min(cdiv(B, 2), min(592, qv_num_sms() * occ)));
+  *n_partial = grid;
+  bwr_mma_kernel<<<grid, NWARP * 32, smem, s>>>((const bf16*)tn, (const bf16*)cg, ldcg, B, Nt, d, partial);
   QV_LAUNCH_CHECK();
   return 0;
 }
