@@ -25,11 +25,9 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, i
     load_vec<EPL>(beta + c0, bt);
     if (gamma2) { load_vec<EPL>(gamma2 + c0, gm2); load_vec<EPL>(beta2 + c0, bt2); }
   }
-  for (long row = (long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long)gridDim.x * wpb) {
-    float v[EPL];
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) v[i] = 0.f;
-    if (act) load_vec<EPL>(x + row * ldx + c0, v);
+  // two rows per iteration: both rows' loads are issued before either row's reductions (a warp otherwise serialises
+  // load latency -> shuffle reductions -> store for each of its ~10 rows)
+  auto finish = [&](float* v, long row) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) { if (GELU_IN) v[i] = gelu_f(v[i]); s += v[i]; }
@@ -54,6 +52,19 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, i
       for (int i = 0; i < EPL; ++i) v[i] = (v[i] - m2) * r2 * gm2[i] + bt2[i];
     }
     if (act) store_vec<EPL>(y + row * ldy + c0, v);
+  };
+  const long stride = (long)gridDim.x * wpb;
+  for (long row = (long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += 2 * stride) {
+    const long row2 = row + stride;
+    float v[EPL], w[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) v[i] = w[i] = 0.f;
+    if (act) {
+      load_vec<EPL>(x + row * ldx + c0, v);
+      if (row2 < rows) load_vec<EPL>(x + row2 * ldx + c0, w);
+    }
+    finish(v, row);
+    if (row2 < rows) finish(w, row2);
   }
 }
 
@@ -152,7 +163,8 @@ int ln_bwd(cudaStream_t s, int dt_x, const void* x, int ldx, int dt_dy, const vo
   const int epl = pick_epl(C);
   QV_CHECK(C <= 256 && C % epl == 0 && ldx % epl == 0 && lddy % epl == 0, "ln_bwd: C=%d ldx=%d lddy=%d unsupported", C, ldx, lddy);
   QV_CHECK(resid == nullptr || (resid != dx_f32 && (const void*)resid != dx_t), "ln_bwd: resid must not alias an output");
-  const int grid = max(1, min(cdiv(rows, 8 * 2), qv_num_sms() * 6));
+  // every CTA ends with 2 * C atomics: keep >= 32 rows per warp before adding CTAs
+  const int grid = max(1, min(cdiv(rows, 8 * 32), qv_num_sms() * 6));
 #define LN_B4(TX, TDY, TO, E, G)                                                                                      \
   ln_bwd_kernel<TX, TDY, TO, E, G><<<grid, 256, 0, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, rows, C, gamma, stats, \
                                                         (TO*)dx_t, dx_f32, resid, dgamma, dbeta)
