@@ -181,7 +181,10 @@ def run_ours(args):
     opt = Q.FusedAdamW(model.named_parameters(), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06, max_grad_norm=0.5)
     nograd = ("swa.norm.", "msda.norm.", "cga.norm.", "write_norm.", "write_compression.", "write_gate.")
     opt.set_grad_mask([not any(s in n for s in nograd) for n in names])
-    reducer = Q.GradAllReducer(opt, n_buckets=4, bank_params=[model.global_bank.global_k, model.global_bank.global_v]) if world > 1 else None
+    # graph mode: forward + backward and clip + AdamW are two CUDA graphs with ONE eager all-reduce of the flat gradient
+    # buffer between them; eager mode (--no-graph): bucketed all-reduces overlapped with backward from autograd hooks
+    reducer = Q.GradAllReducer(opt, n_buckets=4, bank_params=[model.global_bank.global_k, model.global_bank.global_v],
+                               overlap=not args.graph) if world > 1 else None
 
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
@@ -190,14 +193,14 @@ def run_ours(args):
 
     def step(x, y):
         opt.zero_grad()
-        if reducer:
+        if reducer and not args.graph:
             reducer.reset()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = model(x)
         loss = Q.cross_entropy(logits, y, label_smoothing=0.12)
         loss.backward()
         if reducer:
-            reducer.finish()
+            reducer.finish() if not args.graph else reducer.reduce_flat()
         opt.clip()
         opt.step()
         return loss
@@ -210,12 +213,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = L.lib.qavit_launch_count() - l0
     graphed = None
-    if args.graph and (world == 1 or args.graph_dp):
+    if args.graph:
         try:
             graphed = Q.GraphedTrainStep(model, opt, x_dev, y_dev, label_smoothing=0.12, autocast_bf16=True, warmup=3,
-                                         before_backward=reducer.reset if reducer else None,
-                                         after_backward=reducer.finish if reducer else None,
-                                         capture_error_mode="thread_local" if world > 1 else "global")
+                                         capture_error_mode="thread_local" if world > 1 else "global",
+                                         between=reducer.reduce_flat if reducer else None)
         except Exception as e:      # e.g. a process-group build that cannot be captured: run the step eagerly
             print(f"[bench] rank {rank}: CUDA-graph capture of the step failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
             graphed = None
@@ -306,8 +308,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the step eagerly instead of as one CUDA graph")
-    ap.add_argument("--graph-dp", action="store_true", help="experimental: also capture the data-parallel step (NCCL all-reduces "
-                    "inside the graph); off by default, N > 1 runs the step eagerly")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,7 +15,11 @@ import torch.distributed as dist
 
 
 class GradAllReducer:
-    def __init__(self, opt, n_buckets: int = 4, bank_params: Optional[List[torch.nn.Parameter]] = None, group=None):
+    def __init__(self, opt, n_buckets: int = 4, bank_params: Optional[List[torch.nn.Parameter]] = None, group=None,
+                 overlap: bool = True):
+        """overlap=False: no autograd hooks; the caller invokes reduce_flat() once after backward (the form used when
+        forward + backward are replayed as a CUDA graph: one 26 MB all-reduce is ~0.2 % of the step, so overlapping it
+        buys nothing there and the collective stays outside the captured graphs)."""
         self.opt, self.group = opt, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         params = opt.param_groups[0]["params"]
@@ -45,7 +49,7 @@ class GradAllReducer:
         self._handles = []
         self._hooks = []
         self._pindex = {id(p): i for i, p in enumerate(params)}
-        if self.world > 1:
+        if self.world > 1 and overlap:
             for i, p in enumerate(params):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
             try:        # parameters whose gradients the native kernels accumulate in place announce themselves here
@@ -97,6 +101,23 @@ class GradAllReducer:
         else:
             buf.div_(self.world)
             self._handles.append(dist.all_reduce(buf, group=self.group, async_op=True))
+
+    @torch.no_grad()
+    def reduce_flat(self):
+        """One all-reduce (mean) of the whole flat gradient buffer, plus the GlobalTokenBank state, on the current stream."""
+        if self.world == 1:
+            return
+        g = self.opt.flat_g
+        g.div_(self.world)
+        dist.all_reduce(g, group=self.group)
+        if self.bank_params:
+            flat = torch.cat([p.data.reshape(-1) for p in self.bank_params])
+            flat.div_(self.world)
+            dist.all_reduce(flat, group=self.group)
+            o = 0
+            for p in self.bank_params:
+                p.data.copy_(flat[o:o + p.numel()].view(p.shape))
+                o += p.numel()
 
     def finish(self):
         """After backward: flush buckets whose hooks did not all fire, average the bank state, join the side stream."""

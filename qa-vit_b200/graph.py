@@ -17,12 +17,14 @@ class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, opt, example_x: torch.Tensor, example_y: torch.Tensor,
                  label_smoothing: float = 0.0, autocast_bf16: bool = True, warmup: int = 3,
                  before_backward: Optional[Callable[[], None]] = None, after_backward: Optional[Callable[[], None]] = None,
-                 capture_error_mode: str = "global"):
+                 capture_error_mode: str = "global", between: Optional[Callable[[], None]] = None):
+        """between: called eagerly between backward and clip + AdamW (the data-parallel gradient all-reduce).  The step is
+        then two graphs -- [zero_grad, forward, loss, backward] and [clip, AdamW] -- with the collective outside both."""
         self.model, self.opt = model, opt
         self.x = example_x.clone()
         self.y = example_y.clone()
         self.ls, self.amp = label_smoothing, autocast_bf16
-        self._bb, self._ab = before_backward, after_backward
+        self._bb, self._ab, self._between = before_backward, after_backward, between
         self.loss = torch.zeros((), device=self.x.device)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -35,12 +37,20 @@ class GraphedTrainStep:
         # data-parallel runs capture the bucketed NCCL all-reduces too; the process group's watchdog thread issues CUDA
         # calls of its own, hence capture_error_mode="thread_local" there
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
-            self._step_body(eager=False)
+            if between is None:
+                self._step_body(eager=False)
+            else:
+                self._fwd_bwd()
+        self.graph2 = None
+        if between is not None:
+            torch.cuda.synchronize()
+            self.graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph2, pool=self.graph.pool(), capture_error_mode=capture_error_mode):
+                self._update()
         torch.cuda.synchronize()
 
-    def _step_body(self, eager: bool):
-        opt = self.opt
-        opt.zero_grad()
+    def _fwd_bwd(self):
+        self.opt.zero_grad()
         if self._bb:
             self._bb()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
@@ -49,9 +59,17 @@ class GraphedTrainStep:
         loss.backward()
         if self._ab:
             self._ab()
-        opt.clip()
-        opt.step()
         self.loss.copy_(loss.detach())
+
+    def _update(self):
+        self.opt.clip()
+        self.opt.step()
+
+    def _step_body(self, eager: bool):
+        self._fwd_bwd()
+        if eager and self._between:
+            self._between()
+        self._update()
 
     def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Run one training step on (x, y) (host or device tensors; None = reuse the resident batch)."""
@@ -61,4 +79,7 @@ class GraphedTrainStep:
             self.y.copy_(y, non_blocking=True)
         self.opt.write_hyper()          # lr / beta1 / bias corrections of THIS step -> pinned memory the graph reads
         self.graph.replay()
+        if self.graph2 is not None:
+            self._between()
+            self.graph2.replay()
         return self.loss
