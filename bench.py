@@ -110,7 +110,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 64
+    sample = 256
     rate, dt, cores = cpu_step_rate(sample, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
@@ -126,11 +126,14 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def gemm_roofline(device):
-    """Dominant kernel: tc_gemm_nt at the SWA qkv shape ([B*16, 192] x [576, 192]^T), timed alone."""
+def gemm_roofline(device, batch):
+    """Dominant kernel (tc_gemm_nt_kernel, ~23 % of the step over 358 launches) at its largest block shape, the SWA qkv
+    projection [B*16, 192] x [576, 192]^T, timed alone with CUDA events on the launching stream, L2 flushed before
+    every launch.  The step itself is a CUDA graph, so per-kernel events cannot be placed inside it; the kernel's share
+    of the step comes from the ncu launch list in profiles/."""
     import math
     from qavit_b200 import _lib as L
-    M, N, K = 65536, 576, 192
+    M, N, K = batch * 16, 576, 192
     A = torch.randn(M, K, device=device).bfloat16()
     W = torch.randn(N, K, device=device) / math.sqrt(K)
     Wb = W.bfloat16()
@@ -151,7 +154,15 @@ def gemm_roofline(device):
     t = sum(ts) / len(ts)
     bytes_alg = M * K * 2 + N * K * 2 + M * N * 2
     flops = 2.0 * M * N * K
-    return t, bytes_alg, flops
+    return t, bytes_alg, flops, (M, N, K)
+
+
+def measured_traffic(shape):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch at `shape` from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get("x".join(str(v) for v in shape))
 
 
 def run_ours(args):
@@ -265,10 +276,11 @@ def run_ours(args):
 
     if rank == 0:
         hbm, tf_burst, tf_sus, src = peaks()
-        t_g, bytes_g, flops_g = gemm_roofline(dev)
-        roof = {"kernel": "tc_gemm_nt_kernel (SWA qkv projection, M=65536 N=576 K=192, timed alone, L2 flushed)",
+        t_g, bytes_g, flops_g, shape_g = gemm_roofline(dev, B)
+        roof = {"kernel": f"tc_gemm_nt_kernel (SWA qkv projection, M={shape_g[0]} N={shape_g[1]} K={shape_g[2]}, timed alone, L2 flushed)",
                 "bound": "hbm", "achieved": bytes_g / t_g / 1e9, "peak": hbm, "unit": "GB/s", "frac": bytes_g / t_g / 1e9 / hbm,
-                "traffic": None, "peak_source": src, "tensor_tflops": flops_g / t_g / 1e12,
+                "traffic": measured_traffic(shape_g), "algorithmic_bytes": bytes_g, "peak_source": src + " (burst: kernel timed alone)",
+                "tensor_tflops": flops_g / t_g / 1e12,
                 "tensor_frac_of_burst": flops_g / t_g / 1e12 / tf_burst}
         # whole-step tensor utilisation against the sustained peak, F_min_train = 3 x (185.4 + 1.2 + 199.7) MFLOP / image
         f_train = 3 * (185.4 + 1.22 + 199.7) * 1e6
@@ -276,16 +288,16 @@ def run_ours(args):
         roof["step_frac_of_sustained_peak"] = roof["step_tflops_fmin"] / tf_sus
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, dt, cores = cpu_step_rate(64, 4, 1)
+            rate, dt, cores = cpu_step_rate(256, 8, 1)
             cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
-                   "sample": f"64 images/step x 4 steps ({4 * dt:.1f} s), fp32 oracle port, fwd+bwd+clip+AdamW"}
+                   "sample": f"256 images/step x 8 steps ({8 * dt:.1f} s of CPU work), fp32 oracle port, fwd+bwd+clip+AdamW"}
         line = {
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "dropout": 0.0, "drop_path": 0.0, "label_smoothing": 0.12, "optimizer": "AdamW+clip(0.1 per-param, 0.5 global)",
-                       "l2": "working set (saved activations ~1.4 MB/image) >> 126 MB L2; no explicit flush",
+                       "l2": "working set (saved activations ~2.6 MB/image incl. the lateral path, x batch) >> 126 MB L2; no explicit flush",
                        "lateral_cnn_path": "native (qavit_lateral_* / qavit_splitfusion_*)",
                        "cuda_graph": graphed is not None},
             "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
@@ -303,8 +315,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4096, help="images per GPU per step (the reference's 256 was sized for a "
-                    "6 GB laptop GPU; SURVEY.md 8d lists 256 / 1024 / 4096 / 16384 per GPU)")
+    ap.add_argument("--batch", type=int, default=4736, help="images per GPU per step.  The reference's 256 was sized for a 6 GB "
+                    "laptop GPU (SURVEY.md 8d lists 256 / 1024 / 4096 / 16384 per GPU); 4736 = 148 SMs x 32 makes every "
+                    "row count of the step (B*16 and B*64 token rows) a whole number of 128-row GEMM tiles per SM")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the step eagerly instead of as one CUDA graph")

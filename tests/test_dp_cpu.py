@@ -48,6 +48,16 @@ def _worker(rank, world, port, ret):
     red.finish()
     ok = all(torch.allclose(p.grad, torch.full_like(p, (1 + world) / 2)) for p in params)
     ok = ok and torch.allclose(bank.data, torch.full((4,), (1 + world) / 2))
+    # graph-mode flavour: no hooks, one all-reduce of the whole flat buffer (+ the bank state) after backward
+    opt2 = _FakeOpt(params)
+    bank.data.fill_(float(rank + 1))
+    red2 = GradAllReducer(opt2, n_buckets=3, bank_params=[bank], overlap=False)
+    assert not red2._hooks
+    for p in params:
+        p.grad.fill_(float(rank + 1))
+    red2.reduce_flat()
+    ok = ok and all(torch.allclose(p.grad, torch.full_like(p, (1 + world) / 2)) for p in params)
+    ok = ok and torch.allclose(bank.data, torch.full((4,), (1 + world) / 2))
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
