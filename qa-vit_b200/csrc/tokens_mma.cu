@@ -10,6 +10,10 @@
 // to bf16 once into shared memory and read with ldmatrix; outputs leave the accumulator fragments as fp32 float2
 // stores.  A 16-wide problem has no use for a 128-row tcgen05 tile (8 images would have to be stacked block-
 // diagonally), which is why this is warp-level MMA.  HBM-bound in the ideal: one pass over x / dx / up / dup.
+// The FORWARD kernels keep their operands as bf16 PAIRS (hi + lo, v = hi + lo to ~16 mantissa bits) and compute every
+// product as three MMAs (hi*hi + lo*hi + hi*lo): the token stream is the fp32 residual stream, and rounding it to 8
+// mantissa bits in the forward pass moved the whole-model bf16 logits from 0.9e-2 to 1.4-1.9e-2 of the fp32 run (the
+// north-star gate is 1e-2).  The backward kernels use plain bf16 operands, like the reference's autocast bmm / Linear.
 // fp32 runs and other shapes use the SIMT kernels of tokens.cu / misc.cu.
 #include "kernels.h"
 
@@ -56,8 +60,15 @@ __device__ __forceinline__ void ldBt(uint32_t* b, const bf16* base, int pitch, i
   ldsm4t(b, sa(base + (k0 + r + (mat & 1) * 8) * pitch + n0 + (mat >> 1) * 8));
 }
 
-// fp32 global [rows][C] -> bf16 smem [rows][pitch]
-__device__ __forceinline__ void tile_to_bf16(bf16* dst, int pitch, const float* __restrict__ src, int rows, int C) {
+__device__ __forceinline__ void split2(float x, float y, uint32_t* hi, uint32_t* lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const float2 hf = __bfloat1622float2(h);
+  *hi = *reinterpret_cast<const uint32_t*>(&h);
+  *lo = pack2(x - hf.x, y - hf.y);
+}
+// fp32 global [rows][C] -> bf16 hi (/ lo when HL) smem tiles [rows][pitch]
+template <bool HL>
+__device__ __forceinline__ void tile_to_bf16(bf16* dhi, bf16* dlo, int pitch, const float* __restrict__ src, int rows, int C) {
   const int c4n = C / 4, total = rows * c4n;
   for (int base = 0; base < total; base += 8 * blockDim.x) {     // 8 independent 16 B loads in flight per thread
     float4 v[8];
@@ -69,30 +80,58 @@ __device__ __forceinline__ void tile_to_bf16(bf16* dst, int pitch, const float* 
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int i = base + u * blockDim.x + threadIdx.x;
-      if (i < total) *reinterpret_cast<uint2*>(dst + (i / c4n) * pitch + (i % c4n) * 4) = make_uint2(pack2(v[u].x, v[u].y), pack2(v[u].z, v[u].w));
+      if (i < total) {
+        uint32_t h0, l0, h1, l1;
+        split2(v[u].x, v[u].y, &h0, &l0);
+        split2(v[u].z, v[u].w, &h1, &l1);
+        const int o = (i / c4n) * pitch + (i % c4n) * 4;
+        *reinterpret_cast<uint2*>(dhi + o) = make_uint2(h0, h1);
+        if (HL) *reinterpret_cast<uint2*>(dlo + o) = make_uint2(l0, l1);
+      }
     }
+  }
+}
+template <bool HL>
+__device__ __forceinline__ void store_split(bf16* hi, bf16* lo, int idx, float v) {
+  const bf16 h = __float2bfloat16_rn(v);
+  hi[idx] = h;
+  if (HL) lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+// acc += (ah + al) (bh + bl) without the lo * lo term; HL == false: plain bf16 product
+template <bool HL>
+__device__ __forceinline__ void mma3(float* acc, const uint32_t* ah, const uint32_t* al, uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma16816(acc, ah, bh0, bh1);
+  if (HL) {
+    mma16816(acc, al, bh0, bh1);
+    mma16816(acc, ah, bl0, bl1);
   }
 }
 
 struct Smem {
-  bf16* X;     // [N][XP]   stream tile (x or dup)
-  bf16* D;     // [16][XP]  compressed tile (xc or dxc)
-  bf16* S;     // [N][SP]   S or W
-  float* F;    // [N][16]   fp32 S / logits
-  float* R;    // [8][16] + [16] reductions
+  bf16 *X, *XL;   // [N][XP]   stream tile (x or dup), hi / lo
+  bf16 *D, *DL;   // [16][XP]  compressed tile (xc or dxc)
+  bf16 *S, *SL;   // [N][SP]   S or W
+  float* F;       // [N][16]   fp32 S / logits
+  float* R;       // [8][16] + [16] reductions
 };
-__device__ __forceinline__ Smem carve(uint8_t* base, int N, int XP) {
+__device__ __host__ __forceinline__ size_t x_elems(int N, int XP, bool needX) { return needX ? (size_t)N * XP : 0; }
+__device__ __host__ __forceinline__ size_t d_elems(int XP, bool needD) { return needD ? (size_t)M16 * XP : 0; }
+__device__ __forceinline__ Smem carve(uint8_t* base, int N, int XP, bool hl, bool needX = true, bool needD = true) {
   Smem s;
+  const size_t k = hl ? 1 : 0;             // lo tiles exist only in the split-precision kernels
   s.X = reinterpret_cast<bf16*>(base);
-  s.D = s.X + (size_t)N * XP;
-  s.S = s.D + (size_t)M16 * XP;
-  s.F = reinterpret_cast<float*>(s.S + (size_t)N * SP);
+  s.XL = s.X + k * x_elems(N, XP, needX);
+  s.D = s.XL + x_elems(N, XP, needX);
+  s.DL = s.D + k * d_elems(XP, needD);
+  s.S = s.DL + d_elems(XP, needD);
+  s.SL = s.S + k * (size_t)N * SP;
+  s.F = reinterpret_cast<float*>(s.SL + (size_t)N * SP);
   s.R = s.F + (size_t)N * M16;
   return s;
 }
-size_t smem_bytes(int N, int C) {
+size_t smem_bytes(int N, int C, bool hl, bool needX = true, bool needD = true) {
   const int XP = C + 8;
-  return ((size_t)N * XP + (size_t)M16 * XP + (size_t)N * SP) * 2 + ((size_t)N * M16 + 9 * M16) * 4 + 16;
+  return (hl ? 2 : 1) * (x_elems(N, XP, needX) + d_elems(XP, needD) + (size_t)N * SP) * 2 + ((size_t)N * M16 + 9 * M16) * 4 + 16;
 }
 
 // ---------------------------------------------------------------------------------------------- TokenLearner forward
@@ -100,13 +139,13 @@ __global__ void __launch_bounds__(NWARP * 32) tlm_fwd_kernel(const float* __rest
                                                              int C, float* __restrict__ Sout, float* __restrict__ xc) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
-  Smem sm = carve(smraw, N, XP);
+  Smem sm = carve(smraw, N, XP, true, true, false);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int col = tid % M16, part = tid / M16;          // softmax: 8 threads per slot
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     for (int i = tid; i < N * M16; i += blockDim.x) sm.F[i] = __bfloat162float(logits[(long)b * N * M16 + i]);
-    tile_to_bf16(sm.X, XP, x + (long)b * N * C, N, C);
+    tile_to_bf16<true>(sm.X, sm.XL, XP, x + (long)b * N * C, N, C);
     __syncthreads();
     float mx = -INFINITY;
     for (int n = part; n < N; n += 8) mx = fmaxf(mx, sm.F[n * M16 + col]);
@@ -126,18 +165,20 @@ __global__ void __launch_bounds__(NWARP * 32) tlm_fwd_kernel(const float* __rest
     for (int n = part; n < N; n += 8) {
       const float s = sm.F[n * M16 + col] * z;
       Sout[(long)b * N * M16 + n * M16 + col] = s;
-      sm.S[n * SP + col] = __float2bfloat16_rn(s);
+      store_split<true>(sm.S, sm.SL, n * SP + col, s);
     }
     __syncthreads();
     // xc[16, C] = S^T x : A = S^T (from [k = token][m = slot]), B = x (from [k = token][n = channel])
     for (int pair = warp; pair < C / 16; pair += NWARP) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       for (int ks = 0; ks < N / 16; ++ks) {
-        uint32_t a[4], bb[4];
+        uint32_t a[4], al[4], bb[4], bl[4];
         ldAt(a, sm.S, SP, 0, ks * 16, lane);
+        ldAt(al, sm.SL, SP, 0, ks * 16, lane);
         ldBt(bb, sm.X, XP, pair * 16, ks * 16, lane);
-        mma16816(acc[0], a, bb[0], bb[1]);
-        mma16816(acc[1], a, bb[2], bb[3]);
+        ldBt(bl, sm.XL, XP, pair * 16, ks * 16, lane);
+        mma3<true>(acc[0], a, al, bb[0], bb[1], bl[0], bl[1]);
+        mma3<true>(acc[1], a, al, bb[2], bb[3], bl[2], bl[3]);
       }
       float* o = xc + (long)b * M16 * C + pair * 16 + 2 * t;
 #pragma unroll
@@ -155,18 +196,18 @@ __global__ void __launch_bounds__(NWARP * 32) tlm_bwd_kernel(const float* __rest
                                                              bf16* __restrict__ dlogits, float* __restrict__ dx) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
-  Smem sm = carve(smraw, N, XP);
+  Smem sm = carve(smraw, N, XP, false);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     for (int i = tid; i < N * M16; i += blockDim.x) {
       const float s = S[(long)b * N * M16 + i];
       sm.F[i] = s;
-      sm.S[(i / M16) * SP + i % M16] = __float2bfloat16_rn(s);
+      store_split<false>(sm.S, sm.SL, (i / M16) * SP + i % M16, s);
     }
     if (tid < M16) sm.R[tid] = 0.f;
-    tile_to_bf16(sm.X, XP, x + (long)b * N * C, N, C);
-    tile_to_bf16(sm.D, XP, dxc + (long)b * M16 * C, M16, C);
+    tile_to_bf16<false>(sm.X, sm.XL, XP, x + (long)b * N * C, N, C);
+    tile_to_bf16<false>(sm.D, sm.DL, XP, dxc + (long)b * M16 * C, M16, C);
     __syncthreads();
     // dS[N, 16] = x dxc^T (this warp's token tiles), kept in registers until the column sums are known
     constexpr int MAXT = 2;                 // token tiles per warp: N <= 128
@@ -180,11 +221,11 @@ __global__ void __launch_bounds__(NWARP * 32) tlm_bwd_kernel(const float* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) dS[nt][h][j] = 0.f;
       for (int ks = 0; ks < C / 16; ++ks) {
-        uint32_t a[4], bb[4];
+        uint32_t a[4], al[4] = {0u, 0u, 0u, 0u}, bb[4], bl[4] = {0u, 0u, 0u, 0u};
         ldA(a, sm.X, XP, mt * 16, ks * 16, lane);
         ldB(bb, sm.D, XP, 0, ks * 16, lane);
-        mma16816(dS[nt][0], a, bb[0], bb[1]);
-        mma16816(dS[nt][1], a, bb[2], bb[3]);
+        mma3<false>(dS[nt][0], a, al, bb[0], bb[1], bl[0], bl[1]);
+        mma3<false>(dS[nt][1], a, al, bb[2], bb[3], bl[2], bl[3]);
       }
       // partial column sums of S * dS over this tile's rows
       float cs[2][2];
@@ -223,15 +264,15 @@ __global__ void __launch_bounds__(NWARP * 32) tlm_bwd_kernel(const float* __rest
         *reinterpret_cast<uint32_t*>(dlogits + ((long)b * N + r1) * M16 + c) = hi;
       }
       // dx[N, C] = S dxc : A = S (from [m = token][k = slot]), B = dxc (from [k = slot][n = channel])
-      uint32_t a[4];
+      uint32_t a[4], al[4] = {0u, 0u, 0u, 0u};
       ldA(a, sm.S, SP, mt * 16, 0, lane);
       float* o = dx + ((long)b * N + mt * 16) * C + 2 * t;
       for (int pair = 0; pair < C / 16; ++pair) {
-        uint32_t bb[4];
+        uint32_t bb[4], bl[4] = {0u, 0u, 0u, 0u};
         ldBt(bb, sm.D, XP, pair * 16, 0, lane);
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        mma16816(acc[0], a, bb[0], bb[1]);
-        mma16816(acc[1], a, bb[2], bb[3]);
+        mma3<false>(acc[0], a, al, bb[0], bb[1], bl[0], bl[1]);
+        mma3<false>(acc[1], a, al, bb[2], bb[3], bl[2], bl[3]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           *reinterpret_cast<float2*>(o + (long)g * C + pair * 16 + h * 8) = make_float2(acc[h][0], acc[h][1]);
@@ -248,25 +289,27 @@ __global__ void __launch_bounds__(NWARP * 32) upm_fwd_kernel(const float* __rest
                                                              float* __restrict__ up) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
-  Smem sm = carve(smraw, N, XP);
+  Smem sm = carve(smraw, N, XP, true, false, true);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < N * M16; i += blockDim.x) sm.S[(i / M16) * SP + i % M16] = __float2bfloat16_rn(W[i]);
+  for (int i = tid; i < N * M16; i += blockDim.x) store_split<true>(sm.S, sm.SL, (i / M16) * SP + i % M16, W[i]);
   for (int i = tid; i < N; i += blockDim.x) sm.F[i] = bias[i];
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    tile_to_bf16(sm.D, XP, xc + (long)b * M16 * C, M16, C);
+    tile_to_bf16<true>(sm.D, sm.DL, XP, xc + (long)b * M16 * C, M16, C);
     __syncthreads();
     for (int mt = warp; mt < N / 16; mt += NWARP) {
-      uint32_t a[4];
+      uint32_t a[4], al[4];
       ldA(a, sm.S, SP, mt * 16, 0, lane);
+      ldA(al, sm.SL, SP, mt * 16, 0, lane);
       const float b0 = sm.F[mt * 16 + g], b1 = sm.F[mt * 16 + g + 8];
       float* o = up + ((long)b * N + mt * 16) * C + 2 * t;
       for (int pair = 0; pair < C / 16; ++pair) {
-        uint32_t bb[4];
+        uint32_t bb[4], bl[4];
         ldBt(bb, sm.D, XP, pair * 16, 0, lane);
+        ldBt(bl, sm.DL, XP, pair * 16, 0, lane);
         float acc[2][4] = {{b0, b0, b1, b1}, {b0, b0, b1, b1}};
-        mma16816(acc[0], a, bb[0], bb[1]);
-        mma16816(acc[1], a, bb[2], bb[3]);
+        mma3<true>(acc[0], a, al, bb[0], bb[1], bl[0], bl[1]);
+        mma3<true>(acc[1], a, al, bb[2], bb[3], bl[2], bl[3]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           *reinterpret_cast<float2*>(o + (long)g * C + pair * 16 + h * 8) = make_float2(acc[h][0], acc[h][1]);
@@ -283,9 +326,9 @@ __global__ void __launch_bounds__(NWARP * 32) upm_bwd_kernel(const float* __rest
                                                              float* __restrict__ dW, float* __restrict__ dbias) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
-  Smem sm = carve(smraw, N, XP);
+  Smem sm = carve(smraw, N, XP, false);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < N * M16; i += blockDim.x) sm.S[(i / M16) * SP + i % M16] = __float2bfloat16_rn(W[i]);
+  for (int i = tid; i < N * M16; i += blockDim.x) store_split<false>(sm.S, sm.SL, (i / M16) * SP + i % M16, W[i]);
   constexpr int MAXT = 2;
   float aW[MAXT][2][4], aB[MAXT][4];
 #pragma unroll
@@ -296,18 +339,18 @@ __global__ void __launch_bounds__(NWARP * 32) upm_bwd_kernel(const float* __rest
   const uint32_t ones = pack2(1.f, 1.f);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    tile_to_bf16(sm.X, XP, dup + (long)b * N * C, N, C);
-    tile_to_bf16(sm.D, XP, xc + (long)b * M16 * C, M16, C);
+    tile_to_bf16<false>(sm.X, sm.XL, XP, dup + (long)b * N * C, N, C);
+    tile_to_bf16<false>(sm.D, sm.DL, XP, xc + (long)b * M16 * C, M16, C);
     __syncthreads();
     // dxc[16, C] = W^T dup : A = W^T (from [k = token][m = slot]), B = dup (from [k = token][n = channel])
     for (int pair = warp; pair < C / 16; pair += NWARP) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       for (int ks = 0; ks < N / 16; ++ks) {
-        uint32_t a[4], bb[4];
+        uint32_t a[4], al[4] = {0u, 0u, 0u, 0u}, bb[4], bl[4] = {0u, 0u, 0u, 0u};
         ldAt(a, sm.S, SP, 0, ks * 16, lane);
         ldBt(bb, sm.X, XP, pair * 16, ks * 16, lane);
-        mma16816(acc[0], a, bb[0], bb[1]);
-        mma16816(acc[1], a, bb[2], bb[3]);
+        mma3<false>(acc[0], a, al, bb[0], bb[1], bl[0], bl[1]);
+        mma3<false>(acc[1], a, al, bb[2], bb[3], bl[2], bl[3]);
       }
       float* o = dxc + (long)b * M16 * C + pair * 16 + 2 * t;
 #pragma unroll
@@ -322,11 +365,11 @@ __global__ void __launch_bounds__(NWARP * 32) upm_bwd_kernel(const float* __rest
       const int mt = warp + nt * NWARP;
       if (mt >= N / 16) break;
       for (int ks = 0; ks < C / 16; ++ks) {
-        uint32_t a[4], bb[4];
+        uint32_t a[4], al[4] = {0u, 0u, 0u, 0u}, bb[4], bl[4] = {0u, 0u, 0u, 0u};
         ldA(a, sm.X, XP, mt * 16, ks * 16, lane);
         ldB(bb, sm.D, XP, 0, ks * 16, lane);
-        mma16816(aW[nt][0], a, bb[0], bb[1]);
-        mma16816(aW[nt][1], a, bb[2], bb[3]);
+        mma3<false>(aW[nt][0], a, al, bb[0], bb[1], bl[0], bl[1]);
+        mma3<false>(aW[nt][1], a, al, bb[2], bb[3], bl[2], bl[3]);
         mma16816(aB[nt], a, ones, ones);
       }
     }
@@ -359,8 +402,9 @@ __global__ void __launch_bounds__(NWARP * 32) bwr_mma_kernel(const bf16* __restr
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = 2 * d + 8;
   bf16* sX = reinterpret_cast<bf16*>(smraw);                  // [Nt][XP]  [c | tn]
-  bf16* sS = sX + (size_t)Nt * XP;                             // [Nt][SP]
-  float* sF = reinterpret_cast<float*>(sS + (size_t)Nt * SP);  // [Nt][16]
+  bf16* sS = sX + (size_t)Nt * XP;                             // [Nt][SP]  gate, high bf16 part
+  bf16* sL = sS + (size_t)Nt * SP;                             // [Nt][SP]  gate, low part: S = hi + lo to ~16 mantissa bits
+  float* sF = reinterpret_cast<float*>(sL + (size_t)Nt * SP);  // [Nt][16]
   float* sR = sF + (size_t)Nt * M16;                           // [8][16]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int col = tid % M16, part = tid / M16;
@@ -398,11 +442,17 @@ __global__ void __launch_bounds__(NWARP * 32) bwr_mma_kernel(const bf16* __restr
 #pragma unroll
     for (int k = 0; k < 8; ++k) z += sR[k * M16 + col];
     z = 1.f / z;
-    for (int n = part; n < Nt; n += 8) sS[n * SP + col] = __float2bfloat16_rn(sF[n * M16 + col] * z);
+    for (int n = part; n < Nt; n += 8) {
+      const float sv = sF[n * M16 + col] * z;
+      const bf16 hi = __float2bfloat16_rn(sv);
+      sS[n * SP + col] = hi;
+      sL[n * SP + col] = __float2bfloat16_rn(sv - __bfloat162float(hi));
+    }
     __syncthreads();
     for (int ks = 0; ks < Nt / 16; ++ks) {
-      uint32_t a[4];
+      uint32_t a[4], al[4];
       ldAt(a, sS, SP, 0, ks * 16, lane);
+      ldAt(al, sL, SP, 0, ks * 16, lane);
 #pragma unroll
       for (int q = 0; q < MAXP; ++q) {
         const int pair = warp + q * NWARP;
@@ -411,6 +461,8 @@ __global__ void __launch_bounds__(NWARP * 32) bwr_mma_kernel(const bf16* __restr
         ldBt(bb, sX, XP, pair * 16, ks * 16, lane);
         mma16816(acc[q][0], a, bb[0], bb[1]);
         mma16816(acc[q][1], a, bb[2], bb[3]);
+        mma16816(acc[q][0], al, bb[0], bb[1]);
+        mma16816(acc[q][1], al, bb[2], bb[3]);
       }
     }
   }
@@ -445,21 +497,21 @@ int tok_grid(int B, size_t smem) {
 bool tokens_mma_ok(int M, int N, int C) { return M == 16 && N % 16 == 0 && N >= 16 && N <= 128 && C % 16 == 0 && C <= 512; }
 
 int tlm_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, int C, float* S, float* xc) {
-  const size_t smem = smem_bytes(N, C);
+  const size_t smem = smem_bytes(N, C, true, true, false);
   QV_TRY(opt_in(tlm_fwd_kernel, smem));
   tlm_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, (const bf16*)logits, B, N, C, S, xc);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int tlm_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx) {
-  const size_t smem = smem_bytes(N, C);
+  const size_t smem = smem_bytes(N, C, false);
   QV_TRY(opt_in(tlm_bwd_kernel, smem));
   tlm_bwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, S, dxc, B, N, C, (bf16*)dlogits, dx);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int upm_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W, const float* bias, float* up) {
-  const size_t smem = smem_bytes(N, C);
+  const size_t smem = smem_bytes(N, C, true, false, true);
   QV_TRY(opt_in(upm_fwd_kernel, smem));
   upm_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(xc, B, N, C, W, bias, up);
   QV_LAUNCH_CHECK();
@@ -467,7 +519,7 @@ int upm_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W
 }
 int upm_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int C, const float* W, float* dxc, float* dW,
             float* dbias) {
-  const size_t smem = smem_bytes(N, C);
+  const size_t smem = smem_bytes(N, C, false);
   QV_TRY(opt_in(upm_bwd_kernel, smem));
   // the dW / dbias accumulators are flushed with atomics once per CTA: keep the CTA count moderate
   const int grid = max(1, min(B, qv_num_sms() * 3));
@@ -480,7 +532,7 @@ bool bank_write_mma_ok(int Nt, int d, int kb, int ldcg) {
   return kb == 16 && Nt % 16 == 0 && Nt >= 16 && Nt <= 256 && d % 16 == 0 && d <= 256 && ldcg % 8 == 0;
 }
 int bank_write_reduce_mma(cudaStream_t s, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, float* partial, int* n_partial) {
-  const size_t smem = ((size_t)Nt * (2 * d + 8) + (size_t)Nt * SP) * 2 + ((size_t)Nt * M16 + 8 * M16) * 4 + 16;
+  const size_t smem = ((size_t)Nt * (2 * d + 8) + (size_t)2 * Nt * SP) * 2 + ((size_t)Nt * M16 + 8 * M16) * 4 + 16;
   QV_TRY(opt_in(bwr_mma_kernel, smem));
   const int occ = max(1, min(4, (int)(200 * 1024 / (smem + 1024))));
   const int grid = max(1, min(cdiv(B, 2), min(592, qv_num_sms() * occ)));
