@@ -30,6 +30,30 @@ import torch  # noqa: E402
 METRIC = "train images/sec (HQAViT CIFAR-100 shape, fwd+bwd+clip+AdamW)"
 WORKLOAD = "HQAViT CIFAR-100 32x32 training step, bf16, synthetic batch"
 
+# BASELINE.json configs: [1] is the default bench line; [2] / [3] / [4] are selectable for the record (profiles/).
+# fwd MFLOP / image = F_min of SURVEY.md 8d (blocks) + rest of the model.
+WORKLOADS = {
+    "hqavit_c100": dict(family="hqavit", img=32, classes=100, kw={}, ctor={}, fwd_mflop=185.4 + 1.22 + 199.7,
+                        label="HQAViT CIFAR-100 32x32"),
+    "qavitv2_c100": dict(family="qavit", img=32, classes=100, kw={}, ctor=dict(variant="v2"), fwd_mflop=713.4 + 1.22,
+                         label="QAViTv2 CIFAR-100 32x32 (= QAViTV2_EXTREME model)"),
+    "hqavit_tinyin": dict(family="hqavit", img=64, classes=200, kw=dict(depth=12, num_learned_tokens=64),
+                          ctor=dict(stage_depths=(2, 2, 6, 2), square_tokens=True), fwd_mflop=1296.6 + 803.0,
+                          label="HQAViT TinyImageNet 64x64"),
+}
+
+
+def build_workload(Q, name):
+    w = WORKLOADS[name]
+    common = dict(img_size=w["img"], num_classes=w["classes"], dropout=0.0, drop_path=0.0, **w["kw"])
+    if w["family"] == "hqavit":
+        model = Q.HQAViT(Q.HQAViTConfig(**common), **w["ctor"])
+        for n in ("fuse2", "fuse3", "fuse4"):
+            getattr(model, n).cat_mlp[3].p = 0.0
+    else:
+        model = Q.QAViT(Q.QAViTConfig(**common), **w["ctor"])
+    return model, w
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -180,11 +204,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(42)
-    cfg = Q.HQAViTConfig(dropout=0.0, drop_path=0.0)
-    model = Q.HQAViT(cfg)
-    for n in ("fuse2", "fuse3", "fuse4"):
-        getattr(model, n).cat_mlp[3].p = 0.0
-    model = model.to(dev).train().set_precision("bf16")
+    model, wl = build_workload(Q, args.workload)
+    infer = args.mode == "infer"
+    model = model.to(dev).set_precision("bf16")
+    model = model.eval() if infer else model.train()
     if world > 1:       # identical replicas
         for p in model.parameters():
             dist.broadcast(p.data, 0)
@@ -198,11 +221,14 @@ def run_ours(args):
                                overlap=not args.graph) if world > 1 else None
 
     g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
-    y_host = torch.randint(0, 100, (B,), generator=g).pin_memory()
+    x_host = torch.randn(B, 3, wl["img"], wl["img"], generator=g).pin_memory()
+    y_host = torch.randint(0, wl["classes"], (B,), generator=g).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
     def step(x, y):
+        if infer:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return model(x).float().logsumexp(1).mean()      # a scalar that depends on every logit
         opt.zero_grad()
         if reducer and not args.graph:
             reducer.reset()
@@ -224,7 +250,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_step = L.lib.qavit_launch_count() - l0
     graphed = None
-    if args.graph:
+    if args.graph and not infer:
         try:
             graphed = Q.GraphedTrainStep(model, opt, x_dev, y_dev, label_smoothing=0.12, autocast_bf16=True, warmup=3,
                                          capture_error_mode="thread_local" if world > 1 else "global",
@@ -233,6 +259,31 @@ def run_ours(args):
             print(f"[bench] rank {rank}: CUDA-graph capture of the step failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
             graphed = None
             torch.cuda.synchronize()
+
+    if args.graph and infer:
+        class _GraphedInfer:
+            """Eval-mode forward captured once and replayed (the eager forward is launch-bound from Python)."""
+
+            def __init__(self):
+                self.x = x_dev.clone()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        step(self.x, None)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                self.g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.g):
+                    self.out = step(self.x, None)
+
+            def __call__(self, x=None, y=None):
+                if x is not None:
+                    self.x.copy_(x, non_blocking=True)
+                self.g.replay()
+                return self.out
+
+        graphed = _GraphedInfer()
 
     def timed(nsteps, from_host):
         if world > 1:
@@ -283,19 +334,22 @@ def run_ours(args):
                 "tensor_tflops": flops_g / t_g / 1e12,
                 "tensor_frac_of_burst": flops_g / t_g / 1e12 / tf_burst}
         # whole-step tensor utilisation against the sustained peak, F_min_train = 3 x (185.4 + 1.2 + 199.7) MFLOP / image
-        f_train = 3 * (185.4 + 1.22 + 199.7) * 1e6
+        f_train = (1 if infer else 3) * wl["fwd_mflop"] * 1e6
         roof["step_tflops_fmin"] = value / world * f_train / 1e12
         roof["step_frac_of_sustained_peak"] = roof["step_tflops_fmin"] / tf_sus
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "hqavit_c100" and not infer:
             rate, dt, cores = cpu_step_rate(256, 8, 1)
             cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                    "sample": f"256 images/step x 8 steps ({8 * dt:.1f} s of CPU work), fp32 oracle port, fwd+bwd+clip+AdamW"}
+        default = args.workload == "hqavit_c100" and not infer
+        metric = METRIC if default else f"{'inference' if infer else 'train'} images/sec ({wl['label']}" + (")" if infer else ", fwd+bwd+clip+AdamW)")
+        workload = WORKLOAD if default else f"{wl['label']} {'eval-mode forward' if infer else 'training step'}, bf16, synthetic batch"
         line = {
-            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": metric, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+            "config": {"workload": workload, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "dropout": 0.0, "drop_path": 0.0, "label_smoothing": 0.12, "optimizer": "AdamW+clip(0.1 per-param, 0.5 global)",
                        "l2": "working set (saved activations ~2.6 MB/image incl. the lateral path, x batch) >> 126 MB L2; no explicit flush",
                        "lateral_cnn_path": "native (qavit_lateral_* / qavit_splitfusion_*)",
@@ -319,6 +373,8 @@ def main():
                     "laptop GPU (SURVEY.md 8d lists 256 / 1024 / 4096 / 16384 per GPU); 4736 = 148 SMs x 32 makes every "
                     "row count of the step (B*16 and B*64 token rows) a whole number of 128-row GEMM tiles per SM")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hqavit_c100", choices=sorted(WORKLOADS), help="default: BASELINE.json configs[1]")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer: eval-mode forward throughput")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()

@@ -325,11 +325,25 @@ int launch_attn(cudaStream_t s, const AttnP& p) {
 
 }  // namespace
 
-int attn_fwd(cudaStream_t s, int dt, const AttnP& p) {
+// Cross attention (mode 2) has no per-image keys (K / V are the batch-invariant bank projections), so an image with
+// Nt = 16 m query tokens is the same problem as m images of 16 tokens: lets the 64-token blocks (QAViTv2, TinyImageNet)
+// use the 16-query tensor-core kernel.
+static AttnP as_tiles16(const AttnP& p) {
+  AttnP q = p;
+  if (p.mode == 2 && p.Nt > 16 && p.Nt % 16 == 0) {
+    q.B = p.B * (p.Nt / 16);
+    q.Nt = 16;
+  }
+  return q;
+}
+
+int attn_fwd(cudaStream_t s, int dt, const AttnP& p0) {
+  const AttnP p = (dt == QV_BF16) ? as_tiles16(p0) : p0;
   if (dt == QV_BF16 && attn_mma_ok(p)) return attn_mma_fwd(s, p);   // tensor-core path (attn_mma.cu)
   return dt == QV_F32 ? launch_attn<float, false>(s, p) : launch_attn<bf16, false>(s, p);
 }
-int attn_bwd(cudaStream_t s, int dt, const AttnP& p) {
+int attn_bwd(cudaStream_t s, int dt, const AttnP& p0) {
+  const AttnP p = (dt == QV_BF16) ? as_tiles16(p0) : p0;
   if (dt == QV_BF16 && attn_mma_ok(p)) return attn_mma_bwd(s, p);
   return dt == QV_F32 ? launch_attn<float, true>(s, p) : launch_attn<bf16, true>(s, p);
 }
