@@ -287,13 +287,28 @@ int cga_bwd(cudaStream_t s, int dt, const CgaP& p) {
 // them per image, H:617-619).  Single small grid, fp32.
 // =====================================================================================================
 namespace {
-__global__ void small_linear_fwd_kernel(const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * N) return;
-  const int r = idx / N, n = idx % N;
-  float a = b ? b[n] : 0.f;
-  for (int k = 0; k < K; ++k) a = fmaf(X[r * K + k], W[n * K + k], a);
-  Y[idx] = a;
+// One warp per output element group: lanes stride over K (coalesced reads of the W row), shuffle reduction.
+__global__ void __launch_bounds__(128) small_linear_fwd_kernel(const float* __restrict__ X, int rows, int K, const float* __restrict__ W,
+                                                               const float* __restrict__ b, int N, float* __restrict__ Y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;                       // a warp owns output column n for every row: W[n, :] is read once
+  const int n = warp;
+  for (int r0 = 0; r0 < rows; r0 += 8) {
+    float a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float w = W[n * K + k];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r0 + q < rows) a[q] = fmaf(X[(r0 + q) * K + k], w, a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float v = warp_sum(a[q]);
+      if (lane == 0 && r0 + q < rows) Y[(r0 + q) * N + n] = v + (b ? b[n] : 0.f);
+    }
+  }
 }
 // dW[n,k] += sum_r dY[r,n] X[r,k]; db[n] += sum_r dY[r,n]; dX[r,k] += sum_n dY[r,n] W[n,k]
 __global__ void small_linear_bwd_kernel(const float* X, int rows, int K, const float* W, int N, const float* dY,
@@ -313,14 +328,14 @@ __global__ void small_linear_bwd_kernel(const float* X, int rows, int K, const f
   if (idx < rows * K) {
     const int r = idx / K, k = idx % K;
     float a = 0.f;
-    for (int n = 0; n < N; ++n) a = fmaf(dY[r * N + n], W[n * K + k], a);
+    for (int n = 0; n < N; ++n) a = fmaf(dY[r * N + n], W[n * K + k], a);   // lanes = consecutive k: coalesced
     dX[idx] += a;
   }
 }
 }  // namespace
 
 int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
-  small_linear_fwd_kernel<<<cdiv(rows * N, 128), 128, 0, s>>>(X, rows, K, W, b, N, Y);
+  small_linear_fwd_kernel<<<cdiv(N * 32, 128), 128, 0, s>>>(X, rows, K, W, b, N, Y);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -417,15 +417,18 @@ __global__ void fusion_softmax_kernel(const float* w, int n, float* alpha) {
 }
 // raw[i] += sum over rows and the i-th column slice of dfused * fused   (fused_i = alpha_i * b_i)
 template <typename T>
-__global__ void fusion_bwd_kernel(const T* __restrict__ df, const T* __restrict__ f, long rows, int nb, int cw,
-                                  float* __restrict__ raw) {
+__global__ void __launch_bounds__(256) fusion_bwd_kernel(const T* __restrict__ df, const T* __restrict__ f, long rows, int nb, int cw,
+                                                         float* __restrict__ raw) {
   __shared__ float red[4][8];
-  const int C = nb * cw;
+  const int C = nb * cw, v4 = C / 4;            // 4-element vectors never straddle a branch slice (cw % 4 == 0)
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const long total = rows * C;
+  const long total = rows * v4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int br = (int)(i % C) / cw;
-    const float v = ldf(df + i) * ldf(f + i);
+    const int br = (int)(i % v4) * 4 / cw;
+    float a[4], g[4];
+    load_vec<4>(df + i * 4, a);
+    load_vec<4>(f + i * 4, g);
+    const float v = a[0] * g[0] + a[1] * g[1] + a[2] * g[2] + a[3] * g[3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] += (br == k) ? v : 0.f;
   }
@@ -514,7 +517,7 @@ int fusion_softmax(cudaStream_t s, const float* w, int n, float* alpha) {
 int fusion_bwd(cudaStream_t s, int dt, const void* dfused, const void* fused, long rows, int nb, int cw,
                const float* alpha, float* dalpha_raw) {
   (void)alpha;
-  QV_CHECK(nb <= 4, "fusion_bwd: %d branches (<= 4)", nb);
+  QV_CHECK(nb <= 4 && cw % 4 == 0, "fusion_bwd: %d branches (<= 4) of width %d (multiple of 4)", nb, cw);
   if (rows <= 0) return 0;
   const int grid = (int)max(1L, min((long)qv_num_sms() * 4, (rows * nb * cw + 255) / 256));
   DISPATCH_T(dt, (fusion_bwd_kernel<T><<<grid, 256, 0, s>>>((const T*)dfused, (const T*)fused, rows, nb, cw, dalpha_raw)));
