@@ -24,11 +24,13 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _scratch_buf(device, nbytes: int) -> torch.Tensor:
-    """One reusable scratch allocation per device (temporaries of a block call; stream-ordered reuse)."""
-    buf = _scratch.get(device)
+    """One reusable scratch allocation per (device, stream): temporaries of a native call, reused in stream order.
+    Keyed by stream because HQAViT runs its lateral path on a side stream concurrently with the stage-1 blocks."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=device)
-        _scratch[device] = buf
+        _scratch[key] = buf
     return buf
 
 

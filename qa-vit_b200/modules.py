@@ -538,12 +538,28 @@ class HQAViT(_Base):
         buffers = [i for i, n in enumerate(names) if n.endswith(("running_mean", "running_var", "num_batches_tracked"))]
         return QF.LateralFn.apply(x, QF.LateralMeta(c, buffers), *tensors)
 
+    concurrent_lateral = True     # run the lateral path on a side stream next to patch embed + stage 1 (they are independent)
+
     def forward(self, x):
-        R2, R3, R4 = self.lateral(x)
+        side = None
+        if self.concurrent_lateral and x.is_cuda:
+            if getattr(self, "_lat_stream", None) is None:
+                object.__setattr__(self, "_lat_stream", torch.cuda.Stream(device=x.device))
+            side = self._lat_stream
+            main = torch.cuda.current_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                R2, R3, R4 = self.lateral(x)
+            for R in (R2, R3, R4):
+                R.record_stream(main)
+        else:
+            R2, R3, R4 = self.lateral(x)
         T = self.patch_embed(x, self.pos_embed)
         T = self._stream_dropout(T)
         for blk in self.stage1_blocks:
             T = blk(T)
+        if side is not None:
+            torch.cuda.current_stream(x.device).wait_stream(side)
         T = self.fuse2(T, R2)
         for blk in self.stage2_blocks:
             T = blk(T)
