@@ -257,6 +257,7 @@ CgaLay cga_layout(const CgaP& p, bool bwd) {
 int cga_fwd(cudaStream_t s, int dt, const CgaP& p) {
   if (p.B <= 0) return 0;
   if (dt == QV_BF16 && cga_mma_ok(p)) return cga_mma_fwd(s, p);   // tensor-core path (cga_mma.cu)
+  if (dt == QV_BF16 && cga_mma64_ok(p)) return cga_mma64_fwd(s, p);   // 64-token blocks (cga_mma64.cu)
   QV_CHECK(p.cg == 32 && p.cpg == 16 && p.H == 4, "CGA kernels are instantiated for 32 -> 16 channels per group and 4 heads (got %d -> %d, %d heads)", p.cg, p.cpg, p.H);
   const CgaLay ly = cga_layout(p, false);
   const size_t smem = (size_t)ly.total * sizeof(float);
@@ -271,6 +272,7 @@ int cga_fwd(cudaStream_t s, int dt, const CgaP& p) {
 int cga_bwd(cudaStream_t s, int dt, const CgaP& p) {
   if (p.B <= 0) return 0;
   if (dt == QV_BF16 && cga_mma_ok(p)) return cga_mma_bwd(s, p);
+  if (dt == QV_BF16 && cga_mma64_ok(p)) return cga_mma64_bwd(s, p);
   QV_CHECK(p.cg == 32 && p.cpg == 16 && p.H == 4, "CGA kernels are instantiated for 32 -> 16 channels per group and 4 heads");
   const CgaLay ly = cga_layout(p, true);
   const size_t smem = (size_t)ly.total * sizeof(float);

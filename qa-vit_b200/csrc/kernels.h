@@ -164,6 +164,9 @@ int cga_bwd(cudaStream_t s, int dt, const CgaP& p);
 bool cga_mma_ok(const CgaP& p);
 int cga_mma_fwd(cudaStream_t s, const CgaP& p);
 int cga_mma_bwd(cudaStream_t s, const CgaP& p);
+bool cga_mma64_ok(const CgaP& p);   // 64-token blocks: CTA per image, warp per 16-query tile (cga_mma64.cu)
+int cga_mma64_fwd(cudaStream_t s, const CgaP& p);
+int cga_mma64_bwd(cudaStream_t s, const CgaP& p);
 
 // small dense [rows<=64] projections of the bank: Y = X W^T + b and its backward (single CTA, fp32)
 int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y);
