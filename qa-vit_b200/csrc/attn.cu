@@ -340,10 +340,12 @@ static AttnP as_tiles16(const AttnP& p) {
 int attn_fwd(cudaStream_t s, int dt, const AttnP& p0) {
   const AttnP p = (dt == QV_BF16) ? as_tiles16(p0) : p0;
   if (dt == QV_BF16 && attn_mma_ok(p)) return attn_mma_fwd(s, p);   // tensor-core path (attn_mma.cu)
+  if (dt == QV_BF16 && p.wsp && attn_msda64_ok(p)) return attn_msda64_fwd(s, p, p.wsp);
   return dt == QV_F32 ? launch_attn<float, false>(s, p) : launch_attn<bf16, false>(s, p);
 }
 int attn_bwd(cudaStream_t s, int dt, const AttnP& p0) {
   const AttnP p = (dt == QV_BF16) ? as_tiles16(p0) : p0;
   if (dt == QV_BF16 && attn_mma_ok(p)) return attn_mma_bwd(s, p);
+  if (dt == QV_BF16 && p.wsp && attn_msda64_ok(p)) return attn_msda64_bwd(s, p, p.wsp);
   return dt == QV_F32 ? launch_attn<float, true>(s, p) : launch_attn<bf16, true>(s, p);
 }

@@ -113,9 +113,9 @@ struct Saved {  // byte offsets into `saved`
       h_pre, h, dn_stats, hn, cs, pd_stats, hn2, o, out_blk, up, up_stats, wb[W_COUNT], wbt[W_COUNT], wstack, bstack, total;
 };
 struct Scratch {  // byte offsets into `scratch`
-  size_t tl_logits, tn, cgbuf, partial, total_fwd;
+  size_t tl_logits, tn, cgbuf, partial, attn_ws_f, total_fwd;
   size_t d_up, d_blk, d_o, d_hn2, d_cs, d_hn, d_hpre, d_y, d_x1, d_x1t, d_h1, d_h1pre, d_fused, d_nb, d_branch, d_attn,
-      d_qkv, d_kv, d_xp, d_q, d_xn, dKc, dVc, dkbp, dvbp, draw, d_logits, d_tl_ln, total_bwd;
+      d_qkv, d_kv, d_xp, d_q, d_xn, dKc, dVc, dkbp, dvbp, draw, d_logits, d_tl_ln, attn_ws_b, total_bwd;
 };
 
 int msda_tokens(const qavit_block_cfg& c, int side) {
@@ -231,6 +231,7 @@ void layout_scratch(const Dims& D, Scratch* S) {
     S->tn = b.take(R * d * ts);
     S->cgbuf = b.take(R * (d + D.kb) * ts);
     S->partial = b.take((size_t)592 * 2 * D.kb * d * 4);   // bank_write_reduce uses <= 592 CTAs
+    S->attn_ws_f = b.take(D.dt == QV_BF16 && D.Nt > 16 ? attn_msda64_scratch_bytes(D.B, D.d) : 0);
     S->total_fwd = b.off;
   }
   {
@@ -266,6 +267,7 @@ void layout_scratch(const Dims& D, Scratch* S) {
     (void)zero_end;
     S->d_logits = b.take(D.tl ? Rf * D.Nt * ts : 0);
     S->d_tl_ln = b.take(D.tl ? Rf * d * ts : 0);
+    S->attn_ws_b = b.take(D.dt == QV_BF16 && D.Nt > 16 ? attn_msda64_scratch_bytes(D.B, D.d) : 0);
     S->total_bwd = b.off;
   }
 }
@@ -473,6 +475,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.Ek = c.pf(QP_MSDA_EK); p.Ev = c.pf(QP_MSDA_EV);
     p.bank_k = snap_k(c, 1); p.bank_v = snap_v(c, 1);
     p.out = c.sv(S.attn_msda); p.ldo = d;
+    if (dt == QV_BF16 && D.Nt > 16) p.wsp = c.sc(c.X.attn_ws_f);
     QV_TRY(attn_fwd(st, dt, p));
   }
   QV_TRY(gemm_nt(st, dt, c.sv(S.attn_msda), d, R, c.W(W_MSDA_PROJ, c.pf(QP_MSDA_PROJ_W)), epi_t(c, c.pf(QP_MSDA_PROJ_B), c.sv(S.branch[1]), d)));
@@ -688,6 +691,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       p.dq = c.sc(X.d_q); p.lddq = d; p.dqcol = 0;
       p.dkv = c.sc(X.d_kv); p.lddkv = 2 * d; p.dkcol = 0; p.dvcol = d;
       p.dEk = G(QP_MSDA_EK); p.dEv = G(QP_MSDA_EV); p.dbank_k = G(QP_BANK_K); p.dbank_v = G(QP_BANK_V);
+      if (dt == QV_BF16 && D.Nt > 16) p.wsp = c.sc(X.attn_ws_b);
       QV_TRY(attn_bwd(st, dt, p));
       QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_MSDA_QKV_W), G(QP_MSDA_QKV_B), nullptr));
       QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_MSDA_Q, c.pf(QP_MSDA_QKV_W)), acc_xn));

@@ -142,12 +142,18 @@ struct AttnP {
   void* dq; int lddq; int dqcol;             // T
   void* dkv; int lddkv; int dkcol, dvcol;    // T
   float* dEk; float* dEv; float* dbank_k; float* dbank_v;   // fp32 accumulators (mode 2: dKc/dVc in dbank_k/v)
+  void* wsp;                                 // optional workspace (attn_msda64_scratch_bytes) for the hoisted Linformer path
 };
 int attn_fwd(cudaStream_t s, int dt, const AttnP& p);
 bool attn_mma_ok(const AttnP& p);   // bf16 tensor-core (mma.sync) flavour for the 16-query shapes
 int attn_mma_fwd(cudaStream_t s, const AttnP& p);
 int attn_mma_bwd(cudaStream_t s, const AttnP& p);
 int attn_bwd(cudaStream_t s, int dt, const AttnP& p);
+// MSDA with more than 16 query tokens per image on mma.sync, Linformer contraction hoisted (attn_msda64.cu)
+bool attn_msda64_ok(const AttnP& p);
+size_t attn_msda64_scratch_bytes(int B, int D);
+int attn_msda64_fwd(cudaStream_t s, const AttnP& p, void* scratch);
+int attn_msda64_bwd(cudaStream_t s, const AttnP& p, void* scratch);
 
 struct CgaP {
   int B, Nt, G, H, kb, cg, cpg;              // cg = 32 channels/group, cpg = 16 compressed/group
