@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QAVIT_ABI_VERSION 1
+#define QAVIT_ABI_VERSION 2
 
 /* Index of every parameter tensor a (TokenLearner-wrapped) quad block reads.  qavit_block_param_name(i)
  * returns the reference state_dict suffix (relative to the wrapper prefix "stageS_blocks.I." for HQAViT,
@@ -63,6 +63,8 @@ typedef struct qavit_block_cfg {
   int32_t bank_v1;           /* 1: QAViT.py bank constants, no update counter (QAViT.py:203-224)           */
   int32_t train;             /* 1: bank writes happen (module.training)                                    */
   int32_t dtype;             /* 0 fp32, 1 bf16                                                             */
+  float dropout;             /* config.dropout: SDPA dropout_p + the nn.Dropout sites of the block (train only; H:416-465, 648-656, 697-710) */
+  float drop_path;           /* this block's DropPath rate (H:1066-1069, 1187), applied per image in train mode */
 } qavit_block_cfg;
 
 const char* qavit_last_error(void);
@@ -80,9 +82,12 @@ int qavit_block_workspace(const qavit_block_cfg* cfg, size_t* saved_bytes, size_
  * CCFFFN (H:632-712), and -- when cfg->token_learner -- TokenLearner / TokenUpMix (H:971-1031).
  *   params[QP_COUNT] : fp32 parameter tensors (reference layouts); entries not used by the config may be NULL
  *   x   [batch, tokens_full, dim] fp32      out [batch, tokens_full, dim] fp32 */
-int qavit_block_forward(const qavit_block_cfg* cfg, const void* const* params, long long* update_count, const float* x,
-                        float* out, void* saved, void* scratch, void* stream);
+int qavit_block_forward(const qavit_block_cfg* cfg, const void* const* params, long long* update_count,
+                        unsigned long long* rng, const float* x, float* out, void* saved, void* scratch, void* stream);
 
+/* rng: device {seed, offset} Philox state, required when train != 0 and (dropout > 0 or drop_path > 0), else may be
+ * NULL.  Forward snapshots it into `saved` and advances the offset ON THE DEVICE (CUDA-graph replays draw fresh masks);
+ * backward regenerates every mask from the snapshot -- no mask is stored. */
 /* Backward of the above.  grads[QP_COUNT]: fp32 buffers the parameter gradients are ACCUMULATED into (zero them
  * first; NULL for the write_* / branch .norm parameters, which the reference never trains, H:315).
  *   dout [batch, tokens_full, dim] fp32     dx [batch, tokens_full, dim] fp32 (overwritten) */
@@ -109,6 +114,12 @@ int qavit_head_forward(const float* x, int B, int N, int d, const float* ln_w, c
 int qavit_head_backward(const float* x, const float* dlogits, int B, int N, int d, const float* ln_w, const float* stats,
                         const float* pooled, const float* W, int classes, float* dpooled_scratch, float* dx,
                         float* dln_w, float* dln_b, float* dW, float* dbias, void* stream);
+
+/* nn.Dropout on a contiguous fp32 tensor of n elements (n % 8 == 0; pos_drop, H:1155 / 1251): y = x * keep / (1 - p).
+ * Forward writes the rng snapshot it used to snap[2] (device) and advances rng; backward applies the same mask to dy. */
+int qavit_dropout_forward(const float* x, float* y, long long n, float p, unsigned long long* rng, unsigned long long* snap,
+                          void* stream);
+int qavit_dropout_backward(const float* dy, float* dx, long long n, float p, const unsigned long long* snap, void* stream);
 
 /* CrossEntropyLoss(label_smoothing) with optional two-target mixup form (H:1373, 1404-1408).
  *   ya / yb: int64 class ids (yb may be NULL); loss: 1 float; dlogits may be NULL (forward only). */

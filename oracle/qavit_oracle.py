@@ -82,11 +82,25 @@ def _gelu(x: Tensor) -> Tensor:
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
-def _attn(q: Tensor, k: Tensor, v: Tensor) -> Tensor:
+def _attn(q: Tensor, k: Tensor, v: Tensor, keep: Optional[Tensor] = None) -> Tensor:
     """efficient_attention (H:355-397) on its SDPA branch: softmax(q k^T / sqrt(hd)) v,
-    no mask, dropout 0.  q[..., Nq, hd], k/v[..., Nkv, hd]."""
+    no mask.  q[..., Nq, hd], k/v[..., Nkv, hd].  ``keep`` (same shape as the
+    probabilities, values 0 or 1/(1-p)) is SDPA's dropout_p applied as an explicit
+    keep-scale: P <- P * keep, no renormalisation (H:387-392)."""
     s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(q.shape[-1]))
-    return torch.softmax(s, dim=-1) @ v
+    P = torch.softmax(s, dim=-1)
+    if keep is not None:
+        P = P * keep
+    return P @ v
+
+
+def _drop(x: Tensor, masks: Optional[dict], key: str) -> Tensor:
+    """nn.Dropout / DropPath with an explicit keep-scale tensor (0 or 1/(1-p)); identity when
+    ``masks`` is None or has no entry for ``key``.  The masks are test inputs: torch's own RNG
+    stream is not part of the contract, the positions of the dropout sites are."""
+    if masks is None or masks.get(key) is None:
+        return x
+    return x * masks[key]
 
 
 # --------------------------------------------------------------------------- bank
@@ -153,7 +167,7 @@ def _linformer(k: Tensor, v: Tensor, E_k: Tensor, E_v: Tensor) -> Tuple[Tensor, 
     return E_k.t() @ k, E_v.t() @ v
 
 
-def swa(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool) -> Tensor:
+def swa(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool, masks: Optional[dict] = None) -> Tensor:
     """EfficientSpatialWindowAttention.forward (H:441-469)."""
     B, N, C = x.shape
     s = int(math.isqrt(N))
@@ -167,10 +181,11 @@ def swa(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool) -> Te
     bk, bv = bank.read()
     bk = _heads(bk, H).expand(q.shape[0], -1, -1, -1)
     bv = _heads(bv, H).expand(q.shape[0], -1, -1, -1)
-    o = _attn(q, torch.cat([kc, bk], 2), torch.cat([vc, bv], 2))
+    o = _attn(q, torch.cat([kc, bk], 2), torch.cat([vc, bv], 2), masks.get("att_swa") if masks else None)
     o = o.transpose(1, 2).reshape(-1, w * w, C)
     o = _lin(o, sd, p + ".proj")
     o = o.view(B, nh, nh, w, w, C).permute(0, 1, 3, 2, 4, 5).reshape(B, N, C)
+    o = _drop(o, masks, "proj_swa")        # H:465 (elementwise, so applying it after the window reverse is the same op)
     if train:
         bank.write(_ln(o.detach(), sd, p + ".norm"))
     return o
@@ -187,7 +202,7 @@ def msda_pool(x: Tensor, cfg: OracleConfig) -> Tensor:
     return xm[:, : n_out * st].reshape(B, n_out, st, C).mean(2)
 
 
-def msda(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool) -> Tensor:
+def msda(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool, masks: Optional[dict] = None) -> Tensor:
     """EfficientMultiScaleDilatedAttention.forward (H:496-532)."""
     B, N, C = x.shape
     H = cfg.num_heads
@@ -198,14 +213,14 @@ def msda(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool) -> T
     bk = _heads(bk, H).expand(B, -1, -1, -1)
     bv = _heads(bv, H).expand(B, -1, -1, -1)
     q = _lin(x, sd, p + ".qkv").reshape(B, N, 3, H, C // H)[:, :, 0].permute(0, 2, 1, 3)
-    o = _attn(q, torch.cat([kc, bk], 2), torch.cat([vc, bv], 2))
-    o = _lin(o.transpose(1, 2).reshape(B, N, C), sd, p + ".proj")
+    o = _attn(q, torch.cat([kc, bk], 2), torch.cat([vc, bv], 2), masks.get("att_msda") if masks else None)
+    o = _drop(_lin(o.transpose(1, 2).reshape(B, N, C), sd, p + ".proj"), masks, "proj_msda")   # H:529
     if train:
         bank.write(_ln(o.detach(), sd, p + ".norm"))
     return o
 
 
-def cga(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool) -> Tensor:
+def cga(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool, masks: Optional[dict] = None) -> Tensor:
     """EfficientChannelGroupAttention.forward (H:559-595)."""
     B, N, C = x.shape
     G, H = cfg.num_channel_groups, cfg.num_heads
@@ -218,15 +233,15 @@ def cga(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool) -> Te
     bk, bv = bank.read()
     bk = _heads(_lin(bk, sd, p + ".bank_k_proj"), H).expand(B * G, -1, -1, -1)
     bv = _heads(_lin(bv, sd, p + ".bank_v_proj"), H).expand(B * G, -1, -1, -1)
-    o = _attn(q, torch.cat([k, bk], 2), torch.cat([v, bv], 2))
+    o = _attn(q, torch.cat([k, bk], 2), torch.cat([v, bv], 2), masks.get("att_cga") if masks else None)
     o = o.transpose(1, 2).reshape(B, G, N, cpg).permute(0, 2, 1, 3).reshape(B, N, G * cpg)
-    o = _lin(o, sd, p + ".proj")
+    o = _drop(_lin(o, sd, p + ".proj"), masks, "proj_cga")                                    # H:592
     if train:
         bank.write(_ln(o.detach(), sd, p + ".norm"))
     return o
 
 
-def cross(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank) -> Tensor:
+def cross(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, masks: Optional[dict] = None) -> Tensor:
     """CrossAttentionBranch.forward (H:613-626)."""
     B, N, C = x.shape
     H = cfg.num_heads
@@ -234,11 +249,11 @@ def cross(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank) -> Tensor:
     bk, bv = bank.read()
     k = _heads(_lin(bk, sd, p + ".k_proj"), H).expand(B, -1, -1, -1)
     v = _heads(_lin(bv, sd, p + ".v_proj"), H).expand(B, -1, -1, -1)
-    o = _attn(q, k, v).transpose(1, 2).reshape(B, N, C)
-    return _lin(o, sd, p + ".proj")
+    o = _attn(q, k, v, masks.get("att_cross") if masks else None).transpose(1, 2).reshape(B, N, C)
+    return _drop(_lin(o, sd, p + ".proj"), masks, "proj_cross")                               # H:625
 
 
-def ccf_ffn(x: Tensor, sd, p: str, cfg: OracleConfig) -> Tensor:
+def ccf_ffn(x: Tensor, sd, p: str, cfg: OracleConfig, masks: Optional[dict] = None) -> Tensor:
     """CCFFFN.forward: v2 (H:700-712, QAViTv2.py:864-885) / v1 (QAViT.py:571-582)."""
     B, N, _ = x.shape
     s = int(math.isqrt(N))
@@ -255,24 +270,28 @@ def ccf_ffn(x: Tensor, sd, p: str, cfg: OracleConfig) -> Tensor:
     h = img.flatten(2).transpose(1, 2)
     if not v1:
         h = _ln(h, sd, p + ".post_dwconv_norm")
-    h = _lin(h, sd, p + ".fc2")
+    h = _drop(_lin(h, sd, p + ".fc2"), masks, "ffn")                    # H:710 / QAViT.py:582
     if not v1:
         h = h * sd[p + ".gamma"]
     return h
 
 
-def quad_block(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool) -> Tensor:
-    """QuadAttentionBlock.forward (H:1071-1085), dropout = drop_path = 0."""
+def quad_block(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool, masks: Optional[dict] = None) -> Tensor:
+    """QuadAttentionBlock.forward (H:1071-1085).  ``masks`` (train mode only): explicit keep-scale tensors
+    for the block's dropout / DropPath sites -- att_{swa,msda,cga,cross} (attention probabilities),
+    proj_{...} (branch outputs), b1 / b2 (BottleneckMLP, H:654-656), ffn (H:710), path1 / path2
+    ([B, 1, 1], H:1082-1083); None = dropout 0."""
     xn = _ln(x, sd, p + ".norm1")
-    b0 = _lin(_ln(swa(xn, sd, p + ".swa", cfg, bank, train), sd, p + ".norm_swa"), sd, p + ".compress_swa")
-    b1 = _lin(_ln(msda(xn, sd, p + ".msda", cfg, bank, train), sd, p + ".norm_msda"), sd, p + ".compress_msda")
-    b2 = _lin(_ln(cga(xn, sd, p + ".cga", cfg, bank, train), sd, p + ".norm_cga"), sd, p + ".compress_cga")
-    b3 = _lin(_ln(cross(xn, sd, p + ".cross_attn", cfg, bank), sd, p + ".norm_cross"), sd, p + ".compress_cross")
+    b0 = _lin(_ln(swa(xn, sd, p + ".swa", cfg, bank, train, masks), sd, p + ".norm_swa"), sd, p + ".compress_swa")
+    b1 = _lin(_ln(msda(xn, sd, p + ".msda", cfg, bank, train, masks), sd, p + ".norm_msda"), sd, p + ".compress_msda")
+    b2 = _lin(_ln(cga(xn, sd, p + ".cga", cfg, bank, train, masks), sd, p + ".norm_cga"), sd, p + ".compress_cga")
+    b3 = _lin(_ln(cross(xn, sd, p + ".cross_attn", cfg, bank, masks), sd, p + ".norm_cross"), sd, p + ".compress_cross")
     a = torch.softmax(sd[p + ".fusion.fusion_weights"], 0)                       # H:637-640
     f = torch.cat([b0 * a[0], b1 * a[1], b2 * a[2], b3 * a[3]], -1)
-    m = _lin(_gelu(_lin(f, sd, p + ".bottleneck_mlp.fc1")), sd, p + ".bottleneck_mlp.fc2")
-    x = x + m
-    return x + ccf_ffn(_ln(x, sd, p + ".norm2"), sd, p + ".ccf_ffn", cfg)
+    h = _drop(_gelu(_lin(f, sd, p + ".bottleneck_mlp.fc1")), masks, "b1")
+    m = _drop(_lin(h, sd, p + ".bottleneck_mlp.fc2"), masks, "b2")
+    x = x + _drop(m, masks, "path1")
+    return x + _drop(ccf_ffn(_ln(x, sd, p + ".norm2"), sd, p + ".ccf_ffn", cfg, masks), masks, "path2")
 
 
 def token_learner(x: Tensor, sd, p: str) -> Tensor:
@@ -288,13 +307,13 @@ def token_upmix(xc: Tensor, sd, p: str) -> Tensor:
     return _ln(up, sd, p + ".norm")
 
 
-def wrapped_block(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool) -> Tensor:
+def wrapped_block(x: Tensor, sd, p: str, cfg: OracleConfig, bank: Bank, train: bool, masks: Optional[dict] = None) -> Tensor:
     """QuadBlockWithTokenLearner.forward (H:1104-1123)."""
     if cfg.use_token_learner:
         xc = token_learner(x, sd, p + ".token_learner")
-        xc = quad_block(xc, sd, p + ".quad_block", cfg, bank, train)
+        xc = quad_block(xc, sd, p + ".quad_block", cfg, bank, train, masks)
         return token_upmix(xc, sd, p + ".token_upmix")
-    return quad_block(x, sd, p + ".quad_block", cfg, bank, train)
+    return quad_block(x, sd, p + ".quad_block", cfg, bank, train, masks)
 
 
 def patch_embed(x: Tensor, sd, cfg: OracleConfig) -> Tensor:

@@ -21,7 +21,7 @@ class BlockCfg(C.Structure):
         ("n_dilations", C.c_int32), ("dilations", C.c_int32 * 4), ("pool_stride", C.c_int32),
         ("compress_dim", C.c_int32), ("bottleneck_hidden", C.c_int32), ("ffn_hidden", C.c_int32),
         ("ffn_v1", C.c_int32), ("dwconv_bias", C.c_int32), ("bank_v1", C.c_int32), ("train", C.c_int32),
-        ("dtype", C.c_int32),
+        ("dtype", C.c_int32), ("dropout", C.c_float), ("drop_path", C.c_float),
     ]
 
 
@@ -57,13 +57,15 @@ _SIGS = {
     "qavit_launch_count": (_ll, []),
     "qavit_block_param_name": (C.c_char_p, [_i, C.POINTER(_i)]),
     "qavit_block_workspace": (_i, [C.POINTER(BlockCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
-    "qavit_block_forward": (_i, [C.POINTER(BlockCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_block_forward": (_i, [C.POINTER(BlockCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_block_backward": (_i, [C.POINTER(BlockCfg), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_patch_embed_scratch_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "qavit_patch_embed_forward": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "qavit_patch_embed_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "qavit_head_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "qavit_head_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_dropout_forward": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp]),
+    "qavit_dropout_backward": (_i, [_vp, _vp, _ll, _f, _vp, _vp]),
     "qavit_cross_entropy": (_i, [_vp, _vp, _vp, _f, _i, _i, _f, _vp, _vp, _vp]),
     "qavit_clip_grads": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _ll, _vp]),
     "qavit_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp]),

@@ -106,6 +106,11 @@ __device__ void scores_softmax(const Lay& ly, float* sm, int n, float scale) {
   __syncthreads();
 }
 
+// dropout id of probability (query row r, head h, key j): unique within the site (NKV <= 128)
+__device__ __forceinline__ unsigned long long drop_id(const AttnP& p, long r, int h, int j) {
+  return ((unsigned long long)(r * p.H + h) << 7) | (unsigned)j;
+}
+
 template <typename T, int HD>
 __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnP p, Lay ly, int ntask) {
   extern __shared__ float sm[];
@@ -132,6 +137,14 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnP p, Lay ly, int ntask
       }
       __syncthreads();
       scores_softmax<HD>(ly, sm, n, scale);
+      if (p.drop.p > 0.f) {   // SDPA dropout_p: P <- P * keep / (1 - p), no renormalisation
+        const DropState ds = drop_state(p.drop);
+        for (int idx = tid; idx < n * ly.NKV; idx += NT) {
+          const int i = idx / ly.NKV, j = idx % ly.NKV;
+          P[i * ly.SP + j] *= drop_keep1(ds, drop_id(p, rows[q0 + i], h, j));
+        }
+        __syncthreads();
+      }
       for (int idx = tid; idx < n * HD; idx += NT) {
         const int i = idx / HD, d = idx % HD;
         float a = 0.f;
@@ -181,17 +194,25 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask
       __syncthreads();
       scores_softmax<HD>(ly, sm, n, scale);
       // dS = P * (dO Vf^T - rowsum(P * dO Vf^T)) * scale : one warp per query row
+      const bool drop = p.drop.p > 0.f;
+      DropState dst{};
+      if (drop) dst = drop_state(p.drop);
       for (int i = warp; i < n; i += NW) {
         float s = 0.f;
         for (int j = lane; j < NKV; j += 32) {
           float a = 0.f;
 #pragma unroll
           for (int d = 0; d < HD; ++d) a = fmaf(dO[i * HDP + d], Vf[j * HDP + d], a);
+          if (drop) a *= drop_keep1(dst, drop_id(p, rows[q0 + i], h, j));   // d(P_dropped) -> dP
           dS[i * SP + j] = a;
           s = fmaf(a, P[i * SP + j], s);
         }
         s = warp_sum(s);
-        for (int j = lane; j < NKV; j += 32) dS[i * SP + j] = P[i * SP + j] * (dS[i * SP + j] - s) * scale;
+        for (int j = lane; j < NKV; j += 32) {
+          const float pv = P[i * SP + j];
+          dS[i * SP + j] = pv * (dS[i * SP + j] - s) * scale;
+          if (drop) P[i * SP + j] = pv * drop_keep1(dst, drop_id(p, rows[q0 + i], h, j));   // dVf below needs the dropped P
+        }
       }
       __syncthreads();
       // dQ = dS Kf ; dVf += P^T dO ; dKf += dS^T Q

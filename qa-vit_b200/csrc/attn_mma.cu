@@ -238,6 +238,10 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mma_fwd_kernel(AttnP p, int n
     stage_task<NKV, LINF>(p, W, Es, w, h, lane, my_q, my_kv);
     float s[NKV / 8][4], o[HD / 8][4];
     scores_softmax<NKV>(s, W + WarpSmem::Q, W + WarpSmem::KF, scale, lane);
+    if (p.drop.p > 0.f) {   // SDPA dropout_p on the probabilities
+      const DropState ds = drop_state(p.drop);
+      drop_apply_c<NKV / 8>(s, drop_bits_c<NKV / 8>(ds, (uint32_t)task, lane), ds.inv);
+    }
     regA_times_Bt<NKV>(o, s, W + WarpSmem::VF, lane);
     store_rows(out, p.ldo, h * HD, my_q, o, lane);
     __syncwarp();
@@ -371,6 +375,14 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int n
         mma16816(dS[2 * np + 1], a, b[2], b[3]);
       }
     }
+    unsigned long long keep = ~0ull;
+    float kinv = 1.f;
+    if (p.drop.p > 0.f) {   // dP <- d(P_dropped) * keep; P_dropped (for dVf) is formed after the softmax backward
+      const DropState ds = drop_state(p.drop);
+      keep = drop_bits_c<NT>(ds, (uint32_t)task, lane);
+      kinv = ds.inv;
+      drop_apply_c<NT>(dS, keep, kinv);
+    }
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
     for (int n = 0; n < NT; ++n) { r0 += dS[n][0] * P[n][0] + dS[n][1] * P[n][1]; r1 += dS[n][2] * P[n][2] + dS[n][3] * P[n][3]; }
@@ -380,6 +392,10 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int n
     for (int n = 0; n < NT; ++n) {
       dS[n][0] = P[n][0] * (dS[n][0] - r0) * scale; dS[n][1] = P[n][1] * (dS[n][1] - r0) * scale;
       dS[n][2] = P[n][2] * (dS[n][2] - r1) * scale; dS[n][3] = P[n][3] * (dS[n][3] - r1) * scale;
+    }
+    if (p.drop.p > 0.f) drop_apply_c<NT>(P, keep, kinv);
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
       stC(W + WarpSmem::P, PT, 0, n * 8, P[n], lane);
       stC(W + WarpSmem::DS, PT, 0, n * 8, dS[n], lane);
     }

@@ -273,6 +273,10 @@ __global__ void __launch_bounds__(WARPS * 32) msda64_fwd_kernel(AttnP p, const b
       __syncwarp();
       float s[NKV / 8][4], o[HD / 8][4];
       scores_softmax(s, W + WS::Q, W + WS::KF, scale, lane);
+      if (p.drop.p > 0.f) {   // SDPA dropout_p on the probabilities
+        const DropState ds = drop_state(p.drop);
+        drop_apply_c<NKV / 8>(s, drop_bits_c<NKV / 8>(ds, (uint32_t)(task * tiles + qt), lane), ds.inv);
+      }
       regA_times_Bt(o, s, W + WS::VF, lane);
       store16(out + row0 * p.ldo + h * HD, p.ldo, o, lane);
     }
@@ -362,6 +366,14 @@ __global__ void __launch_bounds__(WARPS * 32) msda64_bwd_kernel(AttnP p, const b
           mma16816(dS[2 * np + 1], a, b[2], b[3]);
         }
       }
+      unsigned long long keep = ~0ull;
+      float kinv = 1.f;
+      if (p.drop.p > 0.f) {   // dP <- d(P_dropped) * keep; P_dropped (for dVf) is formed after the softmax backward
+        const DropState ds = drop_state(p.drop);
+        keep = drop_bits_c<NT>(ds, (uint32_t)(task * tiles + qt), lane);
+        kinv = ds.inv;
+        drop_apply_c<NT>(dS, keep, kinv);
+      }
       float r0 = 0.f, r1 = 0.f;
 #pragma unroll
       for (int n = 0; n < NT; ++n) { r0 += dS[n][0] * P[n][0] + dS[n][1] * P[n][1]; r1 += dS[n][2] * P[n][2] + dS[n][3] * P[n][3]; }
@@ -371,6 +383,10 @@ __global__ void __launch_bounds__(WARPS * 32) msda64_bwd_kernel(AttnP p, const b
       for (int n = 0; n < NT; ++n) {
         dS[n][0] = P[n][0] * (dS[n][0] - r0) * scale; dS[n][1] = P[n][1] * (dS[n][1] - r0) * scale;
         dS[n][2] = P[n][2] * (dS[n][2] - r1) * scale; dS[n][3] = P[n][3] * (dS[n][3] - r1) * scale;
+      }
+      if (p.drop.p > 0.f) drop_apply_c<NT>(P, keep, kinv);
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
         stC(W + WS::P, PT, 0, n * 8, P[n], lane);
         stC(W + WS::DS, PT, 0, n * 8, dS[n], lane);
       }

@@ -110,7 +110,7 @@ enum { W_SWA_QKV, W_SWA_PROJ, W_MSDA_Q, W_MSDA_KV, W_MSDA_PROJ, W_CGA_PROJ, W_CR
 struct Saved {  // byte offsets into `saved`
   size_t tl_stats, tl_ln, tl_S, xc, n1_stats, xn, alpha, snap[4], qkv_swa, attn_swa, xp, kv_msda, q_msda, attn_msda,
       attn_cga, kbp, vbp, q_cross, Kc, Vc, attn_cross, branch[4], nb_stats[4], nb[4], fused, h1_pre, h1, x1, n2_stats, y,
-      h_pre, h, dn_stats, hn, cs, pd_stats, hn2, o, out_blk, up, up_stats, wb[W_COUNT], wbt[W_COUNT], wstack, bstack, total;
+      h_pre, h, dn_stats, hn, cs, pd_stats, hn2, o, out_blk, up, up_stats, wb[W_COUNT], wbt[W_COUNT], wstack, bstack, rng, rs, total;
 };
 struct Scratch {  // byte offsets into `scratch`
   size_t tl_logits, tn, cgbuf, partial, attn_ws_f, total_fwd;
@@ -220,6 +220,8 @@ void layout_saved(const Dims& D, Saved* S) {
   }
   S->wstack = b.take((size_t)(d + D.kb) * d * 4);
   S->bstack = b.take((size_t)(d + D.kb) * 4);
+  S->rng = b.take(16);                          // Philox {seed, offset} snapshot of this forward call
+  S->rs = b.take((size_t)2 * D.B * 4);          // DropPath keep scales of the two residual branches
   S->total = b.off;
 }
 
@@ -376,6 +378,35 @@ AttnP attn_params(const Ctx& c, int mode) {
   return p;
 }
 
+// dropout sites of one block call (each call has its own rng snapshot, so ids only need to differ within a block)
+enum { DS_ATT = 1 /* +branch */, DS_PROJ = 5 /* +branch */, DS_B1 = 9, DS_B2 = 10, DS_FFN = 11, DS_PATH = 12 };
+
+struct DropCfg {
+  bool drop = false, path = false;
+  float p = 0.f, p_path = 0.f;
+  const unsigned long long* snap = nullptr;
+  const float *rs1 = nullptr, *rs2 = nullptr;
+  DropP site(uint32_t id) const {   // an nn.Dropout(config.dropout) / SDPA dropout_p site; inactive when !drop
+    DropP d;
+    if (drop) { d.p = p; d.rng = snap; d.site = id; }
+    return d;
+  }
+};
+int make_dropcfg(const Ctx& c, const qavit_block_cfg& cfg, DropCfg* dc) {
+  const bool train = cfg.train != 0;
+  QV_CHECK(cfg.dropout >= 0.f && cfg.dropout < 1.f && cfg.drop_path >= 0.f && cfg.drop_path < 1.f, "dropout=%f / drop_path=%f out of [0, 1)",
+           cfg.dropout, cfg.drop_path);
+  dc->drop = train && cfg.dropout > 0.f;
+  dc->path = train && cfg.drop_path > 0.f;
+  dc->p = cfg.dropout; dc->p_path = cfg.drop_path;
+  dc->snap = static_cast<const unsigned long long*>(c.sv(c.S.rng));
+  if (dc->path) { dc->rs1 = c.svf(c.S.rs); dc->rs2 = c.svf(c.S.rs) + c.D.B; }
+  return 0;
+}
+int drop_inplace(const Ctx& c, const DropCfg& dc, void* x, int C, uint32_t id, const float* rowscale) {
+  return drop_rows(c.st, c.D.dt, x, C, c.D.R, C, dc.site(id), rowscale, c.D.Nt, nullptr, 0, nullptr, nullptr, 0);
+}
+
 }  // namespace
 
 extern "C" int qavit_block_workspace(const qavit_block_cfg* cfg, size_t* saved_bytes, size_t* scratch_bytes) {
@@ -395,7 +426,8 @@ extern "C" int qavit_block_workspace(const qavit_block_cfg* cfg, size_t* saved_b
 // forward
 // =====================================================================================================
 extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const* params, long long* update_count,
-                                   const float* x_in, float* out, void* saved, void* scratch, void* stream) {
+                                   unsigned long long* rng, const float* x_in, float* out, void* saved, void* scratch,
+                                   void* stream) {
   Ctx c;
   QV_TRY(init_ctx(&c, cfg, params, saved, scratch, stream));
   const Dims& D = c.D;
@@ -404,6 +436,16 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   cudaStream_t st = c.st;
   const bool train = cfg->train != 0;
   QV_CHECK(!train || cfg->bank_v1 || update_count, "train mode needs update_count");
+  DropCfg dc;
+  QV_TRY(make_dropcfg(c, *cfg, &dc));
+  if (dc.drop || dc.path) {
+    QV_CHECK(rng, "train-mode dropout / DropPath needs the rng state {seed, offset}");
+    QV_TRY(rng_snapshot_advance(st, rng, static_cast<unsigned long long*>(c.sv(S.rng))));
+    if (dc.path) {
+      DropP d; d.p = dc.p_path; d.rng = dc.snap; d.site = DS_PATH;
+      QV_TRY(droppath_scales(st, d, D.B, c.svf(S.rs), c.svf(S.rs) + D.B));
+    }
+  }
 
   // ---- stacked write weight [write_compression ; write_gate] and the bf16 weight copies (one batched launch)
   if (train) {
@@ -457,9 +499,11 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.Ek = c.pf(QP_SWA_EK); p.Ev = c.pf(QP_SWA_EV);
     p.bank_k = snap_k(c, 0); p.bank_v = snap_v(c, 0);
     p.out = c.sv(S.attn_swa); p.ldo = d;
+    p.drop = dc.site(DS_ATT + 0);
     QV_TRY(attn_fwd(st, dt, p));
   }
   QV_TRY(gemm_nt(st, dt, c.sv(S.attn_swa), d, R, c.W(W_SWA_PROJ, c.pf(QP_SWA_PROJ_W)), epi_t(c, c.pf(QP_SWA_PROJ_B), c.sv(S.branch[0]), d)));
+  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[0]), d, DS_PROJ + 0, nullptr));   // H:465, before the bank write
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[0]), QP_SWA_NORM_W, QP_SWA_NORM_B, update_count));
 
   // ---- MSDA (H:496-532)
@@ -476,9 +520,11 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.bank_k = snap_k(c, 1); p.bank_v = snap_v(c, 1);
     p.out = c.sv(S.attn_msda); p.ldo = d;
     if (dt == QV_BF16 && D.Nt > 16) p.wsp = c.sc(c.X.attn_ws_f);
+    p.drop = dc.site(DS_ATT + 1);
     QV_TRY(attn_fwd(st, dt, p));
   }
   QV_TRY(gemm_nt(st, dt, c.sv(S.attn_msda), d, R, c.W(W_MSDA_PROJ, c.pf(QP_MSDA_PROJ_W)), epi_t(c, c.pf(QP_MSDA_PROJ_B), c.sv(S.branch[1]), d)));
+  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[1]), d, DS_PROJ + 1, nullptr));   // H:529
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[1]), QP_MSDA_NORM_W, QP_MSDA_NORM_B, update_count));
 
   // ---- CGA (H:559-595)
@@ -493,9 +539,11 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.Wv = c.pf(QP_CGA_V_W); p.bv = c.pf(QP_CGA_V_B);
     p.kbp = c.svf(S.kbp); p.vbp = c.svf(S.vbp);
     p.out = c.sv(S.attn_cga); p.ldo = d / 2;
+    p.drop = dc.site(DS_ATT + 2);
     QV_TRY(cga_fwd(st, dt, p));
   }
   QV_TRY(gemm_nt(st, dt, c.sv(S.attn_cga), d / 2, R, c.W(W_CGA_PROJ, c.pf(QP_CGA_PROJ_W)), epi_t(c, c.pf(QP_CGA_PROJ_B), c.sv(S.branch[2]), d)));
+  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[2]), d, DS_PROJ + 2, nullptr));   // H:592
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[2]), QP_CGA_NORM_W, QP_CGA_NORM_B, update_count));
 
   // ---- Cross (H:613-626)
@@ -508,9 +556,11 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.q = c.sv(S.q_cross); p.ldq = d; p.qcol = 0;
     p.kc = c.svf(S.Kc); p.vc = c.svf(S.Vc);
     p.out = c.sv(S.attn_cross); p.ldo = d;
+    p.drop = dc.site(DS_ATT + 3);
     QV_TRY(attn_fwd(st, dt, p));
   }
   QV_TRY(gemm_nt(st, dt, c.sv(S.attn_cross), d, R, c.W(W_CROSS_PROJ, c.pf(QP_CROSS_PROJ_W)), epi_t(c, c.pf(QP_CROSS_PROJ_B), c.sv(S.branch[3]), d)));
+  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[3]), d, DS_PROJ + 3, nullptr));   // H:625
 
   // ---- per-branch LN -> compress -> fusion scale + concat (H:1074-1079)
   static const int kNormW[4] = {QP_NSWA_W, QP_NMSDA_W, QP_NCGA_W, QP_NCROSS_W};
@@ -527,9 +577,16 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     GemmEpi e = epi_t(c, c.pf(QP_BMLP_FC1_B), c.sv(S.h1_pre), D.bh);
     e.gelu = 1; e.C2 = c.sv(S.h1); e.ldc2 = D.bh; e.c2_f32 = dt == QV_F32;
     QV_TRY(gemm_nt(st, dt, c.sv(S.fused), d, R, c.W(W_B1, c.pf(QP_BMLP_FC1_W)), e));
-    GemmEpi e2;
-    e2.bias = c.pf(QP_BMLP_FC2_B); e2.resid = x; e2.ldr = d; e2.C2 = c.sv(S.x1); e2.ldc2 = d; e2.c2_f32 = 1;
-    QV_TRY(gemm_nt(st, dt, c.sv(S.h1), D.bh, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), e2));
+    if (!dc.drop && !dc.path) {
+      GemmEpi e2;
+      e2.bias = c.pf(QP_BMLP_FC2_B); e2.resid = x; e2.ldr = d; e2.C2 = c.sv(S.x1); e2.ldc2 = d; e2.c2_f32 = 1;
+      QV_TRY(gemm_nt(st, dt, c.sv(S.h1), D.bh, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), e2));
+    } else {   // x1 = x + drop_path1(dropout(fc2(dropout(gelu(fc1)))))   (H:654-656, 1082)
+      if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.h1), D.bh, DS_B1, nullptr));
+      void* tmp = c.sc(c.X.tn);   // free since the last bank write
+      QV_TRY(gemm_nt(st, dt, c.sv(S.h1), D.bh, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), epi_t(c, c.pf(QP_BMLP_FC2_B), tmp, d)));
+      QV_TRY(drop_rows(st, dt, tmp, d, R, d, dc.site(DS_B2), dc.rs1, D.Nt, x, d, nullptr, c.svf(S.x1), d));
+    }
   }
   // ---- norm2 + CCF-FFN + residual (H:700-712, 1083)
   float* blk_out = D.tl ? c.svf(S.out_blk) : out;
@@ -543,16 +600,26 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     QV_TRY(ln_fwd(st, dt, c.sv(S.cs), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.pf(QP_FFN_PDN_B), 1e-5f, 0, nullptr, nullptr, dt,
                   c.sv(S.hn2), D.fh, c.svf(S.pd_stats)));
     GemmEpi e = epi_t(c, c.pf(QP_FFN_FC2_B), c.sv(S.o), d);
-    e.resid = c.svf(S.x1); e.ldr = d; e.scale_res = c.pf(QP_FFN_GAMMA); e.C2 = blk_out; e.ldc2 = d; e.c2_f32 = 1;
-    QV_TRY(gemm_nt(st, dt, c.sv(S.hn2), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e));
+    if (!dc.drop && !dc.path) {
+      e.resid = c.svf(S.x1); e.ldr = d; e.scale_res = c.pf(QP_FFN_GAMMA); e.C2 = blk_out; e.ldc2 = d; e.c2_f32 = 1;
+      QV_TRY(gemm_nt(st, dt, c.sv(S.hn2), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e));
+    } else {   // out = x1 + drop_path2(gamma * dropout(fc2))   (H:710-712, 1083); `o` keeps the dropped, path-scaled value
+      QV_TRY(gemm_nt(st, dt, c.sv(S.hn2), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e));
+      QV_TRY(drop_rows(st, dt, c.sv(S.o), d, R, d, dc.site(DS_FFN), dc.rs2, D.Nt, c.svf(S.x1), d, c.pf(QP_FFN_GAMMA), blk_out, d));
+    }
   } else {
     GemmEpi e = epi_t(c, c.pf(QP_FFN_FC1_B), c.sv(S.h_pre), D.fh);
     e.gelu = 1; e.C2 = c.sv(S.h); e.ldc2 = D.fh; e.c2_f32 = dt == QV_F32;
     QV_TRY(gemm_nt(st, dt, c.sv(S.y), d, R, c.W(W_F1, c.pf(QP_FFN_FC1_W)), e));
     QV_TRY(dwconv_fwd(st, dt, c.sv(S.h), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W), cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, nullptr, c.sv(S.cs)));
-    GemmEpi e2;
-    e2.bias = c.pf(QP_FFN_FC2_B); e2.resid = c.svf(S.x1); e2.ldr = d; e2.C2 = blk_out; e2.ldc2 = d; e2.c2_f32 = 1;
-    QV_TRY(gemm_nt(st, dt, c.sv(S.cs), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e2));
+    if (!dc.drop && !dc.path) {
+      GemmEpi e2;
+      e2.bias = c.pf(QP_FFN_FC2_B); e2.resid = c.svf(S.x1); e2.ldr = d; e2.C2 = blk_out; e2.ldc2 = d; e2.c2_f32 = 1;
+      QV_TRY(gemm_nt(st, dt, c.sv(S.cs), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e2));
+    } else {   // QAViT.py:580-582: out = x1 + drop_path2(dropout(fc2))
+      QV_TRY(gemm_nt(st, dt, c.sv(S.cs), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, c.pf(QP_FFN_FC2_B), c.sv(S.o), d)));
+      QV_TRY(drop_rows(st, dt, c.sv(S.o), d, R, d, dc.site(DS_FFN), dc.rs2, D.Nt, c.svf(S.x1), d, nullptr, blk_out, d));
+    }
   }
   // ---- TokenUpMix (H:1016-1031)
   if (D.tl) {
@@ -577,6 +644,8 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
   const int dt = D.dt, d = D.d, R = D.R;
   cudaStream_t st = c.st;
   auto G = [&](int i) { return grads[i]; };
+  DropCfg dc;
+  QV_TRY(make_dropcfg(c, *cfg, &dc));
   const float* x = D.tl ? c.svf(S.xc) : x_in;
   const float* blk_out = D.tl ? c.svf(S.out_blk) : nullptr;
   (void)blk_out;
@@ -597,6 +666,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
   // ---- CCF-FFN backward
   if (!D.v1) {
     QV_TRY(gamma_bwd(st, dt, dblk, c.sv(S.o), (long)R * d, c.pf(QP_FFN_GAMMA), c.sc(X.d_o), G(QP_FFN_GAMMA)));
+    if (dc.drop || dc.path) QV_TRY(drop_inplace(c, dc, c.sc(X.d_o), d, DS_FFN, dc.rs2));
     QV_TRY(gemm_tn(st, dt, c.sc(X.d_o), d, c.sv(S.hn2), D.fh, R, d, D.fh, G(QP_FFN_FC2_W), G(QP_FFN_FC2_B), nullptr));
     QV_TRY(gemm_nn(st, dt, c.sc(X.d_o), d, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, nullptr, c.sc(X.d_hn2), D.fh)));
     QV_TRY(ln_bwd(st, dt, c.sv(S.cs), D.fh, dt, c.sc(X.d_hn2), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.svf(S.pd_stats), 0, dt,
@@ -608,6 +678,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
                   c.sc(X.d_hpre), nullptr, nullptr, G(QP_FFN_DWN_W), G(QP_FFN_DWN_B)));
   } else {
     QV_TRY(cast_f32_to_t(st, dt, dblk, (long)R * d, c.sc(X.d_o)));
+    if (dc.drop || dc.path) QV_TRY(drop_inplace(c, dc, c.sc(X.d_o), d, DS_FFN, dc.rs2));
     QV_TRY(gemm_tn(st, dt, c.sc(X.d_o), d, c.sv(S.cs), D.fh, R, d, D.fh, G(QP_FFN_FC2_W), G(QP_FFN_FC2_B), nullptr));
     QV_TRY(gemm_nn(st, dt, c.sc(X.d_o), d, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, nullptr, c.sc(X.d_cs), D.fh)));
     QV_TRY(dwconv_bwd(st, dt, c.sv(S.h), c.sc(X.d_cs), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W),
@@ -622,8 +693,10 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
                 c.scf(X.d_x1), dblk, G(QP_NORM2_W), G(QP_NORM2_B)));
 
   // ---- BottleneckMLP backward
+  if (dc.drop || dc.path) QV_TRY(drop_inplace(c, dc, c.sc(X.d_x1t), d, DS_B2, dc.rs1));   // only the bottleneck reads d_x1t
   QV_TRY(gemm_tn(st, dt, c.sc(X.d_x1t), d, c.sv(S.h1), D.bh, R, d, D.bh, G(QP_BMLP_FC2_W), G(QP_BMLP_FC2_B), nullptr));
   QV_TRY(gemm_nn(st, dt, c.sc(X.d_x1t), d, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), epi_t(c, nullptr, c.sc(X.d_h1), D.bh)));
+  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sc(X.d_h1), D.bh, DS_B1, nullptr));
   QV_TRY(gelu_bwd(st, dt, c.sv(S.h1_pre), c.sc(X.d_h1), (long)R * D.bh, c.sc(X.d_h1pre)));
   QV_TRY(gemm_tn(st, dt, c.sc(X.d_h1pre), D.bh, c.sv(S.fused), d, R, D.bh, d, G(QP_BMLP_FC1_W), G(QP_BMLP_FC1_B), nullptr));
   QV_TRY(gemm_nn(st, dt, c.sc(X.d_h1pre), D.bh, R, c.W(W_B1, c.pf(QP_BMLP_FC1_W)), epi_t(c, nullptr, c.sc(X.d_fused), d)));
@@ -647,6 +720,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
     QV_TRY(gemm_nn(st, dt, dfs, d, R, c.W(W_C0 + i, c.pf(kCompW[i])), e));
     QV_TRY(ln_bwd(st, dt, c.sv(S.branch[i]), d, dt, c.sc(X.d_nb), d, R, d, c.pf(kNormW[i]), c.svf(S.nb_stats[i]), 0, dt,
                   c.sc(X.d_branch), nullptr, nullptr, G(kNormW[i]), G(kNormW[i] + 1)));
+    if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sc(X.d_branch), d, DS_PROJ + i, nullptr));
     const void* d_branch = c.sc(X.d_branch);
     if (i == 3) {  // ---- cross
       QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_cross), d, R, d, d, G(QP_CROSS_PROJ_W), G(QP_CROSS_PROJ_B), nullptr));
@@ -657,6 +731,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       p.dout = c.sc(X.d_attn); p.lddo = d;
       p.dq = c.sc(X.d_q); p.lddq = d; p.dqcol = 0;
       p.dbank_k = c.scf(X.dKc); p.dbank_v = c.scf(X.dVc);
+      p.drop = dc.site(DS_ATT + 3);
       QV_TRY(attn_bwd(st, dt, p));
       QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_CROSS_Q_W), G(QP_CROSS_Q_B), nullptr));
       QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), acc_xn));
@@ -676,6 +751,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       p.dWq = G(QP_CGA_Q_W); p.dbq = G(QP_CGA_Q_B); p.dWk = G(QP_CGA_K_W); p.dbk = G(QP_CGA_K_B);
       p.dWv = G(QP_CGA_V_W); p.dbv = G(QP_CGA_V_B);
       p.dkbp = c.scf(X.dkbp); p.dvbp = c.scf(X.dvbp);
+      p.drop = dc.site(DS_ATT + 2);
       QV_TRY(cga_bwd(st, dt, p));
       QV_TRY(small_linear_bwd(st, snap_k(c, 2), D.kb, d, c.pf(QP_CGA_BK_W), D.cpg, c.scf(X.dkbp), G(QP_CGA_BK_W), G(QP_CGA_BK_B), G(QP_BANK_K)));
       QV_TRY(small_linear_bwd(st, snap_v(c, 2), D.kb, d, c.pf(QP_CGA_BV_W), D.cpg, c.scf(X.dvbp), G(QP_CGA_BV_W), G(QP_CGA_BV_B), G(QP_BANK_V)));
@@ -692,6 +768,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       p.dkv = c.sc(X.d_kv); p.lddkv = 2 * d; p.dkcol = 0; p.dvcol = d;
       p.dEk = G(QP_MSDA_EK); p.dEv = G(QP_MSDA_EV); p.dbank_k = G(QP_BANK_K); p.dbank_v = G(QP_BANK_V);
       if (dt == QV_BF16 && D.Nt > 16) p.wsp = c.sc(X.attn_ws_b);
+      p.drop = dc.site(DS_ATT + 1);
       QV_TRY(attn_bwd(st, dt, p));
       QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_MSDA_QKV_W), G(QP_MSDA_QKV_B), nullptr));
       QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_MSDA_Q, c.pf(QP_MSDA_QKV_W)), acc_xn));
@@ -711,6 +788,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       p.dq = c.sc(X.d_qkv); p.lddq = 3 * d; p.dqcol = 0;
       p.dkv = c.sc(X.d_qkv); p.lddkv = 3 * d; p.dkcol = d; p.dvcol = 2 * d;
       p.dEk = G(QP_SWA_EK); p.dEv = G(QP_SWA_EV); p.dbank_k = G(QP_BANK_K); p.dbank_v = G(QP_BANK_V);
+      p.drop = dc.site(DS_ATT + 0);
       QV_TRY(attn_bwd(st, dt, p));
       QV_TRY(gemm_tn(st, dt, c.sc(X.d_qkv), 3 * d, c.sv(S.xn), d, R, 3 * d, d, G(QP_SWA_QKV_W), G(QP_SWA_QKV_B), nullptr));
       QV_TRY(gemm_nn(st, dt, c.sc(X.d_qkv), 3 * d, R, c.W(W_SWA_QKV, c.pf(QP_SWA_QKV_W)), acc_xn));
@@ -760,6 +838,24 @@ extern "C" int qavit_head_backward(const float* x, const float* dlogits, int B, 
                                    float* dpooled_scratch, float* dx, float* dln_w, float* dln_b, float* dW, float* dbias,
                                    void* stream) {
   return head_bwd((cudaStream_t)stream, x, dlogits, B, N, d, ln_w, stats, pooled, W, classes, dpooled_scratch, dx, dln_w, dln_b, dW, dbias);
+}
+// nn.Dropout on a contiguous fp32 tensor (pos_drop, H:1155 / 1251).  Forward snapshots {seed, offset} into snap and advances the
+// offset on the device; backward regenerates the mask from snap.
+extern "C" int qavit_dropout_forward(const float* x, float* y, long long n, float p, unsigned long long* rng,
+                                     unsigned long long* snap, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QV_CHECK(x && y && rng && snap && n % 8 == 0 && p >= 0.f && p < 1.f, "dropout_forward: bad argument (n %% 8 == 0, 0 <= p < 1)");
+  QV_TRY(rng_snapshot_advance(st, rng, snap));
+  if (y != x) QV_CUDA(cudaMemcpyAsync(y, x, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  DropP d; d.p = p; d.rng = snap; d.site = 0x9051u;
+  return drop_rows(st, QV_F32, y, 8, n / 8, 8, d, nullptr, 1, nullptr, 0, nullptr, nullptr, 0);
+}
+extern "C" int qavit_dropout_backward(const float* dy, float* dx, long long n, float p, const unsigned long long* snap, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  QV_CHECK(dy && dx && snap && n % 8 == 0, "dropout_backward: bad argument");
+  if (dx != dy) QV_CUDA(cudaMemcpyAsync(dx, dy, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  DropP d; d.p = p; d.rng = snap; d.site = 0x9051u;
+  return drop_rows(st, QV_F32, dx, 8, n / 8, 8, d, nullptr, 1, nullptr, 0, nullptr, nullptr, 0);
 }
 extern "C" int qavit_cross_entropy(const float* logits, const long long* ya, const long long* yb, float lam, int B,
                                    int classes, float label_smoothing, float* loss, float* dlogits, void* stream) {

@@ -90,6 +90,11 @@ __device__ void cga_load_weights(const CgaP& p, const CgaLay& ly, float* sm) {
   }
 }
 
+// dropout id of probability (token row r, group g, head h, key j): unique within the site (NKV <= 128, G * NH <= 32)
+__device__ __forceinline__ unsigned long long cga_drop_id(const CgaP& p, long r, int g, int h, int j) {
+  return ((unsigned long long)((r * p.G + g) * NH + h) << 7) | (unsigned)j;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(NT) cga_fwd_kernel(CgaP p, CgaLay ly) {
   extern __shared__ float sm[];
@@ -105,6 +110,15 @@ __global__ void __launch_bounds__(NT) cga_fwd_kernel(CgaP p, CgaLay ly) {
     for (int q0 = 0; q0 < p.Nt; q0 += ly.QC) {
       const int n = min(ly.QC, p.Nt - q0);
       cga_scores(p, ly, sm, q0, n);
+      if (p.drop.p > 0.f) {   // SDPA dropout_p on the probabilities
+        const DropState ds = drop_state(p.drop);
+        float* Pw = sm + ly.oP;
+        for (int idx = tid; idx < NH * n * ly.NKV; idx += NT) {
+          const int h = idx / (n * ly.NKV), r = idx % (n * ly.NKV), i = r / ly.NKV, j = r % ly.NKV;
+          Pw[(h * ly.QC + i) * ly.SP + j] *= drop_keep1(ds, cga_drop_id(p, (long)b * p.Nt + q0 + i, g, h, j));
+        }
+        __syncthreads();
+      }
       for (int idx = tid; idx < n * cpg; idx += NT) {
         const int i = idx / cpg, o = idx % cpg, h = o / hdc;
         float a = 0.f;
@@ -132,6 +146,9 @@ __global__ void __launch_bounds__(NT) cga_bwd_kernel(CgaP p, CgaLay ly) {
   const float* W = sm + ly.oW;
   float* dW = sm + ly.odW;
   const float scale = rsqrtf((float)hdc);
+  const bool drop = p.drop.p > 0.f;
+  DropState dst{};
+  if (drop) dst = drop_state(p.drop);
   for (int task = blockIdx.x; task < p.B * p.G; task += gridDim.x) {
     const int b = task / p.G, g = task % p.G;
     cga_project<T>(p, ly, sm, b, g);
@@ -147,6 +164,7 @@ __global__ void __launch_bounds__(NT) cga_bwd_kernel(CgaP p, CgaLay ly) {
         const int h = idx / (n * NKV), r = idx % (n * NKV), i = r / NKV, j = r % NKV;
         float a = 0.f;
         _Pragma("unroll") for (int d = 0; d < hdc; ++d) a = fmaf(dO[i * cpg + h * hdc + d], V[j * cpg + h * hdc + d], a);
+        if (drop) a *= drop_keep1(dst, cga_drop_id(p, (long)b * Nt + q0 + i, g, h, j));   // d(P_dropped) -> dP
         dS[(h * ly.QC + i) * SP + j] = a;
       }
       __syncthreads();
@@ -155,11 +173,15 @@ __global__ void __launch_bounds__(NT) cga_bwd_kernel(CgaP p, CgaLay ly) {
         for (int r = warp; r < NH * n; r += NT / 32) {
           const int h = r / n, i = r % n;
           float* ds = dS + (h * ly.QC + i) * SP;
-          const float* pr = P + (h * ly.QC + i) * SP;
+          float* pr = P + (h * ly.QC + i) * SP;
           float s = 0.f;
           for (int j = lane; j < NKV; j += 32) s += ds[j] * pr[j];
           s = warp_sum(s);
-          for (int j = lane; j < NKV; j += 32) ds[j] = pr[j] * (ds[j] - s) * scale;
+          for (int j = lane; j < NKV; j += 32) {
+            const float pv = pr[j];
+            ds[j] = pv * (ds[j] - s) * scale;
+            if (drop) pr[j] = pv * drop_keep1(dst, cga_drop_id(p, (long)b * Nt + q0 + i, g, h, j));   // dV below needs the dropped P
+          }
         }
       }
       __syncthreads();

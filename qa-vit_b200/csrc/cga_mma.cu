@@ -201,6 +201,10 @@ __global__ void __launch_bounds__(WARPS * 32) cga_mma_fwd_kernel(CgaP p) {
       for (int h = 0; h < NH; ++h) {
         float s[4][4], o2[2][4];
         head_scores(s, acc, W + WS::K, h, lane);
+        if (p.drop.p > 0.f) {   // SDPA dropout_p on the probabilities
+          const DropState ds = drop_state(p.drop);
+          drop_apply_c<4>(s, drop_bits_c<4>(ds, (uint32_t)((b * p.G + grp) * NH + h), lane), ds.inv);
+        }
         keys_times(o2, s, W + WS::V, lane);
         head_keep(o, o2, h, lane, false);
       }
@@ -277,6 +281,14 @@ __global__ void __launch_bounds__(WARPS * 32) cga_mma_bwd_kernel(CgaP p) {
           mma16816(dS[2 * np], a, bb[0], bb[1]);
           mma16816(dS[2 * np + 1], a, bb[2], bb[3]);
         }
+        unsigned long long keep = ~0ull;
+        float kinv = 1.f;
+        if (p.drop.p > 0.f) {   // dP <- d(P_dropped) * keep; P_dropped (for dv) is formed after the softmax backward
+          const DropState ds = drop_state(p.drop);
+          keep = drop_bits_c<4>(ds, (uint32_t)((b * p.G + grp) * NH + h), lane);
+          kinv = ds.inv;
+          drop_apply_c<4>(dS, keep, kinv);
+        }
         float r0 = 0.f, r1 = 0.f;
 #pragma unroll
         for (int n = 0; n < 4; ++n) { r0 += dS[n][0] * P[n][0] + dS[n][1] * P[n][1]; r1 += dS[n][2] * P[n][2] + dS[n][3] * P[n][3]; }
@@ -286,6 +298,10 @@ __global__ void __launch_bounds__(WARPS * 32) cga_mma_bwd_kernel(CgaP p) {
         for (int n = 0; n < 4; ++n) {
           dS[n][0] = P[n][0] * (dS[n][0] - r0) * 0.5f; dS[n][1] = P[n][1] * (dS[n][1] - r0) * 0.5f;
           dS[n][2] = P[n][2] * (dS[n][2] - r1) * 0.5f; dS[n][3] = P[n][3] * (dS[n][3] - r1) * 0.5f;
+        }
+        if (p.drop.p > 0.f) drop_apply_c<4>(P, keep, kinv);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
           stC(W + WS::P, PP, 0, n * 8, P[n], lane);
           stC(W + WS::DS, PP, 0, n * 8, dS[n], lane);
         }

@@ -207,6 +207,10 @@ __global__ void __launch_bounds__(WARPS * 32) cga64_fwd_kernel(CgaP p) {
         for (int h = 0; h < NH; ++h) {
           float s[L::NT8][4], o2[2][4];
           head_scores<L::NT8>(s, acc, SH + L::K, h, lane);
+          if (p.drop.p > 0.f) {   // SDPA dropout_p on the probabilities
+            const DropState ds = drop_state(p.drop);
+            drop_apply_c<L::NT8>(s, drop_bits_c<L::NT8>(ds, (uint32_t)(((b * T + tile) * p.G + grp) * NH + h), lane), ds.inv);
+          }
           keys_times<L::KS>(o2, s, SH + L::V, lane);
           head_keep(o, o2, h, lane, false);
         }
@@ -290,6 +294,14 @@ __global__ void __launch_bounds__(WARPS * 32) cga64_bwd_kernel(CgaP p) {
             mma16816(dS[2 * np], a, bb[0], bb[1]);
             mma16816(dS[2 * np + 1], a, bb[2], bb[3]);
           }
+          unsigned long long keep = ~0ull;
+          float kinv = 1.f;
+          if (p.drop.p > 0.f) {   // dP <- d(P_dropped) * keep; P_dropped (for dv) is formed after the softmax backward
+            const DropState ds = drop_state(p.drop);
+            keep = drop_bits_c<L::NT8>(ds, (uint32_t)(((b * T + warp) * p.G + grp) * NH + h), lane);
+            kinv = ds.inv;
+            drop_apply_c<L::NT8>(dS, keep, kinv);
+          }
           float r0 = 0.f, r1 = 0.f;
 #pragma unroll
           for (int n = 0; n < L::NT8; ++n) { r0 += dS[n][0] * P[n][0] + dS[n][1] * P[n][1]; r1 += dS[n][2] * P[n][2] + dS[n][3] * P[n][3]; }
@@ -299,6 +311,10 @@ __global__ void __launch_bounds__(WARPS * 32) cga64_bwd_kernel(CgaP p) {
           for (int n = 0; n < L::NT8; ++n) {
             dS[n][0] = P[n][0] * (dS[n][0] - r0) * 0.5f; dS[n][1] = P[n][1] * (dS[n][1] - r0) * 0.5f;
             dS[n][2] = P[n][2] * (dS[n][2] - r1) * 0.5f; dS[n][3] = P[n][3] * (dS[n][3] - r1) * 0.5f;
+          }
+          if (p.drop.p > 0.f) drop_apply_c<L::NT8>(P, keep, kinv);
+#pragma unroll
+          for (int n = 0; n < L::NT8; ++n) {
             stC(W + L::P, L::PP, 0, n * 8, P[n], lane);
             stC(W + L::DS, L::PP, 0, n * 8, dS[n], lane);
           }

@@ -141,6 +141,81 @@ __device__ __forceinline__ void store_vec(bf16* p, const float* v) {
   else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[EPL / 2 - 1]);
 }
 
+// ---------------------------------------------------------------- counter-based dropout masks
+// Philox4x32-10: 4 x 32 random bits for (key, counter); stateless, so forward and backward regenerate the same
+// dropout mask from (seed, offset, site, element id) instead of storing it.
+__device__ __forceinline__ uint4 philox4x32(uint2 key, uint4 ctr) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// A dropout site of the quad block (nn.Dropout / SDPA dropout_p / DropPath): p == 0 means inactive.  rng = device
+// {seed, offset} snapshot taken by the forward call; 16 random bits per element (p is quantised to 1/65536 and the
+// keep scale uses the quantised value, so the mask stays unbiased).
+struct DropP {
+  float p = 0.f;
+  const unsigned long long* rng = nullptr;
+  uint32_t site = 0;
+};
+struct DropState {
+  uint2 key;
+  uint32_t off_lo, off_hi, thr;
+  float inv;
+};
+__device__ __forceinline__ DropState drop_state(const DropP& d) {
+  DropState s;
+  const unsigned long long seed = d.rng[0], off = d.rng[1];
+  s.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ d.site);
+  s.off_lo = (uint32_t)off; s.off_hi = (uint32_t)(off >> 32);
+  s.thr = (uint32_t)(d.p * 65536.f + 0.5f);
+  s.inv = 65536.f / (65536.f - (float)s.thr);
+  return s;
+}
+// keep scale (0 or 1 / (1 - p)) of one element
+__device__ __forceinline__ float drop_keep1(const DropState& s, unsigned long long id) {
+  const uint4 r = philox4x32(s.key, make_uint4((uint32_t)id, (uint32_t)(id >> 32), s.off_lo, s.off_hi ^ 0x51u));
+  return (r.x & 0xFFFFu) >= s.thr ? s.inv : 0.f;
+}
+// keep scales of 8 consecutive elements; id8 = (index of the first element) / 8
+__device__ __forceinline__ void drop_keep8(const DropState& s, unsigned long long id8, float* sc) {
+  const uint4 r = philox4x32(s.key, make_uint4((uint32_t)id8, (uint32_t)(id8 >> 32), s.off_lo, s.off_hi ^ 0x58u));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sc[2 * i] = (w[i] & 0xFFFFu) >= s.thr ? s.inv : 0.f;
+    sc[2 * i + 1] = (w[i] >> 16) >= s.thr ? s.inv : 0.f;
+  }
+}
+// Keep bits of a [16 x 8 NT] tile held in mma C-fragment layout x[NT][4]: bit (4 n + e) <-> x[n][e].  `tile` is any id
+// unique per 16-row tile within the site; forward and backward of a kernel family use the same ids.
+template <int NT>
+__device__ __forceinline__ unsigned long long drop_bits_c(const DropState& s, uint32_t tile, int lane) {
+  unsigned long long bits = 0;
+#pragma unroll
+  for (int c = 0; c < (NT + 1) / 2; ++c) {
+    const uint4 r = philox4x32(s.key, make_uint4(tile, (uint32_t)(lane | (c << 5)), s.off_lo, s.off_hi ^ 0x5Cu));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((w[i] & 0xFFFFu) >= s.thr) bits |= 1ull << (8 * c + 2 * i);
+      if ((w[i] >> 16) >= s.thr) bits |= 1ull << (8 * c + 2 * i + 1);
+    }
+  }
+  return bits;
+}
+template <int NT>
+__device__ __forceinline__ void drop_apply_c(float (*x)[4], unsigned long long bits, float inv) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[n][e] *= ((bits >> (4 * n + e)) & 1ull) ? inv : 0.f;
+}
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 static inline int qv_num_sms() {
   static int n = 0;

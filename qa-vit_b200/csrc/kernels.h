@@ -119,6 +119,15 @@ int sf_pre_bwd(cudaStream_t s, int dt, const float* Tin, const float* R, const v
                const float* gamma, const float* stats, float* dT, float* dR, float* dgamma, float* dbeta);
 int rng_snapshot_advance(cudaStream_t s, unsigned long long* rng, unsigned long long* snap);
 
+// ---- dropout / DropPath of the quad block (drop.cu).  Masks come from (rng snapshot, site, element index): backward
+// calls the same function on the gradient.
+//   x[i, j] (T, in place) *= keep(i, j) * (rowscale ? rowscale[i / rows_per_img] : 1)
+//   out[i, j] (fp32, optional) = resid[i, j] + (scale ? *scale : 1) * x_new[i, j]
+int drop_rows(cudaStream_t s, int dt, void* x, int ldx, long rows, int C, const DropP& d, const float* rowscale, int rows_per_img,
+              const float* resid, int ldr, const float* scale, float* out, int ldo);
+// DropPath keep scales (H:256-264): rs[b] = floor(1 - p + u_b) / (1 - p) for the two residual branches of a block
+int droppath_scales(cudaStream_t s, const DropP& d, int B, float* rs1, float* rs2);
+
 // ---- norms
 int ln_fwd(cudaStream_t s, int dt_in, const void* x, int ldx, int rows, int C, const float* gamma, const float* beta,
            float eps, int gelu_in, const float* gamma2, const float* beta2, int dt_out, void* y, int ldy, float* stats);
@@ -143,6 +152,7 @@ struct AttnP {
   void* dkv; int lddkv; int dkcol, dvcol;    // T
   float* dEk; float* dEv; float* dbank_k; float* dbank_v;   // fp32 accumulators (mode 2: dKc/dVc in dbank_k/v)
   void* wsp;                                 // optional workspace (attn_msda64_scratch_bytes) for the hoisted Linformer path
+  DropP drop;                                // attention-probability dropout (SDPA dropout_p, H:461/525/621); p == 0: off
 };
 int attn_fwd(cudaStream_t s, int dt, const AttnP& p);
 bool attn_mma_ok(const AttnP& p);   // bf16 tensor-core (mma.sync) flavour for the 16-query shapes
@@ -164,6 +174,7 @@ struct CgaP {
   const void* dout; int lddo;                // T
   float* dxn; int lddx;                      // fp32 accumulate [B*Nt, G*cg]
   float *dWq, *dbq, *dWk, *dbk, *dWv, *dbv, *dkbp, *dvbp;
+  DropP drop;                                // attention-probability dropout (H:587); p == 0: off
 };
 int cga_fwd(cudaStream_t s, int dt, const CgaP& p);
 int cga_bwd(cudaStream_t s, int dt, const CgaP& p);

@@ -19,18 +19,6 @@ template <> struct Vec8<bf16> {
   static __device__ __forceinline__ void st(bf16* p, const float* v) { store_vec<8>(p, v); }
 };
 
-// Philox4x32-10 counter-based generator: 4 x 32 random bits for (key, counter); stateless, so forward and backward
-// regenerate the same dropout mask from (seed, offset, element index) instead of storing it.
-__device__ __forceinline__ uint4 philox4x32(uint2 key, uint4 ctr) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
 // keep-mask scale for 8 consecutive elements starting at element index e0 (multiple of 8): 1 / (1 - p) or 0
 __device__ __forceinline__ void dropout_scale8(const unsigned long long* rng, uint32_t site, unsigned long long e0, float p,
                                                float* sc) {

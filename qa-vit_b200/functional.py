@@ -114,7 +114,8 @@ class QuadBlockFn(torch.autograd.Function):
                 raise RuntimeError("qavit_b200: parameters must be contiguous fp32 tensors")
             params[qi] = t.data_ptr()
         out = torch.empty_like(x)
-        check(lib.qavit_block_forward(C.byref(cfg), params, _ptr(meta.update_count), x.data_ptr(), out.data_ptr(),
+        rng = rng_state(x.device) if (cfg.train and (cfg.dropout > 0 or cfg.drop_path > 0)) else None
+        check(lib.qavit_block_forward(C.byref(cfg), params, _ptr(meta.update_count), _ptr(rng), x.data_ptr(), out.data_ptr(),
                                       saved.data_ptr(), scratch.data_ptr(), _stream()))
         ctx.meta, ctx.saved_buf, ctx.x, ctx.params_arr = meta, saved, x, params
         ctx.tensors = tensors
@@ -391,6 +392,37 @@ def manual_seed(seed: int) -> None:
     """Re-seed the dropout generators of every device (offset back to 0)."""
     for dev, t in _rng_states.items():
         t.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
+
+
+class DropoutFn(torch.autograd.Function):
+    """``nn.Dropout`` on an fp32 tensor (pos_drop, HQAViT_CIFAR100.py:1155 / 1251) with the library's Philox stream."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, p: float):
+        _require_cuda(x, "dropout input")
+        x = x.float().contiguous()
+        if x.numel() % 8:
+            raise RuntimeError("qavit_b200: dropout needs a multiple of 8 elements")
+        y = torch.empty_like(x)
+        snap = torch.empty(2, dtype=torch.int64, device=x.device)
+        check(lib.qavit_dropout_forward(x.data_ptr(), y.data_ptr(), x.numel(), float(p), rng_state(x.device).data_ptr(),
+                                        snap.data_ptr(), _stream()))
+        ctx.snap, ctx.p = snap, float(p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        dy = dy.float().contiguous()
+        dx = torch.empty_like(dy)
+        check(lib.qavit_dropout_backward(dy.data_ptr(), dx.data_ptr(), dy.numel(), ctx.p, ctx.snap.data_ptr(), _stream()))
+        return dx, None
+
+
+def dropout(x: torch.Tensor, p: float, training: bool = True) -> torch.Tensor:
+    """Drop-in for ``F.dropout(x, p, training)`` on CUDA fp32 tensors (mask regenerated in backward, graph-capture safe)."""
+    if not training or p <= 0:
+        return x
+    return DropoutFn.apply(x, p)
 
 
 def _param_array(tensors, n):

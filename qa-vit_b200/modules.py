@@ -266,10 +266,6 @@ class QuadBlockWithTokenLearner(nn.Module):
 def _block_apply(block: QuadAttentionBlock, wrapper: Optional[QuadBlockWithTokenLearner], x: torch.Tensor):
     """Assemble the cfg struct + parameter table and run the native block (forward + autograd backward)."""
     cfg = block.config
-    if block.training and (cfg.dropout > 0 or block.drop_path_rate > 0):
-        raise NotImplementedError(
-            "qavit_b200: train-mode dropout / DropPath inside the quad block is not implemented yet -- construct the "
-            "model with dropout=0.0, drop_path=0.0 (the parity configuration, SURVEY.md 8c)")
     bank = block._bank_ref
     B, N, d = x.shape
     c = BlockCfg()
@@ -291,6 +287,10 @@ def _block_apply(block: QuadAttentionBlock, wrapper: Optional[QuadBlockWithToken
     c.bank_v1 = 1 if bank.v1 else 0
     c.train = 1 if block.training else 0
     c.dtype = QF.resolve_dtype(block.precision)
+    # every nn.Dropout of the block is built from config.dropout (H:416, 486, 556, 611, 1064, 1068); read the live module so
+    # that `.p` edits behave like the reference's
+    c.dropout = float(block.swa.dropout.p)
+    c.drop_path = float(block.drop_path_rate)
 
     tensors, index, no_grad = [], [], []
     for qi, (name, scope) in enumerate(PARAMS):
@@ -355,8 +355,8 @@ class _Base(nn.Module):
         return self
 
     def _stream_dropout(self, T):
-        p = self.config.dropout
-        return F.dropout(T, p, True) if (self.training and p > 0) else T
+        p = float(self.pos_drop.p)
+        return QF.dropout(T, p, True) if (self.training and p > 0) else T
 
 
 class QAViT(_Base):
