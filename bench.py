@@ -30,6 +30,8 @@ import torch  # noqa: E402
 METRIC = "train images/sec (HQAViT CIFAR-100 shape, fwd+bwd+clip+AdamW)"
 WORKLOAD = "HQAViT CIFAR-100 32x32 training step, bf16, synthetic batch"
 
+DEFAULT_DROPOUT, DEFAULT_DROP_PATH = 0.1, 0.1     # the reference defaults (H:56-57); --dropout 0 --drop-path 0 = the parity configuration
+
 # BASELINE.json configs: [1] is the default bench line; [2] / [3] / [4] are selectable for the record (profiles/).
 # fwd MFLOP / image = F_min of SURVEY.md 8d (blocks) + rest of the model.
 WORKLOADS = {
@@ -43,13 +45,14 @@ WORKLOADS = {
 }
 
 
-def build_workload(Q, name):
+def build_workload(Q, name, dropout=0.0, drop_path=0.0):
     w = WORKLOADS[name]
-    common = dict(img_size=w["img"], num_classes=w["classes"], dropout=0.0, drop_path=0.0, **w["kw"])
+    common = dict(img_size=w["img"], num_classes=w["classes"], dropout=dropout, drop_path=drop_path, **w["kw"])
     if w["family"] == "hqavit":
         model = Q.HQAViT(Q.HQAViTConfig(**common), **w["ctor"])
-        for n in ("fuse2", "fuse3", "fuse4"):
-            getattr(model, n).cat_mlp[3].p = 0.0
+        if dropout == 0.0:    # the parity configuration also silences SplitFusion's hard-coded Dropout(0.1) (H:930)
+            for n in ("fuse2", "fuse3", "fuse4"):
+                getattr(model, n).cat_mlp[3].p = 0.0
     else:
         model = Q.QAViT(Q.QAViTConfig(**common), **w["ctor"])
     return model, w
@@ -105,8 +108,9 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_step_rate(sample_b, steps, warmup, threads=None):
-    """The reference training step (CPU restatement, fp32, AdamW + clips) on `sample_b` images; images/sec."""
+def cpu_step_rate(sample_b, steps, warmup, threads=None, dropout=0.0, drop_path=0.0):
+    """The reference training step (CPU restatement, fp32, AdamW + clips) on `sample_b` images; images/sec.
+    dropout / drop_path > 0: Bernoulli masks drawn per step for every site, like the reference's nn.Dropout / SDPA."""
     from oracle import qavit_oracle as O
     if threads:
         torch.set_num_threads(threads)
@@ -118,9 +122,17 @@ def cpu_step_rate(sample_b, steps, warmup, threads=None):
     y = torch.randint(0, 100, (sample_b,), generator=g)
     state = {}
     ts = []
+    mask_fn = None
+    if dropout > 0 or drop_path > 0:
+        nblk = sum(ocfg.stage_depths)
+
+        def mask_fn(i, B, nt):
+            if i == "pos":
+                return (torch.rand(B, nt, ocfg.embed_dim) >= dropout).float() / (1.0 - dropout) if dropout > 0 else None
+            return O.random_masks(ocfg, B, nt, dropout, drop_path * i / max(1, nblk - 1))     # H:1187 linspace(0, drop_path, depth)
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        _, _, grads, new_state = O.loss_and_grads(sd, ocfg, x, y, label_smoothing=0.12)
+        _, _, grads, new_state = O.loss_and_grads(sd, ocfg, x, y, label_smoothing=0.12, mask_fn=mask_fn)
         sd.update(new_state)
         O.clip_grads_(grads)
         O.adamw_step_({k: sd[k] for k in keys}, grads, state, lr=6e-4, beta1=0.95, wd=0.06)
@@ -135,12 +147,13 @@ def run_reference(args):
     if rank != 0:
         return
     sample = 256
-    rate, dt, cores = cpu_step_rate(sample, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)))
+    rate, dt, cores = cpu_step_rate(sample, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)), dropout=args.dropout,
+                                    drop_path=args.drop_path)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
         "steps": max(1, min(args.steps, 8)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "note": "CPU path of the reference step (oracle port, "
+        "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "dropout": args.dropout, "drop_path": args.drop_path, "note": "CPU path of the reference step (oracle port, "
                    "pinned to the live reference's golden vectors); each step = a bounded sample of the workload"},
         "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                          "sample": f"{sample} images/step (of per-GPU batch {args.batch}), fp32, fwd+bwd+clip+AdamW"},
@@ -204,7 +217,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(42)
-    model, wl = build_workload(Q, args.workload)
+    Q.functional.manual_seed(42 + rank)     # dropout masks: independent per replica
+    model, wl = build_workload(Q, args.workload, args.dropout, args.drop_path)
     infer = args.mode == "infer"
     model = model.to(dev).set_precision("bf16")
     model = model.eval() if infer else model.train()
@@ -339,7 +353,7 @@ def run_ours(args):
         roof["step_frac_of_sustained_peak"] = roof["step_tflops_fmin"] / tf_sus
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.workload == "hqavit_c100" and not infer:
-            rate, dt, cores = cpu_step_rate(256, 8, 1)
+            rate, dt, cores = cpu_step_rate(256, 8, 1, dropout=args.dropout, drop_path=args.drop_path)
             cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                    "sample": f"256 images/step x 8 steps ({8 * dt:.1f} s of CPU work), fp32 oracle port, fwd+bwd+clip+AdamW"}
         default = args.workload == "hqavit_c100" and not infer
@@ -350,7 +364,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": workload, "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "dropout": 0.0, "drop_path": 0.0, "label_smoothing": 0.12, "optimizer": "AdamW+clip(0.1 per-param, 0.5 global)",
+                       "dropout": args.dropout, "drop_path": args.drop_path, "label_smoothing": 0.12, "optimizer": "AdamW+clip(0.1 per-param, 0.5 global)",
                        "l2": "working set (saved activations ~2.6 MB/image incl. the lateral path, x batch) >> 126 MB L2; no explicit flush",
                        "lateral_cnn_path": "native (qavit_lateral_* / qavit_splitfusion_*)",
                        "cuda_graph": graphed is not None},
@@ -375,6 +389,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="hqavit_c100", choices=sorted(WORKLOADS), help="default: BASELINE.json configs[1]")
     ap.add_argument("--mode", default="train", choices=["train", "infer"], help="infer: eval-mode forward throughput")
+    ap.add_argument("--dropout", type=float, default=DEFAULT_DROPOUT, help="config.dropout (reference default 0.1, H:56)")
+    ap.add_argument("--drop-path", type=float, default=DEFAULT_DROP_PATH, help="config.drop_path (reference default 0.1, H:57)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()

@@ -402,27 +402,73 @@ def split_fusion(T: Tensor, R: Tensor, sd, p: str) -> Tensor:
 
 
 # --------------------------------------------------------------------------- whole models
+def random_masks(cfg: OracleConfig, B: int, Nt: int, p: float, p_path: float,
+                 generator: Optional[torch.Generator] = None) -> Dict[str, Tensor]:
+    """Bernoulli keep-scale tensors (0 or 1/(1-p)) for every dropout / DropPath site of one
+    quad block, drawn the way nn.Dropout does (H:256-264, 416-465, 648-656, 697-710)."""
+    d, H, G, kb = cfg.embed_dim, cfg.num_heads, cfg.num_channel_groups, cfg.global_bank_size
+    w = cfg.window_size
+    nW = Nt // (w * w)
+    nkv = cfg.linformer_k + kb
+
+    def keep(shape, q):
+        return (torch.rand(shape, generator=generator) >= q).float() / (1.0 - q)
+
+    m: Dict[str, Tensor] = {}
+    if p > 0:
+        m["att_swa"] = keep((B * nW, H, w * w, nkv), p)
+        m["att_msda"] = keep((B, H, Nt, nkv), p)
+        m["att_cga"] = keep((B * G, H, Nt, Nt + kb), p)
+        m["att_cross"] = keep((B, H, Nt, kb), p)
+        for n in ("swa", "msda", "cga", "cross"):
+            m["proj_" + n] = keep((B, Nt, d), p)
+        m["b1"] = keep((B, Nt, d // cfg.bottleneck_ratio), p)
+        m["b2"] = keep((B, Nt, d), p)
+        m["ffn"] = keep((B, Nt, d), p)
+    if p_path > 0:
+        m["path1"] = keep((B, 1, 1), p_path)
+        m["path2"] = keep((B, 1, 1), p_path)
+    return m
+
+
 def forward(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, train: bool = False,
-            new_state: Optional[dict] = None) -> Tensor:
+            new_state: Optional[dict] = None, mask_fn=None) -> Tensor:
     """QAViT.forward (QAViT.py:689-699) / HQAViT.forward (H:1226-1277) -> logits[B, classes].
 
     ``new_state`` (train mode) receives the mutated non-autograd state: global_k/global_v,
-    update_count and BatchNorm running statistics."""
+    update_count and BatchNorm running statistics.  ``mask_fn(block_index, B, tokens)`` (train
+    mode, optional) returns the dropout masks of a block (see quad_block); ``mask_fn("pos", B, N)``
+    the keep-scale tensor of pos_drop (H:1251)."""
     bank = Bank(sd, cfg)
+    blk_no = [0]
+
+    def masks_for(T):
+        if mask_fn is None or not train:
+            return None
+        nt = cfg.num_learned_tokens if (cfg.family == "hqavit" and cfg.use_token_learner) else T.shape[1]
+        blk_no[0] += 1
+        return mask_fn(blk_no[0] - 1, T.shape[0], nt)
+
+    def pos_drop(T):
+        if mask_fn is None or not train:
+            return T
+        pm = mask_fn("pos", T.shape[0], T.shape[1])
+        return T if pm is None else T * pm
+
     if cfg.family == "hqavit":
         hw = cfg.img_size // cfg.patch_size
         f2, f3, f4 = cnn_stem(x, sd, train, new_state)
         R = [rrcv(lmfa(f, sd, f"lmfa{i}", hw), sd, f"rrcv{i}", cfg, hw) for i, f in ((2, f2), (3, f3), (4, f4))]
-        T = patch_embed(x, sd, cfg)
+        T = pos_drop(patch_embed(x, sd, cfg))
         for st, nblk in enumerate(cfg.stage_depths, start=1):
             if st >= 2:
                 T = split_fusion(T, R[st - 2], sd, f"fuse{st}")
             for i in range(nblk):
-                T = wrapped_block(T, sd, f"stage{st}_blocks.{i}", cfg, bank, train)
+                T = wrapped_block(T, sd, f"stage{st}_blocks.{i}", cfg, bank, train, masks_for(T))
     else:
-        T = patch_embed(x, sd, cfg)
+        T = pos_drop(patch_embed(x, sd, cfg))
         for i in range(cfg.depth):
-            T = quad_block(T, sd, f"blocks.{i}", cfg, bank, train)
+            T = quad_block(T, sd, f"blocks.{i}", cfg, bank, train, masks_for(T))
     T = _ln(T, sd, "norm").mean(1)
     logits = _lin(T, sd, "head")
     if new_state is not None and train:
@@ -684,13 +730,14 @@ def trainable_keys(cfg: OracleConfig):
 
 
 def loss_and_grads(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, y: Tensor, label_smoothing: float = 0.0,
-                   train: bool = True):
-    """One training forward+backward.  Returns (logits, loss, grads{key: tensor|None}, new_state)."""
+                   train: bool = True, mask_fn=None):
+    """One training forward+backward.  Returns (logits, loss, grads{key: tensor|None}, new_state).
+    ``mask_fn``: see forward()."""
     leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in trainable_keys(cfg)}
     full = dict(sd)
     full.update(leaves)
     new_state: dict = {}
-    logits = forward(full, cfg, x, train=train, new_state=new_state)
+    logits = forward(full, cfg, x, train=train, new_state=new_state, mask_fn=mask_fn)
     loss = cross_entropy(logits, y, label_smoothing)
     gl = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
     grads = {k: g for k, g in zip(leaves.keys(), gl)}

@@ -3,7 +3,8 @@
 The directory is named ``qa-vit_b200`` (not importable as such); ``import qavit_b200`` resolves here through the
 shim package at the repo root."""
 from ._lib import EXPORTS, LIB_PATH, lib  # noqa: F401  (raises ImportError when the CUDA extension is not built)
-from .functional import cross_entropy  # noqa: F401
+from . import functional  # noqa: F401
+from .functional import cross_entropy, dropout, manual_seed  # noqa: F401
 from .modules import (HQAViT, HQAViTConfig, PatchEmbed, QAViT, QAViTConfig, QuadAttentionBlock,  # noqa: F401
                       QuadBlockWithTokenLearner)
 from .optim import FusedAdamW, clip_grad_norms_  # noqa: F401

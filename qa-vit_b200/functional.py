@@ -376,20 +376,28 @@ def conv1x1(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------------ dropout RNG state
 _rng_states = {}
+_rng_seed = None        # set by manual_seed(); states created later start from it instead of torch.initial_seed()
 
 
 def rng_state(device) -> torch.Tensor:
     """Device-resident Philox state [seed, offset] (int64) behind every in-kernel dropout: forward calls snapshot it
     into their saved buffer and advance the offset on the device, so CUDA-graph replays draw fresh masks."""
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     t = _rng_states.get(device)
     if t is None:
-        t = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        seed = torch.initial_seed() if _rng_seed is None else _rng_seed
+        t = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
         _rng_states[device] = t
     return t
 
 
 def manual_seed(seed: int) -> None:
-    """Re-seed the dropout generators of every device (offset back to 0)."""
+    """Re-seed the dropout generators of every device (offset back to 0); data-parallel ranks should pass distinct
+    seeds (e.g. seed + rank) so that replicas draw independent masks."""
+    global _rng_seed
+    _rng_seed = int(seed)
     for dev, t in _rng_states.items():
         t.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
 

@@ -132,3 +132,84 @@ def test_oracle_equals_live_reference_in_fp64(case):
             assert grads[n] is None, n
         else:
             assert (grads[n] - p.grad).norm().item() <= 1e-10 * p.grad.norm().item() + 1e-12 * gmed, n
+
+
+# ----------------------------------------------------------------------------------------------- dropout placement
+@pytest.mark.skipif(not os.path.isdir(MG.REF), reason="live reference not mounted (GPU box)")
+@pytest.mark.parametrize("case,prefix,wrapped,ntok,nblk", [("qavitv2_c100", "blocks.3", False, 64, 64),
+                                                          ("hqavit_c100", "stage2_blocks.1", True, 64, 16)])
+def test_oracle_dropout_sites_match_live_reference(case, prefix, wrapped, ntok, nblk, monkeypatch):
+    """Pins WHERE the oracle applies dropout / DropPath (quad_block's `masks`) to the live reference block in train mode:
+    the reference's three random sources -- SDPA dropout_p, nn.Dropout, drop_path() -- are replaced by explicit masks
+    handed out in call order, the oracle gets the same masks by name, and in fp64 the two agree to rounding on the
+    output, dx, every parameter gradient and the bank state the (dropped) branch outputs are written into."""
+    mod_name, cls, cfg_cls, over, okw, _ = MG.CASES[case]
+    mod = MG.import_reference(mod_name)
+    mod.HAS_FLASH_ATTN = False
+    p, p_path = 0.1, 0.2
+    torch.manual_seed(3)
+    model = getattr(mod, cls)(getattr(mod, cfg_cls)(dropout=p, drop_path=p_path, **over))
+    cfg = O.OracleConfig(**okw)
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in O.synthetic_state(cfg).items()}
+    model.double()
+    model.load_state_dict(O.with_bank_aliases(sd, cfg), strict=True)
+    model.train()
+    blk = model.get_submodule(prefix)
+    B = 3
+    g = torch.Generator().manual_seed(5)
+    masks = {k: v.double() for k, v in O.random_masks(cfg, B, nblk, p, p_path, g).items()}
+    x = torch.randn(B, ntok, cfg.embed_dim, generator=g, dtype=torch.float64)
+    wgt = torch.randn(B, ntok, cfg.embed_dim, generator=g, dtype=torch.float64)
+
+    # proj_swa is applied by the reference BEFORE the window reverse (H:465-466): hand it over in window layout
+    s, w = int(nblk ** 0.5), cfg.window_size
+    pw = masks["proj_swa"].view(B, s // w, w, s // w, w, -1).permute(0, 1, 3, 2, 4, 5).reshape(-1, w * w, cfg.embed_dim)
+    q_att = [masks[k] for k in ("att_swa", "att_msda", "att_cga", "att_cross")]
+    q_drop = [pw, masks["proj_msda"], masks["proj_cga"], masks["proj_cross"], masks["b1"], masks["b2"], masks["ffn"]]
+    q_path = [masks["path1"], masks["path2"]]
+
+    def sdpa(q, k, v, dropout_p=0.0, **kw):
+        assert dropout_p == p
+        P = torch.softmax((q @ k.transpose(-1, -2)) / q.shape[-1] ** 0.5, -1)
+        return (P * q_att.pop(0)) @ v
+
+    def dropout_forward(self, t):
+        if not self.training or self.p == 0:
+            return t
+        assert self.p == p
+        return t * q_drop.pop(0)
+
+    def drop_path(t, drop_prob=0.0, training=False):
+        if drop_prob == 0.0 or not training:
+            return t
+        return t * q_path.pop(0)
+
+    monkeypatch.setattr(torch.nn.functional, "scaled_dot_product_attention", sdpa)
+    monkeypatch.setattr(torch.nn.Dropout, "forward", dropout_forward)
+    monkeypatch.setattr(mod, "drop_path", drop_path)
+    qb = blk.quad_block if wrapped else blk
+    assert 0 < qb.drop_path1.drop_prob < p_path + 1e-9           # H:1187: linspace(0, drop_path, depth)
+    xl = x.clone().requires_grad_(True)
+    out = blk(xl)
+    (out * wgt).sum().backward()
+    assert not q_att and not q_drop and not q_path               # every site was visited exactly once
+
+    keys = [k for k in O.trainable_keys(cfg) if k.startswith(prefix + ".") or k.startswith("global_bank.")]
+    leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in keys}
+    full = dict(sd)
+    full.update(leaves)
+    xo = x.clone().requires_grad_(True)
+    bank = O.Bank(full, cfg)
+    oo = (O.wrapped_block if wrapped else O.quad_block)(xo, full, prefix, cfg, bank, True, masks)
+    gs = torch.autograd.grad((oo * wgt).sum(), [xo] + list(leaves.values()), allow_unused=True)
+    assert (oo - out).abs().max() < 1e-11
+    assert (gs[0] - xl.grad).abs().max() < 1e-10 * xl.grad.abs().max()
+    named = dict(model.named_parameters())
+    for k, gr in zip(keys, gs[1:]):
+        if gr is None:
+            assert named[k].grad is None, k
+        else:
+            assert (gr - named[k].grad).norm() <= 1e-9 * named[k].grad.norm() + 1e-12, k
+    bk, bv = bank.read()
+    assert (bk - model.global_bank.global_k).abs().max() < 1e-13
+    assert (bv - model.global_bank.global_v).abs().max() < 1e-13
