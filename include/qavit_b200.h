@@ -137,6 +137,21 @@ int qavit_clip_grads(float* grads, const long long* seg_off, const int* seg_flag
 int qavit_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const long long* seg_off,
                      const int* seg_flags, int n_seg, const float* hyper /* device: lr, beta1, beta2, eps, wd, bc1, bc2 */,
                      long long total_elems, void* stream);
+/* Same step with ModelEMA.update (H:139-149) folded in: ema = d * ema + (1 - d) * p_new for every element of the flat
+ * buffer (also segments AdamW skips); d = hyper[7], 1 - d = hyper[8] (rounded from double like torch's alpha).  SURVEY 8(f)-2. */
+int qavit_adamw_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,
+                         const long long* seg_off, const int* seg_flags, int n_seg,
+                         const float* hyper /* device: lr, beta1, beta2, eps, wd, bc1, bc2, ema_decay, 1 - ema_decay */,
+                         long long total_elems, void* stream);
+/* norms[i] = L2 norm of segment i of a flat buffer (0 for segments whose flag bit0 is clear) -- the per-tensor gradient /
+ * parameter norms GradientMonitor.log_gradients collects (H:198-242) without its ~3 k host syncs. */
+int qavit_segment_norms(const float* buf, const long long* seg_off, const int* seg_flags, int n_seg, float* norms,
+                        void* stream);
+/* On-device CutMix (mode 1) / MixUp (mode 2: lam * img + lam_b * img[perm], lam_b = 1 - lam rounded from double like the
+ * torch expression) of img [B, C, H, W] fp32 against img[perm] (H:1379-1399); box = columns [x1, x2) x rows [y1, y2).
+ * out must not alias img.  SURVEY 8(f)-3. */
+int qavit_batch_mix(const float* img, float* out, const long long* perm, int B, int C, int H, int W, int mode, int x1, int y1,
+                    int x2, int y2, float lam, float lam_b, void* stream);
 
 /* nn.LayerNorm (eps configurable, C <= 256) for the modules around the blocks -- SplitFusion / LMFAdapter / RRCV /
  * ConvNeXtBlock norms (H:723, 816, 875, 922-939).  x fp32 or bf16 (x_bf16), y / dy fp32, dx in x's dtype,

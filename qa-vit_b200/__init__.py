@@ -4,12 +4,13 @@ The directory is named ``qa-vit_b200`` (not importable as such); ``import qavit_
 shim package at the repo root."""
 from ._lib import EXPORTS, LIB_PATH, lib  # noqa: F401  (raises ImportError when the CUDA extension is not built)
 from . import functional  # noqa: F401
-from .functional import cross_entropy, dropout, manual_seed  # noqa: F401
+from .functional import batch_mix, cross_entropy, dropout, manual_seed, mix_batch  # noqa: F401
 from .modules import (HQAViT, HQAViTConfig, PatchEmbed, QAViT, QAViTConfig, QuadAttentionBlock,  # noqa: F401
                       QuadBlockWithTokenLearner)
-from .optim import FusedAdamW, clip_grad_norms_  # noqa: F401
+from .optim import FusedAdamW, ModelEMA, clip_grad_norms_  # noqa: F401
 from .dp import GradAllReducer  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
+from .transfer import adjust_positional_embedding, load_pretrained_except_head  # noqa: F401
 
 __all__ = ["QAViT", "HQAViT", "QAViTConfig", "HQAViTConfig", "QuadAttentionBlock", "QuadBlockWithTokenLearner",
            "PatchEmbed", "cross_entropy", "FusedAdamW", "clip_grad_norms_", "GradAllReducer", "GraphedTrainStep"]

@@ -69,6 +69,9 @@ _SIGS = {
     "qavit_cross_entropy": (_i, [_vp, _vp, _vp, _f, _i, _i, _f, _vp, _vp, _vp]),
     "qavit_clip_grads": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _ll, _vp]),
     "qavit_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp]),
+    "qavit_adamw_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp]),
+    "qavit_segment_norms": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "qavit_batch_mix": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "qavit_layer_norm_forward": (_i, [_vp, _i, _ll, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "qavit_layer_norm_backward": (_i, [_vp, _i, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_dwconv_forward": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -403,6 +403,9 @@ int make_dropcfg(const Ctx& c, const qavit_block_cfg& cfg, DropCfg* dc) {
   if (dc->path) { dc->rs1 = c.svf(c.S.rs); dc->rs2 = c.svf(c.S.rs) + c.D.B; }
   return 0;
 }
+// the tcgen05 GEMM epilogue applies a dropout site itself; the fp32 SIMT flavour does not (a drop_rows pass follows it)
+bool fused_nt(const Ctx& c, const Weight& W, int M, int lda) { return c.D.dt == QV_BF16 && W.wb && tc_shape_ok_nt(M, W.N, W.K, lda); }
+bool fused_nn(const Ctx& c, const Weight& W, int M, int ldy) { return c.D.dt == QV_BF16 && W.wbt && tc_shape_ok_nt(M, W.K, W.N, ldy); }
 int drop_inplace(const Ctx& c, const DropCfg& dc, void* x, int C, uint32_t id, const float* rowscale) {
   return drop_rows(c.st, c.D.dt, x, C, c.D.R, C, dc.site(id), rowscale, c.D.Nt, nullptr, 0, nullptr, nullptr, 0);
 }
@@ -484,6 +487,16 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     x = c.svf(S.xc);
   }
 
+  // branch output projection + nn.Dropout (H:464-465): the dropout site rides in the tcgen05 epilogue when there is one
+  auto proj_gemm = [&](const void* A, int lda, const Weight& W, const float* bias, int i) -> int {
+    GemmEpi e = epi_t(c, bias, c.sv(S.branch[i]), d);
+    const bool fused = dc.drop && fused_nt(c, W, R, lda);
+    if (fused) e.drop = dc.site(DS_PROJ + i);
+    QV_TRY(gemm_nt(st, dt, A, lda, R, W, e));
+    if (dc.drop && !fused) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[i]), d, DS_PROJ + i, nullptr));
+    return 0;
+  };
+
   // ---- norm1, fusion weights
   void* xn = c.sv(S.xn);
   QV_TRY(ln_fwd(st, QV_F32, x, d, R, d, c.pf(QP_NORM1_W), c.pf(QP_NORM1_B), 1e-5f, 0, nullptr, nullptr, dt, xn, d, c.svf(S.n1_stats)));
@@ -502,8 +515,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.drop = dc.site(DS_ATT + 0);
     QV_TRY(attn_fwd(st, dt, p));
   }
-  QV_TRY(gemm_nt(st, dt, c.sv(S.attn_swa), d, R, c.W(W_SWA_PROJ, c.pf(QP_SWA_PROJ_W)), epi_t(c, c.pf(QP_SWA_PROJ_B), c.sv(S.branch[0]), d)));
-  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[0]), d, DS_PROJ + 0, nullptr));   // H:465, before the bank write
+  QV_TRY(proj_gemm(c.sv(S.attn_swa), d, c.W(W_SWA_PROJ, c.pf(QP_SWA_PROJ_W)), c.pf(QP_SWA_PROJ_B), 0));   // H:465, before the bank write
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[0]), QP_SWA_NORM_W, QP_SWA_NORM_B, update_count));
 
   // ---- MSDA (H:496-532)
@@ -523,8 +535,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.drop = dc.site(DS_ATT + 1);
     QV_TRY(attn_fwd(st, dt, p));
   }
-  QV_TRY(gemm_nt(st, dt, c.sv(S.attn_msda), d, R, c.W(W_MSDA_PROJ, c.pf(QP_MSDA_PROJ_W)), epi_t(c, c.pf(QP_MSDA_PROJ_B), c.sv(S.branch[1]), d)));
-  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[1]), d, DS_PROJ + 1, nullptr));   // H:529
+  QV_TRY(proj_gemm(c.sv(S.attn_msda), d, c.W(W_MSDA_PROJ, c.pf(QP_MSDA_PROJ_W)), c.pf(QP_MSDA_PROJ_B), 1));   // H:529
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[1]), QP_MSDA_NORM_W, QP_MSDA_NORM_B, update_count));
 
   // ---- CGA (H:559-595)
@@ -542,8 +553,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.drop = dc.site(DS_ATT + 2);
     QV_TRY(cga_fwd(st, dt, p));
   }
-  QV_TRY(gemm_nt(st, dt, c.sv(S.attn_cga), d / 2, R, c.W(W_CGA_PROJ, c.pf(QP_CGA_PROJ_W)), epi_t(c, c.pf(QP_CGA_PROJ_B), c.sv(S.branch[2]), d)));
-  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[2]), d, DS_PROJ + 2, nullptr));   // H:592
+  QV_TRY(proj_gemm(c.sv(S.attn_cga), d / 2, c.W(W_CGA_PROJ, c.pf(QP_CGA_PROJ_W)), c.pf(QP_CGA_PROJ_B), 2));   // H:592
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[2]), QP_CGA_NORM_W, QP_CGA_NORM_B, update_count));
 
   // ---- Cross (H:613-626)
@@ -559,8 +569,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     p.drop = dc.site(DS_ATT + 3);
     QV_TRY(attn_fwd(st, dt, p));
   }
-  QV_TRY(gemm_nt(st, dt, c.sv(S.attn_cross), d, R, c.W(W_CROSS_PROJ, c.pf(QP_CROSS_PROJ_W)), epi_t(c, c.pf(QP_CROSS_PROJ_B), c.sv(S.branch[3]), d)));
-  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.branch[3]), d, DS_PROJ + 3, nullptr));   // H:625
+  QV_TRY(proj_gemm(c.sv(S.attn_cross), d, c.W(W_CROSS_PROJ, c.pf(QP_CROSS_PROJ_W)), c.pf(QP_CROSS_PROJ_B), 3));   // H:625
 
   // ---- per-branch LN -> compress -> fusion scale + concat (H:1074-1079)
   static const int kNormW[4] = {QP_NSWA_W, QP_NMSDA_W, QP_NCGA_W, QP_NCROSS_W};
@@ -576,13 +585,17 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   {
     GemmEpi e = epi_t(c, c.pf(QP_BMLP_FC1_B), c.sv(S.h1_pre), D.bh);
     e.gelu = 1; e.C2 = c.sv(S.h1); e.ldc2 = D.bh; e.c2_f32 = dt == QV_F32;
-    QV_TRY(gemm_nt(st, dt, c.sv(S.fused), d, R, c.W(W_B1, c.pf(QP_BMLP_FC1_W)), e));
-    if (!dc.drop && !dc.path) {
+    const Weight wb1 = c.W(W_B1, c.pf(QP_BMLP_FC1_W)), wb2 = c.W(W_B2, c.pf(QP_BMLP_FC2_W));
+    const bool f1 = dc.drop && fused_nt(c, wb1, R, d), f2 = (dc.drop || dc.path) && fused_nt(c, wb2, R, D.bh);
+    if (f1) e.drop = dc.site(DS_B1);                        // dropout after the activation: C2 only
+    QV_TRY(gemm_nt(st, dt, c.sv(S.fused), d, R, wb1, e));
+    if (dc.drop && !f1) QV_TRY(drop_inplace(c, dc, c.sv(S.h1), D.bh, DS_B1, nullptr));
+    if ((!dc.drop && !dc.path) || f2) {   // x1 = x + drop_path1(dropout(fc2(h1)))   (H:654-656, 1082) in the GEMM epilogue
       GemmEpi e2;
       e2.bias = c.pf(QP_BMLP_FC2_B); e2.resid = x; e2.ldr = d; e2.C2 = c.sv(S.x1); e2.ldc2 = d; e2.c2_f32 = 1;
-      QV_TRY(gemm_nt(st, dt, c.sv(S.h1), D.bh, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), e2));
-    } else {   // x1 = x + drop_path1(dropout(fc2(dropout(gelu(fc1)))))   (H:654-656, 1082)
-      if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sv(S.h1), D.bh, DS_B1, nullptr));
+      if (f2) { e2.drop = dc.site(DS_B2); e2.rowscale = dc.rs1; e2.rows_per_img = D.Nt; }
+      QV_TRY(gemm_nt(st, dt, c.sv(S.h1), D.bh, R, wb2, e2));
+    } else {
       void* tmp = c.sc(c.X.tn);   // free since the last bank write
       QV_TRY(gemm_nt(st, dt, c.sv(S.h1), D.bh, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), epi_t(c, c.pf(QP_BMLP_FC2_B), tmp, d)));
       QV_TRY(drop_rows(st, dt, tmp, d, R, d, dc.site(DS_B2), dc.rs1, D.Nt, x, d, nullptr, c.svf(S.x1), d));
@@ -600,9 +613,12 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     QV_TRY(ln_fwd(st, dt, c.sv(S.cs), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.pf(QP_FFN_PDN_B), 1e-5f, 0, nullptr, nullptr, dt,
                   c.sv(S.hn2), D.fh, c.svf(S.pd_stats)));
     GemmEpi e = epi_t(c, c.pf(QP_FFN_FC2_B), c.sv(S.o), d);
-    if (!dc.drop && !dc.path) {
+    const Weight wf2 = c.W(W_F2, c.pf(QP_FFN_FC2_W));
+    const bool ff = (dc.drop || dc.path) && fused_nt(c, wf2, R, D.fh);
+    if ((!dc.drop && !dc.path) || ff) {
       e.resid = c.svf(S.x1); e.ldr = d; e.scale_res = c.pf(QP_FFN_GAMMA); e.C2 = blk_out; e.ldc2 = d; e.c2_f32 = 1;
-      QV_TRY(gemm_nt(st, dt, c.sv(S.hn2), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e));
+      if (ff) { e.drop = dc.site(DS_FFN); e.rowscale = dc.rs2; e.rows_per_img = D.Nt; }   // `o` = the dropped, path-scaled value
+      QV_TRY(gemm_nt(st, dt, c.sv(S.hn2), D.fh, R, wf2, e));
     } else {   // out = x1 + drop_path2(gamma * dropout(fc2))   (H:710-712, 1083); `o` keeps the dropped, path-scaled value
       QV_TRY(gemm_nt(st, dt, c.sv(S.hn2), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e));
       QV_TRY(drop_rows(st, dt, c.sv(S.o), d, R, d, dc.site(DS_FFN), dc.rs2, D.Nt, c.svf(S.x1), d, c.pf(QP_FFN_GAMMA), blk_out, d));
@@ -612,10 +628,13 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     e.gelu = 1; e.C2 = c.sv(S.h); e.ldc2 = D.fh; e.c2_f32 = dt == QV_F32;
     QV_TRY(gemm_nt(st, dt, c.sv(S.y), d, R, c.W(W_F1, c.pf(QP_FFN_FC1_W)), e));
     QV_TRY(dwconv_fwd(st, dt, c.sv(S.h), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W), cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, nullptr, c.sv(S.cs)));
-    if (!dc.drop && !dc.path) {
+    const Weight wf2 = c.W(W_F2, c.pf(QP_FFN_FC2_W));
+    const bool ff = (dc.drop || dc.path) && fused_nt(c, wf2, R, D.fh);
+    if ((!dc.drop && !dc.path) || ff) {
       GemmEpi e2;
       e2.bias = c.pf(QP_FFN_FC2_B); e2.resid = c.svf(S.x1); e2.ldr = d; e2.C2 = blk_out; e2.ldc2 = d; e2.c2_f32 = 1;
-      QV_TRY(gemm_nt(st, dt, c.sv(S.cs), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), e2));
+      if (ff) { e2.drop = dc.site(DS_FFN); e2.rowscale = dc.rs2; e2.rows_per_img = D.Nt; }
+      QV_TRY(gemm_nt(st, dt, c.sv(S.cs), D.fh, R, wf2, e2));
     } else {   // QAViT.py:580-582: out = x1 + drop_path2(dropout(fc2))
       QV_TRY(gemm_nt(st, dt, c.sv(S.cs), D.fh, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, c.pf(QP_FFN_FC2_B), c.sv(S.o), d)));
       QV_TRY(drop_rows(st, dt, c.sv(S.o), d, R, d, dc.site(DS_FFN), dc.rs2, D.Nt, c.svf(S.x1), d, nullptr, blk_out, d));
@@ -665,8 +684,10 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
 
   // ---- CCF-FFN backward
   if (!D.v1) {
-    QV_TRY(gamma_bwd(st, dt, dblk, c.sv(S.o), (long)R * d, c.pf(QP_FFN_GAMMA), c.sc(X.d_o), G(QP_FFN_GAMMA)));
-    if (dc.drop || dc.path) QV_TRY(drop_inplace(c, dc, c.sc(X.d_o), d, DS_FFN, dc.rs2));
+    {   // d_o = gamma * dblk through the FFN dropout site / DropPath scale (one pass)
+      const DropP site = dc.site(DS_FFN);
+      QV_TRY(gamma_bwd(st, dt, dblk, c.sv(S.o), (long)R * d, c.pf(QP_FFN_GAMMA), c.sc(X.d_o), G(QP_FFN_GAMMA), &site, dc.rs2, D.Nt, d));
+    }
     QV_TRY(gemm_tn(st, dt, c.sc(X.d_o), d, c.sv(S.hn2), D.fh, R, d, D.fh, G(QP_FFN_FC2_W), G(QP_FFN_FC2_B), nullptr));
     QV_TRY(gemm_nn(st, dt, c.sc(X.d_o), d, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, nullptr, c.sc(X.d_hn2), D.fh)));
     QV_TRY(ln_bwd(st, dt, c.sv(S.cs), D.fh, dt, c.sc(X.d_hn2), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.svf(S.pd_stats), 0, dt,
@@ -677,8 +698,12 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
     QV_TRY(ln_bwd(st, dt, c.sv(S.h_pre), D.fh, dt, c.sc(X.d_hn), D.fh, R, D.fh, c.pf(QP_FFN_DWN_W), c.svf(S.dn_stats), 1, dt,
                   c.sc(X.d_hpre), nullptr, nullptr, G(QP_FFN_DWN_W), G(QP_FFN_DWN_B)));
   } else {
-    QV_TRY(cast_f32_to_t(st, dt, dblk, (long)R * d, c.sc(X.d_o)));
-    if (dc.drop || dc.path) QV_TRY(drop_inplace(c, dc, c.sc(X.d_o), d, DS_FFN, dc.rs2));
+    if (dc.drop || dc.path) {
+      const DropP site = dc.site(DS_FFN);
+      QV_TRY(gamma_bwd(st, dt, dblk, nullptr, (long)R * d, nullptr, c.sc(X.d_o), nullptr, &site, dc.rs2, D.Nt, d));
+    } else {
+      QV_TRY(cast_f32_to_t(st, dt, dblk, (long)R * d, c.sc(X.d_o)));
+    }
     QV_TRY(gemm_tn(st, dt, c.sc(X.d_o), d, c.sv(S.cs), D.fh, R, d, D.fh, G(QP_FFN_FC2_W), G(QP_FFN_FC2_B), nullptr));
     QV_TRY(gemm_nn(st, dt, c.sc(X.d_o), d, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, nullptr, c.sc(X.d_cs), D.fh)));
     QV_TRY(dwconv_bwd(st, dt, c.sv(S.h), c.sc(X.d_cs), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W),
@@ -689,14 +714,23 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
   QV_TRY(gemm_tn(st, dt, c.sc(X.d_hpre), D.fh, c.sv(S.y), d, R, D.fh, d, G(QP_FFN_FC1_W), G(QP_FFN_FC1_B), nullptr));
   QV_TRY(gemm_nn(st, dt, c.sc(X.d_hpre), D.fh, R, c.W(W_F1, c.pf(QP_FFN_FC1_W)), epi_t(c, nullptr, c.sc(X.d_y), d)));
   // d_x1 = dblk + LN2-backward(d_y)   (fp32 and a T copy for the next GEMMs)
-  QV_TRY(ln_bwd(st, QV_F32, c.sv(S.x1), d, dt, c.sc(X.d_y), d, R, d, c.pf(QP_NORM2_W), c.svf(S.n2_stats), 0, dt, c.sc(X.d_x1t),
-                c.scf(X.d_x1), dblk, G(QP_NORM2_W), G(QP_NORM2_B)));
+  // (with dropout: the T copy, which only the bottleneck GEMMs read, goes through the B2 site and DropPath scale)
+  {
+    const DropP site = dc.site(DS_B2);
+    QV_TRY(ln_bwd(st, QV_F32, c.sv(S.x1), d, dt, c.sc(X.d_y), d, R, d, c.pf(QP_NORM2_W), c.svf(S.n2_stats), 0, dt, c.sc(X.d_x1t),
+                  c.scf(X.d_x1), dblk, G(QP_NORM2_W), G(QP_NORM2_B), &site, dc.rs1, D.Nt));
+  }
 
   // ---- BottleneckMLP backward
-  if (dc.drop || dc.path) QV_TRY(drop_inplace(c, dc, c.sc(X.d_x1t), d, DS_B2, dc.rs1));   // only the bottleneck reads d_x1t
   QV_TRY(gemm_tn(st, dt, c.sc(X.d_x1t), d, c.sv(S.h1), D.bh, R, d, D.bh, G(QP_BMLP_FC2_W), G(QP_BMLP_FC2_B), nullptr));
-  QV_TRY(gemm_nn(st, dt, c.sc(X.d_x1t), d, R, c.W(W_B2, c.pf(QP_BMLP_FC2_W)), epi_t(c, nullptr, c.sc(X.d_h1), D.bh)));
-  if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sc(X.d_h1), D.bh, DS_B1, nullptr));
+  {
+    const Weight wb2 = c.W(W_B2, c.pf(QP_BMLP_FC2_W));
+    GemmEpi e = epi_t(c, nullptr, c.sc(X.d_h1), D.bh);
+    const bool fused = dc.drop && fused_nn(c, wb2, R, d);
+    if (fused) e.drop = dc.site(DS_B1);
+    QV_TRY(gemm_nn(st, dt, c.sc(X.d_x1t), d, R, wb2, e));
+    if (dc.drop && !fused) QV_TRY(drop_inplace(c, dc, c.sc(X.d_h1), D.bh, DS_B1, nullptr));
+  }
   QV_TRY(gelu_bwd(st, dt, c.sv(S.h1_pre), c.sc(X.d_h1), (long)R * D.bh, c.sc(X.d_h1pre)));
   QV_TRY(gemm_tn(st, dt, c.sc(X.d_h1pre), D.bh, c.sv(S.fused), d, R, D.bh, d, G(QP_BMLP_FC1_W), G(QP_BMLP_FC1_B), nullptr));
   QV_TRY(gemm_nn(st, dt, c.sc(X.d_h1pre), D.bh, R, c.W(W_B1, c.pf(QP_BMLP_FC1_W)), epi_t(c, nullptr, c.sc(X.d_fused), d)));
@@ -718,9 +752,11 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
     GemmEpi e = epi_t(c, nullptr, c.sc(X.d_nb), d);
     e.scale_pre = alpha_i;
     QV_TRY(gemm_nn(st, dt, dfs, d, R, c.W(W_C0 + i, c.pf(kCompW[i])), e));
-    QV_TRY(ln_bwd(st, dt, c.sv(S.branch[i]), d, dt, c.sc(X.d_nb), d, R, d, c.pf(kNormW[i]), c.svf(S.nb_stats[i]), 0, dt,
-                  c.sc(X.d_branch), nullptr, nullptr, G(kNormW[i]), G(kNormW[i] + 1)));
-    if (dc.drop) QV_TRY(drop_inplace(c, dc, c.sc(X.d_branch), d, DS_PROJ + i, nullptr));
+    {   // d_branch goes through the branch's output-dropout site inside the LayerNorm backward
+      const DropP site = dc.site(DS_PROJ + i);
+      QV_TRY(ln_bwd(st, dt, c.sv(S.branch[i]), d, dt, c.sc(X.d_nb), d, R, d, c.pf(kNormW[i]), c.svf(S.nb_stats[i]), 0, dt,
+                    c.sc(X.d_branch), nullptr, nullptr, G(kNormW[i]), G(kNormW[i] + 1), &site));
+    }
     const void* d_branch = c.sc(X.d_branch);
     if (i == 3) {  // ---- cross
       QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_cross), d, R, d, d, G(QP_CROSS_PROJ_W), G(QP_CROSS_PROJ_B), nullptr));

@@ -338,12 +338,17 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const long aux_ld = use_resid ? e.ldr : e.ldg;
     const bool aux_f32 = use_resid ? !e.r_bf16 : !e.g_bf16;
     const int ncols = min(p.BN, p.N - n0);
+    const bool masked = e.drop.p > 0.f, scaled = e.rowscale != nullptr;   // dropout site / DropPath scale on the output
+    DropState dst{};
+    if (masked) dst = drop_state(e.drop);
     int acc = 0;
     uint32_t aph = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       mbar_wait(tfull + acc, aph);
       tc_fence_after();
       const long row0 = (long)mt * BM + quarter * 32;
+      const long my_r = row0 + lane;                                      // this thread's output row
+      const float rsc = scaled ? e.rowscale[min(my_r, (long)p.M - 1) / e.rows_per_img] : 1.f;
       for (int g = sub * EPI_GROUP; g < ncols; g += (EPI_WARPS / 4) * EPI_GROUP) {
         const int gw = min(EPI_GROUP, ncols - g), nch = gw / 16;
         float v[2][16], r[2][16];
@@ -369,6 +374,16 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[c][j] *= gelu_grad_fast_f(r[c][j]);
             }
+            if ((masked || scaled) && !e.gelu) {   // ids of drop_rows on the contiguous [M, N] output
+              float k[16];
+              if (masked) {
+                const unsigned long long id8 = (unsigned long long)(my_r * p.N + n0 + g + c * 16) >> 3;
+                drop_keep8(dst, id8, k);
+                drop_keep8(dst, id8 + 1, k + 8);
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[c][j] *= (masked ? k[j] : 1.f) * rsc;
+            }
           }
         if (e.C) {
 #pragma unroll
@@ -385,6 +400,14 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               if (e.gelu) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[c][j] = gelu_fast_f(v[c][j]);
+                if (masked) {                      // nn.Dropout after the activation (H:654): only C2 is dropped
+                  float k[16];
+                  const unsigned long long id8 = (unsigned long long)(my_r * p.N + n0 + g + c * 16) >> 3;
+                  drop_keep8(dst, id8, k);
+                  drop_keep8(dst, id8 + 1, k + 8);
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[c][j] *= k[j];
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[c][j] = s_res * v[c][j] + (use_resid ? r[c][j] : 0.f);

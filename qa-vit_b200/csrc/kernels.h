@@ -9,7 +9,14 @@ enum { QV_F32 = 0, QV_BF16 = 1 };
 //   C  [i, j] (T or fp32; += if c_accum)  = val            (pre-activation when gelu != 0)
 //   C2 [i, j] (T or fp32)                 = gelu ? gelu(val) : resid[i, j] + (scale_res ? *scale_res : 1) * val
 // gmul (dX GEMMs that feed a GELU backward): val *= gelu'(gmul[i, j]) before C is written; not combined with resid.
+// drop / rowscale (tcgen05 flavour only; the callers in block.cu fall back to a drop_rows pass otherwise): a dropout site
+// on the output with the element ids of drop_rows on a contiguous [M, N] matrix, and a per-image DropPath scale:
+//   gelu == 0: val *= keep(i, j) * rowscale[i / rows_per_img] before C and C2 are formed
+//   gelu != 0: only the activation C2 is dropped (C keeps the pre-activation)
 struct GemmEpi {
+  DropP drop;
+  const float* rowscale = nullptr;
+  int rows_per_img = 1;
   const float* bias = nullptr;
   const float* scale_pre = nullptr;
   const float* scale_res = nullptr;
@@ -131,9 +138,12 @@ int droppath_scales(cudaStream_t s, const DropP& d, int B, float* rs1, float* rs
 // ---- norms
 int ln_fwd(cudaStream_t s, int dt_in, const void* x, int ldx, int rows, int C, const float* gamma, const float* beta,
            float eps, int gelu_in, const float* gamma2, const float* beta2, int dt_out, void* y, int ldy, float* stats);
+// drop / rowscale (optional, C % 8 == 0 and C > 128 only): the T output dx_t additionally goes through a dropout site
+// (ids of drop_rows on [rows, C]) and a per-image scale -- the gradient of a dropped activation; dx_f32 stays unmasked.
 int ln_bwd(cudaStream_t s, int dt_x, const void* x, int ldx, int dt_dy, const void* dy, int lddy, int rows, int C,
            const float* gamma, const float* stats, int gelu_in, int dt_out, void* dx_t, float* dx_f32,
-           const float* resid, float* dgamma, float* dbeta);
+           const float* resid, float* dgamma, float* dbeta, const DropP* drop = nullptr, const float* rowscale = nullptr,
+           int rows_per_img = 1);
 
 // ---- attention family
 struct AttnP {
@@ -206,8 +216,10 @@ int dwconv_fwd(cudaStream_t s, int dt, const void* x, int B, int side, int C, co
 int dwconv_bwd(cudaStream_t s, int dt, const void* x, const void* dy, int B, int side, int C, const float* w,
                const float* bias, const float* scale, void* dx, float* dw, float* dbias, float* dscale);
 int gelu_bwd(cudaStream_t s, int dt, const void* pre, const void* dact, long n, void* dpre);
+// d_o = gamma * dout (* keep * rowscale when drop / rowscale are given: ids of drop_rows on [n / C, C]); dgamma += sum(dout * o).
+// gamma == nullptr: plain cast (QAViT.py's CCFFFN has no gamma), dgamma untouched.
 int gamma_bwd(cudaStream_t s, int dt, const float* dout, const void* o, long n, const float* gamma, void* d_o,
-              float* dgamma);
+              float* dgamma, const DropP* drop = nullptr, const float* rowscale = nullptr, int rows_per_img = 1, int C = 0);
 int cast_f32_to_t(cudaStream_t s, int dt, const float* x, long n, void* y);
 int fusion_softmax(cudaStream_t s, const float* w, int n, float* alpha);
 int fusion_bwd(cudaStream_t s, int dt, const void* dfused, const void* fused, long rows, int nb, int cw,

@@ -402,6 +402,44 @@ __global__ void gamma_bwd_kernel(const float* __restrict__ dout, const T* __rest
     if (threadIdx.x == 0) atomicAdd(dgamma, v);
   }
 }
+// same with a dropout site / DropPath scale on d_o (8 elements per thread: one Philox call); gamma == nullptr: cast only
+template <typename T>
+__global__ void __launch_bounds__(256) gamma_bwd_drop_kernel(const float* __restrict__ dout, const T* __restrict__ o, long n,
+                                                             const float* __restrict__ gamma, T* __restrict__ d_o,
+                                                             float* __restrict__ dgamma, DropP drop,
+                                                             const float* __restrict__ rowscale, int rows_per_img, int C) {
+  __shared__ float red[32];
+  const float g = gamma ? *gamma : 1.f;
+  const bool masked = drop.p > 0.f;
+  DropState dst{};
+  if (masked) dst = drop_state(drop);
+  float acc = 0.f;
+  for (long i8 = (long)blockIdx.x * blockDim.x + threadIdx.x; i8 * 8 < n; i8 += (long)gridDim.x * blockDim.x) {
+    const long i = i8 * 8;
+    float d[8], k[8];
+    load_vec<8>(dout + i, d);
+    if (gamma) {
+      float ov[8];
+      load_vec<8>(o + i, ov);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(d[j], ov[j], acc);
+    }
+    const float rs = rowscale ? rowscale[(i / C) / rows_per_img] : 1.f;
+    if (masked) drop_keep8(dst, (unsigned long long)i8, k);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] *= g * rs * (masked ? k[j] : 1.f);
+    store_vec<8>(d_o + i, d);
+  }
+  if (!gamma) return;
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(dgamma, v);
+  }
+}
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ x, long n, T* __restrict__ y) {
   for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (long)gridDim.x * blockDim.x * 2)
@@ -497,8 +535,17 @@ int gelu_bwd(cudaStream_t s, int dt, const void* pre, const void* dact, long n, 
   QV_LAUNCH_CHECK();
   return 0;
 }
-int gamma_bwd(cudaStream_t s, int dt, const float* dout, const void* o, long n, const float* gamma, void* d_o, float* dgamma) {
+int gamma_bwd(cudaStream_t s, int dt, const float* dout, const void* o, long n, const float* gamma, void* d_o, float* dgamma,
+              const DropP* drop, const float* rowscale, int rows_per_img, int C) {
   if (n <= 0) return 0;
+  const DropP dp = drop ? *drop : DropP();
+  if (dp.p > 0.f || rowscale || !gamma) {
+    QV_CHECK(n % 8 == 0 && C > 0 && C % 8 == 0, "gamma_bwd: fused dropout needs C %% 8 == 0 (C = %d)", C);
+    const int grid = (int)max(1L, min((long)qv_num_sms() * 16, (n / 8 + 255) / 256));
+    DISPATCH_T(dt, (gamma_bwd_drop_kernel<T><<<grid, 256, 0, s>>>(dout, (const T*)o, n, gamma, (T*)d_o, dgamma, dp, rowscale, rows_per_img, C)));
+    QV_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_T(dt, (gamma_bwd_kernel<T><<<ew_grid(n), 256, 0, s>>>(dout, (const T*)o, n, gamma, (T*)d_o, dgamma)));
   QV_LAUNCH_CHECK();
   return 0;

@@ -75,8 +75,12 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const TX* __restrict__ x
                                                      int lddy, int rows, int C, const float* __restrict__ gamma,
                                                      const float* __restrict__ stats, TO* __restrict__ dx_t,
                                                      float* __restrict__ dx_f32, const float* __restrict__ resid,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, DropP drop,
+                                                     const float* __restrict__ rowscale, int rows_per_img) {
   __shared__ float red[2][8][256];
+  const bool masked = EPL == 8 && drop.p > 0.f, scaled = EPL == 8 && rowscale != nullptr;
+  DropState dst{};
+  if (masked) dst = drop_state(drop);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int c0 = lane * EPL;
   const bool act = c0 < C;
@@ -115,8 +119,17 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const TX* __restrict__ x
       dv[i] = d + rs[i];
     }
     if (act) {
-      if (dx_t) store_vec<EPL>(dx_t + row * C + c0, dv);
       if (dx_f32) store_vec<EPL>(dx_f32 + row * C + c0, dv);
+      if (dx_t) {
+        if (EPL == 8 && (masked || scaled)) {   // gradient w.r.t. the pre-dropout activation (dx_f32 stays the stream gradient)
+          const float rsc = scaled ? rowscale[row / rows_per_img] : 1.f;
+          float k[8];
+          if (masked) drop_keep8(dst, (unsigned long long)(row * C + c0) >> 3, k);
+#pragma unroll
+          for (int i = 0; i < EPL; ++i) dv[i] *= (masked ? k[i & 7] : 1.f) * rsc;
+        }
+        store_vec<EPL>(dx_t + row * C + c0, dv);
+      }
     }
   }
   if (dgamma == nullptr) return;
@@ -158,16 +171,18 @@ int ln_fwd(cudaStream_t s, int dt_in, const void* x, int ldx, int rows, int C, c
 
 int ln_bwd(cudaStream_t s, int dt_x, const void* x, int ldx, int dt_dy, const void* dy, int lddy, int rows, int C,
            const float* gamma, const float* stats, int gelu_in, int dt_out, void* dx_t, float* dx_f32,
-           const float* resid, float* dgamma, float* dbeta) {
+           const float* resid, float* dgamma, float* dbeta, const DropP* drop, const float* rowscale, int rows_per_img) {
   if (rows <= 0) return 0;
   const int epl = pick_epl(C);
   QV_CHECK(C <= 256 && C % epl == 0 && ldx % epl == 0 && lddy % epl == 0, "ln_bwd: C=%d ldx=%d lddy=%d unsupported", C, ldx, lddy);
+  const DropP dp = drop ? *drop : DropP();
+  QV_CHECK((dp.p == 0.f && !rowscale) || (epl == 8 && dx_t), "ln_bwd: fused dropout needs C > 128 (8 elements per lane) and a T output");
   QV_CHECK(resid == nullptr || (resid != dx_f32 && (const void*)resid != dx_t), "ln_bwd: resid must not alias an output");
   // every CTA ends with 2 * C atomics: keep >= 32 rows per warp before adding CTAs
   const int grid = max(1, min(cdiv(rows, 8 * 32), qv_num_sms() * 6));
 #define LN_B4(TX, TDY, TO, E, G)                                                                                      \
   ln_bwd_kernel<TX, TDY, TO, E, G><<<grid, 256, 0, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, rows, C, gamma, stats, \
-                                                        (TO*)dx_t, dx_f32, resid, dgamma, dbeta)
+                                                        (TO*)dx_t, dx_f32, resid, dgamma, dbeta, dp, rowscale, rows_per_img)
 #define LN_B3(TX, TDY, TO, G) do { if (epl == 8) LN_B4(TX, TDY, TO, 8, G); else LN_B4(TX, TDY, TO, 4, G); } while (0)
 #define LN_B2(TX, TDY, TO) do { if (gelu_in) LN_B3(TX, TDY, TO, true); else LN_B3(TX, TDY, TO, false); } while (0)
   const int key = dt_x * 4 + dt_dy * 2 + dt_out;

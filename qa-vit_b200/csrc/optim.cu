@@ -82,16 +82,29 @@ __global__ void __launch_bounds__(256) scale_grads_kernel(float* __restrict__ g,
   }
 }
 
-// hyper: lr, beta1, beta2, eps, wd, 1 - beta1^t, 1 - beta2^t
+// hyper: lr, beta1, beta2, eps, wd, 1 - beta1^t, 1 - beta2^t, ema decay d, 1 - d (formed in double on the host, like torch's alpha)
+// EMA: ModelEMA.update (H:139-149) folded in -- ema = d * ema + (1 - d) * p_new for EVERY parameter (also the ones AdamW
+// skips), one extra fp32 stream through the same pass instead of 815 mul_/add_ launches.
+template <bool EMA>
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, const long long* __restrict__ off,
+                                                    float* __restrict__ v, float* __restrict__ ema, const long long* __restrict__ off,
                                                     const int* __restrict__ flags, int n, const float* __restrict__ hyper,
                                                     long long total) {
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6];
   const float step = lr / bc1, rs2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+  const float ed = EMA ? hyper[7] : 0.f, ec = EMA ? hyper[8] : 0.f;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
     const int s = find_seg(off, n, i);
-    if (!(flags[s] & 1)) continue;   // grad is None: skipped entirely, also by weight decay
+    if (!(flags[s] & 1)) {           // grad is None: skipped entirely, also by weight decay
+      if (EMA) {
+        const float4 pp = *reinterpret_cast<const float4*>(p + i);
+        float4 ee = *reinterpret_cast<float4*>(ema + i);
+        ee.x = __fadd_rn(__fmul_rn(ee.x, ed), __fmul_rn(pp.x, ec)); ee.y = __fadd_rn(__fmul_rn(ee.y, ed), __fmul_rn(pp.y, ec));
+        ee.z = __fadd_rn(__fmul_rn(ee.z, ed), __fmul_rn(pp.z, ec)); ee.w = __fadd_rn(__fmul_rn(ee.w, ed), __fmul_rn(pp.w, ec));
+        *reinterpret_cast<float4*>(ema + i) = ee;
+      }
+      continue;
+    }
     float4 pp = *reinterpret_cast<float4*>(p + i);
     const float4 gg = *reinterpret_cast<const float4*>(g + i);
     float4 mm = *reinterpret_cast<float4*>(m + i);
@@ -109,6 +122,32 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     *reinterpret_cast<float4*>(p + i) = pp;
     *reinterpret_cast<float4*>(m + i) = mm;
     *reinterpret_cast<float4*>(v + i) = vv;
+    if (EMA) {   // mul_(decay).add_(p, alpha = 1 - decay): two roundings per term, no fma contraction (bit-exact vs torch)
+      float4 ee = *reinterpret_cast<float4*>(ema + i);
+      ee.x = __fadd_rn(__fmul_rn(ee.x, ed), __fmul_rn(pp.x, ec)); ee.y = __fadd_rn(__fmul_rn(ee.y, ed), __fmul_rn(pp.y, ec));
+      ee.z = __fadd_rn(__fmul_rn(ee.z, ed), __fmul_rn(pp.z, ec)); ee.w = __fadd_rn(__fmul_rn(ee.w, ed), __fmul_rn(pp.w, ec));
+      *reinterpret_cast<float4*>(ema + i) = ee;
+    }
+  }
+}
+
+// CutMix / MixUp of a batch against a permutation of itself (H:1379-1399).  mode 1: pixels inside [x1, x2) x [y1, y2) come
+// from image perm[b]; mode 2: lam * x[b] + (1 - lam) * x[perm[b]] (two roundings like the torch expression).
+__global__ void __launch_bounds__(256) batch_mix_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                        const long long* __restrict__ perm, int B, int C, int H, int W, int mode,
+                                                        int x1, int y1, int x2, int y2, float lam, float lb) {
+  const long long per = (long long)C * H * W, total = (long long)B * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per, r = i % per;
+    const int x = (int)(r % W), y = (int)((r / W) % H);
+    const long long j = perm[b] * per + r;
+    float v = in[i];
+    if (mode == 1) {
+      if (x >= x1 && x < x2 && y >= y1 && y < y2) v = in[j];
+    } else if (mode == 2) {
+      v = __fadd_rn(__fmul_rn(lam, v), __fmul_rn(lb, in[j]));
+    }
+    out[i] = v;
   }
 }
 
@@ -133,7 +172,39 @@ extern "C" int qavit_adamw_step(float* params, const float* grads, float* exp_av
   cudaStream_t s = (cudaStream_t)stream;
   if (n_seg <= 0) return 0;
   const int grid = (int)max(1LL, min((long long)qv_num_sms() * 8, (total / 4 + 255) / 256));
-  adamw_kernel<<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, seg_off, seg_flags, n_seg, hyper, total);
+  adamw_kernel<false><<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, nullptr, seg_off, seg_flags, n_seg, hyper, total);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qavit_adamw_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,
+                                    const long long* seg_off, const int* seg_flags, int n_seg, const float* hyper, long long total,
+                                    void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_seg <= 0) return 0;
+  QV_CHECK(ema, "adamw_ema_step: ema buffer missing");
+  const int grid = (int)max(1LL, min((long long)qv_num_sms() * 8, (total / 4 + 255) / 256));
+  adamw_kernel<true><<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, ema, seg_off, seg_flags, n_seg, hyper, total);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qavit_segment_norms(const float* buf, const long long* seg_off, const int* seg_flags, int n_seg, float* norms,
+                                   void* stream) {
+  if (n_seg <= 0) return 0;
+  seg_norm_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(buf, seg_off, seg_flags, norms);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qavit_batch_mix(const float* in, float* out, const long long* perm, int B, int C, int H, int W, int mode, int x1,
+                               int y1, int x2, int y2, float lam, float lam_b, void* stream) {
+  QV_CHECK(in && out && perm && in != out, "batch_mix: null / aliased argument (out must not alias in: rows are read through perm)");
+  QV_CHECK(mode == 1 || mode == 2, "batch_mix: mode %d (1 = cutmix, 2 = mixup)", mode);
+  const long long total = (long long)B * C * H * W;
+  if (total <= 0) return 0;
+  const int grid = (int)max(1LL, min((long long)qv_num_sms() * 16, (total + 255) / 256));
+  batch_mix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, perm, B, C, H, W, mode, x1, y1, x2, y2, lam, lam_b);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -580,3 +580,49 @@ def cross_entropy(logits: torch.Tensor, target: torch.Tensor, label_smoothing: f
     ya = target.to(torch.int64).contiguous()
     yb = None if target_b is None else target_b.to(torch.int64).contiguous()
     return CrossEntropyFn.apply(logits, ya, yb, lam, label_smoothing)
+
+
+# ------------------------------------------------------------------------------------------------ batch augmentation (8(f)-3)
+def rand_bbox(size, lam, rng=None):
+    """``rand_bbox`` of the reference (HQAViT_CIFAR100.py:1343-1360): centre uniform, side = sqrt(1 - lam) of the image."""
+    import numpy as np
+    rng = np.random if rng is None else rng
+    W, H = size[3], size[2]
+    cut_rat = np.sqrt(1.0 - lam)
+    cut_w, cut_h = int(W * cut_rat), int(H * cut_rat)
+    cx, cy = rng.randint(W), rng.randint(H)
+    return (int(np.clip(cx - cut_w // 2, 0, W)), int(np.clip(cy - cut_h // 2, 0, H)),
+            int(np.clip(cx + cut_w // 2, 0, W)), int(np.clip(cy + cut_h // 2, 0, H)))
+
+
+def batch_mix(inputs: torch.Tensor, perm: torch.Tensor, mode: str, lam: float = 1.0, box=(0, 0, 0, 0)) -> torch.Tensor:
+    """One kernel for ``inputs[:, :, y1:y2, x1:x2] = inputs[perm, :, y1:y2, x1:x2]`` (mode 'cutmix') or
+    ``lam * inputs + (1 - lam) * inputs[perm]`` (mode 'mixup') -- HQAViT_CIFAR100.py:1383-1397."""
+    _require_cuda(inputs, "image batch")
+    x = inputs.float().contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty_like(x)
+    x1, y1, x2, y2 = box
+    check(lib.qavit_batch_mix(x.data_ptr(), out.data_ptr(), perm.to(torch.int64).contiguous().data_ptr(), B, Cc, H, W,
+                              1 if mode == "cutmix" else 2, int(x1), int(y1), int(x2), int(y2), float(lam), 1.0 - float(lam), _stream()))
+    return out
+
+
+def mix_batch(inputs: torch.Tensor, targets: torch.Tensor, config, rng=None):
+    """The augmentation branch of ``train_epoch`` (HQAViT_CIFAR100.py:1379-1399) with the pixel work on the device:
+    returns ``(inputs, targets_a, targets_b, lam, use_mix)``; the loss is then
+    ``cross_entropy(logits, targets_a, label_smoothing, target_b=targets_b, lam=lam)`` (H:1404-1408).  Host-side random
+    draws (np.random.rand / beta / randperm) follow the reference's order."""
+    import numpy as np
+    rng = np.random if rng is None else rng
+    if getattr(config, "use_cutmix", False) and rng.rand() < config.mix_prob:
+        perm = torch.randperm(inputs.size(0)).to(inputs.device)
+        x1, y1, x2, y2 = rand_bbox(inputs.size(), rng.beta(config.cutmix_alpha, config.cutmix_alpha), rng)
+        out = batch_mix(inputs, perm, "cutmix", box=(x1, y1, x2, y2))
+        lam = 1.0 - ((x2 - x1) * (y2 - y1) / float(inputs.size(3) * inputs.size(2)))
+        return out, targets, targets[perm], lam, "cutmix"
+    if getattr(config, "use_mixup", False) and rng.rand() < config.mix_prob:
+        perm = torch.randperm(inputs.size(0)).to(inputs.device)
+        lam = float(rng.beta(config.mixup_alpha, config.mixup_alpha))
+        return batch_mix(inputs, perm, "mixup", lam=lam), targets, targets[perm], lam, "mixup"
+    return inputs, targets, targets, 1.0, None

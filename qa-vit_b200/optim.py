@@ -59,10 +59,44 @@ class FusedAdamW(torch.optim.Optimizer):
         self.seg_flags = torch.zeros(len(params), dtype=torch.int32, device=dev)
         self._flags_host = torch.zeros(len(params), dtype=torch.int32).pin_memory()
         self.norms = torch.zeros(len(params) + 2, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
-        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(12, dtype=torch.float32).pin_memory()
+        self.hyper = torch.zeros(12, dtype=torch.float32, device=dev)
         self.step_count = 0
         self._have_flags = False
+        self.flat_ema: Optional[torch.Tensor] = None      # enable_ema(): EMA of flat_p, updated inside the step kernel
+        self.ema_decay = 0.0
+        self._all_flags = torch.ones(len(params), dtype=torch.int32, device=dev)
+        self._mon = torch.zeros(2 * len(params), dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------ EMA folded into the step
+    def enable_ema(self, decay: float = 0.9999) -> torch.Tensor:
+        """Start tracking ``ema = decay * ema + (1 - decay) * p`` for every parameter inside the AdamW kernel
+        (``ModelEMA.update``, HQAViT_CIFAR100.py:139-149).  Returns the flat EMA buffer (same layout as ``flat_p``)."""
+        if self.flat_ema is None:
+            self.flat_ema = self.flat_p.clone()
+        self.ema_decay = float(decay)
+        return self.flat_ema
+
+    def ema_views(self):
+        """{parameter name: view into the EMA buffer}."""
+        if self.flat_ema is None:
+            raise RuntimeError("enable_ema() first")
+        offs = self.seg_off.tolist()
+        return {n: self.flat_ema[o:o + p.numel()].view(p.shape) for n, p, o in zip(self.names, self.param_groups[0]["params"], offs)}
+
+    # ------------------------------------------------------------------ gradient monitoring without host syncs
+    @torch.no_grad()
+    def monitor_norms(self):
+        """Per-tensor gradient and parameter L2 norms (``GradientMonitor.log_gradients``, H:198-242) as two device
+        vectors in ``self.names`` order, from two launches; call before ``clip()`` for the unclipped gradients."""
+        n = len(self.names)
+        if not self._have_flags:
+            self._sync_flags()
+        check(lib.qavit_segment_norms(self.flat_g.data_ptr(), self.seg_off.data_ptr(), self.seg_flags.data_ptr(), n,
+                                      self._mon.data_ptr(), _stream()))
+        check(lib.qavit_segment_norms(self.flat_p.data_ptr(), self.seg_off.data_ptr(), self._all_flags.data_ptr(), n,
+                                      self._mon[n:].data_ptr(), _stream()))
+        return self._mon[:n], self._mon[n:]
 
     def attach_grads(self):
         """Point every .grad at its slice of the flat gradient buffer (zeroed): autograd then accumulates in place
@@ -116,6 +150,7 @@ class FusedAdamW(torch.optim.Optimizer):
         h = self._hyper_host
         h[0], h[1], h[2], h[3], h[4] = grp["lr"], b1, b2, grp["eps"], grp["weight_decay"]
         h[5], h[6] = 1.0 - b1 ** t, 1.0 - b2 ** t
+        h[7], h[8] = self.ema_decay, 1.0 - self.ema_decay
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -125,11 +160,61 @@ class FusedAdamW(torch.optim.Optimizer):
         if not torch.cuda.is_current_stream_capturing():
             self.write_hyper()
         self.hyper.copy_(self._hyper_host, non_blocking=True)
-        check(lib.qavit_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                   self.seg_off.data_ptr(), self.seg_flags.data_ptr(), len(self.names), self.hyper.data_ptr(),
-                                   self.total, _stream()))
+        if self.flat_ema is not None:
+            check(lib.qavit_adamw_ema_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
+                                           self.exp_avg_sq.data_ptr(), self.flat_ema.data_ptr(), self.seg_off.data_ptr(),
+                                           self.seg_flags.data_ptr(), len(self.names), self.hyper.data_ptr(), self.total, _stream()))
+        else:
+            check(lib.qavit_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                       self.seg_off.data_ptr(), self.seg_flags.data_ptr(), len(self.names), self.hyper.data_ptr(),
+                                       self.total, _stream()))
         return None
 
 
 def clip_grad_norms_(opt: FusedAdamW) -> torch.Tensor:
     return opt.clip()
+
+
+class ModelEMA:
+    """Drop-in for the reference's ``ModelEMA`` (HQAViT_CIFAR100.py:128-184): ``.ema`` is an eval-mode copy of the model,
+    ``update(model)`` / ``set_decay`` / ``compute_distance`` keep their signatures.  With ``optimizer=FusedAdamW`` the
+    parameter average is computed INSIDE the AdamW kernel (one extra fp32 stream instead of 815 ``mul_/add_`` launches):
+    the copy's parameters are re-homed as views of the optimizer's flat EMA buffer and ``update()`` only mirrors the
+    buffers (BatchNorm statistics, ``update_count``), as H:151-156 does."""
+
+    def __init__(self, model: torch.nn.Module, decay: float = 0.9999, device=None, optimizer: Optional[FusedAdamW] = None):
+        from copy import deepcopy
+        if optimizer is None:
+            raise RuntimeError("qavit_b200.ModelEMA needs optimizer=FusedAdamW (the average is fused into its step kernel)")
+        self.ema = deepcopy(model).eval()
+        self.decay = decay
+        self.device = device
+        self.opt = optimizer
+        optimizer.enable_ema(decay)
+        views = optimizer.ema_views()
+        with torch.no_grad():
+            for n, p in self.ema.named_parameters():
+                p.requires_grad_(False)
+                if n in views:
+                    p.data = views[n]
+
+    @torch.no_grad()
+    def update(self, model: torch.nn.Module):
+        ema_buffers = dict(self.ema.named_buffers())
+        for name, buf in model.named_buffers():
+            if name in ema_buffers:
+                ema_buffers[name].copy_(buf)
+
+    def set_decay(self, decay: float):
+        self.decay = decay
+        self.opt.ema_decay = float(decay)
+
+    @torch.no_grad()
+    def compute_distance(self, model: torch.nn.Module):
+        param_dist = (self.opt.flat_ema - self.opt.flat_p).norm().item()
+        ema_buffers = dict(self.ema.named_buffers())
+        sq = 0.0
+        for name, buf in model.named_buffers():
+            if name in ema_buffers and buf.dtype == torch.float32:
+                sq += (ema_buffers[name] - buf).norm().item() ** 2
+        return param_dist, sq ** 0.5

@@ -86,3 +86,39 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src, f"{f} references the oracle"
+
+
+def test_transfer_helpers_follow_the_reference_recipes():
+    """adjust_positional_embedding (HQAViT_Tiny_stl10.py:250-282) and the head-swap load (HQAViT_Tiny_Cifar10.py:445-453)
+    on the drop-in module tree (host-side tensor surgery, no kernel involved)."""
+    import torch.nn.functional as F
+    src = Q.HQAViT(Q.HQAViTConfig(dropout=0.0, drop_path=0.0))
+    dst = Q.HQAViT(Q.HQAViTConfig(num_classes=10, dropout=0.0, drop_path=0.0))
+    loaded, skipped = Q.load_pretrained_except_head(dst, src.state_dict())
+    assert skipped == 2 and loaded == len(src.state_dict()) - 2
+    assert torch.equal(dst.stage3_blocks[0].quad_block.swa.qkv.weight, src.stage3_blocks[0].quad_block.swa.qkv.weight)
+    assert dst.head.weight.shape == (10, 192)
+    old = dst.pos_embed.detach().clone()
+    assert not Q.adjust_positional_embedding(dst, 32)
+    assert Q.adjust_positional_embedding(dst, 96)
+    assert dst.pos_embed.shape == (1, 576, 192) and isinstance(dst.pos_embed, torch.nn.Parameter)
+    want = F.interpolate(old.reshape(1, 8, 8, 192).permute(0, 3, 1, 2), size=(24, 24), mode="bicubic", align_corners=False)
+    assert torch.equal(dst.pos_embed.detach(), want.permute(0, 2, 3, 1).reshape(1, 576, 192))
+    ref_path = "/root/reference"
+    if os.path.isdir(ref_path):        # same result as the reference's own function applied to our module
+        import importlib.util, sys, types
+        for stub in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+            sys.modules.setdefault(stub, types.ModuleType(stub))
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        sys.modules["matplotlib"].use = lambda *a, **k: None
+        try:
+            spec = importlib.util.spec_from_file_location("ref_stl10", os.path.join(ref_path, "HQAViT_Tiny_stl10.py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.path.insert(0, ref_path)
+            spec.loader.exec_module(mod)
+        except Exception as e:          # optional dependency of that script missing in this image
+            pytest.skip(f"reference script not importable here: {e}")
+        other = Q.HQAViT(Q.HQAViTConfig(num_classes=10, dropout=0.0, drop_path=0.0))
+        other.pos_embed.data.copy_(old)
+        mod.adjust_positional_embedding(other, 96)
+        assert torch.equal(other.pos_embed.detach(), dst.pos_embed.detach())

@@ -1,0 +1,132 @@
+"""The pieces of the reference's train loop that sit around the model step: ModelEMA folded into the
+AdamW kernel, GradientMonitor's per-tensor norms, on-device CutMix / MixUp -- each against the reference's torch expression."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import qavit_b200 as Q
+from util import build_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _toy_params(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(192, 192), (192,), (1,), (16, 48), (3, 5, 7), (100, 192)]
+    return [(f"p{i}.{'dwconv.w' if i == 3 else 'w'}", torch.nn.Parameter(torch.randn(s, generator=g).cuda())) for i, s in enumerate(shapes)]
+
+
+def test_adamw_with_fused_ema_matches_torch_adamw_plus_model_ema_update():
+    named = _toy_params()
+    ref = [p.detach().clone().requires_grad_(True) for _, p in named]
+    opt = Q.FusedAdamW(named, lr=3e-3, betas=(0.9, 0.999), weight_decay=0.05, max_grad_norm=None)
+    ema = opt.enable_ema(0.99)
+    topt = torch.optim.AdamW(ref, lr=3e-3, betas=(0.9, 0.999), weight_decay=0.05)
+    tema = [p.detach().clone() for p in ref]
+    has_grad = [True, True, False, True, True, True]        # p2 never receives a gradient (like the bank's write_* tensors)
+    opt.set_grad_mask(has_grad)
+    g = torch.Generator().manual_seed(1)
+    for step in range(4):
+        if step == 2:
+            opt.ema_decay = 0.9                               # ModelEMA.set_decay during warm-up (H:1633-1638)
+        opt.zero_grad()
+        for (n, p), r, h in zip(named, ref, has_grad):
+            gr = torch.randn(p.shape, generator=g).cuda()
+            if h:
+                p.grad.copy_(gr)
+                r.grad = gr.clone()
+            else:
+                r.grad = None
+        opt.step()
+        topt.step()
+        d = opt.ema_decay
+        with torch.no_grad():
+            for e, r in zip(tema, ref):                       # ModelEMA.update, H:146-149
+                e.mul_(d).add_(r.detach(), alpha=1.0 - d)
+    views = opt.ema_views()
+    for (n, p), r, e in zip(named, ref, tema):
+        assert torch.allclose(p.detach(), r.detach(), rtol=2e-6, atol=1e-7), n
+        assert torch.allclose(views[n], e, rtol=2e-6, atol=1e-7), n
+    assert ema.data_ptr() == opt.flat_ema.data_ptr()
+
+
+def test_monitor_norms_match_torch():
+    named = _toy_params(3)
+    opt = Q.FusedAdamW(named, lr=1e-3)
+    opt.zero_grad()
+    for _, p in named:
+        p.grad.copy_(torch.randn_like(p))
+    gn, pn = opt.monitor_norms()
+    for i, (n, p) in enumerate(named):
+        assert abs(gn[i].item() - p.grad.norm().item()) <= 1e-5 * p.grad.norm().item() + 1e-7, n
+        assert abs(pn[i].item() - p.norm().item()) <= 1e-5 * p.norm().item() + 1e-7, n
+
+
+def test_model_ema_drop_in_tracks_parameters_and_buffers():
+    model, ocfg, sd, B = build_model("qavitv2_c100", precision="fp32")
+    model.train()
+    opt = Q.FusedAdamW(model.named_parameters(), lr=1e-2, weight_decay=0.0, max_grad_norm=0.5)
+    ema = Q.ModelEMA(model, decay=0.9, optimizer=opt)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    x = torch.randn(2, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 100, (2,), device="cuda")
+    opt.zero_grad()
+    Q.cross_entropy(model(x), y).backward()
+    opt.clip()
+    opt.step()
+    ema.update(model)
+    ema_p = dict(ema.ema.named_parameters())
+    moved = 0
+    for n, p in model.named_parameters():
+        want = 0.9 * before[n] + 0.1 * p.detach()
+        assert torch.allclose(ema_p[n], want, rtol=1e-5, atol=1e-7), n
+        moved += int(not torch.equal(p.detach(), before[n]))
+    assert moved > 500
+    assert int(ema.ema.global_bank.update_count) == int(model.global_bank.update_count) > 0   # buffers mirrored (H:151-156)
+    assert not ema.ema.training
+    pd, bd = ema.compute_distance(model)
+    assert pd > 0 and bd == 0.0
+    with torch.no_grad():
+        assert ema.ema(x).shape == (2, 100)                  # the averaged copy is a working model
+
+
+@pytest.mark.parametrize("shape", [(7, 3, 32, 32), (4, 3, 64, 64)])
+def test_batch_mix_matches_reference_expressions(shape):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(shape, generator=g).cuda()
+    perm = torch.randperm(shape[0], generator=g).cuda()
+    x1, y1, x2, y2 = 3, 0, 20, 17
+    want = x.clone()
+    want[:, :, y1:y2, x1:x2] = x[perm, :, y1:y2, x1:x2]      # H:1386
+    assert torch.equal(Q.batch_mix(x, perm, "cutmix", box=(x1, y1, x2, y2)), want)
+    lam = 0.37219
+    assert torch.equal(Q.batch_mix(x, perm, "mixup", lam=lam), lam * x + (1 - lam) * x[perm])   # H:1396, bit-exact
+
+
+def test_mix_batch_draw_order_and_two_target_loss():
+    cfg = types.SimpleNamespace(use_cutmix=True, cutmix_alpha=1.0, use_mixup=True, mixup_alpha=0.2, mix_prob=0.6)
+    x = torch.randn(16, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 100, (16,), device="cuda")
+    seen = set()
+    for seed in range(12):
+        rng = np.random.RandomState(seed)
+        probe = np.random.RandomState(seed)
+        first = probe.rand()
+        out, ta, tb, lam, kind = Q.mix_batch(x, y, cfg, rng)
+        seen.add(kind)
+        if first < cfg.mix_prob:                              # the first draw decides CutMix (H:1382)
+            assert kind == "cutmix" and 0.0 <= lam <= 1.0
+            assert torch.equal(ta, y) and out.shape == x.shape
+        elif kind is None:
+            assert out is x and lam == 1.0
+        else:
+            assert kind == "mixup"
+    assert "cutmix" in seen and (None in seen or "mixup" in seen)
+    logits = torch.randn(16, 100, device="cuda", requires_grad=True)
+    out, ta, tb, lam, kind = Q.mix_batch(x, y, cfg, np.random.RandomState(0))
+    loss = Q.cross_entropy(logits, ta, label_smoothing=0.1, target_b=tb, lam=lam)
+    ce = torch.nn.CrossEntropyLoss(label_smoothing=0.1)
+    want = lam * ce(logits, ta) + (1.0 - lam) * ce(logits, tb)     # H:1406
+    assert abs(loss.item() - want.item()) < 1e-5

@@ -8,14 +8,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--model", default="hqavit")
+ap.add_argument("--dropout", type=float, default=0.0)
+ap.add_argument("--drop-path", type=float, default=0.0)
 a = ap.parse_args()
 torch.manual_seed(42)
 if a.model == "hqavit":
-    model = Q.HQAViT(Q.HQAViTConfig(dropout=0.0, drop_path=0.0))
-    for n in ("fuse2", "fuse3", "fuse4"):
-        getattr(model, n).cat_mlp[3].p = 0.0
+    model = Q.HQAViT(Q.HQAViTConfig(dropout=a.dropout, drop_path=a.drop_path))
+    if a.dropout == 0.0:
+        for n in ("fuse2", "fuse3", "fuse4"):
+            getattr(model, n).cat_mlp[3].p = 0.0
 else:
-    model = Q.QAViT(Q.QAViTConfig(dropout=0.0, drop_path=0.0))
+    model = Q.QAViT(Q.QAViTConfig(dropout=a.dropout, drop_path=a.drop_path))
 model = model.cuda().train().set_precision("bf16")
 opt = Q.FusedAdamW(model.named_parameters(), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06, max_grad_norm=0.5)
 nograd = ("swa.norm.", "msda.norm.", "cga.norm.", "write_norm.", "write_compression.", "write_gate.")
