@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) lin_pre_kernel(const bf16* __restrict__ k
       const int l = i / D, c2 = (i % D) * 2;                           // c2 in [0, 2D)
       const int col = c2 < D ? kcol + c2 : vcol + (c2 - D);
       const float2 v = ld2(kv + ((long)b * NM + l) * ldkv + col);
-      sX[l * D2 + c2] = v.x; sX[l * D2 + c2 + 1] = v.y;
+      *reinterpret_cast<float2*>(sX + l * D2 + c2) = v;
     }
     __syncthreads();
     // thread block of 4 (j) x 2 (c) outputs
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256) lin_pre_kernel(const bf16* __restrict__ k
       float a[4][2] = {};
       for (int l = 0; l < L; ++l) {
         const float4 e = *reinterpret_cast<const float4*>(E + l * KLIN);
-        const float x0 = sX[l * D2 + c2], x1 = sX[l * D2 + c2 + 1];
+        const float2 xv = *reinterpret_cast<const float2*>(sX + l * D2 + c2);
+        const float x0 = xv.x, x1 = xv.y;
         a[0][0] = fmaf(e.x, x0, a[0][0]); a[0][1] = fmaf(e.x, x1, a[0][1]);
         a[1][0] = fmaf(e.y, x0, a[1][0]); a[1][1] = fmaf(e.y, x1, a[1][1]);
         a[2][0] = fmaf(e.z, x0, a[2][0]); a[2][1] = fmaf(e.z, x1, a[2][1]);
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(256) lin_post_kernel(const bf16* __restrict__ 
   const int D2 = 2 * D;
   float* sE = sm;                        // [2][L][32]
   float* sX = sE + 2 * L * KLIN;         // [L][2D]
-  float* sG = sX + L * D2;               // [32][2D]
+  float* sG = sX + L * D2;               // [32][2D + 4]: in the dE product a warp's lanes read 32 different rows j at the same
+  const int GP = D2 + 4;                 // column, so the pitch must not be a multiple of 32 banks (2D = 384 was a 32-way conflict)
   for (int i = threadIdx.x; i < 2 * L * KLIN; i += blockDim.x) sE[i] = i < L * KLIN ? Ek[i] : Ev[i - L * KLIN];
   // dE outputs owned by this thread: (which, l, j) = idx, idx + 256, ...  (2 * L * 32 of them)
   constexpr int MAXO = 32;               // 2 * 128 * 32 / 256
@@ -116,10 +118,12 @@ __global__ void __launch_bounds__(256) lin_post_kernel(const bf16* __restrict__ 
       const int l = i / D, c2 = (i % D) * 2;
       const int col = c2 < D ? kcol + c2 : vcol + (c2 - D);
       const float2 v = ld2(kv + ((long)b * NM + l) * ldkv + col);
-      sX[l * D2 + c2] = v.x; sX[l * D2 + c2 + 1] = v.y;
+      *reinterpret_cast<float2*>(sX + l * D2 + c2) = v;
     }
-    for (int i = threadIdx.x; i < KLIN * D2 / 4; i += blockDim.x)
-      *reinterpret_cast<float4*>(sG + i * 4) = *reinterpret_cast<const float4*>(dpre + (long)b * KLIN * D2 + i * 4);
+    for (int i = threadIdx.x; i < KLIN * D2 / 4; i += blockDim.x) {
+      const int j = (i * 4) / D2, c = (i * 4) % D2;
+      *reinterpret_cast<float4*>(sG + j * GP + c) = *reinterpret_cast<const float4*>(dpre + (long)b * KLIN * D2 + i * 4);
+    }
     __syncthreads();
     // dKs / dVs
     for (int i = threadIdx.x; i < L * D; i += blockDim.x) {
@@ -127,7 +131,10 @@ __global__ void __launch_bounds__(256) lin_post_kernel(const bf16* __restrict__ 
       const float* E = sE + (c2 < D ? 0 : L * KLIN) + l * KLIN;
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll 8
-      for (int j = 0; j < KLIN; ++j) { a0 = fmaf(E[j], sG[j * D2 + c2], a0); a1 = fmaf(E[j], sG[j * D2 + c2 + 1], a1); }
+      for (int j = 0; j < KLIN; ++j) {
+        const float2 gv = *reinterpret_cast<const float2*>(sG + j * GP + c2);
+        a0 = fmaf(E[j], gv.x, a0); a1 = fmaf(E[j], gv.y, a1);
+      }
       const int col = c2 < D ? dkcol + c2 : dvcol + (c2 - D);
       *reinterpret_cast<uint32_t*>(dkv + ((long)b * NM + l) * lddkv + col) = pack2(a0, a1);
     }
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(256) lin_post_kernel(const bf16* __restrict__ 
       if (o < nout) {
         const int which = o / (L * KLIN), r = o % (L * KLIN), l = r / KLIN, j = r % KLIN;
         const float* xr = sX + l * D2 + which * D;
-        const float* gr = sG + j * D2 + which * D;
+        const float* gr = sG + j * GP + which * D;
         float a = 0.f;
         for (int c = 0; c < D; c += 4) {
           const float4 x = *reinterpret_cast<const float4*>(xr + c), gq = *reinterpret_cast<const float4*>(gr + c);
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(WARPS * 32) msda64_bwd_kernel(AttnP p, const b
   }
 }
 
-size_t lin_smem(int L, int D, bool post) { return ((size_t)2 * L * KLIN + (size_t)L * 2 * D + (post ? (size_t)KLIN * 2 * D : 0)) * sizeof(float); }
+size_t lin_smem(int L, int D, bool post) { return ((size_t)2 * L * KLIN + (size_t)L * 2 * D + (post ? (size_t)KLIN * (2 * D + 4) : 0)) * sizeof(float); }
 
 }  // namespace
 

@@ -202,6 +202,24 @@ __device__ __forceinline__ void stage_flush(const uint8_t* st, void* C, long ldc
   }
 }
 
+// bf16 flavour with a compile-time number of 16 B chunks per row (8 / 4 / 2 for 64 / 32 / 16 staged columns): fully
+// unrolled, one pointer bump per pass (the generic loop above spent more issue slots on index math than on the copies)
+template <int CPR>
+__device__ __forceinline__ void stage_flush_bf16(const uint8_t* st, void* C, long ldc, long row0, int M, int col0, int lane) {
+  constexpr int RPP = 32 / CPR;                                // rows covered per pass
+  const int r0 = lane / CPR, ch = lane % CPR;
+  const int nvalid = (int)min(32L, (long)M - row0);
+  uint8_t* gp = static_cast<uint8_t*>(C) + ((row0 + r0) * ldc + col0) * 2 + ch * 16;
+  const uint8_t* sp = st + r0 * EPI_ROWB + ch * 16;
+  const long gstep = (long)RPP * ldc * 2;
+#pragma unroll
+  for (int k = 0; k < CPR; ++k) {
+    if (r0 + k * RPP < nvalid) *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+    gp += gstep;
+    sp += RPP * EPI_ROWB;
+  }
+}
+
 // fp32 global [32 rows x gw cols] -> staging (row-contiguous reads)
 __device__ __forceinline__ void stage_fill_f32(uint8_t* st, const float* R, long ldr, long row0, int M, int col0, int gw, int lane) {
   const int cpr = gw / 4;                                      // 8 or 4
@@ -249,6 +267,8 @@ __device__ __forceinline__ void stage_read16(const uint8_t* my_row, int c, bool 
   }
 }
 
+// WIDE: the epilogue flavour is a compile-time choice (two instantiations) so that neither carries the other's registers
+template <bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, NtArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -272,7 +292,10 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS); }
     fence_barrier_init();
   }
-  for (int j = threadIdx.x; j < p.BN; j += NTHREADS) bias_s[j] = (p.e.bias && n0 + j < p.N) ? p.e.bias[n0 + j] : 0.f;
+  {   // WIDE: the bias is staged pre-multiplied by scale_pre so the epilogue is one FFMA per element
+    const float sp0 = (WIDE && p.e.scale_pre) ? *p.e.scale_pre : 1.f;
+    for (int j = threadIdx.x; j < p.BN; j += NTHREADS) bias_s[j] = (p.e.bias && n0 + j < p.N) ? p.e.bias[n0 + j] * sp0 : 0.f;
+  }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -332,8 +355,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const float s_res = e.scale_res ? *e.scale_res : 1.f;
     uint8_t* st = epi_stage + (warp - 2) * EPI_WARP_BYTES;
     uint8_t* my_row = st + lane * EPI_ROWB;
-    const bool use_resid = e.C2 && !e.gelu && e.resid;
-    const bool use_gmul = !use_resid && e.gmul != nullptr;
+    const bool use_resid = !WIDE && e.C2 && !e.gelu && e.resid;
+    const bool use_gmul = !WIDE && !use_resid && e.gmul != nullptr;
     const void* aux = use_resid ? e.resid : e.gmul;
     const long aux_ld = use_resid ? e.ldr : e.ldg;
     const bool aux_f32 = use_resid ? !e.r_bf16 : !e.g_bf16;
@@ -349,6 +372,64 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const long row0 = (long)mt * BM + quarter * 32;
       const long my_r = row0 + lane;                                      // this thread's output row
       const float rsc = scaled ? e.rowscale[min(my_r, (long)p.M - 1) / e.rows_per_img] : 1.f;
+      if (WIDE) {
+        // ---- plain bf16 output (most launches of a step): 64 columns per pass.  A staged row is then 128 B, so the flush
+        // reads whole rows per quarter-warp (no bank conflicts; the 32-column passes were 6-way conflicted, ncu) and writes
+        // 128 B contiguous per row, with half the passes / warp syncs.
+        int slot = 0, gw = 0;
+        for (int g = 0; g < ncols; g += gw, ++slot) {
+          const int rem = ncols - g;
+          gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+          if (slot % (EPI_WARPS / 4) != sub) continue;
+          const int nch = gw / 16;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {            // two 16-column chunks in flight at a time (register budget)
+            if (2 * h >= nch) break;
+            float v[2][16];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              if (2 * h + c < nch)
+                tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN + g + (2 * h + c) * 16), v[c]);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              if (2 * h + c < nch) {
+                const int cc = 2 * h + c;
+                tmem_ld_wait16(v[c]);
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + g + cc * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 b = bp[q];
+                  v[c][4 * q] = fmaf(v[c][4 * q], s_pre, b.x); v[c][4 * q + 1] = fmaf(v[c][4 * q + 1], s_pre, b.y);
+                  v[c][4 * q + 2] = fmaf(v[c][4 * q + 2], s_pre, b.z); v[c][4 * q + 3] = fmaf(v[c][4 * q + 3], s_pre, b.w);
+                }
+                if (masked) {
+                  const unsigned long long id8 = (unsigned long long)(my_r * p.N + n0 + g + cc * 16) >> 3;
+#pragma unroll
+                  for (int hh = 0; hh < 2; ++hh) {
+                    float k[8];
+                    drop_keep8(dst, id8 + hh, k);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[c][hh * 8 + j] *= k[j] * rsc;
+                  }
+                } else if (scaled) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[c][j] *= rsc;
+                }
+                stage_store16(my_row, cc, v[c], false);
+              }
+          }
+          __syncwarp();
+          if (gw == 64) stage_flush_bf16<8>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
+          else if (gw == 32) stage_flush_bf16<4>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
+          else stage_flush_bf16<2>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + acc);
+        if (++acc == 2) { acc = 0; aph ^= 1; }
+        continue;
+      }
       for (int g = sub * EPI_GROUP; g < ncols; g += (EPI_WARPS / 4) * EPI_GROUP) {
         const int gw = min(EPI_GROUP, ncols - g), nch = gw / 16;
         float v[2][16], r[2][16];
@@ -678,9 +759,12 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
   p.stages = p.BN > 208 ? 3 : STAGES;
   const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2) + 256 + EPI_WARPS * EPI_WARP_BYTES + 1024;
   QV_CHECK(smem <= 227 * 1024, "tc_gemm_nt: BN=%d needs %zu B of shared memory", p.BN, smem);
-  QV_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // plain bf16 output -> the 64-column epilogue
+  const bool wide = e.C && !e.C2 && !e.c_f32 && !e.c_accum && !e.gmul;
+  auto kern = wide ? tc_gemm_nt_kernel<true> : tc_gemm_nt_kernel<false>;
+  QV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gx = max(1, min(p.m_tiles, qv_num_sms() / p.n_slices));
-  tc_gemm_nt_kernel<<<dim3(gx, p.n_slices), NTHREADS, smem, s>>>(ma, mw, p);
+  kern<<<dim3(gx, p.n_slices), NTHREADS, smem, s>>>(ma, mw, p);
   QV_LAUNCH_CHECK();
   return 0;
 }
