@@ -59,6 +59,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// smem (128 B-swizzled box) -> global, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -149,6 +159,7 @@ struct NtArgs {
   int m_tiles;
   uint32_t tmem_cols;
   int stages;      // depth of the TMA ring (4; 3 for the widest tiles so staging still fits)
+  int tma_store;   // wide epilogue: 64-column groups leave through a TMA store (map_c valid)
   GemmEpi e;
 };
 
@@ -270,7 +281,8 @@ __device__ __forceinline__ void stage_read16(const uint8_t* my_row, int c, bool 
 // WIDE: the epilogue flavour is a compile-time choice (two instantiations) so that neither carries the other's registers
 template <bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, NtArgs p) {
+tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                  const __grid_constant__ CUtensorMap map_c, NtArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int STG = p.stages;
@@ -278,7 +290,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STG * stage_bytes);
   uint64_t *full = bars, *empty = bars + STG, *tfull = bars + 2 * STG, *tempty = bars + 2 * STG + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STG + 4);
-  uint8_t* epi_stage = smem + STG * stage_bytes + 256;
+  uint8_t* epi_stage = smem + STG * stage_bytes + 1024;   // 1024-aligned: the TMA-store staging of the wide epilogue is swizzled
   float* bias_s = reinterpret_cast<float*>(epi_stage + EPI_WARPS * EPI_WARP_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,6 +300,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
+    if (WIDE && p.tma_store) tma_prefetch_desc(&map_c);
     for (int s = 0; s < STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS); }
     fence_barrier_init();
@@ -364,6 +377,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const bool masked = e.drop.p > 0.f, scaled = e.rowscale != nullptr;   // dropout site / DropPath scale on the output
     DropState dst{};
     if (masked) dst = drop_state(e.drop);
+    int ngroups = 0;                                         // column groups of the wide epilogue: 64 | 32 | 16 wide
+    for (int g = 0; g < ncols; ++ngroups) { const int rem = ncols - g; g += rem >= 64 ? 64 : (rem >= 32 ? 32 : 16); }
     int acc = 0;
     uint32_t aph = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
@@ -377,11 +392,20 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // reads whole rows per quarter-warp (no bank conflicts; the 32-column passes were 6-way conflicted, ncu) and writes
         // 128 B contiguous per row, with half the passes / warp syncs.
         int slot = 0, gw = 0;
+        bool released = false;
         for (int g = 0; g < ncols; g += gw, ++slot) {
           const int rem = ncols - g;
           gw = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
           if (slot % (EPI_WARPS / 4) != sub) continue;
           const int nch = gw / 16;
+          const bool via_tma = p.tma_store && gw == 64;
+          // staging: [32 rows][128 B] swizzled like a SWIZZLE_128B box (16 B chunk j of row r at j ^ (r & 7)) for the TMA
+          // store, or the padded row-major buffer of the flush loops
+          uint8_t* tb = st + ((warp & 1) ? 512 : 0);              // warp regions are 4608 B apart: this is 1024-aligned
+          if (via_tma) {
+            if (lane == 0) tma_store_wait_read();                  // the previous store has finished reading the buffer
+            __syncwarp();
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {            // two 16-column chunks in flight at a time (register budget)
             if (2 * h >= nch) break;
@@ -415,18 +439,47 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                   for (int j = 0; j < 16; ++j) v[c][j] *= rsc;
                 }
-                stage_store16(my_row, cc, v[c], false);
+                if (via_tma) {
+                  uint32_t pk[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    __nv_bfloat162 hv = __floats2bfloat162_rn(v[c][2 * j], v[c][2 * j + 1]);
+                    pk[j] = *reinterpret_cast<uint32_t*>(&hv);
+                  }
+                  uint8_t* rowp = tb + lane * 128;
+                  *reinterpret_cast<uint4*>(rowp + (((2 * cc) ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  *reinterpret_cast<uint4*>(rowp + (((2 * cc + 1) ^ (lane & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                } else {
+                  stage_store16(my_row, cc, v[c], false);
+                }
               }
           }
-          __syncwarp();
-          if (gw == 64) stage_flush_bf16<8>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
-          else if (gw == 32) stage_flush_bf16<4>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
-          else stage_flush_bf16<2>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
-          __syncwarp();
+          if (slot + EPI_WARPS / 4 >= ngroups) {   // this warp's last TMEM read of the tile: hand the accumulator back now,
+            tc_fence_before();                     // before the stores (the MMA of tile + 2 can start during them)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+            released = true;
+          }
+          if (via_tma) {
+            fence_proxy_async();                   // generic-proxy smem writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_c, tb, n0 + g, (int)row0);
+              tma_store_commit();
+            }
+          } else {
+            __syncwarp();
+            if (gw == 64) stage_flush_bf16<8>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
+            else if (gw == 32) stage_flush_bf16<4>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
+            else stage_flush_bf16<2>(st, e.C, e.ldc, row0, p.M, n0 + g, lane);
+            __syncwarp();
+          }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty + acc);
+        if (!released) {                           // a warp with no column group in this tile still has to arrive
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty + acc);
+        }
         if (++acc == 2) { acc = 0; aph ^= 1; }
         continue;
       }
@@ -506,6 +559,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (++acc == 2) { acc = 0; aph ^= 1; }
     }
   }
+  if (WIDE && warp >= 2 && lane == 0) tma_store_wait_all();   // outstanding TMA stores of this warp
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
@@ -757,14 +811,17 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
                (!e.gmul || (e.ldg % (e.g_bf16 ? 8 : 4) == 0 && ((uintptr_t)e.gmul & 15) == 0)),
            "tc_gemm_nt: outputs / residual must be 16 B aligned with 16 B-multiple row pitch");
   p.stages = p.BN > 208 ? 3 : STAGES;
-  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2) + 256 + EPI_WARPS * EPI_WARP_BYTES + 1024;
+  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2) + 1024 + EPI_WARPS * EPI_WARP_BYTES + 1024;
   QV_CHECK(smem <= 227 * 1024, "tc_gemm_nt: BN=%d needs %zu B of shared memory", p.BN, smem);
   // plain bf16 output -> the 64-column epilogue
   const bool wide = e.C && !e.C2 && !e.c_f32 && !e.c_accum && !e.gmul;
   auto kern = wide ? tc_gemm_nt_kernel<true> : tc_gemm_nt_kernel<false>;
+  CUtensorMap mc = ma;
+  p.tma_store = wide && N >= 64;
+  if (p.tma_store) QV_TRY(make_map(&mc, static_cast<const bf16*>(e.C), M, N, e.ldc, 32));   // box = 32 rows x 64 columns
   QV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gx = max(1, min(p.m_tiles, qv_num_sms() / p.n_slices));
-  kern<<<dim3(gx, p.n_slices), NTHREADS, smem, s>>>(ma, mw, p);
+  kern<<<dim3(gx, p.n_slices), NTHREADS, smem, s>>>(ma, mw, mc, p);
   QV_LAUNCH_CHECK();
   return 0;
 }
