@@ -108,6 +108,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_step_rate(sample_b, steps, warmup, threads=None, dropout=0.0, drop_path=0.0):
     """The reference training step (CPU restatement, fp32, AdamW + clips) on `sample_b` images; images/sec.
     dropout / drop_path > 0: Bernoulli masks drawn per step for every site, like the reference's nn.Dropout / SDPA."""
@@ -147,8 +154,9 @@ def run_reference(args):
     if rank != 0:
         return
     sample = 256
-    rate, dt, cores = cpu_step_rate(sample, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)), dropout=args.dropout,
-                                    drop_path=args.drop_path)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can
+    rate, dt, cores = cpu_step_rate(sample, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)), threads=host_threads(),
+                                    dropout=args.dropout, drop_path=args.drop_path)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
         "steps": max(1, min(args.steps, 8)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
@@ -353,7 +361,7 @@ def run_ours(args):
         roof["step_frac_of_sustained_peak"] = roof["step_tflops_fmin"] / tf_sus
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.workload == "hqavit_c100" and not infer:
-            rate, dt, cores = cpu_step_rate(256, 8, 1, dropout=args.dropout, drop_path=args.drop_path)
+            rate, dt, cores = cpu_step_rate(256, 8, 1, threads=host_threads(), dropout=args.dropout, drop_path=args.drop_path)
             cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                    "sample": f"256 images/step x 8 steps ({8 * dt:.1f} s of CPU work), fp32 oracle port, fwd+bwd+clip+AdamW"}
         default = args.workload == "hqavit_c100" and not infer
