@@ -142,11 +142,14 @@ __device__ __forceinline__ void store_vec(bf16* p, const float* v) {
 }
 
 // ---------------------------------------------------------------- counter-based dropout masks
-// Philox4x32-10: 4 x 32 random bits for (key, counter); stateless, so forward and backward regenerate the same
-// dropout mask from (seed, offset, site, element id) instead of storing it.
+// Philox4x32-7: 4 x 32 random bits for (key, counter); stateless, so forward and backward regenerate the same
+// dropout mask from (seed, offset, site, element id) instead of storing it.  7 rounds is the smallest Crush-resistant
+// variant of Salmon et al. (SC'11, table 2; 10 is the conservative default): the dependent multiply chain sits in the
+// latency-bound GEMM epilogue warps, so its length is paid almost fully.  tests/dropout_masks.py mirrors the constant.
+constexpr int QV_PHILOX_ROUNDS = 7;
 __device__ __forceinline__ uint4 philox4x32(uint2 key, uint4 ctr) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < QV_PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);

@@ -13,6 +13,7 @@
 // Descriptor bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables.
 #include <cuda.h>
 
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace {
@@ -817,7 +818,11 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
   const bool wide = e.C && !e.C2 && !e.c_f32 && !e.c_accum && !e.gmul;
   auto kern = wide ? tc_gemm_nt_kernel<true> : tc_gemm_nt_kernel<false>;
   CUtensorMap mc = ma;
-  p.tma_store = wide && N >= 64;
+  // TMA-store epilogue only where a CTA streams enough tiles to amortise the store drain at kernel end (measured: the
+  // 12-tile qkv projection gains 6 %, the 4-tile N = 192 projections lose 6 %); QV_TMA_STORE=0/1 forces it for A/B runs
+  static const int force = [] { const char* v = getenv("QV_TMA_STORE"); return v ? atoi(v) : -1; }();
+  const int tiles_per_cta = p.m_tiles * p.n_slices / max(1, min(p.m_tiles * p.n_slices, qv_num_sms()));
+  p.tma_store = wide && N >= 64 && (force >= 0 ? force != 0 : tiles_per_cta >= 8);
   if (p.tma_store) QV_TRY(make_map(&mc, static_cast<const bf16*>(e.C), M, N, e.ldc, 32));   // box = 32 rows x 64 columns
   QV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gx = max(1, min(p.m_tiles, qv_num_sms() / p.n_slices));

@@ -10,13 +10,14 @@ import torch
 
 DS_ATT, DS_PROJ, DS_B1, DS_B2, DS_FFN, DS_PATH = 1, 5, 9, 10, 11, 12
 M32 = np.uint64(0xFFFFFFFF)
+PHILOX_ROUNDS = 7
 
 
 def philox4x32(key0, key1, c0, c1, c2, c3):
-    """Philox4x32-10 on uint64 numpy arrays holding 32-bit values (broadcastable)."""
+    """Philox4x32-7 (QV_PHILOX_ROUNDS in common.cuh) on uint64 numpy arrays holding 32-bit values (broadcastable)."""
     c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint64) & M32 for c in np.broadcast_arrays(c0, c1, c2, c3)]
     k0, k1 = np.uint64(key0 & 0xFFFFFFFF), np.uint64(key1 & 0xFFFFFFFF)
-    for _ in range(10):
+    for _ in range(PHILOX_ROUNDS):
         p0 = np.uint64(0xD2511F53) * c0
         p1 = np.uint64(0xCD9E8D57) * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & M32

@@ -1,6 +1,6 @@
 """Train-mode dropout / DropPath of the quad block (H:256-264, 416-465, 648-656, 697-710, 1066-1083) through the C ABI.
 
-The kernels draw their masks from a counter-based generator (Philox4x32-10 keyed by {seed, offset, site, element id}), so
+The kernels draw their masks from a counter-based generator (Philox4x32-7 keyed by {seed, offset, site, element id}), so
 the masks are a pure function that `tests/dropout_masks.py` restates on the host; the oracle takes those masks as explicit
 keep-scale tensors.  That turns the dropout run into an element-wise parity test: fp32 run 1e-4 on the block output and
 gradients (same gates as the dropout-free block test), bf16 run at the bf16 gates -- plus rate / unbiasedness / replay
