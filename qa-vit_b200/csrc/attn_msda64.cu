@@ -162,6 +162,162 @@ __global__ void __launch_bounds__(256) lin_post_kernel(const bf16* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core pre / post
+// Same contractions on mma.sync for L <= 48 pooled rows (every shipped 64-token configuration has L = 40): the SIMT
+// kernels above were shared-memory bound (lin_post 17 % of the QAViTv2 step).  One CTA (4 warps) per image, grid-stride;
+// warp w owns columns [96 w, 96 w + 96) of the [K | V] = 2 D = 384 wide matrices, i.e. warps 0-1 the K half, 2-3 the V half.
+constexpr int LPAD = 48;              // pooled rows padded to a multiple of 16 (zero rows)
+constexpr int PX = 2 * WARPS * HD + 8;   // pitch (bf16) of the 384-wide staged matrices: 784 B rows, 16 B aligned, 4-bank skew
+constexpr int PEL = 40;               // pitch of the staged E matrices [LPAD][32]
+constexpr int WCOLS = 96;             // columns per warp
+
+struct LinSmem {
+  static constexpr int E = 0, X = E + 2 * LPAD * PEL, G = X + LPAD * PX, END_PRE = G, END_POST = G + KLIN * PX;
+};
+
+__device__ __forceinline__ void lin_stage_E(bf16* sE, const float* Ek, const float* Ev, int L) {
+  for (int i = threadIdx.x; i < 2 * LPAD * KLIN; i += blockDim.x) {
+    const int which = i / (LPAD * KLIN), r = i % (LPAD * KLIN), l = r / KLIN, j = r % KLIN;
+    sE[which * LPAD * PEL + l * PEL + j] = __float2bfloat16_rn(l < L ? (which ? Ev : Ek)[l * KLIN + j] : 0.f);
+  }
+}
+// Ks | Vs rows of image b -> [LPAD][PX] (rows >= L zero)
+__device__ __forceinline__ void lin_stage_X(bf16* sX, const bf16* kv, int ldkv, int kcol, int vcol, int NM, int L, int D, int b) {
+  const int cpr = 2 * D / 8;
+  for (int i = threadIdx.x; i < LPAD * cpr; i += blockDim.x) {
+    const int l = i / cpr, c = (i % cpr) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (l < L) v = *reinterpret_cast<const uint4*>(kv + ((long)b * NM + l) * ldkv + (c < D ? kcol + c : vcol + (c - D)));
+    *reinterpret_cast<uint4*>(sX + l * PX + c) = v;
+  }
+}
+
+// pre[b, j, c] = sum_l E[l, j] X[l, c]
+__global__ void __launch_bounds__(WARPS * 32) lin_pre_mma_kernel(const bf16* __restrict__ kv, int ldkv, int kcol, int vcol, int NM, int L,
+                                                                 const float* __restrict__ Ek, const float* __restrict__ Ev, int B,
+                                                                 bf16* __restrict__ pre) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sm = reinterpret_cast<bf16*>(smraw);
+  bf16 *sE = sm + LinSmem::E, *sX = sm + LinSmem::X;
+  constexpr int D = WARPS * HD, D2 = 2 * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int c0 = warp * WCOLS;
+  const bf16* E = sE + (c0 >= D ? LPAD * PEL : 0);
+  lin_stage_E(sE, Ek, Ev, L);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    lin_stage_X(sX, kv, ldkv, kcol, vcol, NM, L, D, b);
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < KLIN / 16; ++mt) {
+      float acc[WCOLS / 8][4];
+#pragma unroll
+      for (int n = 0; n < WCOLS / 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < LPAD / 16; ++kk) {
+        uint32_t a[4];
+        ldAt(a, E, PEL, mt * 16, kk * 16, lane);                       // A(m = j, k = l) = E[l][j]
+#pragma unroll
+        for (int np = 0; np < WCOLS / 16; ++np) {
+          uint32_t bb[4];
+          ldBt(bb, sX, PX, c0 + np * 16, kk * 16, lane);               // B(k = l, n = c) = X[l][c]
+          mma16816(acc[2 * np], a, bb[0], bb[1]);
+          mma16816(acc[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+      bf16* dst = pre + ((long)b * KLIN + mt * 16) * D2 + c0;
+#pragma unroll
+      for (int n = 0; n < WCOLS / 8; ++n) {
+        *reinterpret_cast<uint32_t*>(dst + (long)g * D2 + n * 8 + 2 * t) = pack2(acc[n][0], acc[n][1]);
+        *reinterpret_cast<uint32_t*>(dst + (long)(g + 8) * D2 + n * 8 + 2 * t) = pack2(acc[n][2], acc[n][3]);
+      }
+    }
+  }
+}
+
+// dkv[b * NM + l, c] = sum_j E[l, j] dpre[b, j, c];  dE[l, j] += sum_{b, c in half} X[l, c] dpre[b, j, c]
+__global__ void __launch_bounds__(WARPS * 32) lin_post_mma_kernel(const bf16* __restrict__ kv, int ldkv, int kcol, int vcol, int NM, int L,
+                                                                  const float* __restrict__ Ek, const float* __restrict__ Ev, int B,
+                                                                  const float* __restrict__ dpre, bf16* __restrict__ dkv, int lddkv,
+                                                                  int dkcol, int dvcol, float* __restrict__ dEk, float* __restrict__ dEv) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sm = reinterpret_cast<bf16*>(smraw);
+  bf16 *sE = sm + LinSmem::E, *sX = sm + LinSmem::X, *sG = sm + LinSmem::G;
+  constexpr int D = WARPS * HD, D2 = 2 * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int c0 = warp * WCOLS, which = c0 >= D ? 1 : 0;
+  const bf16* E = sE + which * LPAD * PEL;
+  lin_stage_E(sE, Ek, Ev, L);
+  float dEacc[LPAD / 16][KLIN / 8][4];   // this warp's share of dE_k (warps 0-1) or dE_v (warps 2-3): its 96 channels, all images
+#pragma unroll
+  for (int m = 0; m < LPAD / 16; ++m)
+#pragma unroll
+    for (int n = 0; n < KLIN / 8; ++n) dEacc[m][n][0] = dEacc[m][n][1] = dEacc[m][n][2] = dEacc[m][n][3] = 0.f;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    lin_stage_X(sX, kv, ldkv, kcol, vcol, NM, L, D, b);
+    for (int i = threadIdx.x; i < KLIN * D2 / 4; i += blockDim.x) {     // dpre fp32 -> bf16 [32][PX]
+      const int j = (i * 4) / D2, c = (i * 4) % D2;
+      const float4 v = *reinterpret_cast<const float4*>(dpre + (long)b * KLIN * D2 + i * 4);
+      *reinterpret_cast<uint2*>(sG + j * PX + c) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+    }
+    __syncthreads();
+    // ---- dKs / dVs: M = l (LPAD), N = this warp's 96 columns, K = j (32)
+#pragma unroll
+    for (int mt = 0; mt < LPAD / 16; ++mt) {
+      float acc[WCOLS / 8][4];
+#pragma unroll
+      for (int n = 0; n < WCOLS / 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KLIN / 16; ++kk) {
+        uint32_t a[4];
+        ldA(a, E, PEL, mt * 16, kk * 16, lane);                        // A(m = l, k = j) = E[l][j]
+#pragma unroll
+        for (int np = 0; np < WCOLS / 16; ++np) {
+          uint32_t bb[4];
+          ldBt(bb, sG, PX, c0 + np * 16, kk * 16, lane);               // B(k = j, n = c) = dpre[j][c]
+          mma16816(acc[2 * np], a, bb[0], bb[1]);
+          mma16816(acc[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+      const int l0 = mt * 16 + g, l1 = l0 + 8;
+      const int col = (which ? dvcol + (c0 - D) : dkcol + c0);
+      bf16* d0 = dkv + ((long)b * NM + l0) * lddkv + col;
+      bf16* d1 = dkv + ((long)b * NM + l1) * lddkv + col;
+#pragma unroll
+      for (int n = 0; n < WCOLS / 8; ++n) {
+        if (l0 < L) *reinterpret_cast<uint32_t*>(d0 + n * 8 + 2 * t) = pack2(acc[n][0], acc[n][1]);
+        if (l1 < L) *reinterpret_cast<uint32_t*>(d1 + n * 8 + 2 * t) = pack2(acc[n][2], acc[n][3]);
+      }
+    }
+    // ---- dE partial over this warp's 96 channels: M = l, N = j (32), K = c (96)
+#pragma unroll
+    for (int kk = 0; kk < WCOLS / 16; ++kk) {
+      uint32_t bb[2][4];
+      ldB(bb[0], sG, PX, 0, c0 + kk * 16, lane);                        // B(n = j, k = c) = dpre[j][c]
+      ldB(bb[1], sG, PX, 16, c0 + kk * 16, lane);
+#pragma unroll
+      for (int mt = 0; mt < LPAD / 16; ++mt) {
+        uint32_t a[4];
+        ldA(a, sX, PX, mt * 16, c0 + kk * 16, lane);                    // A(m = l, k = c) = X[l][c]
+        mma16816(dEacc[mt][0], a, bb[0][0], bb[0][1]);
+        mma16816(dEacc[mt][1], a, bb[0][2], bb[0][3]);
+        mma16816(dEacc[mt][2], a, bb[1][0], bb[1][1]);
+        mma16816(dEacc[mt][3], a, bb[1][2], bb[1][3]);
+      }
+    }
+  }
+  float* dE = which ? dEv : dEk;
+#pragma unroll
+  for (int mt = 0; mt < LPAD / 16; ++mt)
+#pragma unroll
+    for (int n = 0; n < KLIN / 8; ++n) {
+      const int l0 = mt * 16 + g, l1 = l0 + 8, j = n * 8 + 2 * t;
+      if (l0 < L) { atomicAdd(dE + l0 * KLIN + j, dEacc[mt][n][0]); atomicAdd(dE + l0 * KLIN + j + 1, dEacc[mt][n][1]); }
+      if (l1 < L) { atomicAdd(dE + l1 * KLIN + j, dEacc[mt][n][2]); atomicAdd(dE + l1 * KLIN + j + 1, dEacc[mt][n][3]); }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ attention
 struct WS {   // per-warp bf16 regions
   static constexpr int Q = 0, DO = Q + NQ * PT, KF = DO + NQ * PT, VF = KF + NKV * PT, P = VF + NKV * PT, DS = P + NQ * PT;
@@ -440,8 +596,20 @@ bool attn_msda64_ok(const AttnP& p) {
 }
 size_t attn_msda64_scratch_bytes(int B, int D) { return (size_t)B * KLIN * 2 * D * (2 + 4) + 512; }
 
+static bool lin_mma_ok(const AttnP& p) {
+  return p.L <= LPAD && p.ldkv % 8 == 0 && p.kcol % 8 == 0 && p.vcol % 8 == 0 && p.lddkv % 2 == 0 && p.dkcol % 2 == 0 && p.dvcol % 2 == 0;
+}
+
 static int run_pre(cudaStream_t s, const AttnP& p, bf16* pre) {
   const int D = p.H * HD;
+  if (lin_mma_ok(p)) {
+    const size_t smem = (size_t)LinSmem::END_PRE * sizeof(bf16);
+    QV_CUDA(cudaFuncSetAttribute(lin_pre_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lin_pre_mma_kernel<<<max(1, min(p.B, qv_num_sms() * 4)), WARPS * 32, smem, s>>>((const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L,
+                                                                                 p.Ek, p.Ev, p.B, pre);
+    QV_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = lin_smem(p.L, D, false);
   QV_CHECK(smem <= 200 * 1024, "msda64: Linformer staging needs %zu B of shared memory", smem);
   QV_CUDA(cudaFuncSetAttribute(lin_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -479,6 +647,14 @@ int attn_msda64_bwd(cudaStream_t s, const AttnP& p, void* scratch) {
   const int occ = max(1, min(2, (int)(200 * 1024 / (smem + 1024))));
   msda64_bwd_kernel<<<min(cdiv(ntask, WARPS), qv_num_sms() * occ), WARPS * 32, smem, s>>>(p, pre, dpre, ntask);
   QV_LAUNCH_CHECK();
+  if (lin_mma_ok(p)) {
+    const size_t smem2 = (size_t)LinSmem::END_POST * sizeof(bf16);
+    QV_CUDA(cudaFuncSetAttribute(lin_post_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    lin_post_mma_kernel<<<max(1, min(p.B, qv_num_sms() * 3)), WARPS * 32, smem2, s>>>(
+        (const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L, p.Ek, p.Ev, p.B, dpre, (bf16*)p.dkv, p.lddkv, p.dkcol, p.dvcol, p.dEk, p.dEv);
+    QV_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem2 = lin_smem(p.L, D, true);
   QV_CHECK(smem2 <= 200 * 1024, "msda64: Linformer backward staging needs %zu B of shared memory", smem2);
   QV_CUDA(cudaFuncSetAttribute(lin_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
