@@ -17,14 +17,18 @@ if a.model == "hqavit":
     if a.dropout == 0.0:
         for n in ("fuse2", "fuse3", "fuse4"):
             getattr(model, n).cat_mlp[3].p = 0.0
+elif a.model == "tinyin":
+    model = Q.HQAViT(Q.HQAViTConfig(img_size=64, num_classes=200, depth=12, num_learned_tokens=64, dropout=a.dropout, drop_path=a.drop_path),
+                     stage_depths=(2, 2, 6, 2), square_tokens=True)
 else:
     model = Q.QAViT(Q.QAViTConfig(dropout=a.dropout, drop_path=a.drop_path))
 model = model.cuda().train().set_precision("bf16")
 opt = Q.FusedAdamW(model.named_parameters(), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06, max_grad_norm=0.5)
 nograd = ("swa.norm.", "msda.norm.", "cga.norm.", "write_norm.", "write_compression.", "write_gate.")
 opt.set_grad_mask([not any(s in n for s in nograd) for n, _ in model.named_parameters()])
-x = torch.randn(a.batch, 3, 32, 32, device="cuda")
-y = torch.randint(0, 100, (a.batch,), device="cuda")
+S, NC = (64, 200) if a.model == "tinyin" else (32, 100)
+x = torch.randn(a.batch, 3, S, S, device="cuda")
+y = torch.randint(0, NC, (a.batch,), device="cuda")
 
 def step():
     opt.zero_grad()
