@@ -239,6 +239,12 @@ int tlm_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, in
 int tlm_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx);
 int upm_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W, const float* bias, float* up);
 int upm_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int C, const float* W, float* dxc, float* dW, float* dbias);
+bool tokens_mma64_ok(int M, int N, int C);   // 32 .. 64 learned tokens, <= 256 stream tokens
+int tlm64_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, int M, int C, float* S, float* xc);
+int tlm64_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int M, int C, void* dlogits, float* dx);
+int upm64_fwd(cudaStream_t s, const float* xc, int B, int N, int M, int C, const float* W, const float* bias, float* up);
+int upm64_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int M, int C, const float* W, float* dxc, float* dW,
+              float* dbias);
 bool bank_write_mma_ok(int Nt, int d, int kb, int ldcg);
 int bank_write_reduce_mma(cudaStream_t s, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, float* partial, int* n_partial);
 // register-blocked flavours for 16 learned tokens (tokens.cu)

@@ -756,6 +756,7 @@ int token_learner_fwd(cudaStream_t s, int dt, const float* x, const void* logits
                       float* xc) {
   if (B <= 0) return 0;
   if (dt == QV_BF16 && tokens_mma_ok(M, N, C)) return tlm_fwd(s, x, logits, B, N, C, S, xc);
+  if (dt == QV_BF16 && tokens_mma64_ok(M, N, C)) return tlm64_fwd(s, x, logits, B, N, M, C, S, xc);
   if (tokens16_ok(M, C)) return tl16_fwd(s, dt, x, logits, B, N, C, S, xc);
   QV_CHECK(M % 16 == 0, "token_learner: M=%d must be a multiple of 16", M);
   const size_t smem = (size_t)N * M * sizeof(float);
@@ -769,6 +770,7 @@ int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, co
                       int C, void* dlogits, float* dx) {
   if (B <= 0) return 0;
   if (dt == QV_BF16 && tokens_mma_ok(M, N, C)) return tlm_bwd(s, x, S, dxc, B, N, C, dlogits, dx);
+  if (dt == QV_BF16 && tokens_mma64_ok(M, N, C)) return tlm64_bwd(s, x, S, dxc, B, N, M, C, dlogits, dx);
   if (tokens16_ok(M, C)) return tl16_bwd(s, dt, x, S, dxc, B, N, C, dlogits, dx);
   QV_CHECK(C <= 256, "token_learner_bwd: C=%d > 256", C);
   const size_t smem = (size_t)(2 * N * M + M * (C + 1) + M) * sizeof(float);
@@ -781,6 +783,7 @@ int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, co
 int token_upmix_fwd(cudaStream_t s, int dt, const float* xc, int B, int M, int N, int C, const float* W, const float* bias, float* up) {
   if (B <= 0) return 0;
   if (dt == QV_BF16 && tokens_mma_ok(M, N, C)) return upm_fwd(s, xc, B, N, C, W, bias, up);
+  if (dt == QV_BF16 && tokens_mma64_ok(M, N, C)) return upm64_fwd(s, xc, B, N, M, C, W, bias, up);
   if (tokens16_ok(M, C)) return up16_fwd(s, xc, B, N, C, W, bias, up);
   const size_t smem = (size_t)(N * M + M * C) * sizeof(float);
   QV_TRY(opt_in_smem(token_upmix_fwd_kernel, smem));
@@ -792,6 +795,7 @@ int token_upmix_bwd(cudaStream_t s, int dt, const float* xc, const float* dup, i
                     float* dxc, float* dW, float* dbias) {
   if (B <= 0) return 0;
   if (dt == QV_BF16 && tokens_mma_ok(M, N, C)) return upm_bwd(s, xc, dup, B, N, C, W, dxc, dW, dbias);
+  if (dt == QV_BF16 && tokens_mma64_ok(M, N, C)) return upm64_bwd(s, xc, dup, B, N, M, C, W, dxc, dW, dbias);
   if (tokens16_ok(M, C)) return up16_bwd(s, xc, dup, B, N, C, W, dxc, dW, dbias);
   QV_CHECK(N % 16 == 0, "token_upmix_bwd: N=%d must be a multiple of 16", N);
   const size_t smem = (size_t)(N * M + M * (C + 1) + 16 * (C + 1)) * sizeof(float);

@@ -393,6 +393,315 @@ __global__ void __launch_bounds__(NWARP * 32) upm_bwd_kernel(const float* __rest
   }
 }
 
+// ============================================================================================== 32 / 48 / 64 learned tokens
+// The same four products for MS = 16 m learned tokens (m <= 4) and up to 256 stream tokens -- HQAViT-TinyImageNet has
+// 64 / 256 -- where the one-tile kernels above do not fit (their SIMT stand-ins were 58 % of the TinyImageNet step).  The
+// slot dimension becomes a loop (K loop in the dx / up products, M loop in the xc / dxc products); the stream tile is staged
+// in two channel halves where the split-precision copy (or the fp32 dW accumulator) would not fit next to it.
+constexpr int MAXS = 64;              // learned tokens
+constexpr int MSP = MAXS + 8;         // pitch (bf16) of the [N][MS] matrices: 144 B rows
+constexpr int MAXN = 256;             // stream tokens
+
+// fp32 global rows (row stride ld, columns [c0, c0 + cols)) -> bf16 hi (/ lo) tiles [rows][pitch]
+template <bool HL>
+__device__ __forceinline__ void tile_to_bf16_cols(bf16* dhi, bf16* dlo, int pitch, const float* __restrict__ src, int rows, int ld, int c0,
+                                                  int cols) {
+  const int c4n = cols / 4, total = rows * c4n;
+  for (int base = 0; base < total; base += 8 * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * blockDim.x + threadIdx.x;
+      if (i < total) v[u] = *reinterpret_cast<const float4*>(src + (long)(i / c4n) * ld + c0 + (i % c4n) * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = base + u * blockDim.x + threadIdx.x;
+      if (i < total) {
+        uint32_t h0, l0, h1, l1;
+        split2(v[u].x, v[u].y, &h0, &l0);
+        split2(v[u].z, v[u].w, &h1, &l1);
+        const int o = (i / c4n) * pitch + (i % c4n) * 4;
+        *reinterpret_cast<uint2*>(dhi + o) = make_uint2(h0, h1);
+        if (HL) *reinterpret_cast<uint2*>(dlo + o) = make_uint2(l0, l1);
+      }
+    }
+  }
+}
+
+// ---- TokenLearner forward: xc[MS, C] = softmax_tokens(logits)^T x          (split-precision operands)
+__global__ void __launch_bounds__(NWARP * 32) tlm64_fwd_kernel(const float* __restrict__ x, const bf16* __restrict__ logits, int B, int N,
+                                                               int MS, int C, float* __restrict__ Sout, float* __restrict__ xc) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int CH = C / 2, XPc = CH + 8;
+  bf16* S = reinterpret_cast<bf16*>(smraw);                    // [N][MSP] hi, lo
+  bf16* SL = S + (size_t)N * MSP;
+  uint8_t* U = reinterpret_cast<uint8_t*>(SL + (size_t)N * MSP);
+  float* F = reinterpret_cast<float*>(U);                      // [N][MS] fp32 logits / exp (dead before X is staged)
+  bf16* X = reinterpret_cast<bf16*>(U);                        // [N][XPc] hi, lo: one channel half
+  bf16* XL = X + (size_t)N * XPc;
+  const size_t ubytes = max((size_t)N * MS * 4, (size_t)2 * N * XPc * 2);
+  float* R = reinterpret_cast<float*>(U + ((ubytes + 15) & ~(size_t)15));   // [8][16]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int c16 = tid % M16, part = tid / M16;                 // softmax: 8 threads per slot, 16 slots per pass
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < N * MS; i += blockDim.x) F[i] = __bfloat162float(logits[(long)b * N * MS + i]);
+    __syncthreads();
+    for (int sg = 0; sg < MS / 16; ++sg) {
+      const int col = sg * 16 + c16;
+      float mx = -INFINITY;
+      for (int n = part; n < N; n += 8) mx = fmaxf(mx, F[n * MS + col]);
+      R[part * M16 + c16] = mx;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mx = fmaxf(mx, R[k * M16 + c16]);
+      float z = 0.f;
+      for (int n = part; n < N; n += 8) { const float e = __expf(F[n * MS + col] - mx); F[n * MS + col] = e; z += e; }
+      __syncthreads();
+      R[part * M16 + c16] = z;
+      __syncthreads();
+      z = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) z += R[k * M16 + c16];
+      z = 1.f / z;
+      for (int n = part; n < N; n += 8) {
+        const float sv = F[n * MS + col] * z;
+        Sout[(long)b * N * MS + n * MS + col] = sv;
+        store_split<true>(S, SL, n * MSP + col, sv);
+      }
+      __syncthreads();
+    }
+    for (int ch = 0; ch < 2; ++ch) {
+      __syncthreads();                                         // previous half consumed (and F dead)
+      tile_to_bf16_cols<true>(X, XL, XPc, x + (long)b * N * C, N, C, ch * CH, CH);
+      __syncthreads();
+      const int npair = CH / 16;
+      for (int item = warp; item < (MS / 16) * npair; item += NWARP) {
+        const int ms = item / npair, pair = item % npair;
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int ks = 0; ks < N / 16; ++ks) {
+          uint32_t a[4], al[4], bb[4], bl[4];
+          ldAt(a, S, MSP, ms * 16, ks * 16, lane);             // A(m = slot, k = token) = S[token][slot]
+          ldAt(al, SL, MSP, ms * 16, ks * 16, lane);
+          ldBt(bb, X, XPc, pair * 16, ks * 16, lane);          // B(k = token, n = channel)
+          ldBt(bl, XL, XPc, pair * 16, ks * 16, lane);
+          mma3<true>(acc[0], a, al, bb[0], bb[1], bl[0], bl[1]);
+          mma3<true>(acc[1], a, al, bb[2], bb[3], bl[2], bl[3]);
+        }
+        float* o = xc + ((long)b * MS + ms * 16) * C + ch * CH + pair * 16 + 2 * t;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          *reinterpret_cast<float2*>(o + (long)g * C + h * 8) = make_float2(acc[h][0], acc[h][1]);
+          *reinterpret_cast<float2*>(o + (long)(g + 8) * C + h * 8) = make_float2(acc[h][2], acc[h][3]);
+        }
+      }
+    }
+  }
+}
+
+// ---- TokenUpMix forward: up[N, C] = W[N, MS] xc[MS, C] + bias                (split-precision operands)
+__global__ void __launch_bounds__(NWARP * 32) upm64_fwd_kernel(const float* __restrict__ xc, int B, int N, int MS, int C,
+                                                               const float* __restrict__ W, const float* __restrict__ bias,
+                                                               float* __restrict__ up) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int XP = C + 8;
+  bf16* S = reinterpret_cast<bf16*>(smraw);                    // W hi, lo [N][MSP]
+  bf16* SL = S + (size_t)N * MSP;
+  bf16* D = SL + (size_t)N * MSP;                              // xc hi, lo [MS][XP]
+  bf16* DL = D + (size_t)MS * XP;
+  float* F = reinterpret_cast<float*>(DL + (size_t)MS * XP);   // bias [N]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < N * MS; i += blockDim.x) store_split<true>(S, SL, (i / MS) * MSP + i % MS, W[i]);
+  for (int i = tid; i < N; i += blockDim.x) F[i] = bias[i];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    tile_to_bf16<true>(D, DL, XP, xc + (long)b * MS * C, MS, C);
+    __syncthreads();
+    for (int mt = warp; mt < N / 16; mt += NWARP) {
+      const float b0 = F[mt * 16 + g], b1 = F[mt * 16 + g + 8];
+      float* o = up + ((long)b * N + mt * 16) * C + 2 * t;
+      for (int pair = 0; pair < C / 16; ++pair) {
+        float acc[2][4] = {{b0, b0, b1, b1}, {b0, b0, b1, b1}};
+        for (int ks = 0; ks < MS / 16; ++ks) {
+          uint32_t a[4], al[4], bb[4], bl[4];
+          ldA(a, S, MSP, mt * 16, ks * 16, lane);              // A(m = token, k = slot) = W
+          ldA(al, SL, MSP, mt * 16, ks * 16, lane);
+          ldBt(bb, D, XP, pair * 16, ks * 16, lane);           // B(k = slot, n = channel) = xc
+          ldBt(bl, DL, XP, pair * 16, ks * 16, lane);
+          mma3<true>(acc[0], a, al, bb[0], bb[1], bl[0], bl[1]);
+          mma3<true>(acc[1], a, al, bb[2], bb[3], bl[2], bl[3]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          *reinterpret_cast<float2*>(o + (long)g * C + pair * 16 + h * 8) = make_float2(acc[h][0], acc[h][1]);
+          *reinterpret_cast<float2*>(o + (long)(g + 8) * C + pair * 16 + h * 8) = make_float2(acc[h][2], acc[h][3]);
+        }
+      }
+    }
+  }
+}
+
+// ---- TokenLearner backward: dS = x dxc^T; dlogits = S (dS - colsum(S dS)); dx = S dxc
+__global__ void __launch_bounds__(NWARP * 32) tlm64_bwd_kernel(const float* __restrict__ x, const float* __restrict__ Sg,
+                                                               const float* __restrict__ dxc, int B, int N, int MS, int C,
+                                                               bf16* __restrict__ dlogits, float* __restrict__ dx) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int XP = C + 8;
+  bf16* X = reinterpret_cast<bf16*>(smraw);                    // x [N][XP]
+  bf16* D = X + (size_t)N * XP;                                // dxc [MS][XP]
+  bf16* S = D + (size_t)MS * XP;                               // S [N][MSP]
+  float* R = reinterpret_cast<float*>(S + (size_t)N * MSP);    // column sums [MS]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  constexpr int MAXT = MAXN / 16 / NWARP;                      // token tiles per warp
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < N * MS; i += blockDim.x) S[(i / MS) * MSP + i % MS] = __float2bfloat16_rn(Sg[(long)b * N * MS + i]);
+    if (tid < MS) R[tid] = 0.f;
+    tile_to_bf16<false>(X, X, XP, x + (long)b * N * C, N, C);
+    tile_to_bf16<false>(D, D, XP, dxc + (long)b * MS * C, MS, C);
+    __syncthreads();
+    for (int sg = 0; sg < MS / 16; ++sg) {
+      float dS[MAXT][2][4];
+#pragma unroll
+      for (int nt = 0; nt < MAXT; ++nt) {
+        const int mt = warp + nt * NWARP;
+        if (mt >= N / 16) break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dS[nt][h][j] = 0.f;
+        for (int ks = 0; ks < C / 16; ++ks) {
+          uint32_t a[4], bb[4];
+          ldA(a, X, XP, mt * 16, ks * 16, lane);               // A(m = token, k = channel)
+          ldB(bb, D, XP, sg * 16, ks * 16, lane);              // B(n = slot, k = channel)
+          mma16816(dS[nt][0], a, bb[0], bb[1]);
+          mma16816(dS[nt][1], a, bb[2], bb[3]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = sg * 16 + h * 8 + 2 * t + j;
+            float v = __bfloat162float(S[(mt * 16 + g) * MSP + c]) * dS[nt][h][j] +
+                      __bfloat162float(S[(mt * 16 + g + 8) * MSP + c]) * dS[nt][h][2 + j];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) atomicAdd(R + c, v);
+          }
+      }
+      __syncthreads();                                         // column sums of this slot group complete
+#pragma unroll
+      for (int nt = 0; nt < MAXT; ++nt) {
+        const int mt = warp + nt * NWARP;
+        if (mt >= N / 16) break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = sg * 16 + h * 8 + 2 * t;
+          const float t0 = R[c], t1 = R[c + 1];
+          const int r0 = mt * 16 + g, r1 = r0 + 8;
+          const uint32_t lo = pack2(__bfloat162float(S[r0 * MSP + c]) * (dS[nt][h][0] - t0),
+                                    __bfloat162float(S[r0 * MSP + c + 1]) * (dS[nt][h][1] - t1));
+          const uint32_t hi = pack2(__bfloat162float(S[r1 * MSP + c]) * (dS[nt][h][2] - t0),
+                                    __bfloat162float(S[r1 * MSP + c + 1]) * (dS[nt][h][3] - t1));
+          *reinterpret_cast<uint32_t*>(dlogits + ((long)b * N + r0) * MS + c) = lo;
+          *reinterpret_cast<uint32_t*>(dlogits + ((long)b * N + r1) * MS + c) = hi;
+        }
+      }
+    }
+    // dx[N, C] = S dxc: K loop over the slots
+    for (int mt = warp; mt < N / 16; mt += NWARP) {
+      float* o = dx + ((long)b * N + mt * 16) * C + 2 * t;
+      for (int pair = 0; pair < C / 16; ++pair) {
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int ks = 0; ks < MS / 16; ++ks) {
+          uint32_t a[4], bb[4];
+          ldA(a, S, MSP, mt * 16, ks * 16, lane);              // A(m = token, k = slot)
+          ldBt(bb, D, XP, pair * 16, ks * 16, lane);           // B(k = slot, n = channel)
+          mma16816(acc[0], a, bb[0], bb[1]);
+          mma16816(acc[1], a, bb[2], bb[3]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          *reinterpret_cast<float2*>(o + (long)g * C + pair * 16 + h * 8) = make_float2(acc[h][0], acc[h][1]);
+          *reinterpret_cast<float2*>(o + (long)(g + 8) * C + pair * 16 + h * 8) = make_float2(acc[h][2], acc[h][3]);
+        }
+      }
+    }
+  }
+}
+
+// ---- TokenUpMix backward: dxc = W^T dup; dW += dup xc^T; dbias += rowsum(dup)
+__global__ void __launch_bounds__(NWARP * 32) upm64_bwd_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B, int N,
+                                                               int MS, int C, const float* __restrict__ W, float* __restrict__ dxc,
+                                                               float* __restrict__ dW, float* __restrict__ dbias) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int CH = C / 2, XPc = CH + 8;
+  bf16* S = reinterpret_cast<bf16*>(smraw);                    // W [N][MSP]
+  bf16* X = S + (size_t)N * MSP;                               // dup, one channel half [N][XPc]
+  bf16* D = X + (size_t)N * XPc;                               // xc, one channel half [MS][XPc]
+  float* dWs = reinterpret_cast<float*>(D + (size_t)MS * XPc); // [N][MS] fp32, accumulated over this CTA's images
+  float* dbs = dWs + (size_t)N * MS;                           // [N]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < N * MS; i += blockDim.x) { S[(i / MS) * MSP + i % MS] = __float2bfloat16_rn(W[i]); dWs[i] = 0.f; }
+  for (int i = tid; i < N; i += blockDim.x) dbs[i] = 0.f;
+  const uint32_t ones = pack2(1.f, 1.f);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int ch = 0; ch < 2; ++ch) {
+      __syncthreads();
+      tile_to_bf16_cols<false>(X, X, XPc, dup + (long)b * N * C, N, C, ch * CH, CH);
+      tile_to_bf16_cols<false>(D, D, XPc, xc + (long)b * MS * C, MS, C, ch * CH, CH);
+      __syncthreads();
+      // dxc[MS, half] = W^T dup: A(m = slot, k = token) = W[token][slot], B(k = token, n = channel) = dup
+      const int npair = CH / 16;
+      for (int item = warp; item < (MS / 16) * npair; item += NWARP) {
+        const int ms = item / npair, pair = item % npair;
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        for (int ks = 0; ks < N / 16; ++ks) {
+          uint32_t a[4], bb[4];
+          ldAt(a, S, MSP, ms * 16, ks * 16, lane);
+          ldBt(bb, X, XPc, pair * 16, ks * 16, lane);
+          mma16816(acc[0], a, bb[0], bb[1]);
+          mma16816(acc[1], a, bb[2], bb[3]);
+        }
+        float* o = dxc + ((long)b * MS + ms * 16) * C + ch * CH + pair * 16 + 2 * t;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          *reinterpret_cast<float2*>(o + (long)g * C + h * 8) = make_float2(acc[h][0], acc[h][1]);
+          *reinterpret_cast<float2*>(o + (long)(g + 8) * C + h * 8) = make_float2(acc[h][2], acc[h][3]);
+        }
+      }
+      // dW[N, MS] += dup xc^T over this half's channels (each warp owns its token tiles: plain shared-memory adds)
+      for (int mt = warp; mt < N / 16; mt += NWARP) {
+        float aB[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int sg = 0; sg < MS / 16; ++sg) {
+          float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          for (int ks = 0; ks < CH / 16; ++ks) {
+            uint32_t a[4], bb[4];
+            ldA(a, X, XPc, mt * 16, ks * 16, lane);            // A(m = token, k = channel) = dup
+            ldB(bb, D, XPc, sg * 16, ks * 16, lane);           // B(n = slot, k = channel) = xc
+            mma16816(c[0], a, bb[0], bb[1]);
+            mma16816(c[1], a, bb[2], bb[3]);
+            if (sg == 0) mma16816(aB, a, ones, ones);          // row sums of dup (a B tile of ones)
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float* w0 = dWs + (mt * 16 + g) * MS + sg * 16 + h * 8 + 2 * t;
+            float* w1 = dWs + (mt * 16 + g + 8) * MS + sg * 16 + h * 8 + 2 * t;
+            w0[0] += c[h][0]; w0[1] += c[h][1];
+            w1[0] += c[h][2]; w1[1] += c[h][3];
+          }
+        }
+        if (t == 0) { dbs[mt * 16 + g] += aB[0]; dbs[mt * 16 + g + 8] += aB[2]; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < N * MS; i += blockDim.x) atomicAdd(dW + i, dWs[i]);
+  for (int i = tid; i < N; i += blockDim.x) atomicAdd(dbias + i, dbs[i]);
+}
+
 // ---------------------------------------------------------------------------------------------- bank write reduction
 // GlobalTokenBank.write (H:303-311): per image  K_upd[16, d] = S^T c,  V_upd[16, d] = S^T tn  with S = softmax over the
 // tokens of the gate logits; summed over the batch.  One product per image: [16 slots x Nt] x [Nt x 2d] on mma.sync;
@@ -495,6 +804,42 @@ int tok_grid(int B, size_t smem) {
 }  // namespace
 
 bool tokens_mma_ok(int M, int N, int C) { return M == 16 && N % 16 == 0 && N >= 16 && N <= 128 && C % 16 == 0 && C <= 512; }
+// 32 / 48 / 64 learned tokens, up to 256 stream tokens (tlm64_* / upm64_* kernels)
+bool tokens_mma64_ok(int M, int N, int C) {
+  return M % 16 == 0 && M >= 16 && M <= MAXS && N % 16 == 0 && N >= 16 && N <= MAXN && C % 32 == 0 && C <= 256 && !tokens_mma_ok(M, N, C);
+}
+int tlm64_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, int M, int C, float* S, float* xc) {
+  const int XPc = C / 2 + 8;
+  const size_t ub = max((size_t)N * M * 4, (size_t)2 * N * XPc * 2);
+  const size_t smem = (size_t)2 * N * MSP * 2 + ((ub + 15) & ~(size_t)15) + 8 * M16 * 4 + 16;
+  QV_TRY(opt_in(tlm64_fwd_kernel, smem));
+  tlm64_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, (const bf16*)logits, B, N, M, C, S, xc);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int tlm64_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int M, int C, void* dlogits, float* dx) {
+  const size_t smem = ((size_t)N * (C + 8) + (size_t)M * (C + 8) + (size_t)N * MSP) * 2 + (size_t)M * 4 + 16;
+  QV_TRY(opt_in(tlm64_bwd_kernel, smem));
+  tlm64_bwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, S, dxc, B, N, M, C, (bf16*)dlogits, dx);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int upm64_fwd(cudaStream_t s, const float* xc, int B, int N, int M, int C, const float* W, const float* bias, float* up) {
+  const size_t smem = ((size_t)2 * N * MSP + (size_t)2 * M * (C + 8)) * 2 + (size_t)N * 4 + 16;
+  QV_TRY(opt_in(upm64_fwd_kernel, smem));
+  upm64_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(xc, B, N, M, C, W, bias, up);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int upm64_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int M, int C, const float* W, float* dxc, float* dW,
+              float* dbias) {
+  const int XPc = C / 2 + 8;
+  const size_t smem = ((size_t)N * MSP + (size_t)N * XPc + (size_t)M * XPc) * 2 + ((size_t)N * M + N) * 4 + 16;
+  QV_TRY(opt_in(upm64_bwd_kernel, smem));
+  upm64_bwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(xc, dup, B, N, M, C, W, dxc, dW, dbias);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
 
 int tlm_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, int C, float* S, float* xc) {
   const size_t smem = smem_bytes(N, C, true, true, false);

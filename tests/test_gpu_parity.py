@@ -283,7 +283,8 @@ def test_bf16_vs_fp32_with_reference_init(fam):
         assert e_grad <= max(1e-2, 1.25 * f_grad), (e_grad, f_grad)
 
 
-@pytest.mark.parametrize("case,prefix,ntok", [("hqavit_c100", "stage2_blocks.1", 64), ("qavitv2_c100", "blocks.3", 64)])
+@pytest.mark.parametrize("case,prefix,ntok", [("hqavit_c100", "stage2_blocks.1", 64), ("qavitv2_c100", "blocks.3", 64),
+                                              ("hqavit_tinyin", "stage3_blocks.2", 256)])   # 64 learned / 256 stream tokens
 def test_block_bf16_close_to_fp32(case, prefix, ntok):
     """One block, bf16 run (tcgen05 GEMMs + mma.sync attention) against the fp32 run of the same block: a layout bug in
     a tensor-core path shows up as O(1) error, bf16 rounding as ~1e-2."""
