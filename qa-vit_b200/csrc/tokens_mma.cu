@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(NWARP * 32) upm_bwd_kernel(const float* __rest
 constexpr int MAXS = 64;              // learned tokens
 constexpr int MSP = MAXS + 8;         // pitch (bf16) of the [N][MS] matrices: 144 B rows
 constexpr int MAXN = 256;             // stream tokens
+constexpr int NW64 = 8;               // warps per CTA: the staged tiles allow one CTA per SM, so the CTA itself must hide latency
 
 // fp32 global rows (row stride ld, columns [c0, c0 + cols)) -> bf16 hi (/ lo) tiles [rows][pitch]
 template <bool HL>
@@ -430,7 +431,7 @@ __device__ __forceinline__ void tile_to_bf16_cols(bf16* dhi, bf16* dlo, int pitc
 }
 
 // ---- TokenLearner forward: xc[MS, C] = softmax_tokens(logits)^T x          (split-precision operands)
-__global__ void __launch_bounds__(NWARP * 32) tlm64_fwd_kernel(const float* __restrict__ x, const bf16* __restrict__ logits, int B, int N,
+__global__ void __launch_bounds__(NW64 * 32) tlm64_fwd_kernel(const float* __restrict__ x, const bf16* __restrict__ logits, int B, int N,
                                                                int MS, int C, float* __restrict__ Sout, float* __restrict__ xc) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int CH = C / 2, XPc = CH + 8;
@@ -441,31 +442,40 @@ __global__ void __launch_bounds__(NWARP * 32) tlm64_fwd_kernel(const float* __re
   bf16* X = reinterpret_cast<bf16*>(U);                        // [N][XPc] hi, lo: one channel half
   bf16* XL = X + (size_t)N * XPc;
   const size_t ubytes = max((size_t)N * MS * 4, (size_t)2 * N * XPc * 2);
-  float* R = reinterpret_cast<float*>(U + ((ubytes + 15) & ~(size_t)15));   // [8][16]
+  float* R = reinterpret_cast<float*>(U + ((ubytes + 15) & ~(size_t)15));   // [16][16]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int c16 = tid % M16, part = tid / M16;                 // softmax: 8 threads per slot, 16 slots per pass
+  const int c16 = tid % M16, part = tid / M16;                 // softmax: 16 threads per slot, 16 slots per pass
+  constexpr int NP = NW64 * 32 / M16;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    for (int i = tid; i < N * MS; i += blockDim.x) F[i] = __bfloat162float(logits[(long)b * N * MS + i]);
+    for (int i = tid; i < N * MS / 8; i += blockDim.x) {       // 16 B loads: a scalar loop here serialised on load latency
+      const uint4 q = *reinterpret_cast<const uint4*>(logits + (long)b * N * MS + i * 8);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        F[i * 8 + 2 * j] = f.x; F[i * 8 + 2 * j + 1] = f.y;
+      }
+    }
     __syncthreads();
     for (int sg = 0; sg < MS / 16; ++sg) {
       const int col = sg * 16 + c16;
       float mx = -INFINITY;
-      for (int n = part; n < N; n += 8) mx = fmaxf(mx, F[n * MS + col]);
+      for (int n = part; n < N; n += NP) mx = fmaxf(mx, F[n * MS + col]);
       R[part * M16 + c16] = mx;
       __syncthreads();
 #pragma unroll
-      for (int k = 0; k < 8; ++k) mx = fmaxf(mx, R[k * M16 + c16]);
+      for (int k = 0; k < NP; ++k) mx = fmaxf(mx, R[k * M16 + c16]);
       float z = 0.f;
-      for (int n = part; n < N; n += 8) { const float e = __expf(F[n * MS + col] - mx); F[n * MS + col] = e; z += e; }
+      for (int n = part; n < N; n += NP) { const float e = __expf(F[n * MS + col] - mx); F[n * MS + col] = e; z += e; }
       __syncthreads();
       R[part * M16 + c16] = z;
       __syncthreads();
       z = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) z += R[k * M16 + c16];
+      for (int k = 0; k < NP; ++k) z += R[k * M16 + c16];
       z = 1.f / z;
-      for (int n = part; n < N; n += 8) {
+      for (int n = part; n < N; n += NP) {
         const float sv = F[n * MS + col] * z;
         Sout[(long)b * N * MS + n * MS + col] = sv;
         store_split<true>(S, SL, n * MSP + col, sv);
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(NWARP * 32) tlm64_fwd_kernel(const float* __re
       tile_to_bf16_cols<true>(X, XL, XPc, x + (long)b * N * C, N, C, ch * CH, CH);
       __syncthreads();
       const int npair = CH / 16;
-      for (int item = warp; item < (MS / 16) * npair; item += NWARP) {
+      for (int item = warp; item < (MS / 16) * npair; item += NW64) {
         const int ms = item / npair, pair = item % npair;
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         for (int ks = 0; ks < N / 16; ++ks) {
@@ -501,7 +511,7 @@ __global__ void __launch_bounds__(NWARP * 32) tlm64_fwd_kernel(const float* __re
 }
 
 // ---- TokenUpMix forward: up[N, C] = W[N, MS] xc[MS, C] + bias                (split-precision operands)
-__global__ void __launch_bounds__(NWARP * 32) upm64_fwd_kernel(const float* __restrict__ xc, int B, int N, int MS, int C,
+__global__ void __launch_bounds__(NW64 * 32) upm64_fwd_kernel(const float* __restrict__ xc, int B, int N, int MS, int C,
                                                                const float* __restrict__ W, const float* __restrict__ bias,
                                                                float* __restrict__ up) {
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(NWARP * 32) upm64_fwd_kernel(const float* __re
     __syncthreads();
     tile_to_bf16<true>(D, DL, XP, xc + (long)b * MS * C, MS, C);
     __syncthreads();
-    for (int mt = warp; mt < N / 16; mt += NWARP) {
+    for (int mt = warp; mt < N / 16; mt += NW64) {
       const float b0 = F[mt * 16 + g], b1 = F[mt * 16 + g + 8];
       float* o = up + ((long)b * N + mt * 16) * C + 2 * t;
       for (int pair = 0; pair < C / 16; ++pair) {
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(NWARP * 32) upm64_fwd_kernel(const float* __re
 }
 
 // ---- TokenLearner backward: dS = x dxc^T; dlogits = S (dS - colsum(S dS)); dx = S dxc
-__global__ void __launch_bounds__(NWARP * 32) tlm64_bwd_kernel(const float* __restrict__ x, const float* __restrict__ Sg,
+__global__ void __launch_bounds__(NW64 * 32) tlm64_bwd_kernel(const float* __restrict__ x, const float* __restrict__ Sg,
                                                                const float* __restrict__ dxc, int B, int N, int MS, int C,
                                                                bf16* __restrict__ dlogits, float* __restrict__ dx) {
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -553,10 +563,14 @@ __global__ void __launch_bounds__(NWARP * 32) tlm64_bwd_kernel(const float* __re
   bf16* S = D + (size_t)MS * XP;                               // S [N][MSP]
   float* R = reinterpret_cast<float*>(S + (size_t)N * MSP);    // column sums [MS]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  constexpr int MAXT = MAXN / 16 / NWARP;                      // token tiles per warp
+  constexpr int MAXT = MAXN / 16 / NW64;                       // token tiles per warp
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    for (int i = tid; i < N * MS; i += blockDim.x) S[(i / MS) * MSP + i % MS] = __float2bfloat16_rn(Sg[(long)b * N * MS + i]);
+    for (int i = tid; i < N * MS / 4; i += blockDim.x) {       // 16 B loads
+      const float4 v = *reinterpret_cast<const float4*>(Sg + (long)b * N * MS + i * 4);
+      const int e = i * 4;
+      *reinterpret_cast<uint2*>(S + (e / MS) * MSP + e % MS) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+    }
     if (tid < MS) R[tid] = 0.f;
     tile_to_bf16<false>(X, X, XP, x + (long)b * N * C, N, C);
     tile_to_bf16<false>(D, D, XP, dxc + (long)b * MS * C, MS, C);
@@ -565,7 +579,7 @@ __global__ void __launch_bounds__(NWARP * 32) tlm64_bwd_kernel(const float* __re
       float dS[MAXT][2][4];
 #pragma unroll
       for (int nt = 0; nt < MAXT; ++nt) {
-        const int mt = warp + nt * NWARP;
+        const int mt = warp + nt * NW64;
         if (mt >= N / 16) break;
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -594,7 +608,7 @@ __global__ void __launch_bounds__(NWARP * 32) tlm64_bwd_kernel(const float* __re
       __syncthreads();                                         // column sums of this slot group complete
 #pragma unroll
       for (int nt = 0; nt < MAXT; ++nt) {
-        const int mt = warp + nt * NWARP;
+        const int mt = warp + nt * NW64;
         if (mt >= N / 16) break;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -611,7 +625,7 @@ __global__ void __launch_bounds__(NWARP * 32) tlm64_bwd_kernel(const float* __re
       }
     }
     // dx[N, C] = S dxc: K loop over the slots
-    for (int mt = warp; mt < N / 16; mt += NWARP) {
+    for (int mt = warp; mt < N / 16; mt += NW64) {
       float* o = dx + ((long)b * N + mt * 16) * C + 2 * t;
       for (int pair = 0; pair < C / 16; ++pair) {
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -633,7 +647,7 @@ __global__ void __launch_bounds__(NWARP * 32) tlm64_bwd_kernel(const float* __re
 }
 
 // ---- TokenUpMix backward: dxc = W^T dup; dW += dup xc^T; dbias += rowsum(dup)
-__global__ void __launch_bounds__(NWARP * 32) upm64_bwd_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B, int N,
+__global__ void __launch_bounds__(NW64 * 32) upm64_bwd_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B, int N,
                                                                int MS, int C, const float* __restrict__ W, float* __restrict__ dxc,
                                                                float* __restrict__ dW, float* __restrict__ dbias) {
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -655,7 +669,7 @@ __global__ void __launch_bounds__(NWARP * 32) upm64_bwd_kernel(const float* __re
       __syncthreads();
       // dxc[MS, half] = W^T dup: A(m = slot, k = token) = W[token][slot], B(k = token, n = channel) = dup
       const int npair = CH / 16;
-      for (int item = warp; item < (MS / 16) * npair; item += NWARP) {
+      for (int item = warp; item < (MS / 16) * npair; item += NW64) {
         const int ms = item / npair, pair = item % npair;
         float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         for (int ks = 0; ks < N / 16; ++ks) {
@@ -673,7 +687,7 @@ __global__ void __launch_bounds__(NWARP * 32) upm64_bwd_kernel(const float* __re
         }
       }
       // dW[N, MS] += dup xc^T over this half's channels (each warp owns its token tiles: plain shared-memory adds)
-      for (int mt = warp; mt < N / 16; mt += NWARP) {
+      for (int mt = warp; mt < N / 16; mt += NW64) {
         float aB[4] = {0.f, 0.f, 0.f, 0.f};
         for (int sg = 0; sg < MS / 16; ++sg) {
           float c[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -811,23 +825,23 @@ bool tokens_mma64_ok(int M, int N, int C) {
 int tlm64_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, int M, int C, float* S, float* xc) {
   const int XPc = C / 2 + 8;
   const size_t ub = max((size_t)N * M * 4, (size_t)2 * N * XPc * 2);
-  const size_t smem = (size_t)2 * N * MSP * 2 + ((ub + 15) & ~(size_t)15) + 8 * M16 * 4 + 16;
+  const size_t smem = (size_t)2 * N * MSP * 2 + ((ub + 15) & ~(size_t)15) + 16 * M16 * 4 + 16;
   QV_TRY(opt_in(tlm64_fwd_kernel, smem));
-  tlm64_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, (const bf16*)logits, B, N, M, C, S, xc);
+  tlm64_fwd_kernel<<<tok_grid(B, smem), NW64 * 32, smem, s>>>(x, (const bf16*)logits, B, N, M, C, S, xc);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int tlm64_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int M, int C, void* dlogits, float* dx) {
   const size_t smem = ((size_t)N * (C + 8) + (size_t)M * (C + 8) + (size_t)N * MSP) * 2 + (size_t)M * 4 + 16;
   QV_TRY(opt_in(tlm64_bwd_kernel, smem));
-  tlm64_bwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, S, dxc, B, N, M, C, (bf16*)dlogits, dx);
+  tlm64_bwd_kernel<<<tok_grid(B, smem), NW64 * 32, smem, s>>>(x, S, dxc, B, N, M, C, (bf16*)dlogits, dx);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int upm64_fwd(cudaStream_t s, const float* xc, int B, int N, int M, int C, const float* W, const float* bias, float* up) {
   const size_t smem = ((size_t)2 * N * MSP + (size_t)2 * M * (C + 8)) * 2 + (size_t)N * 4 + 16;
   QV_TRY(opt_in(upm64_fwd_kernel, smem));
-  upm64_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(xc, B, N, M, C, W, bias, up);
+  upm64_fwd_kernel<<<tok_grid(B, smem), NW64 * 32, smem, s>>>(xc, B, N, M, C, W, bias, up);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -836,7 +850,7 @@ int upm64_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, i
   const int XPc = C / 2 + 8;
   const size_t smem = ((size_t)N * MSP + (size_t)N * XPc + (size_t)M * XPc) * 2 + ((size_t)N * M + N) * 4 + 16;
   QV_TRY(opt_in(upm64_bwd_kernel, smem));
-  upm64_bwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(xc, dup, B, N, M, C, W, dxc, dW, dbias);
+  upm64_bwd_kernel<<<tok_grid(B, smem), NW64 * 32, smem, s>>>(xc, dup, B, N, M, C, W, dxc, dW, dbias);
   QV_LAUNCH_CHECK();
   return 0;
 }
