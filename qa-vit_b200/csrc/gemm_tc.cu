@@ -190,30 +190,6 @@ __device__ __forceinline__ void stage_store16(uint8_t* rowp, int c, const float*
   }
 }
 
-// staged [32 rows x gw cols] -> global, consecutive lanes on consecutive 16 B chunks of a row
-__device__ __forceinline__ void stage_flush(const uint8_t* st, void* C, long ldc, bool f32, bool accum, long row0, int M,
-                                            int col0, int gw, int lane) {
-  const int esz = f32 ? 4 : 2;
-  const int cpr = gw * esz / 16;                               // 16 B chunks per row: 2, 4 or 8
-  const int sh = (cpr == 8) ? 3 : (cpr == 4 ? 2 : 1);
-  uint8_t* base = static_cast<uint8_t*>(C);
-  for (int k = 0; k < cpr; ++k) {
-    const int idx = k * 32 + lane, r = idx >> sh, ch = idx & (cpr - 1);
-    const long row = row0 + r;
-    if (row < M) {
-      const uint4 v = *reinterpret_cast<const uint4*>(st + r * EPI_ROWB + ch * 16);
-      uint8_t* g = base + (row * ldc + col0) * esz + ch * 16;
-      if (accum) {
-        float4 o = *reinterpret_cast<float4*>(g);
-        o.x += __uint_as_float(v.x); o.y += __uint_as_float(v.y); o.z += __uint_as_float(v.z); o.w += __uint_as_float(v.w);
-        *reinterpret_cast<float4*>(g) = o;
-      } else {
-        *reinterpret_cast<uint4*>(g) = v;
-      }
-    }
-  }
-}
-
 // bf16 flavour with a compile-time number of 16 B chunks per row (8 / 4 / 2 for 64 / 32 / 16 staged columns): fully
 // unrolled, one pointer bump per pass (the generic loop above spent more issue slots on index math than on the copies)
 template <int CPR>
@@ -230,6 +206,42 @@ __device__ __forceinline__ void stage_flush_bf16(const uint8_t* st, void* C, lon
     gp += gstep;
     sp += RPP * EPI_ROWB;
   }
+}
+
+// any element size: CPR = 16 B chunks per staged row (gw * esz / 16), optional fp32 accumulate
+template <int CPR, bool ACCUM>
+__device__ __forceinline__ void stage_flush_u(const uint8_t* st, void* C, long pitch_bytes, long row0, int M, long col_byte0, int lane) {
+  constexpr int RPP = 32 / CPR;
+  const int r0 = lane / CPR, ch = lane % CPR;
+  const int nvalid = (int)min(32L, (long)M - row0);
+  uint8_t* gp = static_cast<uint8_t*>(C) + (row0 + r0) * pitch_bytes + col_byte0 + ch * 16;
+  const uint8_t* sp = st + r0 * EPI_ROWB + ch * 16;
+#pragma unroll
+  for (int k = 0; k < CPR; ++k) {
+    if (r0 + k * RPP < nvalid) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sp);
+      if (ACCUM) {
+        float4 o = *reinterpret_cast<float4*>(gp);
+        o.x += __uint_as_float(v.x); o.y += __uint_as_float(v.y); o.z += __uint_as_float(v.z); o.w += __uint_as_float(v.w);
+        *reinterpret_cast<float4*>(gp) = o;
+      } else {
+        *reinterpret_cast<uint4*>(gp) = v;
+      }
+    }
+    gp += RPP * pitch_bytes;
+    sp += RPP * EPI_ROWB;
+  }
+}
+__device__ __forceinline__ void stage_flush_any(const uint8_t* st, void* C, long ldc, bool f32, bool accum, long row0, int M, int col0,
+                                                int gw, int lane) {
+  const int esz = f32 ? 4 : 2, cpr = gw * esz / 16;
+  const long pitch = ldc * esz, cb = (long)col0 * esz;
+  if (accum) {
+    if (cpr == 8) stage_flush_u<8, true>(st, C, pitch, row0, M, cb, lane);
+    else stage_flush_u<4, true>(st, C, pitch, row0, M, cb, lane);
+  } else if (cpr == 8) stage_flush_u<8, false>(st, C, pitch, row0, M, cb, lane);
+  else if (cpr == 4) stage_flush_u<4, false>(st, C, pitch, row0, M, cb, lane);
+  else stage_flush_u<2, false>(st, C, pitch, row0, M, cb, lane);
 }
 
 // fp32 global [32 rows x gw cols] -> staging (row-contiguous reads)
@@ -306,8 +318,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS); }
     fence_barrier_init();
   }
-  {   // WIDE: the bias is staged pre-multiplied by scale_pre so the epilogue is one FFMA per element
-    const float sp0 = (WIDE && p.e.scale_pre) ? *p.e.scale_pre : 1.f;
+  {   // the bias is staged pre-multiplied by scale_pre so the epilogue is one FFMA per element
+    const float sp0 = p.e.scale_pre ? *p.e.scale_pre : 1.f;
     for (int j = threadIdx.x; j < p.BN; j += NTHREADS) bias_s[j] = (p.e.bias && n0 + j < p.N) ? p.e.bias[n0 + j] * sp0 : 0.f;
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -504,7 +516,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (c < nch) {
             tmem_ld_wait16(v[c]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[c][j] = (v[c][j] + bias_s[g + c * 16 + j]) * s_pre;
+            for (int j = 0; j < 16; ++j) v[c][j] = fmaf(v[c][j], s_pre, bias_s[g + c * 16 + j]);   // bias staged pre-scaled
             if (use_gmul) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[c][j] *= gelu_grad_fast_f(r[c][j]);
@@ -525,7 +537,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int c = 0; c < 2; ++c)
             if (c < nch) stage_store16(my_row, c, v[c], e.c_f32 != 0);
           __syncwarp();
-          stage_flush(st, e.C, e.ldc, e.c_f32 != 0, e.c_accum != 0, row0, p.M, n0 + g, gw, lane);
+          stage_flush_any(st, e.C, e.ldc, e.c_f32 != 0, e.c_accum != 0, row0, p.M, n0 + g, gw, lane);
           __syncwarp();
         }
         if (e.C2) {
@@ -550,7 +562,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               stage_store16(my_row, c, v[c], e.c2_f32 != 0);
             }
           __syncwarp();
-          stage_flush(st, e.C2, e.ldc2, e.c2_f32 != 0, false, row0, p.M, n0 + g, gw, lane);
+          stage_flush_any(st, e.C2, e.ldc2, e.c2_f32 != 0, false, row0, p.M, n0 + g, gw, lane);
           __syncwarp();
         }
       }
