@@ -172,7 +172,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def gemm_roofline(device, batch):
-    """Dominant kernel (tc_gemm_nt_kernel, ~23 % of the step over 358 launches) at its largest block shape, the SWA qkv
+    """Dominant kernel (tc_gemm_nt_kernel, ~21 % of the step over 358 launches) at its largest block shape, the SWA qkv
     projection [B*16, 192] x [576, 192]^T, timed alone with CUDA events on the launching stream, L2 flushed before
     every launch.  The step itself is a CUDA graph, so per-kernel events cannot be placed inside it; the kernel's share
     of the step comes from the ncu launch list in profiles/."""
