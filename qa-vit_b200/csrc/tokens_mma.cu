@@ -66,27 +66,34 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t* hi, uint32_t*
   *hi = *reinterpret_cast<const uint32_t*>(&h);
   *lo = pack2(x - hf.x, y - hf.y);
 }
-// fp32 global [rows][C] -> bf16 hi (/ lo when HL) smem tiles [rows][pitch]
+// fp32 global [rows][C] -> bf16 hi (/ lo when HL) smem tiles [rows][pitch].  (row, column) of a thread's elements advance
+// incrementally: the i / c4n, i % c4n pair this loop used to evaluate per element was half of all instructions the token
+// kernels executed (ncu source view, profiles/r1_ncu_brief_prof_tok_b4736.txt).
 template <bool HL>
 __device__ __forceinline__ void tile_to_bf16(bf16* dhi, bf16* dlo, int pitch, const float* __restrict__ src, int rows, int C) {
   const int c4n = C / 4, total = rows * c4n;
-  for (int base = 0; base < total; base += 8 * blockDim.x) {     // 8 independent 16 B loads in flight per thread
+  const int step = blockDim.x, srow = step / c4n, scol = step - srow * c4n;
+  int row = threadIdx.x / c4n, col = threadIdx.x - row * c4n;
+  for (int base = 0; base < total; base += 8 * step) {     // 8 independent 16 B loads in flight per thread
     float4 v[8];
+    int o[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int i = base + u * blockDim.x + threadIdx.x;
-      if (i < total) v[u] = *reinterpret_cast<const float4*>(src + (long)(i / c4n) * C + (i % c4n) * 4);
+      const int i = base + u * step + threadIdx.x;
+      if (i < total) v[u] = *reinterpret_cast<const float4*>(src + (long)i * 4);   // full rows: the tile is contiguous
+      o[u] = row * pitch + col * 4;
+      row += srow; col += scol;
+      if (col >= c4n) { col -= c4n; ++row; }
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int i = base + u * blockDim.x + threadIdx.x;
+      const int i = base + u * step + threadIdx.x;
       if (i < total) {
         uint32_t h0, l0, h1, l1;
         split2(v[u].x, v[u].y, &h0, &l0);
         split2(v[u].z, v[u].w, &h1, &l1);
-        const int o = (i / c4n) * pitch + (i % c4n) * 4;
-        *reinterpret_cast<uint2*>(dhi + o) = make_uint2(h0, h1);
-        if (HL) *reinterpret_cast<uint2*>(dlo + o) = make_uint2(l0, l1);
+        *reinterpret_cast<uint2*>(dhi + o[u]) = make_uint2(h0, h1);
+        if (HL) *reinterpret_cast<uint2*>(dlo + o[u]) = make_uint2(l0, l1);
       }
     }
   }
@@ -144,7 +151,15 @@ __global__ void __launch_bounds__(NWARP * 32) tlm_fwd_kernel(const float* __rest
   const int col = tid % M16, part = tid / M16;          // softmax: 8 threads per slot
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    for (int i = tid; i < N * M16; i += blockDim.x) sm.F[i] = __bfloat162float(logits[(long)b * N * M16 + i]);
+    for (int i = tid; i < N * M16 / 8; i += blockDim.x) {      // 16 B loads (the scalar loop was 15 % of the stall samples)
+      const uint4 q = *reinterpret_cast<const uint4*>(logits + (long)b * N * M16 + i * 8);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        sm.F[i * 8 + 2 * j] = f.x; sm.F[i * 8 + 2 * j + 1] = f.y;
+      }
+    }
     tile_to_bf16<true>(sm.X, sm.XL, XP, x + (long)b * N * C, N, C);
     __syncthreads();
     float mx = -INFINITY;
@@ -408,23 +423,28 @@ template <bool HL>
 __device__ __forceinline__ void tile_to_bf16_cols(bf16* dhi, bf16* dlo, int pitch, const float* __restrict__ src, int rows, int ld, int c0,
                                                   int cols) {
   const int c4n = cols / 4, total = rows * c4n;
-  for (int base = 0; base < total; base += 8 * blockDim.x) {
+  const int step = blockDim.x, srow = step / c4n, scol = step - srow * c4n;
+  int row = threadIdx.x / c4n, col = threadIdx.x - row * c4n;
+  for (int base = 0; base < total; base += 8 * step) {
     float4 v[8];
+    int o[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int i = base + u * blockDim.x + threadIdx.x;
-      if (i < total) v[u] = *reinterpret_cast<const float4*>(src + (long)(i / c4n) * ld + c0 + (i % c4n) * 4);
+      const int i = base + u * step + threadIdx.x;
+      if (i < total) v[u] = *reinterpret_cast<const float4*>(src + (long)row * ld + c0 + col * 4);
+      o[u] = row * pitch + col * 4;
+      row += srow; col += scol;
+      if (col >= c4n) { col -= c4n; ++row; }
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int i = base + u * blockDim.x + threadIdx.x;
+      const int i = base + u * step + threadIdx.x;
       if (i < total) {
         uint32_t h0, l0, h1, l1;
         split2(v[u].x, v[u].y, &h0, &l0);
         split2(v[u].z, v[u].w, &h1, &l1);
-        const int o = (i / c4n) * pitch + (i % c4n) * 4;
-        *reinterpret_cast<uint2*>(dhi + o) = make_uint2(h0, h1);
-        if (HL) *reinterpret_cast<uint2*>(dlo + o) = make_uint2(l0, l1);
+        *reinterpret_cast<uint2*>(dhi + o[u]) = make_uint2(h0, h1);
+        if (HL) *reinterpret_cast<uint2*>(dlo + o[u]) = make_uint2(l0, l1);
       }
     }
   }
