@@ -93,6 +93,26 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        T* __restrict__ y) {
   const int lpr = C / 8;
+  if (256 % lpr == 0) {
+    // the thread stride (a multiple of 256 vectors) is a multiple of the vectors per row: a thread stays on the same 8
+    // channels, so the per-channel constants are loaded once and the body is 8 FMAs (the 64-bit modulo + 32 parameter
+    // loads per vector of the generic loop below cost more than the normalisation itself)
+    const int cv = (threadIdx.x % lpr) * 8;
+    float mu[8], sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mu[j] = mr[cv + j]; sc[j] = mr[C + cv + j] * gamma[cv + j]; sh[j] = beta[cv + j]; }
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+      float v[8];
+      Vec8<T>::ld(x + i * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o = fmaf(v[j] - mu[j], sc[j], sh[j]);      // centre first: no cancellation when |mean| >> std
+        v[j] = GELU ? gelu_t<T>(o) : o;
+      }
+      Vec8<T>::st(y + i * 8, v);
+    }
+    return;
+  }
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
     const int cv = (int)(i % lpr) * 8;
     float v[8];
@@ -149,6 +169,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
   const float invn = train ? 1.f / (float)rows : 0.f;
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < C; c += 256) { dgamma[c] += sums[c]; dbeta[c] += sums[C + c]; }
+  }
+  if (256 % lpr == 0) {       // see bn_apply_kernel: the thread keeps its 8 channels, constants live in registers
+    const int cv = (threadIdx.x % lpr) * 8;
+    float mu[8], rs[8], gm[8], bt[8], s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mr[cv + j]; rs[j] = mr[C + cv + j]; gm[j] = gamma[cv + j]; bt[j] = beta[cv + j];
+      s0[j] = invn * sums[cv + j]; s1[j] = invn * sums[C + cv + j];
+    }
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
+      float v[8], g[8];
+      Vec8<T>::ld(x + i * 8, v);
+      Vec8<T>::ld(dy + i * 8, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (v[j] - mu[j]) * rs[j];
+        if (GELU) g[j] *= gelu_grad_t<T>(fmaf(xh, gm[j], bt[j]));
+        v[j] = gm[j] * rs[j] * (g[j] - (s1[j] + xh * s0[j]));
+      }
+      Vec8<T>::st(dx + i * 8, v);
+    }
+    return;
   }
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long)gridDim.x * 256) {
     const int cv = (int)(i % lpr) * 8;
