@@ -763,11 +763,17 @@ __global__ void __launch_bounds__(NWARP * 32) bwr_mma_kernel(const bf16* __restr
     const long row0 = (long)b * Nt;
     __syncthreads();
     for (int i = tid; i < Nt * M16; i += blockDim.x) sF[i] = __bfloat162float(cg[(row0 + i / M16) * ldcg + d + i % M16]);
-    for (int i = tid; i < Nt * 2 * v8; i += blockDim.x) {
-      const int r = i / (2 * v8), c = i % (2 * v8);
-      const uint4 v = c < v8 ? *reinterpret_cast<const uint4*>(cg + (row0 + r) * ldcg + c * 8)
-                             : *reinterpret_cast<const uint4*>(tn + (row0 + r) * d + (c - v8) * 8);
-      *reinterpret_cast<uint4*>(sX + r * XP + c * 8) = v;
+    {   // (row, vector) advance incrementally: no per-element division by the runtime row length
+      const int vpr = 2 * v8, sr = blockDim.x / vpr, sc = blockDim.x - sr * vpr;
+      int r = tid / vpr, c = tid - r * vpr;
+#pragma unroll 3
+      for (int i = tid; i < Nt * vpr; i += blockDim.x) {
+        const uint4 v = c < v8 ? *reinterpret_cast<const uint4*>(cg + (row0 + r) * ldcg + c * 8)
+                               : *reinterpret_cast<const uint4*>(tn + (row0 + r) * d + (c - v8) * 8);
+        *reinterpret_cast<uint4*>(sX + r * XP + c * 8) = v;
+        r += sr; c += sc;
+        if (c >= vpr) { c -= vpr; ++r; }
+      }
     }
     __syncthreads();
     float mx = -INFINITY;
