@@ -1,6 +1,9 @@
 // nn.Dropout / DropPath sites of the quad block that are not inside an attention kernel (H:465, 529, 592, 625 branch
-// output dropout; H:654-656 BottleneckMLP; H:710 CCFFFN; H:1082-1083 DropPath).  One pass over the activation, mask
-// regenerated from the Philox snapshot: backward applies the same function to the gradient.
+// output dropout; H:654-656 BottleneckMLP; H:710 CCFFFN; H:1082-1083 DropPath) as one pass over the activation, the mask
+// regenerated from the Philox snapshot: backward applies the same function to the gradient.  bf16 runs apply these sites
+// inside their producers (tcgen05 GEMM epilogue, ln_bwd, gamma_bwd) with the SAME element ids; this pass serves the fp32
+// run (SIMT GEMMs), shapes the tcgen05 kernel does not take, pos_drop (qavit_dropout_*), and the per-image DropPath
+// scale vector.
 #include "kernels.h"
 
 namespace {

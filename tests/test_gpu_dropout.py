@@ -153,8 +153,8 @@ def test_dropout_fn_rate_replay_and_backward():
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_model_trains_with_reference_default_dropout(precision):
-    """HQAViT with the reference's default dropout = drop_path = 0.1 (H:56-57) runs a train step; eval mode ignores it;
-    over many masks the train-mode logits average to the dropout-free ones within the Monte-Carlo error."""
+    """HQAViT with the reference's default dropout = drop_path = 0.1 (H:56-57) runs a train step with finite loss and
+    gradients, draws a different mask on the next call, and ignores dropout in eval mode."""
     import qavit_b200 as Q
     torch.manual_seed(0)
     model = Q.HQAViT(Q.HQAViTConfig()).cuda().set_precision(precision)
