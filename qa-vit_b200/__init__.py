@@ -7,7 +7,7 @@ from . import functional  # noqa: F401
 from .functional import batch_mix, cross_entropy, dropout, manual_seed, mix_batch  # noqa: F401
 from .modules import (HQAViT, HQAViTConfig, PatchEmbed, QAViT, QAViTConfig, QuadAttentionBlock,  # noqa: F401
                       QuadBlockWithTokenLearner)
-from .optim import FusedAdamW, ModelEMA, clip_grad_norms_  # noqa: F401
+from .optim import FusedAdamW, GradientMonitor, ModelEMA, clip_grad_norms_  # noqa: F401
 from .dp import GradAllReducer  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 from .transfer import adjust_positional_embedding, load_pretrained_except_head  # noqa: F401

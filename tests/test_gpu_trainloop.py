@@ -130,3 +130,33 @@ def test_mix_batch_draw_order_and_two_target_loss():
     ce = torch.nn.CrossEntropyLoss(label_smoothing=0.1)
     want = lam * ce(logits, ta) + (1.0 - lam) * ce(logits, tb)     # H:1406
     assert abs(loss.item() - want.item()) < 1e-5
+
+
+def test_gradient_monitor_drop_in_matches_reference_algorithm():
+    """GradientMonitor.log_gradients (H:197-242) restated with per-tensor torch norms vs the two-launch version."""
+    named = _toy_params(5)
+    opt = Q.FusedAdamW(named, lr=1e-3)
+    has_grad = [True, True, False, True, True, True]
+    opt.set_grad_mask(has_grad)
+    opt.zero_grad()
+    g = torch.Generator().manual_seed(9)
+    for i, (_, p) in enumerate(named):
+        p.grad.copy_(torch.randn(p.shape, generator=g).cuda() * (40.0 if i == 3 else 1.0))   # p3: norm > 10 -> detailed stats
+    mon = Q.GradientMonitor(optimizer=opt)
+    total, pnorm, grad_stats, layer_stats = mon.log_gradients(None, detailed=True)
+    want_t = sum(p.grad.norm().item() ** 2 for (n, p), h in zip(named, has_grad) if h) ** 0.5
+    want_p = sum(p.norm().item() ** 2 for (n, p), h in zip(named, has_grad) if h) ** 0.5
+    assert abs(total - want_t) < 1e-4 * want_t and abs(pnorm - want_p) < 1e-4 * want_p
+    assert mon.grad_norms == [total] and mon.param_norms == [pnorm]
+    assert set(layer_stats) == {".".join(n.split(".")[:2]) for (n, _), h in zip(named, has_grad) if h}
+    assert all(st["count"] == 1 for st in layer_stats.values())
+    big = named[3][0]
+    assert set(grad_stats) == {big} | {n for (n, p), h in zip(named, has_grad) if h and p.grad.norm().item() > 10.0}
+    gs = grad_stats[big]
+    assert abs(gs["grad_max"] - named[3][1].grad.abs().max().item()) < 1e-6 and not gs["has_nan"] and not gs["has_inf"]
+    assert set(mon.layer_grad_history) == set(layer_stats)
+    assert mon.check_explosion(threshold=want_t * 0.5) and mon.explosion_count == 1
+    assert not mon.check_explosion(threshold=want_t * 2.0)
+    named[1][1].grad[0] = float("nan")                                                   # non-finite gradients are reported
+    _, _, grad_stats, _ = mon.log_gradients(None)
+    assert grad_stats[named[1][0]]["has_nan"]
