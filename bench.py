@@ -164,7 +164,8 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "dropout": args.dropout, "drop_path": args.drop_path, "note": "CPU path of the reference step (oracle port, "
                    "pinned to the live reference's golden vectors); each step = a bounded sample of the workload"},
         "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
-                         "sample": f"{sample} images/step (of per-GPU batch {args.batch}), fp32, fwd+bwd+clip+AdamW"},
+                         "sample": f"{sample} images/step (of per-GPU batch {args.batch}), fp32, fwd+bwd+clip+AdamW, dropout {args.dropout} / "
+                                   f"drop_path {args.drop_path} masks drawn per step"},
         "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -363,7 +364,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline and args.workload == "hqavit_c100" and not infer:
             rate, dt, cores = cpu_step_rate(256, 8, 1, threads=host_threads(), dropout=args.dropout, drop_path=args.drop_path)
             cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
-                   "sample": f"256 images/step x 8 steps ({8 * dt:.1f} s of CPU work), fp32 oracle port, fwd+bwd+clip+AdamW"}
+                   "sample": f"256 images/step x 8 steps ({8 * dt:.1f} s of CPU work), fp32 oracle port, fwd+bwd+clip+AdamW, "
+                             f"dropout {args.dropout} / drop_path {args.drop_path} masks drawn per step"}
         default = args.workload == "hqavit_c100" and not infer
         metric = METRIC if default else f"{'inference' if infer else 'train'} images/sec ({wl['label']}" + (")" if infer else ", fwd+bwd+clip+AdamW)")
         workload = WORKLOAD if default else f"{wl['label']} {'eval-mode forward' if infer else 'training step'}, bf16, synthetic batch"
