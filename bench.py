@@ -10,9 +10,11 @@ over one synthetic batch of `--batch` images per GPU (weak scaling).  Prints ONE
   e2e        same step through the public API with the batch coming from pinned host memory every step
              (H2D inside the timed region) and the loss read back to the host every step
   roofline   the dominant kernel (tcgen05 projection GEMM, qkv shape) timed alone with CUDA events
-  cpu_baseline  the CPU oracle port of the reference step on the host cores, on a bounded sample
-  --impl reference   times that CPU path alone (the reference's own implementation of the step is CPU/eager
-             PyTorch; /root/reference does not exist on the GPU box, the oracle is its pinned restatement)
+  cpu_baseline  the reference training step on the host cores, on a bounded sample: the UNMODIFIED reference modules
+             from baseline/_ref (kind "reference"; `python baseline/install_ref.py` copies them in the build container,
+             the directory is git-ignored but travels to the GPU box), else the oracle port (kind "port")
+  gpu_eager_baseline  the same live reference's eager CUDA step under bf16 autocast on this GPU (like-for-like baseline)
+  --impl reference   times the CPU path alone
 """
 import argparse
 import json
@@ -115,9 +117,81 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def live_reference_available():
+    try:
+        from baseline import live_reference as LR
+        return LR.available()
+    except Exception:
+        return False
+
+
+def reference_step_rate(device, batch, steps, warmup, dropout, drop_path, threads=None, flash=None):
+    """The UNMODIFIED reference (baseline/_ref, `python baseline/install_ref.py`) driven the way its own train loop drives
+    it (HQAViT_CIFAR100.py:1401-1439): model.train(), CrossEntropyLoss(label_smoothing), per-parameter 0.1 clip of
+    cnn_stem / dwconv, global 0.5 clip, torch.optim.AdamW, zero_grad.  device 'cpu': fp32 on the host cores (BASELINE.md
+    section 4); a CUDA device: the reference's eager GPU path under torch.autocast(bfloat16) with its GradScaler, stock
+    attention selection (flash_attn when importable and head_dim % 8 == 0, else SDPA; H:359-392).  Returns
+    (images/sec, sec/step, info dict)."""
+    from baseline import live_reference as LR
+    if threads:
+        torch.set_num_threads(threads)
+    mod = LR.import_reference("HQAViT_CIFAR100", flash=flash)
+    torch.manual_seed(42)
+    model = mod.HQAViT(mod.HQAViTConfig(dropout=dropout, drop_path=drop_path))
+    if dropout == 0.0:
+        for n in ("fuse2", "fuse3", "fuse4"):
+            getattr(model, n).cat_mlp[3].p = 0.0
+    dev = torch.device(device)
+    cuda = dev.type == "cuda"
+    model = model.to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06)
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=0.12)
+    scaler = torch.amp.GradScaler("cuda", enabled=cuda)          # H:1590 GradScaler(enabled=use_amp), also with bf16
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, 3, 32, 32, generator=g).to(dev)
+    y = torch.randint(0, 100, (batch,), generator=g).to(dev)
+    clipped = [p for n, p in model.named_parameters() if "cnn_stem" in n or "dwconv" in n]
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=cuda):
+            loss = crit(model(x), y)
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        for p in clipped:
+            if p.grad is not None:
+                torch.nn.utils.clip_grad_norm_([p], max_norm=0.1)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
+        scaler.step(opt)
+        scaler.update()
+        opt.zero_grad()
+        return loss
+
+    ts = []
+    for it in range(warmup + steps):
+        if cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss = step()
+        if cuda:
+            torch.cuda.synchronize()
+        if it >= warmup:
+            ts.append(time.perf_counter() - t0)
+    dt = sum(ts) / len(ts)
+    info = {"has_flash_attn": bool(getattr(mod, "HAS_FLASH_ATTN", False)), "loss": float(loss.item()),
+            "threads": torch.get_num_threads()}
+    del model, opt
+    if cuda:
+        torch.cuda.empty_cache()
+    return batch / dt, dt, info
+
+
 def cpu_step_rate(sample_b, steps, warmup, threads=None, dropout=0.0, drop_path=0.0):
-    """The reference training step (CPU restatement, fp32, AdamW + clips) on `sample_b` images; images/sec.
-    dropout / drop_path > 0: Bernoulli masks drawn per step for every site, like the reference's nn.Dropout / SDPA."""
+    """The reference training step on the host cores, fp32, on `sample_b` images; (images/sec, sec/step, threads, kind).
+    kind "reference": the live reference modules from baseline/_ref; kind "port": the oracle restatement (only when the
+    reference copy is not installed).  dropout / drop_path > 0: masks drawn per step for every site."""
+    if live_reference_available():
+        rate, dt, info = reference_step_rate("cpu", sample_b, steps, warmup, dropout, drop_path, threads=threads)
+        return rate, dt, info["threads"], "reference"
     from oracle import qavit_oracle as O
     if threads:
         torch.set_num_threads(threads)
@@ -146,7 +220,12 @@ def cpu_step_rate(sample_b, steps, warmup, threads=None, dropout=0.0, drop_path=
         if it >= warmup:
             ts.append(time.perf_counter() - t0)
     dt = sum(ts) / len(ts)
-    return sample_b / dt, dt, torch.get_num_threads()
+    return sample_b / dt, dt, torch.get_num_threads(), "port"
+
+
+def _cpu_kind_note(kind):
+    return ("the UNMODIFIED reference modules (baseline/_ref) driven like HQAViT_CIFAR100.py:1401-1439" if kind == "reference"
+            else "oracle port of the reference step (baseline/_ref not installed)")
 
 
 def run_reference(args):
@@ -154,16 +233,17 @@ def run_reference(args):
     if rank != 0:
         return
     sample = 256
+    steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can
-    rate, dt, cores = cpu_step_rate(sample, max(1, min(args.steps, 8)), max(1, min(args.warmup, 2)), threads=host_threads(),
-                                    dropout=args.dropout, drop_path=args.drop_path)
+    rate, dt, cores, kind = cpu_step_rate(sample, steps, warm, threads=host_threads(), dropout=args.dropout, drop_path=args.drop_path)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
-        "steps": max(1, min(args.steps, 8)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "dropout": args.dropout, "drop_path": args.drop_path, "note": "CPU path of the reference step (oracle port, "
-                   "pinned to the live reference's golden vectors); each step = a bounded sample of the workload"},
-        "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "dropout": args.dropout, "drop_path": args.drop_path,
+                   "note": "CPU path of the reference step: " + _cpu_kind_note(kind) + "; each step = a bounded sample of the workload.  "
+                           "This arm is ONE host process per node whatever --gpus says: a ratio against it is only meaningful at N = 1"},
+        "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": kind,
                          "sample": f"{sample} images/step (of per-GPU batch {args.batch}), fp32, fwd+bwd+clip+AdamW, dropout {args.dropout} / "
                                    f"drop_path {args.drop_path} masks drawn per step"},
         "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -362,10 +442,24 @@ def run_ours(args):
         roof["step_frac_of_sustained_peak"] = roof["step_tflops_fmin"] / tf_sus
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.workload == "hqavit_c100" and not infer:
-            rate, dt, cores = cpu_step_rate(256, 8, 1, threads=host_threads(), dropout=args.dropout, drop_path=args.drop_path)
-            cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
-                   "sample": f"256 images/step x 8 steps ({8 * dt:.1f} s of CPU work), fp32 oracle port, fwd+bwd+clip+AdamW, "
+            rate, dt, cores, kind = cpu_step_rate(256, 8, 1, threads=host_threads(), dropout=args.dropout, drop_path=args.drop_path)
+            cpu = {"value": rate, "unit": "images/sec", "cores": cores, "kind": kind,
+                   "sample": f"256 images/step x 8 steps ({8 * dt:.1f} s of CPU work), fp32, {_cpu_kind_note(kind)}, fwd+bwd+clip+AdamW, "
                              f"dropout {args.dropout} / drop_path {args.drop_path} masks drawn per step"}
+        eager = None
+        if world == 1 and not args.no_gpu_eager_baseline and args.workload == "hqavit_c100" and not infer and live_reference_available():
+            # the like-for-like GPU baseline (SURVEY 8d / BASELINE.md 4.5): the live reference's eager CUDA path on this B200
+            eager = {"unit": "images/sec", "what": "UNMODIFIED reference (baseline/_ref) eager CUDA step, torch.autocast(bfloat16) + GradScaler, "
+                     "fwd+bwd+clips+torch.optim.AdamW (HQAViT_CIFAR100.py:1401-1439), same dropout / drop_path, batch resident"}
+            for bb in sorted({256, B}):
+                try:
+                    r, dt_e, info = reference_step_rate(dev, bb, 5, 3, args.dropout, args.drop_path)
+                    eager[f"b{bb}"] = {"value": r, "ms_per_step": dt_e * 1e3}
+                    eager["attention_path"] = ("flash_attn_func where head_dim % 8 == 0, fp32 SDPA for channel-group attention (hd 4)"
+                                               if info["has_flash_attn"] else "F.scaled_dot_product_attention (flash_attn not importable)")
+                except Exception as e:          # e.g. out of memory at the large batch: report, keep the line
+                    eager[f"b{bb}"] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+                    torch.cuda.empty_cache()
         default = args.workload == "hqavit_c100" and not infer
         metric = METRIC if default else f"{'inference' if infer else 'train'} images/sec ({wl['label']}" + (")" if infer else ", fwd+bwd+clip+AdamW)")
         workload = WORKLOAD if default else f"{wl['label']} {'eval-mode forward' if infer else 'training step'}, bf16, synthetic batch"
@@ -380,7 +474,7 @@ def run_ours(args):
                        "cuda_graph": graphed is not None},
             "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
             "final_loss": float(loss.item() if hasattr(loss, "item") else loss),
         }
         print(json.dumps(line))
@@ -402,6 +496,7 @@ def main():
     ap.add_argument("--dropout", type=float, default=DEFAULT_DROPOUT, help="config.dropout (reference default 0.1, H:56)")
     ap.add_argument("--drop-path", type=float, default=DEFAULT_DROP_PATH, help="config.drop_path (reference default 0.1, H:57)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true", help="skip timing the live reference's eager CUDA step")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the step eagerly instead of as one CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define QAVIT_ABI_VERSION 2
+#define QAVIT_ABI_VERSION 3
 
 /* Index of every parameter tensor a (TokenLearner-wrapped) quad block reads.  qavit_block_param_name(i)
  * returns the reference state_dict suffix (relative to the wrapper prefix "stageS_blocks.I." for HQAViT,
@@ -122,9 +122,17 @@ int qavit_dropout_forward(const float* x, float* y, long long n, float p, unsign
 int qavit_dropout_backward(const float* dy, float* dx, long long n, float p, const unsigned long long* snap, void* stream);
 
 /* CrossEntropyLoss(label_smoothing) with optional two-target mixup form (H:1373, 1404-1408).
- *   ya / yb: int64 class ids (yb may be NULL); loss: 1 float; dlogits may be NULL (forward only). */
-int qavit_cross_entropy(const float* logits, const long long* ya, const long long* yb, float lam, int B, int classes,
-                        float label_smoothing, float* loss, float* dlogits, void* stream);
+ *   ya / yb: int64 class ids (yb may be NULL); loss: 1 float; dlogits may be NULL (forward only).
+ *   lam_dev: optional DEVICE scalar overriding lam (the mixup weight of a CUDA-graph-replayed step).
+ *   row_loss: B floats of scratch -- rows are summed in a fixed order, the loss is bitwise reproducible.
+ *   err_flag: optional device int; bit 0 is raised when a label lies outside [0, classes) (torch asserts device-side
+ *   there); such labels are clamped, no out-of-row read happens. */
+int qavit_cross_entropy(const float* logits, const long long* ya, const long long* yb, float lam, const float* lam_dev, int B,
+                        int classes, float label_smoothing, float* loss, float* dlogits, float* row_loss, int* err_flag,
+                        void* stream);
+/* y[i] = x[i] * (*scalar_dev) (chain-rule factor of a scalar loss); cudaMemsetAsync(p, 0, bytes) on the caller's stream. */
+int qavit_scale_by_scalar(const float* x, const float* scalar_dev, long long n, float* y, void* stream);
+int qavit_memset_zero(void* p, size_t bytes, void* stream);
 
 /* Gradient clipping + AdamW on flat fp32 buffers (H:1413-1439; torch.optim.AdamW single-tensor rule).
  * The n_seg segments [seg_off[i], seg_off[i+1]) are the parameter tensors: seg_flags bit0 = has a gradient this

@@ -66,7 +66,9 @@ _SIGS = {
     "qavit_head_backward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_dropout_forward": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp]),
     "qavit_dropout_backward": (_i, [_vp, _vp, _ll, _f, _vp, _vp]),
-    "qavit_cross_entropy": (_i, [_vp, _vp, _vp, _f, _i, _i, _f, _vp, _vp, _vp]),
+    "qavit_cross_entropy": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_scale_by_scalar": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "qavit_memset_zero": (_i, [_vp, C.c_size_t, _vp]),
     "qavit_clip_grads": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _ll, _vp]),
     "qavit_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp]),
     "qavit_adamw_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp]),

@@ -893,9 +893,21 @@ extern "C" int qavit_dropout_backward(const float* dy, float* dx, long long n, f
   DropP d; d.p = p; d.rng = snap; d.site = 0x9051u;
   return drop_rows(st, QV_F32, dx, 8, n / 8, 8, d, nullptr, 1, nullptr, 0, nullptr, nullptr, 0);
 }
-extern "C" int qavit_cross_entropy(const float* logits, const long long* ya, const long long* yb, float lam, int B,
-                                   int classes, float label_smoothing, float* loss, float* dlogits, void* stream) {
-  return ce_loss_fwd_bwd((cudaStream_t)stream, logits, ya, yb, lam, B, classes, label_smoothing, loss, dlogits);
+extern "C" int qavit_cross_entropy(const float* logits, const long long* ya, const long long* yb, float lam, const float* lam_dev,
+                                   int B, int classes, float label_smoothing, float* loss, float* dlogits, float* row_loss,
+                                   int* err_flag, void* stream) {
+  QV_CHECK(logits && ya && loss, "cross_entropy: null argument");
+  return ce_loss_fwd_bwd((cudaStream_t)stream, logits, ya, yb, lam, lam_dev, B, classes, label_smoothing, loss, dlogits, row_loss, err_flag);
+}
+// y = x * (*scalar_dev): the chain-rule factor of a scalar loss (dlogits * dloss) without an ATen kernel
+extern "C" int qavit_scale_by_scalar(const float* x, const float* scalar_dev, long long n, float* y, void* stream) {
+  QV_CHECK(x && scalar_dev && y, "scale_by_scalar: null argument");
+  return scale_by_scalar((cudaStream_t)stream, x, scalar_dev, (long)n, y);
+}
+extern "C" int qavit_memset_zero(void* p, size_t bytes, void* stream) {
+  QV_CHECK(p || bytes == 0, "memset_zero: null argument");
+  if (bytes) QV_CUDA(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+  return 0;
 }
 extern "C" int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,
                                   const float* bias, void* C, int c_f32, void* stream) {

@@ -333,12 +333,17 @@ int head_bwd(cudaStream_t s, const float* x, const float* dlogits, int B, int N,
 // =============================================================================== cross entropy (H:1373, :1404-1408)
 namespace {
 // loss = mean_b [ lam * CE_ls(y_a) + (1 - lam) * CE_ls(y_b) ],  CE_ls = (1-eps) * nll + eps * mean_c(-log p_c)
+// One warp per row writes the row's loss term into row_loss[row] (no atomics); ce_reduce_kernel then sums the rows in a
+// fixed order, so the loss is bitwise reproducible run to run.  Labels outside [0, C) raise bit 0 of *err (torch asserts
+// device-side there) and are clamped so that no read leaves the row.  lam_dev (optional) overrides lam: the mixup weight
+// of a CUDA-graph-replayed step lives on the device.
 __global__ void ce_kernel(const float* __restrict__ logits, const long long* __restrict__ ya,
-                          const long long* __restrict__ yb, float lam, int B, int C, float eps, float* __restrict__ loss,
-                          float* __restrict__ dlogits) {
+                          const long long* __restrict__ yb, float lam, const float* __restrict__ lam_dev, int B, int C, float eps,
+                          float* __restrict__ row_loss, float* __restrict__ dlogits, int* __restrict__ err) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
+  if (lam_dev) lam = *lam_dev;
   const float* l = logits + (long)row * C;
   float m = -INFINITY;
   for (int c = lane; c < C; c += 32) m = fmaxf(m, l[c]);
@@ -348,12 +353,18 @@ __global__ void ce_kernel(const float* __restrict__ logits, const long long* __r
   z = warp_sum(z);
   sl = warp_sum(sl);
   const float lse = m + logf(z);
-  const int a = (int)ya[row], b2 = yb ? (int)yb[row] : a;
+  long long a64 = ya[row], b64 = yb ? yb[row] : a64;
+  if (a64 < 0 || a64 >= C || b64 < 0 || b64 >= C) {
+    if (lane == 0 && err) atomicOr(err, 1);
+    a64 = a64 < 0 ? 0 : (a64 >= C ? C - 1 : a64);
+    b64 = b64 < 0 ? 0 : (b64 >= C ? C - 1 : b64);
+  }
+  const int a = (int)a64, b2 = (int)b64;
   const float wa = yb ? lam : 1.f, wb = yb ? 1.f - lam : 0.f;
   if (lane == 0) {
     const float nll = wa * (lse - l[a]) + wb * (lse - l[b2]);
     const float smooth = lse - sl / C;
-    atomicAdd(loss, ((1.f - eps) * nll + eps * smooth) / B);
+    row_loss[row] = ((1.f - eps) * nll + eps * smooth) / B;
   }
   if (dlogits) {
     for (int c = lane; c < C; c += 32) {
@@ -364,13 +375,41 @@ __global__ void ce_kernel(const float* __restrict__ logits, const long long* __r
     }
   }
 }
+// fixed-order sum of row_loss[0 .. B): thread t adds rows t, t + 1024, ... then a fixed shared-memory tree
+__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_loss, int B, float* __restrict__ loss) {
+  __shared__ float red[1024];
+  float a = 0.f;
+  for (int i = threadIdx.x; i < B; i += 1024) a += row_loss[i];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = red[0];
+}
+__global__ void scale_by_scalar_kernel(const float* __restrict__ x, const float* __restrict__ sc, long n, float* __restrict__ y) {
+  const float s = *sc;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = x[i] * s;
+}
 }  // namespace
 
-int ce_loss_fwd_bwd(cudaStream_t s, const float* logits, const long long* ya, const long long* yb, float lam, int B,
-                    int ncls, float smoothing, float* loss, float* dlogits) {
-  QV_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
-  if (B <= 0) return 0;
-  ce_kernel<<<cdiv(B, 4), 128, 0, s>>>(logits, ya, yb, lam, B, ncls, smoothing, loss, dlogits);
+int ce_loss_fwd_bwd(cudaStream_t s, const float* logits, const long long* ya, const long long* yb, float lam, const float* lam_dev,
+                    int B, int ncls, float smoothing, float* loss, float* dlogits, float* row_loss, int* err) {
+  if (B <= 0) {
+    QV_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+    return 0;
+  }
+  QV_CHECK(row_loss, "cross_entropy: row_loss scratch (B floats) missing");
+  ce_kernel<<<cdiv(B, 4), 128, 0, s>>>(logits, ya, yb, lam, lam_dev, B, ncls, smoothing, row_loss, dlogits, err);
+  QV_LAUNCH_CHECK();
+  ce_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, B, loss);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int scale_by_scalar(cudaStream_t s, const float* x, const float* scalar_dev, long n, float* y) {
+  if (n <= 0) return 0;
+  scale_by_scalar_kernel<<<(int)min((long)qv_num_sms() * 8, (long)cdiv(n, 256)), 256, 0, s>>>(x, scalar_dev, n, y);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -266,5 +266,6 @@ int head_fwd(cudaStream_t s, const float* x, int B, int N, int d, const float* g
 int head_bwd(cudaStream_t s, const float* x, const float* dlogits, int B, int N, int d, const float* gamma,
              const float* stats, const float* pooled, const float* W, int ncls, float* dpooled_scratch, float* dx,
              float* dgamma, float* dbeta, float* dW, float* dbias);
-int ce_loss_fwd_bwd(cudaStream_t s, const float* logits, const long long* ya, const long long* yb, float lam, int B,
-                    int ncls, float smoothing, float* loss, float* dlogits);
+int ce_loss_fwd_bwd(cudaStream_t s, const float* logits, const long long* ya, const long long* yb, float lam, const float* lam_dev,
+                    int B, int ncls, float smoothing, float* loss, float* dlogits, float* row_loss, int* err);
+int scale_by_scalar(cudaStream_t s, const float* x, const float* scalar_dev, long n, float* y);   // y = x * (*scalar_dev)

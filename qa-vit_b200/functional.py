@@ -552,6 +552,30 @@ class SplitFusionFn(torch.autograd.Function):
         return (dT, dR, None, *views)
 
 
+_ce_err = {}
+
+
+def _ce_err_flag(device) -> torch.Tensor:
+    """Device int raised by the loss kernel when a label is out of range (read by check_labels())."""
+    device = torch.device(device)
+    t = _ce_err.get(device)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _ce_err[device] = t
+    return t
+
+
+def check_labels(device=None) -> None:
+    """Raise (like torch's device-side assert, but recoverable) if any cross_entropy() call since the last check saw a
+    target outside [0, classes).  One host sync; the train step itself never synchronises."""
+    for dev, t in list(_ce_err.items()):
+        if device is not None and torch.device(device) != dev:
+            continue
+        if int(t.item()) != 0:
+            t.zero_()
+            raise RuntimeError("qavit_b200.cross_entropy: target out of range [0, num_classes)")
+
+
 class CrossEntropyFn(torch.autograd.Function):
     """CrossEntropyLoss(label_smoothing) and its two-target mixup form -- HQAViT_CIFAR100.py:1373, 1404-1408."""
 
@@ -562,21 +586,31 @@ class CrossEntropyFn(torch.autograd.Function):
         B, ncls = logits.shape
         loss = torch.empty((), dtype=torch.float32, device=logits.device)
         dlogits = torch.empty_like(logits)
-        check(lib.qavit_cross_entropy(logits.data_ptr(), ya.data_ptr(), _ptr(yb), float(lam), B, ncls, float(smoothing),
-                                      loss.data_ptr(), dlogits.data_ptr(), _stream()))
+        row_loss = torch.empty(max(B, 1), dtype=torch.float32, device=logits.device)
+        lam_dev = lam if isinstance(lam, torch.Tensor) else None      # device scalar: graph-replayable mixup weight
+        if lam_dev is not None and (not lam_dev.is_cuda or lam_dev.dtype != torch.float32):
+            raise RuntimeError("qavit_b200.cross_entropy: a tensor `lam` must be a CUDA float32 scalar")
+        check(lib.qavit_cross_entropy(logits.data_ptr(), ya.data_ptr(), _ptr(yb), 1.0 if lam_dev is not None else float(lam),
+                                      _ptr(lam_dev), B, ncls, float(smoothing), loss.data_ptr(), dlogits.data_ptr(),
+                                      row_loss.data_ptr(), _ce_err_flag(logits.device).data_ptr(), _stream()))
         ctx.save_for_backward(dlogits)
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
         (dlogits,) = ctx.saved_tensors
-        return dlogits * dloss, None, None, None, None
+        dloss = dloss.float().contiguous()
+        out = torch.empty_like(dlogits)
+        check(lib.qavit_scale_by_scalar(dlogits.data_ptr(), dloss.data_ptr(), dlogits.numel(), out.data_ptr(), _stream()))
+        return out, None, None, None, None
 
 
 def cross_entropy(logits: torch.Tensor, target: torch.Tensor, label_smoothing: float = 0.0,
-                  target_b: Optional[torch.Tensor] = None, lam: float = 1.0) -> torch.Tensor:
+                  target_b: Optional[torch.Tensor] = None, lam=1.0) -> torch.Tensor:
     """Drop-in for ``nn.CrossEntropyLoss(label_smoothing=...)(logits, target)``; with ``target_b`` the
-    ``lam * CE(a) + (1 - lam) * CE(b)`` mixup form of the reference's train loop."""
+    ``lam * CE(a) + (1 - lam) * CE(b)`` mixup form of the reference's train loop.  ``lam`` may be a CUDA float32 scalar
+    tensor (read on the device: a captured step can change it between replays).  Out-of-range targets raise a device
+    flag that ``check_labels()`` turns into a RuntimeError; the loss is summed in a fixed order (bitwise reproducible)."""
     ya = target.to(torch.int64).contiguous()
     yb = None if target_b is None else target_b.to(torch.int64).contiguous()
     return CrossEntropyFn.apply(logits, ya, yb, lam, label_smoothing)

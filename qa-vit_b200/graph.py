@@ -17,12 +17,16 @@ class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, opt, example_x: torch.Tensor, example_y: torch.Tensor,
                  label_smoothing: float = 0.0, autocast_bf16: bool = True, warmup: int = 3,
                  before_backward: Optional[Callable[[], None]] = None, after_backward: Optional[Callable[[], None]] = None,
-                 capture_error_mode: str = "global", between: Optional[Callable[[], None]] = None):
+                 capture_error_mode: str = "global", between: Optional[Callable[[], None]] = None, mix: bool = False):
         """between: called eagerly between backward and clip + AdamW (the data-parallel gradient all-reduce).  The step is
-        then two graphs -- [zero_grad, forward, loss, backward] and [clip, AdamW] -- with the collective outside both."""
+        then two graphs -- [zero_grad, forward, loss, backward] and [clip, AdamW] -- with the collective outside both.
+        mix: capture the two-target loss lam * CE(y) + (1 - lam) * CE(y_b) of the reference's CutMix / MixUp branch
+        (H:1404-1408); y_b and lam are per-step inputs of __call__ (lam travels with the optimizer's per-step scalars)."""
         self.model, self.opt = model, opt
         self.x = example_x.clone()
         self.y = example_y.clone()
+        self.mix = mix
+        self.yb = example_y.clone() if mix else None
         self.ls, self.amp = label_smoothing, autocast_bf16
         self._bb, self._ab, self._between = before_backward, after_backward, between
         self.loss = torch.zeros((), device=self.x.device)
@@ -30,6 +34,8 @@ class GraphedTrainStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
+                if mix:
+                    self.opt.hyper[9] = 1.0
                 self._step_body(eager=True)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
@@ -55,7 +61,10 @@ class GraphedTrainStep:
             self._bb()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
             logits = self.model(self.x)
-        loss = cross_entropy(logits, self.y, label_smoothing=self.ls)
+        if self.mix:
+            loss = cross_entropy(logits, self.y, label_smoothing=self.ls, target_b=self.yb, lam=self.opt.hyper[9])
+        else:
+            loss = cross_entropy(logits, self.y, label_smoothing=self.ls)
         loss.backward()
         if self._ab:
             self._ab()
@@ -71,14 +80,23 @@ class GraphedTrainStep:
             self._between()
         self._update()
 
-    def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Run one training step on (x, y) (host or device tensors; None = reuse the resident batch)."""
+    def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
+                 y_b: Optional[torch.Tensor] = None, lam: float = 1.0) -> torch.Tensor:
+        """Run one training step on (x, y) (host or device tensors; None = reuse the resident batch).  With mix=True,
+        (y_b, lam) select the two-target loss of this step (y_b None: plain CE, lam = 1)."""
         if x is not None:
             self.x.copy_(x, non_blocking=True)
         if y is not None:
             self.y.copy_(y, non_blocking=True)
-        self.opt.write_hyper()          # lr / beta1 / bias corrections of THIS step -> pinned memory the graph reads
-        self.graph.replay()
+        if self.mix:
+            if y_b is not None:
+                self.yb.copy_(y_b, non_blocking=True)
+            else:
+                lam = 1.0
+        elif y_b is not None:
+            raise RuntimeError("GraphedTrainStep: build with mix=True to use a second target")
+        self.opt.push_hyper(lam)         # lr / beta1 / bias corrections of THIS step -> device buffer (pinned ring + H2D copy
+        self.graph.replay()             #   in stream order BEFORE the replay; the graph itself holds no H2D node)
         if self.graph2 is not None:
             self._between()
             self.graph2.replay()

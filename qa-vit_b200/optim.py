@@ -14,6 +14,11 @@ import torch
 
 from ._lib import check, lib
 
+# parameters the reference never trains: GlobalTokenBank.write runs under no_grad (H:296-321) and the branch `.norm` only
+# feeds it, so autograd leaves their .grad at None and torch.optim.AdamW skips them, weight decay included
+NO_GRAD_NAME_PARTS = ("swa.norm.", "msda.norm.", "cga.norm.", "write_norm.", "write_compression.", "write_gate.")
+_HYPER_SLOTS = 4
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -29,8 +34,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self.names = [n for n, _ in named]
         params = [p for _, p in named]
         dev = params[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("FusedAdamW needs CUDA parameters (no CPU path)")
+        # CPU parameters are accepted for the host-side logic only (state_dict round trips, bucket layout tests);
+        # clip() / step() raise there: the arithmetic has no CPU path
+        self._cuda = dev.type == "cuda"
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.max_grad_norm, self.per_param_clip = max_grad_norm, per_param_clip
         offs, off = [], 0
@@ -57,12 +63,20 @@ class FusedAdamW(torch.optim.Optimizer):
         clip_bit = [2 if any(s in n for s in per_param_clip_names) else 0 for n in self.names]
         self._clip_bits = clip_bit
         self.seg_flags = torch.zeros(len(params), dtype=torch.int32, device=dev)
-        self._flags_host = torch.zeros(len(params), dtype=torch.int32).pin_memory()
+        pin = (lambda t: t.pin_memory()) if self._cuda else (lambda t: t)
+        self._flags_host = pin(torch.zeros(len(params), dtype=torch.int32))
         self.norms = torch.zeros(len(params) + 2, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(12, dtype=torch.float32).pin_memory()
+        # per-step scalars travel through a RING of pinned slots, each guarded by an event recorded after its H2D copy: the
+        # host may run up to _HYPER_SLOTS steps ahead of the GPU without rewriting a slot a pending copy still has to read
+        self._hyper_ring = [pin(torch.zeros(12, dtype=torch.float32)) for _ in range(_HYPER_SLOTS)]
+        self._hyper_evt = [None] * _HYPER_SLOTS
+        self._hyper_i = 0
+        self._hyper_host = self._hyper_ring[0]            # the slot written last (kept for introspection / tests)
         self.hyper = torch.zeros(12, dtype=torch.float32, device=dev)
         self.step_count = 0
         self._have_flags = False
+        self._user_mask = False
+        self._default_mask = [not any(s in n for s in NO_GRAD_NAME_PARTS) for n in self.names]
         self.flat_ema: Optional[torch.Tensor] = None      # enable_ema(): EMA of flat_p, updated inside the step kernel
         self.ema_decay = 0.0
         self._all_flags = torch.ones(len(params), dtype=torch.int32, device=dev)
@@ -101,7 +115,10 @@ class FusedAdamW(torch.optim.Optimizer):
     def attach_grads(self):
         """Point every .grad at its slice of the flat gradient buffer (zeroed): autograd then accumulates in place
         and the DP all-reduce / clip / AdamW kernels see one contiguous tensor."""
-        self.flat_g.zero_()
+        if self._cuda:
+            check(lib.qavit_memset_zero(self.flat_g.data_ptr(), self.flat_g.numel() * 4, _stream()))
+        else:
+            self.flat_g.zero_()
         for p, g in zip(self.param_groups[0]["params"], self._gviews):
             p.grad = g
 
@@ -109,22 +126,34 @@ class FusedAdamW(torch.optim.Optimizer):
         self.attach_grads()
 
     def _sync_flags(self, grads_present: Optional[Sequence[bool]] = None):
+        """seg_flags bit 0 = "this parameter has a gradient".  Without an explicit mask: .grad is not None -- except that an
+        ATTACHED gradient view (attach_grads() makes every .grad non-None) only counts for parameters the reference trains
+        (NO_GRAD_NAME_PARTS: the bank's write_* and the branch .norm stay grad=None there and are skipped by AdamW)."""
         params = self.param_groups[0]["params"]
-        for i, p in enumerate(params):
-            has = (p.grad is not None) if grads_present is None else grads_present[i]
+        for i, (p, gv) in enumerate(zip(params, self._gviews)):
+            if grads_present is not None:
+                has = grads_present[i]
+            elif p.grad is None:
+                has = False
+            elif p.grad.data_ptr() == gv.data_ptr():
+                has = self._default_mask[i]
+            else:
+                has = True
             self._flags_host[i] = (1 if has else 0) | self._clip_bits[i]
         self.seg_flags.copy_(self._flags_host, non_blocking=True)
         self._have_flags = True
 
     def set_grad_mask(self, has_grad: Sequence[bool]):
-        """With attach_grads() every .grad is non-None; the set of parameters the reference leaves at grad=None
-        (bank write_* and branch .norm) must then be declared so AdamW skips them as torch does."""
+        """Explicit has-gradient mask (overrides the name-derived default used with attached gradients)."""
+        self._user_mask = True
         self._sync_flags(list(has_grad))
 
     @torch.no_grad()
     def clip(self) -> torch.Tensor:
         """Per-parameter clip (names containing cnn_stem / dwconv, to 0.1) then global clip to max_grad_norm.
         Returns the device scalar of the global norm (what clip_grad_norm_ returns); no host sync."""
+        if not self._cuda:
+            raise RuntimeError("FusedAdamW.clip: CPU parameters -- the optimizer arithmetic has no CPU path")
         self._gather_foreign_grads()
         if not self._have_flags:
             self._sync_flags()
@@ -140,26 +169,43 @@ class FusedAdamW(torch.optim.Optimizer):
                 g.copy_(p.grad)
                 p.grad = g
 
-    def write_hyper(self):
-        """Advance the step counter and write this step's scalars (lr, betas, eps, wd, bias corrections) into the pinned
-        host buffer the step kernel's H2D copy reads -- the only per-step host work when the step is graph-replayed."""
+    def push_hyper(self, lam: Optional[float] = None):
+        """Advance the step counter and send this step's scalars (lr, betas, eps, wd, bias corrections) to the device buffer
+        the step kernel reads: written into the next pinned ring slot (after waiting for the copy that last read that slot),
+        copied H2D on the current stream, and the slot's event re-recorded.  Stream order protects the device buffer (the
+        previous step's kernel has run before this copy lands); the ring protects the host buffer.  This is the only
+        per-step host work when the step is graph-replayed (GraphedTrainStep calls it before every replay)."""
         grp = self.param_groups[0]
         self.step_count += 1
         b1, b2 = grp["betas"]
         t = self.step_count
-        h = self._hyper_host
+        k = self._hyper_i
+        self._hyper_i = (k + 1) % _HYPER_SLOTS
+        if self._hyper_evt[k] is not None:
+            self._hyper_evt[k].synchronize()
+        h = self._hyper_ring[k]
         h[0], h[1], h[2], h[3], h[4] = grp["lr"], b1, b2, grp["eps"], grp["weight_decay"]
         h[5], h[6] = 1.0 - b1 ** t, 1.0 - b2 ** t
         h[7], h[8] = self.ema_decay, 1.0 - self.ema_decay
+        h[9] = 1.0 if lam is None else float(lam)     # CutMix / MixUp weight of this step (GraphedTrainStep(mix=True) reads hyper[9])
+        self._hyper_host = h
+        self.hyper.copy_(h, non_blocking=True)
+        if self._cuda:
+            if self._hyper_evt[k] is None:
+                self._hyper_evt[k] = torch.cuda.Event()
+            self._hyper_evt[k].record()
+
+    write_hyper = push_hyper      # former name
 
     @torch.no_grad()
     def step(self, closure=None):
+        if not self._cuda:
+            raise RuntimeError("FusedAdamW.step: CPU parameters -- the optimizer arithmetic has no CPU path")
         self._gather_foreign_grads()
         if not self._have_flags:
             self._sync_flags()
         if not torch.cuda.is_current_stream_capturing():
-            self.write_hyper()
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+            self.push_hyper()         # a captured step reads self.hyper, which the replaying caller refreshes eagerly
         if self.flat_ema is not None:
             check(lib.qavit_adamw_ema_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
                                            self.exp_avg_sq.data_ptr(), self.flat_ema.data_ptr(), self.seg_off.data_ptr(),
@@ -169,6 +215,62 @@ class FusedAdamW(torch.optim.Optimizer):
                                        self.seg_off.data_ptr(), self.seg_flags.data_ptr(), len(self.names), self.hyper.data_ptr(),
                                        self.total, _stream()))
         return None
+
+
+    # ------------------------------------------------------------------ checkpoint compatibility with torch.optim.AdamW
+    def state_dict(self):
+        """torch.optim.AdamW's layout (the reference checkpoints ``optimizer.state_dict()``, H:1692 / 1728): per parameter
+        index ``{'step', 'exp_avg', 'exp_avg_sq'}`` (copies out of the flat buffers) for every parameter that has been
+        stepped, plus the param group.  A checkpoint written here loads into torch.optim.AdamW and vice versa."""
+        offs = self.seg_off.tolist()
+        params = self.param_groups[0]["params"]
+        state = {}
+        if self.step_count > 0:
+            flags = self._flags_host.tolist()
+            for i, p in enumerate(params):
+                if not (int(flags[i]) & 1):
+                    continue                      # never received a gradient: torch holds no state for it either
+                o, n = offs[i], p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(params)))
+        out = {"state": state, "param_groups": [group]}
+        if self.flat_ema is not None:
+            out["qavit_ema"] = {"decay": self.ema_decay, "flat": self.flat_ema.clone()}
+        return out
+
+    def load_state_dict(self, sd):
+        """Accepts the dict above or one written by torch.optim.AdamW over the same parameter list (same order)."""
+        groups = sd["param_groups"]
+        params = self.param_groups[0]["params"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(params):
+            raise ValueError(f"loaded state dict holds {len(order)} parameters, this optimizer {len(params)}")
+        g0 = groups[0]
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in g0:
+                self.param_groups[0][k] = tuple(g0[k]) if k == "betas" else g0[k]
+        offs = self.seg_off.tolist()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        pos = {pid: i for i, pid in enumerate(order)}
+        for pid, st in sd["state"].items():
+            i = pos[pid]
+            o, n = offs[i], params[i].numel()
+            if tuple(st["exp_avg"].shape) != tuple(params[i].shape):
+                raise ValueError(f"state of parameter {self.names[i]}: shape {tuple(st['exp_avg'].shape)} != {tuple(params[i].shape)}")
+            self.exp_avg[o:o + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): one shared counter is kept here")
+        self.step_count = steps.pop() if steps else 0
+        if "qavit_ema" in sd:
+            self.enable_ema(sd["qavit_ema"]["decay"]).copy_(sd["qavit_ema"]["flat"])
+        self.state.clear()
 
 
 def clip_grad_norms_(opt: FusedAdamW) -> torch.Tensor:

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/qavit_b200.h but not exported"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.qavit_abi_version() == 2
+    assert lib.qavit_abi_version() == 3
 
 
 def test_param_table_names_exist_in_reference_schema():

@@ -1,0 +1,119 @@
+"""Parity against the LIVE, unmodified reference nn.Modules running on the same B200 (baseline/_ref, installed by
+baseline/install_ref.py): same reference-initialised weights (torch.manual_seed(42), H:1770), same batch.
+
+  fp32 run  vs reference fp32 (TF32 off):                logits 1e-4 (max-norm), argmax exact, all gradients 1e-4
+  bf16 run  vs reference fp32:                           logits 1e-2, all gradients 1e-2  (north-star tolerances)
+  reported next to it: the reference's own torch.autocast(bfloat16) run (SDPA branch of efficient_attention,
+  H:382-392) against its fp32 run -- the bf16 noise floor of the reference graph on this GPU.
+"""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from baseline import live_reference as LR  # noqa: E402
+from util import rel_l2, rel_max  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not LR.available(), reason="baseline/_ref not installed")]
+
+# name: (reference module, config overrides, our ctor, batch, image size)
+LIVE_CASES = {
+    "hqavit_c100": ("HQAViT_CIFAR100", {}, lambda Q, c: Q.HQAViT(c), 16),
+    "qavitv2_c100": ("QAViTv2_CIFAR100", {}, lambda Q, c: Q.QAViT(c, variant="v2"), 16),
+}
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def _run_ref(model, x, y, autocast):
+    m = copy.deepcopy(model).cuda().train()
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=0.1)
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.bfloat16):       # the reference's train loop, H:1401-1408
+            logits = m(x)
+            loss = crit(logits, y)
+    else:
+        logits = m(x)
+        loss = crit(logits, y)
+    loss.backward()
+    grads = {n: (None if p.grad is None else p.grad.detach().float().clone()) for n, p in m.named_parameters()}
+    return logits.detach().float(), loss.item(), grads, m
+
+
+def _run_ours(Q, ctor, rcfg, state, x, y, precision):
+    m = ctor(Q, rcfg)
+    for n in ("fuse2", "fuse3", "fuse4"):
+        if hasattr(m, n):
+            getattr(m, n).cat_mlp[3].p = 0.0
+    m.load_state_dict(state, strict=True)
+    m = m.cuda().train().set_precision(precision)
+    if precision == "bf16":
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = m(x)
+    else:
+        logits = m(x)
+    loss = Q.cross_entropy(logits, y, label_smoothing=0.1)
+    loss.backward()
+    grads = {n: (None if p.grad is None else p.grad.detach().float().clone()) for n, p in m.named_parameters()}
+    return logits.detach().float(), loss.item(), grads, m
+
+
+def _grad_err(a, ref):
+    num = den = 0.0
+    for n, g in ref.items():
+        if g is None:
+            continue
+        num += (a[n] - g).norm().item() ** 2
+        den += g.norm().item() ** 2
+    return (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("case", list(LIVE_CASES))
+def test_against_live_reference_on_gpu(case):
+    import qavit_b200 as Q
+    mod_name, over, ctor, B = LIVE_CASES[case]
+    mod, ref = LR.build(mod_name, **over)
+    rcfg = ref.config
+    state = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, rcfg.in_channels, rcfg.img_size, rcfg.img_size, generator=g).cuda()
+    y = torch.randint(0, rcfg.num_classes, (B,), generator=g).cuda()
+
+    r32_logits, r32_loss, r32_g, r32_m = _run_ref(ref, x, y, autocast=False)
+    r16_logits, r16_loss, r16_g, _ = _run_ref(ref, x, y, autocast=True)
+    o32_logits, o32_loss, o32_g, o32_m = _run_ours(Q, ctor, rcfg, state, x, y, "fp32")
+    o16_logits, o16_loss, o16_g, o16_m = _run_ours(Q, ctor, rcfg, state, x, y, "bf16")
+
+    for n, gr in r32_g.items():
+        assert (o32_g[n] is None) == (gr is None), n
+        assert (o16_g[n] is None) == (gr is None), n
+
+    e32, g32 = rel_max(o32_logits, r32_logits), _grad_err(o32_g, r32_g)
+    e16, g16 = rel_max(o16_logits, r32_logits), _grad_err(o16_g, r32_g)
+    l16 = rel_l2(o16_logits, r32_logits)
+    f16, fg16, fl16 = rel_max(r16_logits, r32_logits), _grad_err(r16_g, r32_g), rel_l2(r16_logits, r32_logits)
+    print(f"\nlive {case}: fp32 ours-vs-ref logits {e32:.2e} grads {g32:.2e} | bf16 ours-vs-ref-fp32 logits {e16:.2e} (l2 {l16:.2e}) "
+          f"grads {g16:.2e} | reference autocast-vs-fp32 logits {f16:.2e} (l2 {fl16:.2e}) grads {fg16:.2e} | "
+          f"ours-bf16 vs ref-autocast logits {rel_max(o16_logits, r16_logits):.2e} grads {_grad_err(o16_g, r16_g):.2e}")
+    # fp32 gate
+    assert e32 < 1e-4 and g32 < 1e-4, (e32, g32)
+    assert abs(o32_loss - r32_loss) < 2e-5
+    assert (o32_logits.argmax(-1) == r32_logits.argmax(-1)).all()
+    assert rel_max(o32_m.global_bank.global_k.data, r32_m.global_bank.global_k.data) < 1e-5
+    assert rel_max(o32_m.global_bank.global_v.data, r32_m.global_bank.global_v.data) < 1e-5
+    if hasattr(r32_m.global_bank, "update_count"):
+        assert int(o32_m.global_bank.update_count) == int(r32_m.global_bank.update_count)
+    # bf16 gate: the north star's 1e-2 against the fp32 reference, on logits and on all gradients together
+    assert e16 < 1e-2 and g16 < 1e-2, (e16, g16)
+    assert abs(o16_loss - r32_loss) < 1e-2 * abs(r32_loss)
+    assert rel_max(o16_m.global_bank.global_k.data, r32_m.global_bank.global_k.data) < 1e-2

@@ -160,3 +160,132 @@ def test_gradient_monitor_drop_in_matches_reference_algorithm():
     named[1][1].grad[0] = float("nan")                                                   # non-finite gradients are reported
     _, _, grad_stats, _ = mon.log_gradients(None)
     assert grad_stats[named[1][0]]["has_nan"]
+
+
+# ------------------------------------------------------------------------------------------------ round-2 additions
+def test_per_step_scalars_do_not_leak_across_steps_when_the_host_runs_ahead():
+    """lr / beta1 / bias corrections travel through a ring of pinned slots + an H2D copy in stream order, so a
+    host that enqueues many graph replays ahead of the GPU cannot make step t read the scalars of step t + k."""
+    named = _toy_params(5)
+    ref = [p.detach().clone().requires_grad_(True) for _, p in named]
+    opt = Q.FusedAdamW(named, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05)
+    topt = torch.optim.AdamW(ref, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05)
+    opt.zero_grad()
+    g = torch.Generator().manual_seed(2)
+    for (_, p), r in zip(named, ref):
+        gr = torch.randn(p.shape, generator=g).cuda()
+        p.grad.copy_(gr)
+        r.grad = gr.clone()
+    opt.set_grad_mask([True] * len(named))
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        opt.step()                      # warm-up outside capture (advances the counter once, mirrored below)
+    torch.cuda.current_stream().wait_stream(s)
+    topt.step()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        opt.step()
+    lrs = [1e-3 * (1 + 7 * (i % 3)) for i in range(24)]
+    b1s = [0.85 + 0.01 * (i % 5) for i in range(24)]
+    busy = torch.randn(8192, 8192, device="cuda")
+    for _ in range(20):                 # ~100 ms of queued work: the host now runs far ahead of the GPU
+        busy = busy @ busy * 1e-4
+    for lr, b1 in zip(lrs, b1s):
+        opt.param_groups[0]["lr"] = lr
+        opt.param_groups[0]["betas"] = (b1, 0.999)
+        opt.push_hyper()
+        graph.replay()
+    torch.cuda.synchronize()
+    for lr, b1 in zip(lrs, b1s):
+        topt.param_groups[0]["lr"] = lr
+        topt.param_groups[0]["betas"] = (b1, 0.999)
+        topt.step()
+    for (n, p), r in zip(named, ref):
+        assert torch.allclose(p.detach(), r.detach(), rtol=1e-5, atol=1e-6), n
+
+
+def test_optimizer_state_dict_resumes_like_torch_adamw():
+    named = _toy_params(6)
+    ref = [p.detach().clone().requires_grad_(True) for _, p in named]
+    opt = Q.FusedAdamW(named, lr=2e-3, betas=(0.9, 0.999), weight_decay=0.05)
+    g = torch.Generator().manual_seed(4)
+
+    def grads():
+        return [torch.randn(p.shape, generator=g).cuda() for _, p in named]
+
+    opt.set_grad_mask([True] * len(named))
+    for _ in range(2):
+        opt.zero_grad()
+        for (_, p), gr in zip(named, grads()):
+            p.grad.copy_(gr)
+        opt.step()
+    sd = opt.state_dict()
+    # resume in torch.optim.AdamW from OUR checkpoint ...
+    cur = [p.detach().clone().requires_grad_(True) for _, p in named]
+    topt = torch.optim.AdamW(cur, lr=1.0)
+    topt.load_state_dict(sd)
+    # ... and in a fresh FusedAdamW from a torch-format checkpoint
+    named2 = [(n, torch.nn.Parameter(p.detach().clone())) for n, p in named]
+    opt2 = Q.FusedAdamW(named2, lr=1.0)
+    opt2.load_state_dict(topt.state_dict())
+    opt2.set_grad_mask([True] * len(named))
+    for _ in range(2):
+        gs = grads()
+        opt.zero_grad()
+        opt2.zero_grad()
+        for (_, p), (_, p2), r, gr in zip(named, named2, cur, gs):
+            p.grad.copy_(gr)
+            p2.grad.copy_(gr)
+            r.grad = gr.clone()
+        opt.step()
+        opt2.step()
+        topt.step()
+    for (n, p), (_, p2), r in zip(named, named2, cur):
+        assert torch.allclose(p.detach(), r.detach(), rtol=2e-6, atol=1e-7), n
+        assert torch.equal(p.detach(), p2.detach()), n
+
+
+def test_cross_entropy_flags_out_of_range_targets_and_is_bitwise_reproducible():
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(4736, 100, generator=g).cuda()
+    y = torch.randint(0, 100, (4736,), generator=g).cuda()
+    a = Q.cross_entropy(logits, y, label_smoothing=0.1)
+    for _ in range(5):
+        assert torch.equal(Q.cross_entropy(logits, y, label_smoothing=0.1), a)        # fixed-order reduction
+    assert abs(a.item() - torch.nn.functional.cross_entropy(logits, y, label_smoothing=0.1).item()) < 1e-5
+    Q.functional.check_labels()                                                      # all in range: no error
+    bad = y.clone()
+    bad[17] = 100
+    Q.cross_entropy(logits, bad, label_smoothing=0.1)
+    with pytest.raises(RuntimeError, match="out of range"):
+        Q.functional.check_labels()
+    Q.functional.check_labels()                                                      # flag was cleared
+    # lam as a device scalar == lam as a float
+    yb = torch.randint(0, 100, (4736,), generator=g).cuda()
+    lam_t = torch.tensor(0.3, device="cuda")
+    assert torch.equal(Q.cross_entropy(logits, y, 0.1, target_b=yb, lam=lam_t), Q.cross_entropy(logits, y, 0.1, target_b=yb, lam=0.3))
+    lg = logits.clone().requires_grad_(True)
+    (Q.cross_entropy(lg, y, label_smoothing=0.1) * 2.5).backward()
+    lt = logits.clone().requires_grad_(True)
+    (torch.nn.functional.cross_entropy(lt, y, label_smoothing=0.1) * 2.5).backward()
+    assert torch.allclose(lg.grad, lt.grad, rtol=1e-4, atol=1e-9)
+
+
+def test_graphed_step_supports_the_two_target_mixup_loss():
+    import copy
+    model, ocfg, sd, _ = build_model("qavitv2_c100", precision="fp32")
+    model.train()
+    B = 4
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, 3, 32, 32, generator=g).cuda()
+    y = torch.randint(0, 100, (B,), generator=g).cuda()
+    yb = torch.randint(0, 100, (B,), generator=g).cuda()
+    opt = Q.FusedAdamW(model.named_parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, max_grad_norm=0.5)
+    step = Q.GraphedTrainStep(model, opt, x, y, label_smoothing=0.1, autocast_bf16=False, warmup=2, mix=True)
+    for lam, second in ((0.3, yb), (1.0, None), (0.75, yb)):
+        snap = copy.deepcopy(model)
+        want = Q.cross_entropy(snap(x), y, label_smoothing=0.1, target_b=second, lam=lam).item()
+        got = step(x, y, y_b=second, lam=lam).item()
+        assert abs(got - want) < 2e-5 * max(1.0, abs(want)), (lam, got, want)
