@@ -142,6 +142,19 @@ int qavit_memset_zero(void* p, size_t bytes, void* stream);
  * norm before the global clip, norms[n_seg + 1] the global clip coefficient. */
 int qavit_clip_grads(float* grads, const long long* seg_off, const int* seg_flags, int n_seg, float per_param_max,
                      float max_norm, float* norms, long long total_elems, void* stream);
+/* Same with a factor `prescale` every gradient carries before clipping (1 / world_size when the buffer holds the SUM over
+ * data-parallel ranks): norms and clip coefficients are those of prescale * g and the factor is folded into the one
+ * scaling pass (the data-parallel mean costs no extra kernel). */
+int qavit_clip_grads_scaled(float* grads, const long long* seg_off, const int* seg_flags, int n_seg, float per_param_max,
+                            float max_norm, float prescale, float* norms, long long total_elems, void* stream);
+/* transforms.ToTensor() + transforms.Normalize(mean, std) of a whole batch on the device (H:1300; HQAViT_C100_Finetune.py:100-116):
+ * out[b, c, y, x] = (in / 255 - mean[c]) / std[c], one rounding per torch op (bit-identical to the torchvision pipeline);
+ * hflip != 0 mirrors every image (RandomHorizontalFlip(p = 1), the second TTA view).  in_kind 0: uint8 [B, H, W, C], 1: uint8
+ * [B, C, H, W], 2: float [B, C, H, W] already in [0, 1].  out: float [B, C, H, W], must not alias in. */
+int qavit_normalize_images(const void* in, int in_kind, int B, int C, int H, int W, const float* mean, const float* stdv, int hflip,
+                           float* out, void* stream);
+/* y[i] = scale * x[i] (bank state averaged over data-parallel ranks: tail of the gradient buffer -> global_k / global_v). */
+int qavit_scaled_copy(const float* x, float scale, long long n, float* y, void* stream);
 int qavit_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const long long* seg_off,
                      const int* seg_flags, int n_seg, const float* hyper /* device: lr, beta1, beta2, eps, wd, bc1, bc2 */,
                      long long total_elems, void* stream);
@@ -224,6 +237,11 @@ int qavit_splitfusion_forward(const qavit_splitfusion_cfg* cfg, const void* cons
 int qavit_splitfusion_backward(const qavit_splitfusion_cfg* cfg, const void* const* params, float* const* grads, const float* T_in,
                                const float* R, const float* dout, float* dT, float* dR, const void* saved, void* scratch,
                                void* stream);
+
+/* Test hook for the fused TokenLearner / TokenUpMix kernels of bf16 runs (H:971-1031; 16 learned tokens, <= 64 stream tokens,
+ * 192 channels).  op 0 / 1 = TokenLearner forward / backward, 2 / 3 = TokenUpMix + LayerNorm forward / backward; `in` / `out` are
+ * arrays of fp32 device pointers in the order documented next to the definition (csrc/block.cu). */
+int qavit_test_tokens_fused(int op, int B, int N, int C, const float* const* in, float* const* out, void* stream);
 
 /* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
 int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,

@@ -11,6 +11,7 @@ from .optim import FusedAdamW, GradientMonitor, ModelEMA, clip_grad_norms_  # no
 from .dp import GradAllReducer  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 from .transfer import adjust_positional_embedding, load_pretrained_except_head  # noqa: F401
+from .evalutil import normalize_batch, tta_views, validate_tta  # noqa: F401
 
 __all__ = ["QAViT", "HQAViT", "QAViTConfig", "HQAViTConfig", "QuadAttentionBlock", "QuadBlockWithTokenLearner",
            "PatchEmbed", "cross_entropy", "FusedAdamW", "clip_grad_norms_", "GradAllReducer", "GraphedTrainStep"]

@@ -70,6 +70,9 @@ _SIGS = {
     "qavit_scale_by_scalar": (_i, [_vp, _vp, _ll, _vp, _vp]),
     "qavit_memset_zero": (_i, [_vp, C.c_size_t, _vp]),
     "qavit_clip_grads": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp, _ll, _vp]),
+    "qavit_clip_grads_scaled": (_i, [_vp, _vp, _vp, _i, _f, _f, _f, _vp, _ll, _vp]),
+    "qavit_normalize_images": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "qavit_scaled_copy": (_i, [_vp, _f, _ll, _vp, _vp]),
     "qavit_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp]),
     "qavit_adamw_ema_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _vp]),
     "qavit_segment_norms": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
@@ -92,6 +95,7 @@ _SIGS = {
     "qavit_test_gemm_nt": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "qavit_test_gemm_epi": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "qavit_test_gemm_tn": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "qavit_test_tokens_fused": (_i, [_i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "qavit_convert_weight": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

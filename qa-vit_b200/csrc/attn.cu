@@ -18,6 +18,7 @@ constexpr int NW = NT / 32;
 
 struct Lay {  // shared-memory carve-up (float offsets), computed on host and passed by value
   int HDP, NKV, SP, QC, nq, L;
+  int e_smem;   // E_k / E_v (and their gradient accumulators) staged in shared memory; 0: read from / atomically added to global
   int oEk, oEv, odEk, odEv, oKs, oVs, oKf, oVf, odKf, odVf, oQ, odO, oP, odS, odbk, odbv, oRow, total;
 };
 
@@ -67,7 +68,7 @@ __device__ void build_kv(const AttnP& p, const Lay& ly, float* sm, const int* ro
     Vf[(p.klin + j) * HDP + d] = p.bank_v[j * D + h * HD + d];
   }
   __syncthreads();
-  const float *Ek = sm + ly.oEk, *Ev = sm + ly.oEv;
+  const float *Ek = ly.e_smem ? sm + ly.oEk : p.Ek, *Ev = ly.e_smem ? sm + ly.oEv : p.Ev;
   for (int idx = tid; idx < p.klin * HD; idx += NT) {
     const int j = idx / HD, d = idx % HD;
     float ak = 0.f, av = 0.f;
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnP p, Lay ly, int ntask
   extern __shared__ float sm[];
   const int tid = threadIdx.x, HDP = ly.HDP;
   int* rows = reinterpret_cast<int*>(sm + ly.oRow);
-  if (p.mode != 2) {
+  if (p.mode != 2 && ly.e_smem) {
     for (int idx = tid; idx < ly.L * p.klin; idx += NT) { sm[ly.oEk + idx] = p.Ek[idx]; sm[ly.oEv + idx] = p.Ev[idx]; }
   }
   const float scale = rsqrtf((float)HD);
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int HDP = ly.HDP, NKV = ly.NKV, SP = ly.SP, D = p.H * HD;
   int* rows = reinterpret_cast<int*>(sm + ly.oRow);
-  if (p.mode != 2) {
+  if (p.mode != 2 && ly.e_smem) {
     for (int idx = tid; idx < ly.L * p.klin; idx += NT) {
       sm[ly.oEk + idx] = p.Ek[idx]; sm[ly.oEv + idx] = p.Ev[idx];
       sm[ly.odEk + idx] = 0.f; sm[ly.odEv + idx] = 0.f;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask
       sm[ly.odbv + j * D + h * HD + d] += dVf[(boff + j) * HDP + d];
     }
     if (p.mode != 2) {
-      const float *Ek = sm + ly.oEk, *Ev = sm + ly.oEv, *Ks = sm + ly.oKs, *Vs = sm + ly.oVs;
+      const float *Ek = ly.e_smem ? sm + ly.oEk : p.Ek, *Ev = ly.e_smem ? sm + ly.oEv : p.Ev, *Ks = sm + ly.oKs, *Vs = sm + ly.oVs;
       float *dEk = sm + ly.odEk, *dEv = sm + ly.odEv;
       // dKsrc[l, d] = sum_j E[l, j] dK'[j, d]
       for (int idx = tid; idx < ly.L * HD; idx += NT) {
@@ -273,15 +274,20 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask
             ak = fmaf(Ks[l * HDP + d], dKf[j * HDP + d], ak);
             av = fmaf(Vs[l * HDP + d], dVf[j * HDP + d], av);
           }
-          dEk[l * p.klin + j] += ak;
-          dEv[l * p.klin + j] += av;
+          if (ly.e_smem) {
+            dEk[l * p.klin + j] += ak;
+            dEv[l * p.klin + j] += av;
+          } else {   // large Linformer matrices (128 x 64 at 224 / 16): accumulate straight into the parameter gradient
+            atomicAdd(p.dEk + l * p.klin + j, ak);
+            atomicAdd(p.dEv + l * p.klin + j, av);
+          }
         }
       }
     }
   }
   __syncthreads();
   // ---- flush the batch-reduced accumulators
-  if (p.mode != 2) {
+  if (p.mode != 2 && ly.e_smem) {
     for (int idx = tid; idx < ly.L * p.klin; idx += NT) {
       atomicAdd(p.dEk + idx, sm[ly.odEk + idx]);
       atomicAdd(p.dEv + idx, sm[ly.odEv + idx]);
@@ -301,10 +307,11 @@ Lay make_layout(const AttnP& p, bool bwd) {
   ly.NKV = (p.mode == 2) ? p.kb : p.klin + p.kb;
   ly.SP = ly.NKV + 1;
   ly.QC = ly.nq < 32 ? ly.nq : 32;
+  ly.e_smem = (ly.L * p.klin * (bwd ? 4 : 2)) <= 16384 ? 1 : 0;     // <= 64 KB of E / dE in shared memory
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-  ly.oEk = take(ly.L * p.klin); ly.oEv = take(ly.L * p.klin);
-  ly.odEk = take(bwd ? ly.L * p.klin : 0); ly.odEv = take(bwd ? ly.L * p.klin : 0);
+  ly.oEk = take(ly.e_smem ? ly.L * p.klin : 0); ly.oEv = take(ly.e_smem ? ly.L * p.klin : 0);
+  ly.odEk = take(bwd && ly.e_smem ? ly.L * p.klin : 0); ly.odEv = take(bwd && ly.e_smem ? ly.L * p.klin : 0);
   ly.oKs = take(ly.L * ly.HDP); ly.oVs = take(ly.L * ly.HDP);
   ly.oKf = take(ly.NKV * ly.HDP); ly.oVf = take(ly.NKV * ly.HDP);
   ly.odKf = take(bwd ? ly.NKV * ly.HDP : 0); ly.odVf = take(bwd ? ly.NKV * ly.HDP : 0);

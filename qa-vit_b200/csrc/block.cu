@@ -101,6 +101,7 @@ struct Dims {
   int B, Nt, Nf, R, Rf, d, H, hd, kb, G, cg, cpg, ws, side, klin, NM, Lm, cd, bh, fh, dt;
   size_t ts;
   bool tl, v1;
+  bool ftok;   // TokenLearner / TokenUpMix run as the fused split-precision kernels of tokens_fused.cu
 };
 
 // gemm weights that get bf16 copies in bf16 runs
@@ -145,6 +146,7 @@ int make_dims(const qavit_block_cfg& c, Dims* D) {
   QV_CHECK(!c.token_learner || c.tokens_full >= c.tokens, "token learner: tokens_full < tokens");
   QV_CHECK(c.token_learner || c.tokens_full == c.tokens, "tokens_full must equal tokens without token learner");
   D->side = side;
+  D->ftok = D->tl && c.dtype == QV_BF16 && tokens_fused_ok(c.tokens, c.tokens_full, c.dim);
   D->NM = msda_tokens(c, side);
   D->Lm = D->NM < c.msda_seq_len ? D->NM : c.msda_seq_len;
   return 0;
@@ -170,8 +172,8 @@ void weight_shape(const Dims& D, int wi, int* N, int* K) {
 void layout_saved(const Dims& D, Saved* S) {
   Bump b;
   const size_t ts = D.ts, R = D.R, Rf = D.Rf, d = D.d;
-  S->tl_stats = b.take(D.tl ? Rf * 8 : 0);
-  S->tl_ln = b.take(D.tl ? Rf * d * ts : 0);
+  S->tl_stats = b.take(D.tl && !D.ftok ? Rf * 8 : 0);
+  S->tl_ln = b.take(D.tl && !D.ftok ? Rf * d * ts : 0);
   S->tl_S = b.take(D.tl ? Rf * D.Nt * 4 : 0);
   S->xc = b.take(D.tl ? R * d * 4 : 0);
   S->n1_stats = b.take(R * 8);
@@ -209,12 +211,12 @@ void layout_saved(const Dims& D, Saved* S) {
   S->hn2 = b.take(R * D.fh * ts);
   S->o = b.take(R * d * ts);
   S->out_blk = b.take(D.tl ? R * d * 4 : 0);
-  S->up = b.take(D.tl ? Rf * d * 4 : 0);
+  S->up = b.take(D.tl && !D.ftok ? Rf * d * 4 : 0);
   S->up_stats = b.take(D.tl ? Rf * 8 : 0);
   for (int i = 0; i < W_COUNT; ++i) {
     int N, K;
     weight_shape(D, i, &N, &K);
-    const bool need = D.dt == QV_BF16 && (i != W_TL || D.tl);
+    const bool need = D.dt == QV_BF16 && (i != W_TL || (D.tl && !D.ftok));
     S->wb[i] = b.take(need ? (size_t)N * K * 2 : 0);
     S->wbt[i] = b.take(need && i != W_WRITE ? (size_t)N * K * 2 : 0);
   }
@@ -229,7 +231,7 @@ void layout_scratch(const Dims& D, Scratch* S) {
   const size_t ts = D.ts, R = D.R, Rf = D.Rf, d = D.d;
   {
     Bump b;
-    S->tl_logits = b.take(D.tl ? Rf * D.Nt * ts : 0);
+    S->tl_logits = b.take(D.tl && !D.ftok ? Rf * D.Nt * ts : 0);
     S->tn = b.take(R * d * ts);
     S->cgbuf = b.take(R * (d + D.kb) * ts);
     S->partial = b.take((size_t)592 * 2 * D.kb * d * 4);   // bank_write_reduce uses <= 592 CTAs
@@ -238,7 +240,7 @@ void layout_scratch(const Dims& D, Scratch* S) {
   }
   {
     Bump b;
-    S->d_up = b.take(D.tl ? Rf * d * 4 : 0);
+    S->d_up = b.take(D.tl && !D.ftok ? Rf * d * 4 : 0);
     S->d_blk = b.take(D.tl ? R * d * 4 : 0);
     S->d_o = b.take(R * d * ts);
     S->d_hn2 = b.take(R * D.fh * ts);
@@ -267,8 +269,8 @@ void layout_scratch(const Dims& D, Scratch* S) {
     S->draw = b.take(16);
     const size_t zero_end = b.off;
     (void)zero_end;
-    S->d_logits = b.take(D.tl ? Rf * D.Nt * ts : 0);
-    S->d_tl_ln = b.take(D.tl ? Rf * d * ts : 0);
+    S->d_logits = b.take(D.tl && !D.ftok ? Rf * D.Nt * ts : 0);
+    S->d_tl_ln = b.take(D.tl && !D.ftok ? Rf * d * ts : 0);
     S->attn_ws_b = b.take(D.dt == QV_BF16 && D.Nt > 16 ? attn_msda64_scratch_bytes(D.B, D.d) : 0);
     S->total_bwd = b.off;
   }
@@ -462,7 +464,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   if (dt == QV_BF16) {
     ConvertJobs jobs{};
     for (int wi = 0; wi < W_COUNT; ++wi) {
-      if ((wi == W_TL && !D.tl) || (wi == W_WRITE && !train)) continue;
+      if ((wi == W_TL && (!D.tl || D.ftok)) || (wi == W_WRITE && !train)) continue;
       int N, K;
       weight_shape(D, wi, &N, &K);
       bf16* wb = reinterpret_cast<bf16*>(c.sv(S.wb[wi]));
@@ -478,7 +480,11 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
 
   // ---- TokenLearner (H:985-1002)
   const float* x = x_in;
-  if (D.tl) {
+  if (D.ftok) {   // LayerNorm + gate + softmax over tokens + pooling in one split-precision kernel; the logits never leave the SM
+    QV_TRY(tlf_fwd(st, x_in, D.B, D.Nf, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), c.pf(QP_TL_FC_W), c.pf(QP_TL_FC_B), 1e-5f, c.svf(S.tl_S),
+                   c.svf(S.xc)));
+    x = c.svf(S.xc);
+  } else if (D.tl) {
     QV_TRY(ln_fwd(st, QV_F32, x_in, d, D.Rf, d, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), 1e-5f, 0, nullptr, nullptr, dt,
                   c.sv(S.tl_ln), d, c.svf(S.tl_stats)));
     QV_TRY(gemm_nt(st, dt, c.sv(S.tl_ln), d, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)),
@@ -641,7 +647,10 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     }
   }
   // ---- TokenUpMix (H:1016-1031)
-  if (D.tl) {
+  if (D.ftok) {   // up-mix GEMM + LayerNorm in one kernel: the [B Nf, d] pre-norm tensor is never written (backward recomputes it)
+    QV_TRY(upf_fwd(st, blk_out, D.B, D.Nf, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.pf(QP_UP_LN_W), c.pf(QP_UP_LN_B), 1e-5f, out,
+                   c.svf(S.up_stats)));
+  } else if (D.tl) {
     QV_TRY(token_upmix_fwd(st, dt, blk_out, D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.svf(S.up)));
     QV_TRY(ln_fwd(st, QV_F32, c.sv(S.up), d, D.Rf, d, c.pf(QP_UP_LN_W), c.pf(QP_UP_LN_B), 1e-5f, 0, nullptr, nullptr, QV_F32, out, d, c.svf(S.up_stats)));
   }
@@ -674,7 +683,11 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
 
   // ---- TokenUpMix backward
   const float* dblk = dout;
-  if (D.tl) {
+  if (D.ftok) {   // (the up-mix bias gradient is exactly zero -- a per-token constant removed by the LayerNorm that follows -- and stays 0)
+    QV_TRY(upf_bwd(st, c.svf(S.out_blk), dout, c.svf(S.up_stats), D.B, D.Nf, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.pf(QP_UP_LN_W),
+                   c.scf(X.d_blk), G(QP_UP_FC_W), G(QP_UP_LN_W), G(QP_UP_LN_B)));
+    dblk = c.scf(X.d_blk);
+  } else if (D.tl) {
     QV_TRY(ln_bwd(st, QV_F32, c.sv(S.up), d, QV_F32, dout, d, D.Rf, d, c.pf(QP_UP_LN_W), c.svf(S.up_stats), 0, QV_F32, nullptr,
                   c.scf(X.d_up), nullptr, G(QP_UP_LN_W), G(QP_UP_LN_B)));
     QV_TRY(token_upmix_bwd(st, dt, c.svf(S.out_blk), c.scf(X.d_up), D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.scf(X.d_blk),
@@ -837,7 +850,10 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
                 c.scf(X.d_x1), G(QP_NORM1_W), G(QP_NORM1_B)));
 
   // ---- TokenLearner backward
-  if (D.tl) {
+  if (D.ftok) {
+    QV_TRY(tlf_bwd(st, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), c.pf(QP_TL_FC_W), 1e-5f, dx,
+                   G(QP_TL_FC_W), G(QP_TL_FC_B), G(QP_TL_LN_W), G(QP_TL_LN_B)));
+  } else if (D.tl) {
     QV_TRY(token_learner_bwd(st, dt, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, D.Nt, d, c.sc(X.d_logits), c.scf(X.d_up)));   // d_up is free again
     QV_TRY(gemm_tn(st, dt, c.sc(X.d_logits), D.Nt, c.sv(S.tl_ln), d, D.Rf, D.Nt, d, G(QP_TL_FC_W), G(QP_TL_FC_B), nullptr));
     QV_TRY(gemm_nn(st, dt, c.sc(X.d_logits), D.Nt, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)), epi_t(c, nullptr, c.sc(X.d_tl_ln), d)));
@@ -931,6 +947,25 @@ extern "C" int qavit_test_gemm_tn(int use_tc, const void* dY, int ldy, const voi
                                   float* dW, float* db, void* stream) {
   if (use_tc) return gemm_tn((cudaStream_t)stream, QV_BF16, dY, ldy, X, ldx, M, N, K, dW, db, nullptr);   // incl. the wide-K transposed flavour
   return simt_gemm_tn((cudaStream_t)stream, QV_F32, dY, ldy, X, ldx, M, N, K, dW, db, nullptr);
+}
+// The fused TokenLearner / TokenUpMix kernels of bf16 runs (16 learned tokens, <= 64 stream tokens, 192 channels) on their own:
+// op 0 = TokenLearner forward, 1 = TokenLearner backward, 2 = TokenUpMix (+ LayerNorm) forward, 3 = its backward.  All fp32, device:
+//   0: in  {x, ln_w, ln_b, W[16, C], b[16]}            out {S[B, N, 16], xc[B, 16, C]}
+//   1: in  {x, S, dxc, ln_w, ln_b, W}                   out {dx[B, N, C], dW, db, dln_w, dln_b}   (parameter gradients accumulated)
+//   2: in  {xc, W[N, 16], b[N], ln_w, ln_b}             out {out[B, N, C], stats[B N, 2]}
+//   3: in  {xc, dout, stats, W, b, ln_w}                out {dxc[B, 16, C], dW, dln_w, dln_b}     (parameter gradients accumulated)
+extern "C" int qavit_test_tokens_fused(int op, int B, int N, int C, const float* const* in, float* const* out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  QV_CHECK(in && out, "tokens_fused: null argument");
+  QV_CHECK(tokens_fused_ok(16, N, C), "tokens_fused: N=%d C=%d not covered (N multiple of 16 <= 64, C = 192)", N, C);
+  switch (op) {
+    case 0: return tlf_fwd(s, in[0], B, N, in[1], in[2], in[3], in[4], 1e-5f, out[0], out[1]);
+    case 1: return tlf_bwd(s, in[0], in[1], in[2], B, N, in[3], in[4], in[5], 1e-5f, out[0], out[1], out[2], out[3], out[4]);
+    case 2: return upf_fwd(s, in[0], B, N, in[1], in[2], in[3], in[4], 1e-5f, out[0], out[1]);
+    case 3: return upf_bwd(s, in[0], in[1], in[2], B, N, in[3], in[4], in[5], out[0], out[1], out[2], out[3]);
+  }
+  qv_set_error("tokens_fused: op %d", op);
+  return 1;
 }
 extern "C" int qavit_convert_weight(const float* w, int N, int K, void* wb, void* wbt, void* stream) {
   return convert_weight((cudaStream_t)stream, w, N, K, (bf16*)wb, (bf16*)wbt);

@@ -245,6 +245,17 @@ int tlm64_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, 
 int upm64_fwd(cudaStream_t s, const float* xc, int B, int N, int M, int C, const float* W, const float* bias, float* up);
 int upm64_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int M, int C, const float* W, float* dxc, float* dW,
               float* dbias);
+// fused wrapper kernels for 16 learned / <= 64 stream tokens / 192 channels (tokens_fused.cu): LayerNorm + gate + softmax + pooling,
+// up-mix + LayerNorm, and their backwards, one launch each, split-precision (bf16 hi + lo) MMAs, fp32 everywhere else
+bool tokens_fused_ok(int M, int N, int C);
+int tlf_fwd(cudaStream_t s, const float* x, int B, int N, const float* gamma, const float* beta, const float* W, const float* bias,
+            float eps, float* S, float* xc);
+int tlf_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, const float* gamma, const float* beta,
+            const float* W, float eps, float* dx, float* dW, float* dbias, float* dgamma, float* dbeta);
+int upf_fwd(cudaStream_t s, const float* xc, int B, int N, const float* W, const float* bias, const float* gamma, const float* beta,
+            float eps, float* out, float* stats);
+int upf_bwd(cudaStream_t s, const float* xc, const float* dout, const float* stats, int B, int N, const float* W, const float* bias,
+            const float* gamma, float* dxc, float* dW, float* dgamma, float* dbeta);
 bool bank_write_mma_ok(int Nt, int d, int kb, int ldcg);
 int bank_write_reduce_mma(cudaStream_t s, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, float* partial, int* n_partial);
 // register-blocked flavours for 16 learned tokens (tokens.cu)

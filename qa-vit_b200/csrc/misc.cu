@@ -16,19 +16,20 @@ namespace {
 // CTA strides over images; thread = channel (its 2 x KB accumulators stay in registers for all images of the CTA);
 // the softmaxed gate tile [Nt][KB] sits in shared memory and is read as broadcast float4s (8 FMAs per shared load);
 // the gate logits of the next image are prefetched into registers while the current image is accumulated.
-template <typename T, int KB>
+// NQ = gate-tile entries per thread: Nt * KB <= NQ * 256 (4 covers the 16 / 64-token blocks, 16 the 196 tokens of 224 / 16).
+template <typename T, int KB, int NQ>
 __global__ void __launch_bounds__(256) bank_write_reduce_kernel(const T* __restrict__ tn, const T* __restrict__ cg, int ldcg,
                                                                 int B, int Nt, int d, float* __restrict__ partial) {
   extern __shared__ __align__(16) float g[];  // [Nt][KB]
   const int c = threadIdx.x;
-  const int ng = Nt * KB;                     // <= 4 * blockDim.x (checked by the launcher)
+  const int ng = Nt * KB;                     // <= NQ * blockDim.x (checked by the launcher)
   float ak[KB], av[KB];
 #pragma unroll
   for (int s = 0; s < KB; ++s) ak[s] = av[s] = 0.f;
-  float pre[4];
+  float pre[NQ];
   auto fetch = [&](int b) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int idx = threadIdx.x + q * blockDim.x;
       pre[q] = idx < ng ? ldf(cg + ((long)b * Nt + idx / KB) * ldcg + d + idx % KB) : 0.f;
     }
@@ -37,15 +38,15 @@ __global__ void __launch_bounds__(256) bank_write_reduce_kernel(const T* __restr
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();                          // previous image's accumulation is done with g
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int idx = threadIdx.x + q * blockDim.x;
       if (idx < ng) g[idx] = pre[q];
     }
     __syncthreads();
     // softmax over the token axis, every thread normalises its own entries (column statistics recomputed per thread)
-    float e[4];
+    float e[NQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int idx = threadIdx.x + q * blockDim.x;
       e[q] = 0.f;
       if (idx < ng) {
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) bank_write_reduce_kernel(const T* __restr
     }
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int idx = threadIdx.x + q * blockDim.x;
       if (idx < ng) g[idx] = e[q];
     }
@@ -145,11 +146,15 @@ int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, in
   if (dt == QV_BF16 && bank_write_mma_ok(Nt, d, kb, ldcg)) return bank_write_reduce_mma(s, tn, cg, ldcg, B, Nt, d, partial, n_partial);
   QV_CHECK(kb == 16, "bank write kernel is instantiated for bank size 16 (got %d)", kb);
   QV_CHECK(d <= 256, "bank write: d=%d > 256", d);
-  QV_CHECK(Nt * kb <= 4 * 256, "bank write: %d tokens x %d slots exceed the gate tile", Nt, kb);
+  QV_CHECK(Nt * kb <= 16 * 256, "bank write: %d tokens x %d slots exceed the gate tile (<= 256 tokens)", Nt, kb);
   const int grid = max(1, min(cdiv(B, 4), min(592, qv_num_sms() * 4)));   // >= 4 images per CTA; 4 CTAs / SM for latency hiding
   *n_partial = grid;
   const size_t smem = (size_t)Nt * kb * sizeof(float);
-  DISPATCH_T(dt, (bank_write_reduce_kernel<T, 16><<<grid, 256, smem, s>>>((const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
+  if (Nt * kb <= 4 * 256) {
+    DISPATCH_T(dt, (bank_write_reduce_kernel<T, 16, 4><<<grid, 256, smem, s>>>((const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
+  } else {
+    DISPATCH_T(dt, (bank_write_reduce_kernel<T, 16, 16><<<grid, 256, smem, s>>>((const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
+  }
   QV_LAUNCH_CHECK();
   return 0;
 }

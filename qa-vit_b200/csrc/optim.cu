@@ -36,14 +36,16 @@ __global__ void __launch_bounds__(256) seg_norm_kernel(const float* __restrict__
 }
 
 // per-segment scale = per-param coef * global coef (written over norms[s]); norms[n] = global norm before global clip
+// prescale: a factor every gradient carries before clipping (1 / world_size when the buffer holds the SUM over data-parallel
+// ranks): norms are taken of prescale * g and the factor is folded into the per-segment scale, so no separate division pass.
 __global__ void __launch_bounds__(1024) clip_coef_kernel(const int* __restrict__ flags, int n, float per_param_max,
-                                                         float max_norm, float* __restrict__ norms) {
+                                                         float max_norm, float prescale, float* __restrict__ norms) {
   __shared__ float red[32];
   __shared__ float gcoef;
   float acc = 0.f;
   for (int s = threadIdx.x; s < n; s += blockDim.x) {
     float c = 1.f;
-    const float nm = norms[s];
+    const float nm = norms[s] * prescale;
     if (flags[s] & 2) c = fminf(1.f, per_param_max / (nm + 1e-6f));
     const float cn = (flags[s] & 1) ? c * nm : 0.f;
     acc += cn * cn;
@@ -57,7 +59,10 @@ __global__ void __launch_bounds__(1024) clip_coef_kernel(const int* __restrict__
     norms[n + 1] = gcoef;
   }
   __syncthreads();
-  for (int s = threadIdx.x; s < n; s += blockDim.x) norms[s] *= gcoef;
+  for (int s = threadIdx.x; s < n; s += blockDim.x) norms[s] *= gcoef * prescale;
+}
+__global__ void scaled_copy_kernel(const float* __restrict__ x, float scale, long n, float* __restrict__ y) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = x[i] * scale;
 }
 
 __device__ __forceinline__ int find_seg(const long long* __restrict__ off, int n, long long i) {
@@ -151,15 +156,60 @@ __global__ void __launch_bounds__(256) batch_mix_kernel(const float* __restrict_
   }
 }
 
+// transforms.ToTensor() + transforms.Normalize(mean, std) (H:1300, HQAViT_C100_Finetune.py:100-103) on a whole batch:
+// out[b, c, y, x] = (in / 255 - mean[c]) / std[c], one rounding per torch op (div, sub, div) so the result is bit-identical to the
+// torchvision pipeline; hflip = RandomHorizontalFlip(p = 1) of the TTA views.  in_kind 0: uint8 [B, H, W, C] (the datasets' raw
+// layout), 1: uint8 [B, C, H, W], 2: float [B, C, H, W] already in [0, 1] (only Normalize is applied).
+__global__ void __launch_bounds__(256) normalize_images_kernel(const void* __restrict__ in, int in_kind, int B, int C, int H, int W,
+                                                               const float* __restrict__ mean, const float* __restrict__ stdv, int hflip,
+                                                               float* __restrict__ out) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % C);
+    const long long b = i / ((long long)W * H * C);
+    const int xs = hflip ? W - 1 - x : x;
+    float v;
+    if (in_kind == 0) v = __fdiv_rn((float)static_cast<const unsigned char*>(in)[((b * H + y) * W + xs) * C + c], 255.f);
+    else if (in_kind == 1) v = __fdiv_rn((float)static_cast<const unsigned char*>(in)[((b * C + c) * H + y) * W + xs], 255.f);
+    else v = static_cast<const float*>(in)[((b * C + c) * H + y) * W + xs];
+    out[i] = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+  }
+}
+
 }  // namespace
+
+extern "C" int qavit_normalize_images(const void* in, int in_kind, int B, int C, int H, int W, const float* mean, const float* stdv,
+                                      int hflip, float* out, void* stream) {
+  QV_CHECK(in && mean && stdv && out && (const void*)in != (const void*)out, "normalize_images: null / aliased argument");
+  QV_CHECK(in_kind >= 0 && in_kind <= 2, "normalize_images: in_kind %d (0 = uint8 NHWC, 1 = uint8 NCHW, 2 = float NCHW)", in_kind);
+  const long long total = (long long)B * C * H * W;
+  if (total <= 0) return 0;
+  const int grid = (int)max(1LL, min((long long)qv_num_sms() * 16, (total + 255) / 256));
+  normalize_images_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_kind, B, C, H, W, mean, stdv, hflip, out);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int qavit_scaled_copy(const float* x, float scale, long long n, float* y, void* stream) {
+  QV_CHECK(x && y, "scaled_copy: null argument");
+  if (n <= 0) return 0;
+  scaled_copy_kernel<<<(int)max(1LL, min((long long)qv_num_sms() * 8, (n + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(x, scale, (long)n, y);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int qavit_clip_grads(float* grads, const long long* seg_off, const int* seg_flags, int n_seg, float per_param_max,
                                 float max_norm, float* norms, long long total, void* stream) {
+  return qavit_clip_grads_scaled(grads, seg_off, seg_flags, n_seg, per_param_max, max_norm, 1.0f, norms, total, stream);
+}
+
+extern "C" int qavit_clip_grads_scaled(float* grads, const long long* seg_off, const int* seg_flags, int n_seg, float per_param_max,
+                                       float max_norm, float prescale, float* norms, long long total, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n_seg <= 0) return 0;
   seg_norm_kernel<<<n_seg, 256, 0, s>>>(grads, seg_off, seg_flags, norms);
   QV_LAUNCH_CHECK();
-  clip_coef_kernel<<<1, 1024, 0, s>>>(seg_flags, n_seg, per_param_max, max_norm, norms);
+  clip_coef_kernel<<<1, 1024, 0, s>>>(seg_flags, n_seg, per_param_max, max_norm, prescale, norms);
   QV_LAUNCH_CHECK();
   const int grid = (int)max(1LL, min((long long)qv_num_sms() * 8, (total / 4 + 255) / 256));
   scale_grads_kernel<<<grid, 256, 0, s>>>(grads, seg_off, seg_flags, n_seg, norms, total);

@@ -13,6 +13,8 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
+from ._lib import check, lib
+
 
 class GradAllReducer:
     def __init__(self, opt, n_buckets: int = 4, bank_params: Optional[List[torch.nn.Parameter]] = None, group=None,
@@ -39,7 +41,14 @@ class GradAllReducer:
             if hi > lo:
                 self.buckets.append((lo, hi, opt.flat_g[offs[lo]:offs[hi]]))
         self.bank_params = bank_params or []
-        self._bank_flat = None
+        nb = sum(p.numel() for p in self.bank_params)
+        if nb > getattr(opt, "tail", 0):
+            raise ValueError(f"GradAllReducer: the bank state ({nb} floats) rides in the tail of the optimizer's gradient buffer; "
+                             f"build FusedAdamW(..., tail_elems>={nb})")
+        self._tail = opt._flat_g_full[total:total + nb]
+        self._full = opt._flat_g_full[:total + nb]
+        self._producers = []
+        opt.grad_prescale = 1.0 / self.world        # buffers hold SUMS over ranks; the mean is folded into opt.clip()
         self._pending = [0] * len(self.buckets)
         self._param_bucket = {}
         for bi, (lo, hi, _) in enumerate(self.buckets):
@@ -91,33 +100,59 @@ class GradAllReducer:
             if self._pending[bi] == 0:
                 self._launch(bi)
 
+    def add_producer_stream(self, stream):
+        """A stream besides the current one on which gradient kernels run (HQAViT's lateral path runs its backward on a
+        side stream): every bucket launch waits for it too, so a bucket mixing main-stream and side-stream parameters
+        is never reduced before both producers are done."""
+        if stream is not None and stream not in self._producers:
+            self._producers.append(stream)
+
+    def _wait_producers(self):
+        self._stream.wait_stream(torch.cuda.current_stream())
+        for ps in self._producers:
+            self._stream.wait_stream(ps)
+
     def _launch(self, bi):
+        """SUM all-reduce of one bucket; the 1 / world of the mean is folded into the optimizer's clip pass."""
         buf = self.buckets[bi][2]
         if self._stream is not None:
-            self._stream.wait_stream(torch.cuda.current_stream())
+            self._wait_producers()
             with torch.cuda.stream(self._stream):
-                buf.div_(self.world)
                 self._handles.append(dist.all_reduce(buf, group=self.group, async_op=True))
         else:
-            buf.div_(self.world)
             self._handles.append(dist.all_reduce(buf, group=self.group, async_op=True))
+
+    def _bank_to_tail(self):
+        o = 0
+        for p in self.bank_params:
+            n = p.numel()
+            if p.is_cuda:
+                check(lib.qavit_scaled_copy(p.data.data_ptr(), 1.0, n, self._tail[o:o + n].data_ptr(), torch.cuda.current_stream().cuda_stream))
+            else:
+                self._tail[o:o + n].copy_(p.data.reshape(-1))
+            o += n
+
+    def _tail_to_bank(self):
+        o = 0
+        for p in self.bank_params:
+            n = p.numel()
+            if p.is_cuda:
+                check(lib.qavit_scaled_copy(self._tail[o:o + n].data_ptr(), 1.0 / self.world, n, p.data.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            else:
+                p.data.copy_((self._tail[o:o + n] / self.world).view(p.shape))
+            o += n
 
     @torch.no_grad()
     def reduce_flat(self):
-        """One all-reduce (mean) of the whole flat gradient buffer, plus the GlobalTokenBank state, on the current stream."""
+        """ONE all-reduce (sum) of the flat gradient buffer with the GlobalTokenBank state riding in its tail, on the current
+        stream; 1 / world is applied to the gradients inside the clip pass and to the bank on its way back."""
         if self.world == 1:
             return
-        g = self.opt.flat_g
-        g.div_(self.world)
-        dist.all_reduce(g, group=self.group)
         if self.bank_params:
-            flat = torch.cat([p.data.reshape(-1) for p in self.bank_params])
-            flat.div_(self.world)
-            dist.all_reduce(flat, group=self.group)
-            o = 0
-            for p in self.bank_params:
-                p.data.copy_(flat[o:o + p.numel()].view(p.shape))
-                o += p.numel()
+            self._bank_to_tail()
+        dist.all_reduce(self._full, group=self.group)
+        if self.bank_params:
+            self._tail_to_bank()
 
     def finish(self):
         """After backward: flush buckets whose hooks did not all fire, average the bank state, join the side stream."""
@@ -128,23 +163,17 @@ class GradAllReducer:
                 self._pending[bi] = 0
                 self._launch(bi)
         if self.bank_params:
-            flat = torch.cat([p.data.reshape(-1) for p in self.bank_params])
+            self._bank_to_tail()
             if self._stream is not None:
-                self._stream.wait_stream(torch.cuda.current_stream())
+                self._wait_producers()
                 with torch.cuda.stream(self._stream):
-                    flat.div_(self.world)
-                    self._handles.append(dist.all_reduce(flat, group=self.group, async_op=True))
+                    self._handles.append(dist.all_reduce(self._tail, group=self.group, async_op=True))
             else:
-                flat.div_(self.world)
-                self._handles.append(dist.all_reduce(flat, group=self.group, async_op=True))
-            self._bank_flat = flat
+                self._handles.append(dist.all_reduce(self._tail, group=self.group, async_op=True))
         for h in self._handles:
             h.wait()
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
-        if self.bank_params and self._bank_flat is not None:
-            o = 0
-            for p in self.bank_params:
-                p.data.copy_(self._bank_flat[o:o + p.numel()].view(p.shape))
-                o += p.numel()
+        if self.bank_params:
+            self._tail_to_bank()
         self._handles = []

@@ -314,17 +314,44 @@ def _block_apply(block: QuadAttentionBlock, wrapper: Optional[QuadBlockWithToken
 
 
 # --------------------------------------------------------------------------------------------- patch embed / models
+class _PatchConv(nn.Conv2d):
+    """``patch_embed.proj``: an nn.Conv2d (same parameters / state_dict keys) whose own forward -- used only when someone calls
+    the conv itself or hangs hooks on it (Grad-CAM registers a forward hook here, test_hqa.py:241-259) -- runs the library's
+    GEMM on the gathered patches (stride == kernel, so the gather is a reshape) and returns [B, d, H/p, W/p]."""
+
+    def forward(self, x):
+        B, Cin, S, S2 = x.shape
+        p = self.kernel_size[0]
+        if self.stride[0] != p or S % p or S2 % p:
+            raise RuntimeError("qavit_b200: patch projection needs stride == kernel and an image divisible by the patch")
+        hp, wp = S // p, S2 // p
+        patches = x.reshape(B, Cin, hp, p, wp, p).permute(0, 2, 4, 1, 3, 5).reshape(B * hp * wp, Cin * p * p)
+        y = QF.linear(patches, self.weight, self.bias)                       # [B hp wp, d]
+        return y.view(B, hp, wp, -1).permute(0, 3, 1, 2)                      # channels-last view of [B, d, hp, wp]
+
+
 class PatchEmbed(nn.Module):
-    """H:1129-1138."""
+    """H:1129-1138.  One native call (gather + GEMM + LayerNorm + pos) -- unless ``proj`` carries hooks: then the projection
+    runs as its own autograd node through ``proj.__call__`` so that forward / backward hooks fire with the reference's
+    [B, d, H/p, W/p] activation (Grad-CAM, test_hqa.py:259), followed by the native LayerNorm."""
 
     def __init__(self, img_size=32, patch_size=4, in_channels=3, embed_dim=192):
         super().__init__()
         self.num_patches = (img_size // patch_size) ** 2
-        self.proj = nn.Conv2d(in_channels, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.proj = _PatchConv(in_channels, embed_dim, kernel_size=patch_size, stride=patch_size)
         self.norm = nn.LayerNorm(embed_dim)
         self.precision = "auto"
 
+    def _hooked(self) -> bool:
+        pj = self.proj
+        return bool(pj._forward_hooks or pj._forward_pre_hooks or pj._backward_hooks or getattr(pj, "_backward_pre_hooks", None))
+
     def forward(self, x, pos: Optional[torch.Tensor] = None):
+        if self._hooked():
+            y = self.proj(x)                                                 # hooks fire here
+            t = y.flatten(2).transpose(1, 2)                                 # H:1137
+            t = QF.LayerNormFn.apply(t, self.norm.weight, self.norm.bias, self.norm.eps)
+            return t if pos is None else t + pos
         return QF.PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, self.norm.weight, self.norm.bias, pos,
                                      QF.resolve_dtype(self.precision))
 
@@ -344,6 +371,15 @@ def _init_weights(m):
 
 class _Base(nn.Module):
     precision = "auto"
+    # The reference's head is an nn.Linear, so under torch.autocast(bfloat16) its logits come back as bf16.  The
+    # native head computes them in fp32; set this to True to round them to the autocast dtype for bit-for-bit dtype parity
+    # with scripts that inspect ``outputs.dtype`` -- off by default because it only loses precision.
+    match_autocast_output_dtype = False
+
+    def _finish_logits(self, logits):
+        if self.match_autocast_output_dtype and torch.is_autocast_enabled():
+            return logits.to(torch.get_autocast_gpu_dtype())
+        return logits
 
     def set_precision(self, precision: str):
         """'auto' (bf16 under torch.autocast, else fp32), 'fp32' or 'bf16' for every native block."""
@@ -385,7 +421,7 @@ class QAViT(_Base):
         T = self._stream_dropout(T)
         for blk in self.blocks:
             T = blk(T)
-        return QF.HeadFn.apply(T, self.norm.weight, self.norm.bias, self.head.weight, self.head.bias)
+        return self._finish_logits(QF.HeadFn.apply(T, self.norm.weight, self.norm.bias, self.head.weight, self.head.bias))
 
 
 # --------------------------------------------------------------------------------------------- HQAViT lateral path (row f-1)
@@ -569,4 +605,4 @@ class HQAViT(_Base):
         T = self.fuse4(T, R4)
         for blk in self.stage4_blocks:
             T = blk(T)
-        return QF.HeadFn.apply(T, self.norm.weight, self.norm.bias, self.head.weight, self.head.bias)
+        return self._finish_logits(QF.HeadFn.apply(T, self.norm.weight, self.norm.bias, self.head.weight, self.head.bias))

@@ -27,7 +27,7 @@ def _stream() -> int:
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=1e-2, max_grad_norm: Optional[float] = None, per_param_clip: float = 0.1,
-                 per_param_clip_names: Sequence[str] = ("cnn_stem", "dwconv")):
+                 per_param_clip_names: Sequence[str] = ("cnn_stem", "dwconv"), tail_elems: int = 0):
         named = [(n, p) for n, p in named_params if p.requires_grad]
         if not named:
             raise ValueError("no parameters")
@@ -46,7 +46,12 @@ class FusedAdamW(torch.optim.Optimizer):
         offs.append(off)
         self.total = off
         self.flat_p = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(off, dtype=torch.float32, device=dev)
+        # the gradient buffer carries a TAIL after the last parameter: the data-parallel reducer parks non-gradient state there
+        # (the GlobalTokenBank's global_k / global_v) so that one all-reduce moves gradients and bank together (dp.py)
+        self.tail = int(tail_elems)
+        self._flat_g_full = torch.zeros(off + self.tail, dtype=torch.float32, device=dev)
+        self.flat_g = self._flat_g_full[:off]
+        self.grad_prescale = 1.0          # set by the data-parallel reducer: the buffer then holds the SUM over ranks
         self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
         self._pviews: List[torch.Tensor] = []
@@ -121,6 +126,7 @@ class FusedAdamW(torch.optim.Optimizer):
             self.flat_g.zero_()
         for p, g in zip(self.param_groups[0]["params"], self._gviews):
             p.grad = g
+        self._scaled = False
 
     def zero_grad(self, set_to_none: bool = True):
         self.attach_grads()
@@ -157,9 +163,10 @@ class FusedAdamW(torch.optim.Optimizer):
         self._gather_foreign_grads()
         if not self._have_flags:
             self._sync_flags()
-        check(lib.qavit_clip_grads(self.flat_g.data_ptr(), self.seg_off.data_ptr(), self.seg_flags.data_ptr(), len(self.names),
-                                   float(self.per_param_clip), float(self.max_grad_norm if self.max_grad_norm else 3.0e38),
-                                   self.norms.data_ptr(), self.total, _stream()))
+        check(lib.qavit_clip_grads_scaled(self.flat_g.data_ptr(), self.seg_off.data_ptr(), self.seg_flags.data_ptr(), len(self.names),
+                                          float(self.per_param_clip), float(self.max_grad_norm if self.max_grad_norm else 3.0e38),
+                                          float(self.grad_prescale), self.norms.data_ptr(), self.total, _stream()))
+        self._scaled = True
         return self.norms[len(self.names)]
 
     def _gather_foreign_grads(self):
@@ -204,6 +211,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._gather_foreign_grads()
         if not self._have_flags:
             self._sync_flags()
+        if self.grad_prescale != 1.0 and not getattr(self, "_scaled", False):
+            self.clip()               # data-parallel mean (1 / world) rides in the clip pass: it must run once per step
         if not torch.cuda.is_current_stream_capturing():
             self.push_hyper()         # a captured step reads self.hyper, which the replaying caller refreshes eagerly
         if self.flat_ema is not None:

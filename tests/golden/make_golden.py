@@ -31,6 +31,14 @@ CASES = {
                      dict(img_size=32, patch_size=4, num_classes=10, window_size=4, dilation_factors=(1, 2),
                           linformer_k=32),
                      dict(family="qavit_v1", num_classes=10, dwconv_bias=True), 2),
+    # the files' OWN defaults: 224 x 224 / patch 16, 196 tokens, 7 x 7 windows (49 tokens), dilations (1, 2, 3), Linformer k = 64
+    # (QAViT.py:39-56, QAViTv2.py:43-60); MSDA pools 270 multi-scale tokens to 135 and truncates to 128 (QAViT.py:413-420)
+    "qavit_v1_224": ("QAViT", "QAViT", "QAViTConfig", {},
+                     dict(family="qavit_v1", img_size=224, patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64,
+                          dwconv_bias=True), 2),
+    "qavitv2b_224": ("QAViTv2", "QAViT", "QAViTConfig", {},
+                     dict(family="qavit_v2", img_size=224, patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64,
+                          dwconv_bias=True), 2),
     "hqavit_tinyin": ("HQAViT_IN_Tiny", "HQAViT", "HQAViTConfig", {},
                       dict(family="hqavit", img_size=64, num_classes=200, depth=12, num_learned_tokens=64,
                            stage_depths=(2, 2, 6, 2)), 2),

@@ -10,22 +10,12 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-class _FakeOpt:
-    """Just the attributes GradAllReducer reads from FusedAdamW (which itself needs CUDA)."""
-
-    def __init__(self, params):
-        offs, off = [], 0
-        for p in params:
-            offs.append(off)
-            off += (p.numel() + 3) // 4 * 4
-        offs.append(off)
-        self.param_groups = [{"params": params}]
-        self.seg_off = torch.tensor(offs)
-        self.flat_g = torch.zeros(off)
-        self._have_flags = False
-        self._flags_host = None
-        for p, o in zip(params, offs):
-            p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
+def _make_opt(params, tail):
+    """The real FusedAdamW on CPU parameters: host-side layout logic only (its arithmetic has no CPU path)."""
+    from qavit_b200.optim import FusedAdamW
+    opt = FusedAdamW([(f"p{i}", p) for i, p in enumerate(params)], lr=1e-3, tail_elems=tail)
+    opt.attach_grads()
+    return opt
 
 
 def _worker(rank, world, port, ret):
@@ -36,8 +26,9 @@ def _worker(rank, world, port, ret):
     torch.manual_seed(0)
     params = [torch.nn.Parameter(torch.randn(s)) for s in [(7, 5), (3,), (64, 16), (10,), (33,), (8, 8)]]
     bank = torch.nn.Parameter(torch.full((4,), float(rank + 1)))
-    opt = _FakeOpt(params)
+    opt = _make_opt(params, 4)
     red = GradAllReducer(opt, n_buckets=3, bank_params=[bank])
+    assert opt.grad_prescale == 1.0 / world          # buffers hold SUMS; the mean is folded into the clip pass
     assert 1 <= len(red.buckets) <= 3
     covered = sorted(i for lo, hi, _ in red.buckets for i in range(lo, hi))
     assert covered == list(range(len(params)))
@@ -46,17 +37,17 @@ def _worker(rank, world, port, ret):
     loss = sum((p * x).sum() for p in params)       # d loss / d p = rank + 1 everywhere
     loss.backward()
     red.finish()
-    ok = all(torch.allclose(p.grad, torch.full_like(p, (1 + world) / 2)) for p in params)
+    ok = all(torch.allclose(p.grad * opt.grad_prescale, torch.full_like(p, (1 + world) / 2)) for p in params)
     ok = ok and torch.allclose(bank.data, torch.full((4,), (1 + world) / 2))
-    # graph-mode flavour: no hooks, one all-reduce of the whole flat buffer (+ the bank state) after backward
-    opt2 = _FakeOpt(params)
+    # graph-mode flavour: no hooks, ONE all-reduce of the whole flat buffer with the bank state in its tail
+    opt2 = _make_opt(params, 4)
     bank.data.fill_(float(rank + 1))
     red2 = GradAllReducer(opt2, n_buckets=3, bank_params=[bank], overlap=False)
     assert not red2._hooks
     for p in params:
         p.grad.fill_(float(rank + 1))
     red2.reduce_flat()
-    ok = ok and all(torch.allclose(p.grad, torch.full_like(p, (1 + world) / 2)) for p in params)
+    ok = ok and all(torch.allclose(p.grad * opt2.grad_prescale, torch.full_like(p, (1 + world) / 2)) for p in params)
     ok = ok and torch.allclose(bank.data, torch.full((4,), (1 + world) / 2))
     ret[rank] = bool(ok)
     dist.destroy_process_group()

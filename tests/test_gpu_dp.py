@@ -1,0 +1,150 @@
+"""Data-parallel correctness on real GPUs over NCCL (needs >= 2 devices: `gpurun --gpus 2`; skipped on a 1-GPU box).
+
+Two ranks, identical replicas, different batch shards.  After the flat all-reduce + clip:
+  * every gradient equals the mean over ranks of the per-rank gradients (gathered with plain torch.distributed calls),
+  * global_k / global_v equal the mean of the rank-local banks, update_count agrees on every rank,
+  * the clip coefficient is that of the MEAN gradient (the 1 / world is folded into the clip pass),
+  * parameters stay identical across ranks after AdamW,
+  * in eval mode (no bank writes: every image independent) the 2-rank result equals ONE rank run on the global batch.
+The overlapped, bucketed flavour (autograd hooks, side stream) is checked against the flat one."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")]
+
+
+def _worker(rank, world, port, family, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import qavit_b200 as Q
+    from util import build_model
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = {}
+    try:
+        Bl = 3
+        g = torch.Generator().manual_seed(77)
+        xg = torch.randn(world * Bl, 3, 32, 32, generator=g)
+        yg = torch.randint(0, 100, (world * Bl,), generator=g)
+        x, y = xg[rank * Bl:(rank + 1) * Bl].to(dev), yg[rank * Bl:(rank + 1) * Bl].to(dev)
+
+        def fresh(train, overlap):
+            model, ocfg, sd, _ = build_model(family, device=dev, precision="fp32")
+            model.train(train)
+            bank = [model.global_bank.global_k, model.global_bank.global_v]
+            opt = Q.FusedAdamW(model.named_parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05, max_grad_norm=0.5,
+                               tail_elems=sum(p.numel() for p in bank))
+            red = Q.GradAllReducer(opt, n_buckets=4, bank_params=bank, overlap=overlap)
+            return model, opt, red
+
+        def fwd_bwd(model, opt, red, xx, yy, overlap):
+            opt.zero_grad()
+            if overlap:
+                red.reset()
+            loss = Q.cross_entropy(model(xx), yy, label_smoothing=0.1)
+            loss.backward()
+            return loss
+
+        # ---- train mode, flat all-reduce
+        model, opt, red = fresh(True, False)
+        fwd_bwd(model, opt, red, x, y, False)
+        local_g = opt.flat_g.clone()
+        local_bank = torch.cat([model.global_bank.global_k.data.reshape(-1), model.global_bank.global_v.data.reshape(-1)])
+        gathered = [torch.empty_like(local_g) for _ in range(world)]
+        dist.all_gather(gathered, local_g)
+        banks = [torch.empty_like(local_bank) for _ in range(world)]
+        dist.all_gather(banks, local_bank)
+        mean_g, mean_bank = torch.stack(gathered).mean(0), torch.stack(banks).mean(0)
+        red.reduce_flat()
+        torch.cuda.synchronize()
+        got_bank = torch.cat([model.global_bank.global_k.data.reshape(-1), model.global_bank.global_v.data.reshape(-1)])
+        out["sum_equals_world_x_mean"] = bool(torch.allclose(opt.flat_g * opt.grad_prescale, mean_g, rtol=1e-6, atol=1e-9))
+        out["bank_mean"] = bool(torch.allclose(got_bank, mean_bank, rtol=1e-6, atol=1e-9))
+        out["banks_differed_before"] = bool((banks[0] - banks[1]).abs().max().item() > 0)
+        cnt = torch.tensor([int(model.global_bank.update_count)], device=dev)
+        cnts = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        out["update_count"] = [int(c) for c in cnts]
+        # clip on the mean gradient: reference = torch's clip on mean_g views
+        offs = opt.seg_off.tolist()
+        flags = opt._flags_host.tolist() if opt._have_flags else None
+        norm = opt.clip()
+        torch.cuda.synchronize()
+        if flags is None:
+            flags = opt._flags_host.tolist()
+        ref = mean_g.clone()
+        tot = 0.0
+        for i, n in enumerate(opt.names):
+            if not (flags[i] & 1):
+                continue
+            seg = ref[offs[i]:offs[i + 1]]
+            if "cnn_stem" in n or "dwconv" in n:
+                seg.mul_(min(1.0, 0.1 / (seg.norm().item() + 1e-6)))
+            tot += seg.norm().item() ** 2
+        tot = tot ** 0.5
+        coef = min(1.0, 0.5 / (tot + 1e-6))
+        mask = torch.zeros_like(ref, dtype=torch.bool)
+        for i in range(len(opt.names)):
+            if flags[i] & 1:
+                mask[offs[i]:offs[i + 1]] = True
+        out["clip_norm"] = abs(norm.item() - tot) < 1e-5 * max(1.0, tot)
+        out["clipped_grads"] = bool(torch.allclose(opt.flat_g[mask], (ref * coef)[mask], rtol=1e-5, atol=1e-9))
+        opt.step()
+        torch.cuda.synchronize()
+        ps = [torch.empty_like(opt.flat_p) for _ in range(world)]
+        dist.all_gather(ps, opt.flat_p)
+        out["params_identical"] = bool(torch.equal(ps[0], ps[1]))
+
+        # ---- train mode, bucketed + overlapped flavour == flat flavour
+        model2, opt2, red2 = fresh(True, True)
+        fwd_bwd(model2, opt2, red2, x, y, True)
+        red2.finish()
+        torch.cuda.synchronize()
+        out["overlap_equals_flat"] = bool(torch.allclose(opt2.flat_g * opt2.grad_prescale, mean_g, rtol=1e-6, atol=1e-9))
+        got2 = torch.cat([model2.global_bank.global_k.data.reshape(-1), model2.global_bank.global_v.data.reshape(-1)])
+        out["overlap_bank_mean"] = bool(torch.allclose(got2, mean_bank, rtol=1e-6, atol=1e-9))
+
+        # ---- eval mode (no bank writes => images independent): 2 ranks x Bl == 1 rank x 2 Bl
+        model3, opt3, red3 = fresh(False, False)
+        fwd_bwd(model3, opt3, red3, x, y, False)
+        red3.reduce_flat()
+        torch.cuda.synchronize()
+        dp_g = (opt3.flat_g * opt3.grad_prescale).clone()
+        model4, opt4, _ = fresh(False, False)
+        opt4.grad_prescale = 1.0
+        fwd_bwd(model4, opt4, None, xg.to(dev), yg.to(dev), False)
+        torch.cuda.synchronize()
+        err = ((dp_g - opt4.flat_g).norm() / opt4.flat_g.norm()).item()
+        out["dp_equals_single_rank_global_batch_relerr"] = err
+    except Exception as e:       # surface the failure in the parent
+        import traceback
+        out["error"] = f"{type(e).__name__}: {e}\\n{traceback.format_exc()}"
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("family", ["qavitv2_c100", "hqavit_c100"])
+def test_two_rank_nccl_allreduce_matches_the_cross_rank_mean(family):
+    import torch.multiprocessing as mp
+    world = 2
+    port = 29600 + os.getpid() % 1500
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, family, ret), nprocs=world, join=True)
+    for rank in range(world):
+        o = ret[rank]
+        print(f"rank {rank} {family}: {o}")
+        assert "error" not in o, o["error"]
+        assert o["sum_equals_world_x_mean"] and o["bank_mean"] and o["banks_differed_before"]
+        assert o["update_count"][0] == o["update_count"][1] > 0
+        assert o["clip_norm"] and o["clipped_grads"] and o["params_identical"]
+        assert o["overlap_equals_flat"] and o["overlap_bank_mean"]
+        assert o["dp_equals_single_rank_global_batch_relerr"] < 1e-5      # eval mode: BatchNorm uses running statistics

@@ -42,6 +42,8 @@ def _our_block(model, prefix, x, wgt):
     ("qavitv2_c100", "blocks.0", False, 64),
     ("hqavit_c100", "stage1_blocks.0", True, 64),
     ("qavit_v1_c10", "blocks.1", False, 64),
+    ("qavit_v1_224", "blocks.2", False, 196),       # QAViT.py's own defaults: 14 x 14 tokens, 7 x 7 windows, k = 64, dilations (1, 2, 3)
+    ("qavitv2b_224", "blocks.5", False, 196),
 ])
 @pytest.mark.parametrize("train", [True, False])
 def test_block_forward_backward_fp32(case, prefix, wrapped, ntok, train):
@@ -284,7 +286,8 @@ def test_bf16_vs_fp32_with_reference_init(fam):
 
 
 @pytest.mark.parametrize("case,prefix,ntok", [("hqavit_c100", "stage2_blocks.1", 64), ("qavitv2_c100", "blocks.3", 64),
-                                              ("hqavit_tinyin", "stage3_blocks.2", 256)])   # 64 learned / 256 stream tokens
+                                              ("hqavit_tinyin", "stage3_blocks.2", 256),    # 64 learned / 256 stream tokens
+                                              ("qavitv2b_224", "blocks.4", 196)])           # 196 tokens: tcgen05 GEMMs + SIMT attention
 def test_block_bf16_close_to_fp32(case, prefix, ntok):
     """One block, bf16 run (tcgen05 GEMMs + mma.sync attention) against the fp32 run of the same block: a layout bug in
     a tensor-core path shows up as O(1) error, bf16 rounding as ~1e-2."""

@@ -289,3 +289,79 @@ def test_graphed_step_supports_the_two_target_mixup_loss():
         want = Q.cross_entropy(snap(x), y, label_smoothing=0.1, target_b=second, lam=lam).item()
         got = step(x, y, y_b=second, lam=lam).item()
         assert abs(got - want) < 2e-5 * max(1.0, abs(want)), (lam, got, want)
+
+
+def test_normalize_batch_is_bit_identical_to_totensor_plus_normalize():
+    g = torch.Generator().manual_seed(0)
+    raw = torch.randint(0, 256, (37, 32, 32, 3), generator=g, dtype=torch.uint8)          # dataset layout [B, H, W, C]
+    mean, std = Q.evalutil.CIFAR100_MEAN, Q.evalutil.CIFAR100_STD
+    t = raw.permute(0, 3, 1, 2).float().div(255)                                          # transforms.ToTensor
+    want = (t - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)  # transforms.Normalize: sub_ then div_
+    got = Q.normalize_batch(raw.cuda(), mean, std)
+    assert torch.equal(got.cpu(), want)
+    assert torch.equal(Q.normalize_batch(raw.cuda(), mean, std, hflip=True).cpu(), want.flip(-1))      # RandomHorizontalFlip(p=1)
+    assert torch.equal(Q.normalize_batch(raw.permute(0, 3, 1, 2).contiguous().cuda(), mean, std).cpu(), want)
+    assert torch.equal(Q.normalize_batch(t.cuda(), mean, std).cpu(), want)
+    v = Q.tta_views(raw.cuda())
+    assert len(v) == 2 and torch.equal(v[1], v[0].flip(-1))
+
+
+def test_validate_tta_matches_the_reference_algorithm():
+    """HQAViT_C100_Finetune.py:345-384 restated with host-side accumulation, against the device-resident drop-in."""
+    model, ocfg, sd, _ = build_model("hqavit_c100", precision="fp32")
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(6, 3, 32, 32, generator=g) for _ in range(3)]
+    ys = [torch.randint(0, 100, (6,), generator=g) for _ in range(3)]
+    loaders = [list(zip(xs, ys)), [(x.flip(-1), y) for x, y in zip(xs, ys)], [(x + 0.05, y) for x, y in zip(xs, ys)]]
+    model.eval()
+    with torch.no_grad():
+        preds = [torch.cat([torch.softmax(model(x.cuda()), 1).cpu() for x, _ in ld]) for ld in loaders]
+        # make the check non-trivial: targets = the ensemble's own prediction on half of the samples
+        ens = torch.stack(preds).mean(0).argmax(1)
+    tgt = torch.cat(ys)
+    tgt[::2] = ens[::2]
+    loaders = [[(x, tgt[6 * i:6 * i + 6]) for i, (x, _) in enumerate(ld)] for ld in loaders]
+    want = 100.0 * ens.eq(tgt).sum().item() / tgt.numel()
+    got = Q.validate_tta(model, loaders)
+    assert abs(got - want) < 1e-9 and want >= 50.0
+    assert not model.training
+    assert Q.validate_tta(model, []) == 0.0
+
+
+def test_forward_hook_on_patch_embed_proj_fires_with_the_conv_activation():
+    """Grad-CAM of the reference (test_hqa.py:241-275) hooks model.patch_embed.proj: the hook must see the [B, d, H/p, W/p]
+    activation and its gradient, and the hooked forward must give the same logits as the fused one."""
+    model, ocfg, sd, _ = build_model("hqavit_c100", precision="fp32")
+    model.eval()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 3, 32, 32, generator=g).cuda()
+    with torch.no_grad():
+        plain = model(x)
+    seen = {}
+
+    def hook(module, inp, out):
+        seen["act"] = out
+        out.register_hook(lambda gr: seen.__setitem__("grad", gr))
+
+    h = model.patch_embed.proj.register_forward_hook(hook)
+    out = model(x)
+    out[:, 3].sum().backward()
+    h.remove()
+    assert torch.allclose(out, plain, rtol=1e-5, atol=1e-6)
+    conv = torch.nn.functional.conv2d(x, model.patch_embed.proj.weight, model.patch_embed.proj.bias, stride=4)
+    assert seen["act"].shape == (2, 192, 8, 8) and torch.allclose(seen["act"], conv, rtol=1e-4, atol=1e-5)
+    assert seen["grad"].shape == (2, 192, 8, 8) and seen["grad"].abs().sum().item() > 0
+    with torch.no_grad():
+        assert torch.equal(model(x), plain)          # hook removed: back on the fused path
+
+
+def test_match_autocast_output_dtype_is_opt_in():
+    model, ocfg, sd, _ = build_model("qavitv2_c100", precision="auto")
+    model.eval()
+    x = torch.randn(2, 3, 32, 32).cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        a = model(x)
+        model.match_autocast_output_dtype = True
+        b = model(x)
+    assert a.dtype == torch.float32 and b.dtype == torch.bfloat16       # the reference's head Linear returns bf16 under autocast
+    assert torch.equal(a.to(torch.bfloat16), b)

@@ -26,6 +26,10 @@ CASES = {
     "hqavit_c100": (dict(family="hqavit"), "hqavit", {}, 4),
     "qavitv2_c100": (dict(family="qavit_v2"), "qavit", dict(variant="v2"), 2),
     "qavit_v1_c10": (dict(family="qavit_v1", num_classes=10, dwconv_bias=True), "qavit", dict(variant="v1"), 2),
+    "qavit_v1_224": (dict(family="qavit_v1", img_size=224, patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64,
+                          dwconv_bias=True), "qavit", dict(variant="v1"), 2),
+    "qavitv2b_224": (dict(family="qavit_v2", img_size=224, patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64,
+                          dwconv_bias=True), "qavit", dict(variant="v2b"), 2),
     "hqavit_tinyin": (dict(family="hqavit", img_size=64, num_classes=200, depth=12, num_learned_tokens=64,
                            stage_depths=(2, 2, 6, 2)), "hqavit", dict(square_tokens=True), 2),
 }
@@ -37,7 +41,8 @@ def build_model(case, device="cuda", precision="fp32"):
     okw, fam, ckw, B = CASES[case]
     ocfg = O.OracleConfig(**okw)
     common = dict(img_size=ocfg.img_size, patch_size=ocfg.patch_size, num_classes=ocfg.num_classes, depth=ocfg.depth,
-                  dropout=0.0, drop_path=0.0)
+                  dropout=0.0, drop_path=0.0, window_size=ocfg.window_size, dilation_factors=tuple(ocfg.dilation_factors),
+                  linformer_k=ocfg.linformer_k)
     if fam == "hqavit":
         cfg = Q.HQAViTConfig(num_learned_tokens=ocfg.num_learned_tokens, **common)
         model = Q.HQAViT(cfg, stage_depths=ocfg.stage_depths, **ckw)
