@@ -65,6 +65,9 @@ typedef struct qavit_block_cfg {
   int32_t dtype;             /* 0 fp32, 1 bf16                                                             */
   float dropout;             /* config.dropout: SDPA dropout_p + the nn.Dropout sites of the block (train only; H:416-465, 648-656, 697-710) */
   float drop_path;           /* this block's DropPath rate (H:1066-1069, 1187), applied per image in train mode */
+  int32_t tokens_out;        /* tokens TokenUpMix emits (its Linear's out_features, fixed at construction: H:1099-1103); 0 = tokens_full.
+                                Differs from tokens_full when a model built for 32 x 32 is fed larger images (STL-10 recipe,
+                                HQAViT_Tiny_stl10.py:250-282: the first block maps 576 -> 16 -> 64 tokens)                  */
 } qavit_block_cfg;
 
 const char* qavit_last_error(void);
@@ -81,7 +84,7 @@ int qavit_block_workspace(const qavit_block_cfg* cfg, size_t* saved_bytes, size_
  * (H:296-321, mutates params[QP_BANK_K/V] and *update_count in train mode), HybridFusion, BottleneckMLP,
  * CCFFFN (H:632-712), and -- when cfg->token_learner -- TokenLearner / TokenUpMix (H:971-1031).
  *   params[QP_COUNT] : fp32 parameter tensors (reference layouts); entries not used by the config may be NULL
- *   x   [batch, tokens_full, dim] fp32      out [batch, tokens_full, dim] fp32 */
+ *   x   [batch, tokens_full, dim] fp32      out [batch, tokens_out (or tokens_full), dim] fp32 */
 int qavit_block_forward(const qavit_block_cfg* cfg, const void* const* params, long long* update_count,
                         unsigned long long* rng, const float* x, float* out, void* saved, void* scratch, void* stream);
 
@@ -90,7 +93,7 @@ int qavit_block_forward(const qavit_block_cfg* cfg, const void* const* params, l
  * backward regenerates every mask from the snapshot -- no mask is stored. */
 /* Backward of the above.  grads[QP_COUNT]: fp32 buffers the parameter gradients are ACCUMULATED into (zero them
  * first; NULL for the write_* / branch .norm parameters, which the reference never trains, H:315).
- *   dout [batch, tokens_full, dim] fp32     dx [batch, tokens_full, dim] fp32 (overwritten) */
+ *   dout [batch, tokens_out (or tokens_full), dim] fp32     dx [batch, tokens_full, dim] fp32 (overwritten) */
 int qavit_block_backward(const qavit_block_cfg* cfg, const void* const* params, float* const* grads, const float* x,
                          const float* dout, float* dx, const void* saved, void* scratch, void* stream);
 
@@ -242,6 +245,9 @@ int qavit_splitfusion_backward(const qavit_splitfusion_cfg* cfg, const void* con
  * 192 channels).  op 0 / 1 = TokenLearner forward / backward, 2 / 3 = TokenUpMix + LayerNorm forward / backward; `in` / `out` are
  * arrays of fp32 device pointers in the order documented next to the definition (csrc/block.cu). */
 int qavit_test_tokens_fused(int op, int B, int N, int C, const float* const* in, float* const* out, void* stream);
+/* Test hook for the fused per-branch LayerNorm + compress Linear + fusion scale kernels (H:1074-1079; d = 192, compress_dim = 48):
+ * op 0 forward, 1 backward; pointer order documented next to the definition (csrc/block.cu). */
+int qavit_test_cmp_fused(int op, long long R, const void* const* in, void* const* out, void* stream);
 
 /* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
 int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,

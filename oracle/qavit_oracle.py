@@ -36,6 +36,9 @@ class OracleConfig:
     """Union of QAViTConfig (QAViT.py:36-56, QAViTv2.py:43-60) and HQAViTConfig (H:42-78)."""
     family: str = "hqavit"           # hqavit | qavit_v1 | qavit_v2
     img_size: int = 32
+    built_img_size: int = 0          # image size the MODULES were built for when it differs from the input (STL-10 fine-tuning feeds
+                                     # 96 x 96 images to the 32 x 32 CIFAR model after resizing pos_embed, HQAViT_Tiny_stl10.py:250-282:
+                                     # TokenUpMix still emits (32 / 4)^2 tokens and LMFAdapter resizes to 8 x 8, H:839-843); 0 = img_size
     patch_size: int = 4
     in_channels: int = 3
     num_classes: int = 100
@@ -456,7 +459,7 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, train: bool = F
         return T if pm is None else T * pm
 
     if cfg.family == "hqavit":
-        hw = cfg.img_size // cfg.patch_size
+        hw = (cfg.built_img_size or cfg.img_size) // cfg.patch_size      # LMFAdapter.target_hw = the grid the model was built for
         f2, f3, f4 = cnn_stem(x, sd, train, new_state)
         R = [rrcv(lmfa(f, sd, f"lmfa{i}", hw), sd, f"rrcv{i}", cfg, hw) for i, f in ((2, f2), (3, f3), (4, f4))]
         T = pos_drop(patch_embed(x, sd, cfg))
@@ -536,7 +539,8 @@ def state_schema(cfg: OracleConfig) -> Dict[str, Tuple[Tuple[int, ...], str]]:
     scale gamma beta fw2 fw4 pos bn_mean bn_var count."""
     d, Kb, H = cfg.embed_dim, cfg.global_bank_size, cfg.num_heads
     G = cfg.num_channel_groups
-    n_tok = (cfg.img_size // cfg.patch_size) ** 2
+    n_tok = (cfg.img_size // cfg.patch_size) ** 2                          # pos_embed rows (resized to the input grid)
+    n_up = ((cfg.built_img_size or cfg.img_size) // cfg.patch_size) ** 2   # TokenUpMix output tokens (fixed at construction)
     p = cfg.patch_size
     S: Dict[str, Tuple[Tuple[int, ...], str]] = {}
 
@@ -655,7 +659,7 @@ def state_schema(cfg: OracleConfig) -> Dict[str, Tuple[Tuple[int, ...], str]]:
                 if cfg.use_token_learner:
                     ln(P + ".token_learner.attention.0", d)
                     lin(P + ".token_learner.attention.1", M, d)
-                    lin(P + ".token_upmix.upsample_attn", n_tok, M)
+                    lin(P + ".token_upmix.upsample_attn", n_up, M)
                     ln(P + ".token_upmix.norm", d)
                 block(P + ".quad_block", M if cfg.use_token_learner else n_tok)
     else:

@@ -21,7 +21,7 @@ class BlockCfg(C.Structure):
         ("n_dilations", C.c_int32), ("dilations", C.c_int32 * 4), ("pool_stride", C.c_int32),
         ("compress_dim", C.c_int32), ("bottleneck_hidden", C.c_int32), ("ffn_hidden", C.c_int32),
         ("ffn_v1", C.c_int32), ("dwconv_bias", C.c_int32), ("bank_v1", C.c_int32), ("train", C.c_int32),
-        ("dtype", C.c_int32), ("dropout", C.c_float), ("drop_path", C.c_float),
+        ("dtype", C.c_int32), ("dropout", C.c_float), ("drop_path", C.c_float), ("tokens_out", C.c_int32),
     ]
 
 
@@ -96,6 +96,7 @@ _SIGS = {
     "qavit_test_gemm_epi": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "qavit_test_gemm_tn": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "qavit_test_tokens_fused": (_i, [_i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    "qavit_test_cmp_fused": (_i, [_i, _ll, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "qavit_convert_weight": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -98,10 +98,15 @@ struct Bump {
 };
 
 struct Dims {
-  int B, Nt, Nf, R, Rf, d, H, hd, kb, G, cg, cpg, ws, side, klin, NM, Lm, cd, bh, fh, dt;
+  int B, Nt, Nf, No, R, Rf, Ro, d, H, hd, kb, G, cg, cpg, ws, side, klin, NM, Lm, cd, bh, fh, dt;
   size_t ts;
   bool tl, v1;
-  bool ftok;   // TokenLearner / TokenUpMix run as the fused split-precision kernels of tokens_fused.cu
+  bool ftok, fup;   // TokenLearner / TokenUpMix run as the fused split-precision kernels of tokens_fused.cu
+  bool fcmp;        // branch LayerNorm + compress + fusion scale of all 4 branches as one kernel per direction (cmp_fused.cu)
+  int tdt;          // storage / GEMM type of the TokenLearner gate path (LN output, logits): fp32 whenever no tensor-core token
+                    // kernel covers the shape (e.g. 576 -> 16 tokens of the 96 x 96 recipe) -- bf16 gate logits under a softmax over
+                    // hundreds of tokens were the largest single bf16 error source of the model
+  size_t tts;
 };
 
 // gemm weights that get bf16 copies in bf16 runs
@@ -115,7 +120,7 @@ struct Saved {  // byte offsets into `saved`
 };
 struct Scratch {  // byte offsets into `scratch`
   size_t tl_logits, tn, cgbuf, partial, attn_ws_f, total_fwd;
-  size_t d_up, d_blk, d_o, d_hn2, d_cs, d_hn, d_hpre, d_y, d_x1, d_x1t, d_h1, d_h1pre, d_fused, d_nb, d_branch, d_attn,
+  size_t d_up, d_blk, d_o, d_hn2, d_cs, d_hn, d_hpre, d_y, d_x1, d_x1t, d_h1, d_h1pre, d_fused, d_nb, d_branch, d_branch3[3], d_attn,
       d_qkv, d_kv, d_xp, d_q, d_xn, dKc, dVc, dkbp, dvbp, draw, d_logits, d_tl_ln, attn_ws_b, total_bwd;
 };
 
@@ -131,6 +136,8 @@ int msda_tokens(const qavit_block_cfg& c, int side) {
 int make_dims(const qavit_block_cfg& c, Dims* D) {
   D->B = c.batch; D->Nt = c.tokens; D->Nf = c.tokens_full; D->tl = c.token_learner != 0;
   D->R = c.batch * c.tokens; D->Rf = c.batch * c.tokens_full;
+  D->No = (c.token_learner && c.tokens_out > 0) ? c.tokens_out : c.tokens_full;      // TokenUpMix output tokens
+  D->Ro = c.batch * D->No;
   D->d = c.dim; D->H = c.heads; D->hd = c.dim / c.heads; D->kb = c.bank_size; D->G = c.groups;
   D->cg = c.dim / c.groups; D->cpg = (c.dim / 2) / c.groups; D->ws = c.window; D->klin = c.linformer_k;
   D->cd = c.compress_dim; D->bh = c.bottleneck_hidden; D->fh = c.ffn_hidden; D->dt = c.dtype; D->v1 = c.ffn_v1 != 0;
@@ -147,6 +154,11 @@ int make_dims(const qavit_block_cfg& c, Dims* D) {
   QV_CHECK(c.token_learner || c.tokens_full == c.tokens, "tokens_full must equal tokens without token learner");
   D->side = side;
   D->ftok = D->tl && c.dtype == QV_BF16 && tokens_fused_ok(c.tokens, c.tokens_full, c.dim);
+  D->fup = D->tl && c.dtype == QV_BF16 && tokens_fused_ok(c.tokens, D->No, c.dim);
+  D->fcmp = c.dtype == QV_BF16 && cmp_fused_ok(c.dim, c.compress_dim);
+  D->tdt = (c.dtype == QV_BF16 && D->tl && !D->ftok && !tokens_mma_ok(c.tokens, c.tokens_full, c.dim) &&
+            !tokens_mma64_ok(c.tokens, c.tokens_full, c.dim)) ? QV_F32 : c.dtype;
+  D->tts = D->tdt == QV_BF16 ? 2 : 4;
   D->NM = msda_tokens(c, side);
   D->Lm = D->NM < c.msda_seq_len ? D->NM : c.msda_seq_len;
   return 0;
@@ -171,9 +183,9 @@ void weight_shape(const Dims& D, int wi, int* N, int* K) {
 
 void layout_saved(const Dims& D, Saved* S) {
   Bump b;
-  const size_t ts = D.ts, R = D.R, Rf = D.Rf, d = D.d;
+  const size_t ts = D.ts, R = D.R, Rf = D.Rf, Ro = D.Ro, d = D.d;
   S->tl_stats = b.take(D.tl && !D.ftok ? Rf * 8 : 0);
-  S->tl_ln = b.take(D.tl && !D.ftok ? Rf * d * ts : 0);
+  S->tl_ln = b.take(D.tl && !D.ftok ? Rf * d * D.tts : 0);
   S->tl_S = b.take(D.tl ? Rf * D.Nt * 4 : 0);
   S->xc = b.take(D.tl ? R * d * 4 : 0);
   S->n1_stats = b.take(R * 8);
@@ -195,7 +207,7 @@ void layout_saved(const Dims& D, Saved* S) {
   S->attn_cross = b.take(R * d * ts);
   for (int i = 0; i < 4; ++i) S->branch[i] = b.take(R * d * ts);
   for (int i = 0; i < 4; ++i) S->nb_stats[i] = b.take(R * 8);
-  for (int i = 0; i < 4; ++i) S->nb[i] = b.take(R * d * ts);
+  for (int i = 0; i < 4; ++i) S->nb[i] = b.take(D.fcmp ? 0 : R * d * ts);   // the fused kernels never materialise LN(branch)
   S->fused = b.take(R * d * ts);
   S->h1_pre = b.take(R * D.bh * ts);
   S->h1 = b.take(R * D.bh * ts);
@@ -211,12 +223,12 @@ void layout_saved(const Dims& D, Saved* S) {
   S->hn2 = b.take(R * D.fh * ts);
   S->o = b.take(R * d * ts);
   S->out_blk = b.take(D.tl ? R * d * 4 : 0);
-  S->up = b.take(D.tl && !D.ftok ? Rf * d * 4 : 0);
-  S->up_stats = b.take(D.tl ? Rf * 8 : 0);
+  S->up = b.take(D.tl && !D.fup ? Ro * d * 4 : 0);
+  S->up_stats = b.take(D.tl ? Ro * 8 : 0);
   for (int i = 0; i < W_COUNT; ++i) {
     int N, K;
     weight_shape(D, i, &N, &K);
-    const bool need = D.dt == QV_BF16 && (i != W_TL || (D.tl && !D.ftok));
+    const bool need = D.dt == QV_BF16 && (i != W_TL || (D.tl && !D.ftok)) && !(D.fcmp && i >= W_C0 && i <= W_C3);
     S->wb[i] = b.take(need ? (size_t)N * K * 2 : 0);
     S->wbt[i] = b.take(need && i != W_WRITE ? (size_t)N * K * 2 : 0);
   }
@@ -228,10 +240,10 @@ void layout_saved(const Dims& D, Saved* S) {
 }
 
 void layout_scratch(const Dims& D, Scratch* S) {
-  const size_t ts = D.ts, R = D.R, Rf = D.Rf, d = D.d;
+  const size_t ts = D.ts, R = D.R, Rf = D.Rf, Ro = D.Ro, d = D.d;
   {
     Bump b;
-    S->tl_logits = b.take(D.tl && !D.ftok ? Rf * D.Nt * ts : 0);
+    S->tl_logits = b.take(D.tl && !D.ftok ? Rf * D.Nt * D.tts : 0);
     S->tn = b.take(R * d * ts);
     S->cgbuf = b.take(R * (d + D.kb) * ts);
     S->partial = b.take((size_t)592 * 2 * D.kb * d * 4);   // bank_write_reduce uses <= 592 CTAs
@@ -240,7 +252,7 @@ void layout_scratch(const Dims& D, Scratch* S) {
   }
   {
     Bump b;
-    S->d_up = b.take(D.tl && !D.ftok ? Rf * d * 4 : 0);
+    S->d_up = b.take(D.tl && !(D.ftok && D.fup) ? (Rf > Ro ? Rf : Ro) * d * 4 : 0);
     S->d_blk = b.take(D.tl ? R * d * 4 : 0);
     S->d_o = b.take(R * d * ts);
     S->d_hn2 = b.take(R * D.fh * ts);
@@ -255,6 +267,7 @@ void layout_scratch(const Dims& D, Scratch* S) {
     S->d_fused = b.take(R * d * ts);
     S->d_nb = b.take(R * d * ts);
     S->d_branch = b.take(R * d * ts);
+    for (int i = 0; i < 3; ++i) S->d_branch3[i] = b.take(D.fcmp ? R * d * ts : 0);   // fused backward emits all four d_branch at once
     S->d_attn = b.take(R * d * ts);
     S->d_qkv = b.take(R * 3 * d * ts);
     S->d_kv = b.take((size_t)D.B * D.NM * 2 * d * ts);
@@ -269,8 +282,8 @@ void layout_scratch(const Dims& D, Scratch* S) {
     S->draw = b.take(16);
     const size_t zero_end = b.off;
     (void)zero_end;
-    S->d_logits = b.take(D.tl && !D.ftok ? Rf * D.Nt * ts : 0);
-    S->d_tl_ln = b.take(D.tl && !D.ftok ? Rf * d * ts : 0);
+    S->d_logits = b.take(D.tl && !D.ftok ? Rf * D.Nt * D.tts : 0);
+    S->d_tl_ln = b.take(D.tl && !D.ftok ? Rf * d * D.tts : 0);
     S->attn_ws_b = b.take(D.dt == QV_BF16 && D.Nt > 16 ? attn_msda64_scratch_bytes(D.B, D.d) : 0);
     S->total_bwd = b.off;
   }
@@ -433,6 +446,7 @@ extern "C" int qavit_block_workspace(const qavit_block_cfg* cfg, size_t* saved_b
 extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const* params, long long* update_count,
                                    unsigned long long* rng, const float* x_in, float* out, void* saved, void* scratch,
                                    void* stream) {
+  QV_RANGE("qavit_block_forward");
   Ctx c;
   QV_TRY(init_ctx(&c, cfg, params, saved, scratch, stream));
   const Dims& D = c.D;
@@ -464,7 +478,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   if (dt == QV_BF16) {
     ConvertJobs jobs{};
     for (int wi = 0; wi < W_COUNT; ++wi) {
-      if ((wi == W_TL && (!D.tl || D.ftok)) || (wi == W_WRITE && !train)) continue;
+      if ((wi == W_TL && (!D.tl || D.ftok)) || (wi == W_WRITE && !train) || (D.fcmp && wi >= W_C0 && wi <= W_C3)) continue;
       int N, K;
       weight_shape(D, wi, &N, &K);
       bf16* wb = reinterpret_cast<bf16*>(c.sv(S.wb[wi]));
@@ -485,11 +499,13 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
                    c.svf(S.xc)));
     x = c.svf(S.xc);
   } else if (D.tl) {
-    QV_TRY(ln_fwd(st, QV_F32, x_in, d, D.Rf, d, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), 1e-5f, 0, nullptr, nullptr, dt,
+    const int tdt = D.tdt;
+    QV_TRY(ln_fwd(st, QV_F32, x_in, d, D.Rf, d, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), 1e-5f, 0, nullptr, nullptr, tdt,
                   c.sv(S.tl_ln), d, c.svf(S.tl_stats)));
-    QV_TRY(gemm_nt(st, dt, c.sv(S.tl_ln), d, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)),
-                   epi_t(c, c.pf(QP_TL_FC_B), c.sc(c.X.tl_logits), D.Nt)));
-    QV_TRY(token_learner_fwd(st, dt, x_in, c.sc(c.X.tl_logits), D.B, D.Nf, D.Nt, d, c.svf(S.tl_S), c.svf(S.xc)));
+    GemmEpi et = epi_t(c, c.pf(QP_TL_FC_B), c.sc(c.X.tl_logits), D.Nt);
+    et.c_f32 = tdt == QV_F32;
+    QV_TRY(gemm_nt(st, tdt, c.sv(S.tl_ln), d, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)), et));
+    QV_TRY(token_learner_fwd(st, tdt, x_in, c.sc(c.X.tl_logits), D.B, D.Nf, D.Nt, d, c.svf(S.tl_S), c.svf(S.xc)));
     x = c.svf(S.xc);
   }
 
@@ -509,6 +525,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   QV_TRY(fusion_softmax(st, c.pf(QP_FUSION_W), 4, c.svf(S.alpha)));
 
   // ---- SWA (H:441-469)
+  nvtxRangePushA("swa");
   QV_TRY(snapshot_bank(c, 0));
   QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_SWA_QKV, c.pf(QP_SWA_QKV_W)), epi_t(c, c.pf(QP_SWA_QKV_B), c.sv(S.qkv_swa), 3 * d)));
   {
@@ -525,6 +542,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[0]), QP_SWA_NORM_W, QP_SWA_NORM_B, update_count));
 
   // ---- MSDA (H:496-532)
+  nvtxRangePop(); nvtxRangePushA("msda");
   QV_TRY(snapshot_bank(c, 1));
   QV_TRY(msda_pool_fwd(st, dt, xn, D.B, D.Nt, D.side, d, cfg->dilations, cfg->n_dilations, cfg->pool_stride, D.NM, c.sv(S.xp)));
   QV_TRY(gemm_nt(st, dt, c.sv(S.xp), d, D.B * D.NM, c.W(W_MSDA_KV, weight_src(c, W_MSDA_KV)),
@@ -545,6 +563,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[1]), QP_MSDA_NORM_W, QP_MSDA_NORM_B, update_count));
 
   // ---- CGA (H:559-595)
+  nvtxRangePop(); nvtxRangePushA("cga");
   QV_TRY(snapshot_bank(c, 2));
   QV_TRY(small_linear_fwd(st, snap_k(c, 2), D.kb, d, c.pf(QP_CGA_BK_W), c.pf(QP_CGA_BK_B), D.cpg, c.svf(S.kbp)));
   QV_TRY(small_linear_fwd(st, snap_v(c, 2), D.kb, d, c.pf(QP_CGA_BV_W), c.pf(QP_CGA_BV_B), D.cpg, c.svf(S.vbp)));
@@ -563,6 +582,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   if (train) QV_TRY(bank_write(c, *cfg, c.sv(S.branch[2]), QP_CGA_NORM_W, QP_CGA_NORM_B, update_count));
 
   // ---- Cross (H:613-626)
+  nvtxRangePop(); nvtxRangePushA("cross");
   QV_TRY(snapshot_bank(c, 3));
   QV_TRY(small_linear_fwd(st, snap_k(c, 3), D.kb, d, c.pf(QP_CROSS_K_W), c.pf(QP_CROSS_K_B), d, c.svf(S.Kc)));
   QV_TRY(small_linear_fwd(st, snap_v(c, 3), D.kb, d, c.pf(QP_CROSS_V_W), c.pf(QP_CROSS_V_B), d, c.svf(S.Vc)));
@@ -578,9 +598,18 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   QV_TRY(proj_gemm(c.sv(S.attn_cross), d, c.W(W_CROSS_PROJ, c.pf(QP_CROSS_PROJ_W)), c.pf(QP_CROSS_PROJ_B), 3));   // H:625
 
   // ---- per-branch LN -> compress -> fusion scale + concat (H:1074-1079)
+  nvtxRangePop(); nvtxRangePushA("fusion+mlp");
   static const int kNormW[4] = {QP_NSWA_W, QP_NMSDA_W, QP_NCGA_W, QP_NCROSS_W};
   static const int kCompW[4] = {QP_CSWA_W, QP_CMSDA_W, QP_CCGA_W, QP_CCROSS_W};
-  for (int i = 0; i < 4; ++i) {
+  if (D.fcmp) {
+    const void* xs[4]; const float *gs[4], *bs[4], *ws[4], *cbs[4]; float* sts[4];
+    for (int i = 0; i < 4; ++i) {
+      xs[i] = c.sv(S.branch[i]); gs[i] = c.pf(kNormW[i]); bs[i] = c.pf(kNormW[i] + 1); ws[i] = c.pf(kCompW[i]); cbs[i] = c.pf(kCompW[i] + 1);
+      sts[i] = c.svf(S.nb_stats[i]);
+    }
+    QV_TRY(cmpf_fwd(st, R, xs, gs, bs, ws, cbs, c.svf(S.alpha), 1e-5f, c.sv(S.fused), sts));
+  }
+  for (int i = 0; i < 4 && !D.fcmp; ++i) {
     QV_TRY(ln_fwd(st, dt, c.sv(S.branch[i]), d, R, d, c.pf(kNormW[i]), c.pf(kNormW[i] + 1), 1e-5f, 0, nullptr, nullptr, dt,
                   c.sv(S.nb[i]), d, c.svf(S.nb_stats[i])));
     GemmEpi e = epi_t(c, c.pf(kCompW[i] + 1), static_cast<uint8_t*>(c.sv(S.fused)) + (size_t)i * D.cd * D.ts, d);
@@ -646,13 +675,15 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
       QV_TRY(drop_rows(st, dt, c.sv(S.o), d, R, d, dc.site(DS_FFN), dc.rs2, D.Nt, c.svf(S.x1), d, nullptr, blk_out, d));
     }
   }
+  nvtxRangePop();
   // ---- TokenUpMix (H:1016-1031)
-  if (D.ftok) {   // up-mix GEMM + LayerNorm in one kernel: the [B Nf, d] pre-norm tensor is never written (backward recomputes it)
-    QV_TRY(upf_fwd(st, blk_out, D.B, D.Nf, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.pf(QP_UP_LN_W), c.pf(QP_UP_LN_B), 1e-5f, out,
+  QV_RANGE("token_upmix");
+  if (D.fup) {   // up-mix GEMM + LayerNorm in one kernel: the [B No, d] pre-norm tensor is never written (backward recomputes it)
+    QV_TRY(upf_fwd(st, blk_out, D.B, D.No, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.pf(QP_UP_LN_W), c.pf(QP_UP_LN_B), 1e-5f, out,
                    c.svf(S.up_stats)));
   } else if (D.tl) {
-    QV_TRY(token_upmix_fwd(st, dt, blk_out, D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.svf(S.up)));
-    QV_TRY(ln_fwd(st, QV_F32, c.sv(S.up), d, D.Rf, d, c.pf(QP_UP_LN_W), c.pf(QP_UP_LN_B), 1e-5f, 0, nullptr, nullptr, QV_F32, out, d, c.svf(S.up_stats)));
+    QV_TRY(token_upmix_fwd(st, dt, blk_out, D.B, D.Nt, D.No, d, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.svf(S.up)));
+    QV_TRY(ln_fwd(st, QV_F32, c.sv(S.up), d, D.Ro, d, c.pf(QP_UP_LN_W), c.pf(QP_UP_LN_B), 1e-5f, 0, nullptr, nullptr, QV_F32, out, d, c.svf(S.up_stats)));
   }
   return 0;
 }
@@ -663,6 +694,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
 extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* const* params, float* const* grads,
                                     const float* x_in, const float* dout, float* dx, const void* saved, void* scratch,
                                     void* stream) {
+  QV_RANGE("qavit_block_backward");
   Ctx c;
   QV_TRY(init_ctx(&c, cfg, params, saved, scratch, stream));
   QV_CHECK(grads && dout && dx, "null argument");
@@ -683,14 +715,14 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
 
   // ---- TokenUpMix backward
   const float* dblk = dout;
-  if (D.ftok) {   // (the up-mix bias gradient is exactly zero -- a per-token constant removed by the LayerNorm that follows -- and stays 0)
-    QV_TRY(upf_bwd(st, c.svf(S.out_blk), dout, c.svf(S.up_stats), D.B, D.Nf, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.pf(QP_UP_LN_W),
+  if (D.fup) {   // (the up-mix bias gradient is exactly zero -- a per-token constant removed by the LayerNorm that follows -- and stays 0)
+    QV_TRY(upf_bwd(st, c.svf(S.out_blk), dout, c.svf(S.up_stats), D.B, D.No, c.pf(QP_UP_FC_W), c.pf(QP_UP_FC_B), c.pf(QP_UP_LN_W),
                    c.scf(X.d_blk), G(QP_UP_FC_W), G(QP_UP_LN_W), G(QP_UP_LN_B)));
     dblk = c.scf(X.d_blk);
   } else if (D.tl) {
-    QV_TRY(ln_bwd(st, QV_F32, c.sv(S.up), d, QV_F32, dout, d, D.Rf, d, c.pf(QP_UP_LN_W), c.svf(S.up_stats), 0, QV_F32, nullptr,
+    QV_TRY(ln_bwd(st, QV_F32, c.sv(S.up), d, QV_F32, dout, d, D.Ro, d, c.pf(QP_UP_LN_W), c.svf(S.up_stats), 0, QV_F32, nullptr,
                   c.scf(X.d_up), nullptr, G(QP_UP_LN_W), G(QP_UP_LN_B)));
-    QV_TRY(token_upmix_bwd(st, dt, c.svf(S.out_blk), c.scf(X.d_up), D.B, D.Nt, D.Nf, d, c.pf(QP_UP_FC_W), c.scf(X.d_blk),
+    QV_TRY(token_upmix_bwd(st, dt, c.svf(S.out_blk), c.scf(X.d_up), D.B, D.Nt, D.No, d, c.pf(QP_UP_FC_W), c.scf(X.d_blk),
                            G(QP_UP_FC_W), G(QP_UP_FC_B)));
     dblk = c.scf(X.d_blk);
   }
@@ -757,20 +789,33 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
   GemmEpi acc_xn;
   acc_xn.C = d_xn; acc_xn.ldc = d; acc_xn.c_f32 = 1; acc_xn.c_accum = 1;
 
+  void* d_branch_buf[4] = {c.sc(X.d_branch), c.sc(X.d_branch), c.sc(X.d_branch), c.sc(X.d_branch)};
+  if (D.fcmp) {   // compress_i and norm_i backward of all four branches in one launch (dropout site of each branch output applied)
+    const void* xs[4]; const float *sts[4], *gs[4], *bs[4], *ws[4]; void* dxs[4]; float *dws[4], *dbs[4], *dgs[4], *dbt[4];
+    DropP sites[4];
+    for (int i = 0; i < 4; ++i) {
+      if (i > 0) d_branch_buf[i] = c.sc(X.d_branch3[i - 1]);
+      xs[i] = c.sv(S.branch[i]); sts[i] = c.svf(S.nb_stats[i]); gs[i] = c.pf(kNormW[i]); bs[i] = c.pf(kNormW[i] + 1); ws[i] = c.pf(kCompW[i]);
+      dxs[i] = d_branch_buf[i]; dws[i] = G(kCompW[i]); dbs[i] = G(kCompW[i] + 1); dgs[i] = G(kNormW[i]); dbt[i] = G(kNormW[i] + 1);
+      sites[i] = dc.site(DS_PROJ + i);
+    }
+    QV_TRY(cmpf_bwd(st, R, xs, sts, gs, bs, ws, c.svf(S.alpha), c.sc(X.d_fused), dxs, dws, dbs, dgs, dbt, sites));
+  }
   for (int i = 3; i >= 0; --i) {
-    // compress_i and norm_i backward -> d_branch
-    const uint8_t* dfs = static_cast<const uint8_t*>(c.sc(X.d_fused)) + (size_t)i * D.cd * D.ts;
-    const float* alpha_i = c.svf(S.alpha) + i;
-    QV_TRY(gemm_tn(st, dt, dfs, d, c.sv(S.nb[i]), d, R, D.cd, d, G(kCompW[i]), G(kCompW[i] + 1), alpha_i));
-    GemmEpi e = epi_t(c, nullptr, c.sc(X.d_nb), d);
-    e.scale_pre = alpha_i;
-    QV_TRY(gemm_nn(st, dt, dfs, d, R, c.W(W_C0 + i, c.pf(kCompW[i])), e));
-    {   // d_branch goes through the branch's output-dropout site inside the LayerNorm backward
+    if (!D.fcmp) {
+      // compress_i and norm_i backward -> d_branch
+      const uint8_t* dfs = static_cast<const uint8_t*>(c.sc(X.d_fused)) + (size_t)i * D.cd * D.ts;
+      const float* alpha_i = c.svf(S.alpha) + i;
+      QV_TRY(gemm_tn(st, dt, dfs, d, c.sv(S.nb[i]), d, R, D.cd, d, G(kCompW[i]), G(kCompW[i] + 1), alpha_i));
+      GemmEpi e = epi_t(c, nullptr, c.sc(X.d_nb), d);
+      e.scale_pre = alpha_i;
+      QV_TRY(gemm_nn(st, dt, dfs, d, R, c.W(W_C0 + i, c.pf(kCompW[i])), e));
+      // d_branch goes through the branch's output-dropout site inside the LayerNorm backward
       const DropP site = dc.site(DS_PROJ + i);
       QV_TRY(ln_bwd(st, dt, c.sv(S.branch[i]), d, dt, c.sc(X.d_nb), d, R, d, c.pf(kNormW[i]), c.svf(S.nb_stats[i]), 0, dt,
                     c.sc(X.d_branch), nullptr, nullptr, G(kNormW[i]), G(kNormW[i] + 1), &site));
     }
-    const void* d_branch = c.sc(X.d_branch);
+    const void* d_branch = d_branch_buf[i];
     if (i == 3) {  // ---- cross
       QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_cross), d, R, d, d, G(QP_CROSS_PROJ_W), G(QP_CROSS_PROJ_B), nullptr));
       QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_CROSS_PROJ, c.pf(QP_CROSS_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d)));
@@ -854,10 +899,13 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
     QV_TRY(tlf_bwd(st, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), c.pf(QP_TL_FC_W), 1e-5f, dx,
                    G(QP_TL_FC_W), G(QP_TL_FC_B), G(QP_TL_LN_W), G(QP_TL_LN_B)));
   } else if (D.tl) {
-    QV_TRY(token_learner_bwd(st, dt, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, D.Nt, d, c.sc(X.d_logits), c.scf(X.d_up)));   // d_up is free again
-    QV_TRY(gemm_tn(st, dt, c.sc(X.d_logits), D.Nt, c.sv(S.tl_ln), d, D.Rf, D.Nt, d, G(QP_TL_FC_W), G(QP_TL_FC_B), nullptr));
-    QV_TRY(gemm_nn(st, dt, c.sc(X.d_logits), D.Nt, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)), epi_t(c, nullptr, c.sc(X.d_tl_ln), d)));
-    QV_TRY(ln_bwd(st, QV_F32, x_in, d, dt, c.sc(X.d_tl_ln), d, D.Rf, d, c.pf(QP_TL_LN_W), c.svf(S.tl_stats), 0, QV_F32, nullptr, dx,
+    const int tdt = D.tdt;
+    QV_TRY(token_learner_bwd(st, tdt, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, D.Nt, d, c.sc(X.d_logits), c.scf(X.d_up)));   // d_up is free again
+    QV_TRY(gemm_tn(st, tdt, c.sc(X.d_logits), D.Nt, c.sv(S.tl_ln), d, D.Rf, D.Nt, d, G(QP_TL_FC_W), G(QP_TL_FC_B), nullptr));
+    GemmEpi et = epi_t(c, nullptr, c.sc(X.d_tl_ln), d);
+    et.c_f32 = tdt == QV_F32;
+    QV_TRY(gemm_nn(st, tdt, c.sc(X.d_logits), D.Nt, D.Rf, c.W(W_TL, c.pf(QP_TL_FC_W)), et));
+    QV_TRY(ln_bwd(st, QV_F32, x_in, d, tdt, c.sc(X.d_tl_ln), d, D.Rf, d, c.pf(QP_TL_LN_W), c.svf(S.tl_stats), 0, QV_F32, nullptr, dx,
                   c.scf(X.d_up), G(QP_TL_LN_W), G(QP_TL_LN_B)));
   }
   return 0;
@@ -965,6 +1013,24 @@ extern "C" int qavit_test_tokens_fused(int op, int B, int N, int C, const float*
     case 3: return upf_bwd(s, in[0], in[1], in[2], B, N, in[3], in[4], in[5], out[0], out[1], out[2], out[3]);
   }
   qv_set_error("tokens_fused: op %d", op);
+  return 1;
+}
+// The fused branch-LayerNorm + compress kernels (cmp_fused.cu; d = 192, compress_dim = 48) on their own.  op 0 = forward, 1 = backward.
+//   0: in  {x0..x3 (bf16 [R, 192]), gamma0..3, beta0..3, W0..3 ([48, 192]), b0..3, alpha[4]}   out {fused (bf16 [R, 192]), stats0..3 ([R, 2])}
+//   1: in  {x0..x3, stats0..3, gamma0..3, beta0..3, W0..3, alpha[4], dfused (bf16 [R, 192])}   out {dx0..3 (bf16), dW0..3, db0..3, dgamma0..3, dbeta0..3}
+extern "C" int qavit_test_cmp_fused(int op, long long R, const void* const* in, void* const* out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  QV_CHECK(in && out, "cmp_fused: null argument");
+  if (op == 0) {
+    return cmpf_fwd(s, (long)R, in, (const float* const*)(in + 4), (const float* const*)(in + 8), (const float* const*)(in + 12),
+                    (const float* const*)(in + 16), (const float*)in[20], 1e-5f, out[0], (float* const*)(out + 1));
+  }
+  if (op == 1) {
+    return cmpf_bwd(s, (long)R, in, (const float* const*)(in + 4), (const float* const*)(in + 8), (const float* const*)(in + 12),
+                    (const float* const*)(in + 16), (const float*)in[20], in[21], out, (float* const*)(out + 4), (float* const*)(out + 8),
+                    (float* const*)(out + 12), (float* const*)(out + 16), nullptr);
+  }
+  qv_set_error("cmp_fused: op %d", op);
   return 1;
 }
 extern "C" int qavit_convert_weight(const float* w, int N, int K, void* wb, void* wbt, void* stream) {

@@ -250,11 +250,11 @@ __global__ void __launch_bounds__(NT) cga_bwd_kernel(CgaP p, CgaLay ly) {
   }
 }
 
-CgaLay cga_layout(const CgaP& p, bool bwd) {
+CgaLay cga_layout_qc(const CgaP& p, bool bwd, int qc) {
   CgaLay ly{};
   ly.NKV = p.Nt + p.kb;
   ly.SP = ly.NKV + 1;
-  ly.QC = p.Nt < 32 ? p.Nt : 32;
+  ly.QC = p.Nt < qc ? p.Nt : qc;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   ly.oX = take(p.Nt * (p.cg + 1));
@@ -271,6 +271,16 @@ CgaLay cga_layout(const CgaP& p, bool bwd) {
   ly.odW = take(bwd ? 3 * p.cpg * p.cg + 3 * p.cpg : 0);
   ly.odkb = take(bwd ? 2 * p.kb * p.cpg : 0);
   ly.total = o;
+  return ly;
+}
+// query-chunk height: 32 rows, halved while the probability tiles [heads][QC][Nkv] do not fit (196 + 16 keys at 224 / 16)
+CgaLay cga_layout(const CgaP& p, bool bwd) {
+  int qc = 32;
+  CgaLay ly = cga_layout_qc(p, bwd, qc);
+  while (qc > 4 && (size_t)ly.total * sizeof(float) > 200 * 1024) {
+    qc >>= 1;
+    ly = cga_layout_qc(p, bwd, qc);
+  }
   return ly;
 }
 

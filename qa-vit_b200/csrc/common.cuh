@@ -7,6 +7,18 @@
 
 typedef __nv_bfloat16 bf16;
 
+// ---------------------------------------------------------------- NVTX ranges (header-only nvtx3; no-ops unless a profiler is attached)
+#include <nvtx3/nvToolsExt.h>
+struct QvRange {
+  explicit QvRange(const char* name) { nvtxRangePushA(name); }
+  ~QvRange() { nvtxRangePop(); }
+  QvRange(const QvRange&) = delete;
+  QvRange& operator=(const QvRange&) = delete;
+};
+#define QV_CONCAT_(a, b) a##b
+#define QV_CONCAT(a, b) QV_CONCAT_(a, b)
+#define QV_RANGE(name) QvRange QV_CONCAT(qv_range_, __LINE__)(name)
+
 // ---------------------------------------------------------------- error plumbing (C-ABI: int status + last error)
 void qv_set_error(const char* fmt, ...);
 #define QV_CHECK(cond, ...)                \

@@ -257,6 +257,82 @@ __global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__
   }
 }
 
+// Banded flavour for maps whose x and dy tiles do not fit shared memory together (24 x 24 maps of the 96 x 96 STL-10 recipe): the
+// map is walked in bands of BH output rows; x rows [y0 - K/2, y0 + BH + K/2) and dy rows [y0, y0 + BH) are staged per band.
+template <typename T, int K>
+__global__ void __launch_bounds__(CS * PG) dw_wgrad_band_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy,
+                                                                int lddy, int B, int H, int W, int C, float* __restrict__ dw,
+                                                                float* __restrict__ dbias, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, const float* __restrict__ scale,
+                                                                float* __restrict__ dscale, int BH) {
+  extern __shared__ float sm[];
+  const int HW = H * W, XR = BH + K - 1;
+  float* xs = sm;                    // [XR * W][CS]
+  float* gs = sm + XR * W * CS;      // [BH * W][CS]
+  const int c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS;
+  float acc[K * K], ab = 0.f;
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) acc[t] = 0.f;
+  const int segs = (W + SEG - 1) / SEG;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int y0 = 0; y0 < H; y0 += BH) {
+      const int y1 = min(H, y0 + BH), ylo = max(0, y0 - K / 2), yhi = min(H, y1 + K / 2);
+      __syncthreads();
+      load_tile(xs, x, ldx, (long)b * HW + (long)ylo * W, (yhi - ylo) * W, c0, C);
+      load_tile(gs, dy, lddy, (long)b * HW + (long)y0 * W, (y1 - y0) * W, c0, C);
+      __syncthreads();
+      for (int task = pg; task < (y1 - y0) * segs; task += PG) {
+        const int py = y0 + task / segs, px0 = (task % segs) * SEG;
+        float g[SEG];
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+          g[j] = (px0 + j < W) ? gs[((py - y0) * W + px0 + j) * CS + cl] : 0.f;
+          ab += g[j];
+        }
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const int yy = py + ky - K / 2;
+          if (yy < 0 || yy >= H) continue;
+          float xr[SEG + K - 1];
+#pragma unroll
+          for (int i = 0; i < SEG + K - 1; ++i) {
+            const int xx = px0 + i - K / 2;
+            xr[i] = (xx >= 0 && xx < W) ? xs[((yy - ylo) * W + xx) * CS + cl] : 0.f;
+          }
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            float a = acc[ky * K + kx];
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) a = fmaf(g[j], xr[j + kx], a);
+            acc[ky * K + kx] = a;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* red = sm;                   // [PG][K*K + 1][CS]
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) red[(pg * (K * K + 1) + t) * CS + cl] = acc[t];
+  red[(pg * (K * K + 1) + K * K) * CS + cl] = ab;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < (K * K + 1) * CS; idx += CS * PG) {
+    const int t = idx / CS, cc = idx % CS;
+    if (c0 + cc >= C) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < PG; ++q) s += red[(q * (K * K + 1) + t) * CS + cc];
+    const float scl = scale ? scale[c0 + cc] : 1.f;
+    if (t < K * K) {
+      atomicAdd(dw + (c0 + cc) * K * K + t, s * scl);
+      if (dscale) atomicAdd(dscale + c0 + cc, s * w[(c0 + cc) * K * K + t]);
+    } else {
+      if (dbias) atomicAdd(dbias + c0 + cc, s * scl);
+      if (dscale && bias) atomicAdd(dscale + c0 + cc, s * bias[c0 + cc]);
+    }
+  }
+}
+
 template <typename T, int K, bool F, int WT>
 int launch_fwd(cudaStream_t s, const DwP& p, dim3 grid, size_t smem) {
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<T, K, F, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -299,8 +375,20 @@ template <typename T, int K>
 int run_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias,
               const DwScale& sc) {
   const size_t tile = (size_t)2 * H * W * CS * sizeof(float), red = (size_t)PG * (K * K + 1) * CS * sizeof(float);
+  if (tile > 200 * 1024) {   // x and dy tiles of the whole map do not fit: banded kernel
+    int BH = H;
+    auto band_bytes = [&](int bh) { return (size_t)(2 * bh + K - 1) * W * CS * sizeof(float); };
+    while (BH > 1 && band_bytes(BH) > 200 * 1024) --BH;
+    const size_t bsm = band_bytes(BH) > red ? band_bytes(BH) : red;
+    QV_CHECK(bsm <= 200 * 1024, "dwconv wgrad: %dx%d feature map too large", H, W);
+    const int cchb = cdiv(C, CS);
+    dim3 gridb(max(1, min(B, qv_num_sms() / cchb)), cchb);
+    QV_CUDA(cudaFuncSetAttribute(dw_wgrad_band_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    dw_wgrad_band_kernel<T, K><<<gridb, CS * PG, bsm, s>>>(x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc.w, sc.bias, sc.scale, sc.dscale, BH);
+    QV_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t smem = tile > red ? tile : red;
-  QV_CHECK(smem <= 200 * 1024, "dwconv wgrad: %dx%d feature map too large", H, W);
   const int cch = cdiv(C, CS);
   const int occ = max(1, min(6, (int)(200 * 1024 / (smem + 1024))));
   dim3 grid(max(1, min(B, qv_num_sms() * occ / cch)), cch);

@@ -124,6 +124,10 @@ int sf_post_bwd(cudaStream_t s, int dt, const SfArgs& a, const float* dout, cons
                 float* dR, void* dglin, void* dcpre, float* d_fin_g, float* d_fin_b, float* d_cat_g, float* d_cat_b, float* draw);
 int sf_pre_bwd(cudaStream_t s, int dt, const float* Tin, const float* R, const void* dg_in, const void* dcat, long rows, int C,
                const float* gamma, const float* stats, float* dT, float* dR, float* dgamma, float* dbeta);
+// F.interpolate(mode = 'bilinear', align_corners = False) of a channels-last [B, Hi, Wi, C] map to [B, Ho, Wo, C] and its backward
+// (din is overwritten) -- LMFAdapter's resize, H:839-843
+int resize_bilinear_fwd(cudaStream_t s, int dt, const void* in, int B, int Hi, int Wi, int Ho, int Wo, int C, void* out);
+int resize_bilinear_bwd(cudaStream_t s, int dt, const void* dout, int B, int Hi, int Wi, int Ho, int Wo, int C, void* din);
 int rng_snapshot_advance(cudaStream_t s, unsigned long long* rng, unsigned long long* snap);
 
 // ---- dropout / DropPath of the quad block (drop.cu).  Masks come from (rng snapshot, site, element index): backward
@@ -256,6 +260,14 @@ int upf_fwd(cudaStream_t s, const float* xc, int B, int N, const float* W, const
             float eps, float* out, float* stats);
 int upf_bwd(cudaStream_t s, const float* xc, const float* dout, const float* stats, int B, int N, const float* W, const float* bias,
             const float* gamma, float* dxc, float* dW, float* dgamma, float* dbeta);
+// per-branch LayerNorm + compress Linear + fusion scale + concat for all 4 branches in one launch, and its backward (cmp_fused.cu);
+// bf16 runs with d = 192, compress_dim = 48.  x[i]: branch outputs [R, 192] bf16; stats[i]: (mean, rstd) per row (written by fwd)
+bool cmp_fused_ok(int d, int cd);
+int cmpf_fwd(cudaStream_t s, long R, const void* const* x, const float* const* gamma, const float* const* beta, const float* const* W,
+             const float* const* bias, const float* alpha, float eps, void* fused, float* const* stats);
+int cmpf_bwd(cudaStream_t s, long R, const void* const* x, const float* const* stats, const float* const* gamma, const float* const* beta,
+             const float* const* W, const float* alpha, const void* dfused, void* const* dx, float* const* dW, float* const* db,
+             float* const* dgamma, float* const* dbeta, const DropP* drop);
 bool bank_write_mma_ok(int Nt, int d, int kb, int ldcg);
 int bank_write_reduce_mma(cudaStream_t s, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, float* partial, int* n_partial);
 // register-blocked flavours for 16 learned tokens (tokens.cu)

@@ -49,7 +49,7 @@ const char* kRrSfx[RR_N] = {"reverse_proj.weight", "reverse_proj.bias", "reembed
 
 int check_cfg(const qavit_lateral_cfg& c) {
   QV_CHECK(c.batch > 0 && c.img_size % 4 == 0, "lateral: img_size %d must be a multiple of 4", c.img_size);
-  QV_CHECK(c.grid == c.img_size / 4, "lateral: token grid %d != img_size / 4 (the bilinear resize of H:824 is not implemented)", c.grid);
+  QV_CHECK(c.grid >= 1 && c.grid <= c.img_size, "lateral: token grid %d", c.grid);
   QV_CHECK(c.c_stem % 8 == 0 && c.c2 % 8 == 0 && c.c3 % 8 == 0 && c.c4 % 8 == 0 && c.rrcv_channels % 8 == 0 && c.dim % 8 == 0,
            "lateral: channel counts must be multiples of 8");
   QV_CHECK(c.c2 <= 256 && c.c3 <= 256 && c.c4 <= 256 && c.rrcv_channels <= 256 && c.dim <= 256, "lateral: channel counts must be <= 256");
@@ -62,13 +62,14 @@ int check_cfg(const qavit_lateral_cfg& c) {
 struct LinPlan { size_t wb = 0, wbt = 0; int N = 0, K = 0; };
 struct CnxPlan { int C; size_t u, stats, n, hpre, h, out; LinPlan w1, w2; };
 struct CbPlan { int Cin, Cout; size_t c, mr, a, wp; LinPlan w; int Kp; };
-struct LmPlan { int C; size_t cat, p, stats, A, A32; LinPlan w; };
+struct LmPlan { int C; size_t cat, pm, p, stats, A, A32; LinPlan w; };   // pm: projection at map resolution (only when it is resized)
 struct RrPlan { size_t r0, r2, stats; CnxPlan blk[4]; LinPlan rev, re; };
 struct Plan {
   int dt, B, d, nb;
   size_t ts;
-  long R1, R;            // rows at the stem resolution (img/2)^2 and at the token resolution (img/4)^2
-  int H1, H;             // side lengths
+  long R1, R, Rt;        // rows at the stem resolution (img/2)^2, the feature-map resolution (img/4)^2 and the token grid
+  int H1, H, Ht;         // side lengths; Ht != H: LMFAdapter resizes its projection bilinearly (H:839-843)
+  bool resize;
   CbPlan cb[4];
   CnxPlan cx[3];
   LmPlan lm[3];
@@ -102,6 +103,9 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
   p.H1 = c.img_size / 2; p.H = c.img_size / 4;
   p.R1 = (long)c.batch * p.H1 * p.H1;
   p.R = (long)c.batch * p.H * p.H;
+  p.Ht = c.grid;
+  p.Rt = (long)c.batch * p.Ht * p.Ht;
+  p.resize = p.Ht != p.H;
   const bool bf = c.dtype == QV_BF16;
   const size_t ts = p.ts;
   const int chans[5] = {c.in_channels, c.c_stem, c.c2, c.c3, c.c4};
@@ -122,18 +126,19 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
     LmPlan& q = p.lm[i];
     q.C = chans[i + 2];
     q.cat = b.take(p.R * 3 * q.C * ts);
-    q.p = b.take(p.R * c.dim * ts);
-    q.stats = b.take(p.R * 8);
-    q.A = b.take(p.R * c.dim * ts);
-    q.A32 = bf ? b.take(p.R * c.dim * 4) : q.A;   // fp32 copy of A for RRCV's residual (autocast keeps LN outputs in fp32)
+    q.pm = b.take(p.resize ? p.R * c.dim * ts : 0);
+    q.p = b.take(p.Rt * c.dim * ts);
+    q.stats = b.take(p.Rt * 8);
+    q.A = b.take(p.Rt * c.dim * ts);
+    q.A32 = bf ? b.take(p.Rt * c.dim * 4) : q.A;   // fp32 copy of A for RRCV's residual (autocast keeps LN outputs in fp32)
     plan_lin(b, q.w, c.dim, 3 * q.C, bf);
   }
   for (int i = 0; i < 3; ++i) {
     RrPlan& q = p.rr[i];
-    q.r0 = b.take(p.R * c.rrcv_channels * ts);
-    for (int j = 0; j < c.rrcv_blocks; ++j) plan_cnx(b, q.blk[j], c.rrcv_channels, p.R, ts, bf);
-    q.r2 = b.take(p.R * c.dim * ts);
-    q.stats = b.take(p.R * 8);
+    q.r0 = b.take(p.Rt * c.rrcv_channels * ts);
+    for (int j = 0; j < c.rrcv_blocks; ++j) plan_cnx(b, q.blk[j], c.rrcv_channels, p.Rt, ts, bf);
+    q.r2 = b.take(p.Rt * c.dim * ts);
+    q.stats = b.take(p.Rt * 8);
     plan_lin(b, q.rev, c.rrcv_channels, c.dim, bf);
     plan_lin(b, q.re, c.dim, c.rrcv_channels, bf);
   }
@@ -148,11 +153,12 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
   p.col0 = s.take(p.R1 * p.cb[0].Kp * ts);
   p.col1 = s.take(p.R * p.cb[1].Kp * ts);
   p.sums = s.take(2 * 2048 * 4);
-  p.wide = s.take(p.R * wide * ts);
-  p.t1 = s.take(p.R * cmax * ts);
-  p.t2 = s.take(p.R * cmax * ts);
+  const long Rm = p.R > p.Rt ? p.R : p.Rt;
+  p.wide = s.take(Rm * wide * ts);
+  p.t1 = s.take(Rm * cmax * ts);
+  p.t2 = s.take(Rm * cmax * ts);
   for (int i = 0; i < 3; ++i) p.df[i] = s.take(p.R * chans[i + 2] * ts);
-  p.dA = s.take(p.R * c.dim * ts);
+  p.dA = s.take(Rm * c.dim * ts);
   p.da0 = s.take(p.R1 * c.c_stem * ts);
   p.dc0 = s.take(p.R1 * c.c_stem * ts);
   p.dwp0 = s.take((size_t)p.cb[0].Cout * p.cb[0].Kp * 4);
@@ -345,6 +351,7 @@ extern "C" int qavit_lateral_workspace(const qavit_lateral_cfg* cfg, size_t* sav
 
 extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* const* params, const float* img, float* R2, float* R3,
                                      float* R4, void* saved, void* scratch, void* stream) {
+  QV_RANGE("qavit_lateral_forward");
   Ctx c;
   QV_TRY(init_ctx(&c, cfg, params, nullptr, saved, scratch, stream));
   const Plan& P = c.P;
@@ -397,20 +404,21 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
     a.y = static_cast<uint8_t*>(c.sv(q.cat)) + (size_t)C * P.ts;
     a.copy = static_cast<uint8_t*>(c.sv(q.cat)) + (size_t)2 * C * P.ts; a.ldcp = 3 * C;
     QV_TRY(dw2d_fwd(st, dt, a, false));
-    QV_TRY(lin_fwd(c, c.sv(q.cat), 3 * C, P.R, q.w, c.pf(pb + LM_PROJ_W), c.pf(pb + LM_PROJ_B), c.sv(q.p)));
-    QV_TRY(rowln_fwd(st, dt, c.sv(q.p), P.R, d, c.pf(pb + LM_LN_W), c.pf(pb + LM_LN_B), 1e-5f, 1, dt, nullptr, nullptr, c.sv(q.A),
+    QV_TRY(lin_fwd(c, c.sv(q.cat), 3 * C, P.R, q.w, c.pf(pb + LM_PROJ_W), c.pf(pb + LM_PROJ_B), c.sv(P.resize ? q.pm : q.p)));
+    if (P.resize) QV_TRY(resize_bilinear_fwd(st, dt, c.sv(q.pm), P.B, P.H, P.H, P.Ht, P.Ht, d, c.sv(q.p)));
+    QV_TRY(rowln_fwd(st, dt, c.sv(q.p), P.Rt, d, c.pf(pb + LM_LN_W), c.pf(pb + LM_LN_B), 1e-5f, 1, dt, nullptr, nullptr, c.sv(q.A),
                      dt == QV_BF16 ? static_cast<float*>(c.sv(q.A32)) : nullptr, static_cast<float*>(c.sv(q.stats))));
     // RRCV
     const RrPlan& r = P.rr[i];
     const int rb = rr_base(*cfg, i);
-    QV_TRY(lin_fwd(c, c.sv(q.A), d, P.R, r.rev, c.pf(rb + RR_REV_W), c.pf(rb + RR_REV_B), c.sv(r.r0)));
+    QV_TRY(lin_fwd(c, c.sv(q.A), d, P.Rt, r.rev, c.pf(rb + RR_REV_W), c.pf(rb + RR_REV_B), c.sv(r.r0)));
     const void* cur = c.sv(r.r0);
     for (int j = 0; j < cfg->rrcv_blocks; ++j) {
-      QV_TRY(cnx_fwd(c, r.blk[j], rr_blk(*cfg, i, j), P.H, cur, c.sv(r.blk[j].out)));
+      QV_TRY(cnx_fwd(c, r.blk[j], rr_blk(*cfg, i, j), P.Ht, cur, c.sv(r.blk[j].out)));
       cur = c.sv(r.blk[j].out);
     }
-    QV_TRY(lin_fwd(c, cur, cfg->rrcv_channels, P.R, r.re, c.pf(rb + RR_RE_W), c.pf(rb + RR_RE_B), c.sv(r.r2)));
-    QV_TRY(rowln_fwd(st, dt, c.sv(r.r2), P.R, d, c.pf(rb + RR_LN_W), c.pf(rb + RR_LN_B), 1e-5f, 0, QV_F32, c.sv(q.A32),
+    QV_TRY(lin_fwd(c, cur, cfg->rrcv_channels, P.Rt, r.re, c.pf(rb + RR_RE_W), c.pf(rb + RR_RE_B), c.sv(r.r2)));
+    QV_TRY(rowln_fwd(st, dt, c.sv(r.r2), P.Rt, d, c.pf(rb + RR_LN_W), c.pf(rb + RR_LN_B), 1e-5f, 0, QV_F32, c.sv(q.A32),
                      c.pf(rb + RR_BETA), Rout[i], nullptr, static_cast<float*>(c.sv(r.stats))));
   }
   return 0;
@@ -419,6 +427,7 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
 extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* const* params, float* const* grads, const float* img,
                                       const float* dR2, const float* dR3, const float* dR4, const void* saved, void* scratch,
                                       void* stream) {
+  QV_RANGE("qavit_lateral_backward");
   Ctx c;
   QV_TRY(init_ctx(&c, cfg, params, grads, saved, scratch, stream));
   QV_CHECK(grads, "lateral_backward: null grads");
@@ -445,20 +454,25 @@ extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* 
       continue;
     }
     // R = A + beta * LN(r2)
-    QV_TRY(rowln_bwd(st, dt, c.sv(r.r2), QV_F32, dRs[i], P.R, d, c.pf(rb + RR_LN_W), c.pf(rb + RR_LN_B), static_cast<const float*>(c.sv(r.stats)),
+    QV_TRY(rowln_bwd(st, dt, c.sv(r.r2), QV_F32, dRs[i], P.Rt, d, c.pf(rb + RR_LN_W), c.pf(rb + RR_LN_B), static_cast<const float*>(c.sv(r.stats)),
                      0, c.pf(rb + RR_BETA), c.gf(rb + RR_BETA), t1, c.gf(rb + RR_LN_W), c.gf(rb + RR_LN_B)));
     const void* last = c.sv(r.blk[cfg->rrcv_blocks - 1].out);
-    QV_TRY(lin_bwd(c, last, rc, t1, P.R, r.re, c.pf(rb + RR_RE_W), c.gf(rb + RR_RE_W), c.gf(rb + RR_RE_B), t2, nullptr));
+    QV_TRY(lin_bwd(c, last, rc, t1, P.Rt, r.re, c.pf(rb + RR_RE_W), c.gf(rb + RR_RE_W), c.gf(rb + RR_RE_B), t2, nullptr));
     for (int j = cfg->rrcv_blocks - 1; j >= 0; --j) {
       const void* in = j == 0 ? c.sv(r.r0) : c.sv(r.blk[j - 1].out);
-      QV_TRY(cnx_bwd(c, r.blk[j], rr_blk(*cfg, i, j), P.H, in, t2, t2, wide, t1));
+      QV_TRY(cnx_bwd(c, r.blk[j], rr_blk(*cfg, i, j), P.Ht, in, t2, t2, wide, t1));
     }
     // dA = dR + dr0 W_rev
-    QV_TRY(lin_bwd(c, c.sv(q.A), d, t2, P.R, r.rev, c.pf(rb + RR_REV_W), c.gf(rb + RR_REV_W), c.gf(rb + RR_REV_B), dA, dRs[i], true));
+    QV_TRY(lin_bwd(c, c.sv(q.A), d, t2, P.Rt, r.rev, c.pf(rb + RR_REV_W), c.gf(rb + RR_REV_W), c.gf(rb + RR_REV_B), dA, dRs[i], true));
     // A = gelu(LN(p))
-    QV_TRY(rowln_bwd(st, dt, c.sv(q.p), dt, dA, P.R, d, c.pf(pb + LM_LN_W), c.pf(pb + LM_LN_B), static_cast<const float*>(c.sv(q.stats)), 1,
+    QV_TRY(rowln_bwd(st, dt, c.sv(q.p), dt, dA, P.Rt, d, c.pf(pb + LM_LN_W), c.pf(pb + LM_LN_B), static_cast<const float*>(c.sv(q.stats)), 1,
                      nullptr, nullptr, t1, c.gf(pb + LM_LN_W), c.gf(pb + LM_LN_B)));
-    QV_TRY(lin_bwd(c, c.sv(q.cat), 3 * C, t1, P.R, q.w, c.pf(pb + LM_PROJ_W), c.gf(pb + LM_PROJ_W), c.gf(pb + LM_PROJ_B), wide, nullptr));
+    const void* dproj = t1;
+    if (P.resize) {   // t2 is free again: gradient of the map-resolution projection
+      QV_TRY(resize_bilinear_bwd(st, dt, t1, P.B, P.H, P.H, P.Ht, P.Ht, d, t2));
+      dproj = t2;
+    }
+    QV_TRY(lin_bwd(c, c.sv(q.cat), 3 * C, dproj, P.R, q.w, c.pf(pb + LM_PROJ_W), c.gf(pb + LM_PROJ_W), c.gf(pb + LM_PROJ_B), wide, nullptr));
     // dcat = [d(dw3) | d(dw5) | d(identity)] -> df
     const uint8_t* g1 = static_cast<const uint8_t*>(wide);
     const uint8_t* g2 = g1 + (size_t)C * P.ts;

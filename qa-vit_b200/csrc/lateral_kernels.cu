@@ -897,3 +897,99 @@ int rng_snapshot_advance(cudaStream_t s, unsigned long long* rng, unsigned long 
   QV_LAUNCH_CHECK();
   return 0;
 }
+
+// =============================================================================== bilinear resize of a channels-last map
+// F.interpolate(x, size = (Ho, Wo), mode = 'bilinear', align_corners = False) of LMFAdapter (H:839-843): taken when a model built
+// for 32 x 32 images is fed larger ones (STL-10 recipe, 96 x 96: 24 x 24 maps -> 8 x 8; the source index is 3 i + 1 exactly, so the
+// resize degenerates to a strided pick there -- zero-weight taps are skipped).  Source index as in ATen's
+// area_pixel_compute_source_index: src = max(0, scale (dst + 0.5) - 0.5), scale = in / out.
+namespace {
+struct Tap { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Tap make_tap(int o, int in, int out) {
+  const float scale = (float)in / (float)out;
+  float src = scale * ((float)o + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  Tap t;
+  t.i0 = min((int)src, in - 1);
+  t.i1 = min(t.i0 + 1, in - 1);
+  t.w1 = src - (float)t.i0;
+  t.w0 = 1.f - t.w1;
+  return t;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) resize_bilinear_fwd_kernel(const T* __restrict__ in, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                                                  T* __restrict__ out) {
+  const int c2n = C / 2;
+  const long total = (long)B * Ho * Wo * c2n;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c2n) * 2;
+    long r = idx / c2n;
+    const int ox = (int)(r % Wo); r /= Wo;
+    const int oy = (int)(r % Ho);
+    const long b = r / Ho;
+    const Tap ty = make_tap(oy, Hi, Ho), tx = make_tap(ox, Wi, Wo);
+    const T* base = in + b * (long)Hi * Wi * C + c;
+    const float2 a = ld2(base + ((long)ty.i0 * Wi + tx.i0) * C), bb = ld2(base + ((long)ty.i0 * Wi + tx.i1) * C);
+    const float2 cc = ld2(base + ((long)ty.i1 * Wi + tx.i0) * C), dd = ld2(base + ((long)ty.i1 * Wi + tx.i1) * C);
+    float2 v;
+    v.x = ty.w0 * (tx.w0 * a.x + tx.w1 * bb.x) + ty.w1 * (tx.w0 * cc.x + tx.w1 * dd.x);
+    v.y = ty.w0 * (tx.w0 * a.y + tx.w1 * bb.y) + ty.w1 * (tx.w0 * cc.y + tx.w1 * dd.y);
+    st2(out + idx * 2, v);
+  }
+}
+// din (pre-zeroed) += taps * dout.  A thread owns two channels of one image and walks the output pixels sequentially: several
+// output pixels can hit the same source pixel, this order has no write races and is deterministic.
+template <typename T>
+__global__ void __launch_bounds__(256) resize_bilinear_bwd_kernel(const T* __restrict__ dout, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                                                  T* __restrict__ din) {
+  const int c2n = C / 2;
+  const long total = (long)B * c2n;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % c2n) * 2;
+    const long b = idx / c2n;
+    T* base = din + b * (long)Hi * Wi * C + c;
+    for (int oy = 0; oy < Ho; ++oy) {
+      const Tap ty = make_tap(oy, Hi, Ho);
+      for (int ox = 0; ox < Wo; ++ox) {
+        const Tap tx = make_tap(ox, Wi, Wo);
+        const float2 g = ld2(dout + ((b * Ho + oy) * (long)Wo + ox) * C + c);
+        const int ys[2] = {ty.i0, ty.i1}, xs[2] = {tx.i0, tx.i1};
+        const float wy[2] = {ty.w0, ty.w1}, wx[2] = {tx.w0, tx.w1};
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float w = wy[i] * wx[j];
+            if (w == 0.f) continue;
+            T* p = base + ((long)ys[i] * Wi + xs[j]) * C;
+            float2 o = ld2(p);
+            o.x += w * g.x; o.y += w * g.y;
+            st2(p, o);
+          }
+      }
+    }
+  }
+}
+}  // namespace
+
+int resize_bilinear_fwd(cudaStream_t s, int dt, const void* in, int B, int Hi, int Wi, int Ho, int Wo, int C, void* out) {
+  QV_CHECK(C % 2 == 0, "resize: channel count must be even");
+  const long total = (long)B * Ho * Wo * (C / 2);
+  if (total <= 0) return 0;
+  const int grid = (int)min((long)qv_num_sms() * 16, (total + 255) / 256);
+  DT_SWITCH(dt, (resize_bilinear_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)in, B, Hi, Wi, Ho, Wo, C, (float*)out)),
+            (resize_bilinear_fwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, B, Hi, Wi, Ho, Wo, C, (bf16*)out)));
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+int resize_bilinear_bwd(cudaStream_t s, int dt, const void* dout, int B, int Hi, int Wi, int Ho, int Wo, int C, void* din) {
+  QV_CHECK(C % 2 == 0, "resize: channel count must be even");
+  const long total = (long)B * (C / 2);
+  if (total <= 0) return 0;
+  QV_CUDA(cudaMemsetAsync(din, 0, (size_t)B * Hi * Wi * C * (dt == QV_BF16 ? 2 : 4), s));
+  const int grid = (int)min((long)qv_num_sms() * 16, (total + 255) / 256);
+  DT_SWITCH(dt, (resize_bilinear_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dout, B, Hi, Wi, Ho, Wo, C, (float*)din)),
+            (resize_bilinear_bwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)dout, B, Hi, Wi, Ho, Wo, C, (bf16*)din)));
+  QV_LAUNCH_CHECK();
+  return 0;
+}

@@ -113,7 +113,8 @@ class QuadBlockFn(torch.autograd.Function):
             if t.dtype != torch.float32 or not t.is_contiguous():
                 raise RuntimeError("qavit_b200: parameters must be contiguous fp32 tensors")
             params[qi] = t.data_ptr()
-        out = torch.empty_like(x)
+        n_out = cfg.tokens_out if (cfg.token_learner and cfg.tokens_out > 0) else x.shape[1]
+        out = torch.empty(x.shape[0], n_out, x.shape[2], dtype=torch.float32, device=x.device)
         rng = rng_state(x.device) if (cfg.train and (cfg.dropout > 0 or cfg.drop_path > 0)) else None
         check(lib.qavit_block_forward(C.byref(cfg), params, _ptr(meta.update_count), _ptr(rng), x.data_ptr(), out.data_ptr(),
                                       saved.data_ptr(), scratch.data_ptr(), _stream()))

@@ -272,6 +272,9 @@ def _block_apply(block: QuadAttentionBlock, wrapper: Optional[QuadBlockWithToken
     c.batch, c.tokens_full = B, N
     c.token_learner = 1 if wrapper is not None else 0
     c.tokens = wrapper.token_learner.num_out_tokens if wrapper is not None else N
+    # TokenUpMix's Linear fixes the number of tokens it emits at construction (H:1099-1103); it differs from N when a model built
+    # for 32 x 32 is fed larger images after adjust_positional_embedding (STL-10 recipe: the first block maps 576 -> 16 -> 64)
+    c.tokens_out = wrapper.token_upmix.upsample_attn.out_features if wrapper is not None else 0
     c.dim, c.heads, c.bank_size, c.groups = d, cfg.num_heads, cfg.global_bank_size, cfg.num_channel_groups
     c.window, c.linformer_k, c.msda_seq_len = cfg.window_size, cfg.linformer_k, block.msda.linformer.seq_len
     dil = tuple(cfg.dilation_factors)

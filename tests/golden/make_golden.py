@@ -39,6 +39,11 @@ CASES = {
     "qavitv2b_224": ("QAViTv2", "QAViT", "QAViTConfig", {},
                      dict(family="qavit_v2", img_size=224, patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64,
                           dwconv_bias=True), 2),
+    # STL-10 fine-tuning recipe (HQAViT_Tiny_stl10.py:250-282, 405-412): the 32 x 32 CIFAR-100 model fed 96 x 96 images after
+    # adjust_positional_embedding(model, 96) and a 10-class head: block 0's TokenLearner sees 576 tokens, TokenUpMix still emits 64,
+    # the lateral path runs on 24 x 24 maps and LMFAdapter resizes them bilinearly to 8 x 8 (H:839-843)
+    "hqavit_stl96": ("HQAViT_CIFAR100", "HQAViT", "HQAViTConfig", {},
+                     dict(family="hqavit", img_size=96, built_img_size=32, num_classes=10), 2),
     "hqavit_tinyin": ("HQAViT_IN_Tiny", "HQAViT", "HQAViTConfig", {},
                       dict(family="hqavit", img_size=64, num_classes=200, depth=12, num_learned_tokens=64,
                            stage_depths=(2, 2, 6, 2)), 2),
@@ -67,6 +72,10 @@ def build_reference(case):
         if hasattr(model, n):
             getattr(model, n).cat_mlp[3].p = 0.0
     ocfg = O.OracleConfig(**okw)
+    if ocfg.built_img_size and ocfg.built_img_size != ocfg.img_size:      # the reference's own transfer recipe
+        stl = import_reference("HQAViT_Tiny_stl10")
+        stl.adjust_positional_embedding(model, ocfg.img_size)
+        model.head = torch.nn.Linear(model.head.in_features, ocfg.num_classes)
     return model, ocfg, B
 
 

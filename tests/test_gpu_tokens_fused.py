@@ -56,9 +56,12 @@ def test_token_learner_fused_forward_and_backward(B, N):
     _call(1, B, N, Cc, [x, S, dxc, lw, lb, W], [dx, dW, db, dlw, dlb])
     assert rel_l2(dx, gx) < TOL, rel_l2(dx, gx)
     assert rel_l2(dW, gW) < TOL, rel_l2(dW, gW)
-    assert rel_l2(dlw, glw) < TOL and rel_l2(dlb, glb) < TOL, (rel_l2(dlw, glw), rel_l2(dlb, glb))
-    # d bias of the gate is exactly zero (a per-slot constant under a softmax over tokens): bounded absolutely
-    assert db.abs().max().item() < 1e-3 * gW.abs().max().item() * Cc ** 0.5 and gb.abs().max().item() < 1e-9
+    assert rel_l2(dlw, glw) < TOL, rel_l2(dlw, glw)
+    # the gate bias AND the LayerNorm bias only add a per-slot constant to the logits, which the softmax over tokens removes: both
+    # gradients are exactly zero in exact arithmetic (fp64: ~1e-15) and are bounded absolutely here
+    assert gb.abs().max().item() < 1e-9 and glb.abs().max().item() < 1e-9
+    assert db.abs().max().item() < 1e-4 * gW.abs().max().item() * Cc ** 0.5
+    assert dlb.abs().max().item() < 1e-4 * glw.abs().max().item()
 
 
 @pytest.mark.parametrize("B,N", [(5, 64), (300, 64), (3, 16), (7, 32)])
@@ -88,3 +91,52 @@ def test_token_upmix_fused_forward_and_backward(B, N):
     assert rel_l2(dW, gW) < TOL, rel_l2(dW, gW)
     assert rel_l2(dlw, glw) < TOL and rel_l2(dlb, glb) < TOL, (rel_l2(dlw, glw), rel_l2(dlb, glb))
     assert gb.abs().max().item() < 1e-9 * max(1.0, gW.abs().max().item())      # exactly zero in exact arithmetic: we add nothing
+
+
+@pytest.mark.parametrize("R", [64, 1000, 20000])
+def test_branch_norm_compress_fused_forward_and_backward(R):
+    """cmp_fused.cu: fused[:, 48 i : 48 i + 48] = alpha_i (LN_i(x_i) W_i^T + b_i) for the four branches (H:1074-1079) and its
+    backward, against torch autograd in fp64 on the same bf16 inputs.  Outputs are bf16: tolerance = bf16 rounding of the result."""
+    from qavit_b200 import _lib as L
+    Cc, Cd = 192, 48
+    g = torch.Generator().manual_seed(R)
+    xs = [(torch.randn(R, Cc, generator=g) * (1 + 0.5 * i) + 0.3).bfloat16().cuda() for i in range(4)]
+    gam = [(1 + 0.2 * torch.randn(Cc, generator=g)).cuda() for _ in range(4)]
+    bet = [(0.1 * torch.randn(Cc, generator=g)).cuda() for _ in range(4)]
+    Ws = [(torch.randn(Cd, Cc, generator=g) * 0.1).cuda() for _ in range(4)]
+    bs = [(0.1 * torch.randn(Cd, generator=g)).cuda() for _ in range(4)]
+    alpha = torch.softmax(torch.randn(4, generator=g), 0).cuda()
+    dfused = torch.randn(R, Cc, generator=g).bfloat16().cuda()
+    fused = torch.empty(R, Cc, dtype=torch.bfloat16, device="cuda")
+    stats = [torch.empty(R, 2, device="cuda") for _ in range(4)]
+    ins = xs + gam + bet + Ws + bs + [alpha]
+    a = (C.c_void_p * len(ins))(*[t.data_ptr() for t in ins])
+    o = (C.c_void_p * 5)(*[t.data_ptr() for t in [fused] + stats])
+    L.check(L.lib.qavit_test_cmp_fused(0, R, a, o, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    leaves = {k: [t.double().requires_grad_(True) for t in v] for k, v in dict(x=xs, g=gam, b=bet, W=Ws, c=bs).items()}
+    ref = torch.cat([alpha[i].double() * (torch.nn.functional.layer_norm(leaves["x"][i], (Cc,), leaves["g"][i], leaves["b"][i], 1e-5)
+                                         @ leaves["W"][i].t() + leaves["c"][i]) for i in range(4)], dim=1)
+    assert rel_l2(fused.float(), ref) < 4e-3, rel_l2(fused.float(), ref)
+    for i in range(4):
+        assert rel_l2(stats[i][:, 0], xs[i].double().mean(-1), floor=1e-3) < 1e-5
+        assert rel_l2(stats[i][:, 1], (xs[i].double().var(-1, unbiased=False) + 1e-5).rsqrt()) < 1e-5
+    flat = leaves["x"] + leaves["g"] + leaves["b"] + leaves["W"] + leaves["c"]
+    grads = torch.autograd.grad((ref * dfused.double()).sum(), flat)
+    gx, gg, gb, gW, gc = (grads[4 * k:4 * k + 4] for k in range(5))
+    dx = [torch.empty(R, Cc, dtype=torch.bfloat16, device="cuda") for _ in range(4)]
+    dW = [torch.zeros(Cd, Cc, device="cuda") for _ in range(4)]
+    db = [torch.zeros(Cd, device="cuda") for _ in range(4)]
+    dg = [torch.zeros(Cc, device="cuda") for _ in range(4)]
+    dbe = [torch.zeros(Cc, device="cuda") for _ in range(4)]
+    ins = xs + stats + gam + bet + Ws + [alpha, dfused]
+    a = (C.c_void_p * len(ins))(*[t.data_ptr() for t in ins])
+    outs = dx + dW + db + dg + dbe
+    o = (C.c_void_p * len(outs))(*[t.data_ptr() for t in outs])
+    L.check(L.lib.qavit_test_cmp_fused(1, R, a, o, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert rel_l2(dx[i].float(), gx[i]) < 6e-3, (i, rel_l2(dx[i].float(), gx[i]))         # bf16 output, bf16 alpha W
+        assert rel_l2(dW[i], gW[i]) < 4e-3, (i, rel_l2(dW[i], gW[i]))
+        assert rel_l2(db[i], gc[i]) < 1e-3, (i, rel_l2(db[i], gc[i]))
+        assert rel_l2(dg[i], gg[i]) < 4e-3 and rel_l2(dbe[i], gb[i]) < 4e-3, (i, rel_l2(dg[i], gg[i]), rel_l2(dbe[i], gb[i]))

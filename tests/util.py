@@ -30,6 +30,7 @@ CASES = {
                           dwconv_bias=True), "qavit", dict(variant="v1"), 2),
     "qavitv2b_224": (dict(family="qavit_v2", img_size=224, patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64,
                           dwconv_bias=True), "qavit", dict(variant="v2b"), 2),
+    "hqavit_stl96": (dict(family="hqavit", img_size=96, built_img_size=32, num_classes=10), "hqavit", {}, 2),
     "hqavit_tinyin": (dict(family="hqavit", img_size=64, num_classes=200, depth=12, num_learned_tokens=64,
                            stage_depths=(2, 2, 6, 2)), "hqavit", dict(square_tokens=True), 2),
 }
@@ -40,7 +41,7 @@ def build_model(case, device="cuda", precision="fp32"):
     import qavit_b200 as Q
     okw, fam, ckw, B = CASES[case]
     ocfg = O.OracleConfig(**okw)
-    common = dict(img_size=ocfg.img_size, patch_size=ocfg.patch_size, num_classes=ocfg.num_classes, depth=ocfg.depth,
+    common = dict(img_size=ocfg.built_img_size or ocfg.img_size, patch_size=ocfg.patch_size, num_classes=ocfg.num_classes, depth=ocfg.depth,
                   dropout=0.0, drop_path=0.0, window_size=ocfg.window_size, dilation_factors=tuple(ocfg.dilation_factors),
                   linformer_k=ocfg.linformer_k)
     if fam == "hqavit":
@@ -52,6 +53,8 @@ def build_model(case, device="cuda", precision="fp32"):
         cfg = Q.QAViTConfig(**common)
         model = Q.QAViT(cfg, **ckw)
     sd = O.synthetic_state(ocfg)
+    if ocfg.built_img_size and ocfg.built_img_size != ocfg.img_size:      # the STL-10 transfer recipe through OUR helpers
+        Q.adjust_positional_embedding(model, ocfg.img_size)
     model.load_state_dict(O.with_bank_aliases(sd, ocfg), strict=True)
     model = model.to(device)
     model.set_precision(precision)
