@@ -43,6 +43,11 @@ WORKLOADS = {
                          label="QAViTv2 CIFAR-100 32x32 (= QAViTV2_EXTREME model)"),
     "qavit_224": dict(family="qavit", img=224, classes=100, kw=dict(patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64),
                       ctor=dict(variant="v2b"), fwd_mflop=2421.0 + 57.8, label="QAViTv2.py defaults 224x224 / patch 16 (196 tokens)"),
+    # BASELINE config 4b: the CIFAR-100 model fed 96 x 96 images after adjust_positional_embedding + a 10-class head (STL-10 recipe,
+    # HQAViT_Tiny_stl10.py:250-282, 405-412).  F_min: lateral path at 24 x 24 maps (9 x stem / LMFA, RRCV + SplitFusion unchanged) ~ 1271,
+    # patch embed 10.6, blocks 185.4 + block 0's 576-token TokenLearner ~ 6
+    "hqavit_stl96": dict(family="hqavit", img=96, built_img=32, classes=10, kw={}, ctor={}, fwd_mflop=1271.0 + 10.6 + 191.4,
+                         label="HQAViT CIFAR-100 model at STL-10 96x96 (resized pos_embed)"),
     "hqavit_tinyin": dict(family="hqavit", img=64, classes=200, kw=dict(depth=12, num_learned_tokens=64),
                           ctor=dict(stage_depths=(2, 2, 6, 2), square_tokens=True), fwd_mflop=1296.6 + 803.0,
                           label="HQAViT TinyImageNet 64x64"),
@@ -51,9 +56,11 @@ WORKLOADS = {
 
 def build_workload(Q, name, dropout=0.0, drop_path=0.0):
     w = WORKLOADS[name]
-    common = dict(img_size=w["img"], num_classes=w["classes"], dropout=dropout, drop_path=drop_path, **w["kw"])
+    common = dict(img_size=w.get("built_img", w["img"]), num_classes=w["classes"], dropout=dropout, drop_path=drop_path, **w["kw"])
     if w["family"] == "hqavit":
         model = Q.HQAViT(Q.HQAViTConfig(**common), **w["ctor"])
+        if w.get("built_img", w["img"]) != w["img"]:
+            Q.adjust_positional_embedding(model, w["img"])
         if dropout == 0.0:    # the parity configuration also silences SplitFusion's hard-coded Dropout(0.1) (H:930)
             for n in ("fuse2", "fuse3", "fuse4"):
                 getattr(model, n).cat_mlp[3].p = 0.0

@@ -114,7 +114,7 @@ enum { W_SWA_QKV, W_SWA_PROJ, W_MSDA_Q, W_MSDA_KV, W_MSDA_PROJ, W_CGA_PROJ, W_CR
        W_C3, W_B1, W_B2, W_F1, W_F2, W_TL, W_WRITE, W_COUNT };
 
 struct Saved {  // byte offsets into `saved`
-  size_t tl_stats, tl_ln, tl_S, xc, n1_stats, xn, alpha, snap[4], qkv_swa, attn_swa, xp, kv_msda, q_msda, attn_msda,
+  size_t tl_stats, tl_ln, tl_S, tl_Z, xc, n1_stats, xn, alpha, snap[4], qkv_swa, attn_swa, xp, kv_msda, q_msda, attn_msda,
       attn_cga, kbp, vbp, q_cross, Kc, Vc, attn_cross, branch[4], nb_stats[4], nb[4], fused, h1_pre, h1, x1, n2_stats, y,
       h_pre, h, dn_stats, hn, cs, pd_stats, hn2, o, out_blk, up, up_stats, wb[W_COUNT], wbt[W_COUNT], wstack, bstack, rng, rs, total;
 };
@@ -187,6 +187,7 @@ void layout_saved(const Dims& D, Saved* S) {
   S->tl_stats = b.take(D.tl && !D.ftok ? Rf * 8 : 0);
   S->tl_ln = b.take(D.tl && !D.ftok ? Rf * d * D.tts : 0);
   S->tl_S = b.take(D.tl ? Rf * D.Nt * 4 : 0);
+  S->tl_Z = b.take(D.ftok ? Rf * D.Nt * 4 : 0);
   S->xc = b.take(D.tl ? R * d * 4 : 0);
   S->n1_stats = b.take(R * 8);
   S->xn = b.take(R * d * ts);
@@ -496,7 +497,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   const float* x = x_in;
   if (D.ftok) {   // LayerNorm + gate + softmax over tokens + pooling in one split-precision kernel; the logits never leave the SM
     QV_TRY(tlf_fwd(st, x_in, D.B, D.Nf, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), c.pf(QP_TL_FC_W), c.pf(QP_TL_FC_B), 1e-5f, c.svf(S.tl_S),
-                   c.svf(S.xc)));
+                   c.svf(S.tl_Z), c.svf(S.xc)));
     x = c.svf(S.xc);
   } else if (D.tl) {
     const int tdt = D.tdt;
@@ -896,7 +897,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
 
   // ---- TokenLearner backward
   if (D.ftok) {
-    QV_TRY(tlf_bwd(st, x_in, c.svf(S.tl_S), dxc, D.B, D.Nf, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), c.pf(QP_TL_FC_W), 1e-5f, dx,
+    QV_TRY(tlf_bwd(st, x_in, c.svf(S.tl_S), c.svf(S.tl_Z), dxc, D.B, D.Nf, c.pf(QP_TL_LN_W), c.pf(QP_TL_LN_B), c.pf(QP_TL_FC_W), 1e-5f, dx,
                    G(QP_TL_FC_W), G(QP_TL_FC_B), G(QP_TL_LN_W), G(QP_TL_LN_B)));
   } else if (D.tl) {
     const int tdt = D.tdt;
@@ -998,8 +999,8 @@ extern "C" int qavit_test_gemm_tn(int use_tc, const void* dY, int ldy, const voi
 }
 // The fused TokenLearner / TokenUpMix kernels of bf16 runs (16 learned tokens, <= 64 stream tokens, 192 channels) on their own:
 // op 0 = TokenLearner forward, 1 = TokenLearner backward, 2 = TokenUpMix (+ LayerNorm) forward, 3 = its backward.  All fp32, device:
-//   0: in  {x, ln_w, ln_b, W[16, C], b[16]}            out {S[B, N, 16], xc[B, 16, C]}
-//   1: in  {x, S, dxc, ln_w, ln_b, W}                   out {dx[B, N, C], dW, db, dln_w, dln_b}   (parameter gradients accumulated)
+//   0: in  {x, ln_w, ln_b, W[16, C], b[16]}            out {S[B, N, 16], xc[B, 16, C], Z[B, N, 16]}
+//   1: in  {x, S, dxc, ln_w, ln_b, W, Z}                out {dx[B, N, C], dW, db, dln_w, dln_b}   (parameter gradients accumulated)
 //   2: in  {xc, W[N, 16], b[N], ln_w, ln_b}             out {out[B, N, C], stats[B N, 2]}
 //   3: in  {xc, dout, stats, W, b, ln_w}                out {dxc[B, 16, C], dW, dln_w, dln_b}     (parameter gradients accumulated)
 extern "C" int qavit_test_tokens_fused(int op, int B, int N, int C, const float* const* in, float* const* out, void* stream) {
@@ -1007,8 +1008,8 @@ extern "C" int qavit_test_tokens_fused(int op, int B, int N, int C, const float*
   QV_CHECK(in && out, "tokens_fused: null argument");
   QV_CHECK(tokens_fused_ok(16, N, C), "tokens_fused: N=%d C=%d not covered (N multiple of 16 <= 64, C = 192)", N, C);
   switch (op) {
-    case 0: return tlf_fwd(s, in[0], B, N, in[1], in[2], in[3], in[4], 1e-5f, out[0], out[1]);
-    case 1: return tlf_bwd(s, in[0], in[1], in[2], B, N, in[3], in[4], in[5], 1e-5f, out[0], out[1], out[2], out[3], out[4]);
+    case 0: return tlf_fwd(s, in[0], B, N, in[1], in[2], in[3], in[4], 1e-5f, out[0], out[2], out[1]);
+    case 1: return tlf_bwd(s, in[0], in[1], in[6], in[2], B, N, in[3], in[4], in[5], 1e-5f, out[0], out[1], out[2], out[3], out[4]);
     case 2: return upf_fwd(s, in[0], B, N, in[1], in[2], in[3], in[4], 1e-5f, out[0], out[1]);
     case 3: return upf_bwd(s, in[0], in[1], in[2], B, N, in[3], in[4], in[5], out[0], out[1], out[2], out[3]);
   }

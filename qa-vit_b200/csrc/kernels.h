@@ -252,10 +252,11 @@ int upm64_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, i
 // fused wrapper kernels for 16 learned / <= 64 stream tokens / 192 channels (tokens_fused.cu): LayerNorm + gate + softmax + pooling,
 // up-mix + LayerNorm, and their backwards, one launch each, split-precision (bf16 hi + lo) MMAs, fp32 everywhere else
 bool tokens_fused_ok(int M, int N, int C);
+// (Z: the LayerNorm-normalised gate projection without its constant term, [B, N, 16] fp32, written by forward for backward)
 int tlf_fwd(cudaStream_t s, const float* x, int B, int N, const float* gamma, const float* beta, const float* W, const float* bias,
-            float eps, float* S, float* xc);
-int tlf_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, const float* gamma, const float* beta,
-            const float* W, float eps, float* dx, float* dW, float* dbias, float* dgamma, float* dbeta);
+            float eps, float* S, float* Z, float* xc);
+int tlf_bwd(cudaStream_t s, const float* x, const float* S, const float* Z, const float* dxc, int B, int N, const float* gamma,
+            const float* beta, const float* W, float eps, float* dx, float* dW, float* dbias, float* dgamma, float* dbeta);
 int upf_fwd(cudaStream_t s, const float* xc, int B, int N, const float* W, const float* bias, const float* gamma, const float* beta,
             float eps, float* out, float* stats);
 int upf_bwd(cudaStream_t s, const float* xc, const float* dout, const float* stats, int B, int N, const float* W, const float* bias,

@@ -205,7 +205,7 @@ constexpr size_t TLF_FWD_SMEM = 2 * al16(FMAXN * FXP * 2) + 2 * al16(FM * FXP * 
 __global__ void __launch_bounds__(FNT, 2) tlf_fwd_kernel(const float* __restrict__ x, int B, int N, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, const float* __restrict__ W,
                                                          const float* __restrict__ bias, float eps, float* __restrict__ Sout,
-                                                         float* __restrict__ xc) {
+                                                         float* __restrict__ Zout, float* __restrict__ xc) {
   extern __shared__ __align__(16) uint8_t smraw[];
   Carve cv(smraw);
   bf16* X = cv.take<bf16>(FMAXN * FXP); bf16* XL = cv.take<bf16>(FMAXN * FXP);
@@ -251,10 +251,15 @@ __global__ void __launch_bounds__(FNT, 2) tlf_fwd_kernel(const float* __restrict
         }
         const int n0 = mt * 16 + g, n1 = n0 + 8, m = nt * 8 + 2 * t;
         const float r0 = rstd_s[n0], u0 = mean_s[n0], r1 = rstd_s[n1], u1 = mean_s[n1];
-        F[n0 * FM + m] = fmaf(r0, acc[0] - u0 * c1[m], c0[m]);
-        F[n0 * FM + m + 1] = fmaf(r0, acc[1] - u0 * c1[m + 1], c0[m + 1]);
-        F[n1 * FM + m] = fmaf(r1, acc[2] - u1 * c1[m], c0[m]);
-        F[n1 * FM + m + 1] = fmaf(r1, acc[3] - u1 * c1[m + 1], c0[m + 1]);
+        // zc = LN-normalised projection without the constant c0: kept for backward, where sum_k g xhat = sum_m dlogits zc
+        const float z00 = r0 * (acc[0] - u0 * c1[m]), z01 = r0 * (acc[1] - u0 * c1[m + 1]);
+        const float z10 = r1 * (acc[2] - u1 * c1[m]), z11 = r1 * (acc[3] - u1 * c1[m + 1]);
+        *reinterpret_cast<float2*>(Zout + ((long)b * N + n0) * FM + m) = make_float2(z00, z01);
+        *reinterpret_cast<float2*>(Zout + ((long)b * N + n1) * FM + m) = make_float2(z10, z11);
+        F[n0 * FM + m] = z00 + c0[m];
+        F[n0 * FM + m + 1] = z01 + c0[m + 1];
+        F[n1 * FM + m] = z10 + c0[m];
+        F[n1 * FM + m + 1] = z11 + c0[m + 1];
       }
     }
     __syncthreads();
@@ -324,11 +329,11 @@ __global__ void __launch_bounds__(FNT, 2) tlf_fwd_kernel(const float* __restrict
 }
 
 // =============================================================================================== TokenLearner backward
-constexpr size_t TLF_BWD_SMEM = 2 * al16(FMAXN * FXP * 2) + 4 * al16(FM * FXP * 2) + 6 * al16(FMAXN * FSP * 2) + al16(FMAXN * FM * 4) +
-                                2 * al16(FMAXN * 4) + 3 * al16(FM * 4) + al16(2 * FMAXN * 2 * 4) + 2 * al16(FC * 4);
+constexpr size_t TLF_BWD_SMEM = 2 * al16(FMAXN * FXP * 2) + 4 * al16(FM * FXP * 2) + 6 * al16(FMAXN * FSP * 2) + 2 * al16(FMAXN * FM * 4) +
+                                2 * al16(FMAXN * 4) + 4 * al16(FM * 4) + al16(2 * FMAXN * 2 * 4) + 2 * al16(FC * 4);
 
 __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict__ x, const float* __restrict__ Sin,
-                                                         const float* __restrict__ dxc, int B, int N,
+                                                         const float* __restrict__ Zin, const float* __restrict__ dxc, int B, int N,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ W, float eps, float* __restrict__ dx,
                                                          float* __restrict__ dW, float* __restrict__ dbias,
@@ -342,6 +347,8 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
   bf16* G = cv.take<bf16>(FMAXN * FSP); bf16* GL = cv.take<bf16>(FMAXN * FSP);  // dlogits
   bf16* H = cv.take<bf16>(FMAXN * FSP); bf16* HL = cv.take<bf16>(FMAXN * FSP);  // dlogits * rstd
   float* F = cv.take<float>(FMAXN * FM);                                        // S fp32
+  float* Zs = cv.take<float>(FMAXN * FM);                                       // zc fp32 (forward's normalised projection)
+  float* c1s = cv.take<float>(FM);                                              // rowsum(gamma (.) W)
   float* mean_s = cv.take<float>(FMAXN); float* rstd_s = cv.take<float>(FMAXN);
   float* R = cv.take<float>(FM); float* Tacc = cv.take<float>(FM); float* Uacc = cv.take<float>(FM);
   float* RS = cv.take<float>(2 * FMAXN * 2);                                    // [half][row][2] partial row sums
@@ -355,6 +362,12 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
   }
   for (int k = tid; k < FC; k += FNT) { gam[k] = gamma[k]; bet[k] = beta[k]; }
   if (tid < FM) { Tacc[tid] = 0.f; Uacc[tid] = 0.f; }
+  for (int m = warp; m < FM; m += FNW) {
+    float a1 = 0.f;
+    for (int k = lane; k < FC; k += 32) a1 = fmaf(W[m * FC + k], gamma[k], a1);
+    a1 = warp_sum(a1);
+    if (lane == 0) c1s[m] = a1;
+  }
   float Pacc[3][4];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -363,11 +376,14 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
 
   XRegs xr;
   DRegs dr;
-  float4 sr = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 sr = make_float4(0.f, 0.f, 0.f, 0.f), zr = make_float4(0.f, 0.f, 0.f, 0.f);
   auto prefetch = [&](int b) {
     xload(xr, x + (long)b * N * FC, N, warp, lane);
     dload(dr, dxc + (long)b * FM * FC, tid);
-    if (tid * 4 < N * FM) sr = __ldg(reinterpret_cast<const float4*>(Sin + (long)b * N * FM) + tid);
+    if (tid * 4 < N * FM) {
+      sr = __ldg(reinterpret_cast<const float4*>(Sin + (long)b * N * FM) + tid);
+      zr = __ldg(reinterpret_cast<const float4*>(Zin + (long)b * N * FM) + tid);
+    }
   };
   if ((int)blockIdx.x < B) prefetch(blockIdx.x);
   const int mt = warp & 3, hf = warp >> 2;      // (token tile, slot half | channel half)
@@ -378,6 +394,7 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
     if (tid * 4 < N * FM) {
       const int n = tid >> 2, c = (tid & 3) * 4;
       *reinterpret_cast<float4*>(F + n * FM + c) = sr;
+      *reinterpret_cast<float4*>(Zs + n * FM + c) = zr;
       store_split4(S, SL, n * FSP + c, sr);
     }
     if (tid < FM) R[tid] = 0.f;
@@ -405,8 +422,11 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
     }
     __syncthreads();
     // ---- dlogits = S (dS - colsum); dl' = dlogits * rstd; T += colsum(dlogits); U += colsum(dl' * mean)
+    // The LayerNorm backward's two row sums follow algebraically from dlogits (no pass over the [N, C] gradient needed):
+    //   sum_k g = sum_m dlogits[n, m] c1[m],   sum_k g xhat = sum_m dlogits[n, m] zc[n, m]        (g = (dlogits W) gamma)
     if (act) {
       const float r0 = rstd_s[n0], r1 = rstd_s[n1], u0 = mean_s[n0], u1 = mean_s[n1];
+      float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const float cs = R[m0 + j];
@@ -415,8 +435,16 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
         store_split(G, GL, n1 * FSP + m0 + j, d1);
         store_split(H, HL, n0 * FSP + m0 + j, d0 * r0);
         store_split(H, HL, n1 * FSP + m0 + j, d1 * r1);
+        const float cc = c1s[m0 + j];
+        s1a = fmaf(d0, cc, s1a); s2a = fmaf(d0, Zs[n0 * FM + m0 + j], s2a);
+        s1b = fmaf(d1, cc, s1b); s2b = fmaf(d1, Zs[n1 * FM + m0 + j], s2b);
         const float tv = g_sum(d0 + d1), uv = g_sum(d0 * r0 * u0 + d1 * r1 * u1);
         if (g == 0) { atomicAdd(Tacc + m0 + j, tv); atomicAdd(Uacc + m0 + j, uv); }
+      }
+      s1a = quad_sum(s1a); s2a = quad_sum(s2a); s1b = quad_sum(s1b); s2b = quad_sum(s2b);
+      if (t == 0) {      // partial over this warp's 8 slots; the other slot half lands in RS[1 - hf]
+        *reinterpret_cast<float2*>(RS + (hf * FMAXN + n0) * 2) = make_float2(s1a, s2a);
+        *reinterpret_cast<float2*>(RS + (hf * FMAXN + n1) * 2) = make_float2(s1b, s2b);
       }
     }
     __syncthreads();
@@ -433,7 +461,7 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
         mma3(Pacc[i], a, al, bh[0], bh[1], bl[0], bl[1]);
       }
     }
-    // ---- d_ln = dlogits W (K = 16), row sums for the LayerNorm backward over this warp's 96 channels
+    // ---- d_ln = dlogits W (K = 16), dxA = S dxc
     uint32_t ag[4], agl[4], as[4], asl[4];
     float r0 = 0.f, r1 = 0.f, u0 = 0.f, u1 = 0.f;
     if (act) {
@@ -442,33 +470,7 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
       ldA(as, S, FSP, mt * 16, 0, lane);
       ldA(asl, SL, FSP, mt * 16, 0, lane);
       r0 = rstd_s[n0]; r1 = rstd_s[n1]; u0 = mean_s[n0]; u1 = mean_s[n1];
-      float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-#pragma unroll
-      for (int pr = 0; pr < 6; ++pr) {
-        const int c0 = hf * 96 + pr * 16;
-        uint32_t bw[4], bwl[4];
-        ldBt(bw, Wt, FXP, c0, 0, lane);
-        ldBt(bwl, WtL, FXP, c0, 0, lane);
-        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        mma3(acc[0], ag, agl, bw[0], bw[1], bwl[0], bwl[1]);
-        mma3(acc[1], ag, agl, bw[2], bw[3], bwl[2], bwl[3]);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = c0 + h * 8 + 2 * t;
-          const float2 xa = pair_val(X, XL, n0 * FXP + c), xb = pair_val(X, XL, n1 * FXP + c);
-          const float g0 = gam[c], g1 = gam[c + 1];
-          const float va0 = acc[h][0] * g0, va1 = acc[h][1] * g1, vb0 = acc[h][2] * g0, vb1 = acc[h][3] * g1;
-          s1a += va0 + va1; s2a += va0 * ((xa.x - u0) * r0) + va1 * ((xa.y - u0) * r0);
-          s1b += vb0 + vb1; s2b += vb0 * ((xb.x - u1) * r1) + vb1 * ((xb.y - u1) * r1);
-        }
-      }
-      s1a = quad_sum(s1a); s2a = quad_sum(s2a); s1b = quad_sum(s1b); s2b = quad_sum(s2b);
-      if (t == 0) {
-        *reinterpret_cast<float2*>(RS + (hf * FMAXN + n0) * 2) = make_float2(s1a, s2a);
-        *reinterpret_cast<float2*>(RS + (hf * FMAXN + n1) * 2) = make_float2(s1b, s2b);
-      }
     }
-    __syncthreads();
     // ---- dx = S dxc + rstd (g - mean(g) - xhat mean(g xhat))
     if (act) {
       const float2 pa0 = *reinterpret_cast<const float2*>(RS + n0 * 2), pa1 = *reinterpret_cast<const float2*>(RS + (FMAXN + n0) * 2);
@@ -835,18 +837,18 @@ int grid_for(int B, int per_sm) { return max(1, min(B, qv_num_sms() * per_sm)); 
 bool tokens_fused_ok(int M, int N, int C) { return M == FM && C == FC && N >= 16 && N <= FMAXN && N % 16 == 0; }
 
 int tlf_fwd(cudaStream_t s, const float* x, int B, int N, const float* gamma, const float* beta, const float* W, const float* bias,
-            float eps, float* S, float* xc) {
+            float eps, float* S, float* Z, float* xc) {
   if (B <= 0) return 0;
   QV_TRY(opt_in(tlf_fwd_kernel, TLF_FWD_SMEM));
-  tlf_fwd_kernel<<<grid_for(B, 2), FNT, TLF_FWD_SMEM, s>>>(x, B, N, gamma, beta, W, bias, eps, S, xc);
+  tlf_fwd_kernel<<<grid_for(B, 2), FNT, TLF_FWD_SMEM, s>>>(x, B, N, gamma, beta, W, bias, eps, S, Z, xc);
   QV_LAUNCH_CHECK();
   return 0;
 }
-int tlf_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, const float* gamma, const float* beta,
-            const float* W, float eps, float* dx, float* dW, float* dbias, float* dgamma, float* dbeta) {
+int tlf_bwd(cudaStream_t s, const float* x, const float* S, const float* Z, const float* dxc, int B, int N, const float* gamma,
+            const float* beta, const float* W, float eps, float* dx, float* dW, float* dbias, float* dgamma, float* dbeta) {
   if (B <= 0) return 0;
   QV_TRY(opt_in(tlf_bwd_kernel, TLF_BWD_SMEM));
-  tlf_bwd_kernel<<<grid_for(B, 2), FNT, TLF_BWD_SMEM, s>>>(x, S, dxc, B, N, gamma, beta, W, eps, dx, dW, dbias, dgamma, dbeta);
+  tlf_bwd_kernel<<<grid_for(B, 2), FNT, TLF_BWD_SMEM, s>>>(x, S, Z, dxc, B, N, gamma, beta, W, eps, dx, dW, dbias, dgamma, dbeta);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -108,9 +108,12 @@ def _worker(rank, world, port, family, ret):
         fwd_bwd(model2, opt2, red2, x, y, True)
         red2.finish()
         torch.cuda.synchronize()
-        out["overlap_equals_flat"] = bool(torch.allclose(opt2.flat_g * opt2.grad_prescale, mean_g, rtol=1e-6, atol=1e-9))
+        # a SECOND forward / backward: kernels that accumulate with fp32 atomics are not bitwise reproducible run to run, so this
+        # comparison is in norm (1e-5), unlike the same-run checks above (exact)
+        rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+        out["overlap_vs_flat_relerr"] = rel(opt2.flat_g * opt2.grad_prescale, mean_g)
         got2 = torch.cat([model2.global_bank.global_k.data.reshape(-1), model2.global_bank.global_v.data.reshape(-1)])
-        out["overlap_bank_mean"] = bool(torch.allclose(got2, mean_bank, rtol=1e-6, atol=1e-9))
+        out["overlap_bank_relerr"] = rel(got2, mean_bank)
 
         # ---- eval mode (no bank writes => images independent): 2 ranks x Bl == 1 rank x 2 Bl
         model3, opt3, red3 = fresh(False, False)
@@ -146,5 +149,5 @@ def test_two_rank_nccl_allreduce_matches_the_cross_rank_mean(family):
         assert o["sum_equals_world_x_mean"] and o["bank_mean"] and o["banks_differed_before"]
         assert o["update_count"][0] == o["update_count"][1] > 0
         assert o["clip_norm"] and o["clipped_grads"] and o["params_identical"]
-        assert o["overlap_equals_flat"] and o["overlap_bank_mean"]
+        assert o["overlap_vs_flat_relerr"] < 1e-5 and o["overlap_bank_relerr"] < 1e-5
         assert o["dp_equals_single_rank_global_batch_relerr"] < 1e-5      # eval mode: BatchNorm uses running statistics

@@ -45,7 +45,8 @@ def test_token_learner_fused_forward_and_backward(B, N):
     dxc = torch.randn(B, 16, Cc, generator=g).cuda()
     S = torch.empty(B, N, 16, device="cuda")
     xc = torch.empty(B, 16, Cc, device="cuda")
-    _call(0, B, N, Cc, [x, lw, lb, W, b], [S, xc])
+    Z = torch.empty(B, N, 16, device="cuda")
+    _call(0, B, N, Cc, [x, lw, lb, W, b], [S, xc, Z])
     leaves = [t.double().requires_grad_(True) for t in (x, lw, lb, W, b)]
     S_ref, xc_ref = _ref_token_learner(*leaves)
     assert rel_l2(S, S_ref) < TOL, rel_l2(S, S_ref)
@@ -53,7 +54,7 @@ def test_token_learner_fused_forward_and_backward(B, N):
     gx, glw, glb, gW, gb = torch.autograd.grad((xc_ref * dxc.double()).sum(), leaves)
     dx = torch.empty_like(x)
     dW, db, dlw, dlb = torch.zeros_like(W), torch.zeros_like(b), torch.zeros_like(lw), torch.zeros_like(lb)
-    _call(1, B, N, Cc, [x, S, dxc, lw, lb, W], [dx, dW, db, dlw, dlb])
+    _call(1, B, N, Cc, [x, S, dxc, lw, lb, W, Z], [dx, dW, db, dlw, dlb])
     assert rel_l2(dx, gx) < TOL, rel_l2(dx, gx)
     assert rel_l2(dW, gW) < TOL, rel_l2(dW, gW)
     assert rel_l2(dlw, glw) < TOL, rel_l2(dlw, glw)
@@ -138,5 +139,5 @@ def test_branch_norm_compress_fused_forward_and_backward(R):
     for i in range(4):
         assert rel_l2(dx[i].float(), gx[i]) < 6e-3, (i, rel_l2(dx[i].float(), gx[i]))         # bf16 output, bf16 alpha W
         assert rel_l2(dW[i], gW[i]) < 4e-3, (i, rel_l2(dW[i], gW[i]))
-        assert rel_l2(db[i], gc[i]) < 1e-3, (i, rel_l2(db[i], gc[i]))
+        assert rel_l2(db[i], gc[i]) < 4e-3, (i, rel_l2(db[i], gc[i]))      # column sums ride the MMA through a (1 / rstd) hi + lo column pair
         assert rel_l2(dg[i], gg[i]) < 4e-3 and rel_l2(dbe[i], gb[i]) < 4e-3, (i, rel_l2(dg[i], gg[i]), rel_l2(dbe[i], gb[i]))

@@ -1,9 +1,7 @@
 mkdir -p gpurun_out/r2
-python -m pytest tests/test_gpu_tokens_fused.py -q -s > gpurun_out/r2/t05_fused.log 2>&1; tail -12 gpurun_out/r2/t05_fused.log
-python -m pytest tests -q -m gpu -s > gpurun_out/r2/t05_all.log 2>&1; tail -6 gpurun_out/r2/t05_all.log
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/r2/bench05.log 2>&1; tail -c 900 gpurun_out/r2/bench05.log
-ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2/launches05.csv python tools/profile_step.py --batch 4736 --dropout 0.1 --drop-path 0.1 > gpurun_out/r2/prof05_ncu.log 2>&1
-python tools/launch_summary.py gpurun_out/r2/launches05.csv 70 > gpurun_out/r2/launches05.summary.txt; head -24 gpurun_out/r2/launches05.summary.txt
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'tlf_bwd|upf_bwd|cmpf_bwd|cga_mma_bwd|attn_mma_bwd' -c 7 -o gpurun_out/r2/ncu05_bwd python tools/profile_step.py --batch 4736 --dropout 0.1 --drop-path 0.1 > gpurun_out/r2/prof05_ncufull.log 2>&1
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'tlf_fwd|cmpf_fwd|upf_fwd' -c 3 -o gpurun_out/r2/ncu05_fwd python tools/profile_step.py --batch 4736 --dropout 0.1 --drop-path 0.1 >> gpurun_out/r2/prof05_ncufull.log 2>&1
-ls -la gpurun_out/r2/ | tail -5
+python -m pytest tests/test_gpu_dp.py tests/test_gpu_tokens_fused.py tests/test_gpu_live_reference.py -q -s > gpurun_out/r2/t06_dp.log 2>&1; tail -8 gpurun_out/r2/t06_dp.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2/bench06_n2.log 2>&1; tail -c 600 gpurun_out/r2/bench06_n2.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 --workload qavitv2_c100 --batch 256 > gpurun_out/r2/bench06_qavitv2_b256_n2.log 2>&1; tail -c 600 gpurun_out/r2/bench06_qavitv2_b256_n2.log
+python bench.py --gpus 1 --steps 20 --warmup 3 --workload qavitv2_c100 --batch 256 > gpurun_out/r2/bench06_qavitv2_b256_n1.log 2>&1; tail -c 400 gpurun_out/r2/bench06_qavitv2_b256_n1.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --no-graph > gpurun_out/r2/bench06_n2_nograph.log 2>&1; tail -c 400 gpurun_out/r2/bench06_n2_nograph.log
+timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python tools/profile_step.py --batch 8 --warmup 1 --dropout 0.1 --drop-path 0.1 > gpurun_out/r2/racecheck06.log 2>&1; tail -5 gpurun_out/r2/racecheck06.log
