@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqavit_b200.so")
+LIB_PATH = os.environ.get("QAVIT_LIB") or os.path.join(_HERE, "libqavit_b200.so")   # QAVIT_LIB: A/B builds of the same ABI (tools/)
 
 
 class BlockCfg(C.Structure):

@@ -114,6 +114,7 @@ __device__ __forceinline__ unsigned long long drop_id(const AttnP& p, long r, in
 
 template <typename T, int HD>
 __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnP p, Lay ly, int ntask) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   const int tid = threadIdx.x, HDP = ly.HDP;
   int* rows = reinterpret_cast<int*>(sm + ly.oRow);
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(AttnP p, Lay ly, int ntask
 
 template <typename T, int HD>
 __global__ void __launch_bounds__(NT) attn_bwd_kernel(AttnP p, Lay ly, int ntask) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int HDP = ly.HDP, NKV = ly.NKV, SP = ly.SP, D = p.H * HD;
@@ -342,10 +344,10 @@ int launch_attn(cudaStream_t s, const AttnP& p) {
   const int grid = min(ntask, qv_num_sms() * occ);
   if (BWD) {
     QV_TRY(set_smem(attn_bwd_kernel<T, 48>, smem));
-    attn_bwd_kernel<T, 48><<<grid, NT, smem, s>>>(p, ly, ntask);
+    qv_launch(attn_bwd_kernel<T, 48>, grid, NT, smem, s, p, ly, ntask);
   } else {
     QV_TRY(set_smem(attn_fwd_kernel<T, 48>, smem));
-    attn_fwd_kernel<T, 48><<<grid, NT, smem, s>>>(p, ly, ntask);
+    qv_launch(attn_fwd_kernel<T, 48>, grid, NT, smem, s, p, ly, ntask);
   }
   QV_LAUNCH_CHECK();
   return 0;

@@ -224,6 +224,7 @@ __device__ __forceinline__ void load_E(bf16* Es, const AttnP& p) {
 
 template <int NKV, bool LINF>
 __global__ void __launch_bounds__(WARPS * 32) attn_mma_fwd_kernel(AttnP p, int ntask) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* Es = reinterpret_cast<bf16*>(smraw);                       // [2][LP][PE]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,6 +330,7 @@ __device__ __forceinline__ void consume_dXf(const AttnP& p, float (*c)[6][4], bf
 
 template <int NKV, bool LINF>
 __global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int ntask) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int D = p.H * HD;
   bf16* Es = reinterpret_cast<bf16*>(smraw);
@@ -450,7 +452,7 @@ int launch(K kernel, cudaStream_t s, const AttnP& p, bool bwd) {
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int occ = max(1, min(4, (int)(220 * 1024 / (smem + 1024))));
   const int grid = min(cdiv(ntask, WARPS), qv_num_sms() * occ);
-  kernel<<<grid, WARPS * 32, smem, s>>>(p, ntask);
+  qv_launch(kernel, grid, WARPS * 32, smem, s, p, ntask);
   QV_LAUNCH_CHECK();
   return 0;
 }

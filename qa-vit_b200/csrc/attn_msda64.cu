@@ -59,6 +59,7 @@ __device__ __forceinline__ void stC(bf16* base, int pitch, int m0, int n0, const
 __global__ void __launch_bounds__(256) lin_pre_kernel(const bf16* __restrict__ kv, int ldkv, int kcol, int vcol, int NM, int L, int D,
                                                       const float* __restrict__ Ek, const float* __restrict__ Ev, int B,
                                                       bf16* __restrict__ pre) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) float sm[];
   float* sE = sm;                        // [2][L][32]
   float* sX = sE + 2 * L * KLIN;         // [L][2D]
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(256) lin_post_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ Ek, const float* __restrict__ Ev, int B,
                                                        const float* __restrict__ dpre, bf16* __restrict__ dkv, int lddkv, int dkcol,
                                                        int dvcol, float* __restrict__ dEk, float* __restrict__ dEv) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) float sm[];
   const int D2 = 2 * D;
   float* sE = sm;                        // [2][L][32]
@@ -196,6 +198,7 @@ __device__ __forceinline__ void lin_stage_X(bf16* sX, const bf16* kv, int ldkv, 
 __global__ void __launch_bounds__(WARPS * 32) lin_pre_mma_kernel(const bf16* __restrict__ kv, int ldkv, int kcol, int vcol, int NM, int L,
                                                                  const float* __restrict__ Ek, const float* __restrict__ Ev, int B,
                                                                  bf16* __restrict__ pre) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* sm = reinterpret_cast<bf16*>(smraw);
   bf16 *sE = sm + LinSmem::E, *sX = sm + LinSmem::X;
@@ -240,6 +243,7 @@ __global__ void __launch_bounds__(WARPS * 32) lin_post_mma_kernel(const bf16* __
                                                                   const float* __restrict__ Ek, const float* __restrict__ Ev, int B,
                                                                   const float* __restrict__ dpre, bf16* __restrict__ dkv, int lddkv,
                                                                   int dkcol, int dvcol, float* __restrict__ dEk, float* __restrict__ dEv) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* sm = reinterpret_cast<bf16*>(smraw);
   bf16 *sE = sm + LinSmem::E, *sX = sm + LinSmem::X, *sG = sm + LinSmem::G;
@@ -418,6 +422,7 @@ __device__ __forceinline__ void store16(bf16* dst, long ld, const float (*o)[4],
 }
 
 __global__ void __launch_bounds__(WARPS * 32) msda64_fwd_kernel(AttnP p, const bf16* __restrict__ pre, int ntask) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   bf16* W = reinterpret_cast<bf16*>(smraw) + warp * WS::END_FWD;
@@ -483,6 +488,7 @@ __device__ __forceinline__ void accumulate(float* acc, float (*dbank)[4], const 
 }
 
 __global__ void __launch_bounds__(WARPS * 32) msda64_bwd_kernel(AttnP p, const bf16* __restrict__ pre, float* __restrict__ dpre, int ntask) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int D = p.H * HD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -605,7 +611,7 @@ static int run_pre(cudaStream_t s, const AttnP& p, bf16* pre) {
   if (lin_mma_ok(p)) {
     const size_t smem = (size_t)LinSmem::END_PRE * sizeof(bf16);
     QV_CUDA(cudaFuncSetAttribute(lin_pre_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lin_pre_mma_kernel<<<max(1, min(p.B, qv_num_sms() * 4)), WARPS * 32, smem, s>>>((const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L,
+    qv_launch(lin_pre_mma_kernel, max(1, min(p.B, qv_num_sms() * 4)), WARPS * 32, smem, s, (const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L,
                                                                                  p.Ek, p.Ev, p.B, pre);
     QV_LAUNCH_CHECK();
     return 0;
@@ -614,7 +620,7 @@ static int run_pre(cudaStream_t s, const AttnP& p, bf16* pre) {
   QV_CHECK(smem <= 200 * 1024, "msda64: Linformer staging needs %zu B of shared memory", smem);
   QV_CUDA(cudaFuncSetAttribute(lin_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int occ = max(1, min(4, (int)(200 * 1024 / (smem + 1024))));
-  lin_pre_kernel<<<max(1, min(p.B, qv_num_sms() * occ)), 256, smem, s>>>((const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L, D, p.Ek, p.Ev,
+  qv_launch(lin_pre_kernel, max(1, min(p.B, qv_num_sms() * occ)), 256, smem, s, (const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L, D, p.Ek, p.Ev,
                                                                         p.B, pre);
   QV_LAUNCH_CHECK();
   return 0;
@@ -629,7 +635,7 @@ int attn_msda64_fwd(cudaStream_t s, const AttnP& p, void* scratch) {
   const size_t smem = (size_t)WARPS * WS::END_FWD * sizeof(bf16);
   QV_CUDA(cudaFuncSetAttribute(msda64_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int occ = max(1, min(4, (int)(200 * 1024 / (smem + 1024))));
-  msda64_fwd_kernel<<<min(cdiv(ntask, WARPS), qv_num_sms() * occ), WARPS * 32, smem, s>>>(p, pre, ntask);
+  qv_launch(msda64_fwd_kernel, min(cdiv(ntask, WARPS), qv_num_sms() * occ), WARPS * 32, smem, s, p, pre, ntask);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -645,12 +651,12 @@ int attn_msda64_bwd(cudaStream_t s, const AttnP& p, void* scratch) {
   const size_t smem = (size_t)WARPS * 2 * KLIN * HD * sizeof(float) + (size_t)WARPS * WS::END_BWD * sizeof(bf16);
   QV_CUDA(cudaFuncSetAttribute(msda64_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int occ = max(1, min(2, (int)(200 * 1024 / (smem + 1024))));
-  msda64_bwd_kernel<<<min(cdiv(ntask, WARPS), qv_num_sms() * occ), WARPS * 32, smem, s>>>(p, pre, dpre, ntask);
+  qv_launch(msda64_bwd_kernel, min(cdiv(ntask, WARPS), qv_num_sms() * occ), WARPS * 32, smem, s, p, pre, dpre, ntask);
   QV_LAUNCH_CHECK();
   if (lin_mma_ok(p)) {
     const size_t smem2 = (size_t)LinSmem::END_POST * sizeof(bf16);
     QV_CUDA(cudaFuncSetAttribute(lin_post_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    lin_post_mma_kernel<<<max(1, min(p.B, qv_num_sms() * 3)), WARPS * 32, smem2, s>>>(
+    qv_launch(lin_post_mma_kernel, max(1, min(p.B, qv_num_sms() * 3)), WARPS * 32, smem2, s, 
         (const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L, p.Ek, p.Ev, p.B, dpre, (bf16*)p.dkv, p.lddkv, p.dkcol, p.dvcol, p.dEk, p.dEv);
     QV_LAUNCH_CHECK();
     return 0;
@@ -659,7 +665,7 @@ int attn_msda64_bwd(cudaStream_t s, const AttnP& p, void* scratch) {
   QV_CHECK(smem2 <= 200 * 1024, "msda64: Linformer backward staging needs %zu B of shared memory", smem2);
   QV_CUDA(cudaFuncSetAttribute(lin_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   const int occ2 = max(1, min(2, (int)(200 * 1024 / (smem2 + 1024))));
-  lin_post_kernel<<<max(1, min(p.B, qv_num_sms() * occ2)), 256, smem2, s>>>((const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L, D, p.Ek, p.Ev,
+  qv_launch(lin_post_kernel, max(1, min(p.B, qv_num_sms() * occ2)), 256, smem2, s, (const bf16*)p.kv, p.ldkv, p.kcol, p.vcol, p.NM, p.L, D, p.Ek, p.Ev,
                                                                            p.B, dpre, (bf16*)p.dkv, p.lddkv, p.dkcol, p.dvcol, p.dEk, p.dEv);
   QV_LAUNCH_CHECK();
   return 0;

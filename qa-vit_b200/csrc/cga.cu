@@ -97,6 +97,7 @@ __device__ __forceinline__ unsigned long long cga_drop_id(const CgaP& p, long r,
 
 template <typename T>
 __global__ void __launch_bounds__(NT) cga_fwd_kernel(CgaP p, CgaLay ly) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   const int tid = threadIdx.x;
   constexpr int cpg = CPG, hdc = HDC;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(NT) cga_fwd_kernel(CgaP p, CgaLay ly) {
 
 template <typename T>
 __global__ void __launch_bounds__(NT) cga_bwd_kernel(CgaP p, CgaLay ly) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   const int tid = threadIdx.x, Nt = p.Nt, NKV = ly.NKV, SP = ly.SP;
   constexpr int cpg = CPG, cg = CG, hdc = HDC;
@@ -295,8 +297,8 @@ int cga_fwd(cudaStream_t s, int dt, const CgaP& p) {
   const size_t smem = (size_t)ly.total * sizeof(float);
   const int occ = max(1, (int)(200 * 1024 / (smem + 1024)));
   const int grid = min(p.B * p.G, qv_num_sms() * min(occ, 8));
-  if (dt == QV_F32) { QV_TRY(set_smem(cga_fwd_kernel<float>, smem)); cga_fwd_kernel<float><<<grid, NT, smem, s>>>(p, ly); }
-  else { QV_TRY(set_smem(cga_fwd_kernel<bf16>, smem)); cga_fwd_kernel<bf16><<<grid, NT, smem, s>>>(p, ly); }
+  if (dt == QV_F32) { QV_TRY(set_smem(cga_fwd_kernel<float>, smem)); qv_launch(cga_fwd_kernel<float>, grid, NT, smem, s, p, ly); }
+  else { QV_TRY(set_smem(cga_fwd_kernel<bf16>, smem)); qv_launch(cga_fwd_kernel<bf16>, grid, NT, smem, s, p, ly); }
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -310,8 +312,8 @@ int cga_bwd(cudaStream_t s, int dt, const CgaP& p) {
   const size_t smem = (size_t)ly.total * sizeof(float);
   const int occ = max(1, (int)(200 * 1024 / (smem + 1024)));
   const int grid = min(p.B * p.G, qv_num_sms() * min(occ, 8));
-  if (dt == QV_F32) { QV_TRY(set_smem(cga_bwd_kernel<float>, smem)); cga_bwd_kernel<float><<<grid, NT, smem, s>>>(p, ly); }
-  else { QV_TRY(set_smem(cga_bwd_kernel<bf16>, smem)); cga_bwd_kernel<bf16><<<grid, NT, smem, s>>>(p, ly); }
+  if (dt == QV_F32) { QV_TRY(set_smem(cga_bwd_kernel<float>, smem)); qv_launch(cga_bwd_kernel<float>, grid, NT, smem, s, p, ly); }
+  else { QV_TRY(set_smem(cga_bwd_kernel<bf16>, smem)); qv_launch(cga_bwd_kernel<bf16>, grid, NT, smem, s, p, ly); }
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -324,6 +326,7 @@ namespace {
 // One warp per output element group: lanes stride over K (coalesced reads of the W row), shuffle reduction.
 __global__ void __launch_bounds__(128) small_linear_fwd_kernel(const float* __restrict__ X, int rows, int K, const float* __restrict__ W,
                                                                const float* __restrict__ b, int N, float* __restrict__ Y) {
+  QV_PDL_ENTRY();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;                       // a warp owns output column n for every row: W[n, :] is read once
   const int n = warp;
@@ -347,6 +350,7 @@ __global__ void __launch_bounds__(128) small_linear_fwd_kernel(const float* __re
 // dW[n,k] += sum_r dY[r,n] X[r,k]; db[n] += sum_r dY[r,n]; dX[r,k] += sum_n dY[r,n] W[n,k]
 __global__ void small_linear_bwd_kernel(const float* X, int rows, int K, const float* W, int N, const float* dY,
                                         float* dW, float* db, float* dX) {
+  QV_PDL_ENTRY();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < N * K) {
     const int n = idx / K, k = idx % K;
@@ -369,7 +373,7 @@ __global__ void small_linear_bwd_kernel(const float* X, int rows, int K, const f
 }  // namespace
 
 int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
-  small_linear_fwd_kernel<<<cdiv(N * 32, 128), 128, 0, s>>>(X, rows, K, W, b, N, Y);
+  qv_launch(small_linear_fwd_kernel, cdiv(N * 32, 128), 128, 0, s, X, rows, K, W, b, N, Y);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -377,7 +381,7 @@ int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const floa
 int small_linear_bwd(cudaStream_t s, const float* X, int rows, int K, const float* W, int N, const float* dY, float* dW,
                      float* db, float* dX_accum) {
   const int n = max(N * K, rows * K);
-  small_linear_bwd_kernel<<<cdiv(n, 128), 128, 0, s>>>(X, rows, K, W, N, dY, dW, db, dX_accum);
+  qv_launch(small_linear_bwd_kernel, cdiv(n, 128), 128, 0, s, X, rows, K, W, N, dY, dW, db, dX_accum);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -180,6 +180,7 @@ __device__ __forceinline__ void keys_times(float (*o)[4], const float (*x)[4], c
 }
 
 __global__ void __launch_bounds__(WARPS * 32) cga_mma_fwd_kernel(CgaP p) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   float* bias = reinterpret_cast<float*>(smraw);                    // [48]
   bf16* Wst = reinterpret_cast<bf16*>(bias + 3 * CPG);              // [48][PW]
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(WARPS * 32) cga_mma_fwd_kernel(CgaP p) {
 }
 
 __global__ void __launch_bounds__(WARPS * 32) cga_mma_bwd_kernel(CgaP p) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   float* bias = reinterpret_cast<float*>(smraw);                    // [48]
   float* dkb = bias + 3 * CPG;                                      // [16][16] d(projected bank k), then v
@@ -428,7 +430,7 @@ int cga_mma_fwd(cudaStream_t s, const CgaP& p) {
   const size_t smem = 3 * CPG * 4 + (size_t)(3 * CPG * PW + 2 * KB * PK + WARPS * WS::END_FWD) * 2;
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(cga_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(cdiv(p.B, WARPS), qv_num_sms() * 4);
-  cga_mma_fwd_kernel<<<grid, WARPS * 32, smem, s>>>(p);
+  qv_launch(cga_mma_fwd_kernel, grid, WARPS * 32, smem, s, p);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -439,7 +441,7 @@ int cga_mma_bwd(cudaStream_t s, const CgaP& p) {
   const size_t smem = (3 * CPG + 2 * KB * CPG) * 4 + (size_t)(3 * CPG * PW + 2 * KB * PK + WARPS * WS::END_BWD) * 2;
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(cga_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(cdiv(p.B, WARPS), qv_num_sms() * 2);
-  cga_mma_bwd_kernel<<<grid, WARPS * 32, smem, s>>>(p);
+  qv_launch(cga_mma_bwd_kernel, grid, WARPS * 32, smem, s, p);
   QV_LAUNCH_CHECK();
   return 0;
 }

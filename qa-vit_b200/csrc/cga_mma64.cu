@@ -183,6 +183,7 @@ __device__ __forceinline__ void load_rows(bf16* dst, int pitch, const bf16* src,
 
 template <int T>
 __global__ void __launch_bounds__(WARPS * 32) cga64_fwd_kernel(CgaP p) {
+  QV_PDL_ENTRY();
   static_assert(T <= WARPS, "one query tile per warp");
   using L = Lay<T>;
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(WARPS * 32) cga64_fwd_kernel(CgaP p) {
 
 template <int T>
 __global__ void __launch_bounds__(WARPS * 32) cga64_bwd_kernel(CgaP p) {
+  QV_PDL_ENTRY();
   static_assert(T <= WARPS, "one query tile per warp");
   using L = Lay<T>;
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -471,7 +473,7 @@ int cga_mma64_fwd(cudaStream_t s, const CgaP& p) {
   QV_CUDA(cudaFuncSetAttribute(cga64_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int occ = max(1, min(6, (int)(200 * 1024 / (smem + 1024))));
   const int grid = min(p.B, qv_num_sms() * occ);
-  cga64_fwd_kernel<4><<<grid, WARPS * 32, smem, s>>>(p);
+  qv_launch(cga64_fwd_kernel<4>, grid, WARPS * 32, smem, s, p);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -483,7 +485,7 @@ int cga_mma64_bwd(cudaStream_t s, const CgaP& p) {
   QV_CUDA(cudaFuncSetAttribute(cga64_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int occ = max(1, min(4, (int)(200 * 1024 / (smem + 1024))));
   const int grid = min(p.B, qv_num_sms() * occ);
-  cga64_bwd_kernel<4><<<grid, WARPS * 32, smem, s>>>(p);
+  qv_launch(cga64_bwd_kernel<4>, grid, WARPS * 32, smem, s, p);
   QV_LAUNCH_CHECK();
   return 0;
 }

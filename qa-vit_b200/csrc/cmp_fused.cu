@@ -137,6 +137,7 @@ struct CmpFwdArgs {
 constexpr size_t CMPF_FWD_SMEM = al16(KTR * KXP * 2) + 2 * al16(KD * KWP * 2) + 2 * al16(KTR * 4) + 2 * al16(KD * 4);
 
 __global__ void __launch_bounds__(KNT, 2) cmpf_fwd_kernel(CmpFwdArgs a) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   Carve cv(smraw);
   bf16* X = cv.take<bf16>(KTR * KXP);
@@ -219,6 +220,7 @@ constexpr size_t CMPF_BWD_SMEM = 2 * al16(KTR * KXP * 2) + al16(KD * KWP * 2) + 
                                  al16(2 * KTR * 2 * 4) + 2 * al16(KC * 4);
 
 __global__ void __launch_bounds__(KNT, 1) cmpf_bwd_kernel(CmpBwdArgs a) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   Carve cv(smraw);
   bf16* X = cv.take<bf16>(KTR * KXP);          // x tile + 8 extra columns: (mean, 1/rstd) as hi | lo pairs, zeros
@@ -469,7 +471,7 @@ int cmpf_fwd(cudaStream_t s, long R, const void* const* x, const float* const* g
   QV_TRY(opt_in(cmpf_fwd_kernel, CMPF_FWD_SMEM));
   const long ntiles = (R + KTR - 1) / KTR;
   const int gx = (int)max(1L, min(ntiles, (long)(qv_num_sms() * 2 + 3) / 4));
-  cmpf_fwd_kernel<<<dim3(gx, 4), KNT, CMPF_FWD_SMEM, s>>>(a);
+  qv_launch(cmpf_fwd_kernel, dim3(gx, 4), KNT, CMPF_FWD_SMEM, s, a);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -488,7 +490,7 @@ int cmpf_bwd(cudaStream_t s, long R, const void* const* x, const float* const* s
   QV_TRY(opt_in(cmpf_bwd_kernel, CMPF_BWD_SMEM));
   const long ntiles = (R + KTR - 1) / KTR;
   const int gx = (int)max(1L, min(ntiles, (long)(qv_num_sms() + 3) / 4));
-  cmpf_bwd_kernel<<<dim3(gx, 4), KNT, CMPF_BWD_SMEM, s>>>(a);
+  qv_launch(cmpf_bwd_kernel, dim3(gx, 4), KNT, CMPF_BWD_SMEM, s, a);
   QV_LAUNCH_CHECK();
   return 0;
 }

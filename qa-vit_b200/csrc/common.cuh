@@ -48,6 +48,44 @@ extern unsigned long long g_qv_launches;   // kernels launched by this library (
     if (_s) return _s;        \
   } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the library starts with QV_PDL_ENTRY(): it lets the NEXT kernel of the stream be scheduled right away
+// (griddepcontrol.launch_dependents) and then waits until the PREVIOUS grid has completed and its writes are visible
+// (griddepcontrol.wait) -- so launch latency, CTA scheduling and (where a kernel moves the wait below its set-up code) barrier
+// initialisation / TMEM allocation / descriptor prefetch overlap the tail of the producer.  Ordering stays transitive because
+// every kernel waits before it touches memory.  qv_launch() attaches the launch attribute; inside a stream capture it becomes
+// a programmatic edge of the CUDA graph.  OFF by default (QAVIT_PDL=1 turns the attribute on; without it both instructions
+// are no-ops): on the headline step graph replay measured 46.5 ms without and 47.1-47.4 ms with programmatic edges, whatever
+// the order of trigger and wait (profiles/r2_pdl_ab.txt) -- the step's kernels are long enough that the graph's ordinary
+// kernel-to-kernel edge is already cheaper than the dependent-launch handshake.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef QV_PDL_MODE
+#define QV_PDL_MODE 0
+#endif
+#if QV_PDL_MODE == 0
+#define QV_PDL_ENTRY() do { pdl_trigger(); pdl_wait(); } while (0)
+#elif QV_PDL_MODE == 1
+#define QV_PDL_ENTRY() do { pdl_wait(); pdl_trigger(); } while (0)
+#else
+#define QV_PDL_ENTRY() do { pdl_wait(); } while (0)
+#endif
+extern int g_qv_pdl;
+template <typename... KArgs, typename... Args>
+inline void qv_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_qv_pdl ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors surface through QV_LAUNCH_CHECK()
+}
+
 // ---------------------------------------------------------------- typed load/store (T = float | bf16, math in fp32)
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }

@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) drop_rows_kernel(T* __restrict__ x, int l
                                                         const float* __restrict__ rowscale, int rows_per_img,
                                                         const float* __restrict__ resid, int ldr, const float* __restrict__ scale,
                                                         float* __restrict__ out, int ldo) {
+  QV_PDL_ENTRY();
   const int cpr = C / 8;
   const long total = rows * cpr;
   const bool masked = d.p > 0.f;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(256) drop_rows_kernel(T* __restrict__ x, int l
 }
 
 __global__ void droppath_scales_kernel(DropP d, int B, float* rs1, float* rs2) {
+  QV_PDL_ENTRY();
   const DropState st = drop_state(d);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * B; i += gridDim.x * blockDim.x)
     (i < B ? rs1 : rs2 - B)[i] = d.p > 0.f ? drop_keep1(st, (unsigned long long)i) : 1.f;
@@ -65,16 +67,16 @@ int drop_rows(cudaStream_t s, int dt, void* x, int ldx, long rows, int C, const 
   const long total = rows * (C / 8);
   const int grid = (int)((total + 255) / 256 < (long)qv_num_sms() * 8 ? (total + 255) / 256 : (long)qv_num_sms() * 8);
   if (dt == QV_F32)
-    drop_rows_kernel<float><<<grid, 256, 0, s>>>((float*)x, ldx, rows, C, d, rowscale, rows_per_img, resid, ldr, scale, out, ldo);
+    qv_launch(drop_rows_kernel<float>, grid, 256, 0, s, (float*)x, ldx, rows, C, d, rowscale, rows_per_img, resid, ldr, scale, out, ldo);
   else
-    drop_rows_kernel<bf16><<<grid, 256, 0, s>>>((bf16*)x, ldx, rows, C, d, rowscale, rows_per_img, resid, ldr, scale, out, ldo);
+    qv_launch(drop_rows_kernel<bf16>, grid, 256, 0, s, (bf16*)x, ldx, rows, C, d, rowscale, rows_per_img, resid, ldr, scale, out, ldo);
   QV_LAUNCH_CHECK();
   return 0;
 }
 
 int droppath_scales(cudaStream_t s, const DropP& d, int B, float* rs1, float* rs2) {
   QV_CHECK(d.p == 0.f || d.rng, "droppath_scales: missing rng snapshot");
-  droppath_scales_kernel<<<cdiv(2 * B, 256), 256, 0, s>>>(d, B, rs1, rs2);
+  qv_launch(droppath_scales_kernel, cdiv(2 * B, 256), 256, 0, s, d, B, rs1, rs2);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(CS * PG) dw_fwd_kernel(const T* __restrict__ x
                                                          const float* __restrict__ scale,
                                                          T* y, int ldy, const T* resid, int ldr,
                                                          const T* resid2, int ldr2, T* __restrict__ copy, int ldcp) {
+  QV_PDL_ENTRY();
   extern __shared__ float xs[];                 // [H*W][CS]
   const int c0 = blockIdx.y * CS, cl = threadIdx.x % CS, pg = threadIdx.x / CS, c = c0 + cl;
   const int HW = H * W;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(CS * PG) dw_wgrad_kernel(const T* __restrict__
                                                            float* __restrict__ dbias, const float* __restrict__ w,
                                                            const float* __restrict__ bias, const float* __restrict__ scale,
                                                            float* __restrict__ dscale) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   const int HW = H * W;
   float* xs = sm;                    // [HW][CS]
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(CS * PG) dw_wgrad_band_kernel(const T* __restr
                                                                 float* __restrict__ dbias, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, const float* __restrict__ scale,
                                                                 float* __restrict__ dscale, int BH) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   const int HW = H * W, XR = BH + K - 1;
   float* xs = sm;                    // [XR * W][CS]
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(CS * PG) dw_wgrad_band_kernel(const T* __restr
 template <typename T, int K, bool F, int WT>
 int launch_fwd(cudaStream_t s, const DwP& p, dim3 grid, size_t smem) {
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<T, K, F, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dw_fwd_kernel<T, K, F, WT><<<grid, CS * PG, smem, s>>>((const T*)p.x, p.ldx, p.B, p.H, p.W, p.C, p.w, p.bias, p.scale, (T*)p.y, p.ldy,
+  qv_launch(dw_fwd_kernel<T, K, F, WT>, grid, CS * PG, smem, s, (const T*)p.x, p.ldx, p.B, p.H, p.W, p.C, p.w, p.bias, p.scale, (T*)p.y, p.ldy,
                                                          (const T*)p.resid, p.ldr, (const T*)p.resid2, p.ldr2, (T*)p.copy, p.ldcp);
   QV_LAUNCH_CHECK();
   return 0;
@@ -366,7 +369,7 @@ template <typename T, int K, int WT>
 int launch_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B, int H, int W, int C, float* dw, float* dbias,
                  dim3 grid, size_t smem, const DwScale& sc) {
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(dw_wgrad_kernel<T, K, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dw_wgrad_kernel<T, K, WT><<<grid, CS * PG, smem, s>>>(x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc.w, sc.bias, sc.scale, sc.dscale);
+  qv_launch(dw_wgrad_kernel<T, K, WT>, grid, CS * PG, smem, s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc.w, sc.bias, sc.scale, sc.dscale);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -384,7 +387,7 @@ int run_wgrad(cudaStream_t s, const T* x, int ldx, const T* dy, int lddy, int B,
     const int cchb = cdiv(C, CS);
     dim3 gridb(max(1, min(B, qv_num_sms() / cchb)), cchb);
     QV_CUDA(cudaFuncSetAttribute(dw_wgrad_band_kernel<T, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-    dw_wgrad_band_kernel<T, K><<<gridb, CS * PG, bsm, s>>>(x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc.w, sc.bias, sc.scale, sc.dscale, BH);
+    qv_launch(dw_wgrad_band_kernel<T, K>, gridb, CS * PG, bsm, s, x, ldx, dy, lddy, B, H, W, C, dw, dbias, sc.w, sc.bias, sc.scale, sc.dscale, BH);
     QV_LAUNCH_CHECK();
     return 0;
   }

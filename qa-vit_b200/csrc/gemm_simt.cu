@@ -21,6 +21,7 @@ struct SimtArgs {
 
 template <typename TA, typename TB, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtArgs p) {
+  QV_PDL_ENTRY();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const TA* A = static_cast<const TA*>(p.A);
@@ -120,9 +121,9 @@ int launch(cudaStream_t s, int dtA, int dtB, SimtArgs& a, int splits) {
   dim3 grid(cdiv(a.N, TN), cdiv(a.M, TM), splits);
   a.kchunk = cdiv(cdiv(a.K, splits), TK) * TK;
   grid.z = cdiv(a.K, a.kchunk);
-  if (dtA == QV_F32 && dtB == QV_F32) simt_gemm_kernel<float, float, A_KC, B_KC><<<grid, 256, 0, s>>>(a);
-  else if (dtA == QV_BF16 && dtB == QV_F32) simt_gemm_kernel<bf16, float, A_KC, B_KC><<<grid, 256, 0, s>>>(a);
-  else if (dtA == QV_BF16 && dtB == QV_BF16) simt_gemm_kernel<bf16, bf16, A_KC, B_KC><<<grid, 256, 0, s>>>(a);
+  if (dtA == QV_F32 && dtB == QV_F32) qv_launch(simt_gemm_kernel<float, float, A_KC, B_KC>, grid, 256, 0, s, a);
+  else if (dtA == QV_BF16 && dtB == QV_F32) qv_launch(simt_gemm_kernel<bf16, float, A_KC, B_KC>, grid, 256, 0, s, a);
+  else if (dtA == QV_BF16 && dtB == QV_BF16) qv_launch(simt_gemm_kernel<bf16, bf16, A_KC, B_KC>, grid, 256, 0, s, a);
   else { qv_set_error("simt_gemm: unsupported dtype pair %d/%d", dtA, dtB); return 1; }
   QV_LAUNCH_CHECK();
   return 0;

@@ -296,6 +296,7 @@ template <bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_c, NtArgs p) {
+  pdl_trigger();   // the wait comes after the set-up that does not touch the producer's memory (barriers, descriptors, TMEM)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int STG = p.stages;
@@ -318,11 +319,12 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS); }
     fence_barrier_init();
   }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  pdl_wait();
   {   // the bias is staged pre-multiplied by scale_pre so the epilogue is one FFMA per element
     const float sp0 = p.e.scale_pre ? *p.e.scale_pre : 1.f;
     for (int j = threadIdx.x; j < p.BN; j += NTHREADS) bias_s[j] = (p.e.bias && n0 + j < p.N) ? p.e.bias[n0 + j] * sp0 : 0.f;
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -597,6 +599,7 @@ struct TnArgs {
 
 __global__ void __launch_bounds__(TN_THREADS, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, TnArgs p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int BOX = 64 * 64 * 2;                    // one [64 rows x 128 B] box
@@ -624,6 +627,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (nmb > 0) {
     if (warp == 0) {
@@ -838,7 +842,7 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
   if (p.tma_store) QV_TRY(make_map(&mc, static_cast<const bf16*>(e.C), M, N, e.ldc, 32));   // box = 32 rows x 64 columns
   QV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gx = max(1, min(p.m_tiles, qv_num_sms() / p.n_slices));
-  kern<<<dim3(gx, p.n_slices), NTHREADS, smem, s>>>(ma, mw, mc, p);
+  qv_launch(kern, dim3(gx, p.n_slices), NTHREADS, smem, s, ma, mw, mc, p);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -872,7 +876,7 @@ int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, 
   const size_t smem = 1024 + (size_t)STAGES * (2 + p.kboxes) * (64 * 64 * 2) + 256;
   QV_CHECK(smem <= 227 * 1024, "tc_gemm_tn: K=%d needs %zu B smem", K, smem);
   QV_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_gemm_tn_kernel<<<dim3(n_tiles, splits), TN_THREADS, smem, s>>>(my, mx, p);
+  qv_launch(tc_gemm_tn_kernel, dim3(n_tiles, splits), TN_THREADS, smem, s, my, mx, p);
   QV_LAUNCH_CHECK();
   return 0;
 }

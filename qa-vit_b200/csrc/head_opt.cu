@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(192) patch_embed_fwd_kernel(const float* __res
                                                               const float* __restrict__ beta,
                                                               const float* __restrict__ pos, float* __restrict__ pre,
                                                               float* __restrict__ stats, float* __restrict__ out) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   const int n_side = S / p, N = n_side * n_side, K = Cin * p * p;
   const int chunks = (N + PE_NC - 1) / PE_NC;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(192) patch_embed_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(192) patch_embed_dw_kernel(const float* __restrict__ img, const float* __restrict__ dpre,
                                                              int B, int Cin, int S, int p, int d,
                                                              float* __restrict__ dW) {
+  QV_PDL_ENTRY();
   extern __shared__ float sP[];  // [PE_NC][PE_KC]
   const int n_side = S / p, N = n_side * n_side, K = Cin * p * p;
   const int chunks = (N + PE_NC - 1) / PE_NC;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(192) patch_embed_dw_kernel(const float* __rest
 // lands in exactly one row) and the convolution is the tcgen05 GEMM; LayerNorm + pos is a warp-per-row kernel.
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, int B, int Cin, int S, int p,
                                                        bf16* __restrict__ col) {
+  QV_PDL_ENTRY();
   const int n_side = S / p, N = n_side * n_side, K = Cin * p * p;
   const long total = (long)B * N * K / 2;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(256) ln_pos_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ pos, float* __restrict__ stats,
                                                          float* __restrict__ out) {
+  QV_PDL_ENTRY();
   const int lane = threadIdx.x & 31, c0 = lane * EPL;
   const bool act = c0 < C;
   const float invC = 1.f / (float)C;
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(256) ln_pos_fwd_kernel(const float* __restrict
 }
 int patchify(cudaStream_t s, const float* img, int B, int Cin, int S, int p, bf16* col) {
   const long total = (long)B * (S / p) * (S / p) * Cin * p * p / 2;
-  patchify_kernel<<<(int)max(1L, min((total + 255) / 256, (long)qv_num_sms() * 8)), 256, 0, s>>>(img, B, Cin, S, p, col);
+  qv_launch(patchify_kernel, (int)max(1L, min((total + 255) / 256, (long)qv_num_sms() * 8)), 256, 0, s, img, B, Cin, S, p, col);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -183,15 +187,15 @@ int patch_embed_fwd(cudaStream_t s, int dt, const float* img, int B, int Cin, in
     e.bias = bias; e.C = pre; e.ldc = d; e.c_f32 = 1;
     QV_TRY(tc_gemm_nt(s, col, K, (int)rows, d, K, wb, e));
     const int grid = (int)max(1L, min((rows + 7) / 8, (long)qv_num_sms() * 8));
-    if (d > 128) ln_pos_fwd_kernel<8><<<grid, 256, 0, s>>>(pre, rows, N, d, gamma, beta, pos, stats, out);
-    else ln_pos_fwd_kernel<4><<<grid, 256, 0, s>>>(pre, rows, N, d, gamma, beta, pos, stats, out);
+    if (d > 128) qv_launch(ln_pos_fwd_kernel<8>, grid, 256, 0, s, pre, rows, N, d, gamma, beta, pos, stats, out);
+    else qv_launch(ln_pos_fwd_kernel<4>, grid, 256, 0, s, pre, rows, N, d, gamma, beta, pos, stats, out);
     QV_LAUNCH_CHECK();
     return 0;
   }
   const size_t smem = (size_t)(PE_NC * PE_KC + d * (PE_KC + 1) + PE_NC * d) * sizeof(float);
   QV_CHECK(smem <= 227 * 1024, "patch_embed: d=%d needs %zu B smem: not supported", d, smem);
   QV_CUDA(cudaFuncSetAttribute(patch_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  patch_embed_fwd_kernel<<<min(B * cdiv(N, PE_NC), qv_num_sms() * 2), 192, smem, s>>>(img, B, Cin, S, p, d, W, bias, gamma, beta, pos, pre, stats, out);
+  qv_launch(patch_embed_fwd_kernel, min(B * cdiv(N, PE_NC), qv_num_sms() * 2), 192, smem, s, img, B, Cin, S, p, d, W, bias, gamma, beta, pos, pre, stats, out);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -217,7 +221,7 @@ int patch_embed_bwd(cudaStream_t s, int dt, const float* img, const float* dout,
   QV_TRY(ln_bwd(s, QV_F32, pre, d, QV_F32, dout, d, B * N, d, gamma, stats, 0, QV_F32, nullptr, dpre, nullptr, dgamma, dbeta));
   QV_TRY(colsum_accum(s, QV_F32, dpre, d, B * N, d, dbias, nullptr));
   const size_t smem = (size_t)PE_NC * PE_KC * sizeof(float);
-  patch_embed_dw_kernel<<<min(B * cdiv(N, PE_NC), qv_num_sms()), 192, smem, s>>>(img, dpre, B, Cin, S, p, d, dW);
+  qv_launch(patch_embed_dw_kernel, min(B * cdiv(N, PE_NC), qv_num_sms()), 192, smem, s, img, dpre, B, Cin, S, p, d, dW);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -228,6 +232,7 @@ namespace {
 __global__ void __launch_bounds__(256) ln_mean_kernel(const float* __restrict__ x, int B, int N, int d,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       float* __restrict__ stats, float* __restrict__ pooled) {
+  QV_PDL_ENTRY();
   __shared__ float acc[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -265,6 +270,7 @@ __global__ void __launch_bounds__(256) ln_mean_bwd_kernel(const float* __restric
                                                           int B, int N, int d, const float* __restrict__ gamma,
                                                           const float* __restrict__ stats, float* __restrict__ dx,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  QV_PDL_ENTRY();
   __shared__ float red[2][8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float ag[8], ab[8];
@@ -310,7 +316,7 @@ int head_fwd(cudaStream_t s, const float* x, int B, int N, int d, const float* g
              const float* bias, int ncls, float* stats, float* pooled, float* logits) {
   if (B <= 0) return 0;
   QV_CHECK(d <= 256, "head: d=%d > 256", d);
-  ln_mean_kernel<<<min(B, qv_num_sms() * 4), 256, 0, s>>>(x, B, N, d, gamma, beta, stats, pooled);
+  qv_launch(ln_mean_kernel, min(B, qv_num_sms() * 4), 256, 0, s, x, B, N, d, gamma, beta, stats, pooled);
   QV_LAUNCH_CHECK();
   GemmEpi e;
   e.bias = bias; e.C = logits; e.ldc = ncls; e.c_f32 = 1;
@@ -325,7 +331,7 @@ int head_bwd(cudaStream_t s, const float* x, const float* dlogits, int B, int N,
   GemmEpi e;
   e.C = dpooled; e.ldc = d; e.c_f32 = 1;
   QV_TRY(simt_gemm_nn(s, QV_F32, dlogits, ncls, B, ncls, d, W, e));
-  ln_mean_bwd_kernel<<<min(cdiv((long)B * N, 8), qv_num_sms() * 4), 256, 0, s>>>(x, dpooled, B, N, d, gamma, stats, dx, dgamma, dbeta);
+  qv_launch(ln_mean_bwd_kernel, min(cdiv((long)B * N, 8), qv_num_sms() * 4), 256, 0, s, x, dpooled, B, N, d, gamma, stats, dx, dgamma, dbeta);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -340,6 +346,7 @@ namespace {
 __global__ void ce_kernel(const float* __restrict__ logits, const long long* __restrict__ ya,
                           const long long* __restrict__ yb, float lam, const float* __restrict__ lam_dev, int B, int C, float eps,
                           float* __restrict__ row_loss, float* __restrict__ dlogits, int* __restrict__ err) {
+  QV_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -377,6 +384,7 @@ __global__ void ce_kernel(const float* __restrict__ logits, const long long* __r
 }
 // fixed-order sum of row_loss[0 .. B): thread t adds rows t, t + 1024, ... then a fixed shared-memory tree
 __global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_loss, int B, float* __restrict__ loss) {
+  QV_PDL_ENTRY();
   __shared__ float red[1024];
   float a = 0.f;
   for (int i = threadIdx.x; i < B; i += 1024) a += row_loss[i];
@@ -389,6 +397,7 @@ __global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict
   if (threadIdx.x == 0) *loss = red[0];
 }
 __global__ void scale_by_scalar_kernel(const float* __restrict__ x, const float* __restrict__ sc, long n, float* __restrict__ y) {
+  QV_PDL_ENTRY();
   const float s = *sc;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = x[i] * s;
 }
@@ -401,15 +410,15 @@ int ce_loss_fwd_bwd(cudaStream_t s, const float* logits, const long long* ya, co
     return 0;
   }
   QV_CHECK(row_loss, "cross_entropy: row_loss scratch (B floats) missing");
-  ce_kernel<<<cdiv(B, 4), 128, 0, s>>>(logits, ya, yb, lam, lam_dev, B, ncls, smoothing, row_loss, dlogits, err);
+  qv_launch(ce_kernel, cdiv(B, 4), 128, 0, s, logits, ya, yb, lam, lam_dev, B, ncls, smoothing, row_loss, dlogits, err);
   QV_LAUNCH_CHECK();
-  ce_reduce_kernel<<<1, 1024, 0, s>>>(row_loss, B, loss);
+  qv_launch(ce_reduce_kernel, 1, 1024, 0, s, row_loss, B, loss);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int scale_by_scalar(cudaStream_t s, const float* x, const float* scalar_dev, long n, float* y) {
   if (n <= 0) return 0;
-  scale_by_scalar_kernel<<<(int)min((long)qv_num_sms() * 8, (long)cdiv(n, 256)), 256, 0, s>>>(x, scalar_dev, n, y);
+  qv_launch(scale_by_scalar_kernel, (int)min((long)qv_num_sms() * 8, (long)cdiv(n, 256)), 256, 0, s, x, scalar_dev, n, y);
   QV_LAUNCH_CHECK();
   return 0;
 }

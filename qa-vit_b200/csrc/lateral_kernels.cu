@@ -42,6 +42,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf
 // against cancellation when |mean| >> std).  Thread = 8 channels x a strided set of rows.
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long rows, int C, float* __restrict__ sums) {
+  QV_PDL_ENTRY();
   extern __shared__ float red[];   // [2C]
   const int lpr = C / 8, cv = (threadIdx.x % lpr) * 8, r0 = threadIdx.x / lpr, rpp = 256 / lpr;
   for (int i = threadIdx.x; i < 2 * C; i += 256) red[i] = 0.f;
@@ -68,6 +69,7 @@ template <typename T>
 __global__ void bn_finalize_kernel(const T* __restrict__ x, const float* __restrict__ sums, long rows, int C, float eps,
                                    float momentum, int train, float* running_mean, float* running_var,
                                    long long* num_batches, float* __restrict__ mr) {
+  QV_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (train) {
@@ -92,6 +94,7 @@ template <typename T, bool GELU>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, long nvec, int C, const float* __restrict__ mr,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        T* __restrict__ y) {
+  QV_PDL_ENTRY();
   const int lpr = C / 8;
   if (256 % lpr == 0) {
     // the thread stride (a multiple of 256 vectors) is a multiple of the vectors per row: a thread stays on the same 8
@@ -131,6 +134,7 @@ template <typename T, bool GELU>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, long rows, int C,
                                                             const float* __restrict__ mr, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ sums) {
+  QV_PDL_ENTRY();
   extern __shared__ float red[];   // [2C]
   const int lpr = C / 8, cv = (threadIdx.x % lpr) * 8, r0 = threadIdx.x / lpr, rpp = 256 / lpr;
   for (int i = threadIdx.x; i < 2 * C; i += 256) red[i] = 0.f;
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const float* __restrict__ beta, const float* __restrict__ sums,
                                                            int train, T* __restrict__ dx, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta) {
+  QV_PDL_ENTRY();
   const int lpr = C / 8;
   const float invn = train ? 1.f / (float)rows : 0.f;
   if (blockIdx.x == 0) {
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 // lines); the Kp-wide row is written as 8-element vectors.  KP8 = Kp / 8 (4 for the 3-channel stem).
 template <typename T, int KP8, int CIN>
 __global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict__ img, int B, int Cin_rt, int S, T* __restrict__ col) {
+  QV_PDL_ENTRY();
   const int Cin = CIN ? CIN : Cin_rt;     // compile-time channel count keeps the row in registers
   const int Ho = S / 2;
   const long rows = (long)B * Ho * Ho;
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(256) im2col_img_kernel(const float* __restrict
 // x [B, Hi, Hi, Cin] (NHWC, Cin % 8 == 0) -> col [B * Ho * Ho, 9 * Cin]
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const T* __restrict__ x, int B, int Hi, int Cin, T* __restrict__ col) {
+  QV_PDL_ENTRY();
   const int Ho = Hi / 2, cv = Cin / 8;
   const long total = (long)B * Ho * Ho * 9 * cv;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
@@ -258,6 +265,7 @@ __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const T* __restrict__ 
 // dx [B, Hi, Hi, Cin] = gather of dcol [B * Ho * Ho, 9 * Cin] (each input pixel feeds <= 2 x 2 output taps)
 template <typename T>
 __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const T* __restrict__ dcol, int B, int Hi, int Cin, T* __restrict__ dx) {
+  QV_PDL_ENTRY();
   const int Ho = Hi / 2, cv = Cin / 8;
   const long total = (long)B * Hi * Hi * cv;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
@@ -287,6 +295,7 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const T* __restrict__ 
 }
 // W [N, Cin, 3, 3] -> Wp [N, Kp] with k = (ky * 3 + kx) * Cin + cin (zero padded); unpack: dW += dWp
 __global__ void conv_w_pack_kernel(const float* __restrict__ W, int N, int Cin, int Kp, float* __restrict__ Wp) {
+  QV_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * Kp) return;
   const int n = i / Kp, k = i % Kp;
@@ -295,6 +304,7 @@ __global__ void conv_w_pack_kernel(const float* __restrict__ W, int N, int Cin, 
   Wp[i] = v;
 }
 __global__ void conv_w_unpack_add_kernel(const float* __restrict__ dWp, int N, int Cin, int Kp, float* __restrict__ dW) {
+  QV_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * Cin * 9) return;
   const int t = i % 9, cin = (i / 9) % Cin, n = i / (9 * Cin);
@@ -308,6 +318,7 @@ __global__ void __launch_bounds__(256) rowln_fwd_kernel(const T* __restrict__ x,
                                                         const float* __restrict__ beta, float eps, int gelu_out,
                                                         const TY* __restrict__ resid, const float* __restrict__ scale,
                                                         TY* __restrict__ y, float* __restrict__ y32, float* __restrict__ stats) {
+  QV_PDL_ENTRY();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, c0 = lane * EPL;
   const bool act = c0 < C;
   const float invC = 1.f / (float)C;
@@ -353,6 +364,7 @@ __global__ void __launch_bounds__(256, 3) rowln_bwd_kernel(const T* __restrict__
                                                         const float* __restrict__ stats, int gelu_out,
                                                         const float* __restrict__ scale, float* __restrict__ dscale,
                                                         T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  QV_PDL_ENTRY();
   __shared__ float red[2][8][256];
   __shared__ float sred[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5, c0 = lane * EPL;
@@ -412,6 +424,7 @@ template <typename T, int EPL>
 __global__ void __launch_bounds__(256) sf_pre_fwd_kernel(const float* __restrict__ Tin, const float* __restrict__ R, long rows, int C,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          T* __restrict__ g_in, T* __restrict__ cat, float* __restrict__ stats) {
+  QV_PDL_ENTRY();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, c0 = lane * EPL;
   const bool act = c0 < C;
   const float invC = 1.f / (float)C;
@@ -513,6 +526,7 @@ __device__ __forceinline__ void softmax2(const float* fw, float* w0, float* w1) 
 template <typename T, int EPL>
 __global__ void __launch_bounds__(256, 3) sf_post_fwd_kernel(SfP p, float* __restrict__ out, float* __restrict__ cat_stats,
                                                           float* __restrict__ fin_stats) {
+  QV_PDL_ENTRY();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, c0 = lane * EPL;
   const bool act = c0 < p.C;
   const float invC = 1.f / (float)p.C;
@@ -557,6 +571,7 @@ __global__ void __launch_bounds__(256, 2) sf_post_bwd_kernel(SfP p, const float*
                                                           float* __restrict__ d_fin_g, float* __restrict__ d_fin_b,
                                                           float* __restrict__ d_cat_g, float* __restrict__ d_cat_b,
                                                           float* __restrict__ draw) {
+  QV_PDL_ENTRY();
   __shared__ float red[4][8][256];
   __shared__ float sred[2][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5, c0 = lane * EPL;
@@ -641,6 +656,7 @@ __global__ void __launch_bounds__(256, 3) sf_pre_bwd_kernel(const float* __restr
                                                          const T* __restrict__ dg_in, const T* __restrict__ dcat, long rows, int C,
                                                          const float* __restrict__ gamma, const float* __restrict__ stats,
                                                          float* dT, float* dR, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  QV_PDL_ENTRY();
   __shared__ float red[2][8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5, c0 = lane * EPL;
   const bool act = c0 < C;
@@ -694,6 +710,7 @@ __global__ void __launch_bounds__(256, 3) sf_pre_bwd_kernel(const float* __restr
 }
 
 __global__ void rng_snapshot_advance_kernel(unsigned long long* rng, unsigned long long* snap) {
+  QV_PDL_ENTRY();
   snap[0] = rng[0];
   snap[1] = rng[1];
   rng[1] += 1;
@@ -716,23 +733,23 @@ int bn_fwd(cudaStream_t s, int dt, const void* x, long rows, int C, const float*
     QV_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(float), s));
     const int rpp = 256 / (C / 8);
     const int grid = (int)max(1L, min((rows + rpp - 1) / rpp, (long)qv_num_sms() * 4));
-    DT_SWITCH(dt, (bn_stats_kernel<float><<<grid, 256, 2 * C * sizeof(float), s>>>((const float*)x, rows, C, sums_scratch)),
-              (bn_stats_kernel<bf16><<<grid, 256, 2 * C * sizeof(float), s>>>((const bf16*)x, rows, C, sums_scratch)));
+    DT_SWITCH(dt, (qv_launch(bn_stats_kernel<float>, grid, 256, 2 * C * sizeof(float), s, (const float*)x, rows, C, sums_scratch)),
+              (qv_launch(bn_stats_kernel<bf16>, grid, 256, 2 * C * sizeof(float), s, (const bf16*)x, rows, C, sums_scratch)));
     QV_LAUNCH_CHECK();
   } else {
     QV_CHECK(running_mean && running_var, "batch_norm: eval mode needs running statistics");
   }
-  DT_SWITCH(dt, (bn_finalize_kernel<float><<<cdiv(C, 128), 128, 0, s>>>((const float*)x, sums_scratch, rows, C, eps, momentum, train,
+  DT_SWITCH(dt, (qv_launch(bn_finalize_kernel<float>, cdiv(C, 128), 128, 0, s, (const float*)x, sums_scratch, rows, C, eps, momentum, train,
                                                                         running_mean, running_var, num_batches, mr)),
-            (bn_finalize_kernel<bf16><<<cdiv(C, 128), 128, 0, s>>>((const bf16*)x, sums_scratch, rows, C, eps, momentum, train,
+            (qv_launch(bn_finalize_kernel<bf16>, cdiv(C, 128), 128, 0, s, (const bf16*)x, sums_scratch, rows, C, eps, momentum, train,
                                                                    running_mean, running_var, num_batches, mr)));
   QV_LAUNCH_CHECK();
   const long nvec = rows * C / 8;
   const int grid = vec_grid(nvec);
-  if (gelu) DT_SWITCH(dt, (bn_apply_kernel<float, true><<<grid, 256, 0, s>>>((const float*)x, nvec, C, mr, gamma, beta, (float*)y)),
-                      (bn_apply_kernel<bf16, true><<<grid, 256, 0, s>>>((const bf16*)x, nvec, C, mr, gamma, beta, (bf16*)y)));
-  else DT_SWITCH(dt, (bn_apply_kernel<float, false><<<grid, 256, 0, s>>>((const float*)x, nvec, C, mr, gamma, beta, (float*)y)),
-                 (bn_apply_kernel<bf16, false><<<grid, 256, 0, s>>>((const bf16*)x, nvec, C, mr, gamma, beta, (bf16*)y)));
+  if (gelu) DT_SWITCH(dt, (qv_launch(bn_apply_kernel<float, true>, grid, 256, 0, s, (const float*)x, nvec, C, mr, gamma, beta, (float*)y)),
+                      (qv_launch(bn_apply_kernel<bf16, true>, grid, 256, 0, s, (const bf16*)x, nvec, C, mr, gamma, beta, (bf16*)y)));
+  else DT_SWITCH(dt, (qv_launch(bn_apply_kernel<float, false>, grid, 256, 0, s, (const float*)x, nvec, C, mr, gamma, beta, (float*)y)),
+                 (qv_launch(bn_apply_kernel<bf16, false>, grid, 256, 0, s, (const bf16*)x, nvec, C, mr, gamma, beta, (bf16*)y)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -744,7 +761,7 @@ int bn_bwd(cudaStream_t s, int dt, const void* x, const void* dy, long rows, int
   const int rpp = 256 / (C / 8);
   const int g1 = (int)max(1L, min((rows + rpp - 1) / rpp, (long)qv_num_sms() * 4));
   const size_t sm = 2 * C * sizeof(float);
-#define BN_R(T, G) bn_bwd_reduce_kernel<T, G><<<g1, 256, sm, s>>>((const T*)x, (const T*)dy, rows, C, mr, gamma, beta, sums_scratch)
+#define BN_R(T, G) qv_launch(bn_bwd_reduce_kernel<T, G>, g1, 256, sm, s, (const T*)x, (const T*)dy, rows, C, mr, gamma, beta, sums_scratch)
   if (gelu) DT_SWITCH(dt, (BN_R(float, true)), (BN_R(bf16, true)));
   else DT_SWITCH(dt, (BN_R(float, false)), (BN_R(bf16, false)));
 #undef BN_R
@@ -752,7 +769,7 @@ int bn_bwd(cudaStream_t s, int dt, const void* x, const void* dy, long rows, int
   const long nvec = rows * C / 8;
   const int g2 = vec_grid(nvec);
 #define BN_A(T, G) \
-  bn_bwd_apply_kernel<T, G><<<g2, 256, 0, s>>>((const T*)x, (const T*)dy, nvec, rows, C, mr, gamma, beta, sums_scratch, train, (T*)dx, dgamma, dbeta)
+  qv_launch(bn_bwd_apply_kernel<T, G>, g2, 256, 0, s, (const T*)x, (const T*)dy, nvec, rows, C, mr, gamma, beta, sums_scratch, train, (T*)dx, dgamma, dbeta)
   if (gelu) DT_SWITCH(dt, (BN_A(float, true)), (BN_A(bf16, true)));
   else DT_SWITCH(dt, (BN_A(float, false)), (BN_A(bf16, false)));
 #undef BN_A
@@ -764,10 +781,10 @@ int im2col_img(cudaStream_t s, int dt, const float* img, int B, int Cin, int S, 
   QV_CHECK(Kp == 32 && Cin <= 3, "im2col_img: in_channels=%d (Kp=%d) not instantiated (<= 3 channels)", Cin, Kp);
   const long rows = (long)B * (S / 2) * (S / 2);
   const int grid = vec_grid(rows);
-  if (Cin == 3) DT_SWITCH(dt, (im2col_img_kernel<float, 4, 3><<<grid, 256, 0, s>>>(img, B, Cin, S, (float*)col)),
-                          (im2col_img_kernel<bf16, 4, 3><<<grid, 256, 0, s>>>(img, B, Cin, S, (bf16*)col)));
-  else DT_SWITCH(dt, (im2col_img_kernel<float, 4, 0><<<grid, 256, 0, s>>>(img, B, Cin, S, (float*)col)),
-                 (im2col_img_kernel<bf16, 4, 0><<<grid, 256, 0, s>>>(img, B, Cin, S, (bf16*)col)));
+  if (Cin == 3) DT_SWITCH(dt, (qv_launch(im2col_img_kernel<float, 4, 3>, grid, 256, 0, s, img, B, Cin, S, (float*)col)),
+                          (qv_launch(im2col_img_kernel<bf16, 4, 3>, grid, 256, 0, s, img, B, Cin, S, (bf16*)col)));
+  else DT_SWITCH(dt, (qv_launch(im2col_img_kernel<float, 4, 0>, grid, 256, 0, s, img, B, Cin, S, (float*)col)),
+                 (qv_launch(im2col_img_kernel<bf16, 4, 0>, grid, 256, 0, s, img, B, Cin, S, (bf16*)col)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -775,26 +792,26 @@ int im2col_nhwc(cudaStream_t s, int dt, const void* x, int B, int Hi, int Cin, v
   QV_CHECK(Cin % 8 == 0 && Hi % 2 == 0, "im2col: Cin=%d Hi=%d unsupported", Cin, Hi);
   const long total = (long)B * (Hi / 2) * (Hi / 2) * 9 * (Cin / 8);
   const int grid = vec_grid(total);
-  DT_SWITCH(dt, (im2col_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)x, B, Hi, Cin, (float*)col)),
-            (im2col_nhwc_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, B, Hi, Cin, (bf16*)col)));
+  DT_SWITCH(dt, (qv_launch(im2col_nhwc_kernel<float>, grid, 256, 0, s, (const float*)x, B, Hi, Cin, (float*)col)),
+            (qv_launch(im2col_nhwc_kernel<bf16>, grid, 256, 0, s, (const bf16*)x, B, Hi, Cin, (bf16*)col)));
   QV_LAUNCH_CHECK();
   return 0;
 }
 int col2im_nhwc(cudaStream_t s, int dt, const void* dcol, int B, int Hi, int Cin, void* dx) {
   const long total = (long)B * Hi * Hi * (Cin / 8);
   const int grid = vec_grid(total);
-  DT_SWITCH(dt, (col2im_nhwc_kernel<float><<<grid, 256, 0, s>>>((const float*)dcol, B, Hi, Cin, (float*)dx)),
-            (col2im_nhwc_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)dcol, B, Hi, Cin, (bf16*)dx)));
+  DT_SWITCH(dt, (qv_launch(col2im_nhwc_kernel<float>, grid, 256, 0, s, (const float*)dcol, B, Hi, Cin, (float*)dx)),
+            (qv_launch(col2im_nhwc_kernel<bf16>, grid, 256, 0, s, (const bf16*)dcol, B, Hi, Cin, (bf16*)dx)));
   QV_LAUNCH_CHECK();
   return 0;
 }
 int conv_w_pack(cudaStream_t s, const float* W, int N, int Cin, int Kp, float* Wp) {
-  conv_w_pack_kernel<<<cdiv((long)N * Kp, 256), 256, 0, s>>>(W, N, Cin, Kp, Wp);
+  qv_launch(conv_w_pack_kernel, cdiv((long)N * Kp, 256), 256, 0, s, W, N, Cin, Kp, Wp);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int conv_w_unpack_add(cudaStream_t s, const float* dWp, int N, int Cin, int Kp, float* dW) {
-  conv_w_unpack_add_kernel<<<cdiv((long)N * Cin * 9, 256), 256, 0, s>>>(dWp, N, Cin, Kp, dW);
+  qv_launch(conv_w_unpack_add_kernel, cdiv((long)N * Cin * 9, 256), 256, 0, s, dWp, N, Cin, Kp, dW);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -809,7 +826,7 @@ int rowln_fwd(cudaStream_t s, int dt, const void* x, long rows, int C, const flo
   QV_CHECK(!(dt == QV_F32 && dt_y == QV_BF16), "rowln_fwd: fp32 input with bf16 output is not instantiated");
   const int grid = row_grid(rows, 8);
 #define RL_F(TX, TY, E) \
-  rowln_fwd_kernel<TX, TY, E><<<grid, 256, 0, s>>>((const TX*)x, rows, C, gamma, beta, eps, gelu_out, (const TY*)resid, scale, (TY*)y, y32, stats)
+  qv_launch(rowln_fwd_kernel<TX, TY, E>, grid, 256, 0, s, (const TX*)x, rows, C, gamma, beta, eps, gelu_out, (const TY*)resid, scale, (TY*)y, y32, stats)
 #define RL_F2(TX, TY) do { if (epl == 8) RL_F(TX, TY, 8); else RL_F(TX, TY, 4); } while (0)
   if (dt == QV_BF16 && dt_y == QV_BF16) RL_F2(bf16, bf16);
   else if (dt == QV_BF16) RL_F2(bf16, float);
@@ -829,7 +846,7 @@ int rowln_bwd(cudaStream_t s, int dt, const void* x, int dt_dy, const void* dy, 
   QV_CHECK(!(dt == QV_F32 && dt_dy == QV_BF16), "rowln_bwd: fp32 activations with bf16 gradients are not instantiated");
   const int grid = row_grid((rows + 1) / 2, 6);
 #define RL_B(TX, TD, E) \
-  rowln_bwd_kernel<TX, TD, E><<<grid, 256, 0, s>>>((const TX*)x, (const TD*)dy, rows, C, gamma, beta, stats, gelu_out, scale, dscale, (TX*)dx, dgamma, dbeta)
+  qv_launch(rowln_bwd_kernel<TX, TD, E>, grid, 256, 0, s, (const TX*)x, (const TD*)dy, rows, C, gamma, beta, stats, gelu_out, scale, dscale, (TX*)dx, dgamma, dbeta)
 #define RL_B2(TX, TD) do { if (epl == 8) RL_B(TX, TD, 8); else RL_B(TX, TD, 4); } while (0)
   if (dt == QV_BF16 && dt_dy == QV_BF16) RL_B2(bf16, bf16);
   else if (dt == QV_BF16) RL_B2(bf16, float);
@@ -845,7 +862,7 @@ int sf_pre_fwd(cudaStream_t s, int dt, const float* Tin, const float* R, long ro
   const int epl = row_epl(C);
   QV_CHECK(C <= 256 && C % epl == 0, "splitfusion: C=%d unsupported", C);
   const int grid = row_grid(rows, 8);
-#define SF_GO(T, E) sf_pre_fwd_kernel<T, E><<<grid, 256, 0, s>>>(Tin, R, rows, C, gamma, beta, (T*)g_in, (T*)cat, stats)
+#define SF_GO(T, E) qv_launch(sf_pre_fwd_kernel<T, E>, grid, 256, 0, s, Tin, R, rows, C, gamma, beta, (T*)g_in, (T*)cat, stats)
   if (dt == QV_BF16) { if (epl == 8) SF_GO(bf16, 8); else SF_GO(bf16, 4); }
   else { if (epl == 8) SF_GO(float, 8); else SF_GO(float, 4); }
 #undef SF_GO
@@ -857,7 +874,7 @@ int sf_post_fwd(cudaStream_t s, int dt, const SfArgs& a, float* out, float* cat_
   const int epl = row_epl(a.C);
   SfP p{a.Tin, a.R, a.glin, a.cpre, a.cat_g, a.cat_b, a.fin_g, a.fin_b, a.fw, a.drop_p, a.rng, a.site, a.rows, a.C};
   const int grid = row_grid(a.rows, 8);
-#define SF_GO(T, E) sf_post_fwd_kernel<T, E><<<grid, 256, 0, s>>>(p, out, cat_stats, fin_stats)
+#define SF_GO(T, E) qv_launch(sf_post_fwd_kernel<T, E>, grid, 256, 0, s, p, out, cat_stats, fin_stats)
   if (dt == QV_BF16) { if (epl == 8) SF_GO(bf16, 8); else SF_GO(bf16, 4); }
   else { if (epl == 8) SF_GO(float, 8); else SF_GO(float, 4); }
 #undef SF_GO
@@ -871,7 +888,7 @@ int sf_post_bwd(cudaStream_t s, int dt, const SfArgs& a, const float* dout, cons
   SfP p{a.Tin, a.R, a.glin, a.cpre, a.cat_g, a.cat_b, a.fin_g, a.fin_b, a.fw, a.drop_p, a.rng, a.site, a.rows, a.C};
   const int grid = row_grid((a.rows + 1) / 2, 4);
 #define SF_GO(T, E) \
-  sf_post_bwd_kernel<T, E><<<grid, 256, 0, s>>>(p, dout, cat_stats, fin_stats, dT, dR, (T*)dglin, (T*)dcpre, d_fin_g, d_fin_b, d_cat_g, d_cat_b, draw)
+  qv_launch(sf_post_bwd_kernel<T, E>, grid, 256, 0, s, p, dout, cat_stats, fin_stats, dT, dR, (T*)dglin, (T*)dcpre, d_fin_g, d_fin_b, d_cat_g, d_cat_b, draw)
   if (dt == QV_BF16) { if (epl == 8) SF_GO(bf16, 8); else SF_GO(bf16, 4); }
   else { if (epl == 8) SF_GO(float, 8); else SF_GO(float, 4); }
 #undef SF_GO
@@ -884,7 +901,7 @@ int sf_pre_bwd(cudaStream_t s, int dt, const float* Tin, const float* R, const v
   const int epl = row_epl(C);
   const int grid = row_grid((rows + 1) / 2, 6);
 #define SF_GO(T, E) \
-  sf_pre_bwd_kernel<T, E><<<grid, 256, 0, s>>>(Tin, R, (const T*)dg_in, (const T*)dcat, rows, C, gamma, stats, dT, dR, dgamma, dbeta)
+  qv_launch(sf_pre_bwd_kernel<T, E>, grid, 256, 0, s, Tin, R, (const T*)dg_in, (const T*)dcat, rows, C, gamma, stats, dT, dR, dgamma, dbeta)
   if (dt == QV_BF16) { if (epl == 8) SF_GO(bf16, 8); else SF_GO(bf16, 4); }
   else { if (epl == 8) SF_GO(float, 8); else SF_GO(float, 4); }
 #undef SF_GO
@@ -893,7 +910,7 @@ int sf_pre_bwd(cudaStream_t s, int dt, const float* Tin, const float* R, const v
 }
 
 int rng_snapshot_advance(cudaStream_t s, unsigned long long* rng, unsigned long long* snap) {
-  rng_snapshot_advance_kernel<<<1, 1, 0, s>>>(rng, snap);
+  qv_launch(rng_snapshot_advance_kernel, 1, 1, 0, s, rng, snap);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -919,6 +936,7 @@ __device__ __forceinline__ Tap make_tap(int o, int in, int out) {
 template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_fwd_kernel(const T* __restrict__ in, int B, int Hi, int Wi, int Ho, int Wo, int C,
                                                                   T* __restrict__ out) {
+  QV_PDL_ENTRY();
   const int c2n = C / 2;
   const long total = (long)B * Ho * Wo * c2n;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -942,6 +960,7 @@ __global__ void __launch_bounds__(256) resize_bilinear_fwd_kernel(const T* __res
 template <typename T>
 __global__ void __launch_bounds__(256) resize_bilinear_bwd_kernel(const T* __restrict__ dout, int B, int Hi, int Wi, int Ho, int Wo, int C,
                                                                   T* __restrict__ din) {
+  QV_PDL_ENTRY();
   const int c2n = C / 2;
   const long total = (long)B * c2n;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -977,8 +996,8 @@ int resize_bilinear_fwd(cudaStream_t s, int dt, const void* in, int B, int Hi, i
   const long total = (long)B * Ho * Wo * (C / 2);
   if (total <= 0) return 0;
   const int grid = (int)min((long)qv_num_sms() * 16, (total + 255) / 256);
-  DT_SWITCH(dt, (resize_bilinear_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)in, B, Hi, Wi, Ho, Wo, C, (float*)out)),
-            (resize_bilinear_fwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)in, B, Hi, Wi, Ho, Wo, C, (bf16*)out)));
+  DT_SWITCH(dt, (qv_launch(resize_bilinear_fwd_kernel<float>, grid, 256, 0, s, (const float*)in, B, Hi, Wi, Ho, Wo, C, (float*)out)),
+            (qv_launch(resize_bilinear_fwd_kernel<bf16>, grid, 256, 0, s, (const bf16*)in, B, Hi, Wi, Ho, Wo, C, (bf16*)out)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -988,8 +1007,8 @@ int resize_bilinear_bwd(cudaStream_t s, int dt, const void* dout, int B, int Hi,
   if (total <= 0) return 0;
   QV_CUDA(cudaMemsetAsync(din, 0, (size_t)B * Hi * Wi * C * (dt == QV_BF16 ? 2 : 4), s));
   const int grid = (int)min((long)qv_num_sms() * 16, (total + 255) / 256);
-  DT_SWITCH(dt, (resize_bilinear_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dout, B, Hi, Wi, Ho, Wo, C, (float*)din)),
-            (resize_bilinear_bwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)dout, B, Hi, Wi, Ho, Wo, C, (bf16*)din)));
+  DT_SWITCH(dt, (qv_launch(resize_bilinear_bwd_kernel<float>, grid, 256, 0, s, (const float*)dout, B, Hi, Wi, Ho, Wo, C, (float*)din)),
+            (qv_launch(resize_bilinear_bwd_kernel<bf16>, grid, 256, 0, s, (const bf16*)dout, B, Hi, Wi, Ho, Wo, C, (bf16*)din)));
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -20,6 +20,7 @@ namespace {
 template <typename T, int KB, int NQ>
 __global__ void __launch_bounds__(256) bank_write_reduce_kernel(const T* __restrict__ tn, const T* __restrict__ cg, int ldcg,
                                                                 int B, int Nt, int d, float* __restrict__ partial) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) float g[];  // [Nt][KB]
   const int c = threadIdx.x;
   const int ng = Nt * KB;                     // <= NQ * blockDim.x (checked by the launcher)
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(256) bank_write_apply_kernel(const float* __re
                                                                int n, float* __restrict__ bank_k,
                                                                float* __restrict__ bank_v,
                                                                long long* __restrict__ update_count, int v1) {
+  QV_PDL_ENTRY();
   float uclamp, rate, bclamp;
   if (v1) { uclamp = 0.1f; rate = 0.01f; bclamp = 1.0f; }                    // QAViT.py:217-224
   else { uclamp = 0.05f; bclamp = 0.5f; rate = (*update_count < 1000) ? 0.005f : 0.01f; }   // H:310-319
@@ -151,9 +153,9 @@ int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, in
   *n_partial = grid;
   const size_t smem = (size_t)Nt * kb * sizeof(float);
   if (Nt * kb <= 4 * 256) {
-    DISPATCH_T(dt, (bank_write_reduce_kernel<T, 16, 4><<<grid, 256, smem, s>>>((const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
+    DISPATCH_T(dt, (qv_launch(bank_write_reduce_kernel<T, 16, 4>, grid, 256, smem, s, (const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
   } else {
-    DISPATCH_T(dt, (bank_write_reduce_kernel<T, 16, 16><<<grid, 256, smem, s>>>((const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
+    DISPATCH_T(dt, (qv_launch(bank_write_reduce_kernel<T, 16, 16>, grid, 256, smem, s, (const T*)tn, (const T*)cg, ldcg, B, Nt, d, partial)));
   }
   QV_LAUNCH_CHECK();
   return 0;
@@ -161,7 +163,7 @@ int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, in
 
 int bank_write_apply(cudaStream_t s, const float* partial, int n_partial, int B, int d, int kb, float* bank_k,
                      float* bank_v, long long* update_count, int v1) {
-  bank_write_apply_kernel<<<cdiv(2 * kb * d, 32), 256, 0, s>>>(partial, n_partial, B, kb * d, bank_k, bank_v, update_count, v1);
+  qv_launch(bank_write_apply_kernel, cdiv(2 * kb * d, 32), 256, 0, s, partial, n_partial, B, kb * d, bank_k, bank_v, update_count, v1);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -183,6 +185,7 @@ __device__ __forceinline__ int msda_src(int m, int side, const DilP& dp) {
 template <typename T>
 __global__ void __launch_bounds__(256) msda_pool_fwd_kernel(const T* __restrict__ xn, int B, int Nt, int side, int C, DilP dp,
                                                             int stride, int NM, T* __restrict__ xp) {
+  QV_PDL_ENTRY();
   extern __shared__ int src[];   // [NM * stride]
   for (int i = threadIdx.x; i < NM * stride; i += blockDim.x) src[i] = msda_src(i, side, dp);
   __syncthreads();
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(256) msda_pool_fwd_kernel(const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) msda_pool_bwd_kernel(const T* __restrict__ dxp, int B, int Nt, int side, int C, DilP dp,
                                                             int stride, int NM, float* __restrict__ dxn) {
+  QV_PDL_ENTRY();
   extern __shared__ int src[];   // [NM * stride]
   for (int i = threadIdx.x; i < NM * stride; i += blockDim.x) src[i] = msda_src(i, side, dp);
   __syncthreads();
@@ -248,7 +252,7 @@ int msda_pool_fwd(cudaStream_t s, int dt, const void* xn, int B, int Nt, int sid
   if (total <= 0) return 0;
   QV_CHECK(C % 4 == 0, "msda pooling: C=%d must be a multiple of 4", C);
   const int grid = (int)max(1L, min((long)qv_num_sms() * 8, (total / 4 + 255) / 256));
-  DISPATCH_T(dt, (msda_pool_fwd_kernel<T><<<grid, 256, (size_t)NM * stride * sizeof(int), s>>>((const T*)xn, B, Nt, side, C, dp, stride, NM, (T*)xp)));
+  DISPATCH_T(dt, (qv_launch(msda_pool_fwd_kernel<T>, grid, 256, (size_t)NM * stride * sizeof(int), s, (const T*)xn, B, Nt, side, C, dp, stride, NM, (T*)xp)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -260,7 +264,7 @@ int msda_pool_bwd(cudaStream_t s, int dt, const void* dxp, int B, int Nt, int si
   if (B <= 0) return 0;
   QV_CHECK(C % 4 == 0, "msda pooling: C=%d must be a multiple of 4", C);
   const int grid = (int)max(1L, min((long)qv_num_sms() * 8, ((long)B * (C / 4) + 255) / 256));
-  DISPATCH_T(dt, (msda_pool_bwd_kernel<T><<<grid, 256, (size_t)NM * stride * sizeof(int), s>>>((const T*)dxp, B, Nt, side, C, dp, stride, NM, dxn)));
+  DISPATCH_T(dt, (qv_launch(msda_pool_bwd_kernel<T>, grid, 256, (size_t)NM * stride * sizeof(int), s, (const T*)dxp, B, Nt, side, C, dp, stride, NM, dxn)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -271,6 +275,7 @@ namespace {
 template <typename T>
 __global__ void dwconv_fwd_kernel(const T* __restrict__ x, int B, int side, int C, const float* __restrict__ w,
                                   const float* __restrict__ bias, const float* __restrict__ scale, T* __restrict__ y) {
+  QV_PDL_ENTRY();
   const int Nt = side * side;
   const long total = (long)B * Nt * C;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -300,6 +305,7 @@ __global__ void dwconv_bwd_kernel(const T* __restrict__ x, const T* __restrict__
                                   const float* __restrict__ w, const float* __restrict__ bias,
                                   const float* __restrict__ scale, T* __restrict__ dx, float* __restrict__ dw,
                                   float* __restrict__ dbias, float* __restrict__ dscale) {
+  QV_PDL_ENTRY();
   const int c = threadIdx.x;
   if (c >= C) return;
   const int Nt = side * side;
@@ -352,7 +358,7 @@ int dwconv_fwd(cudaStream_t s, int dt, const void* x, int B, int side, int C, co
     return dw2d_fwd(s, dt, p, false);
   }
   const int grid = (int)min((long)qv_num_sms() * 8, (total + 255) / 256);
-  DISPATCH_T(dt, (dwconv_fwd_kernel<T><<<grid, 256, 0, s>>>((const T*)x, B, side, C, w, bias, scale, (T*)y)));
+  DISPATCH_T(dt, (qv_launch(dwconv_fwd_kernel<T>, grid, 256, 0, s, (const T*)x, B, side, C, w, bias, scale, (T*)y)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -371,7 +377,7 @@ int dwconv_bwd(cudaStream_t s, int dt, const void* x, const void* dy, int B, int
   QV_CHECK(C <= 256, "dwconv_bwd: C=%d > 256", C);
   const int grid = min(B, qv_num_sms() * 8);
   const int threads = ((C + 31) / 32) * 32;
-  DISPATCH_T(dt, (dwconv_bwd_kernel<T><<<grid, threads, 0, s>>>((const T*)x, (const T*)dy, B, side, C, w, bias, scale,
+  DISPATCH_T(dt, (qv_launch(dwconv_bwd_kernel<T>, grid, threads, 0, s, (const T*)x, (const T*)dy, B, side, C, w, bias, scale,
                                                              (T*)dx, dw, dbias, dscale)));
   QV_LAUNCH_CHECK();
   return 0;
@@ -381,6 +387,7 @@ int dwconv_bwd(cudaStream_t s, int dt, const void* x, const void* dy, int B, int
 namespace {
 template <typename T>
 __global__ void gelu_bwd_kernel(const T* __restrict__ pre, const T* __restrict__ dact, long n, T* __restrict__ dpre) {
+  QV_PDL_ENTRY();
   for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (long)gridDim.x * blockDim.x * 2) {
     const float2 u = ld2(pre + i), g = ld2(dact + i);
     st2(dpre + i, make_float2(g.x * gelu_grad_f(u.x), g.y * gelu_grad_f(u.y)));
@@ -390,6 +397,7 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ pre, const T* __restrict__
 template <typename T>
 __global__ void gamma_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ o, long n,
                                  const float* __restrict__ gamma, T* __restrict__ d_o, float* __restrict__ dgamma) {
+  QV_PDL_ENTRY();
   __shared__ float red[32];
   const float g = *gamma;
   float acc = 0.f;
@@ -413,6 +421,7 @@ __global__ void __launch_bounds__(256) gamma_bwd_drop_kernel(const float* __rest
                                                              const float* __restrict__ gamma, T* __restrict__ d_o,
                                                              float* __restrict__ dgamma, DropP drop,
                                                              const float* __restrict__ rowscale, int rows_per_img, int C) {
+  QV_PDL_ENTRY();
   __shared__ float red[32];
   const float g = gamma ? *gamma : 1.f;
   const bool masked = drop.p > 0.f;
@@ -447,10 +456,12 @@ __global__ void __launch_bounds__(256) gamma_bwd_drop_kernel(const float* __rest
 }
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ x, long n, T* __restrict__ y) {
+  QV_PDL_ENTRY();
   for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (long)gridDim.x * blockDim.x * 2)
     st2(y + i, ld2(x + i));
 }
 __global__ void fusion_softmax_kernel(const float* w, int n, float* alpha) {
+  QV_PDL_ENTRY();
   if (threadIdx.x == 0) {
     float m = -INFINITY, z = 0.f;
     for (int i = 0; i < n; ++i) m = fmaxf(m, w[i]);
@@ -462,6 +473,7 @@ __global__ void fusion_softmax_kernel(const float* w, int n, float* alpha) {
 template <typename T>
 __global__ void __launch_bounds__(256) fusion_bwd_kernel(const T* __restrict__ df, const T* __restrict__ f, long rows, int nb, int cw,
                                                          float* __restrict__ raw) {
+  QV_PDL_ENTRY();
   __shared__ float red[4][8];
   const int C = nb * cw, v4 = C / 4;            // 4-element vectors never straddle a branch slice (cw % 4 == 0)
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -489,6 +501,7 @@ __global__ void __launch_bounds__(256) fusion_bwd_kernel(const T* __restrict__ d
 }
 // dalpha_i = raw_i / alpha_i ; dw_j += alpha_j (dalpha_j - sum_i alpha_i dalpha_i)
 __global__ void fusion_bwd_final_kernel(const float* alpha, const float* raw, int nb, float* dw) {
+  QV_PDL_ENTRY();
   if (threadIdx.x == 0) {
     float dot = 0.f;
     for (int i = 0; i < nb; ++i) dot += raw[i];   // alpha_i * (raw_i / alpha_i)
@@ -498,6 +511,7 @@ __global__ void fusion_bwd_final_kernel(const float* alpha, const float* raw, in
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ dY, int ldy, int M, int N, int rows_per_block,
                               float* __restrict__ db, const float* __restrict__ scale) {
+  QV_PDL_ENTRY();
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   const long r0 = (long)blockIdx.y * rows_per_block;
@@ -516,6 +530,7 @@ __global__ void colsum_kernel(const T* __restrict__ dY, int ldy, int M, int N, i
 }
 __global__ void convert_weight_kernel(const float* __restrict__ w, int N, int K, bf16* __restrict__ wb,
                                       bf16* __restrict__ wbt) {
+  QV_PDL_ENTRY();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * K) return;
   const bf16 v = __float2bfloat16_rn(w[idx]);
@@ -523,6 +538,7 @@ __global__ void convert_weight_kernel(const float* __restrict__ w, int N, int K,
   if (wbt) wbt[(long)(idx % K) * N + idx / K] = v;
 }
 __global__ void convert_weights_batched_kernel(ConvertJobs jobs) {
+  QV_PDL_ENTRY();
   const ConvertJob jb = jobs.j[blockIdx.y];
   const int total = jb.N * jb.K;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -536,7 +552,7 @@ int ew_grid(long n) { return (int)max(1L, min((long)qv_num_sms() * 8, (n / 2 + 2
 
 int gelu_bwd(cudaStream_t s, int dt, const void* pre, const void* dact, long n, void* dpre) {
   if (n <= 0) return 0;
-  DISPATCH_T(dt, (gelu_bwd_kernel<T><<<ew_grid(n), 256, 0, s>>>((const T*)pre, (const T*)dact, n, (T*)dpre)));
+  DISPATCH_T(dt, (qv_launch(gelu_bwd_kernel<T>, ew_grid(n), 256, 0, s, (const T*)pre, (const T*)dact, n, (T*)dpre)));
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -547,22 +563,22 @@ int gamma_bwd(cudaStream_t s, int dt, const float* dout, const void* o, long n, 
   if (dp.p > 0.f || rowscale || !gamma) {
     QV_CHECK(n % 8 == 0 && C > 0 && C % 8 == 0, "gamma_bwd: fused dropout needs C %% 8 == 0 (C = %d)", C);
     const int grid = (int)max(1L, min((long)qv_num_sms() * 16, (n / 8 + 255) / 256));
-    DISPATCH_T(dt, (gamma_bwd_drop_kernel<T><<<grid, 256, 0, s>>>(dout, (const T*)o, n, gamma, (T*)d_o, dgamma, dp, rowscale, rows_per_img, C)));
+    DISPATCH_T(dt, (qv_launch(gamma_bwd_drop_kernel<T>, grid, 256, 0, s, dout, (const T*)o, n, gamma, (T*)d_o, dgamma, dp, rowscale, rows_per_img, C)));
     QV_LAUNCH_CHECK();
     return 0;
   }
-  DISPATCH_T(dt, (gamma_bwd_kernel<T><<<ew_grid(n), 256, 0, s>>>(dout, (const T*)o, n, gamma, (T*)d_o, dgamma)));
+  DISPATCH_T(dt, (qv_launch(gamma_bwd_kernel<T>, ew_grid(n), 256, 0, s, dout, (const T*)o, n, gamma, (T*)d_o, dgamma)));
   QV_LAUNCH_CHECK();
   return 0;
 }
 int cast_f32_to_t(cudaStream_t s, int dt, const float* x, long n, void* y) {
   if (n <= 0) return 0;
-  DISPATCH_T(dt, (cast_kernel<T><<<ew_grid(n), 256, 0, s>>>(x, n, (T*)y)));
+  DISPATCH_T(dt, (qv_launch(cast_kernel<T>, ew_grid(n), 256, 0, s, x, n, (T*)y)));
   QV_LAUNCH_CHECK();
   return 0;
 }
 int fusion_softmax(cudaStream_t s, const float* w, int n, float* alpha) {
-  fusion_softmax_kernel<<<1, 32, 0, s>>>(w, n, alpha);
+  qv_launch(fusion_softmax_kernel, 1, 32, 0, s, w, n, alpha);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -572,12 +588,12 @@ int fusion_bwd(cudaStream_t s, int dt, const void* dfused, const void* fused, lo
   QV_CHECK(nb <= 4 && cw % 4 == 0, "fusion_bwd: %d branches (<= 4) of width %d (multiple of 4)", nb, cw);
   if (rows <= 0) return 0;
   const int grid = (int)max(1L, min((long)qv_num_sms() * 4, (rows * nb * cw + 255) / 256));
-  DISPATCH_T(dt, (fusion_bwd_kernel<T><<<grid, 256, 0, s>>>((const T*)dfused, (const T*)fused, rows, nb, cw, dalpha_raw)));
+  DISPATCH_T(dt, (qv_launch(fusion_bwd_kernel<T>, grid, 256, 0, s, (const T*)dfused, (const T*)fused, rows, nb, cw, dalpha_raw)));
   QV_LAUNCH_CHECK();
   return 0;
 }
 int fusion_bwd_final(cudaStream_t s, const float* alpha, const float* dalpha_raw, int nb, float* dw) {
-  fusion_bwd_final_kernel<<<1, 32, 0, s>>>(alpha, dalpha_raw, nb, dw);
+  qv_launch(fusion_bwd_final_kernel, 1, 32, 0, s, alpha, dalpha_raw, nb, dw);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -587,18 +603,18 @@ int colsum_accum(cudaStream_t s, int dt, const void* dY, int ldy, int M, int N, 
   int gy = max(1, min(cdiv(M, 64), cdiv(qv_num_sms() * 4, gx)));
   const int rpb = cdiv(M, gy);
   gy = cdiv(M, rpb);
-  DISPATCH_T(dt, (colsum_kernel<T><<<dim3(gx, gy), dim3(32, 8), 0, s>>>((const T*)dY, ldy, M, N, rpb, db, scale)));
+  DISPATCH_T(dt, (qv_launch(colsum_kernel<T>, dim3(gx, gy), dim3(32, 8), 0, s, (const T*)dY, ldy, M, N, rpb, db, scale)));
   QV_LAUNCH_CHECK();
   return 0;
 }
 int convert_weights_batched(cudaStream_t s, const ConvertJobs& jobs) {
   if (jobs.n <= 0) return 0;
-  convert_weights_batched_kernel<<<dim3(32, jobs.n), 256, 0, s>>>(jobs);
+  qv_launch(convert_weights_batched_kernel, dim3(32, jobs.n), 256, 0, s, jobs);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int convert_weight(cudaStream_t s, const float* w, int N, int K, bf16* wb, bf16* wbt) {
-  convert_weight_kernel<<<cdiv((long)N * K, 256), 256, 0, s>>>(w, N, K, wb, wbt);
+  qv_launch(convert_weight_kernel, cdiv((long)N * K, 256), 256, 0, s, w, N, K, wb, wbt);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -609,6 +625,7 @@ namespace {
 template <typename T>
 __global__ void token_learner_fwd_kernel(const float* __restrict__ x, const T* __restrict__ logits, int B, int N, int M,
                                          int C, float* __restrict__ S, float* __restrict__ xc) {
+  QV_PDL_ENTRY();
   extern __shared__ float sS[];  // [N][M]
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
@@ -645,6 +662,7 @@ template <typename T>
 __global__ void token_learner_bwd_kernel(const float* __restrict__ x, const float* __restrict__ S,
                                          const float* __restrict__ dxc, int B, int N, int M, int C,
                                          T* __restrict__ dlogits, float* __restrict__ dx) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   float* sS = sm;                 // [N][M]
   float* sdS = sS + N * M;        // [N][M]
@@ -691,6 +709,7 @@ __global__ void token_learner_bwd_kernel(const float* __restrict__ x, const floa
 __global__ void token_upmix_fwd_kernel(const float* __restrict__ xc, int B, int M, int N, int C,
                                        const float* __restrict__ W, const float* __restrict__ bias,
                                        float* __restrict__ up) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   float* sW = sm;            // [N][M]
   float* sX = sm + N * M;    // [M][C]
@@ -712,6 +731,7 @@ __global__ void token_upmix_fwd_kernel(const float* __restrict__ xc, int B, int 
 __global__ void token_upmix_bwd_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B, int M, int N,
                                        int C, const float* __restrict__ W, float* __restrict__ dxc,
                                        float* __restrict__ dW, float* __restrict__ dbias) {
+  QV_PDL_ENTRY();
   extern __shared__ float sm[];
   constexpr int NC = 16;                 // dup rows staged per pass
   float* sW = sm;                        // [N][M]
@@ -766,8 +786,8 @@ int token_learner_fwd(cudaStream_t s, int dt, const float* x, const void* logits
   QV_CHECK(M % 16 == 0, "token_learner: M=%d must be a multiple of 16", M);
   const size_t smem = (size_t)N * M * sizeof(float);
   const int grid = min(B, qv_num_sms() * 8);
-  if (dt == QV_F32) { QV_TRY(opt_in_smem(token_learner_fwd_kernel<float>, smem)); token_learner_fwd_kernel<float><<<grid, 192, smem, s>>>(x, (const float*)logits, B, N, M, C, S, xc); }
-  else { QV_TRY(opt_in_smem(token_learner_fwd_kernel<bf16>, smem)); token_learner_fwd_kernel<bf16><<<grid, 192, smem, s>>>(x, (const bf16*)logits, B, N, M, C, S, xc); }
+  if (dt == QV_F32) { QV_TRY(opt_in_smem(token_learner_fwd_kernel<float>, smem)); qv_launch(token_learner_fwd_kernel<float>, grid, 192, smem, s, x, (const float*)logits, B, N, M, C, S, xc); }
+  else { QV_TRY(opt_in_smem(token_learner_fwd_kernel<bf16>, smem)); qv_launch(token_learner_fwd_kernel<bf16>, grid, 192, smem, s, x, (const bf16*)logits, B, N, M, C, S, xc); }
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -780,8 +800,8 @@ int token_learner_bwd(cudaStream_t s, int dt, const float* x, const float* S, co
   QV_CHECK(C <= 256, "token_learner_bwd: C=%d > 256", C);
   const size_t smem = (size_t)(2 * N * M + M * (C + 1) + M) * sizeof(float);
   const int grid = min(B, qv_num_sms() * 4);
-  if (dt == QV_F32) { QV_TRY(opt_in_smem(token_learner_bwd_kernel<float>, smem)); token_learner_bwd_kernel<float><<<grid, 256, smem, s>>>(x, S, dxc, B, N, M, C, (float*)dlogits, dx); }
-  else { QV_TRY(opt_in_smem(token_learner_bwd_kernel<bf16>, smem)); token_learner_bwd_kernel<bf16><<<grid, 256, smem, s>>>(x, S, dxc, B, N, M, C, (bf16*)dlogits, dx); }
+  if (dt == QV_F32) { QV_TRY(opt_in_smem(token_learner_bwd_kernel<float>, smem)); qv_launch(token_learner_bwd_kernel<float>, grid, 256, smem, s, x, S, dxc, B, N, M, C, (float*)dlogits, dx); }
+  else { QV_TRY(opt_in_smem(token_learner_bwd_kernel<bf16>, smem)); qv_launch(token_learner_bwd_kernel<bf16>, grid, 256, smem, s, x, S, dxc, B, N, M, C, (bf16*)dlogits, dx); }
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -792,7 +812,7 @@ int token_upmix_fwd(cudaStream_t s, int dt, const float* xc, int B, int M, int N
   if (tokens16_ok(M, C)) return up16_fwd(s, xc, B, N, C, W, bias, up);
   const size_t smem = (size_t)(N * M + M * C) * sizeof(float);
   QV_TRY(opt_in_smem(token_upmix_fwd_kernel, smem));
-  token_upmix_fwd_kernel<<<min(B, qv_num_sms() * 4), 192, smem, s>>>(xc, B, M, N, C, W, bias, up);
+  qv_launch(token_upmix_fwd_kernel, min(B, qv_num_sms() * 4), 192, smem, s, xc, B, M, N, C, W, bias, up);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -805,7 +825,7 @@ int token_upmix_bwd(cudaStream_t s, int dt, const float* xc, const float* dup, i
   QV_CHECK(N % 16 == 0, "token_upmix_bwd: N=%d must be a multiple of 16", N);
   const size_t smem = (size_t)(N * M + M * (C + 1) + 16 * (C + 1)) * sizeof(float);
   QV_TRY(opt_in_smem(token_upmix_bwd_kernel, smem));
-  token_upmix_bwd_kernel<<<min(B, qv_num_sms() * 4), 192, smem, s>>>(xc, dup, B, M, N, C, W, dxc, dW, dbias);
+  qv_launch(token_upmix_bwd_kernel, min(B, qv_num_sms() * 4), 192, smem, s, xc, dup, B, M, N, C, W, dxc, dW, dbias);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, i
                                                      float eps, const float* __restrict__ gamma2,
                                                      const float* __restrict__ beta2, TO* __restrict__ y, int ldy,
                                                      float* __restrict__ stats) {
+  QV_PDL_ENTRY();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int c0 = lane * EPL;
   const bool act = c0 < C;
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const TX* __restrict__ x
                                                      float* __restrict__ dx_f32, const float* __restrict__ resid,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, DropP drop,
                                                      const float* __restrict__ rowscale, int rows_per_img) {
+  QV_PDL_ENTRY();
   __shared__ float red[2][8][256];
   const bool masked = EPL == 8 && drop.p > 0.f, scaled = EPL == 8 && rowscale != nullptr;
   DropState dst{};
@@ -155,7 +157,7 @@ int ln_fwd(cudaStream_t s, int dt_in, const void* x, int ldx, int rows, int C, c
   QV_CHECK(C <= 256 && C % epl == 0 && ldx % epl == 0 && ldy % epl == 0, "ln_fwd: C=%d ldx=%d ldy=%d unsupported", C, ldx, ldy);
   const int grid = max(1, min(cdiv(rows, 8), qv_num_sms() * 8));
 #define LN_F3(TI, TO, E, G) \
-  ln_fwd_kernel<TI, TO, E, G><<<grid, 256, 0, s>>>((const TI*)x, ldx, rows, C, gamma, beta, eps, gamma2, beta2, (TO*)y, ldy, stats)
+  qv_launch(ln_fwd_kernel<TI, TO, E, G>, grid, 256, 0, s, (const TI*)x, ldx, rows, C, gamma, beta, eps, gamma2, beta2, (TO*)y, ldy, stats)
 #define LN_F2(TI, TO, G) do { if (epl == 8) LN_F3(TI, TO, 8, G); else LN_F3(TI, TO, 4, G); } while (0)
 #define LN_F(TI, TO) do { if (gelu_in) LN_F2(TI, TO, true); else LN_F2(TI, TO, false); } while (0)
   if (dt_in == QV_F32 && dt_out == QV_F32) LN_F(float, float);
@@ -181,7 +183,7 @@ int ln_bwd(cudaStream_t s, int dt_x, const void* x, int ldx, int dt_dy, const vo
   // every CTA ends with 2 * C atomics: keep >= 32 rows per warp before adding CTAs
   const int grid = max(1, min(cdiv(rows, 8 * 32), qv_num_sms() * 6));
 #define LN_B4(TX, TDY, TO, E, G)                                                                                      \
-  ln_bwd_kernel<TX, TDY, TO, E, G><<<grid, 256, 0, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, rows, C, gamma, stats, \
+  qv_launch(ln_bwd_kernel<TX, TDY, TO, E, G>, grid, 256, 0, s, (const TX*)x, ldx, (const TDY*)dy, lddy, rows, C, gamma, stats, \
                                                         (TO*)dx_t, dx_f32, resid, dgamma, dbeta, dp, rowscale, rows_per_img)
 #define LN_B3(TX, TDY, TO, G) do { if (epl == 8) LN_B4(TX, TDY, TO, 8, G); else LN_B4(TX, TDY, TO, 4, G); } while (0)
 #define LN_B2(TX, TDY, TO) do { if (gelu_in) LN_B3(TX, TDY, TO, true); else LN_B3(TX, TDY, TO, false); } while (0)

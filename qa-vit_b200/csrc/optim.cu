@@ -21,6 +21,7 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // norms[s] = ||g_s||_2, one CTA per segment
 __global__ void __launch_bounds__(256) seg_norm_kernel(const float* __restrict__ g, const long long* __restrict__ off,
                                                        const int* __restrict__ flags, float* __restrict__ norms) {
+  QV_PDL_ENTRY();
   __shared__ float red[32];
   const int s = blockIdx.x;
   float acc = 0.f;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(256) seg_norm_kernel(const float* __restrict__
 // ranks): norms are taken of prescale * g and the factor is folded into the per-segment scale, so no separate division pass.
 __global__ void __launch_bounds__(1024) clip_coef_kernel(const int* __restrict__ flags, int n, float per_param_max,
                                                          float max_norm, float prescale, float* __restrict__ norms) {
+  QV_PDL_ENTRY();
   __shared__ float red[32];
   __shared__ float gcoef;
   float acc = 0.f;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(1024) clip_coef_kernel(const int* __restrict__
   for (int s = threadIdx.x; s < n; s += blockDim.x) norms[s] *= gcoef * prescale;
 }
 __global__ void scaled_copy_kernel(const float* __restrict__ x, float scale, long n, float* __restrict__ y) {
+  QV_PDL_ENTRY();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = x[i] * scale;
 }
 
@@ -77,6 +80,7 @@ __device__ __forceinline__ int find_seg(const long long* __restrict__ off, int n
 __global__ void __launch_bounds__(256) scale_grads_kernel(float* __restrict__ g, const long long* __restrict__ off,
                                                           const int* __restrict__ flags, int n,
                                                           const float* __restrict__ scale, long long total) {
+  QV_PDL_ENTRY();
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
     const int s = find_seg(off, n, i);
     if (!(flags[s] & 1)) continue;
@@ -95,6 +99,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float* __restrict__ v, float* __restrict__ ema, const long long* __restrict__ off,
                                                     const int* __restrict__ flags, int n, const float* __restrict__ hyper,
                                                     long long total) {
+  QV_PDL_ENTRY();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], bc1 = hyper[5], bc2 = hyper[6];
   const float step = lr / bc1, rs2 = rsqrtf(bc2), decay = 1.f - lr * wd;
   const float ed = EMA ? hyper[7] : 0.f, ec = EMA ? hyper[8] : 0.f;
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 __global__ void __launch_bounds__(256) batch_mix_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                         const long long* __restrict__ perm, int B, int C, int H, int W, int mode,
                                                         int x1, int y1, int x2, int y2, float lam, float lb) {
+  QV_PDL_ENTRY();
   const long long per = (long long)C * H * W, total = (long long)B * per;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long b = i / per, r = i % per;
@@ -163,6 +169,7 @@ __global__ void __launch_bounds__(256) batch_mix_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) normalize_images_kernel(const void* __restrict__ in, int in_kind, int B, int C, int H, int W,
                                                                const float* __restrict__ mean, const float* __restrict__ stdv, int hflip,
                                                                float* __restrict__ out) {
+  QV_PDL_ENTRY();
   const long long total = (long long)B * C * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % C);
@@ -185,7 +192,7 @@ extern "C" int qavit_normalize_images(const void* in, int in_kind, int B, int C,
   const long long total = (long long)B * C * H * W;
   if (total <= 0) return 0;
   const int grid = (int)max(1LL, min((long long)qv_num_sms() * 16, (total + 255) / 256));
-  normalize_images_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_kind, B, C, H, W, mean, stdv, hflip, out);
+  qv_launch(normalize_images_kernel, grid, 256, 0, (cudaStream_t)stream, in, in_kind, B, C, H, W, mean, stdv, hflip, out);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -193,7 +200,7 @@ extern "C" int qavit_normalize_images(const void* in, int in_kind, int B, int C,
 extern "C" int qavit_scaled_copy(const float* x, float scale, long long n, float* y, void* stream) {
   QV_CHECK(x && y, "scaled_copy: null argument");
   if (n <= 0) return 0;
-  scaled_copy_kernel<<<(int)max(1LL, min((long long)qv_num_sms() * 8, (n + 255) / 256)), 256, 0, (cudaStream_t)stream>>>(x, scale, (long)n, y);
+  qv_launch(scaled_copy_kernel, (int)max(1LL, min((long long)qv_num_sms() * 8, (n + 255) / 256)), 256, 0, (cudaStream_t)stream, x, scale, (long)n, y);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -207,12 +214,12 @@ extern "C" int qavit_clip_grads_scaled(float* grads, const long long* seg_off, c
                                        float max_norm, float prescale, float* norms, long long total, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n_seg <= 0) return 0;
-  seg_norm_kernel<<<n_seg, 256, 0, s>>>(grads, seg_off, seg_flags, norms);
+  qv_launch(seg_norm_kernel, n_seg, 256, 0, s, grads, seg_off, seg_flags, norms);
   QV_LAUNCH_CHECK();
-  clip_coef_kernel<<<1, 1024, 0, s>>>(seg_flags, n_seg, per_param_max, max_norm, prescale, norms);
+  qv_launch(clip_coef_kernel, 1, 1024, 0, s, seg_flags, n_seg, per_param_max, max_norm, prescale, norms);
   QV_LAUNCH_CHECK();
   const int grid = (int)max(1LL, min((long long)qv_num_sms() * 8, (total / 4 + 255) / 256));
-  scale_grads_kernel<<<grid, 256, 0, s>>>(grads, seg_off, seg_flags, n_seg, norms, total);
+  qv_launch(scale_grads_kernel, grid, 256, 0, s, grads, seg_off, seg_flags, n_seg, norms, total);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -222,7 +229,7 @@ extern "C" int qavit_adamw_step(float* params, const float* grads, float* exp_av
   cudaStream_t s = (cudaStream_t)stream;
   if (n_seg <= 0) return 0;
   const int grid = (int)max(1LL, min((long long)qv_num_sms() * 8, (total / 4 + 255) / 256));
-  adamw_kernel<false><<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, nullptr, seg_off, seg_flags, n_seg, hyper, total);
+  qv_launch(adamw_kernel<false>, grid, 256, 0, s, params, grads, exp_avg, exp_avg_sq, nullptr, seg_off, seg_flags, n_seg, hyper, total);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -234,7 +241,7 @@ extern "C" int qavit_adamw_ema_step(float* params, const float* grads, float* ex
   if (n_seg <= 0) return 0;
   QV_CHECK(ema, "adamw_ema_step: ema buffer missing");
   const int grid = (int)max(1LL, min((long long)qv_num_sms() * 8, (total / 4 + 255) / 256));
-  adamw_kernel<true><<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, ema, seg_off, seg_flags, n_seg, hyper, total);
+  qv_launch(adamw_kernel<true>, grid, 256, 0, s, params, grads, exp_avg, exp_avg_sq, ema, seg_off, seg_flags, n_seg, hyper, total);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -242,7 +249,7 @@ extern "C" int qavit_adamw_ema_step(float* params, const float* grads, float* ex
 extern "C" int qavit_segment_norms(const float* buf, const long long* seg_off, const int* seg_flags, int n_seg, float* norms,
                                    void* stream) {
   if (n_seg <= 0) return 0;
-  seg_norm_kernel<<<n_seg, 256, 0, (cudaStream_t)stream>>>(buf, seg_off, seg_flags, norms);
+  qv_launch(seg_norm_kernel, n_seg, 256, 0, (cudaStream_t)stream, buf, seg_off, seg_flags, norms);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -254,7 +261,7 @@ extern "C" int qavit_batch_mix(const float* in, float* out, const long long* per
   const long long total = (long long)B * C * H * W;
   if (total <= 0) return 0;
   const int grid = (int)max(1LL, min((long long)qv_num_sms() * 16, (total + 255) / 256));
-  batch_mix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, perm, B, C, H, W, mode, x1, y1, x2, y2, lam, lam_b);
+  qv_launch(batch_mix_kernel, grid, 256, 0, (cudaStream_t)stream, in, out, perm, B, C, H, W, mode, x1, y1, x2, y2, lam, lam_b);
   QV_LAUNCH_CHECK();
   return 0;
 }

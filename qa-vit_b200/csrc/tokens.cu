@@ -20,6 +20,7 @@ int opt_in(K kernel, size_t bytes) {
 template <typename T, int CT>
 __global__ void __launch_bounds__(192) tl16_fwd_kernel(const float* __restrict__ x, const T* __restrict__ logits, int B, int N,
                                                        int Crt, float* __restrict__ S, float* __restrict__ xc) {
+  QV_PDL_ENTRY();
   const int C = CT ? CT : Crt;
   extern __shared__ __align__(16) float sS[];   // [N][16]
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -82,6 +83,7 @@ template <typename T, int CT>
 __global__ void __launch_bounds__(256) tl16_bwd_kernel(const float* __restrict__ x, const float* __restrict__ S,
                                                        const float* __restrict__ dxc, int B, int N, int Crt,
                                                        T* __restrict__ dlogits, float* __restrict__ dx) {
+  QV_PDL_ENTRY();
   const int C = CT ? CT : Crt;
   extern __shared__ __align__(16) float sm[];
   constexpr int RC = 64;                          // tokens staged per pass
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(256) tl16_bwd_kernel(const float* __restrict__
 __global__ void __launch_bounds__(192) up16_fwd_kernel(const float* __restrict__ xc, int B, int N, int C,
                                                        const float* __restrict__ W, const float* __restrict__ bias,
                                                        float* __restrict__ up) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) float sW[];    // [N][16] then bias [N]
   float* sb = sW + N * M16;
   for (int idx = threadIdx.x; idx < N * M16; idx += blockDim.x) sW[idx] = W[idx];
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(192) up16_fwd_kernel(const float* __restrict__
 // dxc[b, m, c] = sum_n W[n, m] dup[b, n, c]
 __global__ void __launch_bounds__(192) up16_dx_kernel(const float* __restrict__ dup, int B, int N, int C,
                                                       const float* __restrict__ W, float* __restrict__ dxc) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) float sW[];    // [N][16]
   for (int idx = threadIdx.x; idx < N * M16; idx += blockDim.x) sW[idx] = W[idx];
   __syncthreads();
@@ -218,6 +222,7 @@ __global__ void __launch_bounds__(192) up16_dx_kernel(const float* __restrict__ 
 template <int CT>
 __global__ void __launch_bounds__(256) up16_dw_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B, int N,
                                                       int Crt, float* __restrict__ dW, float* __restrict__ dbias) {
+  QV_PDL_ENTRY();
   const int C = CT ? CT : Crt;
   extern __shared__ __align__(16) float sm[];
   constexpr int RC = 64;
@@ -271,7 +276,7 @@ bool tokens16_ok(int M, int C) { return M == 16 && C % 4 == 0 && C <= 1024; }
 
 int tl16_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, int N, int C, float* S, float* xc) {
   const size_t smem = (size_t)N * M16 * sizeof(float);
-#define TLF(T, CT) do { QV_TRY(opt_in(tl16_fwd_kernel<T, CT>, smem)); tl16_fwd_kernel<T, CT><<<B, 192, smem, s>>>(x, (const T*)logits, B, N, C, S, xc); } while (0)
+#define TLF(T, CT) do { QV_TRY(opt_in(tl16_fwd_kernel<T, CT>, smem)); qv_launch(tl16_fwd_kernel<T, CT>, B, 192, smem, s, x, (const T*)logits, B, N, C, S, xc); } while (0)
   if (dt == QV_F32) { if (C == 192) TLF(float, 192); else TLF(float, 0); }
   else { if (C == 192) TLF(bf16, 192); else TLF(bf16, 0); }
 #undef TLF
@@ -280,7 +285,7 @@ int tl16_fwd(cudaStream_t s, int dt, const float* x, const void* logits, int B, 
 }
 int tl16_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx) {
   const size_t smem = (size_t)(2 * N * M16 + C * M16 + M16 + 64 * (C + 1)) * sizeof(float);
-#define TLB(T, CT) do { QV_TRY(opt_in(tl16_bwd_kernel<T, CT>, smem)); tl16_bwd_kernel<T, CT><<<B, 256, smem, s>>>(x, S, dxc, B, N, C, (T*)dlogits, dx); } while (0)
+#define TLB(T, CT) do { QV_TRY(opt_in(tl16_bwd_kernel<T, CT>, smem)); qv_launch(tl16_bwd_kernel<T, CT>, B, 256, smem, s, x, S, dxc, B, N, C, (T*)dlogits, dx); } while (0)
   if (dt == QV_F32) { if (C == 192) TLB(float, 192); else TLB(float, 0); }
   else { if (C == 192) TLB(bf16, 192); else TLB(bf16, 0); }
 #undef TLB
@@ -290,7 +295,7 @@ int tl16_bwd(cudaStream_t s, int dt, const float* x, const float* S, const float
 int up16_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W, const float* bias, float* up) {
   const size_t smem = (size_t)(N * M16 + N) * sizeof(float);
   QV_TRY(opt_in(up16_fwd_kernel, smem));
-  up16_fwd_kernel<<<min(B, qv_num_sms() * 16), 192, smem, s>>>(xc, B, N, C, W, bias, up);
+  qv_launch(up16_fwd_kernel, min(B, qv_num_sms() * 16), 192, smem, s, xc, B, N, C, W, bias, up);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -298,13 +303,13 @@ int up16_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, in
              float* dbias) {
   size_t smem = (size_t)N * M16 * sizeof(float);
   QV_TRY(opt_in(up16_dx_kernel, smem));
-  up16_dx_kernel<<<min(B, qv_num_sms() * 16), 192, smem, s>>>(dup, B, N, C, W, dxc);
+  qv_launch(up16_dx_kernel, min(B, qv_num_sms() * 16), 192, smem, s, dup, B, N, C, W, dxc);
   QV_LAUNCH_CHECK();
   smem = (size_t)(N * M16 + ((N + 3) & ~3) + C * M16 + 64 * (C + 1)) * sizeof(float);
   const int occ = max(1, (int)(220 * 1024 / (smem + 1024)));
   const int grid = min(B, qv_num_sms() * min(occ, 4));
-  if (C == 192) { QV_TRY(opt_in(up16_dw_kernel<192>, smem)); up16_dw_kernel<192><<<grid, 256, smem, s>>>(xc, dup, B, N, C, dW, dbias); }
-  else { QV_TRY(opt_in(up16_dw_kernel<0>, smem)); up16_dw_kernel<0><<<grid, 256, smem, s>>>(xc, dup, B, N, C, dW, dbias); }
+  if (C == 192) { QV_TRY(opt_in(up16_dw_kernel<192>, smem)); qv_launch(up16_dw_kernel<192>, grid, 256, smem, s, xc, dup, B, N, C, dW, dbias); }
+  else { QV_TRY(opt_in(up16_dw_kernel<0>, smem)); qv_launch(up16_dw_kernel<0>, grid, 256, smem, s, xc, dup, B, N, C, dW, dbias); }
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(FNT, 2) tlf_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ beta, const float* __restrict__ W,
                                                          const float* __restrict__ bias, float eps, float* __restrict__ Sout,
                                                          float* __restrict__ Zout, float* __restrict__ xc) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   Carve cv(smraw);
   bf16* X = cv.take<bf16>(FMAXN * FXP); bf16* XL = cv.take<bf16>(FMAXN * FXP);
@@ -338,6 +339,7 @@ __global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ W, float eps, float* __restrict__ dx,
                                                          float* __restrict__ dW, float* __restrict__ dbias,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   Carve cv(smraw);
   bf16* X = cv.take<bf16>(FMAXN * FXP); bf16* XL = cv.take<bf16>(FMAXN * FXP);
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(FNT, 2) upf_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, float* __restrict__ out,
                                                          float* __restrict__ stats) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   Carve cv(smraw);
   bf16* Wu = cv.take<bf16>(FMAXN * FSP); bf16* WuL = cv.take<bf16>(FMAXN * FSP);   // [token][slot]
@@ -647,6 +650,7 @@ __global__ void __launch_bounds__(FNT, 1) upf_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ bias, const float* __restrict__ gamma,
                                                          float* __restrict__ dxc, float* __restrict__ dW, float* __restrict__ dgamma,
                                                          float* __restrict__ dbeta) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   Carve cv(smraw);
   bf16* Wu = cv.take<bf16>(FMAXN * FSP); bf16* WuL = cv.take<bf16>(FMAXN * FSP);   // [token][slot]
@@ -840,7 +844,7 @@ int tlf_fwd(cudaStream_t s, const float* x, int B, int N, const float* gamma, co
             float eps, float* S, float* Z, float* xc) {
   if (B <= 0) return 0;
   QV_TRY(opt_in(tlf_fwd_kernel, TLF_FWD_SMEM));
-  tlf_fwd_kernel<<<grid_for(B, 2), FNT, TLF_FWD_SMEM, s>>>(x, B, N, gamma, beta, W, bias, eps, S, Z, xc);
+  qv_launch(tlf_fwd_kernel, grid_for(B, 2), FNT, TLF_FWD_SMEM, s, x, B, N, gamma, beta, W, bias, eps, S, Z, xc);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -848,7 +852,7 @@ int tlf_bwd(cudaStream_t s, const float* x, const float* S, const float* Z, cons
             const float* beta, const float* W, float eps, float* dx, float* dW, float* dbias, float* dgamma, float* dbeta) {
   if (B <= 0) return 0;
   QV_TRY(opt_in(tlf_bwd_kernel, TLF_BWD_SMEM));
-  tlf_bwd_kernel<<<grid_for(B, 2), FNT, TLF_BWD_SMEM, s>>>(x, S, Z, dxc, B, N, gamma, beta, W, eps, dx, dW, dbias, dgamma, dbeta);
+  qv_launch(tlf_bwd_kernel, grid_for(B, 2), FNT, TLF_BWD_SMEM, s, x, S, Z, dxc, B, N, gamma, beta, W, eps, dx, dW, dbias, dgamma, dbeta);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -856,7 +860,7 @@ int upf_fwd(cudaStream_t s, const float* xc, int B, int N, const float* W, const
             float eps, float* out, float* stats) {
   if (B <= 0) return 0;
   QV_TRY(opt_in(upf_fwd_kernel, UPF_FWD_SMEM));
-  upf_fwd_kernel<<<grid_for(B, 2), FNT, UPF_FWD_SMEM, s>>>(xc, B, N, W, bias, gamma, beta, eps, out, stats);
+  qv_launch(upf_fwd_kernel, grid_for(B, 2), FNT, UPF_FWD_SMEM, s, xc, B, N, W, bias, gamma, beta, eps, out, stats);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -864,7 +868,7 @@ int upf_bwd(cudaStream_t s, const float* xc, const float* dout, const float* sta
             const float* gamma, float* dxc, float* dW, float* dgamma, float* dbeta) {
   if (B <= 0) return 0;
   QV_TRY(opt_in(upf_bwd_kernel, UPF_BWD_SMEM));
-  upf_bwd_kernel<<<grid_for(B, 1), FNT, UPF_BWD_SMEM, s>>>(xc, dout, stats, B, N, W, bias, gamma, dxc, dW, dgamma, dbeta);
+  qv_launch(upf_bwd_kernel, grid_for(B, 1), FNT, UPF_BWD_SMEM, s, xc, dout, stats, B, N, W, bias, gamma, dxc, dW, dgamma, dbeta);
   QV_LAUNCH_CHECK();
   return 0;
 }

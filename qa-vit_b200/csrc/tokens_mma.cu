@@ -144,6 +144,7 @@ size_t smem_bytes(int N, int C, bool hl, bool needX = true, bool needD = true) {
 // ---------------------------------------------------------------------------------------------- TokenLearner forward
 __global__ void __launch_bounds__(NWARP * 32) tlm_fwd_kernel(const float* __restrict__ x, const bf16* __restrict__ logits, int B, int N,
                                                              int C, float* __restrict__ Sout, float* __restrict__ xc) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
   Smem sm = carve(smraw, N, XP, true, true, false);
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(NWARP * 32) tlm_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(NWARP * 32) tlm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ S,
                                                              const float* __restrict__ dxc, int B, int N, int C,
                                                              bf16* __restrict__ dlogits, float* __restrict__ dx) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
   Smem sm = carve(smraw, N, XP, false);
@@ -302,6 +304,7 @@ __global__ void __launch_bounds__(NWARP * 32) tlm_bwd_kernel(const float* __rest
 __global__ void __launch_bounds__(NWARP * 32) upm_fwd_kernel(const float* __restrict__ xc, int B, int N, int C,
                                                              const float* __restrict__ W, const float* __restrict__ bias,
                                                              float* __restrict__ up) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
   Smem sm = carve(smraw, N, XP, true, false, true);
@@ -339,6 +342,7 @@ __global__ void __launch_bounds__(NWARP * 32) upm_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(NWARP * 32) upm_bwd_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B,
                                                              int N, int C, const float* __restrict__ W, float* __restrict__ dxc,
                                                              float* __restrict__ dW, float* __restrict__ dbias) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
   Smem sm = carve(smraw, N, XP, false);
@@ -453,6 +457,7 @@ __device__ __forceinline__ void tile_to_bf16_cols(bf16* dhi, bf16* dlo, int pitc
 // ---- TokenLearner forward: xc[MS, C] = softmax_tokens(logits)^T x          (split-precision operands)
 __global__ void __launch_bounds__(NW64 * 32) tlm64_fwd_kernel(const float* __restrict__ x, const bf16* __restrict__ logits, int B, int N,
                                                                int MS, int C, float* __restrict__ Sout, float* __restrict__ xc) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int CH = C / 2, XPc = CH + 8;
   bf16* S = reinterpret_cast<bf16*>(smraw);                    // [N][MSP] hi, lo
@@ -534,6 +539,7 @@ __global__ void __launch_bounds__(NW64 * 32) tlm64_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(NW64 * 32) upm64_fwd_kernel(const float* __restrict__ xc, int B, int N, int MS, int C,
                                                                const float* __restrict__ W, const float* __restrict__ bias,
                                                                float* __restrict__ up) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
   bf16* S = reinterpret_cast<bf16*>(smraw);                    // W hi, lo [N][MSP]
@@ -576,6 +582,7 @@ __global__ void __launch_bounds__(NW64 * 32) upm64_fwd_kernel(const float* __res
 __global__ void __launch_bounds__(NW64 * 32) tlm64_bwd_kernel(const float* __restrict__ x, const float* __restrict__ Sg,
                                                                const float* __restrict__ dxc, int B, int N, int MS, int C,
                                                                bf16* __restrict__ dlogits, float* __restrict__ dx) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = C + 8;
   bf16* X = reinterpret_cast<bf16*>(smraw);                    // x [N][XP]
@@ -670,6 +677,7 @@ __global__ void __launch_bounds__(NW64 * 32) tlm64_bwd_kernel(const float* __res
 __global__ void __launch_bounds__(NW64 * 32) upm64_bwd_kernel(const float* __restrict__ xc, const float* __restrict__ dup, int B, int N,
                                                                int MS, int C, const float* __restrict__ W, float* __restrict__ dxc,
                                                                float* __restrict__ dW, float* __restrict__ dbias) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int CH = C / 2, XPc = CH + 8;
   bf16* S = reinterpret_cast<bf16*>(smraw);                    // W [N][MSP]
@@ -742,6 +750,7 @@ __global__ void __launch_bounds__(NW64 * 32) upm64_bwd_kernel(const float* __res
 // the accumulator fragments stay in registers across all images of the CTA and leave once as the CTA's partial sum.
 __global__ void __launch_bounds__(NWARP * 32) bwr_mma_kernel(const bf16* __restrict__ tn, const bf16* __restrict__ cg, int ldcg, int B,
                                                              int Nt, int d, float* __restrict__ partial) {
+  QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int XP = 2 * d + 8;
   bf16* sX = reinterpret_cast<bf16*>(smraw);                  // [Nt][XP]  [c | tn]
@@ -853,21 +862,21 @@ int tlm64_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, 
   const size_t ub = max((size_t)N * M * 4, (size_t)2 * N * XPc * 2);
   const size_t smem = (size_t)2 * N * MSP * 2 + ((ub + 15) & ~(size_t)15) + 16 * M16 * 4 + 16;
   QV_TRY(opt_in(tlm64_fwd_kernel, smem));
-  tlm64_fwd_kernel<<<tok_grid(B, smem), NW64 * 32, smem, s>>>(x, (const bf16*)logits, B, N, M, C, S, xc);
+  qv_launch(tlm64_fwd_kernel, tok_grid(B, smem), NW64 * 32, smem, s, x, (const bf16*)logits, B, N, M, C, S, xc);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int tlm64_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int M, int C, void* dlogits, float* dx) {
   const size_t smem = ((size_t)N * (C + 8) + (size_t)M * (C + 8) + (size_t)N * MSP) * 2 + (size_t)M * 4 + 16;
   QV_TRY(opt_in(tlm64_bwd_kernel, smem));
-  tlm64_bwd_kernel<<<tok_grid(B, smem), NW64 * 32, smem, s>>>(x, S, dxc, B, N, M, C, (bf16*)dlogits, dx);
+  qv_launch(tlm64_bwd_kernel, tok_grid(B, smem), NW64 * 32, smem, s, x, S, dxc, B, N, M, C, (bf16*)dlogits, dx);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int upm64_fwd(cudaStream_t s, const float* xc, int B, int N, int M, int C, const float* W, const float* bias, float* up) {
   const size_t smem = ((size_t)2 * N * MSP + (size_t)2 * M * (C + 8)) * 2 + (size_t)N * 4 + 16;
   QV_TRY(opt_in(upm64_fwd_kernel, smem));
-  upm64_fwd_kernel<<<tok_grid(B, smem), NW64 * 32, smem, s>>>(xc, B, N, M, C, W, bias, up);
+  qv_launch(upm64_fwd_kernel, tok_grid(B, smem), NW64 * 32, smem, s, xc, B, N, M, C, W, bias, up);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -876,7 +885,7 @@ int upm64_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, i
   const int XPc = C / 2 + 8;
   const size_t smem = ((size_t)N * MSP + (size_t)N * XPc + (size_t)M * XPc) * 2 + ((size_t)N * M + N) * 4 + 16;
   QV_TRY(opt_in(upm64_bwd_kernel, smem));
-  upm64_bwd_kernel<<<tok_grid(B, smem), NW64 * 32, smem, s>>>(xc, dup, B, N, M, C, W, dxc, dW, dbias);
+  qv_launch(upm64_bwd_kernel, tok_grid(B, smem), NW64 * 32, smem, s, xc, dup, B, N, M, C, W, dxc, dW, dbias);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -884,21 +893,21 @@ int upm64_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, i
 int tlm_fwd(cudaStream_t s, const float* x, const void* logits, int B, int N, int C, float* S, float* xc) {
   const size_t smem = smem_bytes(N, C, true, true, false);
   QV_TRY(opt_in(tlm_fwd_kernel, smem));
-  tlm_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, (const bf16*)logits, B, N, C, S, xc);
+  qv_launch(tlm_fwd_kernel, tok_grid(B, smem), NWARP * 32, smem, s, x, (const bf16*)logits, B, N, C, S, xc);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int tlm_bwd(cudaStream_t s, const float* x, const float* S, const float* dxc, int B, int N, int C, void* dlogits, float* dx) {
   const size_t smem = smem_bytes(N, C, false);
   QV_TRY(opt_in(tlm_bwd_kernel, smem));
-  tlm_bwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(x, S, dxc, B, N, C, (bf16*)dlogits, dx);
+  qv_launch(tlm_bwd_kernel, tok_grid(B, smem), NWARP * 32, smem, s, x, S, dxc, B, N, C, (bf16*)dlogits, dx);
   QV_LAUNCH_CHECK();
   return 0;
 }
 int upm_fwd(cudaStream_t s, const float* xc, int B, int N, int C, const float* W, const float* bias, float* up) {
   const size_t smem = smem_bytes(N, C, true, false, true);
   QV_TRY(opt_in(upm_fwd_kernel, smem));
-  upm_fwd_kernel<<<tok_grid(B, smem), NWARP * 32, smem, s>>>(xc, B, N, C, W, bias, up);
+  qv_launch(upm_fwd_kernel, tok_grid(B, smem), NWARP * 32, smem, s, xc, B, N, C, W, bias, up);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -908,7 +917,7 @@ int upm_bwd(cudaStream_t s, const float* xc, const float* dup, int B, int N, int
   QV_TRY(opt_in(upm_bwd_kernel, smem));
   // the dW / dbias accumulators are flushed with atomics once per CTA: keep the CTA count moderate
   const int grid = max(1, min(B, qv_num_sms() * 3));
-  upm_bwd_kernel<<<grid, NWARP * 32, smem, s>>>(xc, dup, B, N, C, W, dxc, dW, dbias);
+  qv_launch(upm_bwd_kernel, grid, NWARP * 32, smem, s, xc, dup, B, N, C, W, dxc, dW, dbias);
   QV_LAUNCH_CHECK();
   return 0;
 }
@@ -922,7 +931,7 @@ int bank_write_reduce_mma(cudaStream_t s, const void* tn, const void* cg, int ld
   const int occ = max(1, min(4, (int)(200 * 1024 / (smem + 1024))));
   const int grid = max(1, min(cdiv(B, 2), min(592, qv_num_sms() * occ)));
   *n_partial = grid;
-  bwr_mma_kernel<<<grid, NWARP * 32, smem, s>>>((const bf16*)tn, (const bf16*)cg, ldcg, B, Nt, d, partial);
+  qv_launch(bwr_mma_kernel, grid, NWARP * 32, smem, s, (const bf16*)tn, (const bf16*)cg, ldcg, B, Nt, d, partial);
   QV_LAUNCH_CHECK();
   return 0;
 }

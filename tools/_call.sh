@@ -1,7 +1,6 @@
 mkdir -p gpurun_out/r2
-python -m pytest tests/test_gpu_dp.py tests/test_gpu_tokens_fused.py tests/test_gpu_live_reference.py -q -s > gpurun_out/r2/t06_dp.log 2>&1; tail -8 gpurun_out/r2/t06_dp.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2/bench06_n2.log 2>&1; tail -c 600 gpurun_out/r2/bench06_n2.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 3 --workload qavitv2_c100 --batch 256 > gpurun_out/r2/bench06_qavitv2_b256_n2.log 2>&1; tail -c 600 gpurun_out/r2/bench06_qavitv2_b256_n2.log
-python bench.py --gpus 1 --steps 20 --warmup 3 --workload qavitv2_c100 --batch 256 > gpurun_out/r2/bench06_qavitv2_b256_n1.log 2>&1; tail -c 400 gpurun_out/r2/bench06_qavitv2_b256_n1.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --no-graph > gpurun_out/r2/bench06_n2_nograph.log 2>&1; tail -c 400 gpurun_out/r2/bench06_n2_nograph.log
-timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python tools/profile_step.py --batch 8 --warmup 1 --dropout 0.1 --drop-path 0.1 > gpurun_out/r2/racecheck06.log 2>&1; tail -5 gpurun_out/r2/racecheck06.log
+for v in v1 v2; do
+QAVIT_LIB=$PWD/qa-vit_b200/libqavit_$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/r2/bench09_$v.log 2>&1; tail -c 1800 gpurun_out/r2/bench09_$v.log | grep -o '"ms_per_step": [0-9.]*' | head -1
+done
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/r2/bench09_v0.log 2>&1; tail -c 1800 gpurun_out/r2/bench09_v0.log | grep -o '"ms_per_step": [0-9.]*' | head -1
+QAVIT_PDL=0 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/r2/bench09_off.log 2>&1; tail -c 1800 gpurun_out/r2/bench09_off.log | grep -o '"ms_per_step": [0-9.]*' | head -1
