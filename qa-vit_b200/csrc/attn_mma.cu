@@ -1,15 +1,23 @@
 // Tensor-core attention for the 16-query problems of the quad block (bf16 runs): one WARP per (window, head) task,
-// mma.sync.m16n8k16 (bf16 x bf16 -> fp32) fed by ldmatrix from warp-private shared memory.
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32), every intermediate kept in registers.
 //
 // Why mma.sync and not tcgen05 here: a task is Q[16 x 48] against 48 (or 16) keys -- one m16 tile.  A 128-row UMMA
 // tile would have to stack 8 unrelated tasks block-diagonally (8x wasted MMA) and round-trip S/P through TMEM;
 // m16n8k16 matches the problem exactly and keeps S, P, dS in registers (SURVEY.md 7.2 hard part 3).  The SIMT kernels
 // in attn.cu stay as the fp32 parity path and for shapes outside this file's (nq = 16, L <= 16, k = 32, bank = 16).
 //
-//   forward : K' = E_k^T Ks, V' = E_v^T Vs (Linformer) -> Kf = [K'; bank_k] -> S = Q Kf^T -> softmax -> O = P Vf
-//   backward: recompute P; dP = dO Vf^T; dS = P (dP - rowsum(P dP)) / sqrt(hd); dQ = dS Kf; dVf = P^T dO;
-//             dKf = dS^T Q; bank rows of dKf/dVf -> d bank; Linformer rows -> dKs = E_k dK', dE_k += Ks dK'^T
-// Batch reductions (dE, d bank) accumulate in CTA shared memory (fp32 atomics) and are flushed once per CTA.
+// The Linformer projections K' = E_k^T Ks, V' = E_v^T Vs (H:332-352) are never materialised.  With T = Q Ks^T [16 x 16]:
+//   forward : S = [T E_k | Q Bk^T] / sqrt(hd) -> P = softmax(S) (+ dropout) -> U = P_lin E_v^T -> O = U Vs + P_bank Bv
+//   backward: W = dO Vs^T; dP = [W E_v | dO Bv^T]; dS = P (dP - rowsum(P dP)) / sqrt(hd); X = dS_lin E_k^T;
+//             dQ = X Ks + dS_bank Bk;  dKs = X^T Q;  dVs = U^T dO;  dE_k += T^T dS_lin;  dE_v += W^T P_lin;
+//             dBk += dS_bank^T Q;  dBv += P_bank^T dO
+// (Bk / Bv = the bank snapshot of this head, or the projected bank K / V of the cross branch, where the Linformer half
+// is absent.)  An mma C fragment of a [16 x 16] product IS the A fragment of the next product (same thread <-> element
+// map after packing to bf16), and its transpose is four movmatrix instructions, so the chain never touches shared memory:
+// 84 MMAs per backward task against 180 for the version that formed K', V', dK', dV' in shared memory, no intra-task
+// __syncwarp, and 7 KB instead of 21 KB of shared memory per warp.  The task's inputs (Q, Ks, Vs, dO: 16 x 48 bf16 each)
+// are fetched with cp.async into a double buffer one task ahead.
+// Batch reductions (dE, d bank) accumulate in mma C registers across a warp's tasks and are flushed once per warp.
 #include "kernels.h"
 
 namespace {
@@ -18,6 +26,7 @@ constexpr int HD = 48, NQ = 16, LP = 16, KLIN = 32, KB = 16;
 constexpr int PT = 56;    // pitch (bf16 elements) of 48-wide rows: 112 B -> conflict-free 16 B row accesses
 constexpr int PE = 40;    // pitch of the 32-wide Linformer matrices
 constexpr int WARPS = 4;
+constexpr int MAT = NQ * PT;   // one staged [16 x 48] matrix
 
 __device__ __forceinline__ uint32_t sa(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ldsm4(uint32_t* r, uint32_t addr) {
@@ -25,6 +34,11 @@ __device__ __forceinline__ void ldsm4(uint32_t* r, uint32_t addr) {
 }
 __device__ __forceinline__ void ldsm4t(uint32_t* r, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t movt(uint32_t a) {   // transpose of an 8 x 8 bf16 tile held one row-pair per thread
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
 }
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -35,16 +49,17 @@ __device__ __forceinline__ uint32_t pack2(float x, float y) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ void cp16(bf16* dst, const bf16* src, bool valid) {   // 16 B global -> shared, zero-filled if !valid
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // A fragment (16 x 16) from smem stored [m][k] (k contiguous)
-__device__ __forceinline__ void ldA(uint32_t* a, const bf16* base, int pitch, int m0, int k0, int lane) {
+__device__ __forceinline__ void ldA(uint32_t* a, const bf16* base, int pitch, int k0, int lane) {
   const int mat = lane >> 3, r = lane & 7;
-  ldsm4(a, sa(base + (m0 + r + (mat & 1) * 8) * pitch + k0 + (mat >> 1) * 8));
-}
-// A fragment from smem stored [k][m] (m contiguous): A(m, k) = S[k][m]
-__device__ __forceinline__ void ldAt(uint32_t* a, const bf16* base, int pitch, int m0, int k0, int lane) {
-  const int mat = lane >> 3, r = lane & 7;
-  ldsm4t(a, sa(base + (k0 + r + (mat >> 1) * 8) * pitch + m0 + (mat & 1) * 8));
+  ldsm4(a, sa(base + (r + (mat & 1) * 8) * pitch + k0 + (mat >> 1) * 8));
 }
 // B fragments of TWO adjacent n8 tiles (b[0..1] = tile n0, b[2..3] = tile n0 + 8) from smem stored [n][k]
 __device__ __forceinline__ void ldB(uint32_t* b, const bf16* base, int pitch, int n0, int k0, int lane) {
@@ -56,20 +71,77 @@ __device__ __forceinline__ void ldBt(uint32_t* b, const bf16* base, int pitch, i
   const int mat = lane >> 3, r = lane & 7;
   ldsm4t(b, sa(base + (k0 + r + (mat & 1) * 8) * pitch + n0 + (mat >> 1) * 8));
 }
-// C fragment (rows g / g+8, cols 2t / 2t+1 of an m16n8 tile) -> bf16 smem [m][n]
-__device__ __forceinline__ void stC(bf16* base, int pitch, int m0, int n0, const float* c, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  *reinterpret_cast<uint32_t*>(base + (m0 + g) * pitch + n0 + 2 * t) = pack2(c[0], c[1]);
-  *reinterpret_cast<uint32_t*>(base + (m0 + g + 8) * pitch + n0 + 2 * t) = pack2(c[2], c[3]);
+// two adjacent C tiles (16 x 16, fp32) -> the A fragment of the same matrix in bf16
+__device__ __forceinline__ void packA(uint32_t* a, const float* c0, const float* c1) {
+  a[0] = pack2(c0[0], c0[1]); a[1] = pack2(c0[2], c0[3]); a[2] = pack2(c1[0], c1[1]); a[3] = pack2(c1[2], c1[3]);
+}
+// A fragment of M^T from the A fragment of M (16 x 16)
+__device__ __forceinline__ void transA(uint32_t* t, const uint32_t* a) {
+  t[0] = movt(a[0]); t[1] = movt(a[2]); t[2] = movt(a[1]); t[3] = movt(a[3]);
+}
+// C[16 x 16] (two n8 tiles) = A[16 x 48] * B^T, B staged [n = 16][k = 48]
+__device__ __forceinline__ void mm_k48_n16(float (*c)[4], const uint32_t (*a)[4], const bf16* Bs, int lane) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) c[0][e] = c[1][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+    uint32_t b[4];
+    ldB(b, Bs, PT, 0, kk * 16, lane);
+    mma16816(c[0], a[kk], b[0], b[1]);
+    mma16816(c[1], a[kk], b[2], b[3]);
+  }
+}
+// o[16 x 48] += A[16 x 16] * B, B staged [k = 16][n = 48]
+__device__ __forceinline__ void mm_k16_n48(float (*o)[4], const uint32_t* a, const bf16* Bs, int lane) {
+#pragma unroll
+  for (int np = 0; np < 3; ++np) {
+    uint32_t b[4];
+    ldBt(b, Bs, PT, np * 16, 0, lane);
+    mma16816(o[2 * np], a, b[0], b[1]);
+    mma16816(o[2 * np + 1], a, b[2], b[3]);
+  }
+}
+// o[16 x 48] += A[16 x 16] * B with B already in fragment registers bf[3][4] (ldBt of a [k = 16][n = 48] matrix)
+__device__ __forceinline__ void mm_k16_n48_r(float (*o)[4], const uint32_t* a, const uint32_t (*bf)[4]) {
+#pragma unroll
+  for (int np = 0; np < 3; ++np) {
+    mma16816(o[2 * np], a, bf[np][0], bf[np][1]);
+    mma16816(o[2 * np + 1], a, bf[np][2], bf[np][3]);
+  }
+}
+// c[16 x 32] (4 tiles, overwritten) = A[16 x 16] * E, E staged [k = l][n = j] (j contiguous)
+__device__ __forceinline__ void mm_times_E(float (*c)[4], const uint32_t* a, const bf16* E, int lane) {
+#pragma unroll
+  for (int np = 0; np < 2; ++np) {
+    uint32_t b[4];
+    ldBt(b, E, PE, np * 16, 0, lane);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[2 * np][e] = c[2 * np + 1][e] = 0.f;
+    mma16816(c[2 * np], a, b[0], b[1]);
+    mma16816(c[2 * np + 1], a, b[2], b[3]);
+  }
+}
+// c[16 x 16] (2 tiles) = X[16 x 32] * E^T, X given as its two A fragments, E staged [n = l][k = j]
+__device__ __forceinline__ void mm_times_Et(float (*c)[4], const uint32_t (*xa)[4], const bf16* E, int lane) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) c[0][e] = c[1][e] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    uint32_t b[4];
+    ldB(b, E, PE, 0, kk * 16, lane);
+    mma16816(c[0], xa[kk], b[0], b[1]);
+    mma16816(c[1], xa[kk], b[2], b[3]);
+  }
+}
+// acc[16 x 32] += M^T Y: mt = A fragment of M^T, Y [16 x 32] given as its two A fragments ya[2][4] (k = rows of Y)
+__device__ __forceinline__ void acc_Mt_Y(float (*acc)[4], const uint32_t* mt, const uint32_t (*ya)[4]) {
+#pragma unroll
+  for (int n = 0; n < 4; ++n)   // B tile n (columns 8 n ..): rows 0-7 sit in ya[n / 2][2 (n & 1)], rows 8-15 in the next register
+    mma16816(acc[n], mt, movt(ya[n >> 1][(n & 1) * 2]), movt(ya[n >> 1][(n & 1) * 2 + 1]));
 }
 
-struct WarpSmem {   // per-warp regions (bf16 element offsets from the warp base)
-  static constexpr int Q = 0, DO = Q + NQ * PT, KS = DO + NQ * PT, VS = KS + LP * PT, KF = VS + LP * PT;
-  static constexpr int VF = KF + (KLIN + KB) * PT, P = VF + (KLIN + KB) * PT, DS = P + NQ * PT, END = DS + NQ * PT;
-};
-
 __device__ __forceinline__ int q_row(const AttnP& p, int w, int i) {
-  if (p.mode == 0) {
+  if (p.mode == 0 && p.side != p.ws) {
     const int nws = p.side / p.ws, nW = nws * nws;
     const int b = w / nW, wi = w % nW;
     return b * p.Nt + ((wi / nws) * p.ws + i / p.ws) * p.side + (wi % nws) * p.ws + i % p.ws;
@@ -77,18 +149,7 @@ __device__ __forceinline__ int q_row(const AttnP& p, int w, int i) {
   return w * p.Nt + i;
 }
 
-// 16 rows x 48 bf16 from global (row index from `rowsrc` lane registers) -> smem [16][PT]; rows >= nvalid zeroed
-__device__ __forceinline__ void load_rows(bf16* dst, const bf16* src, long ld, int col, int my_row, int nvalid, int lane) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int c = lane + 32 * k, i = c / 6, ch = c % 6;
-    const int row = __shfl_sync(0xffffffffu, my_row, i);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (i < nvalid) v = *reinterpret_cast<const uint4*>(src + (long)row * ld + col + ch * 8);
-    *reinterpret_cast<uint4*>(dst + i * PT + ch * 8) = v;
-  }
-}
-// 16 x 48 fp32 (row pitch D) -> bf16 smem rows
+// 16 x 48 fp32 (row pitch D) -> bf16 smem rows (once per warp: the bank tile of the warp's head)
 __device__ __forceinline__ void load_bank(bf16* dst, const float* src, int D, int col, int lane) {
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -97,44 +158,49 @@ __device__ __forceinline__ void load_bank(bf16* dst, const float* src, int D, in
     *reinterpret_cast<uint2*>(dst + i * PT + ch * 4) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
   }
 }
-
-// Kf/Vf rows [0, 32) = E^T Xs  (M = 32 (j), N = 48 (d), K = 16 (l))
-__device__ __forceinline__ void linformer_fwd(bf16* Xf, const bf16* E, const bf16* Xs, int lane) {
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    uint32_t a[4];
-    ldAt(a, E, PE, mt * 16, 0, lane);
-#pragma unroll
-    for (int np = 0; np < 3; ++np) {
-      uint32_t b[4];
-      ldBt(b, Xs, PT, np * 16, 0, lane);
-      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-      mma16816(c0, a, b[0], b[1]);
-      mma16816(c1, a, b[2], b[3]);
-      stC(Xf, PT, mt * 16, np * 16, c0, lane);
-      stC(Xf, PT, mt * 16, np * 16 + 8, c1, lane);
-    }
+// E_k / E_v fp32 [L][32] -> bf16 smem [LP][PE] (rows >= L zero): once per CTA
+__device__ __forceinline__ void load_E(bf16* Es, const AttnP& p) {
+  for (int idx = threadIdx.x; idx < 2 * LP * KLIN; idx += blockDim.x) {
+    const int which = idx / (LP * KLIN), r = idx % (LP * KLIN), l = r / KLIN, j = r % KLIN;
+    const float* src = which ? p.Ev : p.Ek;
+    Es[which * LP * PE + l * PE + j] = __float2bfloat16_rn(l < p.L ? src[l * KLIN + j] : 0.f);
   }
 }
 
-// S = Q Kf^T -> softmax probabilities in C-fragment layout s[NT][4] (NT = NKV / 8 key tiles)
-template <int NKV>
-__device__ __forceinline__ void scores_softmax(float (*s)[4], const bf16* Qs, const bf16* Kf, float scale, int lane) {
-  constexpr int NT = NKV / 8;
+// cp.async of one task's inputs into a staging buffer: [Q | Ks | Vs | dO], each [16][PT]; key / value rows >= L zero-filled
+template <bool LINF, bool BWD>
+__device__ __forceinline__ void prefetch_task(const AttnP& p, bf16* buf, int w, int h, int lane) {
+  const bf16* q = static_cast<const bf16*>(p.q);
+  const bf16* kv = static_cast<const bf16*>(p.kv);
+  const bf16* dout = static_cast<const bf16*>(p.dout);
 #pragma unroll
-  for (int n = 0; n < NT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < HD / 16; ++kk) {
-    uint32_t a[4];
-    ldA(a, Qs, PT, 0, kk * 16, lane);
-#pragma unroll
-    for (int np = 0; np < NT / 2; ++np) {
-      uint32_t b[4];
-      ldB(b, Kf, PT, np * 16, kk * 16, lane);
-      mma16816(s[2 * np], a, b[0], b[1]);
-      mma16816(s[2 * np + 1], a, b[2], b[3]);
+  for (int k = 0; k < 3; ++k) {
+    const int c = lane + 32 * k, i = c / 6, ch = c % 6;
+    const int rq = q_row(p, w, i);
+    cp16(buf + i * PT + ch * 8, q + (long)rq * p.ldq + p.qcol + h * HD + ch * 8, true);
+    if (BWD) cp16(buf + 3 * MAT + i * PT + ch * 8, dout + (long)rq * p.lddo + h * HD + ch * 8, true);
+    if (LINF) {
+      const int rk = (p.mode == 0) ? rq : w * p.NM + min(i, p.NM - 1);
+      const bool ok = i < p.L;
+      cp16(buf + MAT + i * PT + ch * 8, kv + (long)rk * p.ldkv + p.kcol + h * HD + ch * 8, ok);
+      cp16(buf + 2 * MAT + i * PT + ch * 8, kv + (long)rk * p.ldkv + p.vcol + h * HD + ch * 8, ok);
     }
   }
+  cp_commit();
+}
+
+// C-layout [16 x 48] registers -> global bf16 rows r0 (fragment rows g) / r1 (rows g + 8); a row < 0 is skipped
+__device__ __forceinline__ void store_rows(bf16* dst, long ld, int col, int r0, int r1, const float (*o)[4], int t) {
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {
+    if (r0 >= 0) *reinterpret_cast<uint32_t*>(dst + (long)r0 * ld + col + n * 8 + 2 * t) = pack2(o[n][0], o[n][1]);
+    if (r1 >= 0) *reinterpret_cast<uint32_t*>(dst + (long)r1 * ld + col + n * 8 + 2 * t) = pack2(o[n][2], o[n][3]);
+  }
+}
+
+// softmax over the NT key tiles of a C-layout score tile (rows g and g + 8)
+template <int NT>
+__device__ __forceinline__ void softmax_c(float (*s)[4], float scale) {
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
@@ -159,191 +225,103 @@ __device__ __forceinline__ void scores_softmax(float (*s)[4], const bf16* Qs, co
   for (int n = 0; n < NT; ++n) { s[n][0] *= z0; s[n][1] *= z0; s[n][2] *= z1; s[n][3] *= z1; }
 }
 
-// out[16 x 48] = X[16 x NKV] (C-layout registers, used as A) * Bs (smem [k][n], n contiguous)
-template <int NKV>
-__device__ __forceinline__ void regA_times_Bt(float (*o)[4], const float (*x)[4], const bf16* Bs, int lane) {
-#pragma unroll
-  for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll
-  for (int kk = 0; kk < NKV / 16; ++kk) {
-    uint32_t a[4] = {pack2(x[2 * kk][0], x[2 * kk][1]), pack2(x[2 * kk][2], x[2 * kk][3]),
-                     pack2(x[2 * kk + 1][0], x[2 * kk + 1][1]), pack2(x[2 * kk + 1][2], x[2 * kk + 1][3])};
-#pragma unroll
-    for (int np = 0; np < HD / 16; ++np) {
-      uint32_t b[4];
-      ldBt(b, Bs, PT, np * 16, kk * 16, lane);
-      mma16816(o[2 * np], a, b[0], b[1]);
-      mma16816(o[2 * np + 1], a, b[2], b[3]);
-    }
-  }
-}
-
-// C-layout [16 x 48] registers -> global bf16 rows
-__device__ __forceinline__ void store_rows(bf16* dst, long ld, int col, int my_row, const float (*o)[4], int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  const int r0 = __shfl_sync(0xffffffffu, my_row, g), r1 = __shfl_sync(0xffffffffu, my_row, g + 8);
-#pragma unroll
-  for (int n = 0; n < HD / 8; ++n) {
-    *reinterpret_cast<uint32_t*>(dst + (long)r0 * ld + col + n * 8 + 2 * t) = pack2(o[n][0], o[n][1]);
-    *reinterpret_cast<uint32_t*>(dst + (long)r1 * ld + col + n * 8 + 2 * t) = pack2(o[n][2], o[n][3]);
-  }
-}
-
-template <int NKV, bool LINF>
-__device__ __forceinline__ void stage_task(const AttnP& p, bf16* W, const bf16* Es, int w, int h, int lane, int& my_q,
-                                           int& my_kv) {
-  const int D = p.H * HD;
-  my_q = q_row(p, w, lane & 15);
-  const bf16* q = static_cast<const bf16*>(p.q);
-  load_rows(W + WarpSmem::Q, q, p.ldq, p.qcol + h * HD, my_q, NQ, lane);
+// scores -> probabilities P[NT][4] (tiles [0, 4) = Linformer keys, last two = bank keys); ta = bf16 A fragment of T = Q Ks^T
+template <bool LINF>
+__device__ __forceinline__ void probabilities(float (*P)[4], uint32_t* ta, const uint32_t (*aq)[4], const bf16* Ks, const bf16* Bk,
+                                              const bf16* Ek, float scale, int lane) {
+  constexpr int LT = LINF ? 4 : 0;
+  mm_k48_n16(P + LT, aq, Bk, lane);
   if (LINF) {
-    my_kv = (p.mode == 0) ? my_q : w * p.NM + min(lane & 15, p.NM - 1);
-    const bf16* kv = static_cast<const bf16*>(p.kv);
-    load_rows(W + WarpSmem::KS, kv, p.ldkv, p.kcol + h * HD, my_kv, p.L, lane);
-    load_rows(W + WarpSmem::VS, kv, p.ldkv, p.vcol + h * HD, my_kv, p.L, lane);
-    load_bank(W + WarpSmem::KF + KLIN * PT, p.bank_k, D, h * HD, lane);
-    load_bank(W + WarpSmem::VF + KLIN * PT, p.bank_v, D, h * HD, lane);
-    __syncwarp();
-    linformer_fwd(W + WarpSmem::KF, Es, W + WarpSmem::KS, lane);
-    linformer_fwd(W + WarpSmem::VF, Es + LP * PE, W + WarpSmem::VS, lane);
-  } else {
-    load_bank(W + WarpSmem::KF, p.kc, D, h * HD, lane);
-    load_bank(W + WarpSmem::VF, p.vc, D, h * HD, lane);
+    float T[2][4];
+    mm_k48_n16(T, aq, Ks, lane);
+    packA(ta, T[0], T[1]);
+    mm_times_E(P, ta, Ek, lane);
   }
-  __syncwarp();
+  softmax_c<LT + 2>(P, scale);
 }
 
-// E_k / E_v fp32 [L][32] -> bf16 smem [LP][PE] (rows >= L zero): once per CTA
-__device__ __forceinline__ void load_E(bf16* Es, const AttnP& p) {
-  for (int idx = threadIdx.x; idx < 2 * LP * KLIN; idx += blockDim.x) {
-    const int which = idx / (LP * KLIN), r = idx % (LP * KLIN), l = r / KLIN, j = r % KLIN;
-    const float* src = which ? p.Ev : p.Ek;
-    Es[which * LP * PE + l * PE + j] = __float2bfloat16_rn(l < p.L ? src[l * KLIN + j] : 0.f);
-  }
-}
-
-template <int NKV, bool LINF>
-__global__ void __launch_bounds__(WARPS * 32) attn_mma_fwd_kernel(AttnP p, int ntask) {
+template <bool LINF>
+__global__ void __launch_bounds__(WARPS * 32, 3) attn_mma_fwd_kernel(AttnP p, int ntask) {
   QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
-  bf16* Es = reinterpret_cast<bf16*>(smraw);                       // [2][LP][PE]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  bf16* W = Es + 2 * LP * PE + warp * WarpSmem::END;
+  constexpr int NT = LINF ? 6 : 2, LT = LINF ? 4 : 0, NM = LINF ? 3 : 1;   // NM staged matrices per task: Q [, Ks, Vs]
+  bf16* Es = reinterpret_cast<bf16*>(smraw);                               // [2][LP][PE]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  bf16* Bk = Es + 2 * LP * PE + warp * 2 * MAT;                            // this warp's head: bank K | bank V
+  bf16* Bv = Bk + MAT;
+  bf16* stage = Es + 2 * LP * PE + WARPS * 2 * MAT + warp * 2 * NM * MAT;  // [2 buffers][NM][16][PT]
+  const int D = p.H * HD, h = warp;                                        // H == WARPS and the task stride is a multiple of it
   if (LINF) load_E(Es, p);
+  load_bank(Bk, LINF ? p.bank_k : p.kc, D, h * HD, lane);
+  load_bank(Bv, LINF ? p.bank_v : p.vc, D, h * HD, lane);
   __syncthreads();
   const float scale = rsqrtf((float)HD);
   bf16* out = static_cast<bf16*>(p.out);
-  for (int task = blockIdx.x * WARPS + warp; task < ntask; task += gridDim.x * WARPS) {
-    const int w = task / p.H, h = task % p.H;
-    int my_q, my_kv;
-    stage_task<NKV, LINF>(p, W, Es, w, h, lane, my_q, my_kv);
-    float s[NKV / 8][4], o[HD / 8][4];
-    scores_softmax<NKV>(s, W + WarpSmem::Q, W + WarpSmem::KF, scale, lane);
+  const int stride = gridDim.x * WARPS;
+  int task = blockIdx.x * WARPS + warp, cur = 0;
+  if (task < ntask) prefetch_task<LINF, false>(p, stage, task / p.H, h, lane);
+  for (; task < ntask; task += stride, cur ^= 1) {
+    const int w = task / p.H;
+    bf16* buf = stage + cur * NM * MAT;
+    if (task + stride < ntask) {
+      prefetch_task<LINF, false>(p, stage + (cur ^ 1) * NM * MAT, (task + stride) / p.H, h, lane);
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncwarp();
+    uint32_t aq[3][4];
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) ldA(aq[kk], buf, PT, kk * 16, lane);
+    float P[NT][4];
+    uint32_t ta[4];
+    probabilities<LINF>(P, ta, aq, buf + MAT, Bk, Es, scale, lane);
     if (p.drop.p > 0.f) {   // SDPA dropout_p on the probabilities
       const DropState ds = drop_state(p.drop);
-      drop_apply_c<NKV / 8>(s, drop_bits_c<NKV / 8>(ds, (uint32_t)task, lane), ds.inv);
+      drop_apply_c<NT>(P, drop_bits_c<NT>(ds, (uint32_t)task, lane), ds.inv);
     }
-    regA_times_Bt<NKV>(o, s, W + WarpSmem::VF, lane);
-    store_rows(out, p.ldo, h * HD, my_q, o, lane);
-    __syncwarp();
-  }
-}
-
-// C[MT*16 x 48] = A^T(smem [k = 16][m]) * B(smem [k = 16][n = 48]) ; c[MT][6][4]
-template <int MT>
-__device__ __forceinline__ void At_times_Bt_k16(float (*c)[6][4], const bf16* As, const bf16* Bs, int lane) {
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    uint32_t a[4];
-    ldAt(a, As, PT, mt * 16, 0, lane);
-#pragma unroll
-    for (int np = 0; np < 3; ++np) {
-      uint32_t b[4];
-      ldBt(b, Bs, PT, np * 16, 0, lane);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) c[mt][2 * np][e] = c[mt][2 * np + 1][e] = 0.f;
-      mma16816(c[mt][2 * np], a, b[0], b[1]);
-      mma16816(c[mt][2 * np + 1], a, b[2], b[3]);
-    }
-  }
-}
-
-// Consume dXf (X = K or V): bank rows -> the warp's register accumulator (a warp always serves the same head);
-// Linformer rows -> dXs = E dX' (global) and dE += Xs dX'^T (accumulated in the mma C registers across tasks).
-template <int NKV, bool LINF>
-__device__ __forceinline__ void consume_dXf(const AttnP& p, float (*c)[6][4], bf16* stage /*[32][PT]*/, const bf16* E,
-                                            const bf16* Xs, float (*dE_acc)[4], float (*dbank_acc)[4], int h, int my_kv,
-                                            int dcol, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  constexpr int MT = NKV / 16;
-#pragma unroll
-  for (int n = 0; n < 6; ++n)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) dbank_acc[n][e] += c[MT - 1][n][e];
-  if (!LINF) return;
-  // dX' (32 x 48) -> bf16 staging [j][d]
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int n = 0; n < 6; ++n) stC(stage, PT, mt * 16, n * 8, c[mt][n], lane);
-  __syncwarp();
-  // dXs[l, d] = sum_j E[l, j] dX'[j, d] : A = E [m = l][k = j], B = dX' [k = j][n = d]
-  {
     float o[6][4];
 #pragma unroll
     for (int n = 0; n < 6; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      uint32_t a[4];
-      ldA(a, E, PE, 0, kk * 16, lane);
-#pragma unroll
-      for (int np = 0; np < 3; ++np) {
-        uint32_t b[4];
-        ldBt(b, stage, PT, np * 16, kk * 16, lane);
-        mma16816(o[2 * np], a, b[0], b[1]);
-        mma16816(o[2 * np + 1], a, b[2], b[3]);
-      }
+    uint32_t pb[4];
+    packA(pb, P[LT], P[LT + 1]);
+    mm_k16_n48(o, pb, Bv, lane);
+    if (LINF) {
+      uint32_t pa[2][4], ua[4];
+      float U[2][4];
+      packA(pa[0], P[0], P[1]);
+      packA(pa[1], P[2], P[3]);
+      mm_times_Et(U, pa, Es + LP * PE, lane);
+      packA(ua, U[0], U[1]);
+      mm_k16_n48(o, ua, buf + 2 * MAT, lane);
     }
-    bf16* dkv = static_cast<bf16*>(p.dkv);
-    const int r0 = __shfl_sync(0xffffffffu, my_kv, g), r1 = __shfl_sync(0xffffffffu, my_kv, g + 8);
-#pragma unroll
-    for (int n = 0; n < 6; ++n) {
-      if (g < p.L) *reinterpret_cast<uint32_t*>(dkv + (long)r0 * p.lddkv + dcol + h * HD + n * 8 + 2 * t) = pack2(o[n][0], o[n][1]);
-      if (g + 8 < p.L) *reinterpret_cast<uint32_t*>(dkv + (long)r1 * p.lddkv + dcol + h * HD + n * 8 + 2 * t) = pack2(o[n][2], o[n][3]);
-    }
+    store_rows(out, p.ldo, h * HD, q_row(p, w, g), q_row(p, w, g + 8), o, t);
+    __syncwarp();   // every lane is done with `buf` before the next iteration's prefetch overwrites it
   }
-  // dE[l, j] += sum_d Xs[l, d] dX'[j, d] : A = Xs [m = l][k = d], B = dX' [n = j][k = d]
-#pragma unroll
-  for (int kk = 0; kk < 3; ++kk) {
-    uint32_t a[4];
-    ldA(a, Xs, PT, 0, kk * 16, lane);
-#pragma unroll
-    for (int np = 0; np < 2; ++np) {
-      uint32_t b[4];
-      ldB(b, stage, PT, np * 16, kk * 16, lane);
-      mma16816(dE_acc[2 * np], a, b[0], b[1]);
-      mma16816(dE_acc[2 * np + 1], a, b[2], b[3]);
-    }
-  }
-  __syncwarp();
 }
 
-template <int NKV, bool LINF>
-__global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int ntask) {
+template <bool LINF>
+__global__ void __launch_bounds__(WARPS * 32, 3) attn_mma_bwd_kernel(AttnP p, int ntask) {
   QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
-  const int D = p.H * HD;
+  constexpr int NT = LINF ? 6 : 2, LT = LINF ? 4 : 0;
+  constexpr int NM = 4;                                                    // Q, Ks, Vs, dO (cross: Ks / Vs slots unused)
   bf16* Es = reinterpret_cast<bf16*>(smraw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  bf16* W = Es + 2 * LP * PE + warp * WarpSmem::END;
+  bf16* Bk = Es + 2 * LP * PE + warp * 2 * MAT;
+  bf16* Bv = Bk + MAT;
+  bf16* stage = Es + 2 * LP * PE + WARPS * 2 * MAT + warp * 2 * NM * MAT;
+  const int D = p.H * HD, h = warp;
   if (LINF) load_E(Es, p);
+  load_bank(Bk, LINF ? p.bank_k : p.kc, D, h * HD, lane);
+  load_bank(Bv, LINF ? p.bank_v : p.vc, D, h * HD, lane);
   __syncthreads();
+  const bf16 *Ek = Es, *Ev = Es + LP * PE;
   const float scale = rsqrtf((float)HD);
-  const bf16* dout = static_cast<const bf16*>(p.dout);
   bf16* dq = static_cast<bf16*>(p.dq);
-  constexpr int NT = NKV / 8;
-  // batch reductions live in registers: H == WARPS and the task stride is a multiple of WARPS, so this warp's head is
-  // fixed (h == warp) and its bank-row gradients are one [16 x 48] C tile per K and V; dE_k / dE_v are [16 x 32] tiles.
+  bf16* dkv = static_cast<bf16*>(p.dkv);
+  // batch reductions live in registers: this warp's head is fixed, so its bank-row gradients are one [16 x 48] C tile per
+  // K and V; dE_k / dE_v are [16 x 32] tiles
   float dbk[6][4], dbv[6][4], dEk[4][4], dEv[4][4];
 #pragma unroll
   for (int n = 0; n < 6; ++n)
@@ -353,33 +331,43 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int n
   for (int n = 0; n < 4; ++n)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dEk[n][e] = dEv[n][e] = 0.f;
-  const int h = warp;
-  for (int task = blockIdx.x * WARPS + warp; task < ntask; task += gridDim.x * WARPS) {
+  const int stride = gridDim.x * WARPS;
+  int task = blockIdx.x * WARPS + warp, cur = 0;
+  if (task < ntask) prefetch_task<LINF, true>(p, stage, task / p.H, h, lane);
+  for (; task < ntask; task += stride, cur ^= 1) {
     const int w = task / p.H;
-    int my_q, my_kv = 0;
-    stage_task<NKV, LINF>(p, W, Es, w, h, lane, my_q, my_kv);
-    load_rows(W + WarpSmem::DO, dout, p.lddo, h * HD, my_q, NQ, lane);
+    bf16* buf = stage + cur * NM * MAT;
+    const bf16 *Qs = buf, *Ks = buf + MAT, *Vs = buf + 2 * MAT, *DOs = buf + 3 * MAT;
+    if (task + stride < ntask) {
+      prefetch_task<LINF, true>(p, stage + (cur ^ 1) * NM * MAT, (task + stride) / p.H, h, lane);
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
     __syncwarp();
     float P[NT][4], dS[NT][4];
-    scores_softmax<NKV>(P, W + WarpSmem::Q, W + WarpSmem::KF, scale, lane);
-    // dP = dO Vf^T
+    uint32_t ta[4], wa[4];
+    {
+      uint32_t aq[3][4];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) dS[n][0] = dS[n][1] = dS[n][2] = dS[n][3] = 0.f;
+      for (int kk = 0; kk < 3; ++kk) ldA(aq[kk], Qs, PT, kk * 16, lane);
+      probabilities<LINF>(P, ta, aq, Ks, Bk, Ek, scale, lane);
+    }
+    {   // dP = [W E_v | dO Bv^T],  W = dO Vs^T
+      uint32_t ado[3][4];
 #pragma unroll
-    for (int kk = 0; kk < HD / 16; ++kk) {
-      uint32_t a[4];
-      ldA(a, W + WarpSmem::DO, PT, 0, kk * 16, lane);
-#pragma unroll
-      for (int np = 0; np < NT / 2; ++np) {
-        uint32_t b[4];
-        ldB(b, W + WarpSmem::VF, PT, np * 16, kk * 16, lane);
-        mma16816(dS[2 * np], a, b[0], b[1]);
-        mma16816(dS[2 * np + 1], a, b[2], b[3]);
+      for (int kk = 0; kk < 3; ++kk) ldA(ado[kk], DOs, PT, kk * 16, lane);
+      mm_k48_n16(dS + LT, ado, Bv, lane);
+      if (LINF) {
+        float Wm[2][4];
+        mm_k48_n16(Wm, ado, Vs, lane);
+        packA(wa, Wm[0], Wm[1]);
+        mm_times_E(dS, wa, Ev, lane);
       }
     }
     unsigned long long keep = ~0ull;
     float kinv = 1.f;
-    if (p.drop.p > 0.f) {   // dP <- d(P_dropped) * keep; P_dropped (for dVf) is formed after the softmax backward
+    if (p.drop.p > 0.f) {   // dP <- d(P_dropped) * keep; P_dropped (for dV) is formed after the softmax backward
       const DropState ds = drop_state(p.drop);
       keep = drop_bits_c<NT>(ds, (uint32_t)task, lane);
       kinv = ds.inv;
@@ -396,25 +384,66 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int n
       dS[n][2] = P[n][2] * (dS[n][2] - r1) * scale; dS[n][3] = P[n][3] * (dS[n][3] - r1) * scale;
     }
     if (p.drop.p > 0.f) drop_apply_c<NT>(P, keep, kinv);
+    // from here on P and dS are only MMA operands: keep their bf16 A fragments (k-step kk = key tiles 2 kk, 2 kk + 1)
+    uint32_t pP[NT / 2][4], pS[NT / 2][4];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      stC(W + WarpSmem::P, PT, 0, n * 8, P[n], lane);
-      stC(W + WarpSmem::DS, PT, 0, n * 8, dS[n], lane);
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      packA(pP[kk], P[2 * kk], P[2 * kk + 1]);
+      packA(pS[kk], dS[2 * kk], dS[2 * kk + 1]);
     }
-    // dQ = dS Kf
-    {
-      float o[HD / 8][4];
-      regA_times_Bt<NKV>(o, dS, W + WarpSmem::KF, lane);
-      store_rows(dq, p.lddq, p.dqcol + h * HD, my_q, o, lane);
+    const int rq0 = q_row(p, w, g), rq1 = q_row(p, w, g + 8);
+    uint32_t xa[4];
+    {   // dQ = X Ks + dS_bank Bk,  X = dS_lin E_k^T
+      float o[6][4];
+#pragma unroll
+      for (int n = 0; n < 6; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+      mm_k16_n48(o, pS[LT / 2], Bk, lane);
+      if (LINF) {
+        float X[2][4];
+        mm_times_Et(X, pS, Ek, lane);
+        packA(xa, X[0], X[1]);
+        mm_k16_n48(o, xa, Ks, lane);
+      }
+      store_rows(dq, p.lddq, p.dqcol + h * HD, rq0, rq1, o, t);
     }
-    __syncwarp();
-    // dVf = P^T dO ; dKf = dS^T Q  (M = NKV keys, N = 48, K = 16 queries); Kf / Vf rows [0, 32) are free from here on
-    {
-      float c[NKV / 16][6][4];
-      At_times_Bt_k16<NKV / 16>(c, W + WarpSmem::P, W + WarpSmem::DO, lane);
-      consume_dXf<NKV, LINF>(p, c, W + WarpSmem::VF, Es + LP * PE, W + WarpSmem::VS, dEv, dbv, h, my_kv, p.dvcol, lane);
-      At_times_Bt_k16<NKV / 16>(c, W + WarpSmem::DS, W + WarpSmem::Q, lane);
-      consume_dXf<NKV, LINF>(p, c, W + WarpSmem::KF, Es, W + WarpSmem::KS, dEk, dbk, h, my_kv, p.dkcol, lane);
+    uint32_t bq[3][4], bdo[3][4], tr[4];   // Q and dO as [k = query][n = channel] B operands
+#pragma unroll
+    for (int np = 0; np < 3; ++np) {
+      ldBt(bq[np], Qs, PT, np * 16, 0, lane);
+      ldBt(bdo[np], DOs, PT, np * 16, 0, lane);
+    }
+    transA(tr, pS[LT / 2]);     // d bank_k += dS_bank^T Q
+    mm_k16_n48_r(dbk, tr, bq);
+    transA(tr, pP[LT / 2]);     // d bank_v += P_bank^T dO
+    mm_k16_n48_r(dbv, tr, bdo);
+    if (LINF) {
+      int rk0, rk1;
+      if (p.mode == 0) { rk0 = rq0; rk1 = rq1; }
+      else { rk0 = w * p.NM + min(g, p.NM - 1); rk1 = w * p.NM + min(g + 8, p.NM - 1); }
+      if (g >= p.L) rk0 = -1;
+      if (g + 8 >= p.L) rk1 = -1;
+      float o[6][4];
+      // dKs = X^T Q
+#pragma unroll
+      for (int n = 0; n < 6; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+      transA(tr, xa);
+      mm_k16_n48_r(o, tr, bq);
+      store_rows(dkv, p.lddkv, p.dkcol + h * HD, rk0, rk1, o, t);
+      // dVs = U^T dO,  U = P_lin E_v^T (dropped probabilities)
+      float U[2][4];
+      uint32_t ua[4];
+      mm_times_Et(U, pP, Ev, lane);
+      packA(ua, U[0], U[1]);
+#pragma unroll
+      for (int n = 0; n < 6; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+      transA(tr, ua);
+      mm_k16_n48_r(o, tr, bdo);
+      store_rows(dkv, p.lddkv, p.dvcol + h * HD, rk0, rk1, o, t);
+      // dE_k += T^T dS_lin,  dE_v += W^T P_lin
+      transA(tr, ta);
+      acc_Mt_Y(dEk, tr, pS);
+      transA(tr, wa);
+      acc_Mt_Y(dEv, tr, pP);
     }
     __syncwarp();
   }
@@ -438,20 +467,14 @@ __global__ void __launch_bounds__(WARPS * 32) attn_mma_bwd_kernel(AttnP p, int n
   }
 }
 
-size_t smem_bytes(const AttnP& p, bool bwd) {
-  (void)p; (void)bwd;
-  return (size_t)(2 * LP * PE + WARPS * WarpSmem::END) * sizeof(bf16);
-}
-
 template <typename K>
-int launch(K kernel, cudaStream_t s, const AttnP& p, bool bwd) {
+int launch(K kernel, cudaStream_t s, const AttnP& p, int staged) {
   const int nwin = (p.mode == 0) ? p.B * (p.side / p.ws) * (p.side / p.ws) : p.B;
   const int ntask = nwin * p.H;
   if (ntask <= 0) return 0;
-  const size_t smem = smem_bytes(p, bwd);
+  const size_t smem = (size_t)(2 * LP * PE + WARPS * 2 * MAT + WARPS * 2 * staged * MAT) * sizeof(bf16);
   if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int occ = max(1, min(4, (int)(220 * 1024 / (smem + 1024))));
-  const int grid = min(cdiv(ntask, WARPS), qv_num_sms() * occ);
+  const int grid = min(cdiv(ntask, WARPS), qv_num_sms() * 3);
   qv_launch(kernel, grid, WARPS * 32, smem, s, p, ntask);
   QV_LAUNCH_CHECK();
   return 0;
@@ -472,10 +495,10 @@ bool attn_mma_ok(const AttnP& p) {
 }
 
 int attn_mma_fwd(cudaStream_t s, const AttnP& p) {
-  if (p.mode == 2) return launch(attn_mma_fwd_kernel<KB, false>, s, p, false);
-  return launch(attn_mma_fwd_kernel<KLIN + KB, true>, s, p, false);
+  if (p.mode == 2) return launch(attn_mma_fwd_kernel<false>, s, p, 1);
+  return launch(attn_mma_fwd_kernel<true>, s, p, 3);
 }
 int attn_mma_bwd(cudaStream_t s, const AttnP& p) {
-  if (p.mode == 2) return launch(attn_mma_bwd_kernel<KB, false>, s, p, true);
-  return launch(attn_mma_bwd_kernel<KLIN + KB, true>, s, p, true);
+  if (p.mode == 2) return launch(attn_mma_bwd_kernel<false>, s, p, 4);
+  return launch(attn_mma_bwd_kernel<true>, s, p, 4);
 }
