@@ -159,7 +159,9 @@ struct NtArgs {
   int n_slices;    // ceil(N / BN)
   int m_tiles;
   uint32_t tmem_cols;
-  int stages;      // depth of the TMA ring (4; 3 for the widest tiles so staging still fits)
+  int stages;      // depth of the TMA ring (4; 3 for the widest tiles so staging still fits; up to 8 A-only stages with w_res)
+  int w_res;       // this CTA's [BN x K] weight slice stays resident in shared memory for all its m-tiles (loaded once): the
+                   // ring then carries A only.  Re-loading W per tile was 60 % of the L2 -> SM bytes of the block projections
   int tma_store;   // wide epilogue: 64-column groups leave through a TMA store (map_c valid)
   GemmEpi e;
 };
@@ -291,36 +293,73 @@ __device__ __forceinline__ void stage_read16(const uint8_t* my_row, int c, bool 
   }
 }
 
+// Diagnostic build only (make EXTRA=-DQV_GEMM_TRACE): per-phase clock64 / globaltimer stamps of the first and the last CTA of
+// an NT launch, read back with qavit_test_gemm_trace_read (tools/gemm_trace.py).
+#ifdef QV_GEMM_TRACE
+__device__ long long g_trace[128];
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TR(i) do { if (blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) { \
+  const int b_ = blockIdx.x ? 32 : 0; g_trace[b_ + (i)] = clock64(); g_trace[64 + b_ + (i)] = gtimer(); } } while (0)
+#else
+#define TR(i) do {} while (0)
+#endif
+
 // WIDE: the epilogue flavour is a compile-time choice (two instantiations) so that neither carries the other's registers
 template <bool WIDE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                   const __grid_constant__ CUtensorMap map_c, NtArgs p) {
   pdl_trigger();   // the wait comes after the set-up that does not touch the producer's memory (barriers, descriptors, TMEM)
+  if (threadIdx.x == 0) TR(0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   const int STG = p.stages;
-  const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2, stage_bytes = a_bytes + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STG * stage_bytes);
-  uint64_t *full = bars, *empty = bars + STG, *tfull = bars + 2 * STG, *tempty = bars + 2 * STG + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STG + 4);
-  uint8_t* epi_stage = smem + STG * stage_bytes + 1024;   // 1024-aligned: the TMA-store staging of the wide epilogue is swizzled
+  const int kblocks = (p.K + BK - 1) / BK;
+  const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2;
+  const int stage_bytes = p.w_res ? a_bytes : a_bytes + w_bytes;
+  uint8_t* w_res_base = smem;                                      // [kblocks][BN x 128 B] swizzled boxes (w_res only)
+  uint8_t* ring = smem + (p.w_res ? kblocks * w_bytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + STG * stage_bytes);
+  uint64_t *full = bars, *empty = bars + STG, *tfull = bars + 2 * STG, *tempty = bars + 2 * STG + 2, *wfull = bars + 2 * STG + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STG + 5);
+  uint8_t* epi_stage = ring + STG * stage_bytes + 1024;   // 1024-aligned: the TMA-store staging of the wide epilogue is swizzled
   float* bias_s = reinterpret_cast<float*>(epi_stage + EPI_WARPS * EPI_WARP_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = (p.K + BK - 1) / BK;
   const int n0 = blockIdx.y * p.BN;
 
+  // producer state (thread 0): the first STG k-blocks are issued BEFORE the CTA-wide set-up barrier -- the ring is empty, so
+  // nothing has to be waited for, and the loads fly while TMEM is allocated and the bias is staged
+  int pr_s = 0, pr_mt = blockIdx.x, pr_kb = 0;
+  uint32_t pr_ph = 0;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_w);
-    if (WIDE && p.tma_store) tma_prefetch_desc(&map_c);
-    for (int s = 0; s < STG; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    // the loads go out first: they need nothing but their own completion barriers
+    for (int s = 0; s < STG; ++s) mbar_init(full + s, 1);
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+    pdl_wait();
+    if (p.w_res) {
+      mbar_expect_tx(wfull, (uint32_t)(kblocks * w_bytes));
+      for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(w_res_base + kb * w_bytes, &map_w, wfull, kb * BK, n0);
+    }
+    for (int n = 0; n < STG && pr_mt < p.m_tiles; ++n) {
+      uint8_t* sa = ring + pr_s * stage_bytes;
+      mbar_expect_tx(full + pr_s, (uint32_t)stage_bytes);
+      tma_load_2d(sa, &map_a, full + pr_s, pr_kb * BK, pr_mt * BM);
+      if (!p.w_res) tma_load_2d(sa + a_bytes, &map_w, full + pr_s, pr_kb * BK, n0);
+      if (++pr_s == STG) { pr_s = 0; pr_ph ^= 1; }
+      if (++pr_kb == kblocks) { pr_kb = 0; pr_mt += gridDim.x; }
+    }
+    TR(12);
+    for (int s = 0; s < STG; ++s) mbar_init(empty + s, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, EPI_WARPS); }
     fence_barrier_init();
+    if (WIDE && p.tma_store) tma_prefetch_desc(&map_c);
+    TR(1);
+  } else {
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    pdl_wait();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
-  pdl_wait();
   {   // the bias is staged pre-multiplied by scale_pre so the epilogue is one FFMA per element
     const float sp0 = p.e.scale_pre ? *p.e.scale_pre : 1.f;
     for (int j = threadIdx.x; j < p.BN; j += NTHREADS) bias_s[j] = (p.e.bias && n0 + j < p.N) ? p.e.bias[n0 + j] * sp0 : 0.f;
@@ -329,21 +368,23 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 32) TR(2);
 
   if (warp == 0) {
     // ================= TMA producer
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
-        for (int kb = 0; kb < kblocks; ++kb) {
+      int s = pr_s, kb = pr_kb;
+      uint32_t ph = pr_ph;
+      for (int mt = pr_mt; mt < p.m_tiles; mt += gridDim.x) {
+        for (; kb < kblocks; ++kb) {
           mbar_wait(empty + s, ph ^ 1);
-          uint8_t* sa = smem + s * stage_bytes;
+          uint8_t* sa = ring + s * stage_bytes;
           mbar_expect_tx(full + s, (uint32_t)stage_bytes);
           tma_load_2d(sa, &map_a, full + s, kb * BK, mt * BM);
-          tma_load_2d(sa + a_bytes, &map_w, full + s, kb * BK, n0);
+          if (!p.w_res) tma_load_2d(sa + a_bytes, &map_w, full + s, kb * BK, n0);
           if (++s == STG) { s = 0; ph ^= 1; }
         }
+        kb = 0;
       }
     }
   } else if (warp == 1) {
@@ -352,15 +393,17 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t idesc = make_idesc(BM, p.BN, 0, 0);
       int s = 0, acc = 0;
       uint32_t ph = 0, aph = 0;
+      if (p.w_res) mbar_wait(wfull, 0);
       for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
         mbar_wait(tempty + acc, aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full + s, ph);
+          if (mt == blockIdx.x && kb == 0) TR(3);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
-          const uint32_t sw = sa + a_bytes;
+          const uint32_t sa = smem_u32(ring + s * stage_bytes);
+          const uint32_t sw = p.w_res ? smem_u32(w_res_base + kb * w_bytes) : sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);
@@ -371,6 +414,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (kb == kblocks - 1) umma_commit(tfull + acc);
           if (++s == STG) { s = 0; ph ^= 1; }
         }
+        if (mt == blockIdx.x) TR(4);
+        if (mt + gridDim.x >= p.m_tiles) TR(7);
         if (++acc == 2) { acc = 0; aph ^= 1; }
       }
     }
@@ -398,6 +443,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     uint32_t aph = 0;
     for (int mt = blockIdx.x; mt < p.m_tiles; mt += gridDim.x) {
       mbar_wait(tfull + acc, aph);
+      if (threadIdx.x == 64) { if (mt == blockIdx.x) TR(5); if (mt + gridDim.x >= p.m_tiles) TR(8); }
       tc_fence_after();
       const long row0 = (long)mt * BM + quarter * 32;
       const long my_r = row0 + lane;                                      // this thread's output row
@@ -495,6 +541,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty + acc);
         }
+        if (threadIdx.x == 64) { if (mt == blockIdx.x) TR(6); if (mt + gridDim.x >= p.m_tiles) TR(9); }
         if (++acc == 2) { acc = 0; aph ^= 1; }
         continue;
       }
@@ -575,9 +622,11 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   }
   if (WIDE && warp >= 2 && lane == 0) tma_store_wait_all();   // outstanding TMA stores of this warp
+  if (threadIdx.x == 64) TR(10);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (threadIdx.x == 0) TR(11);
 }
 
 // ------------------------------------------------------------------------------------------------ dW kernel
@@ -800,6 +849,12 @@ int pick_bn(int N) {
 
 }  // namespace
 
+#ifdef QV_GEMM_TRACE
+extern "C" int qavit_test_gemm_trace_read(long long* host128) {
+  return cudaMemcpyFromSymbol(host128, g_trace, sizeof(long long) * 128) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 bool tc_shape_ok_nt(int M, int N, int K, int lda) {
   return M >= 1 && N >= 16 && N % 16 == 0 && K >= 8 && K % 8 == 0 && lda % 8 == 0;
 }
@@ -828,7 +883,20 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
                (!e.gmul || (e.ldg % (e.g_bf16 ? 8 : 4) == 0 && ((uintptr_t)e.gmul & 15) == 0)),
            "tc_gemm_nt: outputs / residual must be 16 B aligned with 16 B-multiple row pitch");
   p.stages = p.BN > 208 ? 3 : STAGES;
-  const size_t smem = 1024 + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2) + 1024 + EPI_WARPS * EPI_WARP_BYTES + 1024;
+  const size_t fixed = 1024 + 1024 + EPI_WARPS * EPI_WARP_BYTES + 1024;      // alignment slack, barriers, epilogue staging, bias
+  size_t smem = fixed + (size_t)p.stages * (BM * BK * 2 + p.BN * BK * 2);
+  {
+    // resident weight slice: worth it when a CTA streams more than one m-tile and the slice leaves room for >= 4 A stages
+    static const int force_res = [] { const char* v = getenv("QV_W_RES"); return v ? atoi(v) : -1; }();
+    const size_t wres = (size_t)cdiv(K, BK) * p.BN * BK * 2;
+    const size_t cap = 227 * 1024;
+    const int gx0 = max(1, min(p.m_tiles, qv_num_sms() / p.n_slices));
+    if (force_res != 0 && wres + fixed + 4 * (size_t)(BM * BK * 2) <= cap && p.m_tiles > gx0) {
+      p.w_res = 1;
+      p.stages = (int)min((size_t)8, (cap - fixed - wres) / (size_t)(BM * BK * 2));
+      smem = fixed + wres + (size_t)p.stages * (BM * BK * 2);
+    }
+  }
   QV_CHECK(smem <= 227 * 1024, "tc_gemm_nt: BN=%d needs %zu B of shared memory", p.BN, smem);
   // plain bf16 output -> the 64-column epilogue
   const bool wide = e.C && !e.C2 && !e.c_f32 && !e.c_accum && !e.gmul;
