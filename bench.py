@@ -39,6 +39,9 @@ DEFAULT_DROPOUT, DEFAULT_DROP_PATH = 0.1, 0.1     # the reference defaults (H:56
 WORKLOADS = {
     "hqavit_c100": dict(family="hqavit", img=32, classes=100, kw={}, ctor={}, fwd_mflop=185.4 + 1.22 + 199.7,
                         label="HQAViT CIFAR-100 32x32"),
+    # HQAViTv2_CIFAR100.py: same blocks around the ConvNeXt-patchify stem (7 LayerScale blocks at 8 x 8: ~205 MFLOP instead of 98.9)
+    "hqavitv2_c100": dict(family="hqavit", img=32, classes=100, kw={}, ctor=dict(variant="v2"), fwd_mflop=185.4 + 1.22 + 305.8,
+                          label="HQAViTv2 CIFAR-100 32x32"),
     "qavitv2_c100": dict(family="qavit", img=32, classes=100, kw={}, ctor=dict(variant="v2"), fwd_mflop=713.4 + 1.22,
                          label="QAViTv2 CIFAR-100 32x32 (= QAViTV2_EXTREME model)"),
     "qavit_224": dict(family="qavit", img=224, classes=100, kw=dict(patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64),

@@ -215,6 +215,14 @@ typedef struct qavit_lateral_cfg {
   int32_t dim, grid;                 /* embed_dim, tokens per side */
   int32_t train, dtype;
   float bn_eps, bn_momentum;
+  /* stem_kind 0: HQAViT_CIFAR100.py's stem (two 3x3 stride-2 conv + BatchNorm + GELU units, H:742-793).
+   * stem_kind 1: HQAViTv2_CIFAR100.py's stem (V:753-833): 4x4 stride-4 patchify conv + LayerNorm([c2, g, g]), 2 / 3 / 2 ConvNeXt
+   *   blocks with LayerScale at c2 / c3 / c4 channels, LayerNorm([C, g, g]) + 1x1 conv between the stages; c_stem is unused.
+   *   stem_drop_path[j]: DropPath rate of ConvNeXt block j (train mode; the reference hard-codes 0, 0, 0, .1, .1, .1, .1); when any
+   *   is > 0, rng = device {seed, offset} Philox state (snapshotted and advanced by forward, like qavit_splitfusion_forward). */
+  int32_t stem_kind;
+  float stem_drop_path[7];
+  unsigned long long* rng;
 } qavit_lateral_cfg;
 int qavit_lateral_param_count(const qavit_lateral_cfg* cfg);
 const char* qavit_lateral_param_name(const qavit_lateral_cfg* cfg, int index);

@@ -65,6 +65,7 @@ class OracleConfig:
     use_token_learner: bool = True
     num_learned_tokens: int = 16
     stage_depths: Tuple[int, ...] = (2, 2, 2, 2)   # TinyIN: (2, 2, 6, 2)
+    stem: str = "v1"                 # hqavit only: "v2" = HQAViTv2_CIFAR100.py's ConvNeXt-patchify stem (V:753-833)
 
 
 def _ln(x: Tensor, sd, prefix: str, eps: float = 1e-5) -> Tensor:
@@ -374,6 +375,45 @@ def cnn_stem(x: Tensor, sd, train: bool, new_stats) -> Tuple[Tensor, Tensor, Ten
     return f2, f3, f4
 
 
+def convnext_v2(x: Tensor, sd, p: str, keep: Optional[Tensor] = None) -> Tensor:
+    """ConvNeXtBlock.forward of HQAViTv2_CIFAR100.py:735-751: LayerScale gamma after pwconv2, then DropPath
+    (``keep``: per-image keep scale [B], None = identity)."""
+    C = x.shape[1]
+    h = _conv(x, sd, p + ".dwconv", padding=3, groups=C).permute(0, 2, 3, 1)
+    h = _ln(h, sd, p + ".norm", eps=1e-6)
+    h = _lin(_gelu(_lin(h, sd, p + ".pwconv1")), sd, p + ".pwconv2")
+    h = (sd[p + ".gamma"] * h).permute(0, 3, 1, 2)
+    if keep is not None:
+        h = h * keep.view(-1, 1, 1, 1)
+    return x + h
+
+
+def _sln(x: Tensor, sd, p: str) -> Tensor:
+    """nn.LayerNorm([C, H, W], eps=1e-6) on an NCHW map (V:765, 776, 790)."""
+    return F.layer_norm(x, x.shape[1:], sd[p + ".weight"], sd[p + ".bias"], 1e-6)
+
+
+V2_STEM_BLOCKS = ("stage2.0", "stage2.1", "stage3.0", "stage3.1", "stage3.2", "stage4.0", "stage4.1")
+
+
+def cnn_stem_v2(x: Tensor, sd, keeps: Optional[dict] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """CNNStemModel.forward of HQAViTv2_CIFAR100.py:811-829.  ``keeps``: {block name: DropPath keep scale [B]}."""
+    p = "cnn_stem"
+    k = keeps or {}
+    h = _sln(_conv(x, sd, p + ".stem.0", stride=4), sd, p + ".stem.1")
+    for b in V2_STEM_BLOCKS[0:2]:
+        h = convnext_v2(h, sd, f"{p}.{b}", k.get(b))
+    f2 = h
+    h = _conv(_sln(f2, sd, p + ".downsample2.0"), sd, p + ".downsample2.1")
+    for b in V2_STEM_BLOCKS[2:5]:
+        h = convnext_v2(h, sd, f"{p}.{b}", k.get(b))
+    f3 = h
+    h = _conv(_sln(f3, sd, p + ".downsample3.0"), sd, p + ".downsample3.1")
+    for b in V2_STEM_BLOCKS[5:7]:
+        h = convnext_v2(h, sd, f"{p}.{b}", k.get(b))
+    return f2, f3, h
+
+
 def lmfa(feat: Tensor, sd, p: str, target_hw: int) -> Tensor:
     """LMFAdapter.forward (H:819-849)."""
     C = feat.shape[1]
@@ -389,8 +429,8 @@ def rrcv(A: Tensor, sd, p: str, cfg: OracleConfig, hw: int) -> Tensor:
     """RRCV.forward (H:880-907)."""
     B, N, C = A.shape
     r = _conv(A.permute(0, 2, 1).reshape(B, C, hw, hw), sd, p + ".reverse_proj")
-    for i in range(cfg.rrcv_num_blocks):
-        r = convnext(r, sd, f"{p}.blocks.{i}")
+    for i in range(cfg.rrcv_num_blocks):      # HQAViTv2's RRCV uses its LayerScale block (drop_path 0), V:895
+        r = convnext_v2(r, sd, f"{p}.blocks.{i}") if cfg.stem == "v2" else convnext(r, sd, f"{p}.blocks.{i}")
     r = _conv(r, sd, p + ".reembed_proj").flatten(2).transpose(1, 2)
     return A + sd[p + ".beta"] * _ln(r, sd, p + ".norm")
 
@@ -441,7 +481,8 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, train: bool = F
     ``new_state`` (train mode) receives the mutated non-autograd state: global_k/global_v,
     update_count and BatchNorm running statistics.  ``mask_fn(block_index, B, tokens)`` (train
     mode, optional) returns the dropout masks of a block (see quad_block); ``mask_fn("pos", B, N)``
-    the keep-scale tensor of pos_drop (H:1251)."""
+    the keep-scale tensor of pos_drop (H:1251); ``mask_fn("stem", B, 0)`` (HQAViTv2 stem) a dict
+    {block name: DropPath keep scale [B]} or None."""
     bank = Bank(sd, cfg)
     blk_no = [0]
 
@@ -460,7 +501,11 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, train: bool = F
 
     if cfg.family == "hqavit":
         hw = (cfg.built_img_size or cfg.img_size) // cfg.patch_size      # LMFAdapter.target_hw = the grid the model was built for
-        f2, f3, f4 = cnn_stem(x, sd, train, new_state)
+        if cfg.stem == "v2":
+            keeps = mask_fn("stem", x.shape[0], 0) if (mask_fn is not None and train) else None
+            f2, f3, f4 = cnn_stem_v2(x, sd, keeps)
+        else:
+            f2, f3, f4 = cnn_stem(x, sd, train, new_state)
         R = [rrcv(lmfa(f, sd, f"lmfa{i}", hw), sd, f"rrcv{i}", cfg, hw) for i, f in ((2, f2), (3, f3), (4, f4))]
         T = pos_drop(patch_embed(x, sd, cfg))
         for st, nblk in enumerate(cfg.stage_depths, start=1):
@@ -621,7 +666,30 @@ def state_schema(cfg: OracleConfig) -> Dict[str, Tuple[Tuple[int, ...], str]]:
     lin("global_bank.write_gate", Kb, d)
     if cfg.family != "qavit_v1":
         S["global_bank.update_count"] = ((), "count")
-    if cfg.family == "hqavit":
+    if cfg.family == "hqavit" and cfg.stem == "v2":
+        g = (cfg.built_img_size or cfg.img_size) // 4
+
+        def sln(k, c):
+            S[k + ".weight"] = ((c, g, g), "ln_w")
+            S[k + ".bias"] = ((c, g, g), "ln_b")
+
+        def cnx2(k, c):
+            S[k + ".gamma"] = ((c,), "ls_gamma")
+            cnx(k, c)
+
+        conv("cnn_stem.stem.0", cfg.cnn_c2, cfg.in_channels, 4)
+        sln("cnn_stem.stem.1", cfg.cnn_c2)
+        cnx2("cnn_stem.stage2.0", cfg.cnn_c2)
+        cnx2("cnn_stem.stage2.1", cfg.cnn_c2)
+        sln("cnn_stem.downsample2.0", cfg.cnn_c2)
+        conv("cnn_stem.downsample2.1", cfg.cnn_c3, cfg.cnn_c2, 1)
+        for i in range(3):
+            cnx2(f"cnn_stem.stage3.{i}", cfg.cnn_c3)
+        sln("cnn_stem.downsample3.0", cfg.cnn_c3)
+        conv("cnn_stem.downsample3.1", cfg.cnn_c4, cfg.cnn_c3, 1)
+        for i in range(2):
+            cnx2(f"cnn_stem.stage4.{i}", cfg.cnn_c4)
+    if cfg.family == "hqavit" and cfg.stem != "v2":
         conv("cnn_stem.stem.0", 32, cfg.in_channels, 3)
         bn("cnn_stem.stem.1", 32)
         conv("cnn_stem.stage1.0", cfg.cnn_c2, 32, 3)
@@ -633,6 +701,7 @@ def state_schema(cfg: OracleConfig) -> Dict[str, Tuple[Tuple[int, ...], str]]:
         conv("cnn_stem.stage3.0", cfg.cnn_c4, cfg.cnn_c3, 1)
         bn("cnn_stem.stage3.1", cfg.cnn_c4)
         cnx("cnn_stem.stage3.2", cfg.cnn_c4)
+    if cfg.family == "hqavit":
         for i, c in ((2, cfg.cnn_c2), (3, cfg.cnn_c3), (4, cfg.cnn_c4)):
             conv(f"lmfa{i}.dwconv_3x3", c, 1, 3)
             conv(f"lmfa{i}.dwconv_5x5", c, 1, 5)
@@ -642,6 +711,8 @@ def state_schema(cfg: OracleConfig) -> Dict[str, Tuple[Tuple[int, ...], str]]:
             S[f"rrcv{i}.beta"] = ((), "beta")
             conv(f"rrcv{i}.reverse_proj", cfg.rrcv_channels, d, 1)
             for j in range(cfg.rrcv_num_blocks):
+                if cfg.stem == "v2":
+                    S[f"rrcv{i}.blocks.{j}.gamma"] = ((cfg.rrcv_channels,), "ls_gamma")
                 cnx(f"rrcv{i}.blocks.{j}", cfg.rrcv_channels)
             conv(f"rrcv{i}.reembed_proj", d, cfg.rrcv_channels, 1)
             ln(f"rrcv{i}.norm", d)
@@ -677,6 +748,7 @@ _KIND_RECIPE = {
     "bank": (0.0, 0.1), "lf": (0.0, 0.15), "scale": (0.1, 0.02), "gamma": (0.5, 0.0),
     "beta": (0.1, 0.0), "fw2": (0.5, 0.3), "fw4": (1.0, 0.5), "pos": (0.0, 0.1),
     "bn_mean": (0.0, 0.1),
+    "ls_gamma": (0.3, 0.1),      # LayerScale: the reference's 1e-6 init would hide every bug behind it
 }
 
 

@@ -13,5 +13,10 @@ from .graph import GraphedTrainStep  # noqa: F401
 from .transfer import adjust_positional_embedding, load_pretrained_except_head  # noqa: F401
 from .evalutil import normalize_batch, tta_views, validate_tta  # noqa: F401
 
-__all__ = ["QAViT", "HQAViT", "QAViTConfig", "HQAViTConfig", "QuadAttentionBlock", "QuadBlockWithTokenLearner",
+def HQAViTv2(config, **kw):
+    """HQAViTv2_CIFAR100.py's ``HQAViT`` (ConvNeXt-patchify CNN stem with LayerScale, V:753-833) -- ``HQAViT(config, variant="v2")``."""
+    return HQAViT(config, variant="v2", **kw)
+
+
+__all__ = ["QAViT", "HQAViT", "HQAViTv2", "QAViTConfig", "HQAViTConfig", "QuadAttentionBlock", "QuadBlockWithTokenLearner",
            "PatchEmbed", "cross_entropy", "FusedAdamW", "clip_grad_norms_", "GradAllReducer", "GraphedTrainStep"]

@@ -32,6 +32,7 @@ class LateralCfg(C.Structure):
         ("c_stem", C.c_int32), ("c2", C.c_int32), ("c3", C.c_int32), ("c4", C.c_int32),
         ("rrcv_channels", C.c_int32), ("rrcv_blocks", C.c_int32), ("dim", C.c_int32), ("grid", C.c_int32),
         ("train", C.c_int32), ("dtype", C.c_int32), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("stem_kind", C.c_int32), ("stem_drop_path", C.c_float * 7), ("rng", C.c_void_p),
     ]
 
 

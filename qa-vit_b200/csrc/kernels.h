@@ -130,6 +130,25 @@ int resize_bilinear_fwd(cudaStream_t s, int dt, const void* in, int B, int Hi, i
 int resize_bilinear_bwd(cudaStream_t s, int dt, const void* dout, int B, int Hi, int Wi, int Ho, int Wo, int C, void* din);
 int rng_snapshot_advance(cudaStream_t s, unsigned long long* rng, unsigned long long* snap);
 
+// ---- HQAViTv2 stem kernels (stem_v2.cu)
+// patch rows [B * (S/p)^2, Cin * p * p] in (c, ky, kx) order -- the conv weight's own order -- for a stride == kernel convolution
+int patch_rows(cudaStream_t s, int dt, const float* img, int B, int Cin, int S, int p, void* col);
+// nn.LayerNorm([C, H, W]) on a channels-last map [B, HW, C]; gamma / beta keep the [C, H, W] layout; stats[B, 2] = mean | rstd
+bool sln_ok(int HW, int C);
+int sln_fwd(cudaStream_t s, int dt, const void* x, int B, int HW, int C, const float* gamma, const float* beta, float eps, void* y,
+            float* stats);
+// dx = [resid +] LN-backward(dy); dx may alias dy; dgamma / dbeta accumulated
+int sln_bwd(cudaStream_t s, int dt, const void* x, const void* dy, int B, int HW, int C, const float* gamma, const float* stats,
+            const void* resid, void* dx, float* dgamma, float* dbeta);
+// LayerScale folded into pwconv2: Ws = diag(gamma) W, bs = gamma * b; finish turns the gradients wrt (Ws, bs) into those of W, b, gamma
+int layerscale_prepare(cudaStream_t s, const float* W, const float* b, const float* gamma, int N, int K, float* Ws, float* bs);
+int layerscale_finish(cudaStream_t s, const float* G, const float* gb, const float* W, const float* b, const float* gamma, int N, int K,
+                      float* dW, float* db, float* dgamma);
+// y = [resid +] rowscale[row / rows_per_img] * x   (y may alias x)
+int scale_rows(cudaStream_t s, int dt, const void* x, long rows, int C, const float* rowscale, int rows_per_img, const void* resid,
+               void* y);
+int stem_droppath_scales(cudaStream_t s, const unsigned long long* rng, uint32_t site0, int n_sites, int B, const float* rates, float* rs);
+
 // ---- dropout / DropPath of the quad block (drop.cu).  Masks come from (rng snapshot, site, element index): backward
 // calls the same function on the gradient.
 //   x[i, j] (T, in place) *= keep(i, j) * (rowscale ? rowscale[i / rows_per_img] : 1)

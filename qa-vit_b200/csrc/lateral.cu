@@ -1,6 +1,8 @@
 // HQAViT's lateral CNN path (scope row f-1) and SplitFusion as native schedules over the kernels of this directory.
 //   qavit_lateral_*     : CNNStemModel (H:742-793) -> 3 x LMFAdapter (H:799-849) -> 3 x RRCV (H:855-907): image in,
 //                         the three refined token maps R2 / R3 / R4 out, one call per direction.
+//                         stem_kind 1 = HQAViTv2_CIFAR100.py's stem (V:753-833: patchify conv, LayerNorm([C, H, W]), LayerScale
+//                         ConvNeXt blocks with DropPath, LayerNorm + 1x1 conv downsampling), same adapters.
 //   qavit_splitfusion_* : SplitFusion (H:913-965).
 // Every pointwise / 1x1 / 3x3-stride-2 convolution and nn.Linear is a GEMM (tcgen05 in bf16 runs, fp32 SIMT in fp32
 // runs) with bias / GELU / residual / GELU-backward epilogues; depthwise stencils, BatchNorm and the LayerNorm-based
@@ -31,12 +33,23 @@ enum { CX_DW_W, CX_DW_B, CX_LN_W, CX_LN_B, CX_W1, CX_B1, CX_W2, CX_B2, CX_N };
 enum { LM_DW3_W, LM_DW3_B, LM_DW5_W, LM_DW5_B, LM_PROJ_W, LM_PROJ_B, LM_LN_W, LM_LN_B, LM_N };
 enum { RR_REV_W, RR_REV_B, RR_RE_W, RR_RE_B, RR_LN_W, RR_LN_B, RR_BETA, RR_N };
 
+// stem_kind 1 (HQAViTv2): stem conv + spatial LN: 4 entries; ConvNeXt block with LayerScale: 9; downsample (spatial LN + 1x1 conv): 4
+enum { S2_CONV_W, S2_CONV_B, S2_LN_W, S2_LN_B, S2_N };
+enum { CX2_GAMMA = CX_N, CX2_N };
+enum { DS_LN_W, DS_LN_B, DS_W, DS_B, DS_N };
+constexpr int V2_BLOCKS = 7;                                   // 2 at c2, 3 at c3, 2 at c4 (V:770-800)
+const int kV2Stage[V2_BLOCKS] = {0, 0, 1, 1, 1, 2, 2};         // feature stage of block j
+
 int cb_base(int i) { return CB_N * i; }
 int cx_base(int i) { return 4 * CB_N + CX_N * i; }
-int lm_base(int i) { return 4 * CB_N + 3 * CX_N + LM_N * i; }
-int rr_stride(const qavit_lateral_cfg& c) { return RR_N + CX_N * c.rrcv_blocks; }
-int rr_base(const qavit_lateral_cfg& c, int i) { return 4 * CB_N + 3 * CX_N + 3 * LM_N + rr_stride(c) * i; }
-int rr_blk(const qavit_lateral_cfg& c, int i, int j) { return rr_base(c, i) + RR_N + CX_N * j; }
+int v2_cx_base(int j) { return S2_N + CX2_N * j; }
+int v2_ds_base(int i) { return S2_N + CX2_N * V2_BLOCKS + DS_N * i; }
+int stem_count(const qavit_lateral_cfg& c) { return c.stem_kind == 1 ? S2_N + CX2_N * V2_BLOCKS + 2 * DS_N : 4 * CB_N + 3 * CX_N; }
+int lm_base(const qavit_lateral_cfg& c, int i) { return stem_count(c) + LM_N * i; }
+int rr_cx_n(const qavit_lateral_cfg& c) { return c.stem_kind == 1 ? CX2_N : CX_N; }   // HQAViTv2's RRCV blocks carry LayerScale too
+int rr_stride(const qavit_lateral_cfg& c) { return RR_N + rr_cx_n(c) * c.rrcv_blocks; }
+int rr_base(const qavit_lateral_cfg& c, int i) { return stem_count(c) + 3 * LM_N + rr_stride(c) * i; }
+int rr_blk(const qavit_lateral_cfg& c, int i, int j) { return rr_base(c, i) + RR_N + rr_cx_n(c) * j; }
 int param_count(const qavit_lateral_cfg& c) { return rr_base(c, 3); }
 
 const char* kCbSfx[CB_N] = {"weight", "bias", "weight", "bias", "running_mean", "running_var", "num_batches_tracked"};
@@ -55,7 +68,23 @@ int check_cfg(const qavit_lateral_cfg& c) {
   QV_CHECK(c.c2 <= 256 && c.c3 <= 256 && c.c4 <= 256 && c.rrcv_channels <= 256 && c.dim <= 256, "lateral: channel counts must be <= 256");
   QV_CHECK(c.rrcv_blocks >= 1 && c.rrcv_blocks <= 4, "lateral: rrcv_blocks %d (1..4)", c.rrcv_blocks);
   QV_CHECK(c.dtype == QV_F32 || c.dtype == QV_BF16, "lateral: dtype %d", c.dtype);
+  QV_CHECK(c.stem_kind == 0 || c.stem_kind == 1, "lateral: stem_kind %d", c.stem_kind);
+  if (c.stem_kind == 1) {
+    const int hw = (c.img_size / 4) * (c.img_size / 4);
+    QV_CHECK(sln_ok(hw, c.c2) && sln_ok(hw, c.c3) && sln_ok(hw, c.c4),
+             "lateral: the HQAViTv2 stem's LayerNorm([C, %d, %d]) maps must hold 2048 / 4096 / 8192 / 16384 elements", c.img_size / 4,
+             c.img_size / 4);
+    QV_CHECK((c.in_channels * 16) % 8 == 0, "lateral: in_channels %d", c.in_channels);
+    for (int j = 0; j < V2_BLOCKS; ++j)
+      QV_CHECK(c.stem_drop_path[j] >= 0.f && c.stem_drop_path[j] < 1.f, "lateral: stem_drop_path[%d] = %f", j, c.stem_drop_path[j]);
+  }
   return 0;
+}
+bool v2_droppath(const qavit_lateral_cfg& c) {
+  if (c.stem_kind != 1 || !c.train) return false;
+  for (int j = 0; j < V2_BLOCKS; ++j)
+    if (c.stem_drop_path[j] > 0.f) return true;
+  return false;
 }
 
 // ------------------------------------------------------------------------------------------------ plan
@@ -63,9 +92,21 @@ struct LinPlan { size_t wb = 0, wbt = 0; int N = 0, K = 0; };
 struct CnxPlan { int C; size_t u, stats, n, hpre, h, out; LinPlan w1, w2; };
 struct CbPlan { int Cin, Cout; size_t c, mr, a, wp; LinPlan w; int Kp; };
 struct LmPlan { int C; size_t cat, pm, p, stats, A, A32; LinPlan w; };   // pm: projection at map resolution (only when it is resized)
-struct RrPlan { size_t r0, r2, stats; CnxPlan blk[4]; LinPlan rev, re; };
+struct RrPlan { size_t r0, r2, stats; CnxPlan blk[4]; size_t w2s[4], b2s[4]; LinPlan rev, re; };
+struct Cx2Plan { CnxPlan x; size_t w2s, b2s; };                                  // + the LayerScale-folded fp32 pwconv2 copies
+struct DsPlan { int Cin, Cout; size_t stats, n, out; LinPlan w; };
+struct StemV2Plan {
+  int K0;                                                                          // in_channels * 16
+  size_t c0, st0, a0, rs, rng;
+  LinPlan w0;
+  Cx2Plan blk[V2_BLOCKS];
+  DsPlan ds[2];
+  size_t col, G, gb;                                                               // scratch
+};
 struct Plan {
   int dt, B, d, nb;
+  int kind;
+  StemV2Plan v2;
   size_t ts;
   long R1, R, Rt;        // rows at the stem resolution (img/2)^2, the feature-map resolution (img/4)^2 and the token grid
   int H1, H, Ht;         // side lengths; Ht != H: LMFAdapter resizes its projection bilinearly (H:839-843)
@@ -110,7 +151,32 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
   const size_t ts = p.ts;
   const int chans[5] = {c.in_channels, c.c_stem, c.c2, c.c3, c.c4};
   Bump b;
-  for (int i = 0; i < 4; ++i) {
+  p.kind = c.stem_kind;
+  if (p.kind == 1) {
+    StemV2Plan& v = p.v2;
+    v.K0 = c.in_channels * 16;
+    v.c0 = b.take(p.R * c.c2 * ts);
+    v.st0 = b.take((size_t)c.batch * 8);
+    v.a0 = b.take(p.R * c.c2 * ts);
+    v.rs = b.take((size_t)V2_BLOCKS * c.batch * 4);
+    v.rng = b.take(16);
+    plan_lin(b, v.w0, c.c2, v.K0, bf);
+    for (int j = 0; j < V2_BLOCKS; ++j) {
+      const int C = chans[2 + kV2Stage[j]];
+      plan_cnx(b, v.blk[j].x, C, p.R, ts, bf);
+      v.blk[j].w2s = b.take((size_t)C * 4 * C * 4);
+      v.blk[j].b2s = b.take((size_t)C * 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      DsPlan& q = v.ds[i];
+      q.Cin = chans[2 + i]; q.Cout = chans[3 + i];
+      q.stats = b.take((size_t)c.batch * 8);
+      q.n = b.take(p.R * q.Cin * ts);
+      q.out = b.take(p.R * q.Cout * ts);
+      plan_lin(b, q.w, q.Cout, q.Cin, bf);
+    }
+  }
+  for (int i = 0; i < 4 && p.kind == 0; ++i) {
     CbPlan& q = p.cb[i];
     q.Cin = chans[i]; q.Cout = chans[i + 1];
     const long rows = i == 0 ? p.R1 : p.R;
@@ -136,7 +202,11 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
   for (int i = 0; i < 3; ++i) {
     RrPlan& q = p.rr[i];
     q.r0 = b.take(p.Rt * c.rrcv_channels * ts);
-    for (int j = 0; j < c.rrcv_blocks; ++j) plan_cnx(b, q.blk[j], c.rrcv_channels, p.Rt, ts, bf);
+    for (int j = 0; j < c.rrcv_blocks; ++j) {
+      plan_cnx(b, q.blk[j], c.rrcv_channels, p.Rt, ts, bf);
+      q.w2s[j] = b.take(c.stem_kind == 1 ? (size_t)c.rrcv_channels * 4 * c.rrcv_channels * 4 : 0);
+      q.b2s[j] = b.take(c.stem_kind == 1 ? (size_t)c.rrcv_channels * 4 : 0);
+    }
     q.r2 = b.take(p.Rt * c.dim * ts);
     q.stats = b.take(p.Rt * 8);
     plan_lin(b, q.rev, c.rrcv_channels, c.dim, bf);
@@ -149,9 +219,14 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
   for (int i = 2; i < 5; ++i) cmax = chans[i] > cmax ? chans[i] : cmax;
   cmax = c.rrcv_channels > cmax ? c.rrcv_channels : cmax;
   int wide = 4 * cmax;
-  if (p.cb[1].Kp > wide) wide = p.cb[1].Kp;
-  p.col0 = s.take(p.R1 * p.cb[0].Kp * ts);
-  p.col1 = s.take(p.R * p.cb[1].Kp * ts);
+  if (p.kind == 0 && p.cb[1].Kp > wide) wide = p.cb[1].Kp;
+  if (p.kind == 1) {
+    p.v2.col = s.take(p.R * p.v2.K0 * ts);
+    p.v2.G = s.take((size_t)cmax * 4 * cmax * 4);
+    p.v2.gb = s.take((size_t)cmax * 4);
+  }
+  p.col0 = s.take(p.kind == 0 ? p.R1 * p.cb[0].Kp * ts : 0);
+  p.col1 = s.take(p.kind == 0 ? p.R * p.cb[1].Kp * ts : 0);
   p.sums = s.take(2 * 2048 * 4);
   const long Rm = p.R > p.Rt ? p.R : p.Rt;
   p.wide = s.take(Rm * wide * ts);
@@ -159,10 +234,10 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
   p.t2 = s.take(Rm * cmax * ts);
   for (int i = 0; i < 3; ++i) p.df[i] = s.take(p.R * chans[i + 2] * ts);
   p.dA = s.take(Rm * c.dim * ts);
-  p.da0 = s.take(p.R1 * c.c_stem * ts);
-  p.dc0 = s.take(p.R1 * c.c_stem * ts);
-  p.dwp0 = s.take((size_t)p.cb[0].Cout * p.cb[0].Kp * 4);
-  p.dwp1 = s.take((size_t)p.cb[1].Cout * p.cb[1].Kp * 4);
+  p.da0 = s.take(p.kind == 0 ? p.R1 * c.c_stem * ts : 0);
+  p.dc0 = s.take(p.kind == 0 ? p.R1 * c.c_stem * ts : 0);
+  p.dwp0 = s.take(p.kind == 0 ? (size_t)p.cb[0].Cout * p.cb[0].Kp * 4 : 0);
+  p.dwp1 = s.take(p.kind == 0 ? (size_t)p.cb[1].Cout * p.cb[1].Kp * 4 : 0);
   p.scratch_total = s.off;
 }
 
@@ -214,8 +289,18 @@ int lin_bwd(const Ctx& c, const void* x, int ldx, const void* dy, long M, const 
   return 0;
 }
 
+// LayerScale + DropPath of HQAViTv2's stem blocks (V:730-748): out = x + rowscale_b * gamma * pwconv2(...).  gamma is folded into
+// the pwconv2 copies w2s / b2s (fp32, in `saved`, made by convert_all); rowscale == nullptr: no DropPath
+struct Ls {
+  size_t w2s, b2s;
+  const float* rowscale;
+  void* tmp;        // [R, C] scratch (fp32 runs with DropPath: the SIMT GEMM has no row-scale epilogue)
+  float* G;         // [C, 4C] + [C] fp32 scratch for the gradients wrt the folded copies
+  float* gb;
+};
+
 // ---- ConvNeXtBlock (H:718-739): out = x + pwconv2(gelu(pwconv1(LN(dwconv7(x)))))
-int cnx_fwd(const Ctx& c, const CnxPlan& x, int pbase, int H, const void* in, void* out) {
+int cnx_fwd(const Ctx& c, const CnxPlan& x, int pbase, int H, const void* in, void* out, const Ls* ls = nullptr) {
   const Plan& P = c.P;
   const int C = x.C, dt = P.dt;
   const long R = (long)P.B * H * H;
@@ -230,19 +315,46 @@ int cnx_fwd(const Ctx& c, const CnxPlan& x, int pbase, int H, const void* in, vo
   QV_TRY(gemm_nt(c.st, dt, c.sv(x.n), C, (int)R, c.W(x.w1, c.pf(pbase + CX_W1)), e1));
   GemmEpi e2;
   e2.bias = c.pf(pbase + CX_B2); e2.resid = in; e2.ldr = C; e2.r_bf16 = dt == QV_BF16; e2.C2 = out; e2.ldc2 = C; e2.c2_f32 = dt == QV_F32;
-  QV_TRY(gemm_nt(c.st, dt, c.sv(x.h), 4 * C, (int)R, c.W(x.w2, c.pf(pbase + CX_W2)), e2));
+  const float* w2 = c.pf(pbase + CX_W2);
+  if (ls) {
+    w2 = static_cast<const float*>(c.sv(ls->w2s));
+    e2.bias = static_cast<const float*>(c.sv(ls->b2s));
+    if (ls->rowscale && dt == QV_BF16) { e2.rowscale = ls->rowscale; e2.rows_per_img = H * H; }
+    if (ls->rowscale && dt == QV_F32) {
+      GemmEpi e = epi(c, e2.bias, ls->tmp, C);
+      QV_TRY(gemm_nt(c.st, dt, c.sv(x.h), 4 * C, (int)R, c.W(x.w2, w2), e));
+      return scale_rows(c.st, dt, ls->tmp, R, C, ls->rowscale, H * H, in, out);
+    }
+  }
+  QV_TRY(gemm_nt(c.st, dt, c.sv(x.h), 4 * C, (int)R, c.W(x.w2, w2), e2));
   return 0;
 }
 // dx may alias dout; wide: [R, 4C] scratch, tmp: [R, C] scratch
-int cnx_bwd(const Ctx& c, const CnxPlan& x, int pbase, int H, const void* in, const void* dout, void* dx, void* wide, void* tmp) {
+int cnx_bwd(const Ctx& c, const CnxPlan& x, int pbase, int H, const void* in, const void* dout, void* dx, void* wide, void* tmp,
+            const Ls* ls = nullptr) {
   const Plan& P = c.P;
   const int C = x.C, dt = P.dt;
   const long R = (long)P.B * H * H;
-  // pwconv2: dW2 += dout^T h;  dhpre = (dout W2) * gelu'(hpre)
-  QV_TRY(gemm_tn(c.st, dt, dout, C, c.sv(x.h), 4 * C, (int)R, C, 4 * C, c.gf(pbase + CX_W2), c.gf(pbase + CX_B2), nullptr));
+  const void* dy = dout;                       // gradient of the (scaled) pwconv2 output
+  const float* w2 = c.pf(pbase + CX_W2);
+  float *dw2 = c.gf(pbase + CX_W2), *db2 = c.gf(pbase + CX_B2);
+  if (ls) {
+    if (ls->rowscale) {                        // DropPath: dy = rowscale_b * dout (tmp is free until the pwconv1 dX GEMM)
+      QV_TRY(scale_rows(c.st, dt, dout, R, C, ls->rowscale, H * H, nullptr, tmp));
+      dy = tmp;
+    }
+    w2 = static_cast<const float*>(c.sv(ls->w2s));
+    dw2 = ls->G; db2 = ls->gb;
+    QV_CUDA(cudaMemsetAsync(ls->G, 0, ((size_t)C * 4 * C + C) * 4, c.st));   // gb follows G (planned back to back)
+  }
+  // pwconv2: dW2 += dy^T h;  dhpre = (dy W2) * gelu'(hpre)
+  QV_TRY(gemm_tn(c.st, dt, dy, C, c.sv(x.h), 4 * C, (int)R, C, 4 * C, dw2, db2, nullptr));
+  if (ls)
+    QV_TRY(layerscale_finish(c.st, ls->G, ls->gb, c.pf(pbase + CX_W2), c.pf(pbase + CX_B2), c.pf(pbase + CX2_GAMMA), C, 4 * C,
+                             c.gf(pbase + CX_W2), c.gf(pbase + CX_B2), c.gf(pbase + CX2_GAMMA)));
   GemmEpi e = epi(c, nullptr, wide, 4 * C);
   e.gmul = c.sv(x.hpre); e.ldg = 4 * C; e.g_bf16 = dt == QV_BF16;
-  QV_TRY(gemm_nn(c.st, dt, dout, C, (int)R, c.W(x.w2, c.pf(pbase + CX_W2)), e));
+  QV_TRY(gemm_nn(c.st, dt, dy, C, (int)R, c.W(x.w2, w2), e));
   // pwconv1
   QV_TRY(gemm_tn(c.st, dt, wide, 4 * C, c.sv(x.n), C, (int)R, 4 * C, C, c.gf(pbase + CX_W1), c.gf(pbase + CX_B1), nullptr));
   QV_TRY(gemm_nn(c.st, dt, wide, 4 * C, (int)R, c.W(x.w1, c.pf(pbase + CX_W1)), epi(c, nullptr, tmp, C)));
@@ -265,8 +377,21 @@ int convert_all(const Ctx& c, bool train) {
   (void)train;
   const Plan& P = c.P;
   const qavit_lateral_cfg& cfg = *c.cfg;
+  if (P.kind == 1) {   // LayerScale folded into fp32 copies of pwconv2 (the source of the bf16 copies below)
+    for (int j = 0; j < V2_BLOCKS; ++j) {
+      const int pb = v2_cx_base(j), C = P.v2.blk[j].x.C;
+      QV_TRY(layerscale_prepare(c.st, c.pf(pb + CX_W2), c.pf(pb + CX_B2), c.pf(pb + CX2_GAMMA), C, 4 * C,
+                                static_cast<float*>(c.sv(P.v2.blk[j].w2s)), static_cast<float*>(c.sv(P.v2.blk[j].b2s))));
+    }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < cfg.rrcv_blocks; ++j) {
+        const int pb = rr_blk(cfg, i, j), C = cfg.rrcv_channels;
+        QV_TRY(layerscale_prepare(c.st, c.pf(pb + CX_W2), c.pf(pb + CX_B2), c.pf(pb + CX2_GAMMA), C, 4 * C,
+                                  static_cast<float*>(c.sv(P.rr[i].w2s[j])), static_cast<float*>(c.sv(P.rr[i].b2s[j]))));
+      }
+  }
   // packed fp32 copies of the two 3x3 stride-2 conv weights (k = (ky, kx, cin) order, zero padded)
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2 && P.kind == 0; ++i)
     QV_TRY(conv_w_pack(c.st, c.pf(cb_base(i) + CB_W), P.cb[i].Cout, P.cb[i].Cin, P.cb[i].Kp, static_cast<float*>(c.sv(P.cb[i].wp))));
   if (P.dt != QV_BF16) return 0;
   ConvertJobs jobs{};
@@ -275,17 +400,27 @@ int convert_all(const Ctx& c, bool train) {
     if (jobs.n == 24) { QV_TRY(convert_weights_batched(c.st, jobs)); jobs.n = 0; }
     return 0;
   };
-  for (int i = 0; i < 4; ++i)
+  if (P.kind == 1) {
+    QV_TRY(add(P.v2.w0, c.pf(S2_CONV_W)));
+    for (int j = 0; j < V2_BLOCKS; ++j) {
+      QV_TRY(add(P.v2.blk[j].x.w1, c.pf(v2_cx_base(j) + CX_W1)));
+      QV_TRY(add(P.v2.blk[j].x.w2, static_cast<const float*>(c.sv(P.v2.blk[j].w2s))));
+    }
+    for (int i = 0; i < 2; ++i) QV_TRY(add(P.v2.ds[i].w, c.pf(v2_ds_base(i) + DS_W)));
+  }
+  for (int i = 0; i < 4 && P.kind == 0; ++i)
     QV_TRY(add(P.cb[i].w, i < 2 ? static_cast<const float*>(c.sv(P.cb[i].wp)) : c.pf(cb_base(i) + CB_W)));
   for (int i = 0; i < 3; ++i) {
-    QV_TRY(add(P.cx[i].w1, c.pf(cx_base(i) + CX_W1)));
-    QV_TRY(add(P.cx[i].w2, c.pf(cx_base(i) + CX_W2)));
-    QV_TRY(add(P.lm[i].w, c.pf(lm_base(i) + LM_PROJ_W)));
+    if (P.kind == 0) {
+      QV_TRY(add(P.cx[i].w1, c.pf(cx_base(i) + CX_W1)));
+      QV_TRY(add(P.cx[i].w2, c.pf(cx_base(i) + CX_W2)));
+    }
+    QV_TRY(add(P.lm[i].w, c.pf(lm_base(cfg, i) + LM_PROJ_W)));
     QV_TRY(add(P.rr[i].rev, c.pf(rr_base(cfg, i) + RR_REV_W)));
     QV_TRY(add(P.rr[i].re, c.pf(rr_base(cfg, i) + RR_RE_W)));
     for (int j = 0; j < cfg.rrcv_blocks; ++j) {
       QV_TRY(add(P.rr[i].blk[j].w1, c.pf(rr_blk(cfg, i, j) + CX_W1)));
-      QV_TRY(add(P.rr[i].blk[j].w2, c.pf(rr_blk(cfg, i, j) + CX_W2)));
+      QV_TRY(add(P.rr[i].blk[j].w2, P.kind == 1 ? static_cast<const float*>(c.sv(P.rr[i].w2s[j])) : c.pf(rr_blk(cfg, i, j) + CX_W2)));
     }
   }
   if (jobs.n) QV_TRY(convert_weights_batched(c.st, jobs));
@@ -322,14 +457,42 @@ extern "C" const char* qavit_lateral_param_name(const qavit_lateral_cfg* cfg, in
   static const char* kCb[4][2] = {{"cnn_stem.stem.0", "cnn_stem.stem.1"}, {"cnn_stem.stage1.0", "cnn_stem.stage1.1"},
                                   {"cnn_stem.stage2.0", "cnn_stem.stage2.1"}, {"cnn_stem.stage3.0", "cnn_stem.stage3.1"}};
   static const char* kCx[3] = {"cnn_stem.stage1.3", "cnn_stem.stage2.2", "cnn_stem.stage3.2"};
+  static const char* kV2Blk[V2_BLOCKS] = {"cnn_stem.stage2.0", "cnn_stem.stage2.1", "cnn_stem.stage3.0", "cnn_stem.stage3.1",
+                                          "cnn_stem.stage3.2", "cnn_stem.stage4.0", "cnn_stem.stage4.1"};
+  if (cfg->stem_kind == 1 && index < stem_count(*cfg)) {
+    static const char* kS2[S2_N] = {"cnn_stem.stem.0.weight", "cnn_stem.stem.0.bias", "cnn_stem.stem.1.weight", "cnn_stem.stem.1.bias"};
+    static const char* kDs[DS_N] = {"0.weight", "0.bias", "1.weight", "1.bias"};
+    if (index < S2_N) {
+      snprintf(buf, sizeof(buf), "%s", kS2[index]);
+    } else if (index < v2_ds_base(0)) {
+      const int j = (index - S2_N) / CX2_N, k = (index - S2_N) % CX2_N;
+      snprintf(buf, sizeof(buf), "%s.%s", kV2Blk[j], k == CX2_GAMMA ? "gamma" : kCxSfx[k]);
+    } else {
+      const int i = (index - v2_ds_base(0)) / DS_N, k = (index - v2_ds_base(0)) % DS_N;
+      snprintf(buf, sizeof(buf), "cnn_stem.downsample%d.%s", i + 2, kDs[k]);
+    }
+    return buf;
+  }
+  if (cfg->stem_kind == 1) {
+    if (index < rr_base(*cfg, 0)) {
+      const int i = (index - lm_base(*cfg, 0)) / LM_N, k = (index - lm_base(*cfg, 0)) % LM_N;
+      snprintf(buf, sizeof(buf), "lmfa%d.%s", i + 2, kLmSfx[k]);
+    } else {
+      const int rel = index - rr_base(*cfg, 0), i = rel / rr_stride(*cfg), k = rel % rr_stride(*cfg);
+      if (k < RR_N) snprintf(buf, sizeof(buf), "rrcv%d.%s", i + 2, kRrSfx[k]);
+      else snprintf(buf, sizeof(buf), "rrcv%d.blocks.%d.%s", i + 2, (k - RR_N) / CX2_N,
+                    (k - RR_N) % CX2_N == CX2_GAMMA ? "gamma" : kCxSfx[(k - RR_N) % CX2_N]);
+    }
+    return buf;
+  }
   if (index < cx_base(0)) {
     const int i = index / CB_N, k = index % CB_N;
     snprintf(buf, sizeof(buf), "%s.%s", kCb[i][k < BN_W ? 0 : 1], kCbSfx[k]);
-  } else if (index < lm_base(0)) {
+  } else if (index < lm_base(*cfg, 0)) {
     const int i = (index - cx_base(0)) / CX_N, k = (index - cx_base(0)) % CX_N;
     snprintf(buf, sizeof(buf), "%s.%s", kCx[i], kCxSfx[k]);
   } else if (index < rr_base(*cfg, 0)) {
-    const int i = (index - lm_base(0)) / LM_N, k = (index - lm_base(0)) % LM_N;
+    const int i = (index - lm_base(*cfg, 0)) / LM_N, k = (index - lm_base(*cfg, 0)) % LM_N;
     snprintf(buf, sizeof(buf), "lmfa%d.%s", i + 2, kLmSfx[k]);
   } else {
     const int rel = index - rr_base(*cfg, 0), i = rel / rr_stride(*cfg), k = rel % rr_stride(*cfg);
@@ -361,10 +524,39 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
   QV_TRY(convert_all(c, train));
   float* sums = static_cast<float*>(c.sc(P.sums));
 
-  // ---- CNNStemModel: (conv -> BN [-> GELU]) x 4 with a ConvNeXt block after units 1..3
   const void* feat[3];
   const void* prev = nullptr;
-  for (int i = 0; i < 4; ++i) {
+  if (P.kind == 1) {
+    // ---- HQAViTv2 stem (V:811-827): patchify conv -> LN([c2, g, g]) -> 2 blocks -> [LN + 1x1 conv -> 3 blocks] -> [... -> 2 blocks]
+    const StemV2Plan& v = P.v2;
+    const int HW = P.H * P.H;
+    const bool dp = v2_droppath(*cfg);
+    float* rs = static_cast<float*>(c.sv(v.rs));
+    if (dp) {
+      QV_CHECK(cfg->rng, "lateral: stem DropPath needs the rng state");
+      QV_TRY(rng_snapshot_advance(st, cfg->rng, static_cast<unsigned long long*>(c.sv(v.rng))));
+      QV_TRY(stem_droppath_scales(st, static_cast<const unsigned long long*>(c.sv(v.rng)), 0x5C00u, V2_BLOCKS, P.B, cfg->stem_drop_path, rs));
+    }
+    QV_TRY(patch_rows(st, dt, img, P.B, cfg->in_channels, cfg->img_size, 4, c.sc(v.col)));
+    QV_TRY(lin_fwd(c, c.sc(v.col), v.K0, P.R, v.w0, c.pf(S2_CONV_W), c.pf(S2_CONV_B), c.sv(v.c0)));
+    QV_TRY(sln_fwd(st, dt, c.sv(v.c0), P.B, HW, cfg->c2, c.pf(S2_LN_W), c.pf(S2_LN_B), 1e-6f, c.sv(v.a0), static_cast<float*>(c.sv(v.st0))));
+    prev = c.sv(v.a0);
+    for (int j = 0; j < V2_BLOCKS; ++j) {
+      if (j > 0 && kV2Stage[j] != kV2Stage[j - 1]) {           // downsample between stages
+        const DsPlan& q = v.ds[kV2Stage[j] - 1];
+        const int pb = v2_ds_base(kV2Stage[j] - 1);
+        QV_TRY(sln_fwd(st, dt, prev, P.B, HW, q.Cin, c.pf(pb + DS_LN_W), c.pf(pb + DS_LN_B), 1e-6f, c.sv(q.n), static_cast<float*>(c.sv(q.stats))));
+        QV_TRY(lin_fwd(c, c.sv(q.n), q.Cin, P.R, q.w, c.pf(pb + DS_W), c.pf(pb + DS_B), c.sv(q.out)));
+        prev = c.sv(q.out);
+      }
+      Ls ls{v.blk[j].w2s, v.blk[j].b2s, (dp && cfg->stem_drop_path[j] > 0.f) ? rs + (size_t)j * P.B : nullptr, c.sc(P.t1), nullptr, nullptr};
+      QV_TRY(cnx_fwd(c, v.blk[j].x, v2_cx_base(j), P.H, prev, c.sv(v.blk[j].x.out), &ls));
+      prev = c.sv(v.blk[j].x.out);
+      feat[kV2Stage[j]] = prev;
+    }
+  }
+  // ---- CNNStemModel: (conv -> BN [-> GELU]) x 4 with a ConvNeXt block after units 1..3
+  for (int i = 0; i < 4 && P.kind == 0; ++i) {
     const CbPlan& q = P.cb[i];
     const int pb = cb_base(i);
     const long rows = i == 0 ? P.R1 : P.R;
@@ -395,7 +587,7 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
   float* Rout[3] = {R2, R3, R4};
   for (int i = 0; i < 3; ++i) {
     const LmPlan& q = P.lm[i];
-    const int pb = lm_base(i), C = q.C;
+    const int pb = lm_base(*cfg, i), C = q.C;
     DwP a{};
     a.x = feat[i]; a.ldx = C; a.B = P.B; a.H = P.H; a.W = P.H; a.C = C; a.K = 3; a.w = c.pf(pb + LM_DW3_W); a.bias = c.pf(pb + LM_DW3_B);
     a.y = c.sv(q.cat); a.ldy = 3 * C;
@@ -414,7 +606,8 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
     QV_TRY(lin_fwd(c, c.sv(q.A), d, P.Rt, r.rev, c.pf(rb + RR_REV_W), c.pf(rb + RR_REV_B), c.sv(r.r0)));
     const void* cur = c.sv(r.r0);
     for (int j = 0; j < cfg->rrcv_blocks; ++j) {
-      QV_TRY(cnx_fwd(c, r.blk[j], rr_blk(*cfg, i, j), P.Ht, cur, c.sv(r.blk[j].out)));
+      Ls ls{r.w2s[j], r.b2s[j], nullptr, nullptr, nullptr, nullptr};
+      QV_TRY(cnx_fwd(c, r.blk[j], rr_blk(*cfg, i, j), P.Ht, cur, c.sv(r.blk[j].out), P.kind == 1 ? &ls : nullptr));
       cur = c.sv(r.blk[j].out);
     }
     QV_TRY(lin_fwd(c, cur, cfg->rrcv_channels, P.Rt, r.re, c.pf(rb + RR_RE_W), c.pf(rb + RR_RE_B), c.sv(r.r2)));
@@ -441,12 +634,13 @@ extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* 
   void* t2 = c.sc(P.t2);
   const float* dRs[3] = {dR2, dR3, dR4};
   const void* feat[3] = {c.sv(P.cx[0].out), c.sv(P.cx[1].out), c.sv(P.cx[2].out)};
+  if (P.kind == 1) { feat[0] = c.sv(P.v2.blk[1].x.out); feat[1] = c.sv(P.v2.blk[4].x.out); feat[2] = c.sv(P.v2.blk[6].x.out); }
 
   // ---- RRCV + LMFAdapter backward per stage: dR_i -> df_i
   for (int i = 2; i >= 0; --i) {
     const LmPlan& q = P.lm[i];
     const RrPlan& r = P.rr[i];
-    const int rb = rr_base(*cfg, i), pb = lm_base(i), C = q.C;
+    const int rb = rr_base(*cfg, i), pb = lm_base(*cfg, i), C = q.C;
     void* df = c.sc(P.df[i]);
     void* dA = c.sc(P.dA);
     if (dRs[i] == nullptr) {   // this stage's fusion is not part of the graph
@@ -460,7 +654,9 @@ extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* 
     QV_TRY(lin_bwd(c, last, rc, t1, P.Rt, r.re, c.pf(rb + RR_RE_W), c.gf(rb + RR_RE_W), c.gf(rb + RR_RE_B), t2, nullptr));
     for (int j = cfg->rrcv_blocks - 1; j >= 0; --j) {
       const void* in = j == 0 ? c.sv(r.r0) : c.sv(r.blk[j - 1].out);
-      QV_TRY(cnx_bwd(c, r.blk[j], rr_blk(*cfg, i, j), P.Ht, in, t2, t2, wide, t1));
+      float* G = P.kind == 1 ? static_cast<float*>(c.sc(P.v2.G)) : nullptr;
+      Ls ls{r.w2s[j], r.b2s[j], nullptr, nullptr, G, G ? G + (size_t)rc * 4 * rc : nullptr};
+      QV_TRY(cnx_bwd(c, r.blk[j], rr_blk(*cfg, i, j), P.Ht, in, t2, t2, wide, t1, P.kind == 1 ? &ls : nullptr));
     }
     // dA = dR + dr0 W_rev
     QV_TRY(lin_bwd(c, c.sv(q.A), d, t2, P.Rt, r.rev, c.pf(rb + RR_REV_W), c.gf(rb + RR_REV_W), c.gf(rb + RR_REV_B), dA, dRs[i], true));
@@ -487,6 +683,38 @@ extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* 
     QV_TRY(dw2d_fwd(st, dt, a, true));
   }
 
+  if (P.kind == 1) {
+    // ---- HQAViTv2 stem backward: blocks 6 .. 0; the gradient of a stage's feature map (df[stage], from its LMFAdapter) joins at
+    // the stage's last block, the downsample's gradient is added to the previous stage's df by the LayerNorm backward
+    const StemV2Plan& v = P.v2;
+    const int HW = P.H * P.H;
+    const bool dp = v2_droppath(*cfg);
+    const float* rs = static_cast<const float*>(c.sv(v.rs));
+    float* G = static_cast<float*>(c.sc(v.G));
+    for (int j = V2_BLOCKS - 1; j >= 0; --j) {
+      const int stg = kV2Stage[j], C = v.blk[j].x.C;
+      const bool last_of_stage = j == V2_BLOCKS - 1 || kV2Stage[j + 1] != stg;
+      const bool first_of_stage = j == 0 || kV2Stage[j - 1] != stg;
+      const void* in = first_of_stage ? (stg == 0 ? c.sv(v.a0) : c.sv(v.ds[stg - 1].out)) : c.sv(v.blk[j - 1].x.out);
+      const void* dout = last_of_stage ? c.sc(P.df[stg]) : t2;
+      Ls ls{v.blk[j].w2s, v.blk[j].b2s, (dp && cfg->stem_drop_path[j] > 0.f) ? rs + (size_t)j * P.B : nullptr, nullptr, G, G + (size_t)C * 4 * C};
+      QV_TRY(cnx_bwd(c, v.blk[j].x, v2_cx_base(j), P.H, in, dout, t2, wide, t1, &ls));
+      if (first_of_stage && stg > 0) {        // downsample: 1x1 conv, then LN([Cin, g, g]) of the previous stage's feature map
+        const DsPlan& q = v.ds[stg - 1];
+        const int pb = v2_ds_base(stg - 1);
+        QV_TRY(lin_bwd(c, c.sv(q.n), q.Cin, t2, P.R, q.w, c.pf(pb + DS_W), c.gf(pb + DS_W), c.gf(pb + DS_B), t1, nullptr));
+        void* dprev = c.sc(P.df[stg - 1]);
+        QV_TRY(sln_bwd(st, dt, feat[stg - 1], t1, P.B, HW, q.Cin, c.pf(pb + DS_LN_W), static_cast<const float*>(c.sv(q.stats)), dprev, dprev,
+                       c.gf(pb + DS_LN_W), c.gf(pb + DS_LN_B)));
+      }
+    }
+    // stem: LN([c2, g, g]) backward, then the patchify conv's weight / bias gradient (the image receives none)
+    QV_TRY(sln_bwd(st, dt, c.sv(v.c0), t2, P.B, HW, cfg->c2, c.pf(S2_LN_W), static_cast<const float*>(c.sv(v.st0)), nullptr, t1,
+                   c.gf(S2_LN_W), c.gf(S2_LN_B)));
+    QV_TRY(patch_rows(st, dt, img, P.B, cfg->in_channels, cfg->img_size, 4, c.sc(v.col)));
+    QV_TRY(lin_bwd(c, c.sc(v.col), v.K0, t1, P.R, v.w0, c.pf(S2_CONV_W), c.gf(S2_CONV_W), c.gf(S2_CONV_B), nullptr, nullptr));
+    return 0;
+  }
   // ---- CNN stem backward: units 3, 2, 1 (ConvNeXt -> BN -> conv), then unit 0
   for (int i = 3; i >= 1; --i) {
     const CbPlan& q = P.cb[i];

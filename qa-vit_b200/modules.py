@@ -448,6 +448,37 @@ class ConvNeXtBlock(_LateralHolder):
         self.pwconv2 = nn.Linear(4 * dim, dim)
 
 
+class ConvNeXtBlockV2(_LateralHolder):
+    """HQAViTv2_CIFAR100.py:718-751: ConvNeXt block with LayerScale ``gamma`` and DropPath (``drop_path_rate``)."""
+
+    def __init__(self, dim, drop_path=0., layer_scale_init_value=1e-6):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, kernel_size=7, padding=3, groups=dim)
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.pwconv1 = nn.Linear(dim, 4 * dim)
+        self.act = nn.GELU()
+        self.pwconv2 = nn.Linear(4 * dim, dim)
+        self.gamma = nn.Parameter(layer_scale_init_value * torch.ones(dim))
+        self.drop_path_rate = float(drop_path)
+
+
+class CNNStemModelV2(_LateralHolder):
+    """HQAViTv2_CIFAR100.py:753-833: 4x4 patchify stem + LayerNorm([c2, g, g]); stages of 2 / 3 / 2 LayerScale ConvNeXt blocks at
+    c2 / c3 / c4 channels on the g x g map, LayerNorm([C, g, g]) + 1x1 conv between them.  (The reference hard-codes g = 8.)"""
+
+    def __init__(self, in_ch=3, c2=64, c3=128, c4=256, grid=8):
+        super().__init__()
+        self.stem = nn.Sequential(nn.Conv2d(in_ch, c2, kernel_size=4, stride=4), nn.LayerNorm([c2, grid, grid], eps=1e-6))
+        self.stage2 = nn.Sequential(ConvNeXtBlockV2(c2, 0.0), ConvNeXtBlockV2(c2, 0.0))
+        self.downsample2 = nn.Sequential(nn.LayerNorm([c2, grid, grid], eps=1e-6), nn.Conv2d(c2, c3, kernel_size=1))
+        self.stage3 = nn.Sequential(ConvNeXtBlockV2(c3, 0.0), ConvNeXtBlockV2(c3, 0.1), ConvNeXtBlockV2(c3, 0.1))
+        self.downsample3 = nn.Sequential(nn.LayerNorm([c3, grid, grid], eps=1e-6), nn.Conv2d(c3, c4, kernel_size=1))
+        self.stage4 = nn.Sequential(ConvNeXtBlockV2(c4, 0.1), ConvNeXtBlockV2(c4, 0.1))
+
+    def blocks_in_order(self):
+        return [*self.stage2, *self.stage3, *self.stage4]
+
+
 class CNNStemModel(_LateralHolder):
     """H:742-793."""
 
@@ -475,10 +506,11 @@ class LMFAdapter(_LateralHolder):
 class RRCV(_LateralHolder):
     """H:855-907."""
 
-    def __init__(self, embed_dim: int, rec_channels: int = 64, num_blocks: int = 1):
+    def __init__(self, embed_dim: int, rec_channels: int = 64, num_blocks: int = 1, layer_scale: bool = False):
         super().__init__()
         self.reverse_proj = nn.Conv2d(embed_dim, rec_channels, 1)
-        self.blocks = nn.ModuleList([ConvNeXtBlock(rec_channels) for _ in range(num_blocks)])
+        blk = ConvNeXtBlockV2 if layer_scale else ConvNeXtBlock       # HQAViTv2's RRCV blocks carry LayerScale (V:718-751, 895)
+        self.blocks = nn.ModuleList([blk(rec_channels) for _ in range(num_blocks)])
         self.reembed_proj = nn.Conv2d(rec_channels, embed_dim, 1)
         self.norm = nn.LayerNorm(embed_dim)
         self.beta = nn.Parameter(torch.tensor(0.1))
@@ -518,8 +550,10 @@ class HQAViT(_Base):
     """H:1141-1277.  ``stage_depths`` = (2, 2, 2, 2) for CIFAR-100, (2, 2, 6, 2) for TinyImageNet
     (HQAViT_IN_Tiny.py:1399-1420; that file also forces a square number of learned tokens)."""
 
-    def __init__(self, config, stage_depths: Optional[Tuple[int, ...]] = None, square_tokens: bool = False):
+    def __init__(self, config, stage_depths: Optional[Tuple[int, ...]] = None, square_tokens: bool = False, variant: str = "v1"):
         super().__init__()
+        assert variant in ("v1", "v2"), variant      # v2: HQAViTv2_CIFAR100.py (same model around a ConvNeXt-patchify stem)
+        self.variant = variant
         self.config = config
         d = config.embed_dim
         if stage_depths is None:
@@ -532,13 +566,16 @@ class HQAViT(_Base):
         self.pos_embed = nn.Parameter(torch.zeros(1, self.num_patches, d))
         self.pos_drop = nn.Dropout(config.dropout)
         self.global_bank = GlobalTokenBank(config.global_bank_size, d)
-        self.cnn_stem = CNNStemModel(config.in_channels, config.cnn_c2, config.cnn_c3, config.cnn_c4)
+        if variant == "v2":
+            self.cnn_stem = CNNStemModelV2(config.in_channels, config.cnn_c2, config.cnn_c3, config.cnn_c4, grid=config.img_size // 4)
+        else:
+            self.cnn_stem = CNNStemModel(config.in_channels, config.cnn_c2, config.cnn_c3, config.cnn_c4)
         self.lmfa2 = LMFAdapter(config.cnn_c2, d, target_hw=self.H)
         self.lmfa3 = LMFAdapter(config.cnn_c3, d, target_hw=self.H)
         self.lmfa4 = LMFAdapter(config.cnn_c4, d, target_hw=self.H)
-        self.rrcv2 = RRCV(d, config.rrcv_channels, config.rrcv_num_blocks)
-        self.rrcv3 = RRCV(d, config.rrcv_channels, config.rrcv_num_blocks)
-        self.rrcv4 = RRCV(d, config.rrcv_channels, config.rrcv_num_blocks)
+        self.rrcv2 = RRCV(d, config.rrcv_channels, config.rrcv_num_blocks, variant == "v2")
+        self.rrcv3 = RRCV(d, config.rrcv_channels, config.rrcv_num_blocks, variant == "v2")
+        self.rrcv4 = RRCV(d, config.rrcv_channels, config.rrcv_num_blocks, variant == "v2")
         self.fuse2 = SplitFusion(d)
         self.fuse3 = SplitFusion(d)
         self.fuse4 = SplitFusion(d)
@@ -561,15 +598,34 @@ class HQAViT(_Base):
         cfg = self.config
         c = LateralCfg()
         c.batch, c.img_size, c.in_channels = x.shape[0], x.shape[-1], x.shape[1]
-        c.c_stem = self.cnn_stem.stem[0].out_channels
-        c.c2, c.c3, c.c4 = (self.cnn_stem.stage1[0].out_channels, self.cnn_stem.stage2[0].out_channels,
-                            self.cnn_stem.stage3[0].out_channels)
+        v2 = self.variant == "v2"
+        rng = None
+        if v2:
+            c.stem_kind = 1
+            c.c_stem = 32
+            c.c2, c.c3, c.c4 = (self.cnn_stem.stem[0].out_channels, self.cnn_stem.downsample2[1].out_channels,
+                                self.cnn_stem.downsample3[1].out_channels)
+            for j, blk in enumerate(self.cnn_stem.blocks_in_order()):
+                c.stem_drop_path[j] = float(blk.drop_path_rate)
+            if self.training and any(blk.drop_path_rate > 0 for blk in self.cnn_stem.blocks_in_order()):
+                # its own Philox state: the lateral path runs on a side stream next to calls that advance the shared one
+                if getattr(self, "_stem_rng", None) is None or self._stem_rng.device != x.device:
+                    seed = torch.initial_seed() if QF._rng_seed is None else QF._rng_seed
+                    object.__setattr__(self, "_stem_rng", torch.tensor([(seed ^ 0x5C5C5C5C) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64,
+                                                                       device=x.device))
+                rng = self._stem_rng
+                c.rng = rng.data_ptr()
+        else:
+            c.c_stem = self.cnn_stem.stem[0].out_channels
+            c.c2, c.c3, c.c4 = (self.cnn_stem.stage1[0].out_channels, self.cnn_stem.stage2[0].out_channels,
+                                self.cnn_stem.stage3[0].out_channels)
         c.rrcv_channels, c.rrcv_blocks = self.rrcv2.reverse_proj.out_channels, len(self.rrcv2.blocks)
         c.dim, c.grid = cfg.embed_dim, self.H
         c.train = 1 if self.training else 0
         c.dtype = QF.resolve_dtype(self.precision)
-        bn = self.cnn_stem.stem[1]
-        c.bn_eps, c.bn_momentum = float(bn.eps), float(bn.momentum)
+        if not v2:
+            bn = self.cnn_stem.stem[1]
+            c.bn_eps, c.bn_momentum = float(bn.eps), float(bn.momentum)
         if self._lateral_names is None:
             self._lateral_names = lateral_param_names(c)
         names = self._lateral_names

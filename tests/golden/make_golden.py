@@ -44,6 +44,8 @@ CASES = {
     # the lateral path runs on 24 x 24 maps and LMFAdapter resizes them bilinearly to 8 x 8 (H:839-843)
     "hqavit_stl96": ("HQAViT_CIFAR100", "HQAViT", "HQAViTConfig", {},
                      dict(family="hqavit", img_size=96, built_img_size=32, num_classes=10), 2),
+    # HQAViTv2_CIFAR100.py: the same model around a ConvNeXt-patchify stem (LayerNorm([C, 8, 8]), LayerScale, DropPath), V:753-833
+    "hqavitv2_c100": ("HQAViTv2_CIFAR100", "HQAViT", "HQAViTConfig", {}, dict(family="hqavit", stem="v2"), 2),
     "hqavit_tinyin": ("HQAViT_IN_Tiny", "HQAViT", "HQAViTConfig", {},
                       dict(family="hqavit", img_size=64, num_classes=200, depth=12, num_learned_tokens=64,
                            stage_depths=(2, 2, 6, 2)), 2),
@@ -71,6 +73,10 @@ def build_reference(case):
     for n in ("fuse2", "fuse3", "fuse4"):                   # hidden Dropout(0.1), H:930
         if hasattr(model, n):
             getattr(model, n).cat_mlp[3].p = 0.0
+    if hasattr(model, "cnn_stem"):                          # hard-coded DropPath(0.1) of HQAViTv2's stem blocks, V:787-799
+        for m in model.cnn_stem.modules():
+            if hasattr(m, "drop_path"):
+                m.drop_path = torch.nn.Identity()
     ocfg = O.OracleConfig(**okw)
     if ocfg.built_img_size and ocfg.built_img_size != ocfg.img_size:      # the reference's own transfer recipe
         stl = import_reference("HQAViT_Tiny_stl10")

@@ -174,3 +174,44 @@ def test_model_trains_with_reference_default_dropout(precision):
         model.eval()
         e1, e2 = model(x), model(x)
         assert torch.equal(e1, e2)                                    # eval: no dropout
+
+
+def test_hqavitv2_stem_droppath_matches_oracle():
+    """DropPath of the HQAViTv2 stem's ConvNeXt blocks (HQAViTv2_CIFAR100.py:748, 787-799): per-image keep scales drawn in-kernel
+    (site 0x5C00 + block, element = image) against the oracle fed the restated scales -- whole model, fp32 run, all gradients."""
+    import qavit_b200 as Q
+    from dropout_masks import Site
+    model, ocfg, sd, _ = build_model("hqavitv2_c100", precision="fp32")
+    model.train()
+    rates = [0.0, 0.3, 0.0, 0.25, 0.1, 0.4, 0.2]
+    for blk, r in zip(model.cnn_stem.blocks_in_order(), rates):
+        blk.drop_path_rate = r
+    B = 6
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    y = torch.randint(0, 100, (B,), generator=g)
+    seed, offset = 0x0BADC0FFEE123, 40
+    object.__setattr__(model, "_stem_rng", torch.tensor([seed, offset], dtype=torch.int64, device="cuda"))
+    logits = model(x.cuda())
+    loss = Q.cross_entropy(logits, y.cuda(), label_smoothing=0.1)
+    loss.backward()
+    assert model._stem_rng.tolist()[1] > offset          # the state advanced on the device
+
+    keeps = {name: Site(seed, offset, 0x5C00 + j, r).keep1(np.arange(B)) for j, (name, r) in enumerate(zip(O.V2_STEM_BLOCKS, rates)) if r > 0}
+    assert any((k == 0).any() for k in keeps.values()), "pick a seed that drops something"
+
+    def mask_fn(which, Bq, n):
+        return keeps if which == "stem" else None
+    ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd, ocfg, x, y, label_smoothing=0.1, mask_fn=mask_fn)
+    assert rel_max(logits, ref_logits) < 1e-4
+    assert abs(loss.item() - ref_loss.item()) < 2e-5
+    named = dict(model.named_parameters())
+    num = den = 0.0
+    for k, gr in ref_grads.items():
+        if gr is None:
+            continue
+        num += (named[k].grad.cpu() - gr).norm().item() ** 2
+        den += gr.norm().item() ** 2
+    assert (num / den) ** 0.5 < 1e-4
+    for k in ("cnn_stem.stage3.1.gamma", "cnn_stem.stage4.0.pwconv2.weight", "cnn_stem.stem.0.weight", "cnn_stem.downsample2.0.weight"):
+        assert rel_l2(named[k].grad, ref_grads[k]) < 5e-4, k

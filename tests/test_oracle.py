@@ -111,7 +111,7 @@ def test_three_optimizer_steps_match_reference_golden(case):
 
 
 @pytest.mark.skipif(not os.path.isdir(MG.REF), reason="live reference not mounted (GPU box)")
-@pytest.mark.parametrize("case", ["hqavit_c100", "qavitv2_c100", "qavit_v1_224"])
+@pytest.mark.parametrize("case", ["hqavit_c100", "qavitv2_c100", "qavit_v1_224", "hqavitv2_c100"])
 def test_oracle_equals_live_reference_in_fp64(case):
     """In double precision the restatement and the reference agree to rounding on every gradient element."""
     model, cfg, B = MG.build_reference(case)

@@ -31,6 +31,7 @@ CASES = {
     "qavitv2b_224": (dict(family="qavit_v2", img_size=224, patch_size=16, window_size=7, dilation_factors=(1, 2, 3), linformer_k=64,
                           dwconv_bias=True), "qavit", dict(variant="v2b"), 2),
     "hqavit_stl96": (dict(family="hqavit", img_size=96, built_img_size=32, num_classes=10), "hqavit", {}, 2),
+    "hqavitv2_c100": (dict(family="hqavit", stem="v2"), "hqavit", dict(variant="v2"), 2),
     "hqavit_tinyin": (dict(family="hqavit", img_size=64, num_classes=200, depth=12, num_learned_tokens=64,
                            stage_depths=(2, 2, 6, 2)), "hqavit", dict(square_tokens=True), 2),
 }
@@ -49,6 +50,9 @@ def build_model(case, device="cuda", precision="fp32"):
         model = Q.HQAViT(cfg, stage_depths=ocfg.stage_depths, **ckw)
         for n in ("fuse2", "fuse3", "fuse4"):
             getattr(model, n).cat_mlp[3].p = 0.0
+        if model.variant == "v2":                      # hard-coded DropPath(0.1) of the v2 stem's blocks
+            for blk in model.cnn_stem.blocks_in_order():
+                blk.drop_path_rate = 0.0
     else:
         cfg = Q.QAViTConfig(**common)
         model = Q.QAViT(cfg, **ckw)
