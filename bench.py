@@ -265,34 +265,52 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def gemm_roofline(device, batch):
-    """Dominant kernel (tc_gemm_nt_kernel, ~21 % of the step over 358 launches) at its largest block shape, the SWA qkv
-    projection [B*16, 192] x [576, 192]^T, timed alone with CUDA events on the launching stream, L2 flushed before
-    every launch.  The step itself is a CUDA graph, so per-kernel events cannot be placed inside it; the kernel's share
-    of the step comes from the ncu launch list in profiles/."""
+    """Dominant kernel (tc_gemm_nt_kernel, ~21 % of the step over ~280 launches) at its largest block shape, the SWA qkv
+    projection [B*16, 192] x [576, 192]^T.  The step is a CUDA graph, so per-kernel events cannot be placed inside it; the
+    kernel is timed live on its own launching stream with CUDA events in two ways:
+      train  : 48 launches back to back between ONE pair of events, rotating over 6 operand sets (6 x 116 MB >> 126 MB L2, so no
+               launch finds its operands in cache) -> average launch duration in the middle of a stream of kernels, which is how it
+               runs inside the step (roofline.achieved uses this one);
+      single : one launch between a pair of events, L2 flushed before -- includes ~7 us of event / launch latency that the kernel
+               never pays inside the graph (in-kernel clock64 trace, tools/gemm_trace.py: 25 us from first CTA start to last CTA exit).
+    Returns (t_train, t_single, algorithmic bytes, flops, shape)."""
     import math
     from qavit_b200 import _lib as L
     M, N, K = batch * 16, 576, 192
-    A = torch.randn(M, K, device=device).bfloat16()
     W = torch.randn(N, K, device=device) / math.sqrt(K)
     Wb = W.bfloat16()
     bias = torch.zeros(N, device=device)
-    C = torch.empty(M, N, device=device, dtype=torch.bfloat16)
+    sets = [(torch.randn(M, K, device=device).bfloat16(), torch.empty(M, N, device=device, dtype=torch.bfloat16)) for _ in range(6)]
     flush = torch.empty(1 << 30, dtype=torch.uint8, device=device)   # > L2; also keeps the GPU busy while the launch is enqueued
     s = torch.cuda.current_stream().cuda_stream
-    ts = []
+
+    def launch(A, C):
+        L.check(L.lib.qavit_test_gemm_nt(1, A.data_ptr(), K, M, N, K, W.data_ptr(), Wb.data_ptr(), bias.data_ptr(), C.data_ptr(), 0, s))
+
+    singles = []
     for i in range(8):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        L.check(L.lib.qavit_test_gemm_nt(1, A.data_ptr(), K, M, N, K, W.data_ptr(), Wb.data_ptr(), bias.data_ptr(), C.data_ptr(), 0, s))
+        launch(*sets[0])
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
-            ts.append(e0.elapsed_time(e1) * 1e-3)
-    t = sum(ts) / len(ts)
+            singles.append(e0.elapsed_time(e1) * 1e-3)
+    trains, R = [], 48
+    for i in range(5):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(R):
+            launch(*sets[r % len(sets)])
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            trains.append(e0.elapsed_time(e1) * 1e-3 / R)
     bytes_alg = M * K * 2 + N * K * 2 + M * N * 2
     flops = 2.0 * M * N * K
-    return t, bytes_alg, flops, (M, N, K)
+    return sum(trains) / len(trains), sum(singles) / len(singles), bytes_alg, flops, (M, N, K)
 
 
 def measured_traffic(shape):
@@ -444,9 +462,13 @@ def run_ours(args):
 
     if rank == 0:
         hbm, tf_burst, tf_sus, src = peaks()
-        t_g, bytes_g, flops_g, shape_g = gemm_roofline(dev, B)
-        roof = {"kernel": f"tc_gemm_nt_kernel (SWA qkv projection, M={shape_g[0]} N={shape_g[1]} K={shape_g[2]}, timed alone, L2 flushed)",
+        t_g, t_single, bytes_g, flops_g, shape_g = gemm_roofline(dev, B)
+        roof = {"kernel": f"tc_gemm_nt_kernel (SWA qkv projection, M={shape_g[0]} N={shape_g[1]} K={shape_g[2]})",
+                "timing": "CUDA events around 48 back-to-back launches on the launching stream, 6 rotating operand sets (700 MB >> L2): "
+                          "average launch duration; single_launch_us = one launch per event pair, L2 flushed (adds ~7 us of event / "
+                          "launch latency)",
                 "bound": "hbm", "achieved": bytes_g / t_g / 1e9, "peak": hbm, "unit": "GB/s", "frac": bytes_g / t_g / 1e9 / hbm,
+                "launch_us": t_g * 1e6, "single_launch_us": t_single * 1e6, "frac_single_launch": bytes_g / t_single / 1e9 / hbm,
                 "traffic": measured_traffic(shape_g), "algorithmic_bytes": bytes_g, "peak_source": src + " (burst: kernel timed alone)",
                 "tensor_tflops": flops_g / t_g / 1e12,
                 "tensor_frac_of_burst": flops_g / t_g / 1e12 / tf_burst}

@@ -229,6 +229,22 @@ const char* qavit_lateral_param_name(const qavit_lateral_cfg* cfg, int index);
 int qavit_lateral_workspace(const qavit_lateral_cfg* cfg, size_t* saved_bytes, size_t* scratch_bytes);
 int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* const* params, const float* img, float* R2, float* R3,
                           float* R4, void* saved, void* scratch, void* stream);
+/* The same path in phases, so that a caller can overlap it with the token path stage by stage (R_i is first needed by fuse_i;
+ * dR_i is known right after fuse_i's backward): `parts` selects the stem (feature maps kept in `saved`; its backward consumes the
+ * three feature-map gradients, which the adapters' backward leaves in `saved`) and / or the LMFAdapter + RRCV chain of stage 2 / 3 / 4.
+ * Forward: the stem part must run first (it also makes the bf16 weight copies of every part).  Backward: every adapter part must
+ * have run (with dR_i == NULL if that stage took no part in the loss) before the stem part.  All parts of one forward / backward
+ * share `saved`; calls that may run concurrently need distinct `scratch`. */
+#define QAVIT_LATERAL_STEM 1u
+#define QAVIT_LATERAL_ADAPTER2 2u
+#define QAVIT_LATERAL_ADAPTER3 4u
+#define QAVIT_LATERAL_ADAPTER4 8u
+#define QAVIT_LATERAL_ALL 15u
+int qavit_lateral_forward_parts(const qavit_lateral_cfg* cfg, const void* const* params, const float* img, float* R2, float* R3,
+                                float* R4, void* saved, void* scratch, void* stream, unsigned parts);
+int qavit_lateral_backward_parts(const qavit_lateral_cfg* cfg, const void* const* params, float* const* grads, const float* img,
+                                 const float* dR2, const float* dR3, const float* dR4, const void* saved, void* scratch, void* stream,
+                                 unsigned parts);
 /* dR2..dR4 may be NULL (stage not fused); parameter gradients are accumulated; the image receives no gradient. */
 int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* const* params, float* const* grads, const float* img,
                            const float* dR2, const float* dR3, const float* dR4, const void* saved, void* scratch, void* stream);

@@ -89,6 +89,9 @@ _SIGS = {
     "qavit_lateral_workspace": (_i, [C.POINTER(LateralCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "qavit_lateral_forward": (_i, [C.POINTER(LateralCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "qavit_lateral_backward": (_i, [C.POINTER(LateralCfg), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qavit_lateral_forward_parts": (_i, [C.POINTER(LateralCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint]),
+    "qavit_lateral_backward_parts": (_i, [C.POINTER(LateralCfg), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                          C.c_uint]),
     "qavit_splitfusion_param_name": (C.c_char_p, [_i]),
     "qavit_splitfusion_workspace": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "qavit_splitfusion_forward": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -571,8 +571,8 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   // ---- CGA (H:559-595)
   nvtxRangePop(); nvtxRangePushA("cga");
   QV_TRY(snapshot_bank(c, 2));
-  QV_TRY(small_linear_fwd(st, snap_k(c, 2), D.kb, d, c.pf(QP_CGA_BK_W), c.pf(QP_CGA_BK_B), D.cpg, c.svf(S.kbp)));
-  QV_TRY(small_linear_fwd(st, snap_v(c, 2), D.kb, d, c.pf(QP_CGA_BV_W), c.pf(QP_CGA_BV_B), D.cpg, c.svf(S.vbp)));
+  QV_TRY(small_linear_fwd2(st, D.kb, d, D.cpg, snap_k(c, 2), c.pf(QP_CGA_BK_W), c.pf(QP_CGA_BK_B), c.svf(S.kbp),
+                           snap_v(c, 2), c.pf(QP_CGA_BV_W), c.pf(QP_CGA_BV_B), c.svf(S.vbp)));
   {
     CgaP p{};
     p.B = D.B; p.Nt = D.Nt; p.G = D.G; p.H = D.H; p.kb = D.kb; p.cg = D.cg; p.cpg = D.cpg;
@@ -590,8 +590,8 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   // ---- Cross (H:613-626)
   nvtxRangePop(); nvtxRangePushA("cross");
   QV_TRY(snapshot_bank(c, 3));
-  QV_TRY(small_linear_fwd(st, snap_k(c, 3), D.kb, d, c.pf(QP_CROSS_K_W), c.pf(QP_CROSS_K_B), d, c.svf(S.Kc)));
-  QV_TRY(small_linear_fwd(st, snap_v(c, 3), D.kb, d, c.pf(QP_CROSS_V_W), c.pf(QP_CROSS_V_B), d, c.svf(S.Vc)));
+  QV_TRY(small_linear_fwd2(st, D.kb, d, d, snap_k(c, 3), c.pf(QP_CROSS_K_W), c.pf(QP_CROSS_K_B), c.svf(S.Kc),
+                           snap_v(c, 3), c.pf(QP_CROSS_V_W), c.pf(QP_CROSS_V_B), c.svf(S.Vc)));
   QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), epi_t(c, c.pf(QP_CROSS_Q_B), c.sv(S.q_cross), d)));
   {
     AttnP p = attn_params(c, 2);
@@ -835,8 +835,8 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       QV_TRY(attn_bwd(st, dt, p));
       QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_CROSS_Q_W), G(QP_CROSS_Q_B), nullptr));
       QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), acc_xn));
-      QV_TRY(small_linear_bwd(st, snap_k(c, 3), D.kb, d, c.pf(QP_CROSS_K_W), d, c.scf(X.dKc), G(QP_CROSS_K_W), G(QP_CROSS_K_B), G(QP_BANK_K)));
-      QV_TRY(small_linear_bwd(st, snap_v(c, 3), D.kb, d, c.pf(QP_CROSS_V_W), d, c.scf(X.dVc), G(QP_CROSS_V_W), G(QP_CROSS_V_B), G(QP_BANK_V)));
+      QV_TRY(small_linear_bwd2(st, D.kb, d, d, snap_k(c, 3), c.pf(QP_CROSS_K_W), c.scf(X.dKc), G(QP_CROSS_K_W), G(QP_CROSS_K_B), G(QP_BANK_K),
+                               snap_v(c, 3), c.pf(QP_CROSS_V_W), c.scf(X.dVc), G(QP_CROSS_V_W), G(QP_CROSS_V_B), G(QP_BANK_V)));
     } else if (i == 2) {  // ---- CGA
       QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_cga), d / 2, R, d, d / 2, G(QP_CGA_PROJ_W), G(QP_CGA_PROJ_B), nullptr));
       QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_CGA_PROJ, c.pf(QP_CGA_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d / 2)));
@@ -853,8 +853,8 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       p.dkbp = c.scf(X.dkbp); p.dvbp = c.scf(X.dvbp);
       p.drop = dc.site(DS_ATT + 2);
       QV_TRY(cga_bwd(st, dt, p));
-      QV_TRY(small_linear_bwd(st, snap_k(c, 2), D.kb, d, c.pf(QP_CGA_BK_W), D.cpg, c.scf(X.dkbp), G(QP_CGA_BK_W), G(QP_CGA_BK_B), G(QP_BANK_K)));
-      QV_TRY(small_linear_bwd(st, snap_v(c, 2), D.kb, d, c.pf(QP_CGA_BV_W), D.cpg, c.scf(X.dvbp), G(QP_CGA_BV_W), G(QP_CGA_BV_B), G(QP_BANK_V)));
+      QV_TRY(small_linear_bwd2(st, D.kb, d, D.cpg, snap_k(c, 2), c.pf(QP_CGA_BK_W), c.scf(X.dkbp), G(QP_CGA_BK_W), G(QP_CGA_BK_B), G(QP_BANK_K),
+                               snap_v(c, 2), c.pf(QP_CGA_BV_W), c.scf(X.dvbp), G(QP_CGA_BV_W), G(QP_CGA_BV_B), G(QP_BANK_V)));
     } else if (i == 1) {  // ---- MSDA
       QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_msda), d, R, d, d, G(QP_MSDA_PROJ_W), G(QP_MSDA_PROJ_B), nullptr));
       QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_MSDA_PROJ, c.pf(QP_MSDA_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d)));
@@ -987,14 +987,15 @@ extern "C" int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int
   return simt_gemm_nt((cudaStream_t)stream, QV_F32, A, lda, M, N, K, W, e);
 }
 // mode 0: C = A W^T + b | 1: C = pre, C2 = gelu(pre) | 2: C2 = aux + pre (aux bf16 residual) | 3: C = pre * gelu'(aux)
+//      4: C = gelu'(pre), C2 = gelu(pre) | 5: C = pre * aux
 extern "C" int qavit_test_gemm_epi(const void* A, int lda, int M, int N, int K, const void* Wb, const float* bias, void* C,
                                    void* C2, int mode, const void* aux, void* stream) {
   GemmEpi e;
   e.bias = bias;
-  if (mode == 0 || mode == 1 || mode == 3) { e.C = C; e.ldc = N; }
-  if (mode == 1) { e.gelu = 1; e.C2 = C2; e.ldc2 = N; }
+  if (mode != 2) { e.C = C; e.ldc = N; }
+  if (mode == 1 || mode == 4) { e.gelu = 1; e.C2 = C2; e.ldc2 = N; e.gelu_dgrad = mode == 4; }
   if (mode == 2) { e.resid = aux; e.ldr = N; e.r_bf16 = 1; e.C2 = C2; e.ldc2 = N; }
-  if (mode == 3) { e.gmul = aux; e.ldg = N; e.g_bf16 = 1; }
+  if (mode == 3 || mode == 5) { e.gmul = aux; e.ldg = N; e.g_bf16 = 1; e.gmul_raw = mode == 5; }
   return tc_gemm_nt((cudaStream_t)stream, (const bf16*)A, lda, M, N, K, (const bf16*)Wb, e);
 }
 extern "C" int qavit_test_gemm_tn(int use_tc, const void* dY, int ldy, const void* X, int ldx, int M, int N, int K,

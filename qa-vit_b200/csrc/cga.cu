@@ -323,65 +323,99 @@ int cga_bwd(cudaStream_t s, int dt, const CgaP& p) {
 // them per image, H:617-619).  Single small grid, fp32.
 // =====================================================================================================
 namespace {
-// One warp per output element group: lanes stride over K (coalesced reads of the W row), shuffle reduction.
-__global__ void __launch_bounds__(128) small_linear_fwd_kernel(const float* __restrict__ X, int rows, int K, const float* __restrict__ W,
-                                                               const float* __restrict__ b, int N, float* __restrict__ Y) {
+struct SmallLin {
+  const float* X; const float* W; const float* b; float* Y;      // forward
+  const float* dY; float* dW; float* db; float* dX;              // backward (accumulated)
+};
+struct SmallLin2 { SmallLin p[2]; };
+
+// One warp per output column n for every row (W[n, :] is read once): lanes stride over K (coalesced), shuffle reduction.
+// blockIdx.y selects the problem: the K and V projections of a bank snapshot go out as ONE launch.
+__global__ void __launch_bounds__(128) small_linear_fwd_kernel(SmallLin2 pp, int rows, int K, int N) {
   QV_PDL_ENTRY();
+  const SmallLin& q = pp.p[blockIdx.y];
+  const float* __restrict__ X = q.X;
+  const float* __restrict__ W = q.W;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N) return;                       // a warp owns output column n for every row: W[n, :] is read once
+  if (warp >= N) return;
   const int n = warp;
-  for (int r0 = 0; r0 < rows; r0 += 8) {
-    float a[8];
+  for (int r0 = 0; r0 < rows; r0 += 16) {
+    float a[16];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+    for (int i = 0; i < 16; ++i) a[i] = 0.f;
     for (int k = lane; k < K; k += 32) {
       const float w = W[n * K + k];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (r0 + q < rows) a[q] = fmaf(X[(r0 + q) * K + k], w, a[q]);
+      for (int i = 0; i < 16; ++i)
+        if (r0 + i < rows) a[i] = fmaf(X[(r0 + i) * K + k], w, a[i]);
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float v = warp_sum(a[q]);
-      if (lane == 0 && r0 + q < rows) Y[(r0 + q) * N + n] = v + (b ? b[n] : 0.f);
+    for (int i = 0; i < 16; ++i) {
+      const float v = warp_sum(a[i]);
+      if (lane == 0 && r0 + i < rows) q.Y[(r0 + i) * N + n] = v + (q.b ? q.b[n] : 0.f);
     }
   }
 }
 // dW[n,k] += sum_r dY[r,n] X[r,k]; db[n] += sum_r dY[r,n]; dX[r,k] += sum_n dY[r,n] W[n,k]
-__global__ void small_linear_bwd_kernel(const float* X, int rows, int K, const float* W, int N, const float* dY,
-                                        float* dW, float* db, float* dX) {
+__global__ void __launch_bounds__(128) small_linear_bwd_kernel(SmallLin2 pp, int rows, int K, int N) {
   QV_PDL_ENTRY();
+  const SmallLin& q = pp.p[blockIdx.y];
+  const float* X = q.X;
+  const float* W = q.W;
+  const float* dY = q.dY;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < N * K) {
     const int n = idx / K, k = idx % K;
     float a = 0.f;
     for (int r = 0; r < rows; ++r) a = fmaf(dY[r * N + n], X[r * K + k], a);
-    dW[idx] += a;
+    q.dW[idx] += a;
   }
   if (idx < N) {
     float a = 0.f;
     for (int r = 0; r < rows; ++r) a += dY[r * N + idx];
-    db[idx] += a;
+    q.db[idx] += a;
   }
   if (idx < rows * K) {
     const int r = idx / K, k = idx % K;
-    float a = 0.f;
-    for (int n = 0; n < N; ++n) a = fmaf(dY[r * N + n], W[n * K + k], a);   // lanes = consecutive k: coalesced
-    dX[idx] += a;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                    // four chains: the N-long dependent FMA chain was the kernel
+    int n = 0;
+    for (; n + 4 <= N; n += 4) {
+      a0 = fmaf(dY[r * N + n], W[n * K + k], a0);                    // lanes = consecutive k: coalesced
+      a1 = fmaf(dY[r * N + n + 1], W[(n + 1) * K + k], a1);
+      a2 = fmaf(dY[r * N + n + 2], W[(n + 2) * K + k], a2);
+      a3 = fmaf(dY[r * N + n + 3], W[(n + 3) * K + k], a3);
+    }
+    for (; n < N; ++n) a0 = fmaf(dY[r * N + n], W[n * K + k], a0);
+    q.dX[idx] += (a0 + a1) + (a2 + a3);
   }
 }
 }  // namespace
 
-int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
-  qv_launch(small_linear_fwd_kernel, cdiv(N * 32, 128), 128, 0, s, X, rows, K, W, b, N, Y);
+int small_linear_fwd2(cudaStream_t s, int rows, int K, int N, const float* X0, const float* W0, const float* b0, float* Y0,
+                      const float* X1, const float* W1, const float* b1, float* Y1) {
+  SmallLin2 pp{};
+  pp.p[0].X = X0; pp.p[0].W = W0; pp.p[0].b = b0; pp.p[0].Y = Y0;
+  pp.p[1].X = X1; pp.p[1].W = W1; pp.p[1].b = b1; pp.p[1].Y = Y1;
+  qv_launch(small_linear_fwd_kernel, dim3(cdiv(N * 32, 128), X1 ? 2 : 1), 128, 0, s, pp, rows, K, N);
   QV_LAUNCH_CHECK();
   return 0;
 }
+int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y) {
+  return small_linear_fwd2(s, rows, K, N, X, W, b, Y, nullptr, nullptr, nullptr, nullptr);
+}
 
-int small_linear_bwd(cudaStream_t s, const float* X, int rows, int K, const float* W, int N, const float* dY, float* dW,
-                     float* db, float* dX_accum) {
+// NOTE: the two problems of a pair must not share an accumulated output (both bank projections add into different dX here)
+int small_linear_bwd2(cudaStream_t s, int rows, int K, int N, const float* X0, const float* W0, const float* dY0, float* dW0, float* db0,
+                      float* dX0, const float* X1, const float* W1, const float* dY1, float* dW1, float* db1, float* dX1) {
+  SmallLin2 pp{};
+  pp.p[0].X = X0; pp.p[0].W = W0; pp.p[0].dY = dY0; pp.p[0].dW = dW0; pp.p[0].db = db0; pp.p[0].dX = dX0;
+  pp.p[1].X = X1; pp.p[1].W = W1; pp.p[1].dY = dY1; pp.p[1].dW = dW1; pp.p[1].db = db1; pp.p[1].dX = dX1;
   const int n = max(N * K, rows * K);
-  qv_launch(small_linear_bwd_kernel, cdiv(n, 128), 128, 0, s, X, rows, K, W, N, dY, dW, db, dX_accum);
+  qv_launch(small_linear_bwd_kernel, dim3(cdiv(n, 128), X1 ? 2 : 1), 128, 0, s, pp, rows, K, N);
   QV_LAUNCH_CHECK();
   return 0;
+}
+int small_linear_bwd(cudaStream_t s, const float* X, int rows, int K, const float* W, int N, const float* dY, float* dW,
+                     float* db, float* dX_accum) {
+  return small_linear_bwd2(s, rows, K, N, X, W, dY, dW, db, dX_accum, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }

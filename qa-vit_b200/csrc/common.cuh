@@ -141,6 +141,14 @@ __device__ __forceinline__ float gelu_grad_fast_f(float x) {
   const float du = fmaf(0.1070322243f, x2, 0.7978845608f);
   return fmaf(0.5f * x * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
 }
+// value and derivative from one tanh
+__device__ __forceinline__ void gelu_both_fast_f(float x, float& g, float& dg) {
+  const float x2 = x * x;
+  const float t = tanh_approx_f(x * fmaf(0.0356774081f, x2, 0.7978845608f));
+  const float hx = 0.5f * x;
+  g = fmaf(hx, t, hx);
+  dg = fmaf(hx * fmaf(0.1070322243f, x2, 0.7978845608f), fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
+}
 // type-selected: exact for fp32 activations, fast for bf16 activations
 template <typename T> __device__ __forceinline__ float gelu_t(float x) { return sizeof(T) == 2 ? gelu_fast_f(x) : gelu_f(x); }
 template <typename T> __device__ __forceinline__ float gelu_grad_t(float x) { return sizeof(T) == 2 ? gelu_grad_fast_f(x) : gelu_grad_f(x); }

@@ -89,8 +89,11 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtArgs p) {
       val *= s_pre;
       if (e.gmul) {
         const long gi_ = (long)gi * e.ldg + gj;
-        val *= gelu_grad_f(e.g_bf16 ? ldf(static_cast<const bf16*>(e.gmul) + gi_) : static_cast<const float*>(e.gmul)[gi_]);
+        const float gv = e.g_bf16 ? ldf(static_cast<const bf16*>(e.gmul) + gi_) : static_cast<const float*>(e.gmul)[gi_];
+        val *= e.gmul_raw ? gv : gelu_grad_f(gv);
       }
+      const float pre = val;
+      if (e.gelu && e.gelu_dgrad) val = gelu_grad_f(pre);
       if (e.C) {
         if (e.c_f32) {
           float* c_ = static_cast<float*>(e.C) + (long)gi * e.ldc + gj;
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(SimtArgs p) {
           const long ri = (long)gi * e.ldr + gj;
           rv = e.r_bf16 ? ldf(static_cast<const bf16*>(e.resid) + ri) : static_cast<const float*>(e.resid)[ri];
         }
-        float v2 = e.gelu ? gelu_f(val) : rv + s_res * val;
+        float v2 = e.gelu ? gelu_f(pre) : rv + s_res * val;
         if (e.c2_f32) static_cast<float*>(e.C2)[(long)gi * e.ldc2 + gj] = v2;
         else stf(static_cast<bf16*>(e.C2) + (long)gi * e.ldc2 + gj, v2);
       }

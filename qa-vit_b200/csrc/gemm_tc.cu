@@ -567,8 +567,13 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[c][j] = fmaf(v[c][j], s_pre, bias_s[g + c * 16 + j]);   // bias staged pre-scaled
             if (use_gmul) {
+              if (e.gmul_raw) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[c][j] *= gelu_grad_fast_f(r[c][j]);
+                for (int j = 0; j < 16; ++j) v[c][j] *= r[c][j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[c][j] *= gelu_grad_fast_f(r[c][j]);
+              }
             }
             if ((masked || scaled) && !e.gelu) {   // ids of drop_rows on the contiguous [M, N] output
               float k[16];
@@ -581,7 +586,19 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               for (int j = 0; j < 16; ++j) v[c][j] *= (masked ? k[j] : 1.f) * rsc;
             }
           }
-        if (e.C) {
+        const bool dual_dg = e.gelu && e.gelu_dgrad && e.C && e.C2;   // C = gelu'(pre), C2 = gelu(pre): one tanh for both
+        if (dual_dg) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (c < nch) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) gelu_both_fast_f(v[c][j], v[c][j], r[c][j]);   // v <- gelu, r <- gelu'
+              stage_store16(my_row, c, r[c], e.c_f32 != 0);
+            }
+          __syncwarp();
+          stage_flush_any(st, e.C, e.ldc, e.c_f32 != 0, false, row0, p.M, n0 + g, gw, lane);
+          __syncwarp();
+        } else if (e.C) {
 #pragma unroll
           for (int c = 0; c < 2; ++c)
             if (c < nch) stage_store16(my_row, c, v[c], e.c_f32 != 0);
@@ -594,8 +611,10 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int c = 0; c < 2; ++c)
             if (c < nch) {
               if (e.gelu) {
+                if (!dual_dg) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[c][j] = gelu_fast_f(v[c][j]);
+                  for (int j = 0; j < 16; ++j) v[c][j] = gelu_fast_f(v[c][j]);
+                }
                 if (masked) {                      // nn.Dropout after the activation (H:654): only C2 is dropped
                   float k[16];
                   const unsigned long long id8 = (unsigned long long)(my_r * p.N + n0 + g + c * 16) >> 3;

@@ -21,12 +21,14 @@ struct GemmEpi {
   const float* scale_pre = nullptr;
   const float* scale_res = nullptr;
   int gelu = 0;
+  int gelu_dgrad = 0;            // with gelu: C receives gelu'(pre) instead of pre (the factor the backward multiplies by)
   const void* resid = nullptr;   // fp32, or bf16 when r_bf16
   int ldr = 0;
   int r_bf16 = 0;
   const void* gmul = nullptr;    // fp32, or bf16 when g_bf16: the stored pre-activation
   int ldg = 0;
   int g_bf16 = 0;
+  int gmul_raw = 0;              // gmul holds the factor itself (written by a gelu_dgrad forward), not the pre-activation
   void* C = nullptr;
   int ldc = 0;
   int c_f32 = 0;
@@ -222,6 +224,11 @@ int cga_mma64_bwd(cudaStream_t s, const CgaP& p);
 int small_linear_fwd(cudaStream_t s, const float* X, int rows, int K, const float* W, const float* b, int N, float* Y);
 int small_linear_bwd(cudaStream_t s, const float* X, int rows, int K, const float* W, int N, const float* dY,
                      float* dW, float* db, float* dX_accum);
+// two same-shape problems in one launch (the K and V projections of one bank snapshot); outputs must be distinct
+int small_linear_fwd2(cudaStream_t s, int rows, int K, int N, const float* X0, const float* W0, const float* b0, float* Y0,
+                      const float* X1, const float* W1, const float* b1, float* Y1);
+int small_linear_bwd2(cudaStream_t s, int rows, int K, int N, const float* X0, const float* W0, const float* dY0, float* dW0, float* db0,
+                      float* dX0, const float* X1, const float* W1, const float* dY1, float* dW1, float* db1, float* dX1);
 
 // ---- bank write (train-mode forward only, no gradient)
 int bank_write_reduce(cudaStream_t s, int dt, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, int kb,

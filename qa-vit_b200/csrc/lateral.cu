@@ -212,6 +212,9 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
     plan_lin(b, q.rev, c.rrcv_channels, c.dim, bf);
     plan_lin(b, q.re, c.dim, c.rrcv_channels, bf);
   }
+  // gradients of the three feature maps: written by the adapters' backward, consumed by the stem's backward -- they live in `saved`
+  // (not scratch) because the phases may be separate calls (qavit_lateral_backward_parts)
+  for (int i = 0; i < 3; ++i) p.df[i] = b.take(p.R * chans[i + 2] * ts);
   p.saved_total = b.off;
 
   Bump s;
@@ -232,7 +235,6 @@ void make_plan(const qavit_lateral_cfg& c, Plan* P) {
   p.wide = s.take(Rm * wide * ts);
   p.t1 = s.take(Rm * cmax * ts);
   p.t2 = s.take(Rm * cmax * ts);
-  for (int i = 0; i < 3; ++i) p.df[i] = s.take(p.R * chans[i + 2] * ts);
   p.dA = s.take(Rm * c.dim * ts);
   p.da0 = s.take(p.kind == 0 ? p.R1 * c.c_stem * ts : 0);
   p.dc0 = s.take(p.kind == 0 ? p.R1 * c.c_stem * ts : 0);
@@ -312,6 +314,7 @@ int cnx_fwd(const Ctx& c, const CnxPlan& x, int pbase, int H, const void* in, vo
                 c.sv(x.n), C, static_cast<float*>(c.sv(x.stats))));
   GemmEpi e1 = epi(c, c.pf(pbase + CX_B1), c.sv(x.hpre), 4 * C);
   e1.gelu = 1; e1.C2 = c.sv(x.h); e1.ldc2 = 4 * C; e1.c2_f32 = dt == QV_F32;
+  e1.gelu_dgrad = dt == QV_BF16;   // bf16 runs keep gelu'(pre) in x.hpre: backward's epilogue is then one multiply (was 11 instructions)
   QV_TRY(gemm_nt(c.st, dt, c.sv(x.n), C, (int)R, c.W(x.w1, c.pf(pbase + CX_W1)), e1));
   GemmEpi e2;
   e2.bias = c.pf(pbase + CX_B2); e2.resid = in; e2.ldr = C; e2.r_bf16 = dt == QV_BF16; e2.C2 = out; e2.ldc2 = C; e2.c2_f32 = dt == QV_F32;
@@ -353,7 +356,7 @@ int cnx_bwd(const Ctx& c, const CnxPlan& x, int pbase, int H, const void* in, co
     QV_TRY(layerscale_finish(c.st, ls->G, ls->gb, c.pf(pbase + CX_W2), c.pf(pbase + CX_B2), c.pf(pbase + CX2_GAMMA), C, 4 * C,
                              c.gf(pbase + CX_W2), c.gf(pbase + CX_B2), c.gf(pbase + CX2_GAMMA)));
   GemmEpi e = epi(c, nullptr, wide, 4 * C);
-  e.gmul = c.sv(x.hpre); e.ldg = 4 * C; e.g_bf16 = dt == QV_BF16;
+  e.gmul = c.sv(x.hpre); e.ldg = 4 * C; e.g_bf16 = dt == QV_BF16; e.gmul_raw = dt == QV_BF16;
   QV_TRY(gemm_nn(c.st, dt, dy, C, (int)R, c.W(x.w2, w2), e));
   // pwconv1
   QV_TRY(gemm_tn(c.st, dt, wide, 4 * C, c.sv(x.n), C, (int)R, 4 * C, C, c.gf(pbase + CX_W1), c.gf(pbase + CX_B1), nullptr));
@@ -514,6 +517,11 @@ extern "C" int qavit_lateral_workspace(const qavit_lateral_cfg* cfg, size_t* sav
 
 extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* const* params, const float* img, float* R2, float* R3,
                                      float* R4, void* saved, void* scratch, void* stream) {
+  return qavit_lateral_forward_parts(cfg, params, img, R2, R3, R4, saved, scratch, stream, QAVIT_LATERAL_ALL);
+}
+
+extern "C" int qavit_lateral_forward_parts(const qavit_lateral_cfg* cfg, const void* const* params, const float* img, float* R2, float* R3,
+                                           float* R4, void* saved, void* scratch, void* stream, unsigned parts) {
   QV_RANGE("qavit_lateral_forward");
   Ctx c;
   QV_TRY(init_ctx(&c, cfg, params, nullptr, saved, scratch, stream));
@@ -521,12 +529,14 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
   const int dt = P.dt, d = P.d;
   const bool train = cfg->train != 0;
   cudaStream_t st = c.st;
-  QV_TRY(convert_all(c, train));
+  const bool do_stem = (parts & QAVIT_LATERAL_STEM) != 0;
+  if (do_stem) QV_TRY(convert_all(c, train));      // every GEMM weight of the path, adapters included
   float* sums = static_cast<float*>(c.sc(P.sums));
 
-  const void* feat[3];
+  const void* feat[3] = {c.sv(P.cx[0].out), c.sv(P.cx[1].out), c.sv(P.cx[2].out)};
+  if (P.kind == 1) { feat[0] = c.sv(P.v2.blk[1].x.out); feat[1] = c.sv(P.v2.blk[4].x.out); feat[2] = c.sv(P.v2.blk[6].x.out); }
   const void* prev = nullptr;
-  if (P.kind == 1) {
+  if (P.kind == 1 && do_stem) {
     // ---- HQAViTv2 stem (V:811-827): patchify conv -> LN([c2, g, g]) -> 2 blocks -> [LN + 1x1 conv -> 3 blocks] -> [... -> 2 blocks]
     const StemV2Plan& v = P.v2;
     const int HW = P.H * P.H;
@@ -552,11 +562,10 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
       Ls ls{v.blk[j].w2s, v.blk[j].b2s, (dp && cfg->stem_drop_path[j] > 0.f) ? rs + (size_t)j * P.B : nullptr, c.sc(P.t1), nullptr, nullptr};
       QV_TRY(cnx_fwd(c, v.blk[j].x, v2_cx_base(j), P.H, prev, c.sv(v.blk[j].x.out), &ls));
       prev = c.sv(v.blk[j].x.out);
-      feat[kV2Stage[j]] = prev;
     }
   }
   // ---- CNNStemModel: (conv -> BN [-> GELU]) x 4 with a ConvNeXt block after units 1..3
-  for (int i = 0; i < 4 && P.kind == 0; ++i) {
+  for (int i = 0; i < 4 && P.kind == 0 && do_stem; ++i) {
     const CbPlan& q = P.cb[i];
     const int pb = cb_base(i);
     const long rows = i == 0 ? P.R1 : P.R;
@@ -580,12 +589,13 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
     if (i >= 1) {
       QV_TRY(cnx_fwd(c, P.cx[i - 1], cx_base(i - 1), P.H, prev, c.sv(P.cx[i - 1].out)));
       prev = c.sv(P.cx[i - 1].out);
-      feat[i - 1] = prev;
     }
   }
   // ---- LMFAdapter + RRCV per fusion stage
   float* Rout[3] = {R2, R3, R4};
   for (int i = 0; i < 3; ++i) {
+    if (!(parts & (QAVIT_LATERAL_ADAPTER2 << i))) continue;
+    QV_CHECK(Rout[i], "lateral_forward: null output for adapter %d", i + 2);
     const LmPlan& q = P.lm[i];
     const int pb = lm_base(*cfg, i), C = q.C;
     DwP a{};
@@ -620,6 +630,12 @@ extern "C" int qavit_lateral_forward(const qavit_lateral_cfg* cfg, const void* c
 extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* const* params, float* const* grads, const float* img,
                                       const float* dR2, const float* dR3, const float* dR4, const void* saved, void* scratch,
                                       void* stream) {
+  return qavit_lateral_backward_parts(cfg, params, grads, img, dR2, dR3, dR4, saved, scratch, stream, QAVIT_LATERAL_ALL);
+}
+
+extern "C" int qavit_lateral_backward_parts(const qavit_lateral_cfg* cfg, const void* const* params, float* const* grads, const float* img,
+                                            const float* dR2, const float* dR3, const float* dR4, const void* saved, void* scratch,
+                                            void* stream, unsigned parts) {
   QV_RANGE("qavit_lateral_backward");
   Ctx c;
   QV_TRY(init_ctx(&c, cfg, params, grads, saved, scratch, stream));
@@ -638,10 +654,11 @@ extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* 
 
   // ---- RRCV + LMFAdapter backward per stage: dR_i -> df_i
   for (int i = 2; i >= 0; --i) {
+    if (!(parts & (QAVIT_LATERAL_ADAPTER2 << i))) continue;
     const LmPlan& q = P.lm[i];
     const RrPlan& r = P.rr[i];
     const int rb = rr_base(*cfg, i), pb = lm_base(*cfg, i), C = q.C;
-    void* df = c.sc(P.df[i]);
+    void* df = c.sv(P.df[i]);
     void* dA = c.sc(P.dA);
     if (dRs[i] == nullptr) {   // this stage's fusion is not part of the graph
       QV_CUDA(cudaMemsetAsync(df, 0, (size_t)P.R * C * P.ts, st));
@@ -683,6 +700,7 @@ extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* 
     QV_TRY(dw2d_fwd(st, dt, a, true));
   }
 
+  if (!(parts & QAVIT_LATERAL_STEM)) return 0;
   if (P.kind == 1) {
     // ---- HQAViTv2 stem backward: blocks 6 .. 0; the gradient of a stage's feature map (df[stage], from its LMFAdapter) joins at
     // the stage's last block, the downsample's gradient is added to the previous stage's df by the LayerNorm backward
@@ -696,14 +714,14 @@ extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* 
       const bool last_of_stage = j == V2_BLOCKS - 1 || kV2Stage[j + 1] != stg;
       const bool first_of_stage = j == 0 || kV2Stage[j - 1] != stg;
       const void* in = first_of_stage ? (stg == 0 ? c.sv(v.a0) : c.sv(v.ds[stg - 1].out)) : c.sv(v.blk[j - 1].x.out);
-      const void* dout = last_of_stage ? c.sc(P.df[stg]) : t2;
+      const void* dout = last_of_stage ? c.sv(P.df[stg]) : t2;
       Ls ls{v.blk[j].w2s, v.blk[j].b2s, (dp && cfg->stem_drop_path[j] > 0.f) ? rs + (size_t)j * P.B : nullptr, nullptr, G, G + (size_t)C * 4 * C};
       QV_TRY(cnx_bwd(c, v.blk[j].x, v2_cx_base(j), P.H, in, dout, t2, wide, t1, &ls));
       if (first_of_stage && stg > 0) {        // downsample: 1x1 conv, then LN([Cin, g, g]) of the previous stage's feature map
         const DsPlan& q = v.ds[stg - 1];
         const int pb = v2_ds_base(stg - 1);
         QV_TRY(lin_bwd(c, c.sv(q.n), q.Cin, t2, P.R, q.w, c.pf(pb + DS_W), c.gf(pb + DS_W), c.gf(pb + DS_B), t1, nullptr));
-        void* dprev = c.sc(P.df[stg - 1]);
+        void* dprev = c.sv(P.df[stg - 1]);
         QV_TRY(sln_bwd(st, dt, feat[stg - 1], t1, P.B, HW, q.Cin, c.pf(pb + DS_LN_W), static_cast<const float*>(c.sv(q.stats)), dprev, dprev,
                        c.gf(pb + DS_LN_W), c.gf(pb + DS_LN_B)));
       }
@@ -719,12 +737,12 @@ extern "C" int qavit_lateral_backward(const qavit_lateral_cfg* cfg, const void* 
   for (int i = 3; i >= 1; --i) {
     const CbPlan& q = P.cb[i];
     const int pb = cb_base(i);
-    void* df = c.sc(P.df[i - 1]);
+    void* df = c.sv(P.df[i - 1]);
     QV_TRY(cnx_bwd(c, P.cx[i - 1], cx_base(i - 1), P.H, c.sv(q.a), df, t2, wide, t1));
     QV_TRY(bn_bwd(st, dt, c.sv(q.c), t2, P.R, q.Cout, c.pf(pb + BN_W), c.pf(pb + BN_B), static_cast<const float*>(c.sv(q.mr)), train,
                   i < 2, sums, t1, c.gf(pb + BN_W), c.gf(pb + BN_B)));
     if (i >= 2) {   // 1x1 conv: the input is the previous stage's feature map, its gradient accumulates into df[i - 2]
-      void* dprev = c.sc(P.df[i - 2]);
+      void* dprev = c.sv(P.df[i - 2]);
       QV_TRY(lin_bwd(c, feat[i - 2], q.Cin, t1, P.R, q.w, c.pf(pb + CB_W), c.gf(pb + CB_W), c.gf(pb + CB_B), dprev, dprev));
     } else {        // 3x3 stride-2 conv on the stem output
       float* dwp = static_cast<float*>(c.sc(P.dwp1));

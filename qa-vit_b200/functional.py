@@ -516,6 +516,81 @@ class LateralFn(torch.autograd.Function):
         return (None, None, *views)
 
 
+class LateralState:
+    """What the phases of one lateral forward / backward share (qavit_lateral_*_parts): the configuration, the full parameter
+    pointer table (the C side indexes it globally), the `saved` buffer and which adapters' backward has run."""
+
+    def __init__(self, cfg: LateralCfg, names, tensors, buffer_idx, img):
+        self.cfg, self.names, self.tensors, self.buffers, self.img = cfg, names, tensors, set(buffer_idx), img
+        self.params = _param_array(tensors, len(tensors))
+        saved_b, scratch_b = C.c_size_t(0), C.c_size_t(0)
+        check(lib.qavit_lateral_workspace(C.byref(cfg), C.byref(saved_b), C.byref(scratch_b)))
+        self.scratch_bytes = scratch_b.value
+        self.saved = torch.empty(saved_b.value, dtype=torch.uint8, device=img.device)
+        self.bwd_done = [False, False, False]
+        # indices of each part's tensors: 0 = cnn_stem, 1..3 = lmfa{2,3,4} + rrcv{2,3,4}
+        self.part_idx = [[i for i, n in enumerate(names) if n.startswith("cnn_stem.")]]
+        for k in (2, 3, 4):
+            self.part_idx.append([i for i, n in enumerate(names) if n.startswith((f"lmfa{k}.", f"rrcv{k}."))])
+
+    def part_tensors(self, part):
+        return [self.tensors[i] for i in self.part_idx[part]]
+
+
+class LateralPartFn(torch.autograd.Function):
+    """One phase of the lateral path.  part 0: image -> token (the stem's feature maps stay in state.saved; the token only carries
+    the autograd dependency); part k = 1..3: token -> R_{k+1} (LMFAdapter + RRCV of stage k + 1).  Separate autograd nodes let the
+    adapters' backward start as soon as their dR is known and the stem's backward run last, all on the lateral side stream, next to
+    the token path's blocks (H:1236-1247 computes the same three tensors up front)."""
+
+    @staticmethod
+    def forward(ctx, inp, state: LateralState, part: int, *tensors):
+        cfg = state.cfg
+        dev = state.img.device
+        scratch = _scratch_buf(dev, state.scratch_bytes)
+        out = None
+        Rp = [None, None, None]
+        if part == 0:
+            out = torch.zeros(1, dtype=torch.float32, device=dev)
+        else:
+            N = cfg.grid * cfg.grid
+            out = torch.empty(cfg.batch, N, cfg.dim, dtype=torch.float32, device=dev)
+            Rp[part - 1] = out.data_ptr()
+        check(lib.qavit_lateral_forward_parts(C.byref(cfg), state.params, state.img.data_ptr(), Rp[0], Rp[1], Rp[2],
+                                              state.saved.data_ptr(), scratch.data_ptr(), _stream(), 1 << part))
+        ctx.state, ctx.part, ctx.tensors = state, part, tensors
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        state, part = ctx.state, ctx.part
+        cfg, dev = state.cfg, state.img.device
+        idx = state.part_idx[part]
+        skip = {j for j, i in enumerate(idx) if i in state.buffers}
+        arr, views, direct = _grad_arrays(ctx.tensors, skip, dev)
+        full = (C.c_void_p * len(state.tensors))()
+        for j, i in enumerate(idx):
+            full[i] = arr[j]
+        scratch = _scratch_buf(dev, state.scratch_bytes)
+        dR = [None, None, None]
+        parts = 1 << part
+        if part == 0:
+            for k in range(3):                      # an adapter that took no part in the loss: its feature-map gradient is zero
+                if not state.bwd_done[k]:
+                    check(lib.qavit_lateral_backward_parts(C.byref(cfg), state.params, full, state.img.data_ptr(), None, None, None,
+                                                           state.saved.data_ptr(), scratch.data_ptr(), _stream(), 2 << k))
+        else:
+            dR[part - 1] = dout.float().contiguous()
+            state.bwd_done[part - 1] = True
+        check(lib.qavit_lateral_backward_parts(C.byref(cfg), state.params, full, state.img.data_ptr(), _ptr(dR[0]), _ptr(dR[1]),
+                                               _ptr(dR[2]), state.saved.data_ptr(), scratch.data_ptr(), _stream(), parts))
+        if part == 0:
+            state.saved = None
+        _notify(direct)
+        dinp = None if part == 0 else torch.zeros(1, dtype=torch.float32, device=dev)
+        return (dinp, None, None, *views)
+
+
 class SplitFusionFn(torch.autograd.Function):
     """SplitFusion.forward -- HQAViT_CIFAR100.py:945-963."""
 

@@ -15,6 +15,8 @@ import math
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -593,8 +595,9 @@ class HQAViT(_Base):
         self.apply(_init_weights)
         self._lateral_names = None
 
-    def lateral(self, x):
-        """cnn_stem -> lmfa{2,3,4} -> rrcv{2,3,4} (H:1236-1247) as one native call: image -> (R2, R3, R4)."""
+    def lateral(self, x, phased: bool = False):
+        """cnn_stem -> lmfa{2,3,4} -> rrcv{2,3,4} (H:1236-1247) as one native call: image -> (R2, R3, R4).
+        phased=True: only the stem runs here -> (state, token); lateral_adapter(state, token, k) then yields R_k."""
         cfg = self.config
         c = LateralCfg()
         c.batch, c.img_size, c.in_channels = x.shape[0], x.shape[-1], x.shape[1]
@@ -631,37 +634,57 @@ class HQAViT(_Base):
         names = self._lateral_names
         tensors = [_resolve(self, n) for n in names]
         buffers = [i for i, n in enumerate(names) if n.endswith(("running_mean", "running_var", "num_batches_tracked"))]
-        return QF.LateralFn.apply(x, QF.LateralMeta(c, buffers), *tensors)
+        if not phased:
+            return QF.LateralFn.apply(x, QF.LateralMeta(c, buffers), *tensors)
+        QF._require_cuda(x, "image batch")
+        state = QF.LateralState(c, names, tensors, buffers, x.detach().float().contiguous())
+        state.rng_keepalive = rng
+        token = QF.LateralPartFn.apply(x, state, 0, *state.part_tensors(0))
+        return state, token
 
-    concurrent_lateral = True     # run the lateral path on a side stream next to patch embed + stage 1 (they are independent)
+    def lateral_adapter(self, state, token, k):
+        """LMFAdapter + RRCV of stage k (2..4) on the stem's feature maps -> R_k (phased form of lateral())."""
+        return QF.LateralPartFn.apply(token, state, k - 1, *state.part_tensors(k - 1))
+
+    # The lateral path runs on a side stream, in phases: the stem next to patch embed + stage 1, the adapter of stage k issued right
+    # before fuse_k -- so adapters 3 / 4 overlap the blocks of stages 2 / 3, and in backward every adapter starts as soon as its dR is
+    # known (autograd runs a node's backward on its forward stream) instead of after fuse2's backward.
+    concurrent_lateral = os.environ.get("QAVIT_LATERAL_SERIAL", "0") != "1"
 
     def forward(self, x):
-        side = None
-        if self.concurrent_lateral and x.is_cuda:
+        concurrent = self.concurrent_lateral and x.is_cuda
+        if not concurrent:
+            R2, R3, R4 = self.lateral(x)
+            Rs = {2: R2, 3: R3, 4: R4}
+        else:
             if getattr(self, "_lat_stream", None) is None:
                 object.__setattr__(self, "_lat_stream", torch.cuda.Stream(device=x.device))
             side = self._lat_stream
             main = torch.cuda.current_stream(x.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                R2, R3, R4 = self.lateral(x)
-            for R in (R2, R3, R4):
-                R.record_stream(main)
-        else:
-            R2, R3, R4 = self.lateral(x)
+                state, token = self.lateral(x, phased=True)
+
+        def R_of(k):
+            if not concurrent:
+                return Rs[k]
+            with torch.cuda.stream(side):
+                R = self.lateral_adapter(state, token, k)
+            R.record_stream(main)
+            main.wait_stream(side)
+            return R
+
         T = self.patch_embed(x, self.pos_embed)
         T = self._stream_dropout(T)
         for blk in self.stage1_blocks:
             T = blk(T)
-        if side is not None:
-            torch.cuda.current_stream(x.device).wait_stream(side)
-        T = self.fuse2(T, R2)
+        T = self.fuse2(T, R_of(2))
         for blk in self.stage2_blocks:
             T = blk(T)
-        T = self.fuse3(T, R3)
+        T = self.fuse3(T, R_of(3))
         for blk in self.stage3_blocks:
             T = blk(T)
-        T = self.fuse4(T, R4)
+        T = self.fuse4(T, R_of(4))
         for blk in self.stage4_blocks:
             T = blk(T)
         return self._finish_logits(QF.HeadFn.apply(T, self.norm.weight, self.norm.bias, self.head.weight, self.head.bias))

@@ -79,7 +79,7 @@ def test_tcgen05_gemm_tn(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 192, 192), (1000, 1024, 256), (640, 256, 1024), (130, 64, 288)])
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
 def test_tcgen05_gemm_fused_epilogues(M, N, K, mode):
     """GELU dual output, bf16 residual and GELU-backward multiply epilogues of the tcgen05 NT GEMM (lateral path)."""
     L = _lib()
@@ -100,6 +100,12 @@ def test_tcgen05_gemm_fused_epilogues(M, N, K, mode):
         assert (C2.double() - torch.nn.functional.gelu(pre)).abs().max().item() < tol * 4
     elif mode == 2:
         assert (C2.double() - (pre + aux.double())).abs().max().item() < tol * 6
+    elif mode == 4:     # forward stores gelu'(pre) (what backward multiplies by) next to gelu(pre)
+        dg = 0.5 * (1 + torch.erf(pre / 2 ** 0.5)) + pre * torch.exp(-0.5 * pre * pre) / (2 * torch.pi) ** 0.5
+        assert (C.double() - dg).abs().max().item() < tol
+        assert (C2.double() - torch.nn.functional.gelu(pre)).abs().max().item() < tol * 4
+    elif mode == 5:
+        assert (C.double() - pre * aux.double()).abs().max().item() < tol * 6
     else:
         x = aux.double()
         dg = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5

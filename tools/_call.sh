@@ -1,2 +1,3 @@
-mkdir -p gpurun_out/r2
-python -m pytest tests -m gpu -q > gpurun_out/r2/t21_all.log 2>&1; tail -8 gpurun_out/r2/t21_all.log
+QAVIT_LATERAL_SERIAL=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline 2>&1 | tail -1 | grep -o '"ms_per_step": [0-9.]*' | head -1
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline 2>&1 | tail -1 | grep -o '"ms_per_step": [0-9.]*' | head -1
+python bench.py --steps 10 --warmup 3 --no-graph --no-cpu-baseline --no-gpu-eager-baseline 2>&1 | tail -1 | grep -o '"ms_per_step": [0-9.]*' | head -1

@@ -1,0 +1,53 @@
+"""In-situ kernel durations of the headline training step (torch.profiler / CUPTI activity records: no replay, no cache flush, the
+real stream concurrency) -- the complement of the ncu launch lists, whose per-kernel times are cold-cache and serialised.
+    python tools/kineto_step.py [--graph] [--batch 4736] [--top 60]"""
+import argparse, collections, os, re, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import qavit_b200 as Q
+from torch.profiler import ProfilerActivity, profile
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=4736)
+ap.add_argument("--graph", action="store_true")
+ap.add_argument("--top", type=int, default=60)
+ap.add_argument("--dropout", type=float, default=0.1)
+a = ap.parse_args()
+torch.manual_seed(42)
+model = Q.HQAViT(Q.HQAViTConfig(dropout=a.dropout, drop_path=a.dropout)).cuda().train().set_precision("bf16")
+opt = Q.FusedAdamW(model.named_parameters(), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06, max_grad_norm=0.5)
+x = torch.randn(a.batch, 3, 32, 32, device="cuda")
+y = torch.randint(0, 100, (a.batch,), device="cuda")
+
+def eager():
+    opt.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = model(x)
+    loss = Q.cross_entropy(logits, y, label_smoothing=0.12)
+    loss.backward()
+    opt.clip()
+    opt.step()
+
+if a.graph:
+    g = Q.GraphedTrainStep(model, opt, x, y, label_smoothing=0.12)
+    step = lambda: g(x, y)
+else:
+    step = eager
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+agg = collections.defaultdict(lambda: [0, 0.0])
+t0, t1 = min(e.time_range.start for e in evs), max(e.time_range.end for e in evs)
+for e in evs:
+    n = re.sub(r"\(.*", "", e.name.replace("(anonymous namespace)::", "").replace("void ", ""))[:80]
+    agg[n][0] += 1
+    agg[n][1] += e.time_range.end - e.time_range.start
+tot = sum(v[1] for v in agg.values())
+print(f"2 steps: wall {t1 - t0:.0f} us, sum of kernel durations {tot:.0f} us over {sum(v[0] for v in agg.values())} records")
+for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
+    print(f"{t / 2:10.1f} us {100 * t / tot:5.1f}%  n={n // 2:4d} avg={t / n:8.1f}  {k}")
