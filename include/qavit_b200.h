@@ -265,6 +265,18 @@ int qavit_splitfusion_backward(const qavit_splitfusion_cfg* cfg, const void* con
                                const float* R, const float* dout, float* dT, float* dR, const void* saved, void* scratch,
                                void* stream);
 
+/* ---- Data-parallel gradient all-reduce (scope row D1; new: the reference is single-GPU).  One process per GPU; `comm` is the
+ * caller's ncclComm_t (in a PyTorch process: ProcessGroupNCCL._comm_ptr()), `stream` the stream the reduction is ordered on.
+ * The library resolves NCCL from the libnccl.so.2 already loaded in the process (it does not link against it).
+ *   qavit_dp_available     : 1 when NCCL could be resolved
+ *   qavit_dp_comm_info     : size / rank of the communicator
+ *   qavit_dp_allreduce_sum : in-place SUM all-reduce of n_buckets fp32 device ranges as one NCCL group -- the buckets are contiguous
+ *                            ranges of the flat gradient buffer (+ the GlobalTokenBank state riding in its tail); the 1 / world of the
+ *                            mean is applied by qavit_clip_grads_scaled's grad_prescale, so no extra pass touches the gradients. */
+int qavit_dp_available(void);
+int qavit_dp_comm_info(void* comm, int* world, int* rank);
+int qavit_dp_allreduce_sum(void* comm, float* const* bufs, const size_t* counts, int n_buckets, void* stream);
+
 /* Test hook for the fused TokenLearner / TokenUpMix kernels of bf16 runs (H:971-1031; 16 learned tokens, <= 64 stream tokens,
  * 192 channels).  op 0 / 1 = TokenLearner forward / backward, 2 / 3 = TokenUpMix + LayerNorm forward / backward; `in` / `out` are
  * arrays of fp32 device pointers in the order documented next to the definition (csrc/block.cu). */

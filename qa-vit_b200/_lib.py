@@ -92,6 +92,9 @@ _SIGS = {
     "qavit_lateral_forward_parts": (_i, [C.POINTER(LateralCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint]),
     "qavit_lateral_backward_parts": (_i, [C.POINTER(LateralCfg), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                           C.c_uint]),
+    "qavit_dp_available": (_i, []),
+    "qavit_dp_comm_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "qavit_dp_allreduce_sum": (_i, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t), _i, _vp]),
     "qavit_splitfusion_param_name": (C.c_char_p, [_i]),
     "qavit_splitfusion_workspace": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "qavit_splitfusion_forward": (_i, [C.POINTER(SplitFusionCfg), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -13,7 +13,31 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
+import ctypes as C
+
 from ._lib import check, lib
+
+
+def native_comm(group=None):
+    """ncclComm_t of the process group's NCCL backend on the current device (ProcessGroupNCCL._comm_ptr), or None when the group is
+    not NCCL / the communicator is not created yet / this torch build does not expose it.  The C ABI's qavit_dp_* take it."""
+    try:
+        if not (dist.is_initialized() and torch.cuda.is_available() and lib.qavit_dp_available()):
+            return None
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        be = pg._get_backend(torch.device("cuda", torch.cuda.current_device()))
+        ptr = be._comm_ptr()
+        return int(ptr) if ptr else None
+    except Exception:
+        return None
+
+
+def native_allreduce_sum(comm: int, tensors) -> None:
+    """qavit_dp_allreduce_sum on the current stream: one NCCL group over the given contiguous fp32 CUDA tensors, in place."""
+    n = len(tensors)
+    bufs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    counts = (C.c_size_t * n)(*[t.numel() for t in tensors])
+    check(lib.qavit_dp_allreduce_sum(comm, bufs, counts, n, torch.cuda.current_stream().cuda_stream))
 
 
 class GradAllReducer:
@@ -23,6 +47,8 @@ class GradAllReducer:
         forward + backward are replayed as a CUDA graph: one 26 MB all-reduce is ~0.2 % of the step, so overlapping it
         buys nothing there and the collective stays outside the captured graphs)."""
         self.opt, self.group = opt, group
+        self.native = True          # reduce_flat() goes through the C ABI (qavit_dp_allreduce_sum) when the group's ncclComm_t is available
+        self._comm = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         params = opt.param_groups[0]["params"]
         offs = opt.seg_off.tolist()
@@ -70,35 +96,44 @@ class GradAllReducer:
 
     def reset(self):
         """Call before every backward: every bucket waits for all of its parameters that will get a gradient."""
-        flags = self.opt._flags_host if self.opt._have_flags else None
+        if not self.opt._have_flags and hasattr(self.opt, "_sync_flags"):
+            self.opt._sync_flags()               # name-derived has-gradient mask: without it a bucket would wait for parameters
+        flags = self.opt._flags_host if self.opt._have_flags else None      # that never report and only leave in finish()
         for bi, (lo, hi, _) in enumerate(self.buckets):
             self._pending[bi] = sum(1 for i in range(lo, hi) if flags is None or int(flags[i]) & 1)
         self._handles = []
-        self._seen = set()
+        self._done = set()                       # parameter indices already counted this backward
+        self._launched = set()
         self._multi = {id(p) for p in self.bank_params}
+        self._flags = flags
+
+    def _mark_ready(self, i):
+        """Parameter i's gradient kernels are enqueued.  Two sources report -- autograd's post-accumulate hook and the native
+        kernels' callback (gradients accumulated in place into the flat buffer) -- and BOTH may fire for the same parameter:
+        count each parameter once (counting twice launched every bucket at its half-way point: 10 % wrong sums, r2 debug)."""
+        if i in self._done:
+            return
+        self._done.add(i)
+        if self._flags is not None and not (int(self._flags[i]) & 1):
+            return                               # not part of the bucket's count
+        bi = self._param_bucket[i]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and bi not in self._launched:
+            self._launch(bi)
 
     def _make_hook(self, i):
-        def hook(_p):
-            bi = self._param_bucket[i]
-            self._pending[bi] -= 1
-            if self._pending[bi] == 0:
-                self._launch(bi)
+        def hook(p):
+            if id(p) in self._multi:             # the bank is written by every block: it leaves in finish()
+                return
+            self._mark_ready(i)
         return hook
 
     def _on_native_ready(self, params):
         for p in params:
             i = self._pindex.get(id(p))
-            if i is None:
+            if i is None or id(p) in self._multi:
                 continue
-            bi = self._param_bucket[i]
-            if p in self._seen:            # shared parameters (the bank) are reported by every block: count once,
-                continue                   # when the LAST user has run -- handled by finish() for those
-            self._seen.add(p)
-            if id(p) in self._multi:
-                continue
-            self._pending[bi] -= 1
-            if self._pending[bi] == 0:
-                self._launch(bi)
+            self._mark_ready(i)
 
     def add_producer_stream(self, stream):
         """A stream besides the current one on which gradient kernels run (HQAViT's lateral path runs its backward on a
@@ -115,6 +150,7 @@ class GradAllReducer:
     def _launch(self, bi):
         """SUM all-reduce of one bucket; the 1 / world of the mean is folded into the optimizer's clip pass."""
         buf = self.buckets[bi][2]
+        self._launched.add(bi)
         if self._stream is not None:
             self._wait_producers()
             with torch.cuda.stream(self._stream):
@@ -150,7 +186,12 @@ class GradAllReducer:
             return
         if self.bank_params:
             self._bank_to_tail()
-        dist.all_reduce(self._full, group=self.group)
+        if self.native and self._comm is None and self._full.is_cuda:
+            self._comm = native_comm(self.group)           # exists once the group has run its first collective
+        if self.native and self._comm is not None and self._full.is_cuda:
+            native_allreduce_sum(self._comm, [self._full])  # the C ABI's qavit_dp_allreduce_sum on the current stream
+        else:
+            dist.all_reduce(self._full, group=self.group)
         if self.bank_params:
             self._tail_to_bank()
 
@@ -159,7 +200,7 @@ class GradAllReducer:
         if self.world == 1:
             return
         for bi in range(len(self.buckets)):
-            if self._pending[bi] > 0:
+            if bi not in self._launched:
                 self._pending[bi] = 0
                 self._launch(bi)
         if self.bank_params:

@@ -1,6 +1,7 @@
 """Data-parallel correctness on real GPUs over NCCL (needs >= 2 devices: `gpurun --gpus 2`; skipped on a 1-GPU box).
 
-Two ranks, identical replicas, different batch shards.  After the flat all-reduce + clip:
+Two ranks, identical replicas, different batch shards.  After the flat all-reduce (the C ABI's qavit_dp_allreduce_sum on the process
+group's own ncclComm_t) + clip:
   * every gradient equals the mean over ranks of the per-rank gradients (gathered with plain torch.distributed calls),
   * global_k / global_v equal the mean of the rank-local banks, update_count agrees on every rank,
   * the clip coefficient is that of the MEAN gradient (the 1 / world is folded into the clip pass),
@@ -65,6 +66,7 @@ def _worker(rank, world, port, family, ret):
         mean_g, mean_bank = torch.stack(gathered).mean(0), torch.stack(banks).mean(0)
         red.reduce_flat()
         torch.cuda.synchronize()
+        out["native_c_abi"] = red._comm is not None       # the reduction went through qavit_dp_allreduce_sum with torch's ncclComm_t
         got_bank = torch.cat([model.global_bank.global_k.data.reshape(-1), model.global_bank.global_v.data.reshape(-1)])
         out["sum_equals_world_x_mean"] = bool(torch.allclose(opt.flat_g * opt.grad_prescale, mean_g, rtol=1e-6, atol=1e-9))
         out["bank_mean"] = bool(torch.allclose(got_bank, mean_bank, rtol=1e-6, atol=1e-9))
@@ -146,6 +148,7 @@ def test_two_rank_nccl_allreduce_matches_the_cross_rank_mean(family):
         o = ret[rank]
         print(f"rank {rank} {family}: {o}")
         assert "error" not in o, o["error"]
+        assert o["native_c_abi"], "reduce_flat fell back to torch.distributed: qavit_dp_* not exercised"
         assert o["sum_equals_world_x_mean"] and o["bank_mean"] and o["banks_differed_before"]
         assert o["update_count"][0] == o["update_count"][1] > 0
         assert o["clip_norm"] and o["clipped_grads"] and o["params_identical"]
