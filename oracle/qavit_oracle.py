@@ -435,11 +435,13 @@ def rrcv(A: Tensor, sd, p: str, cfg: OracleConfig, hw: int) -> Tensor:
     return A + sd[p + ".beta"] * _ln(r, sd, p + ".norm")
 
 
-def split_fusion(T: Tensor, R: Tensor, sd, p: str) -> Tensor:
-    """SplitFusion.forward (H:941-965) with the hard-coded Dropout(0.1) (H:930) at p=0."""
+def split_fusion(T: Tensor, R: Tensor, sd, p: str, keep: Optional[Tensor] = None) -> Tensor:
+    """SplitFusion.forward (H:941-965); ``keep``: keep-scale tensor [B, N, d] of the hard-coded Dropout(0.1) after the GELU of
+    cat_mlp (H:930), None = p 0."""
     gate = torch.sigmoid(_lin(_ln(T + R, sd, p + ".gate_norm"), sd, p + ".gate_fc"))
     t_add = T + gate * R
-    t_cat = T + _gelu(_ln(_lin(torch.cat([T, R], -1), sd, p + ".cat_mlp.0"), sd, p + ".cat_mlp.1"))
+    m = _gelu(_ln(_lin(torch.cat([T, R], -1), sd, p + ".cat_mlp.0"), sd, p + ".cat_mlp.1"))
+    t_cat = T + (m if keep is None else m * keep)
     w = torch.softmax(sd[p + ".fusion_weights"], 0)
     return _ln(w[0] * t_add + w[1] * t_cat, sd, p + ".final_norm")
 
@@ -481,7 +483,8 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, train: bool = F
     ``new_state`` (train mode) receives the mutated non-autograd state: global_k/global_v,
     update_count and BatchNorm running statistics.  ``mask_fn(block_index, B, tokens)`` (train
     mode, optional) returns the dropout masks of a block (see quad_block); ``mask_fn("pos", B, N)``
-    the keep-scale tensor of pos_drop (H:1251); ``mask_fn("stem", B, 0)`` (HQAViTv2 stem) a dict
+    the keep-scale tensor of pos_drop (H:1251); ``mask_fn("fuse2" | "fuse3" | "fuse4", B, N)`` that of
+    SplitFusion's Dropout (H:930) or None; ``mask_fn("stem", B, 0)`` (HQAViTv2 stem) a dict
     {block name: DropPath keep scale [B]} or None."""
     bank = Bank(sd, cfg)
     blk_no = [0]
@@ -510,7 +513,8 @@ def forward(sd: Dict[str, Tensor], cfg: OracleConfig, x: Tensor, train: bool = F
         T = pos_drop(patch_embed(x, sd, cfg))
         for st, nblk in enumerate(cfg.stage_depths, start=1):
             if st >= 2:
-                T = split_fusion(T, R[st - 2], sd, f"fuse{st}")
+                fk = mask_fn(f"fuse{st}", T.shape[0], T.shape[1]) if (mask_fn is not None and train) else None
+                T = split_fusion(T, R[st - 2], sd, f"fuse{st}", fk)
             for i in range(nblk):
                 T = wrapped_block(T, sd, f"stage{st}_blocks.{i}", cfg, bank, train, masks_for(T))
     else:

@@ -20,6 +20,10 @@
 // Batch reductions (dE, d bank) accumulate in mma C registers across a warp's tasks and are flushed once per warp.
 #include "kernels.h"
 
+#ifndef ATTB_M
+#define ATTB_M 3   // CTAs per SM the backward kernel is compiled for (A/B knob)
+#endif
+
 namespace {
 
 constexpr int HD = 48, NQ = 16, LP = 16, KLIN = 32, KB = 16;
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) attn_mma_fwd_kernel(AttnP p, in
 }
 
 template <bool LINF>
-__global__ void __launch_bounds__(WARPS * 32, 3) attn_mma_bwd_kernel(AttnP p, int ntask) {
+__global__ void __launch_bounds__(WARPS * 32, ATTB_M) attn_mma_bwd_kernel(AttnP p, int ntask) {
   QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   constexpr int NT = LINF ? 6 : 2, LT = LINF ? 4 : 0;

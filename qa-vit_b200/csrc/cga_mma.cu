@@ -13,6 +13,11 @@ constexpr int PK = 24;    // pitch of 16-wide rows (q, k, v)
 constexpr int PP = 40;    // pitch of 32-wide rows (P, dS)
 constexpr int PD = 56;    // pitch of the 48-wide [dq | dk | dv] staging
 constexpr int WARPS = 4;
+#ifndef CGA_WB
+#define CGA_WB 12
+#endif
+constexpr int WARPS_BWD = CGA_WB;   // backward: 17.5 KB of warp-private tiles + 168 registers per thread -- ONE 12-warp CTA fills an SM's shared
+                                // memory (223 KB) and register file (63 K); 4-warp CTAs fitted only twice (8 warps per SM, ncu: 12 % occupancy)
 
 __device__ __forceinline__ uint32_t sa(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ldsm4(uint32_t* r, uint32_t addr) {
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(WARPS * 32) cga_mma_fwd_kernel(CgaP p) {
   }
 }
 
-__global__ void __launch_bounds__(WARPS * 32) cga_mma_bwd_kernel(CgaP p) {
+__global__ void __launch_bounds__(WARPS_BWD * 32, 1) cga_mma_bwd_kernel(CgaP p) {
   QV_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t smraw[];
   float* bias = reinterpret_cast<float*>(smraw);                    // [48]
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(WARPS * 32) cga_mma_bwd_kernel(CgaP p) {
   __syncthreads();
   const bf16* dout = static_cast<const bf16*>(p.dout);
   float dWacc[3][4][4], dbacc[6][2];
+  constexpr int WARPS = WARPS_BWD;
 #pragma unroll
   for (int m = 0; m < 3; ++m)
 #pragma unroll
@@ -438,10 +444,10 @@ int cga_mma_fwd(cudaStream_t s, const CgaP& p) {
 int cga_mma_bwd(cudaStream_t s, const CgaP& p) {
   if (p.B <= 0) return 0;
   QV_CHECK(p.lddo % 8 == 0 && p.lddx % 2 == 0, "cga_mma_bwd: unaligned gradient buffers");
-  const size_t smem = (3 * CPG + 2 * KB * CPG) * 4 + (size_t)(3 * CPG * PW + 2 * KB * PK + WARPS * WS::END_BWD) * 2;
-  if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(cga_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = min(cdiv(p.B, WARPS), qv_num_sms() * 2);
-  qv_launch(cga_mma_bwd_kernel, grid, WARPS * 32, smem, s, p);
+  const size_t smem = (3 * CPG + 2 * KB * CPG) * 4 + (size_t)(3 * CPG * PW + 2 * KB * PK + WARPS_BWD * WS::END_BWD) * 2;
+  QV_CUDA(cudaFuncSetAttribute(cga_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = min(cdiv(p.B, WARPS_BWD), qv_num_sms() * (WARPS_BWD >= 12 ? 1 : 2));
+  qv_launch(cga_mma_bwd_kernel, grid, WARPS_BWD * 32, smem, s, p);
   QV_LAUNCH_CHECK();
   return 0;
 }

@@ -19,23 +19,18 @@ template <> struct Vec8<bf16> {
   static __device__ __forceinline__ void st(bf16* p, const float* v) { store_vec<8>(p, v); }
 };
 
-// keep-mask scale for 8 consecutive elements starting at element index e0 (multiple of 8): 1 / (1 - p) or 0
+// keep-mask scale for 8 consecutive elements starting at element index e0 (multiple of 8): the scheme of drop_rows / the GEMM
+// epilogues (drop_keep8: ONE Philox call per 8 elements, 16 random bits each; was two calls with 24 bits) -- so the mask of
+// SplitFusion's Dropout is Site(seed, offset, site, p).keep_rows(rows, C) in tests/dropout_masks.py
 __device__ __forceinline__ void dropout_scale8(const unsigned long long* rng, uint32_t site, unsigned long long e0, float p,
                                                float* sc) {
-  const unsigned long long seed = rng[0], off = rng[1];
-  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ site);
-  const float keep = 1.f / (1.f - p);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const unsigned long long q = (e0 >> 2) + h;
-    const uint4 r = philox4x32(key, make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)off, (uint32_t)(off >> 32)));
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sc[h * 4 + i] = ((w[i] >> 8) * (1.0f / 16777216.0f)) >= p ? keep : 0.f;
-  }
+  DropP d;
+  d.p = p; d.rng = rng; d.site = site;
+  const DropState st = drop_state(d);
+  drop_keep8(st, e0 >> 3, sc);
 }
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm
 // sums[0..C) += sum_rows (x - shift), sums[C..2C) += sum_rows (x - shift)^2, shift = x[0, c]  (guards the variance
@@ -523,8 +518,14 @@ __device__ __forceinline__ void softmax2(const float* fw, float* w0, float* w1) 
 }
 
 // K2: out = LN_final(w0 * (T + sigmoid(glin) * R) + w1 * (T + dropout(gelu(LN_cat(cpre)))))
+#ifndef SFF_M
+#define SFF_M 3
+#endif
+#ifndef SFP_M
+#define SFP_M 3
+#endif
 template <typename T, int EPL>
-__global__ void __launch_bounds__(256, 3) sf_post_fwd_kernel(SfP p, float* __restrict__ out, float* __restrict__ cat_stats,
+__global__ void __launch_bounds__(256, SFF_M) sf_post_fwd_kernel(SfP p, float* __restrict__ out, float* __restrict__ cat_stats,
                                                           float* __restrict__ fin_stats) {
   QV_PDL_ENTRY();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, c0 = lane * EPL;
@@ -564,8 +565,14 @@ __global__ void __launch_bounds__(256, 3) sf_post_fwd_kernel(SfP p, float* __res
 
 // K2 backward: dT_part (fp32), dR_part, dglin, dcpre (T-type); column gradients of final_norm / cat_mlp.1 and the two
 // fusion-weight partials (draw[2], before the softmax backward) accumulated.
+#ifndef SFB_T
+#define SFB_T 128
+#endif
+#ifndef SFB_M
+#define SFB_M 3
+#endif
 template <typename T, int EPL>
-__global__ void __launch_bounds__(256, 2) sf_post_bwd_kernel(SfP p, const float* __restrict__ dout, const float* __restrict__ cat_stats,
+__global__ void __launch_bounds__(SFB_T, SFB_M) sf_post_bwd_kernel(SfP p, const float* __restrict__ dout, const float* __restrict__ cat_stats,
                                                           const float* __restrict__ fin_stats, float* __restrict__ dT,
                                                           float* __restrict__ dR, T* __restrict__ dglin, T* __restrict__ dcpre,
                                                           float* __restrict__ d_fin_g, float* __restrict__ d_fin_b,
@@ -652,7 +659,7 @@ __global__ void __launch_bounds__(256, 2) sf_post_bwd_kernel(SfP p, const float*
 
 // K1 backward: ds = LN_gate-backward(dg_in);  dT = dT_part + ds + dcat[:, :C];  dR = dR_part + ds + dcat[:, C:]
 template <typename T, int EPL>
-__global__ void __launch_bounds__(256, 3) sf_pre_bwd_kernel(const float* __restrict__ Tin, const float* __restrict__ R,
+__global__ void __launch_bounds__(256, SFP_M) sf_pre_bwd_kernel(const float* __restrict__ Tin, const float* __restrict__ R,
                                                          const T* __restrict__ dg_in, const T* __restrict__ dcat, long rows, int C,
                                                          const float* __restrict__ gamma, const float* __restrict__ stats,
                                                          float* dT, float* dR, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -886,9 +893,9 @@ int sf_post_bwd(cudaStream_t s, int dt, const SfArgs& a, const float* dout, cons
                 float* dR, void* dglin, void* dcpre, float* d_fin_g, float* d_fin_b, float* d_cat_g, float* d_cat_b, float* draw) {
   const int epl = row_epl(a.C);
   SfP p{a.Tin, a.R, a.glin, a.cpre, a.cat_g, a.cat_b, a.fin_g, a.fin_b, a.fw, a.drop_p, a.rng, a.site, a.rows, a.C};
-  const int grid = row_grid((a.rows + 1) / 2, 4);
+  const int grid = row_grid((a.rows + 1) / 2, 4 * (256 / SFB_T));
 #define SF_GO(T, E) \
-  qv_launch(sf_post_bwd_kernel<T, E>, grid, 256, 0, s, p, dout, cat_stats, fin_stats, dT, dR, (T*)dglin, (T*)dcpre, d_fin_g, d_fin_b, d_cat_g, d_cat_b, draw)
+  qv_launch(sf_post_bwd_kernel<T, E>, grid, SFB_T, 0, s, p, dout, cat_stats, fin_stats, dT, dR, (T*)dglin, (T*)dcpre, d_fin_g, d_fin_b, d_cat_g, d_cat_b, draw)
   if (dt == QV_BF16) { if (epl == 8) SF_GO(bf16, 8); else SF_GO(bf16, 4); }
   else { if (epl == 8) SF_GO(float, 8); else SF_GO(float, 4); }
 #undef SF_GO

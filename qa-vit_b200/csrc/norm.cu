@@ -71,8 +71,11 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, i
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) [+ resid],  g = dy * gamma;  dgamma += dy * xhat, dbeta += dy.
 // dx is written as T (dx_t) and / or fp32 (dx_f32).  resid must not alias an output.
+#ifndef LNB_M
+#define LNB_M 3
+#endif
 template <typename TX, typename TDY, typename TO, int EPL, bool GELU_IN>
-__global__ void __launch_bounds__(256, 3) ln_bwd_kernel(const TX* __restrict__ x, int ldx, const TDY* __restrict__ dy,
+__global__ void __launch_bounds__(256, LNB_M) ln_bwd_kernel(const TX* __restrict__ x, int ldx, const TDY* __restrict__ dy,
                                                      int lddy, int rows, int C, const float* __restrict__ gamma,
                                                      const float* __restrict__ stats, TO* __restrict__ dx_t,
                                                      float* __restrict__ dx_f32, const float* __restrict__ resid,

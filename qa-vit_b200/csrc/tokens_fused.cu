@@ -25,6 +25,10 @@
 // (the predecessors serialised load / convert / MMA per image and ran at 1.4 - 2.5 TB/s).
 #include "kernels.h"
 
+#ifndef TLFB_M
+#define TLFB_M 2   // CTAs per SM the backward kernel is compiled for (A/B knob)
+#endif
+
 namespace {
 
 constexpr int FC = 192;         // channels
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(FNT, 2) tlf_fwd_kernel(const float* __restrict
 constexpr size_t TLF_BWD_SMEM = 2 * al16(FMAXN * FXP * 2) + 4 * al16(FM * FXP * 2) + 6 * al16(FMAXN * FSP * 2) + 2 * al16(FMAXN * FM * 4) +
                                 2 * al16(FMAXN * 4) + 4 * al16(FM * 4) + al16(2 * FMAXN * 2 * 4) + 2 * al16(FC * 4);
 
-__global__ void __launch_bounds__(FNT, 2) tlf_bwd_kernel(const float* __restrict__ x, const float* __restrict__ Sin,
+__global__ void __launch_bounds__(FNT, TLFB_M) tlf_bwd_kernel(const float* __restrict__ x, const float* __restrict__ Sin,
                                                          const float* __restrict__ Zin, const float* __restrict__ dxc, int B, int N,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ W, float eps, float* __restrict__ dx,

@@ -215,3 +215,41 @@ def test_hqavitv2_stem_droppath_matches_oracle():
     assert (num / den) ** 0.5 < 1e-4
     for k in ("cnn_stem.stage3.1.gamma", "cnn_stem.stage4.0.pwconv2.weight", "cnn_stem.stem.0.weight", "cnn_stem.downsample2.0.weight"):
         assert rel_l2(named[k].grad, ref_grads[k]) < 5e-4, k
+
+
+def test_splitfusion_dropout_matches_oracle():
+    """SplitFusion's hard-coded Dropout(0.1) after cat_mlp's GELU (H:930): in-kernel masks (site 0x5F01, drop_rows ids on the
+    [B N, d] matrix, one Philox offset per call) against the oracle fed the restated masks -- whole model, fp32 run, all gradients."""
+    import qavit_b200 as Q
+    from dropout_masks import Site
+    model, ocfg, sd, _ = build_model("hqavit_c100", precision="fp32")
+    model.train()
+    ps = {"fuse2": 0.1, "fuse3": 0.3, "fuse4": 0.2}
+    for n, p in ps.items():
+        getattr(model, n).cat_mlp[3].p = p
+    B, N, d = 5, 64, 192
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    y = torch.randint(0, 100, (B,), generator=g)
+    seed, offset = 0x5EEDFACE1234, 100
+    _set_rng(seed, offset)
+    logits = model(x.cuda())
+    loss = Q.cross_entropy(logits, y.cuda(), label_smoothing=0.1)
+    loss.backward()
+    # the three SplitFusion calls are the only rng users of this configuration: offsets offset, offset + 1, offset + 2
+    keeps = {n: Site(seed, offset + i, 0x5F01, p).keep_rows(B * N, d).view(B, N, d) for i, (n, p) in enumerate(ps.items())}
+    assert all(0.5 * p < (k == 0).float().mean().item() < 1.5 * p for (n, p), k in zip(ps.items(), keeps.values()))
+
+    def mask_fn(which, Bq, n):
+        return keeps.get(which) if isinstance(which, str) else None
+    ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd, ocfg, x, y, label_smoothing=0.1, mask_fn=mask_fn)
+    assert rel_max(logits, ref_logits) < 1e-4
+    assert abs(loss.item() - ref_loss.item()) < 2e-5
+    named = dict(model.named_parameters())
+    num = den = 0.0
+    for k, gr in ref_grads.items():
+        if gr is None:
+            continue
+        num += (named[k].grad.cpu() - gr).norm().item() ** 2
+        den += gr.norm().item() ** 2
+    assert (num / den) ** 0.5 < 1e-4
