@@ -551,7 +551,8 @@ class LateralPartFn(torch.autograd.Function):
         out = None
         Rp = [None, None, None]
         if part == 0:
-            out = torch.zeros(1, dtype=torch.float32, device=dev)
+            out = torch.empty(1, dtype=torch.float32, device=dev)    # never read: it only orders the stem's backward after the adapters'
+            ctx.set_materialize_grads(False)                          # ... whose token gradient is None (no ATen fill / add kernels)
         else:
             N = cfg.grid * cfg.grid
             out = torch.empty(cfg.batch, N, cfg.dim, dtype=torch.float32, device=dev)
@@ -587,8 +588,7 @@ class LateralPartFn(torch.autograd.Function):
         if part == 0:
             state.saved = None
         _notify(direct)
-        dinp = None if part == 0 else torch.zeros(1, dtype=torch.float32, device=dev)
-        return (dinp, None, None, *views)
+        return (None, None, None, *views)
 
 
 class SplitFusionFn(torch.autograd.Function):

@@ -80,10 +80,35 @@ class GraphedTrainStep:
             self._between()
         self._update()
 
+    def prefetch(self, x: torch.Tensor, y: torch.Tensor) -> None:
+        """Start the host -> device copy of the NEXT step's batch (pinned host tensors) on a copy stream, into a staging pair; the
+        next ``__call__()`` without arguments consumes it.  Called right after launching step i, the copy of batch i + 1 runs under
+        step i instead of in front of step i + 1 (58 MB per step at the headline batch: ~2 % of the step)."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.x.device)
+            self._xs, self._ys = torch.empty_like(self.x), torch.empty_like(self.y)
+            self._stage_ready, self._stage_free = torch.cuda.Event(), torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(self.x.device))
+            self._pending = False
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free)          # the step that consumed the previous staging pair has read it
+        with torch.cuda.stream(cs):
+            self._xs.copy_(x, non_blocking=True)
+            self._ys.copy_(y, non_blocking=True)
+            self._stage_ready.record(cs)
+        self._pending = True
+
     def __call__(self, x: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
                  y_b: Optional[torch.Tensor] = None, lam: float = 1.0) -> torch.Tensor:
-        """Run one training step on (x, y) (host or device tensors; None = reuse the resident batch).  With mix=True,
-        (y_b, lam) select the two-target loss of this step (y_b None: plain CE, lam = 1)."""
+        """Run one training step on (x, y) (host or device tensors; None = the prefetched batch if prefetch() was called, else the
+        resident batch).  With mix=True, (y_b, lam) select the two-target loss of this step (y_b None: plain CE, lam = 1)."""
+        if x is None and getattr(self, "_pending", False):
+            main = torch.cuda.current_stream(self.x.device)
+            main.wait_event(self._stage_ready)
+            self.x.copy_(self._xs, non_blocking=True)      # device -> device into the graph's static input
+            self.y.copy_(self._ys, non_blocking=True)
+            self._stage_free.record(main)
+            self._pending = False
         if x is not None:
             self.x.copy_(x, non_blocking=True)
         if y is not None:

@@ -367,3 +367,32 @@ def test_match_autocast_output_dtype_is_opt_in():
         b = model(x)
     assert a.dtype == torch.float32 and b.dtype == torch.bfloat16       # the reference's head Linear returns bf16 under autocast
     assert torch.equal(a.to(torch.bfloat16), b)
+
+
+def test_graphed_step_prefetch_pipeline_equals_direct_copies():
+    """GraphedTrainStep.prefetch(): the next batch's pinned-host -> device copy runs on a copy stream under the current step; the
+    step sequence must see exactly the batches it would see with the copy in front of each step."""
+    import copy
+    base, ocfg, sd, _ = build_model("qavitv2_c100", precision="fp32")
+    base.train()
+    B, n = 4, 4
+    g = torch.Generator().manual_seed(21)
+    xs = [torch.randn(B, 3, 32, 32, generator=g).pin_memory() for _ in range(n)]
+    ys = [torch.randint(0, 100, (B,), generator=g).pin_memory() for _ in range(n)]
+
+    def make():
+        m = copy.deepcopy(base)
+        opt = Q.FusedAdamW(m.named_parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.05, max_grad_norm=0.5)
+        return Q.GraphedTrainStep(m, opt, xs[0].cuda(), ys[0].cuda(), label_smoothing=0.1, autocast_bf16=False, warmup=2)
+    a, b = make(), make()
+    direct = [a(xs[i], ys[i]).item() for i in range(n)]
+    piped = []
+    b.prefetch(xs[0], ys[0])
+    for i in range(n):
+        loss = b()
+        if i + 1 < n:
+            b.prefetch(xs[i + 1], ys[i + 1])
+        piped.append(loss.item())
+    assert len(set(round(v, 3) for v in direct)) > 1          # the batches differ, so the losses do
+    for d, p in zip(direct, piped):
+        assert abs(d - p) < 1e-4 * max(1.0, abs(d)), (direct, piped)
