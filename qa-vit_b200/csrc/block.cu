@@ -108,6 +108,10 @@ struct Dims {
   bool tl, v1;
   bool ftok, fup;   // TokenLearner / TokenUpMix run as the fused split-precision kernels of tokens_fused.cu
   bool fcmp;        // branch LayerNorm + compress + fusion scale of all 4 branches as one kernel per direction (cmp_fused.cu)
+  bool xstk;        // the three projections that read norm1's output -- swa.qkv (3d), msda.qkv's q rows (d), cross_attn.q_proj (d) -- run
+                    // as ONE [R, d] x [5d, d]^T GEMM into one [R, 5d] buffer (consumers index it with a row pitch of 5d); backward: one
+                    // dX GEMM over K = 5d and one dW GEMM whose rows scatter to the three parameters' gradients (tc_gemm_tn_seg)
+  int ldp, ldq1;    // row pitch of the qkv_swa buffer / of the q_msda and q_cross buffers (5d when stacked, else 3d / d)
   int tdt;          // storage / GEMM type of the TokenLearner gate path (LN output, logits): fp32 whenever no tensor-core token
                     // kernel covers the shape (e.g. 576 -> 16 tokens of the 96 x 96 recipe) -- bf16 gate logits under a softmax over
                     // hundreds of tokens were the largest single bf16 error source of the model
@@ -116,17 +120,17 @@ struct Dims {
 
 // gemm weights that get bf16 copies in bf16 runs
 enum { W_SWA_QKV, W_SWA_PROJ, W_MSDA_Q, W_MSDA_KV, W_MSDA_PROJ, W_CGA_PROJ, W_CROSS_Q, W_CROSS_PROJ, W_C0, W_C1, W_C2,
-       W_C3, W_B1, W_B2, W_F1, W_F2, W_TL, W_WRITE, W_COUNT };
+       W_C3, W_B1, W_B2, W_F1, W_F2, W_TL, W_WRITE, W_XSTK, W_COUNT };
 
 struct Saved {  // byte offsets into `saved`
   size_t tl_stats, tl_ln, tl_S, tl_Z, xc, n1_stats, xn, alpha, snap[4], qkv_swa, attn_swa, xp, kv_msda, q_msda, attn_msda,
       attn_cga, kbp, vbp, q_cross, Kc, Vc, attn_cross, branch[4], nb_stats[4], nb[4], fused, h1_pre, h1, x1, n2_stats, y,
-      h_pre, h, dn_stats, hn, cs, pd_stats, hn2, o, out_blk, up, up_stats, wb[W_COUNT], wbt[W_COUNT], wstack, bstack, rng, rs, total;
+      h_pre, h, dn_stats, hn, cs, pd_stats, hn2, o, out_blk, up, up_stats, wb[W_COUNT], wbt[W_COUNT], wstack, bstack, bxstk, rng, rs, total;
 };
 struct Scratch {  // byte offsets into `scratch`
   size_t tl_logits, tn, cgbuf, partial, attn_ws_f, total_fwd;
   size_t d_up, d_blk, d_o, d_hn2, d_cs, d_hn, d_hpre, d_y, d_x1, d_x1t, d_h1, d_h1pre, d_fused, d_nb, d_branch, d_branch3[3], d_attn,
-      d_qkv, d_kv, d_xp, d_q, d_xn, dKc, dVc, dkbp, dvbp, draw, d_logits, d_tl_ln, attn_ws_b, total_bwd;
+      d_qkv, d_kv, d_xp, d_q, d_qc, d_xn, dKc, dVc, dkbp, dvbp, draw, d_logits, d_tl_ln, attn_ws_b, total_bwd;
 };
 
 int msda_tokens(const qavit_block_cfg& c, int side) {
@@ -164,6 +168,10 @@ int make_dims(const qavit_block_cfg& c, Dims* D) {
   D->tdt = (c.dtype == QV_BF16 && D->tl && !D->ftok && !tokens_mma_ok(c.tokens, c.tokens_full, c.dim) &&
             !tokens_mma64_ok(c.tokens, c.tokens_full, c.dim)) ? QV_F32 : c.dtype;
   D->tts = D->tdt == QV_BF16 ? 2 : 4;
+  D->xstk = c.dtype == QV_BF16 && tc_shape_ok_nt(D->R, 5 * c.dim, c.dim, c.dim) && tc_shape_ok_nt(D->R, c.dim, 5 * c.dim, 5 * c.dim) &&
+            tc_shape_ok_tn(D->R, 5 * c.dim, c.dim, 5 * c.dim, c.dim) && getenv("QV_NO_XSTK") == nullptr;
+  D->ldp = D->xstk ? 5 * c.dim : 3 * c.dim;
+  D->ldq1 = D->xstk ? 5 * c.dim : c.dim;
   D->NM = msda_tokens(c, side);
   D->Lm = D->NM < c.msda_seq_len ? D->NM : c.msda_seq_len;
   return 0;
@@ -182,6 +190,7 @@ void weight_shape(const Dims& D, int wi, int* N, int* K) {
     case W_F2: *N = d; *K = D.fh; break;
     case W_TL: *N = D.Nt; *K = d; break;
     case W_WRITE: *N = d + D.kb; *K = d; break;
+    case W_XSTK: *N = 5 * d; *K = d; break;
     default: *N = d; *K = d; break;
   }
 }
@@ -198,16 +207,16 @@ void layout_saved(const Dims& D, Saved* S) {
   S->xn = b.take(R * d * ts);
   S->alpha = b.take(16);
   for (int i = 0; i < 4; ++i) S->snap[i] = b.take(2 * D.kb * d * 4);
-  S->qkv_swa = b.take(R * 3 * d * ts);
+  S->qkv_swa = b.take(R * (D.xstk ? 5 : 3) * d * ts);        // stacked: [qkv_swa (3d) | q_msda (d) | q_cross (d)] per row
   S->attn_swa = b.take(R * d * ts);
   S->xp = b.take((size_t)D.B * D.NM * d * ts);
   S->kv_msda = b.take((size_t)D.B * D.NM * 2 * d * ts);
-  S->q_msda = b.take(R * d * ts);
+  S->q_msda = D.xstk ? S->qkv_swa + 3 * d * ts : b.take(R * d * ts);
   S->attn_msda = b.take(R * d * ts);
   S->attn_cga = b.take(R * (d / 2) * ts);
   S->kbp = b.take(D.kb * D.cpg * 4);
   S->vbp = b.take(D.kb * D.cpg * 4);
-  S->q_cross = b.take(R * d * ts);
+  S->q_cross = D.xstk ? S->qkv_swa + 4 * d * ts : b.take(R * d * ts);
   S->Kc = b.take(D.kb * d * 4);
   S->Vc = b.take(D.kb * d * 4);
   S->attn_cross = b.take(R * d * ts);
@@ -234,12 +243,15 @@ void layout_saved(const Dims& D, Saved* S) {
   for (int i = 0; i < W_COUNT; ++i) {
     int N, K;
     weight_shape(D, i, &N, &K);
-    const bool need = D.dt == QV_BF16 && (i != W_TL || (D.tl && !D.ftok)) && !(D.fcmp && i >= W_C0 && i <= W_C3);
+    const bool stacked_away = D.xstk && (i == W_SWA_QKV || i == W_MSDA_Q || i == W_CROSS_Q);
+    const bool need = D.dt == QV_BF16 && (i != W_TL || (D.tl && !D.ftok)) && !(D.fcmp && i >= W_C0 && i <= W_C3) && !stacked_away &&
+                      (i != W_XSTK || D.xstk);
     S->wb[i] = b.take(need ? (size_t)N * K * 2 : 0);
     S->wbt[i] = b.take(need && i != W_WRITE ? (size_t)N * K * 2 : 0);
   }
   S->wstack = b.take((size_t)(d + D.kb) * d * 4);
   S->bstack = b.take((size_t)(d + D.kb) * 4);
+  S->bxstk = b.take(D.xstk ? (size_t)5 * d * 4 : 0);
   S->rng = b.take(16);                          // Philox {seed, offset} snapshot of this forward call
   S->rs = b.take((size_t)2 * D.B * 4);          // DropPath keep scales of the two residual branches
   S->total = b.off;
@@ -275,10 +287,11 @@ void layout_scratch(const Dims& D, Scratch* S) {
     S->d_branch = b.take(R * d * ts);
     for (int i = 0; i < 3; ++i) S->d_branch3[i] = b.take(D.fcmp ? R * d * ts : 0);   // fused backward emits all four d_branch at once
     S->d_attn = b.take(R * d * ts);
-    S->d_qkv = b.take(R * 3 * d * ts);
+    S->d_qkv = b.take(R * (D.xstk ? 5 : 3) * d * ts);        // stacked: [d_qkv_swa | d_q_msda | d_q_cross] per row
     S->d_kv = b.take((size_t)D.B * D.NM * 2 * d * ts);
     S->d_xp = b.take((size_t)D.B * D.NM * d * ts);
-    S->d_q = b.take(R * d * ts);
+    S->d_q = D.xstk ? S->d_qkv + 3 * d * ts : b.take(R * d * ts);
+    S->d_qc = D.xstk ? S->d_qkv + 4 * d * ts : S->d_q;
     // ---- zero-initialised accumulators, contiguous: d_xn | dKc | dVc | dkbp | dvbp | draw
     S->d_xn = b.take(R * d * 4);
     S->dKc = b.take(D.kb * d * 4);
@@ -485,10 +498,18 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
     ConvertJobs jobs{};
     for (int wi = 0; wi < W_COUNT; ++wi) {
       if ((wi == W_TL && (!D.tl || D.ftok)) || (wi == W_WRITE && !train) || (D.fcmp && wi >= W_C0 && wi <= W_C3)) continue;
+      if (D.xstk && (wi == W_SWA_QKV || wi == W_MSDA_Q || wi == W_CROSS_Q)) continue;
+      if (wi == W_XSTK && !D.xstk) continue;
       int N, K;
       weight_shape(D, wi, &N, &K);
       bf16* wb = reinterpret_cast<bf16*>(c.sv(S.wb[wi]));
-      if (wi == W_WRITE) {   // two sources stacked along N
+      if (wi == W_XSTK) {    // three sources stacked along N (rows), their transposes side by side in the [d, 5d] copy, biases concatenated
+        bf16* wbt = reinterpret_cast<bf16*>(c.sv(S.wbt[wi]));
+        float* bs = c.svf(S.bxstk);
+        jobs.j[jobs.n++] = ConvertJob{c.pf(QP_SWA_QKV_W), 3 * d, d, wb, wbt, 5 * d, c.pf(QP_SWA_QKV_B), bs, 3 * d};
+        jobs.j[jobs.n++] = ConvertJob{c.pf(QP_MSDA_QKV_W), d, d, wb + (size_t)3 * d * d, wbt + 3 * d, 5 * d, c.pf(QP_MSDA_QKV_B), bs + 3 * d, d};
+        jobs.j[jobs.n++] = ConvertJob{c.pf(QP_CROSS_Q_W), d, d, wb + (size_t)4 * d * d, wbt + 4 * d, 5 * d, c.pf(QP_CROSS_Q_B), bs + 4 * d, d};
+      } else if (wi == W_WRITE) {   // two sources stacked along N
         jobs.j[jobs.n++] = ConvertJob{c.pf(QP_BANK_WC_W), d, K, wb, nullptr};
         jobs.j[jobs.n++] = ConvertJob{c.pf(QP_BANK_WG_W), D.kb, K, wb + (size_t)d * K, nullptr};
       } else {
@@ -533,11 +554,14 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   // ---- SWA (H:441-469)
   nvtxRangePushA("swa");
   QV_TRY(snapshot_bank(c, 0));
-  QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_SWA_QKV, c.pf(QP_SWA_QKV_W)), epi_t(c, c.pf(QP_SWA_QKV_B), c.sv(S.qkv_swa), 3 * d)));
+  if (D.xstk)   // swa.qkv | msda q | cross q in one launch (the other two consumers read their column slices later)
+    QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_XSTK, nullptr), epi_t(c, c.svf(S.bxstk), c.sv(S.qkv_swa), 5 * d)));
+  else
+    QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_SWA_QKV, c.pf(QP_SWA_QKV_W)), epi_t(c, c.pf(QP_SWA_QKV_B), c.sv(S.qkv_swa), 3 * d)));
   {
     AttnP p = attn_params(c, 0);
-    p.q = c.sv(S.qkv_swa); p.ldq = 3 * d; p.qcol = 0;
-    p.kv = c.sv(S.qkv_swa); p.ldkv = 3 * d; p.kcol = d; p.vcol = 2 * d;
+    p.q = c.sv(S.qkv_swa); p.ldq = D.ldp; p.qcol = 0;
+    p.kv = c.sv(S.qkv_swa); p.ldkv = D.ldp; p.kcol = d; p.vcol = 2 * d;
     p.Ek = c.pf(QP_SWA_EK); p.Ev = c.pf(QP_SWA_EV);
     p.bank_k = snap_k(c, 0); p.bank_v = snap_v(c, 0);
     p.out = c.sv(S.attn_swa); p.ldo = d;
@@ -553,10 +577,10 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   QV_TRY(msda_pool_fwd(st, dt, xn, D.B, D.Nt, D.side, d, cfg->dilations, cfg->n_dilations, cfg->pool_stride, D.NM, c.sv(S.xp)));
   QV_TRY(gemm_nt(st, dt, c.sv(S.xp), d, D.B * D.NM, c.W(W_MSDA_KV, weight_src(c, W_MSDA_KV)),
                  epi_t(c, c.pf(QP_MSDA_QKV_B) + d, c.sv(S.kv_msda), 2 * d)));
-  QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_MSDA_Q, c.pf(QP_MSDA_QKV_W)), epi_t(c, c.pf(QP_MSDA_QKV_B), c.sv(S.q_msda), d)));
+  if (!D.xstk) QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_MSDA_Q, c.pf(QP_MSDA_QKV_W)), epi_t(c, c.pf(QP_MSDA_QKV_B), c.sv(S.q_msda), d)));
   {
     AttnP p = attn_params(c, 1);
-    p.q = c.sv(S.q_msda); p.ldq = d; p.qcol = 0;
+    p.q = c.sv(S.q_msda); p.ldq = D.ldq1; p.qcol = 0;
     p.kv = c.sv(S.kv_msda); p.ldkv = 2 * d; p.kcol = 0; p.vcol = d;
     p.Ek = c.pf(QP_MSDA_EK); p.Ev = c.pf(QP_MSDA_EV);
     p.bank_k = snap_k(c, 1); p.bank_v = snap_v(c, 1);
@@ -592,10 +616,10 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   QV_TRY(snapshot_bank(c, 3));
   QV_TRY(small_linear_fwd2(st, D.kb, d, d, snap_k(c, 3), c.pf(QP_CROSS_K_W), c.pf(QP_CROSS_K_B), c.svf(S.Kc),
                            snap_v(c, 3), c.pf(QP_CROSS_V_W), c.pf(QP_CROSS_V_B), c.svf(S.Vc)));
-  QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), epi_t(c, c.pf(QP_CROSS_Q_B), c.sv(S.q_cross), d)));
+  if (!D.xstk) QV_TRY(gemm_nt(st, dt, xn, d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), epi_t(c, c.pf(QP_CROSS_Q_B), c.sv(S.q_cross), d)));
   {
     AttnP p = attn_params(c, 2);
-    p.q = c.sv(S.q_cross); p.ldq = d; p.qcol = 0;
+    p.q = c.sv(S.q_cross); p.ldq = D.ldq1; p.qcol = 0;
     p.kc = c.svf(S.Kc); p.vc = c.svf(S.Vc);
     p.out = c.sv(S.attn_cross); p.ldo = d;
     p.drop = dc.site(DS_ATT + 3);
@@ -826,15 +850,17 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_cross), d, R, d, d, G(QP_CROSS_PROJ_W), G(QP_CROSS_PROJ_B), nullptr));
       QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_CROSS_PROJ, c.pf(QP_CROSS_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d)));
       AttnP p = attn_params(c, 2);
-      p.q = c.sv(S.q_cross); p.ldq = d; p.qcol = 0;
+      p.q = c.sv(S.q_cross); p.ldq = D.ldq1; p.qcol = 0;
       p.kc = c.svf(S.Kc); p.vc = c.svf(S.Vc);
       p.dout = c.sc(X.d_attn); p.lddo = d;
-      p.dq = c.sc(X.d_q); p.lddq = d; p.dqcol = 0;
+      p.dq = c.sc(X.d_qc); p.lddq = D.ldq1; p.dqcol = 0;
       p.dbank_k = c.scf(X.dKc); p.dbank_v = c.scf(X.dVc);
       p.drop = dc.site(DS_ATT + 3);
       QV_TRY(attn_bwd(st, dt, p));
-      QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_CROSS_Q_W), G(QP_CROSS_Q_B), nullptr));
-      QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), acc_xn));
+      if (!D.xstk) {
+        QV_TRY(gemm_tn(st, dt, c.sc(X.d_qc), d, c.sv(S.xn), d, R, d, d, G(QP_CROSS_Q_W), G(QP_CROSS_Q_B), nullptr));
+        QV_TRY(gemm_nn(st, dt, c.sc(X.d_qc), d, R, c.W(W_CROSS_Q, c.pf(QP_CROSS_Q_W)), acc_xn));
+      }
       QV_TRY(small_linear_bwd2(st, D.kb, d, d, snap_k(c, 3), c.pf(QP_CROSS_K_W), c.scf(X.dKc), G(QP_CROSS_K_W), G(QP_CROSS_K_B), G(QP_BANK_K),
                                snap_v(c, 3), c.pf(QP_CROSS_V_W), c.scf(X.dVc), G(QP_CROSS_V_W), G(QP_CROSS_V_B), G(QP_BANK_V)));
     } else if (i == 2) {  // ---- CGA
@@ -859,19 +885,21 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_msda), d, R, d, d, G(QP_MSDA_PROJ_W), G(QP_MSDA_PROJ_B), nullptr));
       QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_MSDA_PROJ, c.pf(QP_MSDA_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d)));
       AttnP p = attn_params(c, 1);
-      p.q = c.sv(S.q_msda); p.ldq = d; p.qcol = 0;
+      p.q = c.sv(S.q_msda); p.ldq = D.ldq1; p.qcol = 0;
       p.kv = c.sv(S.kv_msda); p.ldkv = 2 * d; p.kcol = 0; p.vcol = d;
       p.Ek = c.pf(QP_MSDA_EK); p.Ev = c.pf(QP_MSDA_EV);
       p.bank_k = snap_k(c, 1); p.bank_v = snap_v(c, 1);
       p.dout = c.sc(X.d_attn); p.lddo = d;
-      p.dq = c.sc(X.d_q); p.lddq = d; p.dqcol = 0;
+      p.dq = c.sc(X.d_q); p.lddq = D.ldq1; p.dqcol = 0;
       p.dkv = c.sc(X.d_kv); p.lddkv = 2 * d; p.dkcol = 0; p.dvcol = d;
       p.dEk = G(QP_MSDA_EK); p.dEv = G(QP_MSDA_EV); p.dbank_k = G(QP_BANK_K); p.dbank_v = G(QP_BANK_V);
       if (dt == QV_BF16 && D.Nt > 16) p.wsp = c.sc(X.attn_ws_b);
       p.drop = dc.site(DS_ATT + 1);
       QV_TRY(attn_bwd(st, dt, p));
-      QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_MSDA_QKV_W), G(QP_MSDA_QKV_B), nullptr));
-      QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_MSDA_Q, c.pf(QP_MSDA_QKV_W)), acc_xn));
+      if (!D.xstk) {
+        QV_TRY(gemm_tn(st, dt, c.sc(X.d_q), d, c.sv(S.xn), d, R, d, d, G(QP_MSDA_QKV_W), G(QP_MSDA_QKV_B), nullptr));
+        QV_TRY(gemm_nn(st, dt, c.sc(X.d_q), d, R, c.W(W_MSDA_Q, c.pf(QP_MSDA_QKV_W)), acc_xn));
+      }
       QV_TRY(gemm_tn(st, dt, c.sc(X.d_kv), 2 * d, c.sv(S.xp), d, D.B * D.NM, 2 * d, d, G(QP_MSDA_QKV_W) + (size_t)d * d,
                      G(QP_MSDA_QKV_B) + d, nullptr));
       QV_TRY(gemm_nn(st, dt, c.sc(X.d_kv), 2 * d, D.B * D.NM, c.W(W_MSDA_KV, weight_src(c, W_MSDA_KV)), epi_t(c, nullptr, c.sc(X.d_xp), d)));
@@ -880,19 +908,30 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
       QV_TRY(gemm_tn(st, dt, d_branch, d, c.sv(S.attn_swa), d, R, d, d, G(QP_SWA_PROJ_W), G(QP_SWA_PROJ_B), nullptr));
       QV_TRY(gemm_nn(st, dt, d_branch, d, R, c.W(W_SWA_PROJ, c.pf(QP_SWA_PROJ_W)), epi_t(c, nullptr, c.sc(X.d_attn), d)));
       AttnP p = attn_params(c, 0);
-      p.q = c.sv(S.qkv_swa); p.ldq = 3 * d; p.qcol = 0;
-      p.kv = c.sv(S.qkv_swa); p.ldkv = 3 * d; p.kcol = d; p.vcol = 2 * d;
+      p.q = c.sv(S.qkv_swa); p.ldq = D.ldp; p.qcol = 0;
+      p.kv = c.sv(S.qkv_swa); p.ldkv = D.ldp; p.kcol = d; p.vcol = 2 * d;
       p.Ek = c.pf(QP_SWA_EK); p.Ev = c.pf(QP_SWA_EV);
       p.bank_k = snap_k(c, 0); p.bank_v = snap_v(c, 0);
       p.dout = c.sc(X.d_attn); p.lddo = d;
-      p.dq = c.sc(X.d_qkv); p.lddq = 3 * d; p.dqcol = 0;
-      p.dkv = c.sc(X.d_qkv); p.lddkv = 3 * d; p.dkcol = d; p.dvcol = 2 * d;
+      p.dq = c.sc(X.d_qkv); p.lddq = D.ldp; p.dqcol = 0;
+      p.dkv = c.sc(X.d_qkv); p.lddkv = D.ldp; p.dkcol = d; p.dvcol = 2 * d;
       p.dEk = G(QP_SWA_EK); p.dEv = G(QP_SWA_EV); p.dbank_k = G(QP_BANK_K); p.dbank_v = G(QP_BANK_V);
       p.drop = dc.site(DS_ATT + 0);
       QV_TRY(attn_bwd(st, dt, p));
-      QV_TRY(gemm_tn(st, dt, c.sc(X.d_qkv), 3 * d, c.sv(S.xn), d, R, 3 * d, d, G(QP_SWA_QKV_W), G(QP_SWA_QKV_B), nullptr));
-      QV_TRY(gemm_nn(st, dt, c.sc(X.d_qkv), 3 * d, R, c.W(W_SWA_QKV, c.pf(QP_SWA_QKV_W)), acc_xn));
+      if (!D.xstk) {
+        QV_TRY(gemm_tn(st, dt, c.sc(X.d_qkv), 3 * d, c.sv(S.xn), d, R, 3 * d, d, G(QP_SWA_QKV_W), G(QP_SWA_QKV_B), nullptr));
+        QV_TRY(gemm_nn(st, dt, c.sc(X.d_qkv), 3 * d, R, c.W(W_SWA_QKV, c.pf(QP_SWA_QKV_W)), acc_xn));
+      }
     }
+  }
+  if (D.xstk) {   // [d_qkv_swa | d_q_msda | d_q_cross] against norm1's output: one dW GEMM scattered to the three parameters, one dX GEMM
+    TnSegs sg;
+    sg.n = 3;
+    sg.end[0] = 3 * d; sg.end[1] = 4 * d; sg.end[2] = 5 * d;
+    sg.dW[0] = G(QP_SWA_QKV_W); sg.dW[1] = G(QP_MSDA_QKV_W); sg.dW[2] = G(QP_CROSS_Q_W);
+    sg.db[0] = G(QP_SWA_QKV_B); sg.db[1] = G(QP_MSDA_QKV_B); sg.db[2] = G(QP_CROSS_Q_B);
+    QV_TRY(tc_gemm_tn_seg(st, static_cast<const bf16*>(c.sc(X.d_qkv)), 5 * d, static_cast<const bf16*>(c.sv(S.xn)), d, R, 5 * d, d, sg));
+    QV_TRY(gemm_nn(st, dt, c.sc(X.d_qkv), 5 * d, R, c.W(W_XSTK, nullptr), acc_xn));
   }
 
   // ---- norm1 backward: d_x = d_x1 + LN1-backward(d_xn)

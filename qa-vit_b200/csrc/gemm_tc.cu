@@ -663,7 +663,13 @@ struct TnArgs {
   float* db;           // optional bias gradient: column sums of dY, accumulated by the otherwise idle epilogue warps
   int db_mode;         // 1: dY is the A operand (columns n0 .. n0+127 of this CTA); 2: dY is the B operand (CTAs with n0 == 0)
   int db_cols;         // number of dY columns
+  TnSegs segs;         // segs.n > 0: rows of the product are scattered to per-segment dW / db (non-transposed flavour, db_mode 1)
 };
+__device__ __forceinline__ int tn_seg_of(const TnSegs& g, int n) {
+  int i = 0;
+  while (i + 1 < g.n && n >= g.end[i]) ++i;
+  return i;
+}
 
 __global__ void __launch_bounds__(TN_THREADS, 1)
 tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x, TnArgs p) {
@@ -682,7 +688,7 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
   const int mb1 = min(p.mblocks, mb0 + p.mb_per_cta);
   const int nmb = mb1 - mb0;
 
-  const bool do_db = p.db != nullptr && (p.db_mode == 1 || blockIdx.x == 0);
+  const bool do_db = (p.db != nullptr || p.segs.n > 0) && (p.db_mode == 1 || blockIdx.x == 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_y);
     tma_prefetch_desc(&map_x);
@@ -779,8 +785,17 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
           const int item = t + h * 128;
           if (item < nitems) {
             const int col = cbase + (item % (ncol / 2)) * 2;
-            if (col < p.db_cols) atomicAdd(p.db + col, acc[h][0] * sc);
-            if (col + 1 < p.db_cols) atomicAdd(p.db + col + 1, acc[h][1] * sc);
+            if (p.segs.n > 0) {
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2)
+                if (col + e2 < p.db_cols) {
+                  const int sg = tn_seg_of(p.segs, col + e2);
+                  if (p.segs.db[sg]) atomicAdd(p.segs.db[sg] + (col + e2 - (sg ? p.segs.end[sg - 1] : 0)), acc[h][e2] * sc);
+                }
+            } else {
+              if (col < p.db_cols) atomicAdd(p.db + col, acc[h][0] * sc);
+              if (col + 1 < p.db_cols) atomicAdd(p.db + col + 1, acc[h][1] * sc);
+            }
           }
         }
       }
@@ -798,6 +813,10 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_consta
           }
         } else if (n < p.N) {
           float* dst = p.dW + (long)n * p.K + c0;
+          if (p.segs.n > 0) {
+            const int sg = tn_seg_of(p.segs, n);
+            dst = p.segs.dW[sg] + (long)(n - (sg ? p.segs.end[sg - 1] : 0)) * p.K + c0;
+          }
           if (c0 + 16 <= p.K && (p.K & 3) == 0) {      // 16 B vector reductions: 4x fewer RED instructions
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
@@ -934,8 +953,18 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
   return 0;
 }
 
+static int tc_gemm_tn_impl(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
+                           const float* scale, int transposed, int ldw, float* db, int db_mode, int db_cols, const TnSegs* segs);
 int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
                const float* scale, int transposed, int ldw, float* db, int db_mode, int db_cols) {
+  return tc_gemm_tn_impl(s, dY, ldy, X, ldx, M, N, K, dW, scale, transposed, ldw, db, db_mode, db_cols, nullptr);
+}
+int tc_gemm_tn_seg(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, const TnSegs& segs) {
+  QV_CHECK(segs.n >= 1 && segs.n <= 4 && segs.end[segs.n - 1] == N, "tc_gemm_tn_seg: segments must cover the %d rows", N);
+  return tc_gemm_tn_impl(s, dY, ldy, X, ldx, M, N, K, segs.dW[0], nullptr, 0, 0, nullptr, 1, N, &segs);
+}
+static int tc_gemm_tn_impl(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
+                           const float* scale, int transposed, int ldw, float* db, int db_mode, int db_cols, const TnSegs* segs) {
   if (M <= 0) return 0;
   QV_CHECK(tc_shape_ok_tn(M, N, K, ldy, ldx), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
   TnArgs p{};
@@ -951,6 +980,7 @@ int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, 
   p.db = db;
   p.db_mode = db_mode;
   p.db_cols = db_cols;
+  if (segs) p.segs = *segs;
   const int n_tiles = cdiv(N, BM);
   // Every CTA ends with 128 x K fp32 atomics, so a CTA must own enough rows to amortise them: >= 16 m-blocks
   // (1024 rows) each, and no more CTAs than SMs.

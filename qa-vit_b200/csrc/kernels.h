@@ -68,11 +68,17 @@ int tc_gemm_nt(cudaStream_t s, const bf16* A, int lda, int M, int N, int K, cons
 // accumulated inside the same kernel (the bias gradient; no separate pass over dY).
 int tc_gemm_tn(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, float* dW,
                const float* scale, int transposed = 0, int ldw = 0, float* db = nullptr, int db_mode = 0, int db_cols = 0);
+// dW / db of a STACKED projection: row n of the product belongs to segment i (end[i - 1] <= n < end[i]) and lands in that segment's
+// own gradient tensors (the stacked weights are separate parameters)
+struct TnSegs { int n = 0; int end[4] = {0, 0, 0, 0}; float* dW[4] = {nullptr, nullptr, nullptr, nullptr}; float* db[4] = {nullptr, nullptr, nullptr, nullptr}; };
+int tc_gemm_tn_seg(cudaStream_t s, const bf16* dY, int ldy, const bf16* X, int ldx, int M, int N, int K, const TnSegs& segs);
 bool tc_shape_ok_nt(int M, int N, int K, int lda);
 bool tc_shape_ok_tn(int M, int N, int K, int ldy, int ldx);
 int colsum_accum(cudaStream_t s, int dt, const void* dY, int ldy, int M, int N, float* db, const float* scale);
 int convert_weight(cudaStream_t s, const float* w, int N, int K, bf16* wb, bf16* wbt);
-struct ConvertJob { const float* w; int N, K; bf16* wb; bf16* wbt; };
+// wbt (optional): the transpose, row pitch ldt (0 = N) -- a slice of a wider stacked [K, sum N] matrix when ldt > N.
+// bsrc / bdst (optional): bn floats copied alongside (the bias slice of a stacked projection)
+struct ConvertJob { const float* w; int N, K; bf16* wb; bf16* wbt; int ldt = 0; const float* bsrc = nullptr; float* bdst = nullptr; int bn = 0; };
 struct ConvertJobs { ConvertJob j[24]; int n; };
 int convert_weights_batched(cudaStream_t s, const ConvertJobs& jobs);   // all fp32 -> bf16 (+ transposed) copies, one launch
 

@@ -544,8 +544,10 @@ __global__ void convert_weights_batched_kernel(ConvertJobs jobs) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const bf16 v = __float2bfloat16_rn(jb.w[idx]);
     jb.wb[idx] = v;
-    if (jb.wbt) jb.wbt[(long)(idx % jb.K) * jb.N + idx / jb.K] = v;
+    if (jb.wbt) jb.wbt[(long)(idx % jb.K) * (jb.ldt ? jb.ldt : jb.N) + idx / jb.K] = v;
   }
+  if (jb.bdst && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < jb.bn; i += blockDim.x) jb.bdst[i] = jb.bsrc[i];
 }
 int ew_grid(long n) { return (int)max(1L, min((long)qv_num_sms() * 8, (n / 2 + 255) / 256)); }
 }  // namespace
