@@ -431,6 +431,7 @@ int wgrad_t(cudaStream_t s, int K, const T* x, int ldx, const T* dy, int lddy, i
 int dw2d_fwd(cudaStream_t s, int dt, const DwP& p, bool flip) {
   if (p.B <= 0) return 0;
   QV_CHECK(p.C % 2 == 0 && p.ldx % 2 == 0, "dwconv: channel count / row pitch must be even");
+  if (dt == QV_BF16 && dwt_ok(p)) return dwt_fwd(s, p, flip);      // 8 x 8 maps: the stencil as a tensor-core product (dwconv_mma.cu)
   return dt == QV_BF16 ? fwd_t<bf16>(s, p, flip) : fwd_t<float>(s, p, flip);
 }
 int dw2d_wgrad(cudaStream_t s, int dt, int K, const void* x, int ldx, const void* dy, int lddy, int B, int H, int W, int C,

@@ -95,6 +95,9 @@ struct DwP {
   void* copy; int ldcp;
 };
 int dw2d_fwd(cudaStream_t s, int dt, const DwP& p, bool flip);
+// bf16, 8 x 8 maps, C % 16 == 0, no output scale: the same operation on mma.sync (dwconv_mma.cu); dw2d_fwd dispatches to it
+bool dwt_ok(const DwP& p);
+int dwt_fwd(cudaStream_t s, const DwP& p, bool flip);
 // optional scaled form y = scale * (conv(x) + bias): dw / dbias are scaled, dscale[c] += sum dy * (conv(x) + bias)
 struct DwScale { const float* w = nullptr; const float* bias = nullptr; const float* scale = nullptr; float* dscale = nullptr; };
 int dw2d_wgrad(cudaStream_t s, int dt, int K, const void* x, int ldx, const void* dy, int lddy, int B, int H, int W, int C,

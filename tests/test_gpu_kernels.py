@@ -182,3 +182,39 @@ def test_clip_and_adamw_match_torch():
         ropt.step()
         for n in shapes:
             assert (ours[n].data - ref[n].data).abs().max().item() < 2e-6, (n, step)
+
+
+@pytest.mark.parametrize("K", [3, 5, 7])
+@pytest.mark.parametrize("C,B", [(64, 37), (128, 16), (256, 5)])
+def test_depthwise_8x8_tensor_core_path_matches_conv2d(K, C, B):
+    """bf16 depthwise k x k convolution on 8 x 8 channels-last maps (dwconv_mma.cu: the stencil as a per-channel 64 x 64 Toeplitz
+    product on mma.sync) and its input gradient (flipped taps) against torch.nn.functional.conv2d in fp64 on the bf16-rounded
+    operands; B = 37 / 5 leave a partial 16-image tile."""
+    import torch.nn.functional as F
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(K * 100 + C)
+    x = torch.randn(B, 8, 8, C, device="cuda", generator=g).bfloat16()               # channels-last rows [B * 64, C]
+    w = torch.randn(C, K, K, device="cuda", generator=g) / K
+    bias = torch.randn(C, device="cuda", generator=g)
+    y = torch.zeros(B, 8, 8, C, device="cuda", dtype=torch.bfloat16)
+    L.check(L.lib.qavit_dwconv_forward(x.data_ptr(), 1, B, 8, 8, C, K, w.data_ptr(), bias.data_ptr(), y.data_ptr(), _s()))
+    wq = w.bfloat16().double()                                                       # the kernel rounds its taps to bf16
+    xr = x.double().permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, wq.view(C, 1, K, K), bias.double(), padding=K // 2, groups=C).permute(0, 2, 3, 1)
+    err = (y.double() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err                        # bf16 output rounding
+    # backward: dx = conv(dy, flipped taps); dw / dbias from the CUDA-core kernel
+    dy = torch.randn(B, 8, 8, C, device="cuda", generator=g).bfloat16()
+    dx = torch.zeros_like(dy)
+    dw = torch.zeros(C, K, K, device="cuda")
+    db = torch.zeros(C, device="cuda")
+    L.check(L.lib.qavit_dwconv_backward(x.data_ptr(), dy.data_ptr(), 1, B, 8, 8, C, K, w.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                        db.data_ptr(), _s()))
+    torch.cuda.synchronize()
+    xg = xr.clone().requires_grad_(True)
+    wg = wq.clone().view(C, 1, K, K).requires_grad_(True)
+    out = F.conv2d(xg, wg, None, padding=K // 2, groups=C)
+    out.backward(dy.double().permute(0, 3, 1, 2))
+    rdx = xg.grad.permute(0, 2, 3, 1)
+    assert (dx.double() - rdx).abs().max().item() < 2e-2 * max(1.0, rdx.abs().max().item())
+    assert (dw.double() - wg.grad.view(C, K, K)).abs().max().item() < 2e-2 * max(1.0, wg.grad.abs().max().item())
