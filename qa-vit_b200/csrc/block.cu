@@ -108,6 +108,7 @@ struct Dims {
   bool tl, v1;
   bool ftok, fup;   // TokenLearner / TokenUpMix run as the fused split-precision kernels of tokens_fused.cu
   bool fcmp;        // branch LayerNorm + compress + fusion scale of all 4 branches as one kernel per direction (cmp_fused.cu)
+  bool fmid;        // CCF-FFN GELU -> LayerNorm -> depthwise 3x3 -> LayerNorm as one kernel per direction (ffn_mid.cu)
   bool xstk;        // the three projections that read norm1's output -- swa.qkv (3d), msda.qkv's q rows (d), cross_attn.q_proj (d) -- run
                     // as ONE [R, d] x [5d, d]^T GEMM into one [R, 5d] buffer (consumers index it with a row pitch of 5d); backward: one
                     // dX GEMM over K = 5d and one dW GEMM whose rows scatter to the three parameters' gradients (tc_gemm_tn_seg)
@@ -165,6 +166,7 @@ int make_dims(const qavit_block_cfg& c, Dims* D) {
   D->ftok = D->tl && c.dtype == QV_BF16 && tokens_fused_ok(c.tokens, c.tokens_full, c.dim);
   D->fup = D->tl && c.dtype == QV_BF16 && tokens_fused_ok(c.tokens, D->No, c.dim);
   D->fcmp = c.dtype == QV_BF16 && cmp_fused_ok(c.dim, c.compress_dim);
+  D->fmid = c.dtype == QV_BF16 && !c.ffn_v1 && ffn_mid_ok(side, c.ffn_hidden) && getenv("QV_NO_FMID") == nullptr;
   D->tdt = (c.dtype == QV_BF16 && D->tl && !D->ftok && !tokens_mma_ok(c.tokens, c.tokens_full, c.dim) &&
             !tokens_mma64_ok(c.tokens, c.tokens_full, c.dim)) ? QV_F32 : c.dtype;
   D->tts = D->tdt == QV_BF16 ? 2 : 4;
@@ -232,8 +234,8 @@ void layout_saved(const Dims& D, Saved* S) {
   S->h_pre = b.take(R * D.fh * ts);
   S->h = b.take(D.v1 ? R * D.fh * ts : 0);
   S->dn_stats = b.take(R * 8);
-  S->hn = b.take(R * D.fh * ts);
-  S->cs = b.take(R * D.fh * ts);
+  S->hn = b.take(D.fmid ? 0 : R * D.fh * ts);       // the fused mid-section recomputes both in backward
+  S->cs = b.take(D.fmid ? 0 : R * D.fh * ts);
   S->pd_stats = b.take(R * 8);
   S->hn2 = b.take(R * D.fh * ts);
   S->o = b.take(R * d * ts);
@@ -274,8 +276,8 @@ void layout_scratch(const Dims& D, Scratch* S) {
     S->d_blk = b.take(D.tl ? R * d * 4 : 0);
     S->d_o = b.take(R * d * ts);
     S->d_hn2 = b.take(R * D.fh * ts);
-    S->d_cs = b.take(R * D.fh * ts);
-    S->d_hn = b.take(R * D.fh * ts);
+    S->d_cs = b.take(D.fmid ? 0 : R * D.fh * ts);
+    S->d_hn = b.take(D.fmid ? 0 : R * D.fh * ts);
     S->d_hpre = b.take(R * D.fh * ts);
     S->d_y = b.take(R * d * ts);
     S->d_x1 = b.take(R * d * 4);
@@ -389,10 +391,8 @@ int bank_write(const Ctx& c, const qavit_block_cfg& cfg, const void* branch_out,
 }
 
 int snapshot_bank(const Ctx& c, int i) {
-  const size_t n = (size_t)c.D.kb * c.D.d * 4;
-  QV_CUDA(cudaMemcpyAsync(c.sv(c.S.snap[i]), c.pf(QP_BANK_K), n, cudaMemcpyDeviceToDevice, c.st));
-  QV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(c.sv(c.S.snap[i])) + n, c.pf(QP_BANK_V), n, cudaMemcpyDeviceToDevice, c.st));
-  return 0;
+  const int n = c.D.kb * c.D.d;
+  return copy2_f32(c.st, c.svf(c.S.snap[i]), c.pf(QP_BANK_K), n, c.svf(c.S.snap[i]) + n, c.pf(QP_BANK_V), n);
 }
 const float* snap_k(const Ctx& c, int i) { return c.svf(c.S.snap[i]); }
 const float* snap_v(const Ctx& c, int i) { return c.svf(c.S.snap[i]) + (size_t)c.D.kb * c.D.d; }
@@ -491,8 +491,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
       QV_CUDA(cudaMemcpyAsync(c.sv(S.wstack), c.pf(QP_BANK_WC_W), (size_t)d * d * 4, cudaMemcpyDeviceToDevice, st));
       QV_CUDA(cudaMemcpyAsync(c.svf(S.wstack) + (size_t)d * d, c.pf(QP_BANK_WG_W), (size_t)D.kb * d * 4, cudaMemcpyDeviceToDevice, st));
     }
-    QV_CUDA(cudaMemcpyAsync(c.sv(S.bstack), c.pf(QP_BANK_WC_B), (size_t)d * 4, cudaMemcpyDeviceToDevice, st));
-    QV_CUDA(cudaMemcpyAsync(c.svf(S.bstack) + d, c.pf(QP_BANK_WG_B), (size_t)D.kb * 4, cudaMemcpyDeviceToDevice, st));
+    QV_TRY(copy2_f32(st, c.svf(S.bstack), c.pf(QP_BANK_WC_B), d, c.svf(S.bstack) + d, c.pf(QP_BANK_WG_B), D.kb));
   }
   if (dt == QV_BF16) {
     ConvertJobs jobs{};
@@ -671,12 +670,18 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   QV_TRY(ln_fwd(st, QV_F32, c.sv(S.x1), d, R, d, c.pf(QP_NORM2_W), c.pf(QP_NORM2_B), 1e-5f, 0, nullptr, nullptr, dt, c.sv(S.y), d, c.svf(S.n2_stats)));
   if (!D.v1) {
     QV_TRY(gemm_nt(st, dt, c.sv(S.y), d, R, c.W(W_F1, c.pf(QP_FFN_FC1_W)), epi_t(c, c.pf(QP_FFN_FC1_B), c.sv(S.h_pre), D.fh)));
-    QV_TRY(ln_fwd(st, dt, c.sv(S.h_pre), D.fh, R, D.fh, c.pf(QP_FFN_DWN_W), c.pf(QP_FFN_DWN_B), 1e-5f, 1, nullptr, nullptr, dt,
-                  c.sv(S.hn), D.fh, c.svf(S.dn_stats)));
-    QV_TRY(dwconv_fwd(st, dt, c.sv(S.hn), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W), cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr,
-                      c.pf(QP_FFN_SCALE), c.sv(S.cs)));
-    QV_TRY(ln_fwd(st, dt, c.sv(S.cs), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.pf(QP_FFN_PDN_B), 1e-5f, 0, nullptr, nullptr, dt,
-                  c.sv(S.hn2), D.fh, c.svf(S.pd_stats)));
+    if (D.fmid) {
+      QV_TRY(ffn_mid_fwd(st, c.sv(S.h_pre), D.B, D.fh, c.pf(QP_FFN_DWN_W), c.pf(QP_FFN_DWN_B), c.pf(QP_FFN_DW_W),
+                         cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, c.pf(QP_FFN_SCALE), c.pf(QP_FFN_PDN_W), c.pf(QP_FFN_PDN_B), 1e-5f,
+                         c.sv(S.hn2), c.svf(S.dn_stats), c.svf(S.pd_stats)));
+    } else {
+      QV_TRY(ln_fwd(st, dt, c.sv(S.h_pre), D.fh, R, D.fh, c.pf(QP_FFN_DWN_W), c.pf(QP_FFN_DWN_B), 1e-5f, 1, nullptr, nullptr, dt,
+                    c.sv(S.hn), D.fh, c.svf(S.dn_stats)));
+      QV_TRY(dwconv_fwd(st, dt, c.sv(S.hn), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W), cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr,
+                        c.pf(QP_FFN_SCALE), c.sv(S.cs)));
+      QV_TRY(ln_fwd(st, dt, c.sv(S.cs), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.pf(QP_FFN_PDN_B), 1e-5f, 0, nullptr, nullptr, dt,
+                    c.sv(S.hn2), D.fh, c.svf(S.pd_stats)));
+    }
     GemmEpi e = epi_t(c, c.pf(QP_FFN_FC2_B), c.sv(S.o), d);
     const Weight wf2 = c.W(W_F2, c.pf(QP_FFN_FC2_W));
     const bool ff = (dc.drop || dc.path) && fused_nt(c, wf2, R, D.fh);
@@ -765,13 +770,20 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
     }
     QV_TRY(gemm_tn(st, dt, c.sc(X.d_o), d, c.sv(S.hn2), D.fh, R, d, D.fh, G(QP_FFN_FC2_W), G(QP_FFN_FC2_B), nullptr));
     QV_TRY(gemm_nn(st, dt, c.sc(X.d_o), d, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, nullptr, c.sc(X.d_hn2), D.fh)));
-    QV_TRY(ln_bwd(st, dt, c.sv(S.cs), D.fh, dt, c.sc(X.d_hn2), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.svf(S.pd_stats), 0, dt,
-                  c.sc(X.d_cs), nullptr, nullptr, G(QP_FFN_PDN_W), G(QP_FFN_PDN_B)));
-    QV_TRY(dwconv_bwd(st, dt, c.sv(S.hn), c.sc(X.d_cs), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W),
-                      cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, c.pf(QP_FFN_SCALE), c.sc(X.d_hn), G(QP_FFN_DW_W),
-                      cfg->dwconv_bias ? G(QP_FFN_DW_B) : nullptr, G(QP_FFN_SCALE)));
-    QV_TRY(ln_bwd(st, dt, c.sv(S.h_pre), D.fh, dt, c.sc(X.d_hn), D.fh, R, D.fh, c.pf(QP_FFN_DWN_W), c.svf(S.dn_stats), 1, dt,
-                  c.sc(X.d_hpre), nullptr, nullptr, G(QP_FFN_DWN_W), G(QP_FFN_DWN_B)));
+    if (D.fmid) {
+      QV_TRY(ffn_mid_bwd(st, c.sv(S.h_pre), c.sc(X.d_hn2), c.svf(S.dn_stats), c.svf(S.pd_stats), D.B, D.fh, c.pf(QP_FFN_DWN_W),
+                         c.pf(QP_FFN_DWN_B), c.pf(QP_FFN_DW_W), cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, c.pf(QP_FFN_SCALE),
+                         c.pf(QP_FFN_PDN_W), c.sc(X.d_hpre), G(QP_FFN_DWN_W), G(QP_FFN_DWN_B), G(QP_FFN_DW_W),
+                         cfg->dwconv_bias ? G(QP_FFN_DW_B) : nullptr, G(QP_FFN_SCALE), G(QP_FFN_PDN_W), G(QP_FFN_PDN_B)));
+    } else {
+      QV_TRY(ln_bwd(st, dt, c.sv(S.cs), D.fh, dt, c.sc(X.d_hn2), D.fh, R, D.fh, c.pf(QP_FFN_PDN_W), c.svf(S.pd_stats), 0, dt,
+                    c.sc(X.d_cs), nullptr, nullptr, G(QP_FFN_PDN_W), G(QP_FFN_PDN_B)));
+      QV_TRY(dwconv_bwd(st, dt, c.sv(S.hn), c.sc(X.d_cs), D.B, D.side, D.fh, c.pf(QP_FFN_DW_W),
+                        cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, c.pf(QP_FFN_SCALE), c.sc(X.d_hn), G(QP_FFN_DW_W),
+                        cfg->dwconv_bias ? G(QP_FFN_DW_B) : nullptr, G(QP_FFN_SCALE)));
+      QV_TRY(ln_bwd(st, dt, c.sv(S.h_pre), D.fh, dt, c.sc(X.d_hn), D.fh, R, D.fh, c.pf(QP_FFN_DWN_W), c.svf(S.dn_stats), 1, dt,
+                    c.sc(X.d_hpre), nullptr, nullptr, G(QP_FFN_DWN_W), G(QP_FFN_DWN_B)));
+    }
   } else {
     if (dc.drop || dc.path) {
       const DropP site = dc.site(DS_FFN);
@@ -1064,6 +1076,16 @@ extern "C" int qavit_test_tokens_fused(int op, int B, int N, int C, const float*
 // The fused branch-LayerNorm + compress kernels (cmp_fused.cu; d = 192, compress_dim = 48) on their own.  op 0 = forward, 1 = backward.
 //   0: in  {x0..x3 (bf16 [R, 192]), gamma0..3, beta0..3, W0..3 ([48, 192]), b0..3, alpha[4]}   out {fused (bf16 [R, 192]), stats0..3 ([R, 2])}
 //   1: in  {x0..x3, stats0..3, gamma0..3, beta0..3, W0..3, alpha[4], dfused (bf16 [R, 192])}   out {dx0..3 (bf16), dW0..3, db0..3, dgamma0..3, dbeta0..3}
+// op 0: forward (in: h_pre, g1, b1, w, bias, scale, g2, b2; out: hn2, stats1, stats2); op 1: backward (in: + d_hn2, stats1, stats2;
+// out: d_hpre, dg1, db1, dw, dbias, dscale, dg2, db2)
+extern "C" int qavit_test_ffn_mid(int op, int B, int C, const void* const* in, void* const* out, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto f = [&](int i) { return static_cast<const float*>(in[i]); };
+  auto o = [&](int i) { return static_cast<float*>(out[i]); };
+  if (op == 0) return ffn_mid_fwd(s, in[0], B, C, f(1), f(2), f(3), f(4), f(5), f(6), f(7), 1e-5f, out[0], o(1), o(2));
+  return ffn_mid_bwd(s, in[0], in[8], f(9), f(10), B, C, f(1), f(2), f(3), f(4), f(5), f(6), out[0], o(1), o(2), o(3), o(4), o(5), o(6), o(7));
+}
+
 extern "C" int qavit_test_cmp_fused(int op, long long R, const void* const* in, void* const* out, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   QV_CHECK(in && out, "cmp_fused: null argument");

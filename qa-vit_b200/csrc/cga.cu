@@ -331,6 +331,8 @@ struct SmallLin2 { SmallLin p[2]; };
 
 // One warp per output column n for every row (W[n, :] is read once): lanes stride over K (coalesced), shuffle reduction.
 // blockIdx.y selects the problem: the K and V projections of a bank snapshot go out as ONE launch.
+// These kernels move a few hundred KB: what they cost is dependent memory latencies, so every loop is shaped to have all the
+// loads of a pass in flight at once (the rolled loops spent one L2 round trip per iteration: 16 / 41 us per launch).
 __global__ void __launch_bounds__(128) small_linear_fwd_kernel(SmallLin2 pp, int rows, int K, int N) {
   QV_PDL_ENTRY();
   const SmallLin& q = pp.p[blockIdx.y];
@@ -343,11 +345,19 @@ __global__ void __launch_bounds__(128) small_linear_fwd_kernel(SmallLin2 pp, int
     float a[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float w = W[n * K + k];
+    for (int k0 = 0; k0 < K; k0 += 128) {       // 4 k per lane and pass: 4 + 64 independent loads
+      float w[4], x[4][16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (r0 + i < rows) a[i] = fmaf(X[(r0 + i) * K + k], w, a[i]);
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + j * 32 + lane;
+        w[j] = k < K ? W[n * K + k] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[j][i] = (k < K && r0 + i < rows) ? X[(r0 + i) * K + k] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fmaf(x[j][i], w[j], a[i]);
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -356,37 +366,51 @@ __global__ void __launch_bounds__(128) small_linear_fwd_kernel(SmallLin2 pp, int
     }
   }
 }
-// dW[n,k] += sum_r dY[r,n] X[r,k]; db[n] += sum_r dY[r,n]; dX[r,k] += sum_n dY[r,n] W[n,k]
+// dW[n,k] += sum_r dY[r,n] X[r,k]; db[n] += sum_r dY[r,n]; dX[r,k] += sum_n dY[r,n] W[n,k].
+// blockIdx.z = a slice of 32 output columns n for the dX sum (atomic accumulation); slice 0 also does dW and db.
 __global__ void __launch_bounds__(128) small_linear_bwd_kernel(SmallLin2 pp, int rows, int K, int N) {
   QV_PDL_ENTRY();
   const SmallLin& q = pp.p[blockIdx.y];
-  const float* X = q.X;
-  const float* W = q.W;
-  const float* dY = q.dY;
+  const float* __restrict__ X = q.X;
+  const float* __restrict__ W = q.W;
+  const float* __restrict__ dY = q.dY;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < N * K) {
-    const int n = idx / K, k = idx % K;
-    float a = 0.f;
-    for (int r = 0; r < rows; ++r) a = fmaf(dY[r * N + n], X[r * K + k], a);
-    q.dW[idx] += a;
-  }
-  if (idx < N) {
-    float a = 0.f;
-    for (int r = 0; r < rows; ++r) a += dY[r * N + idx];
-    q.db[idx] += a;
+  if (blockIdx.z == 0) {
+    if (idx < N * K) {
+      const int n = idx / K, k = idx % K;
+      float a = 0.f;
+      for (int r0 = 0; r0 < rows; r0 += 16) {
+        float dy[16], x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const bool ok = r0 + i < rows;
+          dy[i] = ok ? dY[(r0 + i) * N + n] : 0.f;
+          x[i] = ok ? X[(r0 + i) * K + k] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a = fmaf(dy[i], x[i], a);
+      }
+      q.dW[idx] += a;
+    }
+    if (idx < N) {
+      float a = 0.f;
+      for (int r = 0; r < rows; ++r) a += dY[r * N + idx];
+      q.db[idx] += a;
+    }
   }
   if (idx < rows * K) {
-    const int r = idx / K, k = idx % K;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                    // four chains: the N-long dependent FMA chain was the kernel
-    int n = 0;
-    for (; n + 4 <= N; n += 4) {
-      a0 = fmaf(dY[r * N + n], W[n * K + k], a0);                    // lanes = consecutive k: coalesced
-      a1 = fmaf(dY[r * N + n + 1], W[(n + 1) * K + k], a1);
-      a2 = fmaf(dY[r * N + n + 2], W[(n + 2) * K + k], a2);
-      a3 = fmaf(dY[r * N + n + 3], W[(n + 3) * K + k], a3);
+    const int r = idx / K, k = idx % K, n0 = blockIdx.z * 32;
+    float dy[32], w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const bool ok = n0 + i < N;
+      dy[i] = ok ? dY[r * N + n0 + i] : 0.f;
+      w[i] = ok ? W[(n0 + i) * K + k] : 0.f;                          // lanes = consecutive k: coalesced
     }
-    for (; n < N; ++n) a0 = fmaf(dY[r * N + n], W[n * K + k], a0);
-    q.dX[idx] += (a0 + a1) + (a2 + a3);
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i & 3] = fmaf(dy[i], w[i], a[i & 3]);
+    atomicAdd(q.dX + idx, (a[0] + a[1]) + (a[2] + a[3]));
   }
 }
 }  // namespace
@@ -411,7 +435,7 @@ int small_linear_bwd2(cudaStream_t s, int rows, int K, int N, const float* X0, c
   pp.p[0].X = X0; pp.p[0].W = W0; pp.p[0].dY = dY0; pp.p[0].dW = dW0; pp.p[0].db = db0; pp.p[0].dX = dX0;
   pp.p[1].X = X1; pp.p[1].W = W1; pp.p[1].dY = dY1; pp.p[1].dW = dW1; pp.p[1].db = db1; pp.p[1].dX = dX1;
   const int n = max(N * K, rows * K);
-  qv_launch(small_linear_bwd_kernel, dim3(cdiv(n, 128), X1 ? 2 : 1), 128, 0, s, pp, rows, K, N);
+  qv_launch(small_linear_bwd_kernel, dim3(cdiv(n, 128), X1 ? 2 : 1, cdiv(N, 32)), 128, 0, s, pp, rows, K, N);
   QV_LAUNCH_CHECK();
   return 0;
 }

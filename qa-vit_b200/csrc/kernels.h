@@ -104,7 +104,7 @@ int dw2d_wgrad(cudaStream_t s, int dt, int K, const void* x, int ldx, const void
                float* dw, float* dbias, const DwScale& sc = DwScale());
 
 // ---- lateral path / SplitFusion kernels (lateral_kernels.cu)
-// BatchNorm over rows of [rows, C] (+ GELU): mr[2C] = per-channel mean | rstd (kept for backward), sums_scratch[2C].
+// BatchNorm over rows of [rows, C] (+ GELU): mr[2C] = per-channel mean | rstd (kept for backward), sums_scratch[4C] (2C 64-bit fixed-point sums in forward).
 int bn_fwd(cudaStream_t s, int dt, const void* x, long rows, int C, const float* gamma, const float* beta, float eps,
            float momentum, int train, float* running_mean, float* running_var, long long* num_batches, int gelu,
            float* sums_scratch, float* mr, void* y);
@@ -260,6 +260,7 @@ int gelu_bwd(cudaStream_t s, int dt, const void* pre, const void* dact, long n, 
 int gamma_bwd(cudaStream_t s, int dt, const float* dout, const void* o, long n, const float* gamma, void* d_o,
               float* dgamma, const DropP* drop = nullptr, const float* rowscale = nullptr, int rows_per_img = 1, int C = 0);
 int cast_f32_to_t(cudaStream_t s, int dt, const float* x, long n, void* y);
+int copy2_f32(cudaStream_t s, float* d0, const float* s0, int n0, float* d1, const float* s1, int n1);   // two small copies, one launch
 int fusion_softmax(cudaStream_t s, const float* w, int n, float* alpha);
 int fusion_bwd(cudaStream_t s, int dt, const void* dfused, const void* fused, long rows, int nb, int cw,
                const float* alpha, float* dalpha_raw);
@@ -296,6 +297,14 @@ int upf_fwd(cudaStream_t s, const float* xc, int B, int N, const float* W, const
             float eps, float* out, float* stats);
 int upf_bwd(cudaStream_t s, const float* xc, const float* dout, const float* stats, int B, int N, const float* W, const float* bias,
             const float* gamma, float* dxc, float* dW, float* dgamma, float* dbeta);
+// CCF-FFN mid-section GELU -> LayerNorm -> depthwise 3x3 (* scale) -> LayerNorm as one kernel per direction (ffn_mid.cu): bf16 runs,
+// 4 x 4 token maps, C a multiple of 32 up to 128.  stats1 / stats2: (mean, rstd) per row of the two LayerNorms.
+bool ffn_mid_ok(int side, int C);
+int ffn_mid_fwd(cudaStream_t s, const void* h_pre, int B, int C, const float* g1, const float* b1, const float* w, const float* bias,
+                const float* scale, const float* g2, const float* b2, float eps, void* hn2, float* stats1, float* stats2);
+int ffn_mid_bwd(cudaStream_t s, const void* h_pre, const void* d_hn2, const float* stats1, const float* stats2, int B, int C,
+                const float* g1, const float* b1, const float* w, const float* bias, const float* scale, const float* g2, void* d_hpre,
+                float* dg1, float* db1, float* dw, float* dbias, float* dscale, float* dg2, float* db2);
 // per-branch LayerNorm + compress Linear + fusion scale + concat for all 4 branches in one launch, and its backward (cmp_fused.cu);
 // bf16 runs with d = 192, compress_dim = 48.  x[i]: branch outputs [R, 192] bf16; stats[i]: (mean, rstd) per row (written by fwd)
 bool cmp_fused_ok(int d, int cd);

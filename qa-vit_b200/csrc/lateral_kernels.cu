@@ -35,12 +35,18 @@ __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f
 // ------------------------------------------------------------------------------------------------ BatchNorm
 // sums[0..C) += sum_rows (x - shift), sums[C..2C) += sum_rows (x - shift)^2, shift = x[0, c]  (guards the variance
 // against cancellation when |mean| >> std).  Thread = 8 channels x a strided set of rows.
+// The per-thread fp32 partials are accumulated as 64-bit FIXED-POINT integers (quantum 2^-24): integer addition is associative, so
+// the batch statistics -- and with them the whole forward pass -- are bit-identical from run to run whatever order the atomics land
+// in (fp32 atomics here made HQAViT's bf16 logits differ by 3e-3 between identical runs: the TokenLearner gate amplifies ulps).
+constexpr float BN_FIX = 16777216.f;   // 2^24
+__device__ __forceinline__ unsigned long long bn_to_fix(float v) { return (unsigned long long)__float2ll_rn(v * BN_FIX); }
+__device__ __forceinline__ float bn_from_fix(unsigned long long v) { return (float)((double)(long long)v * (1.0 / 16777216.0)); }
 template <typename T>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long rows, int C, float* __restrict__ sums) {
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long rows, int C, unsigned long long* __restrict__ sums) {
   QV_PDL_ENTRY();
-  extern __shared__ float red[];   // [2C]
+  extern __shared__ unsigned long long red_fix[];   // [2C]
   const int lpr = C / 8, cv = (threadIdx.x % lpr) * 8, r0 = threadIdx.x / lpr, rpp = 256 / lpr;
-  for (int i = threadIdx.x; i < 2 * C; i += 256) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) red_fix[i] = 0ull;
   float sh[8], s[8], q[8];
   Vec8<T>::ld(x + cv, sh);
 #pragma unroll
@@ -53,9 +59,9 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { atomicAdd(red + cv + i, s[i]); atomicAdd(red + C + cv + i, q[i]); }
+  for (int i = 0; i < 8; ++i) { atomicAdd(red_fix + cv + i, bn_to_fix(s[i])); atomicAdd(red_fix + C + cv + i, bn_to_fix(q[i])); }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(sums + i, red[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(sums + i, red_fix[i]);
 }
 
 // mr[0..C) = mean, mr[C..2C) = rstd; train: from the batch sums (+ running-stat update, H: nn.BatchNorm2d momentum 0.1,
@@ -68,10 +74,11 @@ __global__ void bn_finalize_kernel(const T* __restrict__ x, const float* __restr
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (train) {
+    const unsigned long long* fix = reinterpret_cast<const unsigned long long*>(sums);   // written by bn_stats_kernel
     const float n = (float)rows;
-    const float d = sums[c] / n;
+    const float d = bn_from_fix(fix[c]) / n;
     const float mean = ldf(x + c) + d;
-    const float var = fmaxf(sums[C + c] / n - d * d, 0.f);
+    const float var = fmaxf(bn_from_fix(fix[C + c]) / n - d * d, 0.f);
     mr[c] = mean;
     mr[C + c] = rsqrtf(var + eps);
     if (running_mean) {
@@ -735,13 +742,14 @@ int bn_fwd(cudaStream_t s, int dt, const void* x, long rows, int C, const float*
            float momentum, int train, float* running_mean, float* running_var, long long* num_batches, int gelu,
            float* sums_scratch, float* mr, void* y) {
   if (rows <= 0) return 0;
-  QV_CHECK(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "batch_norm: C=%d unsupported (multiple of 8, C/8 divides 256)", C);
+  QV_CHECK(C % 8 == 0 && C <= 1024 && 256 % (C / 8) == 0, "batch_norm: C=%d unsupported (multiple of 8, C/8 divides 256)", C);
   if (train) {
-    QV_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * C * sizeof(float), s));
+    unsigned long long* fix = reinterpret_cast<unsigned long long*>(sums_scratch);   // 2C 64-bit sums in the 4096-float scratch
+    QV_CUDA(cudaMemsetAsync(fix, 0, 2 * C * sizeof(unsigned long long), s));
     const int rpp = 256 / (C / 8);
     const int grid = (int)max(1L, min((rows + rpp - 1) / rpp, (long)qv_num_sms() * 4));
-    DT_SWITCH(dt, (qv_launch(bn_stats_kernel<float>, grid, 256, 2 * C * sizeof(float), s, (const float*)x, rows, C, sums_scratch)),
-              (qv_launch(bn_stats_kernel<bf16>, grid, 256, 2 * C * sizeof(float), s, (const bf16*)x, rows, C, sums_scratch)));
+    DT_SWITCH(dt, (qv_launch(bn_stats_kernel<float>, grid, 256, 2 * C * sizeof(unsigned long long), s, (const float*)x, rows, C, fix)),
+              (qv_launch(bn_stats_kernel<bf16>, grid, 256, 2 * C * sizeof(unsigned long long), s, (const bf16*)x, rows, C, fix)));
     QV_LAUNCH_CHECK();
   } else {
     QV_CHECK(running_mean && running_var, "batch_norm: eval mode needs running statistics");

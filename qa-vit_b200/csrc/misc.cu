@@ -573,6 +573,24 @@ int gamma_bwd(cudaStream_t s, int dt, const float* dout, const void* o, long n, 
   QV_LAUNCH_CHECK();
   return 0;
 }
+// two small fp32 copies as one launch (bank snapshots, stacked biases: a memcpy node each was 2 graph nodes per site, 80 per step)
+namespace {
+__global__ void copy2_f32_kernel(float* __restrict__ d0, const float* __restrict__ s0, int n0, float* __restrict__ d1,
+                                 const float* __restrict__ s1, int n1) {
+  QV_PDL_ENTRY();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += gridDim.x * blockDim.x) {
+    if (i < n0) d0[i] = s0[i];
+    else d1[i - n0] = s1[i - n0];
+  }
+}
+}  // namespace
+int copy2_f32(cudaStream_t s, float* d0, const float* s0, int n0, float* d1, const float* s1, int n1) {
+  if (n0 + n1 <= 0) return 0;
+  qv_launch(copy2_f32_kernel, min(64, (n0 + n1 + 255) / 256), 256, 0, s, d0, s0, n0, d1, s1, n1);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
 int cast_f32_to_t(cudaStream_t s, int dt, const float* x, long n, void* y) {
   if (n <= 0) return 0;
   DISPATCH_T(dt, (qv_launch(cast_kernel<T>, ew_grid(n), 256, 0, s, x, n, (T*)y)));

@@ -134,6 +134,11 @@ def test_against_live_reference_on_gpu(case):
     r16_logits, r16_loss, r16_g, _ = _run_ref(ref, x, y, autocast=True)
     o32_logits, o32_loss, o32_g, o32_m = _run_ours(Q, ctor, rcfg, state, x, y, "fp32", our_post)
     o16_logits, o16_loss, o16_g, o16_m = _run_ours(Q, ctor, rcfg, state, x, y, "bf16", our_post)
+    # HQAViT in bf16 at a batch of 4 is a sensitive measurement: the TokenLearner gate amplifies last-bit differences.  The forward
+    # pass is bit-reproducible (BatchNorm statistics are summed in fixed point, the bank write reduces in a fixed order: the three
+    # logits errors printed below are identical); fp32 atomics remain in backward (dW / dbias sums), which moves the gradient error by
+    # ~1 % between runs -- the gates look at the MEDIAN of three runs for that family.
+    extra16 = [_run_ours(Q, ctor, rcfg, state, x, y, "bf16", our_post) for _ in range(2)] if case.startswith("hqavit") else []
 
     for n, gr in r32_g.items():
         assert (o32_g[n] is None) == (gr is None), n
@@ -141,6 +146,11 @@ def test_against_live_reference_on_gpu(case):
 
     e32, g32 = rel_max(o32_logits, r32_logits), _grad_err(o32_g, r32_g)
     e16, g16 = rel_max(o16_logits, r32_logits), _grad_err(o16_g, r32_g)
+    if extra16:
+        es = sorted([e16] + [rel_max(r[0], r32_logits) for r in extra16])
+        gs = sorted([g16] + [_grad_err(r[2], r32_g) for r in extra16])
+        print(f"\nlive {case}: three bf16 runs: logits {es}, grads {gs}")
+        e16, g16 = es[1], gs[1]
     l16 = rel_l2(o16_logits, r32_logits)
     f16, fg16, fl16 = rel_max(r16_logits, r32_logits), _grad_err(r16_g, r32_g), rel_l2(r16_logits, r32_logits)
     print(f"\nlive {case}: fp32 ours-vs-ref logits {e32:.2e} grads {g32:.2e} | bf16 ours-vs-ref-fp32 logits {e16:.2e} (l2 {l16:.2e}) "
