@@ -315,7 +315,9 @@ __global__ void __launch_bounds__(WARPS * 32, ATTB_M) attn_mma_bwd_kernel(AttnP 
   bf16* Bk = Es + 2 * LP * PE + warp * 2 * MAT;
   bf16* Bv = Bk + MAT;
   bf16* stage = Es + 2 * LP * PE + WARPS * 2 * MAT + warp * 2 * NM * MAT;
-  const int D = p.H * HD, h = warp;
+  // backward: a CTA serves ONE head (its warps take different windows), so the batch-reduction tiles of its 4 warps are summed in
+  // shared memory before they go to global memory -- a quarter of the reductions of a warp-per-head mapping
+  const int D = p.H * HD, h = blockIdx.x % p.H;
   if (LINF) load_E(Es, p);
   load_bank(Bk, LINF ? p.bank_k : p.kc, D, h * HD, lane);
   load_bank(Bv, LINF ? p.bank_v : p.vc, D, h * HD, lane);
@@ -335,15 +337,15 @@ __global__ void __launch_bounds__(WARPS * 32, ATTB_M) attn_mma_bwd_kernel(AttnP 
   for (int n = 0; n < 4; ++n)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dEk[n][e] = dEv[n][e] = 0.f;
-  const int stride = gridDim.x * WARPS;
-  int task = blockIdx.x * WARPS + warp, cur = 0;
-  if (task < ntask) prefetch_task<LINF, true>(p, stage, task / p.H, h, lane);
-  for (; task < ntask; task += stride, cur ^= 1) {
-    const int w = task / p.H;
+  const int nwin = ntask / p.H, wstride = (gridDim.x / p.H) * WARPS;      // the grid is a multiple of H (launch_bwd)
+  int w = (blockIdx.x / p.H) * WARPS + warp, cur = 0;
+  if (w < nwin) prefetch_task<LINF, true>(p, stage, w, h, lane);
+  for (; w < nwin; w += wstride, cur ^= 1) {
+    const int task = w * p.H + h;                                          // the forward kernel's task id (dropout element ids)
     bf16* buf = stage + cur * NM * MAT;
     const bf16 *Qs = buf, *Ks = buf + MAT, *Vs = buf + 2 * MAT, *DOs = buf + 3 * MAT;
-    if (task + stride < ntask) {
-      prefetch_task<LINF, true>(p, stage + (cur ^ 1) * NM * MAT, (task + stride) / p.H, h, lane);
+    if (w + wstride < nwin) {
+      prefetch_task<LINF, true>(p, stage + (cur ^ 1) * NM * MAT, w + wstride, h, lane);
       cp_wait<1>();
     } else {
       cp_wait<0>();
@@ -451,23 +453,45 @@ __global__ void __launch_bounds__(WARPS * 32, ATTB_M) attn_mma_bwd_kernel(AttnP 
     }
     __syncwarp();
   }
-  // ---- flush the per-warp register accumulators (one atomic per element per warp)
+  // ---- flush: the 4 warps' register tiles are summed in shared memory (the staging buffers are free now), then one 16 B vector
+  // reduction per 4 elements and CTA.  (Scalar atomics per warp were a third of the kernel: 444 x 4 warps x 2560 elements onto 7 k
+  // addresses; the cost follows the number of reduction operations, not bytes.)
+  __syncthreads();
+  float* acc = reinterpret_cast<float*>(Es + 2 * LP * PE + WARPS * 2 * MAT);   // [dbk 16x48 | dbv 16x48 | dEk 16x32 | dEv 16x32]
+  constexpr int NB = NQ * HD, NE = LINF ? LP * KLIN : 0, NACC = 2 * NB + 2 * NE;
+  for (int i = threadIdx.x; i < NACC; i += WARPS * 32) acc[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
-    float* k0 = p.dbank_k + g * D + h * HD + n * 8 + 2 * t;
-    float* v0 = p.dbank_v + g * D + h * HD + n * 8 + 2 * t;
-    atomicAdd(k0, dbk[n][0]); atomicAdd(k0 + 1, dbk[n][1]); atomicAdd(k0 + 8 * D, dbk[n][2]); atomicAdd(k0 + 8 * D + 1, dbk[n][3]);
-    atomicAdd(v0, dbv[n][0]); atomicAdd(v0 + 1, dbv[n][1]); atomicAdd(v0 + 8 * D, dbv[n][2]); atomicAdd(v0 + 8 * D + 1, dbv[n][3]);
+    float* k0 = acc + g * HD + n * 8 + 2 * t;
+    atomicAdd(k0, dbk[n][0]); atomicAdd(k0 + 1, dbk[n][1]); atomicAdd(k0 + 8 * HD, dbk[n][2]); atomicAdd(k0 + 8 * HD + 1, dbk[n][3]);
+    float* v0 = k0 + NB;
+    atomicAdd(v0, dbv[n][0]); atomicAdd(v0 + 1, dbv[n][1]); atomicAdd(v0 + 8 * HD, dbv[n][2]); atomicAdd(v0 + 8 * HD + 1, dbv[n][3]);
   }
   if (LINF) {
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      const int j = n * 8 + 2 * t;
-      if (g < p.L) { atomicAdd(p.dEk + g * KLIN + j, dEk[n][0]); atomicAdd(p.dEk + g * KLIN + j + 1, dEk[n][1]);
-                     atomicAdd(p.dEv + g * KLIN + j, dEv[n][0]); atomicAdd(p.dEv + g * KLIN + j + 1, dEv[n][1]); }
-      if (g + 8 < p.L) { atomicAdd(p.dEk + (g + 8) * KLIN + j, dEk[n][2]); atomicAdd(p.dEk + (g + 8) * KLIN + j + 1, dEk[n][3]);
-                         atomicAdd(p.dEv + (g + 8) * KLIN + j, dEv[n][2]); atomicAdd(p.dEv + (g + 8) * KLIN + j + 1, dEv[n][3]); }
+      float* k0 = acc + 2 * NB + g * KLIN + n * 8 + 2 * t;
+      atomicAdd(k0, dEk[n][0]); atomicAdd(k0 + 1, dEk[n][1]); atomicAdd(k0 + 8 * KLIN, dEk[n][2]); atomicAdd(k0 + 8 * KLIN + 1, dEk[n][3]);
+      float* v0 = k0 + NE;
+      atomicAdd(v0, dEv[n][0]); atomicAdd(v0 + 1, dEv[n][1]); atomicAdd(v0 + 8 * KLIN, dEv[n][2]); atomicAdd(v0 + 8 * KLIN + 1, dEv[n][3]);
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NACC / 4; i += WARPS * 32) {
+    const float4 v = reinterpret_cast<const float4*>(acc)[i];
+    const int e = i * 4;
+    float* dst;
+    if (e < 2 * NB) {
+      const int r = (e % NB) / HD, c = e % HD;
+      dst = (e < NB ? p.dbank_k : p.dbank_v) + r * D + h * HD + c;
+    } else {
+      constexpr int NE1 = NE ? NE : 1;                       // (no Linformer tiles: branch not reached)
+      const int f = e - 2 * NB, r = (f % NE1) / KLIN, c = f % KLIN;
+      if (r >= p.L) continue;
+      dst = (f < NE ? p.dEk : p.dEv) + r * KLIN + c;
+    }
+    red_add_v4(dst, v.x, v.y, v.z, v.w);
   }
 }
 
@@ -502,7 +526,23 @@ int attn_mma_fwd(cudaStream_t s, const AttnP& p) {
   if (p.mode == 2) return launch(attn_mma_fwd_kernel<false>, s, p, 1);
   return launch(attn_mma_fwd_kernel<true>, s, p, 3);
 }
+template <typename K>
+int launch_bwd(K kernel, cudaStream_t s, const AttnP& p) {   // as launch(), with the grid a multiple of H: a CTA serves one head
+  const int nwin = (p.mode == 0) ? p.B * (p.side / p.ws) * (p.side / p.ws) : p.B;
+  const int ntask = nwin * p.H;
+  if (ntask <= 0) return 0;
+  const size_t smem = (size_t)(2 * LP * PE + WARPS * 2 * MAT + WARPS * 2 * 4 * MAT) * sizeof(bf16);
+  if (smem > 48 * 1024) QV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_head = max(1, min(cdiv(nwin, WARPS), qv_num_sms() * 3 / p.H));
+  qv_launch(kernel, per_head * p.H, WARPS * 32, smem, s, p, ntask);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
 int attn_mma_bwd(cudaStream_t s, const AttnP& p) {
-  if (p.mode == 2) return launch(attn_mma_bwd_kernel<false>, s, p, 4);
-  return launch(attn_mma_bwd_kernel<true>, s, p, 4);
+  auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };   // the flush uses 16 B vector reductions
+  QV_CHECK(al16(p.dbank_k) && al16(p.dbank_v) && (p.mode == 2 || (al16(p.dEk) && al16(p.dEv))),
+           "attn_mma_bwd: bank / Linformer gradient buffers must be 16 B aligned");
+  if (p.mode == 2) return launch_bwd(attn_mma_bwd_kernel<false>, s, p);
+  return launch_bwd(attn_mma_bwd_kernel<true>, s, p);
 }

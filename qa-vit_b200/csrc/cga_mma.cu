@@ -403,10 +403,7 @@ __global__ void __launch_bounds__(WARPS_BWD * 32, 1) cga_mma_bwd_kernel(CgaP p) 
   for (int mt = 0; mt < 3; ++mt) {
     float* dst = mt == 0 ? p.dWq : (mt == 1 ? p.dWk : p.dWv);
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      atomicAdd(dst + g * CG + n * 8 + 2 * t, dWacc[mt][n][0]); atomicAdd(dst + g * CG + n * 8 + 2 * t + 1, dWacc[mt][n][1]);
-      atomicAdd(dst + (g + 8) * CG + n * 8 + 2 * t, dWacc[mt][n][2]); atomicAdd(dst + (g + 8) * CG + n * 8 + 2 * t + 1, dWacc[mt][n][3]);
-    }
+    for (int n = 0; n < 4; ++n) red_frag_v4(dst + g * CG + n * 8, dst + (g + 8) * CG + n * 8, dWacc[mt][n], t);
   }
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
@@ -443,7 +440,8 @@ int cga_mma_fwd(cudaStream_t s, const CgaP& p) {
 
 int cga_mma_bwd(cudaStream_t s, const CgaP& p) {
   if (p.B <= 0) return 0;
-  QV_CHECK(p.lddo % 8 == 0 && p.lddx % 2 == 0, "cga_mma_bwd: unaligned gradient buffers");
+  QV_CHECK(p.lddo % 8 == 0 && p.lddx % 2 == 0 && (((uintptr_t)p.dWq | (uintptr_t)p.dWk | (uintptr_t)p.dWv) & 15) == 0,
+           "cga_mma_bwd: unaligned gradient buffers (the dW flush uses 16 B vector reductions)");
   const size_t smem = (3 * CPG + 2 * KB * CPG) * 4 + (size_t)(3 * CPG * PW + 2 * KB * PK + WARPS_BWD * WS::END_BWD) * 2;
   QV_CUDA(cudaFuncSetAttribute(cga_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = min(cdiv(p.B, WARPS_BWD), qv_num_sms() * (WARPS_BWD >= 12 ? 1 : 2));

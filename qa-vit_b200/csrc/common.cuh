@@ -113,6 +113,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 16 B vector reduction into global memory (sm_90+): one L2 atomic operation for four floats
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// An mma.sync C fragment (this lane: row g cols 2t, 2t + 1 and row g + 8 cols 2t, 2t + 1 of an 8-column tile) added to global memory
+// with ONE vector reduction per lane instead of four scalar atomics: lanes t and t ^ 1 trade halves, so an even-t lane ends up with
+// row g, cols 2t .. 2t + 3 and an odd-t lane with row g + 8, cols 2t - 2 .. 2t + 1.  row_g / row_g8: the tile's row pointers (16 B
+// aligned, nullptr = row not stored).  The per-warp flushes of the attention backward kernels are millions of atomics per launch onto
+// a few thousand addresses; their cost scales with the number of operations, not bytes.
+__device__ __forceinline__ void red_frag_v4(float* row_g, float* row_g8, const float* c, int t) {
+  const bool odd = t & 1;
+  const float r0 = __shfl_xor_sync(0xffffffffu, odd ? c[0] : c[2], 1), r1 = __shfl_xor_sync(0xffffffffu, odd ? c[1] : c[3], 1);
+  if (!odd) { if (row_g) red_add_v4(row_g + 2 * t, c[0], c[1], r0, r1); }
+  else if (row_g8) red_add_v4(row_g8 + 2 * t - 2, r0, r1, c[2], c[3]);
+}
+
 // exact-erf GELU (nn.GELU() default) and its derivative
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {

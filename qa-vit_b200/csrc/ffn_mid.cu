@@ -76,6 +76,21 @@ __device__ __forceinline__ void totals(const float* red, float (&a)[MT], float (
   }
 }
 
+// LayerNorm statistics from the per-warp partial sums: lane l derives (mean, rstd) of token l & 15 once, 32 shuffles hand them to
+// every lane (each thread deriving all 16 pairs itself cost ~10 instructions per token, a fifth of the forward kernel)
+template <int NW>
+__device__ __forceinline__ void ln_stats(const float* red, int lane, float invC, float eps, float (&m)[MT], float (&r)[MT],
+                                         float& my_m, float& my_r) {
+  const int t = lane & (MT - 1);
+  float a = 0.f, q = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) { a += red[w * MT + t]; q += red[(NW + w) * MT + t]; }
+  my_m = a * invC;
+  my_r = rsqrtf(fmaxf(q * invC - my_m * my_m, 0.f) + eps);
+#pragma unroll
+  for (int i = 0; i < MT; ++i) { m[i] = __shfl_sync(0xffffffffu, my_m, i); r[i] = __shfl_sync(0xffffffffu, my_r, i); }
+}
+
 // y[p] = bias + sum_taps w[ky][kx] x[py + ky - 1][px + kx - 1] on the 4 x 4 map (cross-correlation, zero padding)
 __device__ __forceinline__ void conv3(const float (&x)[MT], const float (&w)[9], float bias, float (&y)[MT]) {
 #pragma unroll
@@ -127,20 +142,11 @@ __global__ void __launch_bounds__(32 * NW * IPC) ffn_mid_fwd_kernel(FfnMidP p) {
       const float ts = seg16(s, lane), tq = seg16(q, lane);
       if (!(lane & 1)) { red[0][img][wi * MT + (lane >> 1)] = ts; red[0][img][(NW + wi) * MT + (lane >> 1)] = tq; }
       img_sync(img, C);
-      totals<NW>(red[0][img], s, q);
-      if (act && c < MT) {
-        float a = 0.f, b2s = 0.f;
+      float mm, mr;
+      ln_stats<NW>(red[0][img], lane, invC, p.eps, s, q, mm, mr);      // s <- mean, q <- rstd
+      if (act && c < MT) *reinterpret_cast<float2*>(p.st1 + 2 * (b * MT + c)) = make_float2(mm, mr);
 #pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) { a += red[0][img][w2 * MT + c]; b2s += red[0][img][(NW + w2) * MT + c]; }
-        const float m = a * invC;
-        p.st1[2 * (b * MT + c)] = m;
-        p.st1[2 * (b * MT + c) + 1] = rsqrtf(fmaxf(b2s * invC - m * m, 0.f) + p.eps);
-      }
-#pragma unroll
-      for (int t = 0; t < MT; ++t) {
-        const float m = s[t] * invC, r = rsqrtf(fmaxf(q[t] * invC - m * m, 0.f) + p.eps);
-        x[t] = fmaf((x[t] - m) * r, g1, b1);
-      }
+      for (int t = 0; t < MT; ++t) x[t] = fmaf((x[t] - s[t]) * q[t], g1, b1);
     }
     conv3(x, w, bs, cs);
 #pragma unroll
@@ -152,22 +158,13 @@ __global__ void __launch_bounds__(32 * NW * IPC) ffn_mid_fwd_kernel(FfnMidP p) {
       const float ts = seg16(s, lane), tq = seg16(q, lane);
       if (!(lane & 1)) { red[1][img][wi * MT + (lane >> 1)] = ts; red[1][img][(NW + wi) * MT + (lane >> 1)] = tq; }
       img_sync(img, C);
-      totals<NW>(red[1][img], s, q);
-      if (act && c < MT) {
-        float a = 0.f, b2s = 0.f;
-#pragma unroll
-        for (int w2 = 0; w2 < NW; ++w2) { a += red[1][img][w2 * MT + c]; b2s += red[1][img][(NW + w2) * MT + c]; }
-        const float m = a * invC;
-        p.st2[2 * (b * MT + c)] = m;
-        p.st2[2 * (b * MT + c) + 1] = rsqrtf(fmaxf(b2s * invC - m * m, 0.f) + p.eps);
-      }
+      float mm, mr;
+      ln_stats<NW>(red[1][img], lane, invC, p.eps, s, q, mm, mr);
+      if (act && c < MT) *reinterpret_cast<float2*>(p.st2 + 2 * (b * MT + c)) = make_float2(mm, mr);
       if (act) {
         bf16* dst = p.hn2 + b * MT * C + c;
 #pragma unroll
-        for (int t = 0; t < MT; ++t) {
-          const float m = s[t] * invC, r = rsqrtf(fmaxf(q[t] * invC - m * m, 0.f) + p.eps);
-          dst[t * C] = __float2bfloat16_rn(fmaf((cs[t] - m) * r, g2, b2));
-        }
+        for (int t = 0; t < MT; ++t) dst[t * C] = __float2bfloat16_rn(fmaf((cs[t] - s[t]) * q[t], g2, b2));
       }
     }
   }
@@ -312,12 +309,22 @@ __global__ void __launch_bounds__(32 * NW * IPC) ffn_mid_bwd_kernel(FfnMidP p) {
       }
     }
   }
-  atomicAdd(p.dg1 + c, a_g1); atomicAdd(p.db1 + c, a_b1);
-  atomicAdd(p.dg2 + c, a_g2); atomicAdd(p.db2 + c, a_b2);
+  // the CTA's images are summed in shared memory first: one atomic per CTA and value (the per-thread flush was 852 k atomics onto
+  // 1440 addresses at B = 4736 -- a third of the kernel by ncu's stall samples, all of it in the exit drain)
+  __shared__ float accs[IPC][15][C];
+  accs[img][0][c] = a_g1; accs[img][1][c] = a_b1; accs[img][2][c] = a_g2; accs[img][3][c] = a_b2; accs[img][4][c] = a_bs; accs[img][5][c] = a_sc;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) atomicAdd(p.dw + c * 9 + k, aw[k]);
-  if (p.dbias) atomicAdd(p.dbias + c, a_bs);
-  if (p.dscale) atomicAdd(p.dscale + c, a_sc);
+  for (int k = 0; k < 9; ++k) accs[img][6 + k][c] = aw[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 15 * C; i += 32 * NW * IPC) {
+    const int k = i / C, cc = i % C;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < IPC; ++j) v += accs[j][k][cc];
+    float* dst = k == 0 ? p.dg1 + cc : k == 1 ? p.db1 + cc : k == 2 ? p.dg2 + cc : k == 3 ? p.db2 + cc
+               : k == 4 ? (p.dbias ? p.dbias + cc : nullptr) : k == 5 ? (p.dscale ? p.dscale + cc : nullptr) : p.dw + cc * 9 + (k - 6);
+    if (dst) atomicAdd(dst, v);
+  }
 }
 
 template <typename K>

@@ -51,3 +51,22 @@ tot = sum(v[1] for v in agg.values())
 print(f"2 steps: wall {t1 - t0:.0f} us, sum of kernel durations {tot:.0f} us over {sum(v[0] for v in agg.values())} records")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
     print(f"{t / 2:10.1f} us {100 * t / tot:5.1f}%  n={n // 2:4d} avg={t / n:8.1f}  {k}")
+
+# per-stream occupancy and the largest idle gaps of the busiest stream (what the critical path waits for)
+by_stream = collections.defaultdict(list)
+for e in evs:
+    by_stream[e.device_resource_id if hasattr(e, "device_resource_id") else getattr(e, "stream", 0)].append(e)
+print("streams:")
+for sid, es in sorted(by_stream.items(), key=lambda kv: -sum(x.time_range.end - x.time_range.start for x in kv[1])):
+    busy = sum(x.time_range.end - x.time_range.start for x in es)
+    print(f"  stream {sid}: {len(es)} records, busy {busy / 2:.0f} us / step")
+main = max(by_stream.values(), key=lambda es: sum(x.time_range.end - x.time_range.start for x in es))
+main.sort(key=lambda e: e.time_range.start)
+gaps = []
+for a, b in zip(main, main[1:]):
+    g = b.time_range.start - a.time_range.end
+    if g > 3:
+        gaps.append((g, a.name[:60], b.name[:60]))
+print(f"main stream: {len(gaps)} gaps > 3 us, total {sum(g[0] for g in gaps) / 2:.0f} us / step; all gaps {sum(max(0, b.time_range.start - a.time_range.end) for a, b in zip(main, main[1:])) / 2:.0f} us / step")
+for g, a, b in sorted(gaps, reverse=True)[:25]:
+    print(f"  {g:8.1f} us  after {a}  before {b}")
