@@ -429,10 +429,13 @@ __global__ void __launch_bounds__(KNT, 1) cmpf_bwd_kernel(CmpBwdArgs a) {
     }
   }
   __syncthreads();
-  for (int i = tid; i < KD * KC; i += KNT) {
+  for (int i = tid * 4; i < KD * KC; i += KNT * 4) {          // 16 B vector reductions: a quarter of the atomic operations
     const int j = i / KC, k = i - j * KC;
     const float U = Pb[j * PBP + KC] + Pb[j * PBP + KC + 2], Td = Pb[j * PBP + KC + 1] + Pb[j * PBP + KC + 3];
-    atomicAdd(a.dW[br] + i, al * (gam[k] * (Pb[j * PBP + k] - U) + bet[k] * Td));
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = al * (gam[k + e] * (Pb[j * PBP + k + e] - U) + bet[k + e] * Td);
+    red_add_v4(a.dW[br] + i, v[0], v[1], v[2], v[3]);
   }
   for (int k = tid; k < KC; k += KNT) {
     float dg = 0.f, db = 0.f;
@@ -487,6 +490,7 @@ int cmpf_bwd(cudaStream_t s, long R, const void* const* x, const float* const* s
     if (drop) a.drop[i] = drop[i];
   }
   a.dfused = static_cast<const bf16*>(dfused); a.alpha = alpha; a.R = R;
+  for (int i = 0; i < 4; ++i) QV_CHECK(((uintptr_t)dW[i] & 15) == 0, "cmpf_bwd: dW[%d] must be 16 B aligned (vector reductions)", i);
   QV_TRY(opt_in(cmpf_bwd_kernel, CMPF_BWD_SMEM));
   const long ntiles = (R + KTR - 1) / KTR;
   const int gx = (int)max(1L, min(ntiles, (long)(qv_num_sms() + 3) / 4));

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256, LNB_M) ln_bwd_kernel(const TX* __restrict
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, DropP drop,
                                                      const float* __restrict__ rowscale, int rows_per_img) {
   QV_PDL_ENTRY();
-  __shared__ float red[2][8][256];
+  __shared__ __align__(16) float red[2][8][256];
   const bool masked = EPL == 8 && drop.p > 0.f, scaled = EPL == 8 && rowscale != nullptr;
   DropState dst{};
   if (masked) dst = drop_state(drop);
@@ -141,11 +141,16 @@ __global__ void __launch_bounds__(256, LNB_M) ln_bwd_kernel(const TX* __restrict
 #pragma unroll
   for (int i = 0; i < EPL; ++i) { red[0][warp][lane * EPL + i] = ag[i]; red[1][warp][lane * EPL + i] = ab[i]; }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < wpb; ++w) { a += red[0][w][c]; b += red[1][w][c]; }
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, b);
+  // 16 B vector reductions (C is a multiple of EPL >= 4): every CTA ends with 2 C / 4 atomic operations instead of 2 C
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int w = 0; w < wpb; ++w) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&red[0][w][c]), x1 = *reinterpret_cast<const float4*>(&red[1][w][c]);
+      a.x += x0.x; a.y += x0.y; a.z += x0.z; a.w += x0.w;
+      b.x += x1.x; b.y += x1.y; b.z += x1.z; b.w += x1.w;
+    }
+    red_add_v4(dgamma + c, a.x, a.y, a.z, a.w);
+    red_add_v4(dbeta + c, b.x, b.y, b.z, b.w);
   }
 }
 
@@ -183,6 +188,7 @@ int ln_bwd(cudaStream_t s, int dt_x, const void* x, int ldx, int dt_dy, const vo
   const DropP dp = drop ? *drop : DropP();
   QV_CHECK((dp.p == 0.f && !rowscale) || (epl == 8 && dx_t), "ln_bwd: fused dropout needs C > 128 (8 elements per lane) and a T output");
   QV_CHECK(resid == nullptr || (resid != dx_f32 && (const void*)resid != dx_t), "ln_bwd: resid must not alias an output");
+  QV_CHECK((((uintptr_t)dgamma | (uintptr_t)dbeta) & 15) == 0, "ln_bwd: dgamma / dbeta must be 16 B aligned (vector reductions)");
   // every CTA ends with 2 * C atomics: keep >= 32 rows per warp before adding CTAs
   const int grid = max(1, min(cdiv(rows, 8 * 32), qv_num_sms() * 6));
 #define LN_B4(TX, TDY, TO, E, G)                                                                                      \

@@ -527,9 +527,12 @@ __global__ void __launch_bounds__(FNT, TLFB_M) tlf_bwd_kernel(const float* __res
     }
   }
   __syncthreads();
-  for (int i = tid; i < FM * FC; i += FNT) {
+  for (int i = tid * 4; i < FM * FC; i += FNT * 4) {          // 16 B vector reductions: a quarter of the atomic operations
     const int m = i / FC, k = i - m * FC;
-    atomicAdd(dW + i, gam[k] * (Pb[i] - Uacc[m]) + bet[k] * Tacc[m]);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = gam[k + e] * (Pb[i + e] - Uacc[m]) + bet[k + e] * Tacc[m];
+    red_add_v4(dW + i, v[0], v[1], v[2], v[3]);
   }
   for (int k = tid; k < FC; k += FNT) {
     float dg = 0.f, db = 0.f;
@@ -854,6 +857,7 @@ int tlf_fwd(cudaStream_t s, const float* x, int B, int N, const float* gamma, co
 }
 int tlf_bwd(cudaStream_t s, const float* x, const float* S, const float* Z, const float* dxc, int B, int N, const float* gamma,
             const float* beta, const float* W, float eps, float* dx, float* dW, float* dbias, float* dgamma, float* dbeta) {
+  QV_CHECK(((uintptr_t)dW & 15) == 0, "tlf_bwd: dW must be 16 B aligned (vector reductions)");
   if (B <= 0) return 0;
   QV_TRY(opt_in(tlf_bwd_kernel, TLF_BWD_SMEM));
   qv_launch(tlf_bwd_kernel, grid_for(B, 2), FNT, TLF_BWD_SMEM, s, x, S, Z, dxc, B, N, gamma, beta, W, eps, dx, dW, dbias, dgamma, dbeta);

@@ -1,6 +1,6 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropout.py tests/test_gpu_live_reference.py -m gpu -q -x 2>&1 | tail -2
+python -m pytest tests -m gpu -q -x 2>&1 | tail -2
 B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline"
 ms() { tail -1 | grep -o '"ms_per_step": [0-9.]*\|"gpu_launches": [0-9]*' | head -3 | tr '\n' ' '; echo; }
 echo "step:"; $B 2>&1 | ms
 echo "step:"; $B 2>&1 | ms
-python tools/kineto_step.py --graph --top 40 2>&1 | grep "attn_mma_bwd\|cga_mma_bwd\|wall"
+python tools/kineto_step.py --graph --top 40 2>&1 | grep "tlf_bwd\|cmpf_bwd\|ln_bwd\|wall"
