@@ -1,6 +1,12 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -2
-B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline"
-ms() { tail -1 | grep -o '"ms_per_step": [0-9.]*\|"gpu_launches": [0-9]*' | head -3 | tr '\n' ' '; echo; }
-echo "step:"; $B 2>&1 | ms
-echo "step:"; $B 2>&1 | ms
-python tools/kineto_step.py --graph --top 40 2>&1 | grep "tlf_bwd\|cmpf_bwd\|ln_bwd\|wall"
+mkdir -p gpurun_out/r2
+O=gpurun_out/r2
+python bench.py > $O/bench41_default_with_baselines.log 2>&1; tail -1 $O/bench41_default_with_baselines.log | cut -c1-300
+python bench.py --impl reference --steps 8 --warmup 3 > $O/bench41_reference_arm.log 2>&1; tail -1 $O/bench41_reference_arm.log | cut -c1-200
+for w in hqavitv2_c100 qavitv2_c100 hqavit_stl96 hqavit_tinyin; do
+  python bench.py --workload $w --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > $O/bench41_$w.log 2>&1; tail -1 $O/bench41_$w.log | cut -c1-160
+done
+for w in hqavit_c100 qavitv2_c100; do
+  python bench.py --workload $w --mode infer --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > $O/bench41_infer_$w.log 2>&1; tail -1 $O/bench41_infer_$w.log | cut -c1-160
+done
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > $O/launch_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/launches_v2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > $O/launch_ncu.log 2>&1
+tail -2 $O/launch_ncu.log | cut -c1-200

@@ -8,7 +8,12 @@ tot = 0.0
 for row in csv.DictReader(lines):
     if row.get("Metric Name") != "gpu__time_duration.sum":
         continue
-    v = float(row["Metric Value"].replace(",", ""))
+    try:
+        v = float(row["Metric Value"].replace(",", ""))
+    except ValueError:
+        continue
+    if v != v:            # ncu occasionally reports one launch as nan
+        continue
     u = row["Metric Unit"]
     v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
     name = row["Kernel Name"].replace("(anonymous namespace)::", "").replace("void ", "")
@@ -18,6 +23,7 @@ for row in csv.DictReader(lines):
     agg[name][0] += 1
     agg[name][1] += v
     tot += v
-print(f"total {tot:.1f} us over {sum(a[0] for a in agg.values())} launches")
+steps = max(1, next((a[0] for k, a in agg.items() if k.endswith("::ce_kernel")), 1))   # one cross-entropy launch per step
+print(f"{steps} step(s): {tot / steps:.1f} us of kernel time and {sum(a[0] for a in agg.values()) / steps:.0f} launches per step (serialised, cold cache)")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    print(f"{t:10.1f} us {100 * t / tot:5.1f}%  n={n:4d} avg={t / n:8.1f}  {k}")
+    print(f"{t / steps:10.1f} us {100 * t / tot:5.1f}%  n={n / steps:6.1f} avg={t / n:8.1f}  {k}")
