@@ -1,5 +1,4 @@
 mkdir -p gpurun_out/r2
-O=gpurun_out/r2
-python tools/fmid_probe.py > $O/fmid_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:ffn_mid -s 6 -c 4 -o $O/fmid_final -f python tools/fmid_probe.py > $O/fmid_ncu.log 2>&1
-python tools/gemm_one.py 75776 576 192 > $O/gemm_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:tc_gemm_nt -s 2 -c 1 -o $O/gemm_qkv_final -f python tools/gemm_one.py 75776 576 192 > $O/gemm_ncu.log 2>&1
-cat $O/fmid_plain.log $O/gemm_plain.log; tail -1 $O/fmid_ncu.log; tail -1 $O/gemm_ncu.log
+python -m pytest tests -m gpu -q -x -k "dp or nccl or rank" 2>&1 | tail -3 | tee gpurun_out/r2/t41_dp.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2/bench41_n2.log 2>&1; tail -1 gpurun_out/r2/bench41_n2.log | cut -c1-400
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --workload qavitv2_c100 --batch 256 > gpurun_out/r2/bench41_qavitv2_b256_n2.log 2>&1; tail -1 gpurun_out/r2/bench41_qavitv2_b256_n2.log | cut -c1-400
