@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(WARPS * 32) cga64_bwd_kernel(CgaP p) {
       if (active) project(acc, SH + L::X, SH + L::K, SH + L::V, W + L::Q, Wst, bias, grp, row0, lane);
       __syncthreads();
       float dq[2][4];
+      float dk[L::KS][2][4], dv[L::KS][2][4];
       if (active) {
         float dO[2][4];
 #pragma unroll
@@ -272,7 +273,6 @@ __global__ void __launch_bounds__(WARPS * 32) cga64_bwd_kernel(CgaP p) {
           const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(SH + L::DO + (row0 + g + 8) * PO + grp * CPG + n * 8 + 2 * t));
           dO[n][0] = lo.x; dO[n][1] = lo.y; dO[n][2] = hi.x; dO[n][3] = hi.y;
         }
-        float dk[L::KS][2][4], dv[L::KS][2][4];
 #pragma unroll
         for (int n = 0; n < 2; ++n)
 #pragma unroll
@@ -343,19 +343,28 @@ __global__ void __launch_bounds__(WARPS * 32) cga64_bwd_kernel(CgaP p) {
           }
           __syncwarp();
         }
-        // this query tile's contribution to every key of the image -> shared fp32 accumulators
-#pragma unroll
-        for (int mt = 0; mt < L::KS; ++mt)
-#pragma unroll
-          for (int n = 0; n < 2; ++n) {
-            const int c = n * 8 + 2 * t, ra = (mt * 16 + g) * CPG, rb = (mt * 16 + g + 8) * CPG;
-            atomicAdd(dKs + ra + c, dk[mt][n][0]); atomicAdd(dKs + ra + c + 1, dk[mt][n][1]);
-            atomicAdd(dKs + rb + c, dk[mt][n][2]); atomicAdd(dKs + rb + c + 1, dk[mt][n][3]);
-            atomicAdd(dVs + ra + c, dv[mt][n][0]); atomicAdd(dVs + ra + c + 1, dv[mt][n][1]);
-            atomicAdd(dVs + rb + c, dv[mt][n][2]); atomicAdd(dVs + rb + c + 1, dv[mt][n][3]);
-          }
       }
-      __syncthreads();                                              // dK / dV of the group are complete
+      // this query tile's contribution to every key of the image -> shared fp32 accumulators, one warp after the other with plain
+      // read-modify-writes.  (fp32 atomicAdd on shared memory compiles to a compare-and-swap loop -- ATOMS.CAST.SPIN: 80 of them per
+      // lane and group, with all four warps on the same addresses.)  The fixed order also makes the sums reproducible.
+      for (int w = 0; w < WARPS; ++w) {
+        if (warp == w && active) {
+#pragma unroll
+          for (int mt = 0; mt < L::KS; ++mt)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              const int c = n * 8 + 2 * t, ra = (mt * 16 + g) * CPG, rb = (mt * 16 + g + 8) * CPG;
+              float2* ka = reinterpret_cast<float2*>(dKs + ra + c); float2* kb2 = reinterpret_cast<float2*>(dKs + rb + c);
+              float2* va = reinterpret_cast<float2*>(dVs + ra + c); float2* vb2 = reinterpret_cast<float2*>(dVs + rb + c);
+              float2 x;
+              x = *ka; x.x += dk[mt][n][0]; x.y += dk[mt][n][1]; *ka = x;
+              x = *kb2; x.x += dk[mt][n][2]; x.y += dk[mt][n][3]; *kb2 = x;
+              x = *va; x.x += dv[mt][n][0]; x.y += dv[mt][n][1]; *va = x;
+              x = *vb2; x.x += dv[mt][n][2]; x.y += dv[mt][n][3]; *vb2 = x;
+            }
+        }
+        __syncthreads();                                            // after the last pass: dK / dV of the group are complete
+      }
       for (int i = threadIdx.x; i < KB * CPG; i += blockDim.x) {   // bank rows -> d(projected bank)
         dkb[i] += dKs[L::NT * CPG + i];
         dvb[i] += dVs[L::NT * CPG + i];

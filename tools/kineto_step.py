@@ -12,12 +12,15 @@ ap.add_argument("--batch", type=int, default=4736)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--top", type=int, default=60)
 ap.add_argument("--dropout", type=float, default=0.1)
+ap.add_argument("--workload", default="hqavit_c100", help="one of bench.py's WORKLOADS")
 a = ap.parse_args()
 torch.manual_seed(42)
-model = Q.HQAViT(Q.HQAViTConfig(dropout=a.dropout, drop_path=a.dropout)).cuda().train().set_precision("bf16")
+import bench
+model, w = bench.build_workload(Q, a.workload, a.dropout, a.dropout)
+model = model.cuda().train().set_precision("bf16")
 opt = Q.FusedAdamW(model.named_parameters(), lr=6e-4, betas=(0.95, 0.999), weight_decay=0.06, max_grad_norm=0.5)
-x = torch.randn(a.batch, 3, 32, 32, device="cuda")
-y = torch.randint(0, 100, (a.batch,), device="cuda")
+x = torch.randn(a.batch, 3, w["img"], w["img"], device="cuda")
+y = torch.randint(0, w["classes"], (a.batch,), device="cuda")
 
 def eager():
     opt.zero_grad()
