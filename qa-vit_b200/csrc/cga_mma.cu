@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(WARPS_BWD * 32, 1) cga_mma_bwd_kernel(CgaP p) 
     for (int n = 0; n < 4; ++n) dWacc[m][n][0] = dWacc[m][n][1] = dWacc[m][n][2] = dWacc[m][n][3] = 0.f;
 #pragma unroll
   for (int n = 0; n < 6; ++n) dbacc[n][0] = dbacc[n][1] = 0.f;
+  float dkbr[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dvbr[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 
   for (int b = blockIdx.x * WARPS + warp; b < p.B; b += gridDim.x * WARPS) {
     __syncwarp();
@@ -336,14 +337,12 @@ __global__ void __launch_bounds__(WARPS_BWD * 32, 1) cga_mma_bwd_kernel(CgaP p) 
         }
         __syncwarp();
       }
-      // bank rows (keys 16..31) -> d(projected bank)
+      // bank rows (keys 16..31) -> d(projected bank): summed in registers over groups and images, flushed once per warp (shared-memory
+      // fp32 atomics are compare-and-swap loops: 16 per lane and group with 12 warps on the same 512 addresses)
 #pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        atomicAdd(dkb + g * CPG + n * 8 + 2 * t, dk[1][n][0]); atomicAdd(dkb + g * CPG + n * 8 + 2 * t + 1, dk[1][n][1]);
-        atomicAdd(dkb + (g + 8) * CPG + n * 8 + 2 * t, dk[1][n][2]); atomicAdd(dkb + (g + 8) * CPG + n * 8 + 2 * t + 1, dk[1][n][3]);
-        atomicAdd(dvb + g * CPG + n * 8 + 2 * t, dv[1][n][0]); atomicAdd(dvb + g * CPG + n * 8 + 2 * t + 1, dv[1][n][1]);
-        atomicAdd(dvb + (g + 8) * CPG + n * 8 + 2 * t, dv[1][n][2]); atomicAdd(dvb + (g + 8) * CPG + n * 8 + 2 * t + 1, dv[1][n][3]);
-      }
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dkbr[n][e] += dk[1][n][e]; dvbr[n][e] += dv[1][n][e]; }
       // [dq | dk | dv] (16 x 48): bias grads, staging for dW, A operand for dx
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
@@ -399,6 +398,13 @@ __global__ void __launch_bounds__(WARPS_BWD * 32, 1) cga_mma_bwd_kernel(CgaP p) 
     }
   }
   // ---- flush the per-warp accumulators
+#pragma unroll
+  for (int n = 0; n < 2; ++n) {
+    atomicAdd(dkb + g * CPG + n * 8 + 2 * t, dkbr[n][0]); atomicAdd(dkb + g * CPG + n * 8 + 2 * t + 1, dkbr[n][1]);
+    atomicAdd(dkb + (g + 8) * CPG + n * 8 + 2 * t, dkbr[n][2]); atomicAdd(dkb + (g + 8) * CPG + n * 8 + 2 * t + 1, dkbr[n][3]);
+    atomicAdd(dvb + g * CPG + n * 8 + 2 * t, dvbr[n][0]); atomicAdd(dvb + g * CPG + n * 8 + 2 * t + 1, dvbr[n][1]);
+    atomicAdd(dvb + (g + 8) * CPG + n * 8 + 2 * t, dvbr[n][2]); atomicAdd(dvb + (g + 8) * CPG + n * 8 + 2 * t + 1, dvbr[n][3]);
+  }
 #pragma unroll
   for (int mt = 0; mt < 3; ++mt) {
     float* dst = mt == 0 ? p.dWq : (mt == 1 ? p.dWk : p.dWv);
