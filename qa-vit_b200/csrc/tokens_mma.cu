@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(NWARP * 32) bwr_mma_kernel(const bf16* __restr
   }
 }
 
-// Same reduction for short images (Nt <= 32, HQAViT's 16 learned tokens): the sum over the batch lets G images be STACKED along the
+// Same reduction for short images (Nt <= 64; HQAViT's 16 learned tokens, QAViTv2's 64): the sum over the batch lets G images be STACKED along the
 // contraction (token) axis -- [16 slots x G Nt] x [G Nt x 2d] -- so one CTA iteration (one load phase, one softmax phase, three
 // barriers) covers G images instead of one; the per-(image, slot) softmax over <= 32 tokens is a serial loop of one thread.
 // (The one-image-per-iteration kernel above spent its time in 7 barriers per 16-row image: 55 us for 60 MB, ncu.)
@@ -881,20 +881,47 @@ __global__ void __launch_bounds__(GWARP * 32) bwr_mma_grp_kernel(const bf16* __r
       }
     }
     __syncthreads();
-    for (int pq = tid; pq < nimg * M16; pq += blockDim.x) {      // softmax over the Nt tokens of (image, slot)
-      const int col = pq % M16;
-      float* f = sF + (pq / M16) * Nt * M16 + col;
-      float mx = -INFINITY;
-      for (int n = 0; n < Nt; ++n) mx = fmaxf(mx, f[n * M16]);
-      float z = 0.f;
-      for (int n = 0; n < Nt; ++n) { const float e = __expf(f[n * M16] - mx); f[n * M16] = e; z += e; }
-      z = 1.f / z;
-      const int r0 = (pq / M16) * Nt;
-      for (int n = 0; n < Nt; ++n) {
-        const float sv = f[n * M16] * z;
-        const bf16 hi = __float2bfloat16_rn(sv);
-        sS[(r0 + n) * SP + col] = hi;
-        sL[(r0 + n) * SP + col] = __float2bfloat16_rn(sv - __bfloat162float(hi));
+    // softmax over the Nt tokens of (image, slot)
+    if (Nt <= 32) {                                              // short images: one thread per pair (64 pairs per pass)
+      for (int pq = tid; pq < nimg * M16; pq += blockDim.x) {
+        const int col = pq % M16;
+        float* f = sF + (pq / M16) * Nt * M16 + col;
+        float mx = -INFINITY;
+        for (int n = 0; n < Nt; ++n) mx = fmaxf(mx, f[n * M16]);
+        float z = 0.f;
+        for (int n = 0; n < Nt; ++n) { const float e = __expf(f[n * M16] - mx); f[n * M16] = e; z += e; }
+        z = 1.f / z;
+        const int r0 = (pq / M16) * Nt;
+        for (int n = 0; n < Nt; ++n) {
+          const float sv = f[n * M16] * z;
+          const bf16 hi = __float2bfloat16_rn(sv);
+          sS[(r0 + n) * SP + col] = hi;
+          sL[(r0 + n) * SP + col] = __float2bfloat16_rn(sv - __bfloat162float(hi));
+        }
+      }
+    } else {
+      // 16 lanes per pair, tokens strided over them, shuffle reductions inside the half-warp (one thread per pair walking 64 tokens
+      // three times was the longest phase of a pass; at 16 tokens the serial loop above is the faster one: 36 vs 47 us per launch)
+      for (int pq0 = 0; pq0 < nimg * M16; pq0 += blockDim.x / 16) {
+        const int pq = pq0 + tid / 16, part = tid & 15;
+        const bool on = pq < nimg * M16;
+        const int col = on ? pq % M16 : 0, r0 = on ? (pq / M16) * Nt : 0;
+        float* f = sF + r0 * M16 + col;
+        float mx = -INFINITY;
+        if (on) for (int n = part; n < Nt; n += 16) mx = fmaxf(mx, f[n * M16]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float z = 0.f;
+        if (on) for (int n = part; n < Nt; n += 16) { const float e = __expf(f[n * M16] - mx); f[n * M16] = e; z += e; }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        z = 1.f / z;
+        if (on) for (int n = part; n < Nt; n += 16) {
+          const float sv = f[n * M16] * z;
+          const bf16 hi = __float2bfloat16_rn(sv);
+          sS[(r0 + n) * SP + col] = hi;
+          sL[(r0 + n) * SP + col] = __float2bfloat16_rn(sv - __bfloat162float(hi));
+        }
       }
     }
     __syncthreads();
@@ -1017,7 +1044,7 @@ bool bank_write_mma_ok(int Nt, int d, int kb, int ldcg) {
   return kb == 16 && Nt % 16 == 0 && Nt >= 16 && Nt <= 256 && d % 16 == 0 && d <= 256 && ldcg % 8 == 0;
 }
 int bank_write_reduce_mma(cudaStream_t s, const void* tn, const void* cg, int ldcg, int B, int Nt, int d, float* partial, int* n_partial) {
-  if (Nt <= 32) {   // stacked-image flavour
+  if (Nt <= 64) {   // stacked-image flavour (one 64-token image per pass at Nt = 64)
     const int G = 64 / Nt;
     const int R = G * Nt;
     const size_t smem = ((size_t)R * (2 * d + 8) + (size_t)2 * R * SP) * 2 + (size_t)R * M16 * 4 + 16;
