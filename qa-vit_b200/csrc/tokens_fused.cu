@@ -383,18 +383,30 @@ __global__ void __launch_bounds__(FNT, TLFB_M) tlf_bwd_kernel(const float* __res
   XRegs xr;
   DRegs dr;
   float4 sr = make_float4(0.f, 0.f, 0.f, 0.f), zr = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto prefetch = [&](int b) {
-    xload(xr, x + (long)b * N * FC, N, warp, lane);
+  // the next image's x tile is prefetched into registers (48 per thread) at the top of an iteration; its small tiles (dxc, S, Z: 20
+  // more registers) are only pulled into L2 mid-iteration and loaded at the top of their own iteration, ahead of the LayerNorm pass
+  // over the x registers -- with all 68 held for a whole iteration, ptxas spilled eight of them right behind their loads and the
+  // spill stores waited out the full memory latency (6.5 % of the kernel's stall samples on one STL)
+  auto prefetch_x = [&](int b) { xload(xr, x + (long)b * N * FC, N, warp, lane); };
+  auto load_small = [&](int b) {
     dload(dr, dxc + (long)b * FM * FC, tid);
     if (tid * 4 < N * FM) {
       sr = __ldg(reinterpret_cast<const float4*>(Sin + (long)b * N * FM) + tid);
       zr = __ldg(reinterpret_cast<const float4*>(Zin + (long)b * N * FM) + tid);
     }
   };
-  if ((int)blockIdx.x < B) prefetch(blockIdx.x);
+  auto l2_small = [&](int b) {        // 128 B lines: dxc 96, S and Z N / 2 each
+    const char* q = nullptr;
+    if (tid < 96) q = reinterpret_cast<const char*>(dxc + (long)b * FM * FC) + tid * 128;
+    else if (tid < 96 + N / 2) q = reinterpret_cast<const char*>(Sin + (long)b * N * FM) + (tid - 96) * 128;
+    else if (tid >= 128 && tid < 128 + N / 2) q = reinterpret_cast<const char*>(Zin + (long)b * N * FM) + (tid - 128) * 128;
+    if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+  };
+  if ((int)blockIdx.x < B) prefetch_x(blockIdx.x);
   const int mt = warp & 3, hf = warp >> 2;      // (token tile, slot half | channel half)
   const bool act = mt < MT;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    load_small(b);
     xstore<true>(xr, X, XL, mean_s, rstd_s, nullptr, N, warp, lane, eps);
     dstore(dr, D, DL, tid);
     if (tid * 4 < N * FM) {
@@ -404,7 +416,7 @@ __global__ void __launch_bounds__(FNT, TLFB_M) tlf_bwd_kernel(const float* __res
       store_split4(S, SL, n * FSP + c, sr);
     }
     if (tid < FM) R[tid] = 0.f;
-    if (b + (int)gridDim.x < B) prefetch(b + gridDim.x);
+    if (b + (int)gridDim.x < B) prefetch_x(b + gridDim.x);
     __syncthreads();
     // ---- dS[N, 16] = x dxc^T ; column sums of S * dS
     float dS[4] = {0.f, 0.f, 0.f, 0.f};
@@ -454,6 +466,7 @@ __global__ void __launch_bounds__(FNT, TLFB_M) tlf_bwd_kernel(const float* __res
       }
     }
     __syncthreads();
+    if (b + (int)gridDim.x < B) l2_small(b + gridDim.x);
     // ---- P[16, C] += dl'^T x (persistent accumulators): warp = 3 channel tiles of 8
     for (int ks = 0; ks < MT; ++ks) {
       uint32_t a[4], al[4];
