@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(FNT, 2) tlf_fwd_kernel(const float* __restrict
     {
       const int mt = warp & 3, nt = warp >> 2;
       if (mt < MT) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
         for (int ks = 0; ks < FC / 16; ++ks) {
           uint32_t a[4], al[4], bh[2], bl[2];
@@ -252,8 +252,12 @@ __global__ void __launch_bounds__(FNT, 2) tlf_fwd_kernel(const float* __restrict
           ldA(al, XL, FXP, mt * 16, ks * 16, lane);
           ldB2(bh, Wg, FXP, nt * 8, ks * 16, lane);
           ldB2(bl, WgL, FXP, nt * 8, ks * 16, lane);
-          mma3(acc, a, al, bh[0], bh[1], bl[0], bl[1]);
+          mma16816(acc, a, bh[0], bh[1]);       // three independent chains (one accumulator = 36 dependent MMAs per image)
+          mma16816(acc1, al, bh[0], bh[1]);
+          mma16816(acc2, a, bl[0], bl[1]);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += acc1[j] + acc2[j];
         const int n0 = mt * 16 + g, n1 = n0 + 8, m = nt * 8 + 2 * t;
         const float r0 = rstd_s[n0], u0 = mean_s[n0], r1 = rstd_s[n1], u1 = mean_s[n1];
         // zc = LN-normalised projection without the constant c0: kept for backward, where sum_k g xhat = sum_m dlogits zc
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(FNT, TLFB_M) tlf_bwd_kernel(const float* __res
     if (b + (int)gridDim.x < B) prefetch_x(b + gridDim.x);
     __syncthreads();
     // ---- dS[N, 16] = x dxc^T ; column sums of S * dS
-    float dS[4] = {0.f, 0.f, 0.f, 0.f};
+    float dS[4] = {0.f, 0.f, 0.f, 0.f}, dS1[4] = {0.f, 0.f, 0.f, 0.f}, dS2[4] = {0.f, 0.f, 0.f, 0.f};
     const int n0 = mt * 16 + g, n1 = n0 + 8, m0 = hf * 8 + 2 * t;
     if (act) {
 #pragma unroll 4
@@ -429,8 +433,12 @@ __global__ void __launch_bounds__(FNT, TLFB_M) tlf_bwd_kernel(const float* __res
         ldA(al, XL, FXP, mt * 16, ks * 16, lane);
         ldB2(bh, D, FXP, hf * 8, ks * 16, lane);
         ldB2(bl, DL, FXP, hf * 8, ks * 16, lane);
-        mma3(dS, a, al, bh[0], bh[1], bl[0], bl[1]);
+        mma16816(dS, a, bh[0], bh[1]);          // three independent chains
+        mma16816(dS1, al, bh[0], bh[1]);
+        mma16816(dS2, a, bl[0], bl[1]);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dS[j] += dS1[j] + dS2[j];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         float v = F[n0 * FM + m0 + j] * dS[j] + F[n1 * FM + m0 + j] * dS[2 + j];
@@ -706,7 +714,7 @@ __global__ void __launch_bounds__(FNT, 1) upf_bwd_kernel(const float* __restrict
   for (int pr = 0; pr < 6; ++pr)
 #pragma unroll
     for (int h = 0; h < 2; ++h) { dgam[pr][h][0] = dgam[pr][h][1] = 0.f; dbet[pr][h][0] = dbet[pr][h][1] = 0.f; }
-  float aW[4] = {0.f, 0.f, 0.f, 0.f};
+  float aW[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // hi hi | lo hi | hi lo: three independent MMA chains
   __syncthreads();
   uint32_t a[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
   float b0 = 0.f, b1 = 0.f;
@@ -820,7 +828,9 @@ __global__ void __launch_bounds__(FNT, 1) upf_bwd_kernel(const float* __restrict
         ldA(gl, GL, FXP, mt * 16, ks * 16, lane);
         ldB2(bh, D, FXP, hf * 8, ks * 16, lane);
         ldB2(bl, DL, FXP, hf * 8, ks * 16, lane);
-        mma3(aW, ga, gl, bh[0], bh[1], bl[0], bl[1]);
+        mma16816(aW[0], ga, bh[0], bh[1]);      // (one accumulator made the 36 MMAs of an image one dependent chain)
+        mma16816(aW[1], gl, bh[0], bh[1]);
+        mma16816(aW[2], ga, bl[0], bl[1]);
       }
     }
     __syncthreads();
@@ -828,8 +838,8 @@ __global__ void __launch_bounds__(FNT, 1) upf_bwd_kernel(const float* __restrict
   // ---- flush
   if (act) {
     const int m = hf * 8 + 2 * t;
-    atomicAdd(dW + n0 * FM + m, aW[0]); atomicAdd(dW + n0 * FM + m + 1, aW[1]);
-    atomicAdd(dW + n1 * FM + m, aW[2]); atomicAdd(dW + n1 * FM + m + 1, aW[3]);
+    atomicAdd(dW + n0 * FM + m, aW[0][0] + aW[1][0] + aW[2][0]); atomicAdd(dW + n0 * FM + m + 1, aW[0][1] + aW[1][1] + aW[2][1]);
+    atomicAdd(dW + n1 * FM + m, aW[0][2] + aW[1][2] + aW[2][2]); atomicAdd(dW + n1 * FM + m + 1, aW[0][3] + aW[1][3] + aW[2][3]);
 #pragma unroll
     for (int pr = 0; pr < 6; ++pr)
 #pragma unroll
