@@ -1,3 +1,3 @@
 # scratch command file for `gpurun -- 'bash tools/_call.sh'` (edited per experiment)
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+mkdir -p gpurun_out/r2
+python tools/kineto_step.py --graph --top 200 2>&1 | grep -v "Warn\|_warn_once" > gpurun_out/r2/kineto_final.txt; head -3 gpurun_out/r2/kineto_final.txt; grep "stream\|gaps" gpurun_out/r2/kineto_final.txt | head -5
