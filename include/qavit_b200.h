@@ -286,9 +286,9 @@ int qavit_test_tokens_fused(int op, int B, int N, int C, const float* const* in,
 int qavit_test_cmp_fused(int op, long long R, const void* const* in, void* const* out, void* stream);
 
 /* Test hook for the fused CCF-FFN mid-section of bf16 runs (H:704-709: GELU -> dwconv_norm -> depthwise 3x3 * scale ->
- * post_dwconv_norm on 4 x 4 token maps, C a multiple of 32 up to 128): op 0 forward, 1 backward; pointer order documented next to
+ * post_dwconv_norm on side x side token maps; side 4: C a multiple of 32 up to 128, side 8: C a multiple of 8 up to 128): op 0 forward, 1 backward; pointer order documented next to
  * the definition (csrc/block.cu). */
-int qavit_test_ffn_mid(int op, int B, int C, const void* const* in, void* const* out, void* stream);
+int qavit_test_ffn_mid(int op, int B, int side, int C, const void* const* in, void* const* out, void* stream);
 
 /* Unit-test hooks for the GEMM flavours (bf16 tcgen05 and fp32 SIMT) behind the block. */
 int qavit_test_gemm_nt(int use_tc, const void* A, int lda, int M, int N, int K, const float* W, const void* Wb,

@@ -104,7 +104,7 @@ _SIGS = {
     "qavit_test_gemm_tn": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "qavit_test_tokens_fused": (_i, [_i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "qavit_test_cmp_fused": (_i, [_i, _ll, C.POINTER(_vp), C.POINTER(_vp), _vp]),
-    "qavit_test_ffn_mid": (_i, [_i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    "qavit_test_ffn_mid": (_i, [_i, _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "qavit_convert_weight": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

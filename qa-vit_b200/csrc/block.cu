@@ -166,7 +166,10 @@ int make_dims(const qavit_block_cfg& c, Dims* D) {
   D->ftok = D->tl && c.dtype == QV_BF16 && tokens_fused_ok(c.tokens, c.tokens_full, c.dim);
   D->fup = D->tl && c.dtype == QV_BF16 && tokens_fused_ok(c.tokens, D->No, c.dim);
   D->fcmp = c.dtype == QV_BF16 && cmp_fused_ok(c.dim, c.compress_dim);
-  D->fmid = c.dtype == QV_BF16 && !c.ffn_v1 && ffn_mid_ok(side, c.ffn_hidden) && getenv("QV_NO_FMID") == nullptr;
+  // (8 x 8 maps: the shared-memory tile flavour of ffn_mid.cu is correct but measured SLOWER than the three-kernel chain -- 266 + 612 us
+  // against 177 + 362 us per block at B = 4736, QAViTv2 step 79.0 vs 76.5 ms -- so it stays opt-in: QV_FMID_TILE=1)
+  D->fmid = c.dtype == QV_BF16 && !c.ffn_v1 && ffn_mid_ok(side, c.ffn_hidden) && getenv("QV_NO_FMID") == nullptr &&
+            (side == 4 || getenv("QV_FMID_TILE") != nullptr);
   D->tdt = (c.dtype == QV_BF16 && D->tl && !D->ftok && !tokens_mma_ok(c.tokens, c.tokens_full, c.dim) &&
             !tokens_mma64_ok(c.tokens, c.tokens_full, c.dim)) ? QV_F32 : c.dtype;
   D->tts = D->tdt == QV_BF16 ? 2 : 4;
@@ -671,7 +674,7 @@ extern "C" int qavit_block_forward(const qavit_block_cfg* cfg, const void* const
   if (!D.v1) {
     QV_TRY(gemm_nt(st, dt, c.sv(S.y), d, R, c.W(W_F1, c.pf(QP_FFN_FC1_W)), epi_t(c, c.pf(QP_FFN_FC1_B), c.sv(S.h_pre), D.fh)));
     if (D.fmid) {
-      QV_TRY(ffn_mid_fwd(st, c.sv(S.h_pre), D.B, D.fh, c.pf(QP_FFN_DWN_W), c.pf(QP_FFN_DWN_B), c.pf(QP_FFN_DW_W),
+      QV_TRY(ffn_mid_fwd(st, c.sv(S.h_pre), D.B, D.side, D.fh, c.pf(QP_FFN_DWN_W), c.pf(QP_FFN_DWN_B), c.pf(QP_FFN_DW_W),
                          cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, c.pf(QP_FFN_SCALE), c.pf(QP_FFN_PDN_W), c.pf(QP_FFN_PDN_B), 1e-5f,
                          c.sv(S.hn2), c.svf(S.dn_stats), c.svf(S.pd_stats)));
     } else {
@@ -771,7 +774,7 @@ extern "C" int qavit_block_backward(const qavit_block_cfg* cfg, const void* cons
     QV_TRY(gemm_tn(st, dt, c.sc(X.d_o), d, c.sv(S.hn2), D.fh, R, d, D.fh, G(QP_FFN_FC2_W), G(QP_FFN_FC2_B), nullptr));
     QV_TRY(gemm_nn(st, dt, c.sc(X.d_o), d, R, c.W(W_F2, c.pf(QP_FFN_FC2_W)), epi_t(c, nullptr, c.sc(X.d_hn2), D.fh)));
     if (D.fmid) {
-      QV_TRY(ffn_mid_bwd(st, c.sv(S.h_pre), c.sc(X.d_hn2), c.svf(S.dn_stats), c.svf(S.pd_stats), D.B, D.fh, c.pf(QP_FFN_DWN_W),
+      QV_TRY(ffn_mid_bwd(st, c.sv(S.h_pre), c.sc(X.d_hn2), c.svf(S.dn_stats), c.svf(S.pd_stats), D.B, D.side, D.fh, c.pf(QP_FFN_DWN_W),
                          c.pf(QP_FFN_DWN_B), c.pf(QP_FFN_DW_W), cfg->dwconv_bias ? c.pf(QP_FFN_DW_B) : nullptr, c.pf(QP_FFN_SCALE),
                          c.pf(QP_FFN_PDN_W), c.sc(X.d_hpre), G(QP_FFN_DWN_W), G(QP_FFN_DWN_B), G(QP_FFN_DW_W),
                          cfg->dwconv_bias ? G(QP_FFN_DW_B) : nullptr, G(QP_FFN_SCALE), G(QP_FFN_PDN_W), G(QP_FFN_PDN_B)));
@@ -1078,12 +1081,13 @@ extern "C" int qavit_test_tokens_fused(int op, int B, int N, int C, const float*
 //   1: in  {x0..x3, stats0..3, gamma0..3, beta0..3, W0..3, alpha[4], dfused (bf16 [R, 192])}   out {dx0..3 (bf16), dW0..3, db0..3, dgamma0..3, dbeta0..3}
 // op 0: forward (in: h_pre, g1, b1, w, bias, scale, g2, b2; out: hn2, stats1, stats2); op 1: backward (in: + d_hn2, stats1, stats2;
 // out: d_hpre, dg1, db1, dw, dbias, dscale, dg2, db2)
-extern "C" int qavit_test_ffn_mid(int op, int B, int C, const void* const* in, void* const* out, void* stream) {
+extern "C" int qavit_test_ffn_mid(int op, int B, int side, int C, const void* const* in, void* const* out, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto f = [&](int i) { return static_cast<const float*>(in[i]); };
   auto o = [&](int i) { return static_cast<float*>(out[i]); };
-  if (op == 0) return ffn_mid_fwd(s, in[0], B, C, f(1), f(2), f(3), f(4), f(5), f(6), f(7), 1e-5f, out[0], o(1), o(2));
-  return ffn_mid_bwd(s, in[0], in[8], f(9), f(10), B, C, f(1), f(2), f(3), f(4), f(5), f(6), out[0], o(1), o(2), o(3), o(4), o(5), o(6), o(7));
+  QV_CHECK(ffn_mid_ok(side, C), "ffn_mid: side=%d C=%d not covered", side, C);
+  if (op == 0) return ffn_mid_fwd(s, in[0], B, side, C, f(1), f(2), f(3), f(4), f(5), f(6), f(7), 1e-5f, out[0], o(1), o(2));
+  return ffn_mid_bwd(s, in[0], in[8], f(9), f(10), B, side, C, f(1), f(2), f(3), f(4), f(5), f(6), out[0], o(1), o(2), o(3), o(4), o(5), o(6), o(7));
 }
 
 extern "C" int qavit_test_cmp_fused(int op, long long R, const void* const* in, void* const* out, void* stream) {

@@ -327,6 +327,256 @@ __global__ void __launch_bounds__(32 * NW * IPC) ffn_mid_bwd_kernel(FfnMidP p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 8 x 8 maps (64 tokens)
+// MEASURED SLOWER than the ln_fwd + dw_fwd + ln_fwd chain it would replace (266 + 612 us against 177 + 362 us per block at B = 4736,
+// C = 96: eight serial token iterations per warp with two shuffle reductions each, erf per element, nine shared loads per stencil
+// output), so block.cu routes 8 x 8 maps here only with QV_FMID_TILE=1; kept with its parity test as the starting point for a
+// register-tiled version.
+// Same operation for 64-token blocks (QAViTv2, HQAViT-TinyImageNet): a channel's map no longer fits a thread's registers, so the
+// image lives in shared memory as fp32 [token][channel] tiles and every phase is "a warp takes a token, its lanes stride over the
+// channels": conflict-free shared memory, coalesced global rows, LayerNorm sums by one warp reduction per token, and the stencil reads
+// its neighbours from the tile.  One CTA per image (8 warps), persistent over images; parameters staged in shared memory once; per-lane
+// channel accumulators for the parameter gradients, reduced over the CTA's warps in shared memory before the atomics.
+constexpr int TW = 8;                      // warps per CTA
+constexpr int TCH = 4;                     // channels per lane: C <= 128
+
+struct TilePar {                           // parameters in shared memory: [g1 | b1 | g2 | b2 | scale | bias | w (9 C)]
+  const float *g1, *b1, *g2, *b2, *sc, *bs, *w;
+  __device__ TilePar(const float* base, int C) : g1(base), b1(base + C), g2(base + 2 * C), b2(base + 3 * C), sc(base + 4 * C), bs(base + 5 * C), w(base + 6 * C) {}
+};
+__device__ __forceinline__ void stage_params(float* base, const FfnMidP& p, int C) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    base[c] = p.g1[c]; base[C + c] = p.b1 ? p.b1[c] : 0.f; base[2 * C + c] = p.g2[c]; base[3 * C + c] = p.b2 ? p.b2[c] : 0.f;
+    base[4 * C + c] = p.scale ? p.scale[c] : 1.f; base[5 * C + c] = p.bias ? p.bias[c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) base[6 * C + i] = p.w[i];
+}
+
+template <int SIDE>
+__global__ void __launch_bounds__(TW * 32) ffn_mid_tile_fwd_kernel(FfnMidP p, int C) {
+  QV_PDL_ENTRY();
+  constexpr int NT = SIDE * SIDE;
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm;                            // gelu(x), then hn
+  float* Bt = A + NT * C;                   // the raw bf16 image first, then cs
+  float* par = Bt + NT * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_params(par, p, C);
+  const TilePar P(par, C);
+  const float invC = 1.f / C;
+  for (long b = blockIdx.x; b < p.B; b += gridDim.x) {
+    __syncthreads();                         // parameters staged / previous image's tiles consumed
+    // the image comes in as ONE wave of independent 16 B loads (a global load per token iteration cost a memory round trip each)
+    const bf16* src = reinterpret_cast<const bf16*>(Bt);
+    for (int i = threadIdx.x; i < NT * C / 8; i += TW * 32)
+      reinterpret_cast<uint4*>(Bt)[i] = reinterpret_cast<const uint4*>(p.h_pre + b * NT * C)[i];
+    __syncthreads();
+    for (int t = warp; t < NT; t += TW) {    // gelu + LayerNorm 1 statistics
+      float s = 0.f, q = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float v = mid_gelu(__bfloat162float(src[t * C + c]));
+        A[t * C + c] = v; s += v; q = fmaf(v, v, q);
+      }
+      s = warp_sum(s); q = warp_sum(q);
+      const float m = s * invC, r = rsqrtf(fmaxf(q * invC - m * m, 0.f) + p.eps);
+      for (int c = lane; c < C; c += 32) A[t * C + c] = fmaf((A[t * C + c] - m) * r, P.g1[c], P.b1[c]);   // hn (own elements)
+      if (lane == 0) *reinterpret_cast<float2*>(p.st1 + 2 * (b * NT + t)) = make_float2(m, r);
+    }
+    __syncthreads();
+    for (int t = warp; t < NT; t += TW) {    // stencil * scale + LayerNorm 2 statistics
+      const int py = t / SIDE, px = t % SIDE;
+      float s = 0.f, q = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        float a = P.bs[c];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yy = py + ky - 1, xx = px + kx - 1;
+            if (yy >= 0 && yy < SIDE && xx >= 0 && xx < SIDE) a = fmaf(P.w[c * 9 + ky * 3 + kx], A[(yy * SIDE + xx) * C + c], a);
+          }
+        a *= P.sc[c];
+        Bt[t * C + c] = a; s += a; q = fmaf(a, a, q);
+      }
+      s = warp_sum(s); q = warp_sum(q);
+      const float m = s * invC, r = rsqrtf(fmaxf(q * invC - m * m, 0.f) + p.eps);
+      bf16* dst = p.hn2 + (b * NT + t) * C;
+      for (int c = lane; c < C; c += 32) dst[c] = __float2bfloat16_rn(fmaf((Bt[t * C + c] - m) * r, P.g2[c], P.b2[c]));
+      if (lane == 0) *reinterpret_cast<float2*>(p.st2 + 2 * (b * NT + t)) = make_float2(m, r);
+    }
+  }
+}
+
+template <int SIDE>
+__global__ void __launch_bounds__(TW * 32) ffn_mid_tile_bwd_kernel(FfnMidP p, int C) {
+  QV_PDL_ENTRY();
+  constexpr int NT = SIDE * SIDE;
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm;                            // xh1 (LayerNorm-1-normalised gelu(x))
+  float* Bt = A + NT * C;                   // the raw bf16 dy first, then cv = conv(hn) + bias
+  float* Dt = Bt + NT * C;                  // dy, then dconv
+  float* par = Dt + NT * C;
+  float4* sst = reinterpret_cast<float4*>(par + 15 * C + (4 - (15 * C) % 4) % 4);   // (mean1, rstd1, mean2, rstd2) per token
+  bf16* Xr = reinterpret_cast<bf16*>(sst + NT);                                     // the raw bf16 x of the image (gelu' at the end)
+  float* red;                               // [TW][15][C] only at the very end: overlays the tiles (see below)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_params(par, p, C);
+  const TilePar P(par, C);
+  const float invC = 1.f / C;
+  // per-lane accumulators for channels lane, lane + 32, ...: dg1, db1, dg2, db2, dbias, dscale, 9 taps
+  float acc[15][TCH];
+#pragma unroll
+  for (int k = 0; k < 15; ++k)
+#pragma unroll
+    for (int j = 0; j < TCH; ++j) acc[k][j] = 0.f;
+  for (long b = blockIdx.x; b < p.B; b += gridDim.x) {
+    __syncthreads();
+    // x, dy and the statistics come in as ONE wave of independent loads (per-token global loads cost a memory round trip each)
+    const bf16* src = Xr;
+    const bf16* dsrc = reinterpret_cast<const bf16*>(Bt);
+    for (int i = threadIdx.x; i < NT * C / 8; i += TW * 32) {
+      reinterpret_cast<uint4*>(Xr)[i] = reinterpret_cast<const uint4*>(p.h_pre + b * NT * C)[i];
+      reinterpret_cast<uint4*>(Bt)[i] = reinterpret_cast<const uint4*>(p.d_hn2 + b * NT * C)[i];
+    }
+    for (int t = threadIdx.x; t < NT; t += TW * 32) {
+      const float2 a1 = *reinterpret_cast<const float2*>(p.st1 + 2 * (b * NT + t)), a2 = *reinterpret_cast<const float2*>(p.st2 + 2 * (b * NT + t));
+      sst[t] = make_float4(a1.x, a1.y, a2.x, a2.y);
+    }
+    __syncthreads();
+    for (int t = warp; t < NT; t += TW) {    // xh1, dy
+      const float4 s4 = sst[t];
+      const float2 s1 = make_float2(s4.x, s4.y);
+      for (int c = lane; c < C; c += 32) {
+        A[t * C + c] = (mid_gelu(__bfloat162float(src[t * C + c])) - s1.x) * s1.y;
+        Dt[t * C + c] = __bfloat162float(dsrc[t * C + c]);
+      }
+    }
+    __syncthreads();
+    for (int t = warp; t < NT; t += TW) {    // cv = stencil(hn) + bias
+      const int py = t / SIDE, px = t % SIDE;
+      for (int c = lane; c < C; c += 32) {
+        float a = P.bs[c];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yy = py + ky - 1, xx = px + kx - 1;
+            if (yy >= 0 && yy < SIDE && xx >= 0 && xx < SIDE)
+              a = fmaf(P.w[c * 9 + ky * 3 + kx], fmaf(A[(yy * SIDE + xx) * C + c], P.g1[c], P.b1[c]), a);
+          }
+        Bt[t * C + c] = a;
+      }
+    }
+    __syncthreads();
+    for (int t = warp; t < NT; t += TW) {    // LayerNorm 2 backward: Dt <- dconv
+      const float2 s2 = make_float2(sst[t].z, sst[t].w);
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int j = 0; j < TCH; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          const float dy = Dt[t * C + c], xh2 = (Bt[t * C + c] * P.sc[c] - s2.x) * s2.y, d = dy * P.g2[c];
+          acc[2][j] = fmaf(dy, xh2, acc[2][j]); acc[3][j] += dy;
+          sa += d; sb = fmaf(d, xh2, sb);
+        }
+      }
+      sa = warp_sum(sa) * invC; sb = warp_sum(sb) * invC;
+#pragma unroll
+      for (int j = 0; j < TCH; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          const float cv = Bt[t * C + c], xh2 = (cv * P.sc[c] - s2.x) * s2.y;
+          const float dcs = s2.y * (Dt[t * C + c] * P.g2[c] - sa - xh2 * sb);
+          acc[5][j] = fmaf(dcs, cv, acc[5][j]);
+          const float dc = dcs * P.sc[c];
+          acc[4][j] += dc;
+          Dt[t * C + c] = dc;
+        }
+      }
+    }
+    __syncthreads();
+    for (int t = warp; t < NT; t += TW) {    // stencil backward (taps + transposed stencil), LayerNorm 1 backward, gelu'
+      const int py = t / SIDE, px = t % SIDE;
+      const float2 s1 = make_float2(sst[t].x, sst[t].y);
+      float dh[TCH], sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int j = 0; j < TCH; ++j) {
+        const int c = lane + 32 * j;
+        dh[j] = 0.f;
+        if (c < C) {
+          const float dc = Dt[t * C + c];
+          float a = 0.f;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int yy = py + ky - 1, xx = px + kx - 1;     // input position this output read through tap (ky, kx)
+              if (yy >= 0 && yy < SIDE && xx >= 0 && xx < SIDE)
+                acc[6 + ky * 3 + kx][j] = fmaf(dc, fmaf(A[(yy * SIDE + xx) * C + c], P.g1[c], P.b1[c]), acc[6 + ky * 3 + kx][j]);
+              const int oy = py - ky + 1, ox = px - kx + 1;     // output position that read this input through tap (ky, kx)
+              if (oy >= 0 && oy < SIDE && ox >= 0 && ox < SIDE) a = fmaf(P.w[c * 9 + ky * 3 + kx], Dt[(oy * SIDE + ox) * C + c], a);
+            }
+          const float xh1 = A[t * C + c];
+          acc[0][j] = fmaf(a, xh1, acc[0][j]); acc[1][j] += a;
+          dh[j] = a * P.g1[c];
+          sa += dh[j]; sb = fmaf(dh[j], xh1, sb);
+        }
+      }
+      sa = warp_sum(sa) * invC; sb = warp_sum(sb) * invC;
+      bf16* dst = p.d_hpre + (b * NT + t) * C;
+#pragma unroll
+      for (int j = 0; j < TCH; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          float gv, dg;
+          mid_gelu_both(__bfloat162float(src[t * C + c]), gv, dg);
+          dst[c] = __float2bfloat16_rn(s1.y * (dh[j] - sa - A[t * C + c] * sb) * dg);
+        }
+      }
+    }
+  }
+  // ---- the warps' channel accumulators meet in shared memory (over the tiles, which are dead now), one atomic per value and CTA
+  __syncthreads();
+  red = sm;
+#pragma unroll
+  for (int k = 0; k < 15; ++k)
+#pragma unroll
+    for (int j = 0; j < TCH; ++j) {
+      const int c = lane + 32 * j;
+      if (c < C) red[(warp * 15 + k) * C + c] = acc[k][j];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 15 * C; i += TW * 32) {
+    const int k = i / C, c = i % C;
+    float v = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < TW; ++w2) v += red[(w2 * 15 + k) * C + c];
+    float* dst = k == 0 ? p.dg1 + c : k == 1 ? p.db1 + c : k == 2 ? p.dg2 + c : k == 3 ? p.db2 + c
+               : k == 4 ? (p.dbias ? p.dbias + c : nullptr) : k == 5 ? (p.dscale ? p.dscale + c : nullptr) : p.dw + c * 9 + (k - 6);
+    if (dst) atomicAdd(dst, v);
+  }
+}
+
+template <int SIDE>
+int launch_tile(cudaStream_t s, const FfnMidP& p, int C, bool bwd) {
+  constexpr int NT = SIDE * SIDE;
+  const size_t fwd_b = ((size_t)2 * NT * C + 15 * C) * 4, bwd_b = ((size_t)3 * NT * C + 15 * C + 4 + 4 * NT) * 4 + (size_t)NT * C * 2;
+  const size_t smem = bwd ? max(bwd_b, (size_t)TW * 15 * C * 4) : fwd_b;
+  QV_CHECK(smem <= 200 * 1024, "ffn_mid: %zu B of shared memory", smem);
+  auto kf = ffn_mid_tile_fwd_kernel<SIDE>;
+  auto kb = ffn_mid_tile_bwd_kernel<SIDE>;
+  if (smem > 48 * 1024) {
+    if (bwd) QV_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else QV_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  const int per_sm = max(1, min(8, (int)(220 * 1024 / (smem + 1024))));
+  const int grid = (int)max(1L, min((long)p.B, (long)qv_num_sms() * per_sm));
+  if (bwd) qv_launch(kb, grid, TW * 32, smem, s, p, C);
+  else qv_launch(kf, grid, TW * 32, smem, s, p, C);
+  QV_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename K>
 int grid_for(K kernel, int threads, long ngroups) {
   int per_sm = 1;
@@ -353,27 +603,27 @@ int dispatch(cudaStream_t s, const FfnMidP& p, int C, bool bwd) {
 
 }  // namespace
 
-bool ffn_mid_ok(int side, int C) { return side == 4 && C % 32 == 0 && C >= 32 && C <= 128; }
+bool ffn_mid_ok(int side, int C) { return (side == 4 && C % 32 == 0 && C >= 32 && C <= 128) || (side == 8 && C % 8 == 0 && C >= 8 && C <= 128); }
 
-int ffn_mid_fwd(cudaStream_t s, const void* h_pre, int B, int C, const float* g1, const float* b1, const float* w, const float* bias,
+int ffn_mid_fwd(cudaStream_t s, const void* h_pre, int B, int side, int C, const float* g1, const float* b1, const float* w, const float* bias,
                 const float* scale, const float* g2, const float* b2, float eps, void* hn2, float* stats1, float* stats2) {
   if (B <= 0) return 0;
-  QV_CHECK(ffn_mid_ok(4, C), "ffn_mid: C=%d is not a multiple of 32 in [32, 128]", C);
+  QV_CHECK(ffn_mid_ok(side, C), "ffn_mid: side=%d C=%d not covered (4 x 4 maps: C a multiple of 32 in [32, 128]; 8 x 8 maps: C a multiple of 8 <= 128)", side, C);
   FfnMidP p{};
   p.h_pre = static_cast<const bf16*>(h_pre); p.g1 = g1; p.b1 = b1; p.w = w; p.bias = bias; p.scale = scale; p.g2 = g2; p.b2 = b2;
   p.st1 = stats1; p.st2 = stats2; p.hn2 = static_cast<bf16*>(hn2); p.B = B; p.eps = eps;
-  return dispatch(s, p, C, false);
+  return side == 8 ? launch_tile<8>(s, p, C, false) : dispatch(s, p, C, false);
 }
 
-int ffn_mid_bwd(cudaStream_t s, const void* h_pre, const void* d_hn2, const float* stats1, const float* stats2, int B, int C,
+int ffn_mid_bwd(cudaStream_t s, const void* h_pre, const void* d_hn2, const float* stats1, const float* stats2, int B, int side, int C,
                 const float* g1, const float* b1, const float* w, const float* bias, const float* scale, const float* g2, void* d_hpre,
                 float* dg1, float* db1, float* dw, float* dbias, float* dscale, float* dg2, float* db2) {
   if (B <= 0) return 0;
-  QV_CHECK(ffn_mid_ok(4, C), "ffn_mid: C=%d is not a multiple of 32 in [32, 128]", C);
+  QV_CHECK(ffn_mid_ok(side, C), "ffn_mid: side=%d C=%d not covered (4 x 4 maps: C a multiple of 32 in [32, 128]; 8 x 8 maps: C a multiple of 8 <= 128)", side, C);
   FfnMidP p{};
   p.h_pre = static_cast<const bf16*>(h_pre); p.d_hn2 = static_cast<const bf16*>(d_hn2); p.g1 = g1; p.b1 = b1; p.w = w; p.bias = bias;
   p.scale = scale; p.g2 = g2; p.st1 = const_cast<float*>(stats1); p.st2 = const_cast<float*>(stats2);
   p.d_hpre = static_cast<bf16*>(d_hpre); p.dg1 = dg1; p.db1 = db1; p.dw = dw; p.dbias = dbias; p.dscale = dscale; p.dg2 = dg2; p.db2 = db2;
   p.B = B;
-  return dispatch(s, p, C, true);
+  return side == 8 ? launch_tile<8>(s, p, C, true) : dispatch(s, p, C, true);
 }

@@ -298,11 +298,12 @@ int upf_fwd(cudaStream_t s, const float* xc, int B, int N, const float* W, const
 int upf_bwd(cudaStream_t s, const float* xc, const float* dout, const float* stats, int B, int N, const float* W, const float* bias,
             const float* gamma, float* dxc, float* dW, float* dgamma, float* dbeta);
 // CCF-FFN mid-section GELU -> LayerNorm -> depthwise 3x3 (* scale) -> LayerNorm as one kernel per direction (ffn_mid.cu): bf16 runs,
-// 4 x 4 token maps, C a multiple of 32 up to 128.  stats1 / stats2: (mean, rstd) per row of the two LayerNorms.
+// 4 x 4 token maps (register kernel, C a multiple of 32 up to 128) and 8 x 8 maps (shared-memory tile kernel, C a multiple of 8 <= 128).
+// stats1 / stats2: (mean, rstd) per row of the two LayerNorms.
 bool ffn_mid_ok(int side, int C);
-int ffn_mid_fwd(cudaStream_t s, const void* h_pre, int B, int C, const float* g1, const float* b1, const float* w, const float* bias,
+int ffn_mid_fwd(cudaStream_t s, const void* h_pre, int B, int side, int C, const float* g1, const float* b1, const float* w, const float* bias,
                 const float* scale, const float* g2, const float* b2, float eps, void* hn2, float* stats1, float* stats2);
-int ffn_mid_bwd(cudaStream_t s, const void* h_pre, const void* d_hn2, const float* stats1, const float* stats2, int B, int C,
+int ffn_mid_bwd(cudaStream_t s, const void* h_pre, const void* d_hn2, const float* stats1, const float* stats2, int B, int side, int C,
                 const float* g1, const float* b1, const float* w, const float* bias, const float* scale, const float* g2, void* d_hpre,
                 float* dg1, float* db1, float* dw, float* dbias, float* dscale, float* dg2, float* db2);
 // per-branch LayerNorm + compress Linear + fusion scale + concat for all 4 branches in one launch, and its backward (cmp_fused.cu);

@@ -220,28 +220,31 @@ def test_depthwise_8x8_tensor_core_path_matches_conv2d(K, C, B):
     assert (dw.double() - wg.grad.view(C, K, K)).abs().max().item() < 2e-2 * max(1.0, wg.grad.abs().max().item())
 
 
-@pytest.mark.parametrize("C,B,bias", [(96, 37, False), (96, 300, True), (32, 9, True), (64, 5, False), (128, 7, True)])
-def test_ffn_mid_fused_matches_autograd(C, B, bias):
+@pytest.mark.parametrize("side,C,B,bias", [(4, 96, 37, False), (4, 96, 300, True), (4, 32, 9, True), (4, 64, 5, False), (4, 128, 7, True),
+                                           (8, 96, 37, False), (8, 96, 700, True), (8, 48, 3, True), (8, 128, 5, False)])
+def test_ffn_mid_fused_matches_autograd(side, C, B, bias):
     """CCF-FFN mid-section as one kernel per direction (ffn_mid.cu; H:704-709): GELU -> LayerNorm -> depthwise 3x3 (+ bias) * scale
-    -> LayerNorm on 4 x 4 token maps, against torch autograd in fp64 on the bf16-rounded inputs.  Outputs are bf16 (2^-9 relative
-    rounding); parameter gradients are fp32 sums and are held to 1e-3.  B = 37 / 9 / 5 / 7 leave a partial group of images."""
+    -> LayerNorm on 4 x 4 token maps (register kernel) and 8 x 8 maps (shared-memory tile kernel), against torch autograd in fp64 on
+    the bf16-rounded inputs.  Outputs are bf16 (2^-9 relative rounding); parameter gradients are fp32 sums and are held to 1e-3.
+    The small B leave a partial group of images / idle CTAs; B = 700 makes a CTA walk several images."""
     import ctypes as Ct
     import torch.nn.functional as F
     from util import rel_l2
     L = _lib()
-    g = torch.Generator(device="cuda").manual_seed(C * 7 + B)
+    T = side * side
+    g = torch.Generator(device="cuda").manual_seed(C * 7 + B + side)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
-    h_pre = (rn(B, 16, C) * 1.2 + 0.1).bfloat16()
+    h_pre = (rn(B, T, C) * 1.2 + 0.1).bfloat16()
     g1, b1, g2, b2 = 1 + 0.2 * rn(C), 0.1 * rn(C), 1 + 0.2 * rn(C), 0.1 * rn(C)
     w, cb, sc = rn(C, 3, 3) / 3, 0.2 * rn(C), 1 + 0.3 * rn(C)
-    d_hn2 = rn(B, 16, C).bfloat16()
-    hn2 = torch.empty(B, 16, C, device="cuda", dtype=torch.bfloat16)
-    st1, st2 = torch.empty(B * 16, 2, device="cuda"), torch.empty(B * 16, 2, device="cuda")
+    d_hn2 = rn(B, T, C).bfloat16()
+    hn2 = torch.empty(B, T, C, device="cuda", dtype=torch.bfloat16)
+    st1, st2 = torch.empty(B * T, 2, device="cuda"), torch.empty(B * T, 2, device="cuda")
 
     def call(op, ins, outs):
         a = (Ct.c_void_p * len(ins))(*[t.data_ptr() if t is not None else None for t in ins])
         o = (Ct.c_void_p * len(outs))(*[t.data_ptr() if t is not None else None for t in outs])
-        L.check(L.lib.qavit_test_ffn_mid(op, B, C, a, o, _s()))
+        L.check(L.lib.qavit_test_ffn_mid(op, B, side, C, a, o, _s()))
         torch.cuda.synchronize()
 
     params = [g1, b1, w, cb if bias else None, sc, g2, b2]
@@ -249,7 +252,7 @@ def test_ffn_mid_fused_matches_autograd(C, B, bias):
     leaves = [t.double().requires_grad_(True) for t in (h_pre, g1, b1, w, cb, sc, g2, b2)]
     x, G1, B1, W, CB, SC, G2, B2 = leaves
     h = F.layer_norm(F.gelu(x), (C,), G1, B1, 1e-5)
-    img = h.transpose(1, 2).reshape(B, C, 4, 4)
+    img = h.transpose(1, 2).reshape(B, C, side, side)
     img = F.conv2d(img, W.view(C, 1, 3, 3), CB if bias else None, padding=1, groups=C) * SC.view(1, C, 1, 1)
     ref = F.layer_norm(img.flatten(2).transpose(1, 2), (C,), G2, B2, 1e-5)
     assert rel_l2(hn2, ref) < 4e-3, rel_l2(hn2, ref)                                  # bf16 output

@@ -1,3 +1,5 @@
 # scratch command file for `gpurun -- 'bash tools/_call.sh'` (edited per experiment)
 mkdir -p gpurun_out/r2
-python tools/kineto_step.py --graph --top 200 2>&1 | grep -v "Warn\|_warn_once" > gpurun_out/r2/kineto_final.txt; head -3 gpurun_out/r2/kineto_final.txt; grep "stream\|gaps" gpurun_out/r2/kineto_final.txt | head -5
+python -m pytest tests -m gpu -q -x 2>&1 | tail -2 | tee gpurun_out/r2/t44_all.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python bench.py --workload qavitv2_c100 --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline 2>&1 | tail -1 | cut -c1-230
