@@ -1,5 +1,5 @@
 # scratch command file for `gpurun -- 'bash tools/_call.sh'` (edited per experiment)
-mkdir -p gpurun_out/r2
-python -m pytest tests -m gpu -q -x 2>&1 | tail -2 | tee gpurun_out/r2/t44_all.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python bench.py --workload qavitv2_c100 --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline 2>&1 | tail -1 | cut -c1-230
+B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline"
+ms() { tail -1 | grep -o '"ms_per_step": [0-9.]*' | head -1; }
+echo "lateral path on the main stream (QAVIT_LATERAL_SERIAL=1):"; QAVIT_LATERAL_SERIAL=1 $B 2>&1 | ms
+echo "lateral path on its side stream (default):"; $B 2>&1 | ms
